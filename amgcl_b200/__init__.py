@@ -1,0 +1,451 @@
+"""amgcl_b200 -- B200-native solve-phase backend for AMGCL.
+
+The product is native:
+
+  include/amgcl_b200.h              C ABI (the drop-in boundary)
+  amgcl_b200/csrc/*.cu(h)           hand-written sm_100a kernels behind it
+  include/amgcl/backend/b200.hpp    C++ binding to amgcl::backend (the reference is C++)
+  amgcl_b200/host/dropin.cpp        AMGCL's own make_solver<amg<...>, cg|bicgstab>
+                                    instantiated on that backend
+
+This Python package is only the ctypes loader that bench.py and the tests use
+to drive those libraries; it contains no numerical code and has NO CPU
+fallback: constructing a :class:`Context` without a CUDA device raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from . import build as _build
+
+__all__ = ["lib", "dropin_lib", "Context", "Vector", "Csr", "Coarse", "DropinSolver",
+           "poisson3d", "B200Error", "RELAX", "KRYLOV"]
+
+_c = ctypes
+_i64 = _c.c_int64
+_dbl = _c.c_double
+_vp = _c.c_void_p
+_P = _c.POINTER
+
+RELAX = {"damped_jacobi": 0, "spai0": 1}
+KRYLOV = {"cg": 0, "bicgstab": 1}
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+_lib = None
+_dropin = None
+
+
+def lib():
+    """ctypes handle of libamgcl_b200.so (built in-tree on first use)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_CUDA
+    if not os.path.isfile(path):
+        path = _build.build_cuda()
+    L = _c.CDLL(path, mode=_c.RTLD_GLOBAL)
+    L.b200_last_error.restype = _c.c_char_p
+    L.b200_version.restype = _c.c_char_p
+    sigs = {
+        "b200_device_count": [],
+        "b200_ctx_create": [_c.c_int, _P(_vp)],
+        "b200_ctx_destroy": [_vp],
+        "b200_ctx_default": [_P(_vp)],
+        "b200_ctx_set_stream": [_vp, _vp],
+        "b200_ctx_get_stream": [_vp, _P(_vp)],
+        "b200_ctx_device": [_vp, _P(_c.c_int)],
+        "b200_ctx_sync": [_vp],
+        "b200_ctx_launch_count": [_vp, _P(_c.c_uint64)],
+        "b200_ctx_reset_launch_count": [_vp],
+        "b200_ctx_set_option": [_vp, _c.c_char_p, _i64],
+        "b200_ctx_get_option": [_vp, _c.c_char_p, _P(_i64)],
+        "b200_vec_create": [_vp, _c.c_size_t, _P(_vp)],
+        "b200_vec_wrap": [_vp, _vp, _c.c_size_t, _P(_vp)],
+        "b200_vec_destroy": [_vp],
+        "b200_vec_size": [_vp, _P(_c.c_size_t)],
+        "b200_vec_bytes": [_vp, _P(_c.c_size_t)],
+        "b200_vec_data": [_vp, _P(_vp)],
+        "b200_vec_upload": [_vp, _vp, _c.c_size_t],
+        "b200_vec_download": [_vp, _vp, _c.c_size_t],
+        "b200_csr_create_i64": [_vp, _i64, _i64, _vp, _vp, _vp, _P(_vp)],
+        "b200_csr_create_i32": [_vp, _i64, _i64, _vp, _vp, _vp, _P(_vp)],
+        "b200_csr_destroy": [_vp],
+        "b200_csr_rows": [_vp, _P(_c.c_size_t)],
+        "b200_csr_cols": [_vp, _P(_c.c_size_t)],
+        "b200_csr_nonzeros": [_vp, _P(_c.c_size_t)],
+        "b200_csr_bytes": [_vp, _P(_c.c_size_t)],
+        "b200_csr_plan": [_vp, _P(_c.c_int), _P(_i64), _P(_i64)],
+        "b200_spmv": [_vp, _dbl, _vp, _vp, _dbl, _vp],
+        "b200_residual": [_vp, _vp, _vp, _vp, _vp],
+        "b200_clear": [_vp, _vp],
+        "b200_copy": [_vp, _vp, _vp],
+        "b200_dot": [_vp, _vp, _vp, _P(_dbl)],
+        "b200_axpby": [_vp, _dbl, _vp, _dbl, _vp],
+        "b200_axpbypcz": [_vp, _dbl, _vp, _dbl, _vp, _dbl, _vp],
+        "b200_vmul": [_vp, _dbl, _vp, _vp, _dbl, _vp],
+        "b200_relax": [_vp, _vp, _vp, _vp, _vp, _vp, _dbl],
+        "b200_coarse_create_i64": [_vp, _i64, _vp, _vp, _vp, _P(_vp)],
+        "b200_coarse_create_i32": [_vp, _i64, _vp, _vp, _vp, _P(_vp)],
+        "b200_coarse_destroy": [_vp],
+        "b200_coarse_bytes": [_vp, _P(_c.c_size_t)],
+        "b200_coarse_solve": [_vp, _vp, _vp, _vp],
+    }
+    for name, args in sigs.items():
+        fn = getattr(L, name)
+        fn.argtypes = args
+        fn.restype = _c.c_int
+    _lib = L
+    return L
+
+
+def dropin_lib():
+    """ctypes handle of libamgcl_b200_dropin.so (AMGCL templates on backend::b200)."""
+    global _dropin
+    if _dropin is not None:
+        return _dropin
+    lib()   # libamgcl_b200.so first (RTLD_GLOBAL) so the dependency resolves
+    path = _build.LIB_DROPIN
+    if not os.path.isfile(path):
+        path = _build.build_dropin()
+    D = _c.CDLL(path)
+    D.dropin_last_error.restype = _c.c_char_p
+    D.dropin_create.argtypes = [_vp, _i64, _vp, _vp, _vp, _c.c_int, _c.c_int, _dbl, _c.c_int,
+                                _c.c_int, _P(_vp)]
+    D.dropin_create.restype = _c.c_int
+    D.dropin_destroy.argtypes = [_vp]
+    D.dropin_destroy.restype = None
+    D.dropin_solve.argtypes = [_vp, _vp, _vp, _P(_i64), _P(_dbl)]
+    D.dropin_solve.restype = _c.c_int
+    D.dropin_upload_rhs.argtypes = [_vp, _vp]
+    D.dropin_upload_rhs.restype = _c.c_int
+    D.dropin_solve_resident.argtypes = [_vp, _P(_i64), _P(_dbl)]
+    D.dropin_solve_resident.restype = _c.c_int
+    D.dropin_download_x.argtypes = [_vp, _vp]
+    D.dropin_download_x.restype = _c.c_int
+    D.dropin_apply_precond.argtypes = [_vp, _vp, _vp]
+    D.dropin_apply_precond.restype = _c.c_int
+    D.dropin_report.argtypes = [_vp, _c.c_char_p, _i64]
+    D.dropin_report.restype = _i64
+    D.dropin_bytes.argtypes = [_vp]
+    D.dropin_bytes.restype = _i64
+    _dropin = D
+    return D
+
+
+def _check(rc, what=""):
+    if rc != 0:
+        msg = lib().b200_last_error().decode(errors="replace")
+        raise B200Error("%s failed (%d): %s" % (what or "b200 call", rc, msg))
+
+
+def _f64(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_vp)
+
+
+class Context:
+    """Device + stream + scratch (b200_ctx_t)."""
+
+    def __init__(self, device=0, stream=None):
+        L = lib()
+        if L.b200_device_count() <= 0:
+            raise B200Error("amgcl_b200 requires a CUDA device (no CPU fallback)")
+        self.h = _vp()
+        _check(L.b200_ctx_create(int(device), _c.byref(self.h)), "b200_ctx_create")
+        if stream is not None:
+            self.set_stream(stream)
+
+    def set_stream(self, cuda_stream):
+        _check(lib().b200_ctx_set_stream(self.h, _vp(int(cuda_stream) if cuda_stream else 0)))
+
+    def sync(self):
+        _check(lib().b200_ctx_sync(self.h), "b200_ctx_sync")
+
+    def set_option(self, key, value):
+        _check(lib().b200_ctx_set_option(self.h, key.encode(), int(value)), "b200_ctx_set_option")
+
+    def get_option(self, key):
+        v = _i64()
+        _check(lib().b200_ctx_get_option(self.h, key.encode(), _c.byref(v)))
+        return v.value
+
+    @property
+    def launches(self):
+        v = _c.c_uint64()
+        _check(lib().b200_ctx_launch_count(self.h, _c.byref(v)))
+        return v.value
+
+    def reset_launches(self):
+        _check(lib().b200_ctx_reset_launch_count(self.h))
+
+    def close(self):
+        if self.h:
+            lib().b200_ctx_destroy(self.h)
+            self.h = _vp()
+
+    # -- factories --------------------------------------------------------
+    def vector(self, data_or_n):
+        return Vector(self, data_or_n)
+
+    def csr(self, nrows, ncols, ptr, col, val):
+        return Csr(self, nrows, ncols, ptr, col, val)
+
+    def coarse(self, n, ptr, col, val):
+        return Coarse(self, n, ptr, col, val)
+
+    # -- primitives (thin, 1:1 with the C ABI) ------------------------------
+    def spmv(self, alpha, A, x, beta, y):
+        _check(lib().b200_spmv(self.h, alpha, A.h, x.h, beta, y.h), "b200_spmv")
+
+    def residual(self, f, A, x, r):
+        _check(lib().b200_residual(self.h, f.h, A.h, x.h, r.h), "b200_residual")
+
+    def clear(self, x):
+        _check(lib().b200_clear(self.h, x.h), "b200_clear")
+
+    def copy(self, x, y):
+        _check(lib().b200_copy(self.h, x.h, y.h), "b200_copy")
+
+    def dot(self, x, y):
+        r = _dbl()
+        _check(lib().b200_dot(self.h, x.h, y.h, _c.byref(r)), "b200_dot")
+        return r.value
+
+    def axpby(self, a, x, b, y):
+        _check(lib().b200_axpby(self.h, a, x.h, b, y.h), "b200_axpby")
+
+    def axpbypcz(self, a, x, b, y, c, z):
+        _check(lib().b200_axpbypcz(self.h, a, x.h, b, y.h, c, z.h), "b200_axpbypcz")
+
+    def vmul(self, alpha, x, y, beta, z):
+        _check(lib().b200_vmul(self.h, alpha, x.h, y.h, beta, z.h), "b200_vmul")
+
+    def relax(self, A, rhs, x, tmp, diag, omega):
+        _check(lib().b200_relax(self.h, A.h, rhs.h, x.h, tmp.h, diag.h, omega), "b200_relax")
+
+    def coarse_solve(self, S, rhs, x):
+        _check(lib().b200_coarse_solve(self.h, S.h, rhs.h, x.h), "b200_coarse_solve")
+
+
+class Vector:
+    """Device FP64 vector (b200_vec_t)."""
+
+    def __init__(self, ctx, data_or_n):
+        self.ctx = ctx
+        self.h = _vp()
+        if isinstance(data_or_n, (int, np.integer)):
+            self.n = int(data_or_n)
+            _check(lib().b200_vec_create(ctx.h, self.n, _c.byref(self.h)), "b200_vec_create")
+        else:
+            a = _f64(data_or_n)
+            self.n = a.size
+            _check(lib().b200_vec_create(ctx.h, self.n, _c.byref(self.h)), "b200_vec_create")
+            self.upload(a)
+
+    def upload(self, a):
+        a = _f64(a)
+        _check(lib().b200_vec_upload(self.h, _ptr(a), a.size), "b200_vec_upload")
+
+    def numpy(self):
+        out = np.empty(self.n, dtype=np.float64)
+        _check(lib().b200_vec_download(self.h, _ptr(out), self.n), "b200_vec_download")
+        return out
+
+    def data_ptr(self):
+        p = _vp()
+        _check(lib().b200_vec_data(self.h, _c.byref(p)))
+        return p.value or 0
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().b200_vec_destroy(self.h)
+                self.h = _vp()
+        except Exception:
+            pass
+
+
+class Csr:
+    """Device CSR matrix + row-block plan (b200_csr_t)."""
+
+    def __init__(self, ctx, nrows, ncols, ptr, col, val):
+        self.ctx = ctx
+        self.h = _vp()
+        val = _f64(val)
+        ptr = np.ascontiguousarray(ptr)
+        col = np.ascontiguousarray(col)
+        if ptr.dtype == np.int32 and col.dtype == np.int32:
+            fn = lib().b200_csr_create_i32
+        else:
+            ptr = np.ascontiguousarray(ptr, dtype=np.int64)
+            col = np.ascontiguousarray(col, dtype=np.int64)
+            fn = lib().b200_csr_create_i64
+        _check(fn(ctx.h, int(nrows), int(ncols), _ptr(ptr), _ptr(col), _ptr(val),
+                  _c.byref(self.h)), "b200_csr_create")
+        self.nrows, self.ncols, self.nnz = int(nrows), int(ncols), int(ptr[-1])
+
+    def plan(self):
+        lanes = _c.c_int()
+        nb = _i64()
+        nl = _i64()
+        _check(lib().b200_csr_plan(self.h, _c.byref(lanes), _c.byref(nb), _c.byref(nl)))
+        return {"lanes": lanes.value, "blocks": nb.value, "long_blocks": nl.value}
+
+    def bytes(self):
+        b = _c.c_size_t()
+        _check(lib().b200_csr_bytes(self.h, _c.byref(b)))
+        return b.value
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().b200_csr_destroy(self.h)
+                self.h = _vp()
+        except Exception:
+            pass
+
+
+class Coarse:
+    """Coarsest-level device solver (b200_coarse_t)."""
+
+    def __init__(self, ctx, n, ptr, col, val):
+        self.ctx = ctx
+        self.h = _vp()
+        ptr = np.ascontiguousarray(ptr, dtype=np.int64)
+        col = np.ascontiguousarray(col, dtype=np.int64)
+        val = _f64(val)
+        _check(lib().b200_coarse_create_i64(ctx.h, int(n), _ptr(ptr), _ptr(col), _ptr(val),
+                                            _c.byref(self.h)), "b200_coarse_create")
+        self.n = int(n)
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().b200_coarse_destroy(self.h)
+                self.h = _vp()
+        except Exception:
+            pass
+
+
+class DropinSolver:
+    """amgcl::make_solver<amg<backend::b200<double>, smoothed_aggregation, RELAX>, KRYLOV>
+    -- the reference's own templates running on the B200 backend."""
+
+    def __init__(self, ptr, col, val, relax="damped_jacobi", krylov="cg", tol=1e-8,
+                 maxiter=100, coarse_enough=-1, ctx=None):
+        D = dropin_lib()
+        self.ptr = np.ascontiguousarray(ptr, dtype=np.int64)
+        self.col = np.ascontiguousarray(col, dtype=np.int64)
+        self.val = _f64(val)
+        self.n = self.ptr.size - 1
+        self.ctx = ctx
+        self.h = _vp()
+        rc = D.dropin_create(ctx.h if ctx is not None else None, self.n, _ptr(self.ptr),
+                             _ptr(self.col), _ptr(self.val), RELAX[relax], KRYLOV[krylov],
+                             float(tol), int(maxiter), int(coarse_enough), _c.byref(self.h))
+        if rc != 0:
+            raise B200Error("dropin_create: " + D.dropin_last_error().decode(errors="replace"))
+
+    def _err(self, what):
+        raise B200Error(what + ": " + dropin_lib().dropin_last_error().decode(errors="replace"))
+
+    def solve(self, rhs, x0=None):
+        """End-to-end call with host buffers. Returns (x, iters, resid)."""
+        rhs = _f64(rhs)
+        x = np.zeros(self.n) if x0 is None else _f64(x0).copy()
+        it = _i64()
+        res = _dbl()
+        if dropin_lib().dropin_solve(self.h, _ptr(rhs), _ptr(x), _c.byref(it), _c.byref(res)):
+            self._err("dropin_solve")
+        return x, it.value, res.value
+
+    def solve_into(self, rhs, x):
+        """Same as solve() but on caller-provided (e.g. pinned) host arrays; x is in/out."""
+        it = _i64()
+        res = _dbl()
+        if dropin_lib().dropin_solve(self.h, _ptr(rhs), _ptr(x), _c.byref(it), _c.byref(res)):
+            self._err("dropin_solve")
+        return it.value, res.value
+
+    def upload_rhs(self, rhs):
+        rhs = _f64(rhs)
+        if dropin_lib().dropin_upload_rhs(self.h, _ptr(rhs)):
+            self._err("dropin_upload_rhs")
+
+    def solve_resident(self):
+        it = _i64()
+        res = _dbl()
+        if dropin_lib().dropin_solve_resident(self.h, _c.byref(it), _c.byref(res)):
+            self._err("dropin_solve_resident")
+        return it.value, res.value
+
+    def download_x(self):
+        x = np.empty(self.n)
+        if dropin_lib().dropin_download_x(self.h, _ptr(x)):
+            self._err("dropin_download_x")
+        return x
+
+    def apply_precond(self, f):
+        f = _f64(f)
+        x = np.empty(self.n)
+        if dropin_lib().dropin_apply_precond(self.h, _ptr(f), _ptr(x)):
+            self._err("dropin_apply_precond")
+        return x
+
+    def report(self):
+        need = dropin_lib().dropin_report(self.h, None, 0)
+        buf = _c.create_string_buffer(int(need))
+        dropin_lib().dropin_report(self.h, buf, need)
+        return buf.value.decode(errors="replace")
+
+    def close(self):
+        if self.h:
+            dropin_lib().dropin_destroy(self.h)
+            self.h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def poisson3d(n, dtype_index=np.int64):
+    """3-D 7-point Poisson problem on an n^3 grid, natural ordering (i fastest),
+    Dirichlet by truncation, diag 6, off-diag -1, rhs == 1: the same system the
+    reference's tests generate (tests/sample_problem.hpp:11-82, anisotropy 1),
+    built here with numpy.  Returns (ptr, col, val, rhs)."""
+    n = int(n)
+    n3 = n * n * n
+    idx = np.arange(n3, dtype=np.int64)
+    i = idx % n
+    j = (idx // n) % n
+    k = idx // (n * n)
+    # neighbour order inside a row: k-1, j-1, i-1, diag, i+1, j+1, k+1
+    offs = np.array([-n * n, -n, -1, 0, 1, n, n * n], dtype=np.int64)
+    mask = np.empty((n3, 7), dtype=bool)
+    mask[:, 0] = k > 0
+    mask[:, 1] = j > 0
+    mask[:, 2] = i > 0
+    mask[:, 3] = True
+    mask[:, 4] = i + 1 < n
+    mask[:, 5] = j + 1 < n
+    mask[:, 6] = k + 1 < n
+    del i, j, k
+    counts = mask.sum(axis=1)
+    ptr = np.zeros(n3 + 1, dtype=np.int64)
+    np.cumsum(counts, out=ptr[1:])
+    cols = (idx[:, None] + offs[None, :])[mask]
+    vals = np.broadcast_to(np.array([-1.0, -1.0, -1.0, 6.0, -1.0, -1.0, -1.0]), (n3, 7))[mask]
+    rhs = np.ones(n3)
+    return (ptr.astype(dtype_index), np.ascontiguousarray(cols, dtype=dtype_index),
+            np.ascontiguousarray(vals, dtype=np.float64), rhs)

@@ -1,0 +1,987 @@
+// capi.cu -- implementation of the C ABI declared in include/amgcl_b200.h.
+//
+// Host-side logic only: argument checking, the row-block plan, lazy-clear
+// bookkeeping and kernel launches.  There is deliberately no CPU fallback: every
+// entry point needs a CUDA device and reports B200_ECUDA otherwise.
+#include "common.cuh"
+#include "csr_kernels.cuh"
+#include "vec_kernels.cuh"
+#include "coarse_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <mutex>
+#include <new>
+
+// ---------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------
+namespace b200 {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string &msg) { g_last_error = msg; }
+
+int fail(int code, const std::string &msg) {
+    g_last_error = msg;
+    return code;
+}
+
+int cuda_fail(cudaError_t rc, const char *what, const char *file, int line) {
+    char buf[512];
+    snprintf(buf, sizeof(buf), "CUDA error %d (%s) in %s at %s:%d", (int)rc,
+             cudaGetErrorString(rc), what, file, line);
+    g_last_error = buf;
+    cudaGetLastError();   // clear the sticky-less error state
+    return rc == cudaErrorMemoryAllocation ? B200_ENOMEM : B200_ECUDA;
+}
+
+// device guard: every entry point runs with the context's device current
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; }
+        if (prev != dev) ok = (cudaSetDevice(dev) == cudaSuccess);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// Lazy clear bookkeeping ------------------------------------------------------
+static int materialize(b200_vec_t v) {
+    if (v->zero_pending) {
+        B200_CUDA(cudaMemsetAsync(v->ptr, 0, v->n * sizeof(double), v->ctx->stream));
+        v->zero_pending = false;
+    }
+    return B200_OK;
+}
+// pointer for reading (or read-modify-write)
+static int rd(b200_vec_t v, const double **p) {
+    int rc = materialize(v);
+    *p = v->ptr;
+    return rc;
+}
+// pointer for a full overwrite
+static double *wr(b200_vec_t v) {
+    v->zero_pending = false;
+    return v->ptr;
+}
+
+static int grid_for(const b200_ctx_t ctx, size_t n_items, int per_thread_items) {
+    // enough CTAs to cover the range once, capped at 8 CTAs per SM (2048 threads)
+    size_t want = (n_items + (size_t)kThreads * per_thread_items - 1) /
+                  ((size_t)kThreads * per_thread_items);
+    size_t cap = (size_t)ctx->sm_count * 8;
+    if (want < 1) want = 1;
+    return (int)std::min(want, cap);
+}
+
+} // namespace b200
+
+using namespace b200;
+
+#define CHECK_CTX(ctx) B200_REQUIRE((ctx) != nullptr, "null context")
+#define GUARD(ctx)                                                             \
+    DeviceGuard guard__((ctx)->device);                                        \
+    if (!guard__.ok) return fail(B200_ECUDA, "cudaSetDevice failed")
+
+// ---------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------
+extern "C" const char *b200_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" const char *b200_version(void) { return "amgcl_b200 0.1.0 sm_100a"; }
+
+extern "C" int b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" int b200_ctx_create(int device, b200_ctx_t *out) {
+    B200_REQUIRE(out != nullptr, "null output pointer");
+    *out = nullptr;
+    int ndev = 0;
+    B200_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(B200_EINVAL, "no such CUDA device");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(B200_ECUDA, "cudaSetDevice failed");
+
+    b200_ctx_s *ctx = new (std::nothrow) b200_ctx_s();
+    if (!ctx) return fail(B200_ENOMEM, "out of host memory");
+    ctx->device = device;
+    cudaDeviceProp prop;
+    B200_CUDA(cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    if (prop.major < 10) {
+        delete ctx;
+        return fail(B200_ECUDA, "amgcl_b200 needs an sm_100a (Blackwell B200) device");
+    }
+    B200_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
+    B200_CUDA(cudaMalloc(&ctx->dot_partial, kDotMaxBlocks * sizeof(double)));
+    B200_CUDA(cudaMalloc(&ctx->dot_ticket, sizeof(unsigned int)));
+    B200_CUDA(cudaMemset(ctx->dot_ticket, 0, sizeof(unsigned int)));
+    B200_CUDA(cudaHostAlloc(&ctx->dot_result_h, 8 * sizeof(double), cudaHostAllocMapped));
+    B200_CUDA(cudaHostGetDevicePointer(&ctx->dot_result_d, ctx->dot_result_h, 0));
+    *out = ctx;
+    return B200_OK;
+}
+
+extern "C" int b200_ctx_destroy(b200_ctx_t ctx) {
+    if (!ctx) return B200_OK;
+    GUARD(ctx);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->dot_partial) cudaFree(ctx->dot_partial);
+    if (ctx->dot_ticket) cudaFree(ctx->dot_ticket);
+    if (ctx->dot_result_h) cudaFreeHost(ctx->dot_result_h);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return B200_OK;
+}
+
+extern "C" int b200_ctx_default(b200_ctx_t *out) {
+    B200_REQUIRE(out != nullptr, "null output pointer");
+    static std::mutex mtx;
+    static b200_ctx_t def = nullptr;
+    std::lock_guard<std::mutex> lock(mtx);
+    if (!def) {
+        int dev = 0;
+        B200_CUDA(cudaGetDevice(&dev));
+        int rc = b200_ctx_create(dev, &def);
+        if (rc != B200_OK) return rc;
+    }
+    *out = def;
+    return B200_OK;
+}
+
+extern "C" int b200_ctx_set_stream(b200_ctx_t ctx, void *cuda_stream) {
+    CHECK_CTX(ctx);
+    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return B200_OK;
+}
+
+extern "C" int b200_ctx_get_stream(b200_ctx_t ctx, void **cuda_stream) {
+    CHECK_CTX(ctx);
+    B200_REQUIRE(cuda_stream != nullptr, "null output pointer");
+    *cuda_stream = ctx->stream;
+    return B200_OK;
+}
+
+extern "C" int b200_ctx_device(b200_ctx_t ctx, int *device) {
+    CHECK_CTX(ctx);
+    B200_REQUIRE(device != nullptr, "null output pointer");
+    *device = ctx->device;
+    return B200_OK;
+}
+
+extern "C" int b200_ctx_sync(b200_ctx_t ctx) {
+    CHECK_CTX(ctx);
+    GUARD(ctx);
+    B200_CUDA(cudaStreamSynchronize(ctx->stream));
+    return B200_OK;
+}
+
+extern "C" int b200_ctx_launch_count(b200_ctx_t ctx, uint64_t *count) {
+    CHECK_CTX(ctx);
+    B200_REQUIRE(count != nullptr, "null output pointer");
+    *count = ctx->launches;
+    return B200_OK;
+}
+
+extern "C" int b200_ctx_reset_launch_count(b200_ctx_t ctx) {
+    CHECK_CTX(ctx);
+    ctx->launches = 0;
+    return B200_OK;
+}
+
+static int64_t *option_slot(b200_ctx_t ctx, const char *key) {
+    if (!key) return nullptr;
+    if (!strcmp(key, "spmv_variant")) return &ctx->opt_spmv_variant;
+    if (!strcmp(key, "fuse_relax")) return &ctx->opt_fuse_relax;
+    if (!strcmp(key, "zero_shortcut")) return &ctx->opt_zero_shortcut;
+    if (!strcmp(key, "nnz_cap")) return &ctx->opt_nnz_cap;
+    if (!strcmp(key, "lanes")) return &ctx->opt_lanes;
+    if (!strcmp(key, "ctas_per_sm")) return &ctx->opt_ctas_per_sm;
+    if (!strcmp(key, "stages")) return &ctx->opt_stages;
+    return nullptr;
+}
+
+extern "C" int b200_ctx_set_option(b200_ctx_t ctx, const char *key, int64_t value) {
+    CHECK_CTX(ctx);
+    int64_t *slot = option_slot(ctx, key);
+    if (!slot) return fail(B200_EINVAL, std::string("unknown option: ") + (key ? key : "(null)"));
+    if (slot == &ctx->opt_nnz_cap) {
+        if (value < 256 || value > kNnzCapMax || (value % 8))
+            return fail(B200_EINVAL, "nnz_cap must be a multiple of 8 in [256, 6144]");
+    } else if (slot == &ctx->opt_lanes) {
+        if (value != 0 && (value < 1 || value > 32 || (value & (value - 1))))
+            return fail(B200_EINVAL, "lanes must be 0 (auto) or a power of two <= 32");
+    } else if (slot == &ctx->opt_stages) {
+        if (value < 1 || value > 8) return fail(B200_EINVAL, "stages must be in [1, 8]");
+    } else if (slot == &ctx->opt_ctas_per_sm) {
+        if (value < 1 || value > 8) return fail(B200_EINVAL, "ctas_per_sm must be in [1, 8]");
+    } else if (slot == &ctx->opt_spmv_variant) {
+        if (value < 0 || value > 1) return fail(B200_EINVAL, "spmv_variant must be 0 or 1");
+    }
+    *slot = value;
+    return B200_OK;
+}
+
+extern "C" int b200_ctx_get_option(b200_ctx_t ctx, const char *key, int64_t *value) {
+    CHECK_CTX(ctx);
+    B200_REQUIRE(value != nullptr, "null output pointer");
+    int64_t *slot = option_slot(ctx, key);
+    if (!slot) return fail(B200_EINVAL, std::string("unknown option: ") + (key ? key : "(null)"));
+    *value = *slot;
+    return B200_OK;
+}
+
+// ---------------------------------------------------------------------------
+// vectors
+// ---------------------------------------------------------------------------
+extern "C" int b200_vec_create(b200_ctx_t ctx, size_t n, b200_vec_t *out) {
+    CHECK_CTX(ctx);
+    B200_REQUIRE(out != nullptr, "null output pointer");
+    *out = nullptr;
+    GUARD(ctx);
+    b200_vec_s *v = new (std::nothrow) b200_vec_s();
+    if (!v) return fail(B200_ENOMEM, "out of host memory");
+    v->ctx = ctx;
+    v->n = n;
+    v->owned = true;
+    // +2 doubles of padding so 16-byte vector accesses of the tail stay in bounds
+    cudaError_t rc = cudaMalloc(&v->ptr, (n + 2) * sizeof(double));
+    if (rc != cudaSuccess) {
+        delete v;
+        return cuda_fail(rc, "cudaMalloc(vector)", __FILE__, __LINE__);
+    }
+    v->zero_pending = true;   // logically zero; memset only if somebody looks
+    *out = v;
+    return B200_OK;
+}
+
+extern "C" int b200_vec_wrap(b200_ctx_t ctx, double *device_ptr, size_t n, b200_vec_t *out) {
+    CHECK_CTX(ctx);
+    B200_REQUIRE(out != nullptr, "null output pointer");
+    B200_REQUIRE(device_ptr != nullptr || n == 0, "null device pointer");
+    B200_REQUIRE((reinterpret_cast<uintptr_t>(device_ptr) & 7) == 0, "device pointer not 8-byte aligned");
+    b200_vec_s *v = new (std::nothrow) b200_vec_s();
+    if (!v) return fail(B200_ENOMEM, "out of host memory");
+    v->ctx = ctx;
+    v->n = n;
+    v->ptr = device_ptr;
+    v->owned = false;
+    v->zero_pending = false;
+    *out = v;
+    return B200_OK;
+}
+
+extern "C" int b200_vec_destroy(b200_vec_t v) {
+    if (!v) return B200_OK;
+    GUARD(v->ctx);
+    if (v->owned && v->ptr) {
+        // cudaFree synchronises the device, so no kernel can still be using it
+        cudaFree(v->ptr);
+    }
+    delete v;
+    return B200_OK;
+}
+
+extern "C" int b200_vec_size(b200_vec_t v, size_t *n) {
+    B200_REQUIRE(v && n, "null argument");
+    *n = v->n;
+    return B200_OK;
+}
+
+extern "C" int b200_vec_bytes(b200_vec_t v, size_t *bytes) {
+    B200_REQUIRE(v && bytes, "null argument");
+    *bytes = v->n * sizeof(double);
+    return B200_OK;
+}
+
+extern "C" int b200_vec_data(b200_vec_t v, double **device_ptr) {
+    B200_REQUIRE(v && device_ptr, "null argument");
+    GUARD(v->ctx);
+    int rc = materialize(v);
+    *device_ptr = v->ptr;
+    return rc;
+}
+
+extern "C" int b200_vec_upload(b200_vec_t v, const double *host, size_t n) {
+    B200_REQUIRE(v && (host || n == 0), "null argument");
+    B200_REQUIRE(n == v->n, "size mismatch in vector upload");
+    GUARD(v->ctx);
+    if (n) {
+        B200_CUDA(cudaMemcpyAsync(wr(v), host, n * sizeof(double), cudaMemcpyHostToDevice,
+                                  v->ctx->stream));
+        B200_CUDA(cudaStreamSynchronize(v->ctx->stream));
+    }
+    v->zero_pending = false;
+    return B200_OK;
+}
+
+extern "C" int b200_vec_download(b200_vec_t v, double *host, size_t n) {
+    B200_REQUIRE(v && (host || n == 0), "null argument");
+    B200_REQUIRE(n == v->n, "size mismatch in vector download");
+    GUARD(v->ctx);
+    if (!n) return B200_OK;
+    if (v->zero_pending) {          // nothing to fetch: the vector is zero
+        B200_CUDA(cudaStreamSynchronize(v->ctx->stream));
+        memset(host, 0, n * sizeof(double));
+        return B200_OK;
+    }
+    B200_CUDA(cudaMemcpyAsync(host, v->ptr, n * sizeof(double), cudaMemcpyDeviceToHost,
+                              v->ctx->stream));
+    B200_CUDA(cudaStreamSynchronize(v->ctx->stream));
+    return B200_OK;
+}
+
+// ---------------------------------------------------------------------------
+// matrices
+// ---------------------------------------------------------------------------
+namespace b200 {
+
+static int choose_lanes(double avg) {
+    if (avg <= 12.0) return 1;
+    if (avg <= 24.0) return 2;
+    if (avg <= 48.0) return 4;
+    if (avg <= 96.0) return 8;
+    if (avg <= 192.0) return 16;
+    return 32;
+}
+
+
+// Row-block plan (pure host logic, also exported as b200_plan_i64 for tests):
+// consecutive rows, starting at a multiple of four, are packed greedily while
+// they fit `rows_cap` rows and `nnz_cap` non-zeros.  A block that still exceeds
+// nnz_cap (a single quad of very long rows) is counted as "long" and is handled
+// by the strided path of the kernels.
+struct RowBlockPlan {
+    int lanes = 1, rows_cap = 256, nnz_cap = 2048;
+    int64_t nlong = 0;
+    std::vector<int2> blk;   // {first row, first non-zero}; last entry = {nrows, nnz}
+};
+
+template <class Ptr>
+static void build_plan(int64_t nrows, const Ptr *ptr, int lanes_opt, int nnz_cap,
+                       RowBlockPlan &plan) {
+    const int64_t nnz = nrows ? (int64_t)ptr[nrows] : 0;
+    const double avg = nrows ? (double)nnz / (double)nrows : 0.0;
+    const int lanes = lanes_opt ? lanes_opt : choose_lanes(avg);
+    const int groups = kThreads / lanes;
+    // rows per block: a multiple of the number of row groups, sized so a typical
+    // block fills the stage
+    int k = 1;
+    if (avg > 0.0) k = (int)std::floor((double)nnz_cap / (avg * groups));
+    k = std::max(1, std::min(k, kRowsCapMax / groups));
+    int rows_cap = std::min(kRowsCapMax, groups * k);
+    rows_cap = std::max(4, rows_cap & ~3);
+    plan.lanes = lanes; plan.rows_cap = rows_cap; plan.nnz_cap = nnz_cap; plan.nlong = 0;
+    plan.blk.clear();
+    plan.blk.reserve((size_t)(nnz / std::max(1, nnz_cap / 2) + nrows / rows_cap + 16));
+    int64_t r = 0;
+    while (r < nrows) {
+        const int64_t r0 = r;
+        const int64_t e0 = (int64_t)ptr[r0];
+        // always take the first quad, then grow quad by quad while it fits
+        int64_t r1 = std::min<int64_t>(nrows, r0 + 4);
+        while (r1 < nrows) {
+            const int64_t rn = std::min<int64_t>(nrows, r1 + 4);
+            if (rn - r0 > rows_cap) break;
+            if ((int64_t)ptr[rn] - e0 > nnz_cap) break;
+            r1 = rn;
+        }
+        if ((int64_t)ptr[r1] - e0 > nnz_cap) ++plan.nlong;
+        plan.blk.push_back(make_int2((int)r0, (int)e0));
+        r = r1;
+    }
+    plan.blk.push_back(make_int2((int)nrows, (int)nnz));
+}
+
+template <class Ptr, class Col>
+static int csr_create(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *ptr,
+                      const Col *col, const double *val, b200_csr_t *out) {
+    CHECK_CTX(ctx);
+    B200_REQUIRE(out != nullptr, "null output pointer");
+    *out = nullptr;
+    B200_REQUIRE(nrows >= 0 && ncols >= 0, "negative matrix dimension");
+    B200_REQUIRE(ptr != nullptr, "null row pointer array");
+    const int64_t imax = std::numeric_limits<int32_t>::max();
+    if (nrows >= imax - 8 || ncols >= imax) return fail(B200_ERANGE, "matrix dimension exceeds int32");
+    B200_REQUIRE(ptr[0] == 0, "ptr[0] must be 0");
+    const int64_t nnz = (int64_t)ptr[nrows];
+    if (nnz < 0) return fail(B200_EINVAL, "negative number of non-zeros");
+    if (nnz >= imax - 8) return fail(B200_ERANGE, "number of non-zeros exceeds int32");
+    B200_REQUIRE(nnz == 0 || (col != nullptr && val != nullptr), "null col/val array");
+    GUARD(ctx);
+
+    // ---- narrow indices, validate ------------------------------------------
+    std::vector<int32_t> hptr((size_t)nrows + 1), hcol((size_t)nnz);
+    for (int64_t i = 0; i <= nrows; ++i) {
+        const int64_t p = (int64_t)ptr[i];
+        if (i && p < (int64_t)ptr[i - 1]) return fail(B200_EINVAL, "row pointers not monotone");
+        hptr[(size_t)i] = (int32_t)p;
+    }
+    for (int64_t e = 0; e < nnz; ++e) {
+        const int64_t c = (int64_t)col[e];
+        if (c < 0 || c >= ncols) return fail(B200_EINVAL, "column index out of range");
+        hcol[(size_t)e] = (int32_t)c;
+    }
+
+    // ---- row-block plan -------------------------------------------------------
+    RowBlockPlan plan;
+    build_plan(nrows, hptr.data(), (int)ctx->opt_lanes, (int)ctx->opt_nnz_cap, plan);
+    const int lanes = plan.lanes, rows_cap = plan.rows_cap, nnz_cap = plan.nnz_cap;
+    const int64_t nlong = plan.nlong;
+    std::vector<int2> &blk = plan.blk;
+    const int64_t nblocks = (int64_t)blk.size() - 1;
+
+    // ---- upload ---------------------------------------------------------------------
+    b200_csr_s *A = new (std::nothrow) b200_csr_s();
+    if (!A) return fail(B200_ENOMEM, "out of host memory");
+    A->ctx = ctx; A->nrows = nrows; A->ncols = ncols; A->nnz = nnz;
+    A->lanes = lanes; A->rows_cap = rows_cap; A->nnz_cap = nnz_cap;
+    A->nblocks = nblocks; A->nlong = nlong;
+    // padding: bulk copies round sizes up to 16 bytes
+    const size_t ptr_bytes = ((size_t)nrows + 1 + 8) * sizeof(int);
+    const size_t col_bytes = ((size_t)nnz + 8) * sizeof(int);
+    const size_t val_bytes = ((size_t)nnz + 4) * sizeof(double);
+    const size_t blk_bytes = ((size_t)nblocks + 1) * sizeof(int2);
+    auto cleanup = [&]() {
+        if (A->ptr) cudaFree(A->ptr);
+        if (A->col) cudaFree(A->col);
+        if (A->val) cudaFree(A->val);
+        if (A->blk) cudaFree(A->blk);
+        delete A;
+    };
+#define CSR_CUDA(call)                                                         \
+    do {                                                                       \
+        cudaError_t rc__ = (call);                                             \
+        if (rc__ != cudaSuccess) {                                             \
+            cleanup();                                                         \
+            return cuda_fail(rc__, #call, __FILE__, __LINE__);                 \
+        }                                                                      \
+    } while (0)
+    CSR_CUDA(cudaMalloc(&A->ptr, ptr_bytes));
+    CSR_CUDA(cudaMalloc(&A->col, col_bytes));
+    CSR_CUDA(cudaMalloc(&A->val, val_bytes));
+    CSR_CUDA(cudaMalloc(&A->blk, blk_bytes));
+    CSR_CUDA(cudaMemsetAsync(A->ptr, 0, ptr_bytes, ctx->stream));
+    CSR_CUDA(cudaMemsetAsync(A->col, 0, col_bytes, ctx->stream));
+    CSR_CUDA(cudaMemsetAsync(A->val, 0, val_bytes, ctx->stream));
+    CSR_CUDA(cudaMemcpyAsync(A->ptr, hptr.data(), ((size_t)nrows + 1) * sizeof(int),
+                             cudaMemcpyHostToDevice, ctx->stream));
+    if (nnz) {
+        CSR_CUDA(cudaMemcpyAsync(A->col, hcol.data(), (size_t)nnz * sizeof(int),
+                                 cudaMemcpyHostToDevice, ctx->stream));
+        CSR_CUDA(cudaMemcpyAsync(A->val, val, (size_t)nnz * sizeof(double),
+                                 cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CSR_CUDA(cudaMemcpyAsync(A->blk, blk.data(), blk_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CSR_CUDA(cudaStreamSynchronize(ctx->stream));   // host staging buffers die here
+#undef CSR_CUDA
+    A->bytes = ptr_bytes + col_bytes + val_bytes + blk_bytes;
+    *out = A;
+    return B200_OK;
+}
+
+// ---- launch one streaming pass over A ------------------------------------------------
+template <int MODE, int L>
+static int launch_csr_L(b200_ctx_t ctx, b200_csr_t A, const CsrArgs &args) {
+    const StageLayout lay = stage_layout(A->rows_cap, A->nnz_cap);
+    if (ctx->opt_spmv_variant == 0) {
+        const int smem = kHeaderBytes + lay.bytes;
+        static bool attr_set[64] = {};   // per instantiation and device
+        if (!attr_set[ctx->device & 63]) {
+            B200_CUDA(cudaFuncSetAttribute(csr_block_kernel<MODE, L>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_set[ctx->device & 63] = true;
+        }
+        csr_block_kernel<MODE, L><<<(unsigned)A->nblocks, kThreads, smem, ctx->stream>>>(args);
+    } else {
+        int stages = (int)ctx->opt_stages;
+        const int max_smem = 227 * 1024;
+        const int per_cta_budget = max_smem / (int)ctx->opt_ctas_per_sm - 1024;
+        while (stages > 1 && kHeaderBytes + stages * lay.bytes > per_cta_budget) --stages;
+        const int smem = kHeaderBytes + stages * lay.bytes;
+        static bool attr_set[64] = {};
+        if (!attr_set[ctx->device & 63]) {
+            B200_CUDA(cudaFuncSetAttribute(csr_ring_kernel<MODE, L>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+            attr_set[ctx->device & 63] = true;
+        }
+        const int64_t cap = (int64_t)ctx->sm_count * ctx->opt_ctas_per_sm;
+        const unsigned grid = (unsigned)std::min<int64_t>(A->nblocks, cap);
+        csr_ring_kernel<MODE, L><<<grid, kThreads, smem, ctx->stream>>>(args, stages);
+    }
+    B200_CHECK_LAUNCH();
+    ctx->launches++;
+    return B200_OK;
+}
+
+template <int MODE>
+static int launch_csr(b200_ctx_t ctx, b200_csr_t A, const CsrArgs &args) {
+    if (A->nblocks == 0) return B200_OK;
+    switch (A->lanes) {
+    case 1:  return launch_csr_L<MODE, 1>(ctx, A, args);
+    case 2:  return launch_csr_L<MODE, 2>(ctx, A, args);
+    case 4:  return launch_csr_L<MODE, 4>(ctx, A, args);
+    case 8:  return launch_csr_L<MODE, 8>(ctx, A, args);
+    case 16: return launch_csr_L<MODE, 16>(ctx, A, args);
+    default: return launch_csr_L<MODE, 32>(ctx, A, args);
+    }
+}
+
+static CsrArgs base_args(b200_csr_t A) {
+    CsrArgs a;
+    memset(&a, 0, sizeof(a));
+    a.ptr = A->ptr; a.col = A->col; a.val = A->val; a.blk = A->blk;
+    a.nrows = (int)A->nrows; a.nblocks = (int)A->nblocks;
+    a.rows_cap = A->rows_cap; a.nnz_cap = A->nnz_cap;
+    return a;
+}
+
+// ---- element-wise launch helper ---------------------------------------------------------
+template <class F, bool RY, bool RZ>
+static int launch_ew(b200_ctx_t ctx, size_t n, F f, const double *x, const double *y,
+                     const double *z, double *out) {
+    if (n == 0) return B200_OK;
+    const bool vec_ok = aligned16(x) && aligned16(out) && (!RY || aligned16(y)) &&
+                        (!RZ || aligned16(z));
+    const int grid = grid_for(ctx, n, 4);
+    ew_kernel<F, RY, RZ><<<grid, kThreads, 0, ctx->stream>>>(n, f, x, y, z, out, vec_ok);
+    B200_CHECK_LAUNCH();
+    ctx->launches++;
+    return B200_OK;
+}
+
+} // namespace b200
+
+extern "C" int b200_csr_create_i64(b200_ctx_t ctx, int64_t nrows, int64_t ncols,
+                                   const int64_t *ptr, const int64_t *col, const double *val,
+                                   b200_csr_t *A) {
+    return csr_create(ctx, nrows, ncols, ptr, col, val, A);
+}
+
+extern "C" int b200_csr_create_i32(b200_ctx_t ctx, int64_t nrows, int64_t ncols,
+                                   const int32_t *ptr, const int32_t *col, const double *val,
+                                   b200_csr_t *A) {
+    return csr_create(ctx, nrows, ncols, ptr, col, val, A);
+}
+
+extern "C" int b200_plan_i64(int64_t nrows, const int64_t *ptr, int lanes, int nnz_cap,
+                             int32_t *blk_out, int64_t blk_capacity, int64_t *nblocks,
+                             int *lanes_out, int *rows_cap_out, int64_t *nlong_out) {
+    B200_REQUIRE(nrows >= 0 && ptr != nullptr && nblocks != nullptr, "bad argument");
+    B200_REQUIRE(nnz_cap >= 256 && nnz_cap <= kNnzCapMax && nnz_cap % 8 == 0, "bad nnz_cap");
+    B200_REQUIRE(lanes == 0 || (lanes >= 1 && lanes <= 32 && !(lanes & (lanes - 1))), "bad lanes");
+    RowBlockPlan plan;
+    build_plan(nrows, ptr, lanes, nnz_cap, plan);
+    *nblocks = (int64_t)plan.blk.size() - 1;
+    if (lanes_out) *lanes_out = plan.lanes;
+    if (rows_cap_out) *rows_cap_out = plan.rows_cap;
+    if (nlong_out) *nlong_out = plan.nlong;
+    if (blk_out) {
+        if ((int64_t)plan.blk.size() > blk_capacity)
+            return fail(B200_EINVAL, "plan output buffer too small");
+        for (size_t i = 0; i < plan.blk.size(); ++i) {
+            blk_out[2 * i] = plan.blk[i].x;
+            blk_out[2 * i + 1] = plan.blk[i].y;
+        }
+    }
+    return B200_OK;
+}
+
+extern "C" int b200_csr_destroy(b200_csr_t A) {
+    if (!A) return B200_OK;
+    GUARD(A->ctx);
+    if (A->ptr) cudaFree(A->ptr);
+    if (A->col) cudaFree(A->col);
+    if (A->val) cudaFree(A->val);
+    if (A->blk) cudaFree(A->blk);
+    delete A;
+    return B200_OK;
+}
+
+extern "C" int b200_csr_rows(b200_csr_t A, size_t *n) {
+    B200_REQUIRE(A && n, "null argument");
+    *n = (size_t)A->nrows;
+    return B200_OK;
+}
+extern "C" int b200_csr_cols(b200_csr_t A, size_t *n) {
+    B200_REQUIRE(A && n, "null argument");
+    *n = (size_t)A->ncols;
+    return B200_OK;
+}
+extern "C" int b200_csr_nonzeros(b200_csr_t A, size_t *n) {
+    B200_REQUIRE(A && n, "null argument");
+    *n = (size_t)A->nnz;
+    return B200_OK;
+}
+extern "C" int b200_csr_bytes(b200_csr_t A, size_t *bytes) {
+    B200_REQUIRE(A && bytes, "null argument");
+    *bytes = A->bytes;
+    return B200_OK;
+}
+extern "C" int b200_csr_plan(b200_csr_t A, int *lanes_per_row, int64_t *n_blocks,
+                             int64_t *n_long_blocks) {
+    B200_REQUIRE(A, "null argument");
+    if (lanes_per_row) *lanes_per_row = A->lanes;
+    if (n_blocks) *n_blocks = A->nblocks;
+    if (n_long_blocks) *n_long_blocks = A->nlong;
+    return B200_OK;
+}
+
+// ---------------------------------------------------------------------------
+// primitives
+// ---------------------------------------------------------------------------
+extern "C" int b200_spmv(b200_ctx_t ctx, double alpha, b200_csr_t A, b200_vec_t x, double beta,
+                         b200_vec_t y) {
+    CHECK_CTX(ctx);
+    B200_REQUIRE(A && x && y, "null argument");
+    B200_REQUIRE((int64_t)x->n == A->ncols, "spmv: x size != matrix columns");
+    B200_REQUIRE((int64_t)y->n == A->nrows, "spmv: y size != matrix rows");
+    B200_REQUIRE(x != y && x->ptr != y->ptr, "spmv: x and y must not alias");
+    GUARD(ctx);
+    CsrArgs a = base_args(A);
+    int rc = rd(x, &a.x);
+    if (rc) return rc;
+    a.alpha = alpha; a.beta = beta;
+    if (beta == 0.0 || y->zero_pending) {
+        a.y = wr(y);
+        return launch_csr<MODE_SPMV>(ctx, A, a);
+    }
+    a.y = y->ptr;
+    return launch_csr<MODE_SPMV_ACC>(ctx, A, a);
+}
+
+extern "C" int b200_residual(b200_ctx_t ctx, b200_vec_t f, b200_csr_t A, b200_vec_t x,
+                             b200_vec_t r) {
+    CHECK_CTX(ctx);
+    B200_REQUIRE(f && A && x && r, "null argument");
+    B200_REQUIRE((int64_t)x->n == A->ncols, "residual: x size != matrix columns");
+    B200_REQUIRE((int64_t)f->n == A->nrows && (int64_t)r->n == A->nrows,
+                 "residual: rhs/r size != matrix rows");
+    B200_REQUIRE(x != r && x->ptr != r->ptr, "residual: x and r must not alias");
+    GUARD(ctx);
+    CsrArgs a = base_args(A);
+    int rc = rd(x, &a.x);
+    if (rc) return rc;
+    rc = rd(f, &a.f);
+    if (rc) return rc;
+    a.y = (f == r) ? r->ptr : wr(r);   // r == f is fine: each row reads f[r] before writing
+    return launch_csr<MODE_RESID>(ctx, A, a);
+}
+
+extern "C" int b200_clear(b200_ctx_t ctx, b200_vec_t x) {
+    CHECK_CTX(ctx);
+    B200_REQUIRE(x, "null argument");
+    if (ctx->opt_zero_shortcut) {
+        x->zero_pending = true;
+        return B200_OK;
+    }
+    GUARD(ctx);
+    x->zero_pending = true;
+    return materialize(x);
+}
+
+extern "C" int b200_copy(b200_ctx_t ctx, b200_vec_t x, b200_vec_t y) {
+    CHECK_CTX(ctx);
+    B200_REQUIRE(x && y, "null argument");
+    B200_REQUIRE(x->n == y->n, "copy: size mismatch");
+    if (x == y || x->ptr == y->ptr) return B200_OK;
+    if (x->zero_pending) {
+        y->zero_pending = true;
+        return B200_OK;
+    }
+    GUARD(ctx);
+    return launch_ew<CopyF, false, false>(ctx, x->n, CopyF(), x->ptr, nullptr, nullptr, wr(y));
+}
+
+extern "C" int b200_dot(b200_ctx_t ctx, b200_vec_t x, b200_vec_t y, double *result) {
+    CHECK_CTX(ctx);
+    B200_REQUIRE(x && y && result, "null argument");
+    B200_REQUIRE(x->n == y->n, "dot: size mismatch");
+    GUARD(ctx);
+    if (x->n == 0 || x->zero_pending || y->zero_pending) {
+        B200_CUDA(cudaStreamSynchronize(ctx->stream));
+        *result = 0.0;
+        return B200_OK;
+    }
+    const bool vec_ok = aligned16(x->ptr) && aligned16(y->ptr);
+    int grid = std::min(grid_for(ctx, x->n, 8), kDotMaxBlocks);
+    dot_kernel<<<grid, kThreads, 0, ctx->stream>>>(x->n, x->ptr, y->ptr, ctx->dot_partial,
+                                                   ctx->dot_ticket, ctx->dot_result_d, vec_ok);
+    B200_CHECK_LAUNCH();
+    ctx->launches++;
+    B200_CUDA(cudaStreamSynchronize(ctx->stream));
+    *result = *reinterpret_cast<volatile double *>(ctx->dot_result_h);
+    return B200_OK;
+}
+
+extern "C" int b200_axpby(b200_ctx_t ctx, double a, b200_vec_t x, double b, b200_vec_t y) {
+    CHECK_CTX(ctx);
+    B200_REQUIRE(x && y, "null argument");
+    B200_REQUIRE(x->n == y->n, "axpby: size mismatch");
+    GUARD(ctx);
+    const double *px;
+    int rc = rd(x, &px);
+    if (rc) return rc;
+    if (b == 0.0 || y->zero_pending) {
+        AxF f{a};
+        return launch_ew<AxF, false, false>(ctx, x->n, f, px, nullptr, nullptr, wr(y));
+    }
+    AxpbyF f{a, b};
+    return launch_ew<AxpbyF, true, false>(ctx, x->n, f, px, y->ptr, nullptr, y->ptr);
+}
+
+extern "C" int b200_axpbypcz(b200_ctx_t ctx, double a, b200_vec_t x, double b, b200_vec_t y,
+                             double c, b200_vec_t z) {
+    CHECK_CTX(ctx);
+    B200_REQUIRE(x && y && z, "null argument");
+    B200_REQUIRE(x->n == y->n && x->n == z->n, "axpbypcz: size mismatch");
+    GUARD(ctx);
+    const double *px, *py;
+    int rc = rd(x, &px);
+    if (rc) return rc;
+    rc = rd(y, &py);
+    if (rc) return rc;
+    if (c == 0.0 || z->zero_pending) {
+        AxpbyZF f{a, b};
+        return launch_ew<AxpbyZF, true, false>(ctx, x->n, f, px, py, nullptr, wr(z));
+    }
+    AxpbypczF f{a, b, c};
+    return launch_ew<AxpbypczF, true, true>(ctx, x->n, f, px, py, z->ptr, z->ptr);
+}
+
+extern "C" int b200_vmul(b200_ctx_t ctx, double alpha, b200_vec_t x, b200_vec_t y, double beta,
+                         b200_vec_t z) {
+    CHECK_CTX(ctx);
+    B200_REQUIRE(x && y && z, "null argument");
+    B200_REQUIRE(x->n == y->n && x->n == z->n, "vmul: size mismatch");
+    GUARD(ctx);
+    const double *px, *py;
+    int rc = rd(x, &px);
+    if (rc) return rc;
+    rc = rd(y, &py);
+    if (rc) return rc;
+    if (beta == 0.0 || z->zero_pending) {
+        VmulF f{alpha};
+        return launch_ew<VmulF, true, false>(ctx, x->n, f, px, py, nullptr, wr(z));
+    }
+    VmulAccF f{alpha, beta};
+    return launch_ew<VmulAccF, true, true>(ctx, x->n, f, px, py, z->ptr, z->ptr);
+}
+
+// ---------------------------------------------------------------------------
+// smoother sweep
+// ---------------------------------------------------------------------------
+extern "C" int b200_relax(b200_ctx_t ctx, b200_csr_t A, b200_vec_t rhs, b200_vec_t x,
+                          b200_vec_t tmp, b200_vec_t diag, double omega) {
+    CHECK_CTX(ctx);
+    B200_REQUIRE(A && rhs && x && tmp && diag, "null argument");
+    B200_REQUIRE(A->nrows == A->ncols, "relax: matrix must be square");
+    B200_REQUIRE((int64_t)x->n == A->nrows && (int64_t)rhs->n == A->nrows &&
+                     (int64_t)diag->n == A->nrows && (int64_t)tmp->n == A->nrows,
+                 "relax: vector size != matrix rows");
+    B200_REQUIRE(x != tmp && x->ptr != tmp->ptr && x != rhs && tmp != rhs,
+                 "relax: x, tmp and rhs must be distinct vectors");
+    GUARD(ctx);
+    const double *pf, *pd;
+    int rc = rd(rhs, &pf);
+    if (rc) return rc;
+    rc = rd(diag, &pd);
+    if (rc) return rc;
+
+    if (x->zero_pending && ctx->opt_zero_shortcut) {
+        // residual(rhs, A, 0) == rhs exactly, so the sweep reduces to a scaling
+        const int grid = grid_for(ctx, x->n, 2);
+        relax_zero_kernel<<<grid, kThreads, 0, ctx->stream>>>(x->n, omega, pd, pf, wr(x));
+        B200_CHECK_LAUNCH();
+        ctx->launches++;
+        return B200_OK;
+    }
+
+    if (!ctx->opt_fuse_relax) {
+        // the literal reference sequence: tmp = rhs - A x ; x = omega*diag.*tmp + x
+        rc = b200_residual(ctx, rhs, A, x, tmp);
+        if (rc) return rc;
+        return b200_vmul(ctx, omega, diag, tmp, 1.0, x);
+    }
+
+    CsrArgs a = base_args(A);
+    rc = rd(x, &a.x);
+    if (rc) return rc;
+    a.f = pf; a.d = pd; a.alpha = omega;
+    a.y = wr(tmp);
+    rc = launch_csr<MODE_RELAX>(ctx, A, a);
+    if (rc) return rc;
+    if (x->owned && tmp->owned) {
+        std::swap(x->ptr, tmp->ptr);          // x now holds the new iterate
+    } else {
+        B200_CUDA(cudaMemcpyAsync(x->ptr, tmp->ptr, x->n * sizeof(double),
+                                  cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    return B200_OK;
+}
+
+// ---------------------------------------------------------------------------
+// coarse solve
+// ---------------------------------------------------------------------------
+namespace b200 {
+
+template <class Ptr, class Col>
+static int coarse_create(b200_ctx_t ctx, int64_t n, const Ptr *ptr, const Col *col,
+                         const double *val, b200_coarse_t *out) {
+    CHECK_CTX(ctx);
+    B200_REQUIRE(out != nullptr, "null output pointer");
+    *out = nullptr;
+    B200_REQUIRE(n > 0 && n <= 16384, "coarse solver: n must be in [1, 16384]");
+    B200_REQUIRE(ptr && ptr[0] == 0, "bad row pointer array");
+    const int64_t nnz = (int64_t)ptr[n];
+    B200_REQUIRE(nnz >= 0 && (nnz == 0 || (col && val)), "bad col/val array");
+    GUARD(ctx);
+
+    std::vector<int32_t> hptr((size_t)n + 1), hcol((size_t)nnz);
+    for (int64_t i = 0; i <= n; ++i) hptr[(size_t)i] = (int32_t)ptr[i];
+    for (int64_t e = 0; e < nnz; ++e) {
+        const int64_t c = (int64_t)col[e];
+        if (c < 0 || c >= n) return fail(B200_EINVAL, "coarse solver: column index out of range");
+        hcol[(size_t)e] = (int32_t)c;
+    }
+
+    const int N = (int)n;
+    int *dptr = nullptr, *dcol = nullptr, *dpiv = nullptr;
+    double *dval = nullptr, *M = nullptr, *colk = nullptr, *pivval = nullptr, *Ainv = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(dptr); cudaFree(dcol); cudaFree(dval); cudaFree(M);
+        cudaFree(colk); cudaFree(dpiv); cudaFree(pivval);
+    };
+#define CO_CUDA(call)                                                          \
+    do {                                                                       \
+        cudaError_t rc__ = (call);                                             \
+        if (rc__ != cudaSuccess) {                                             \
+            cleanup();                                                         \
+            cudaFree(Ainv);                                                    \
+            return cuda_fail(rc__, #call, __FILE__, __LINE__);                 \
+        }                                                                      \
+    } while (0)
+    const size_t Mbytes = (size_t)N * 2 * N * sizeof(double);
+    CO_CUDA(cudaMalloc(&dptr, ((size_t)N + 1) * sizeof(int)));
+    CO_CUDA(cudaMalloc(&dcol, std::max<size_t>(1, (size_t)nnz) * sizeof(int)));
+    CO_CUDA(cudaMalloc(&dval, std::max<size_t>(1, (size_t)nnz) * sizeof(double)));
+    CO_CUDA(cudaMalloc(&M, Mbytes));
+    CO_CUDA(cudaMalloc(&colk, (size_t)N * sizeof(double)));
+    CO_CUDA(cudaMalloc(&dpiv, sizeof(int)));
+    CO_CUDA(cudaMalloc(&pivval, ((size_t)N + 1) * sizeof(double)));
+    CO_CUDA(cudaMalloc(&Ainv, (size_t)N * N * sizeof(double)));
+    cudaStream_t st = ctx->stream;
+    CO_CUDA(cudaMemcpyAsync(dptr, hptr.data(), ((size_t)N + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+    if (nnz) {
+        CO_CUDA(cudaMemcpyAsync(dcol, hcol.data(), (size_t)nnz * sizeof(int), cudaMemcpyHostToDevice, st));
+        CO_CUDA(cudaMemcpyAsync(dval, val, (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    CO_CUDA(cudaMemsetAsync(M, 0, Mbytes, st));
+    coarse_scatter_kernel<<<(N + 127) / 128, 128, 0, st>>>(N, dptr, dcol, dval, M);
+    CO_CUDA(cudaGetLastError());
+    ctx->launches++;
+
+    const int gcol2 = (2 * N + kThreads - 1) / kThreads;
+    const int gcol1 = (N + kThreads - 1) / kThreads;
+    const int ysplit = std::max(1, std::min(N, (ctx->sm_count * 4) / std::max(1, gcol2)));
+    for (int k = 0; k < N; ++k) {
+        coarse_pivot_kernel<<<1, kThreads, 0, st>>>(N, k, M, dpiv, pivval + k);
+        coarse_colk_kernel<<<gcol1, kThreads, 0, st>>>(N, k, M, dpiv, colk);
+        coarse_swap_scale_kernel<<<gcol2, kThreads, 0, st>>>(N, k, M, dpiv, pivval + k);
+        const int gx = (2 * N - k + kThreads - 1) / kThreads;
+        coarse_eliminate_kernel<<<dim3(gx, ysplit), kThreads, 0, st>>>(N, k, M, colk);
+        ctx->launches += 4;
+    }
+    CO_CUDA(cudaGetLastError());
+    {
+        const size_t tot = (size_t)N * N;
+        coarse_extract_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(N, M, Ainv);
+        CO_CUDA(cudaGetLastError());
+        ctx->launches++;
+    }
+    std::vector<double> hpiv((size_t)N);
+    CO_CUDA(cudaMemcpyAsync(hpiv.data(), pivval, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CO_CUDA(cudaStreamSynchronize(st));
+#undef CO_CUDA
+    cleanup();
+    double pmax = 0.0, pmin = std::numeric_limits<double>::infinity();
+    for (double p : hpiv) {
+        const double a = std::fabs(p);
+        if (!(a == a)) { pmin = 0.0; break; }   // NaN
+        pmax = std::max(pmax, a);
+        pmin = std::min(pmin, a);
+    }
+    if (!(pmin > 0.0) || pmin < pmax * 1e-14 || !std::isfinite(pmax)) {
+        cudaFree(Ainv);
+        return fail(B200_ESINGULAR, "coarse matrix is numerically singular");
+    }
+
+    b200_coarse_s *S = new (std::nothrow) b200_coarse_s();
+    if (!S) {
+        cudaFree(Ainv);
+        return fail(B200_ENOMEM, "out of host memory");
+    }
+    S->ctx = ctx; S->n = n; S->Ainv = Ainv; S->bytes = (size_t)N * N * sizeof(double);
+    *out = S;
+    return B200_OK;
+}
+
+} // namespace b200
+
+extern "C" int b200_coarse_create_i64(b200_ctx_t ctx, int64_t n, const int64_t *ptr,
+                                      const int64_t *col, const double *val, b200_coarse_t *S) {
+    return coarse_create(ctx, n, ptr, col, val, S);
+}
+extern "C" int b200_coarse_create_i32(b200_ctx_t ctx, int64_t n, const int32_t *ptr,
+                                      const int32_t *col, const double *val, b200_coarse_t *S) {
+    return coarse_create(ctx, n, ptr, col, val, S);
+}
+
+extern "C" int b200_coarse_destroy(b200_coarse_t S) {
+    if (!S) return B200_OK;
+    GUARD(S->ctx);
+    if (S->Ainv) cudaFree(S->Ainv);
+    delete S;
+    return B200_OK;
+}
+
+extern "C" int b200_coarse_bytes(b200_coarse_t S, size_t *bytes) {
+    B200_REQUIRE(S && bytes, "null argument");
+    *bytes = S->bytes;
+    return B200_OK;
+}
+
+extern "C" int b200_coarse_solve(b200_ctx_t ctx, b200_coarse_t S, b200_vec_t rhs, b200_vec_t x) {
+    CHECK_CTX(ctx);
+    B200_REQUIRE(S && rhs && x, "null argument");
+    B200_REQUIRE((int64_t)rhs->n == S->n && (int64_t)x->n == S->n, "coarse solve: size mismatch");
+    B200_REQUIRE(rhs != x && rhs->ptr != x->ptr, "coarse solve: rhs and x must not alias");
+    GUARD(ctx);
+    const double *pr;
+    int rc = rd(rhs, &pr);
+    if (rc) return rc;
+    const int N = (int)S->n;
+    const int warps_per_cta = kThreads / 32;
+    coarse_gemv_kernel<<<(N + warps_per_cta - 1) / warps_per_cta, kThreads, 0, ctx->stream>>>(
+        N, S->Ainv, pr, wr(x));
+    B200_CHECK_LAUNCH();
+    ctx->launches++;
+    return B200_OK;
+}

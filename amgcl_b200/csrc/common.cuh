@@ -1,0 +1,198 @@
+// common.cuh -- shared definitions for the B200 solve-phase backend.
+//
+// Device objects behind the opaque C handles of include/amgcl_b200.h, error
+// plumbing, and the sm_100a PTX helpers (mbarrier + 1-D TMA bulk copies) the
+// streaming kernels are built from.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <string>
+#include <vector>
+
+#include "../../include/amgcl_b200.h"
+
+namespace b200 {
+
+// ---------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------
+void set_error(const std::string &msg);
+int  fail(int code, const std::string &msg);
+int  cuda_fail(cudaError_t rc, const char *what, const char *file, int line);
+
+#define B200_CUDA(call)                                                        \
+    do {                                                                       \
+        cudaError_t rc__ = (call);                                             \
+        if (rc__ != cudaSuccess)                                               \
+            return ::b200::cuda_fail(rc__, #call, __FILE__, __LINE__);         \
+    } while (0)
+
+#define B200_CHECK_LAUNCH()                                                    \
+    do {                                                                       \
+        cudaError_t rc__ = cudaGetLastError();                                 \
+        if (rc__ != cudaSuccess)                                               \
+            return ::b200::cuda_fail(rc__, "kernel launch", __FILE__, __LINE__); \
+    } while (0)
+
+#define B200_REQUIRE(cond, msg)                                                \
+    do {                                                                       \
+        if (!(cond)) return ::b200::fail(B200_EINVAL, msg);                    \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// hardware constants (B200: 148 SMs, 227 KB smem / CTA)
+// ---------------------------------------------------------------------------
+constexpr int kThreads      = 256;    // threads per CTA in every streaming kernel
+constexpr int kRowsCapMax   = 1024;   // most rows a row block may hold
+constexpr int kNnzCapMax    = 6144;   // most non-zeros a staged row block may hold
+constexpr int kDotMaxBlocks = 2048;   // upper bound on partial sums of one dot product
+
+} // namespace b200
+
+// ---------------------------------------------------------------------------
+// objects behind the opaque handles
+// ---------------------------------------------------------------------------
+struct b200_ctx_s {
+    int          device      = 0;
+    int          sm_count    = 148;
+    cudaStream_t own_stream  = nullptr;
+    cudaStream_t stream      = nullptr;   // stream in use (own or external)
+    uint64_t     launches    = 0;
+
+    // dot product scratch: per-CTA partial sums, completion ticket, result
+    double       *dot_partial = nullptr;  // [kDotMaxBlocks] device
+    unsigned int *dot_ticket  = nullptr;  // device, self-resetting
+    double       *dot_result_h = nullptr; // pinned + mapped host scalar(s)
+    double       *dot_result_d = nullptr; // device alias of dot_result_h
+
+    // tuning
+    int64_t opt_spmv_variant  = 0;
+    int64_t opt_fuse_relax    = 1;
+    int64_t opt_zero_shortcut = 1;
+    int64_t opt_nnz_cap       = 2048;
+    int64_t opt_lanes         = 0;        // 0 = choose from average row length
+    int64_t opt_ctas_per_sm   = 2;        // persistent variant: CTAs per SM
+    int64_t opt_stages        = 4;        // persistent variant: ring depth
+};
+
+struct b200_vec_s {
+    b200_ctx_t ctx   = nullptr;
+    double    *ptr   = nullptr;
+    size_t     n     = 0;
+    bool       owned = true;
+    // Lazy clear: the vector is logically zero but the memset has not been
+    // issued.  Set by b200_clear, consumed by b200_relax (which then skips the
+    // A-pass), dropped by any full overwrite, materialised by any other read.
+    bool       zero_pending = false;
+};
+
+struct b200_csr_s {
+    b200_ctx_t ctx   = nullptr;
+    int64_t    nrows = 0, ncols = 0, nnz = 0;
+    int       *ptr   = nullptr;   // [nrows+1] (+ padding) device
+    int       *col   = nullptr;   // [nnz]     (+ padding) device
+    double    *val   = nullptr;   // [nnz]     (+ padding) device
+    // row-block plan
+    int        lanes    = 1;      // lanes cooperating on one row (power of two <= 32)
+    int        rows_cap = 256;    // rows per block   (multiple of kThreads / lanes)
+    int        nnz_cap  = 2048;   // staged non-zeros per block
+    int64_t    nblocks  = 0;
+    int64_t    nlong    = 0;      // blocks too long to stage (handled by the strided path)
+    int2      *blk      = nullptr;// [nblocks+1] device: {first row, first nnz} per block
+    size_t     bytes    = 0;
+};
+
+struct b200_coarse_s {
+    b200_ctx_t ctx  = nullptr;
+    int64_t    n    = 0;
+    double    *Ainv = nullptr;    // [n*n] row-major device
+    size_t     bytes = 0;
+};
+
+// ---------------------------------------------------------------------------
+// PTX helpers: mbarrier, TMA 1-D bulk copy, L2 policies
+// ---------------------------------------------------------------------------
+namespace b200 {
+namespace ptx {
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count)
+                 : "memory");
+}
+
+// Make mbarrier initialisation visible to the async (TMA) proxy.
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+// Order generic-proxy accesses to shared memory before subsequent async-proxy ones.
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "B200_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra B200_DONE_%=;\n"
+        "bra B200_WAIT_%=;\n"
+        "B200_DONE_%=:\n"
+        "}\n" ::"r"(smem_addr(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// L2 eviction policy for data streamed exactly once per kernel (matrix values
+// and column indices): evict-first keeps them from displacing the gathered
+// x-vector, which is reused by neighbouring rows and later kernels.
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier.
+// dst and src must be 16-byte aligned and bytes a multiple of 16.  SASS: UBLKCP.
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes,
+                                         uint64_t *bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+        "[%0], [%1], %2, [%3], %4;" ::"r"(smem_addr(dst)),
+        "l"(src), "r"(bytes), "r"(smem_addr(bar)), "l"(policy)
+        : "memory");
+}
+
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes,
+                                         uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes "
+        "[%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
+        "l"(src), "r"(bytes), "r"(smem_addr(bar))
+        : "memory");
+}
+
+// streaming (read-once) 16-byte global load that does not allocate in L1
+__device__ __forceinline__ double2 ld_stream2(const double *p) {
+    double2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];"
+                 : "=d"(r.x), "=d"(r.y)
+                 : "l"(p));
+    return r;
+}
+
+} // namespace ptx
+} // namespace b200

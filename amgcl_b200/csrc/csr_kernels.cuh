@@ -1,0 +1,286 @@
+// csr_kernels.cuh -- the streaming CSR kernels of the V-cycle.
+//
+// One kernel template covers every pass over a CSR operator in the AMGCL solve
+// phase:
+//
+//   MODE_SPMV   y = alpha*A*x (+ beta*y)      backend::spmv      matrix_ops.hpp:47-83
+//   MODE_RESID  y = f - A*x                   backend::residual  matrix_ops.hpp:85-115
+//   MODE_RELAX  y = x + (alpha*d).*(f - A*x)  damped_jacobi / spai0 sweep
+//                                             damped_jacobi.hpp:103-132, spai0.hpp:86-109
+//
+// Data movement.  The matrix is cut (on the host, once, at upload) into row
+// blocks: runs of consecutive rows starting at a multiple of four whose
+// non-zeros fit a shared-memory stage.  A block's slice of `val`, `col` and
+// `ptr` is contiguous in global memory, so one elected thread fetches it with
+// three 1-D TMA bulk copies (cp.async.bulk -> SASS UBLKCP) that complete on an
+// mbarrier; the matrix stream never passes through registers and is tagged
+// L2::evict_first so it does not displace the gathered x-vector.  Rows are
+// then reduced out of shared memory by groups of L lanes (L = 1..32, chosen
+// from the average row length) with a shuffle tree; with L == 1 the summation
+// order is exactly the reference's sequential `sum += a.value()*x[a.col()]`.
+//
+// Two schedulers over the same stage code:
+//   variant 0: one row block per CTA, latency hidden by several CTAs per SM;
+//   variant 1: persistent CTAs walking the block list with an S-deep ring of
+//              stages, so S*CTAs/SM bulk copies are always in flight per SM.
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+enum { MODE_SPMV = 0, MODE_SPMV_ACC = 1, MODE_RESID = 2, MODE_RELAX = 3 };
+
+struct CsrArgs {
+    const int    *ptr;
+    const int    *col;
+    const double *val;
+    const int2   *blk;    // [nblocks+1]: {first row, first non-zero} of each block
+    int           nrows;
+    int           nblocks;
+    int           rows_cap;
+    int           nnz_cap;
+    const double *x;      // gathered vector
+    double       *y;      // output
+    const double *f;      // rhs          (RESID, RELAX)
+    const double *d;      // diagonal     (RELAX)
+    double        alpha;  // SPMV: alpha; RELAX: omega
+    double        beta;   // SPMV_ACC
+};
+
+// ---- shared memory layout of one stage --------------------------------------
+struct StageLayout {
+    int val_off, col_off, ptr_off, bytes;
+};
+__host__ __device__ inline StageLayout stage_layout(int rows_cap, int nnz_cap) {
+    StageLayout s;
+    s.val_off = 0;
+    int val_bytes = (nnz_cap + 2) * 8;             // +2: source aligned down to 16 B
+    val_bytes = (val_bytes + 15) & ~15;
+    s.col_off = s.val_off + val_bytes;
+    int col_bytes = (nnz_cap + 8) * 4;             // +3 align down, +3 round up
+    col_bytes = (col_bytes + 15) & ~15;
+    s.ptr_off = s.col_off + col_bytes;
+    int ptr_bytes = (rows_cap + 4) * 4;
+    ptr_bytes = (ptr_bytes + 15) & ~15;
+    s.bytes = s.ptr_off + ptr_bytes;
+    return s;
+}
+constexpr int kHeaderBytes = 256;   // mbarriers + per-stage block descriptors
+
+struct BlockDesc {      // written by the producer thread, read by everyone after the wait
+    int r0, r1;         // row range
+    int e0, e1;         // non-zero range
+};
+
+// ---- issue the bulk copies of one row block ----------------------------------
+__device__ __forceinline__ BlockDesc load_desc(const CsrArgs &a, int b) {
+    const int2 lo = __ldg(a.blk + b);
+    const int2 hi = __ldg(a.blk + b + 1);
+    BlockDesc d;
+    d.r0 = lo.x; d.e0 = lo.y;
+    d.r1 = hi.x; d.e1 = hi.y;
+    return d;
+}
+
+// Returns true if the block was staged (false: too long, use the strided path).
+__device__ __forceinline__ bool issue_block(const CsrArgs &a, const BlockDesc &d, char *stage,
+                                            const StageLayout &lay, uint64_t *bar,
+                                            uint64_t policy) {
+    const int nnz = d.e1 - d.e0;
+    if (nnz > a.nnz_cap) {
+        // nothing to stage: complete the phase with a plain arrive
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ptx::smem_addr(bar))
+                     : "memory");
+        return false;
+    }
+    const int a0 = d.e0 & ~1;                       // val source aligned to 16 B
+    const int nval = ((d.e1 - a0) + 1) & ~1;
+    const int c0 = d.e0 & ~3;                       // col source aligned to 16 B
+    const int ncol = ((d.e1 - c0) + 3) & ~3;
+    const int nptr = ((d.r1 - d.r0 + 1) + 3) & ~3;  // r0 is a multiple of 4
+    const uint32_t bytes = nval * 8 + ncol * 4 + nptr * 4;
+    ptx::mbar_expect_tx(bar, bytes);
+    if (nval) ptx::bulk_g2s(stage + lay.val_off, a.val + a0, nval * 8, bar, policy);
+    if (ncol) ptx::bulk_g2s(stage + lay.col_off, a.col + c0, ncol * 4, bar, policy);
+    ptx::bulk_g2s(stage + lay.ptr_off, a.ptr + d.r0, nptr * 4, bar, policy);
+    return true;
+}
+
+// ---- per-row epilogue ----------------------------------------------------------
+template <int MODE>
+__device__ __forceinline__ void store_row(const CsrArgs &a, int r, double sum) {
+    if (MODE == MODE_SPMV) {
+        a.y[r] = a.alpha * sum;
+    } else if (MODE == MODE_SPMV_ACC) {
+        a.y[r] = a.alpha * sum + a.beta * a.y[r];
+    } else if (MODE == MODE_RESID) {
+        a.y[r] = a.f[r] - sum;
+    } else {
+        // x_new = (omega*d)*t + x with t = f - A x; same association as the
+        // reference's vmul  z = a*x*y + b*z  (builtin.hpp:1238-1265)
+        const double t = a.f[r] - sum;
+        a.y[r] = fma(a.alpha * a.d[r], t, a.x[r]);
+    }
+}
+
+// ---- reduce the rows of a staged block out of shared memory ---------------------
+template <int MODE, int L>
+__device__ __forceinline__ void compute_staged(const CsrArgs &a, const BlockDesc &d,
+                                               const char *stage, const StageLayout &lay) {
+    const double *val_s = reinterpret_cast<const double *>(stage + lay.val_off);
+    const int    *col_s = reinterpret_cast<const int *>(stage + lay.col_off);
+    const int    *ptr_s = reinterpret_cast<const int *>(stage + lay.ptr_off);
+    const int vo = d.e0 & ~1;
+    const int co = d.e0 & ~3;
+    constexpr int G = kThreads / L;
+    const int g    = threadIdx.x / L;
+    const int lane = threadIdx.x % L;
+    const int nr   = d.r1 - d.r0;
+    const double *__restrict__ x = a.x;
+
+    for (int base = 0; base < nr; base += G) {
+        const int  rr    = base + g;
+        const bool valid = rr < nr;
+        double sum = 0.0;
+        if (valid) {
+            const int beg = ptr_s[rr];
+            const int end = ptr_s[rr + 1];
+            for (int e = beg + lane; e < end; e += 4 * L) {
+                const int  e1 = e + L, e2 = e + 2 * L, e3 = e + 3 * L;
+                const bool p1 = e1 < end, p2 = e2 < end, p3 = e3 < end;
+                const int  c0 = col_s[e - co];
+                const int  c1 = p1 ? col_s[e1 - co] : c0;
+                const int  c2 = p2 ? col_s[e2 - co] : c0;
+                const int  c3 = p3 ? col_s[e3 - co] : c0;
+                const double v0 = val_s[e - vo];
+                const double v1 = p1 ? val_s[e1 - vo] : 0.0;
+                const double v2 = p2 ? val_s[e2 - vo] : 0.0;
+                const double v3 = p3 ? val_s[e3 - vo] : 0.0;
+                const double x0 = __ldg(x + c0);
+                const double x1 = __ldg(x + c1);
+                const double x2 = __ldg(x + c2);
+                const double x3 = __ldg(x + c3);
+                sum = fma(v0, x0, sum);
+                if (p1) sum = fma(v1, x1, sum);
+                if (p2) sum = fma(v2, x2, sum);
+                if (p3) sum = fma(v3, x3, sum);
+            }
+        }
+        if (L > 1) {
+#pragma unroll
+            for (int o = L / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        }
+        if (valid && lane == 0) store_row<MODE>(a, d.r0 + rr, sum);
+    }
+}
+
+// ---- rows too long to stage: whole CTA strides over each row -----------------------
+template <int MODE>
+__device__ __forceinline__ void compute_long(const CsrArgs &a, const BlockDesc &d,
+                                             double *red_s /* >= 8 doubles */) {
+    const double *__restrict__ x = a.x;
+    for (int r = d.r0; r < d.r1; ++r) {
+        const int beg = __ldg(a.ptr + r), end = __ldg(a.ptr + r + 1);
+        double sum = 0.0;
+        for (int e = beg + threadIdx.x; e < end; e += kThreads)
+            sum = fma(__ldg(a.val + e), __ldg(x + __ldg(a.col + e)), sum);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        __syncthreads();                       // red_s free from the previous row
+        if ((threadIdx.x & 31) == 0) red_s[threadIdx.x >> 5] = sum;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double tot = 0.0;
+#pragma unroll
+            for (int w = 0; w < kThreads / 32; ++w) tot += red_s[w];
+            store_row<MODE>(a, r, tot);
+        }
+    }
+}
+
+// ---- variant 0: one row block per CTA -----------------------------------------------
+template <int MODE, int L>
+__global__ void __launch_bounds__(kThreads, 4) csr_block_kernel(const CsrArgs a) {
+    extern __shared__ __align__(128) char smem[];
+    uint64_t *bar   = reinterpret_cast<uint64_t *>(smem);
+    double   *red_s = reinterpret_cast<double *>(smem + 64);
+    char     *stage = smem + kHeaderBytes;
+    const StageLayout lay = stage_layout(a.rows_cap, a.nnz_cap);
+
+    const int b = blockIdx.x;
+    const BlockDesc d = load_desc(a, b);          // broadcast loads, uniform
+    const bool staged = (d.e1 - d.e0) <= a.nnz_cap;
+
+    if (staged) {
+        if (threadIdx.x == 0) {
+            ptx::mbar_init(bar, 1);
+            ptx::fence_mbar_init();
+            issue_block(a, d, stage, lay, bar, ptx::policy_evict_first());
+        }
+        __syncthreads();
+        ptx::mbar_wait(bar, 0);
+        compute_staged<MODE, L>(a, d, stage, lay);
+    } else {
+        compute_long<MODE>(a, d, red_s);
+    }
+}
+
+// ---- variant 1: persistent CTAs, S-deep ring of stages ----------------------------------
+template <int MODE, int L>
+__global__ void __launch_bounds__(kThreads, 2) csr_ring_kernel(const CsrArgs a, const int nstages) {
+    extern __shared__ __align__(128) char smem[];
+    uint64_t  *bars  = reinterpret_cast<uint64_t *>(smem);                 // [<=8]
+    double    *red_s = reinterpret_cast<double *>(smem + 64);              // [8]
+    BlockDesc *descs = reinterpret_cast<BlockDesc *>(smem + 128);          // [<=8]
+    const StageLayout lay = stage_layout(a.rows_cap, a.nnz_cap);
+    char *stages = smem + kHeaderBytes;
+
+    const int first = blockIdx.x;
+    const int step  = gridDim.x;
+    const int mine  = (a.nblocks - first + step - 1) / step;   // blocks this CTA owns
+    uint64_t policy = 0;
+
+    if (threadIdx.x == 0) {
+        policy = ptx::policy_evict_first();
+        for (int s = 0; s < nstages; ++s) ptx::mbar_init(bars + s, 1);
+        ptx::fence_mbar_init();
+        const int pre = mine < nstages ? mine : nstages;
+        for (int i = 0; i < pre; ++i) {
+            const BlockDesc d = load_desc(a, first + i * step);
+            descs[i] = d;
+            issue_block(a, d, stages + (size_t)i * lay.bytes, lay, bars + i, policy);
+        }
+    }
+    __syncthreads();
+
+    int s = 0, parity = 0;
+    for (int i = 0; i < mine; ++i) {
+        ptx::mbar_wait(bars + s, parity);
+        const BlockDesc d = descs[s];
+        if ((d.e1 - d.e0) <= a.nnz_cap)
+            compute_staged<MODE, L>(a, d, stages + (size_t)s * lay.bytes, lay);
+        else
+            compute_long<MODE>(a, d, red_s);
+        __syncthreads();                 // every thread is done with stage s (and descs[s])
+        if (threadIdx.x == 0 && i + nstages < mine) {
+            const BlockDesc n = load_desc(a, first + (i + nstages) * step);
+            descs[s] = n;
+            issue_block(a, n, stages + (size_t)s * lay.bytes, lay, bars + s, policy);
+        }
+        if (++s == nstages) { s = 0; parity ^= 1; }
+    }
+}
+
+// ---- x == 0 shortcut of the smoother sweep: x = (omega*d).*rhs ---------------------------
+__global__ void __launch_bounds__(kThreads) relax_zero_kernel(size_t n, double omega,
+                                                              const double *__restrict__ d,
+                                                              const double *__restrict__ f,
+                                                              double *__restrict__ x) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        // (omega*d)*(f - 0) + 0, written as the reference evaluates it
+        x[i] = fma(omega * d[i], f[i], 0.0);
+    }
+}
+
+} // namespace b200

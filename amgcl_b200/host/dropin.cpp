@@ -1,0 +1,207 @@
+// dropin.cpp -- the drop-in proof: UNMODIFIED amgcl::make_solver / amg / cg /
+// bicgstab (compiled from the reference headers) instantiated on
+// amgcl::backend::b200<double>.  Everything numerical at solve time runs in
+// libamgcl_b200.so; AMGCL contributes the host-side setup (smoothed
+// aggregation coarsening, Galerkin products) and the host control flow of the
+// V-cycle and the Krylov loop, exactly as with its own cuda backend
+// (tutorial/1.poisson3Db/poisson3Db_cuda.cu:51-87).
+//
+// Exposed as a small C API so bench.py / tests can drive it through ctypes.
+// Build: see amgcl_b200/build.py (needs the AMGCL headers on the include path;
+// the resulting .so is self-contained apart from libamgcl_b200.so).
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <sstream>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include <amgcl/backend/b200.hpp>
+#include <amgcl/adapter/crs_tuple.hpp>
+#include <amgcl/make_solver.hpp>
+#include <amgcl/amg.hpp>
+#include <amgcl/coarsening/smoothed_aggregation.hpp>
+#include <amgcl/relaxation/damped_jacobi.hpp>
+#include <amgcl/relaxation/spai0.hpp>
+#include <amgcl/solver/cg.hpp>
+#include <amgcl/solver/bicgstab.hpp>
+
+namespace {
+
+typedef amgcl::backend::b200<double> Backend;
+
+thread_local std::string g_error;
+
+struct SolverBase {
+    virtual ~SolverBase() {}
+    virtual std::tuple<size_t, double> solve(const Backend::vector &f, Backend::vector &x) = 0;
+    virtual void apply_precond(const Backend::vector &f, Backend::vector &x) = 0;
+    virtual std::string report() const = 0;
+    virtual size_t bytes() const = 0;
+};
+
+template <template <class> class Relax, template <class, class> class Krylov>
+struct SolverImpl : SolverBase {
+    typedef amgcl::make_solver<
+        amgcl::amg<Backend, amgcl::coarsening::smoothed_aggregation, Relax>,
+        Krylov<Backend, amgcl::solver::detail::default_inner_product>
+        > Solver;
+
+    std::unique_ptr<Solver> S;
+
+    SolverImpl(size_t n, const int64_t *ptr, const int64_t *col, const double *val,
+               double tol, int maxiter, int coarse_enough, const Backend::params &bprm)
+    {
+        typename Solver::params prm;
+        prm.solver.tol = tol;
+        prm.solver.maxiter = maxiter;
+        if (coarse_enough >= 0) prm.precond.coarse_enough = coarse_enough;
+        auto A = std::make_tuple(
+                n,
+                amgcl::make_iterator_range(ptr, ptr + n + 1),
+                amgcl::make_iterator_range(col, col + ptr[n]),
+                amgcl::make_iterator_range(val, val + ptr[n]));
+        S.reset(new Solver(A, prm, bprm));
+    }
+
+    std::tuple<size_t, double> solve(const Backend::vector &f, Backend::vector &x) override {
+        return (*S)(f, x);
+    }
+    void apply_precond(const Backend::vector &f, Backend::vector &x) override {
+        S->precond().apply(f, x);
+    }
+    std::string report() const override {
+        std::ostringstream os;
+        os << *S;
+        return os.str();
+    }
+    size_t bytes() const override { return amgcl::backend::bytes(*S); }
+};
+
+struct Handle {
+    size_t n;
+    Backend::params bprm;
+    std::unique_ptr<SolverBase> solver;
+    std::shared_ptr<Backend::vector> f, x;
+};
+
+} // namespace
+
+extern "C" {
+
+const char *dropin_last_error() { return g_error.c_str(); }
+
+// relax: 0 = damped_jacobi, 1 = spai0 ; krylov: 0 = cg, 1 = bicgstab
+// ctx: a b200_ctx_t or NULL for the library default
+int dropin_create(void *ctx, int64_t n, const int64_t *ptr, const int64_t *col, const double *val,
+                  int relax, int krylov, double tol, int maxiter, int coarse_enough, void **out)
+{
+    try {
+        std::unique_ptr<Handle> h(new Handle());
+        h->n = (size_t)n;
+        h->bprm = Backend::params(static_cast<b200_ctx_t>(ctx));
+        using namespace amgcl;
+        if (relax == 0 && krylov == 0)
+            h->solver.reset(new SolverImpl<relaxation::damped_jacobi, solver::cg>(n, ptr, col, val, tol, maxiter, coarse_enough, h->bprm));
+        else if (relax == 0 && krylov == 1)
+            h->solver.reset(new SolverImpl<relaxation::damped_jacobi, solver::bicgstab>(n, ptr, col, val, tol, maxiter, coarse_enough, h->bprm));
+        else if (relax == 1 && krylov == 0)
+            h->solver.reset(new SolverImpl<relaxation::spai0, solver::cg>(n, ptr, col, val, tol, maxiter, coarse_enough, h->bprm));
+        else if (relax == 1 && krylov == 1)
+            h->solver.reset(new SolverImpl<relaxation::spai0, solver::bicgstab>(n, ptr, col, val, tol, maxiter, coarse_enough, h->bprm));
+        else {
+            g_error = "unknown relax/krylov selector";
+            return -1;
+        }
+        h->f = Backend::create_vector(n, h->bprm);
+        h->x = Backend::create_vector(n, h->bprm);
+        *out = h.release();
+        return 0;
+    } catch (const std::exception &e) {
+        g_error = e.what();
+        return -1;
+    }
+}
+
+void dropin_destroy(void *handle) { delete static_cast<Handle *>(handle); }
+
+// End-to-end call with HOST buffers: H2D(rhs), solve from x0 = x_host (in/out), D2H(x).
+int dropin_solve(void *handle, const double *rhs_host, double *x_host, int64_t *iters, double *resid)
+{
+    Handle *h = static_cast<Handle *>(handle);
+    try {
+        h->f->upload(rhs_host);
+        h->x->upload(x_host);
+        size_t it; double r;
+        std::tie(it, r) = h->solver->solve(*h->f, *h->x);
+        h->x->download(x_host);
+        *iters = (int64_t)it; *resid = r;
+        return 0;
+    } catch (const std::exception &e) {
+        g_error = e.what();
+        return -1;
+    }
+}
+
+// Device-resident variant: rhs uploaded beforehand, x0 = 0, x stays on the device.
+int dropin_upload_rhs(void *handle, const double *rhs_host)
+{
+    Handle *h = static_cast<Handle *>(handle);
+    try { h->f->upload(rhs_host); return 0; }
+    catch (const std::exception &e) { g_error = e.what(); return -1; }
+}
+
+int dropin_solve_resident(void *handle, int64_t *iters, double *resid)
+{
+    Handle *h = static_cast<Handle *>(handle);
+    try {
+        amgcl::backend::clear(*h->x);
+        size_t it; double r;
+        std::tie(it, r) = h->solver->solve(*h->f, *h->x);
+        *iters = (int64_t)it; *resid = r;
+        return 0;
+    } catch (const std::exception &e) {
+        g_error = e.what();
+        return -1;
+    }
+}
+
+int dropin_download_x(void *handle, double *x_host)
+{
+    Handle *h = static_cast<Handle *>(handle);
+    try { h->x->download(x_host); return 0; }
+    catch (const std::exception &e) { g_error = e.what(); return -1; }
+}
+
+// One application of the AMG preconditioner x = M^-1 f (a single V-cycle), host buffers.
+int dropin_apply_precond(void *handle, const double *f_host, double *x_host)
+{
+    Handle *h = static_cast<Handle *>(handle);
+    try {
+        h->f->upload(f_host);
+        h->solver->apply_precond(*h->f, *h->x);
+        h->x->download(x_host);
+        return 0;
+    } catch (const std::exception &e) {
+        g_error = e.what();
+        return -1;
+    }
+}
+
+// Text report of solver + hierarchy (amg.hpp:561-598).  Returns the needed size.
+int64_t dropin_report(void *handle, char *buf, int64_t size)
+{
+    Handle *h = static_cast<Handle *>(handle);
+    const std::string s = h->solver->report();
+    if (buf && size > 0) {
+        const size_t m = std::min<size_t>(s.size(), (size_t)size - 1);
+        memcpy(buf, s.data(), m);
+        buf[m] = 0;
+    }
+    return (int64_t)s.size() + 1;
+}
+
+int64_t dropin_bytes(void *handle) { return (int64_t)static_cast<Handle *>(handle)->solver->bytes(); }
+
+} // extern "C"

@@ -1,0 +1,544 @@
+#ifndef AMGCL_BACKEND_B200_HPP
+#define AMGCL_BACKEND_B200_HPP
+
+/**
+ * \file   amgcl/backend/b200.hpp
+ * \brief  B200-native solve-phase backend for AMGCL (drop-in for backend::cuda).
+ *
+ * Usage is identical to the reference CUDA backend
+ * (tutorial/1.poisson3Db/poisson3Db_cuda.cu:51-87):
+ *
+ * \code
+ *   typedef amgcl::backend::b200<double> Backend;
+ *   typedef amgcl::make_solver<
+ *       amgcl::amg<Backend, amgcl::coarsening::smoothed_aggregation,
+ *                  amgcl::relaxation::damped_jacobi>,   // or spai0
+ *       amgcl::solver::cg<Backend>                      // or bicgstab
+ *       > Solver;
+ *   Backend::params bprm;                 // default: library context on the current device
+ *   Solver solve(std::tie(n, ptr, col, val), prm, bprm);
+ *   auto f = Backend::copy_vector(rhs, bprm);
+ *   auto x = Backend::create_vector(n, bprm);
+ *   std::tie(iters, error) = solve(*f, *x);
+ * \endcode
+ *
+ * The header owns no numerical code: every primitive forwards to the C ABI of
+ * libamgcl_b200.so (include/amgcl_b200.h), whose kernels are hand-written
+ * sm_100a CUDA.  It implements the concept amgcl/backend/cuda.hpp:472-807
+ * satisfies: a backend struct plus partial specialisations of the *_impl
+ * customisation points of amgcl/backend/interface.hpp:191-249.  In addition
+ * relaxation::damped_jacobi and relaxation::spai0 are specialised for this
+ * backend so a smoother sweep is ONE fused pass over A instead of
+ * residual + vmul (damped_jacobi.hpp:108-109, spai0.hpp:91-92).
+ */
+
+#include <memory>
+#include <string>
+#include <vector>
+#include <type_traits>
+
+#include <amgcl/util.hpp>
+#include <amgcl/backend/builtin.hpp>
+#include <amgcl/backend/interface.hpp>
+#include <amgcl/relaxation/damped_jacobi.hpp>
+#include <amgcl/relaxation/spai0.hpp>
+
+#include <amgcl_b200.h>
+
+namespace amgcl {
+namespace backend {
+
+namespace detail {
+/// Turns a non-zero C ABI status into the reference's error convention
+/// (precondition() -> std::runtime_error, util.hpp:89-99; cf. AMGCL_CALL_CUDA,
+/// cuda.hpp:91-108).
+inline void b200_check(int rc, const char *what) {
+    if (rc != B200_OK) {
+        std::string msg = std::string("b200 backend: ") + what + " failed (" +
+            std::to_string(rc) + "): " + b200_last_error();
+        precondition(false, msg);
+    }
+}
+#define AMGCL_CALL_B200(call) ::amgcl::backend::detail::b200_check(call, #call)
+
+inline b200_ctx_t b200_default_ctx() {
+    b200_ctx_t ctx = 0;
+    AMGCL_CALL_B200(b200_ctx_default(&ctx));
+    return ctx;
+}
+} // namespace detail
+
+/// Parameters of the b200 backend: the library context (device + stream).
+/// Plays the role of cuda<>::params::cusparse_handle (cuda.hpp:490-507).
+struct b200_params {
+    b200_ctx_t ctx;
+    b200_params(b200_ctx_t ctx = 0) : ctx(ctx) {}
+    b200_ctx_t context() const { return ctx ? ctx : detail::b200_default_ctx(); }
+};
+
+/// Device vector (replaces thrust::device_vector<real>, cuda.hpp:483).
+template <typename real>
+class b200_vector {
+    static_assert(std::is_same<real, double>::value, "b200 backend is FP64");
+    public:
+        typedef real value_type;
+
+        b200_vector() : ctx(0), h(0), n(0) {}
+
+        b200_vector(size_t n, const b200_params &prm = b200_params())
+            : ctx(prm.context()), h(0), n(n)
+        {
+            AMGCL_CALL_B200(b200_vec_create(ctx, n, &h));
+        }
+
+        b200_vector(const real *host, size_t n, const b200_params &prm = b200_params())
+            : ctx(prm.context()), h(0), n(n)
+        {
+            AMGCL_CALL_B200(b200_vec_create(ctx, n, &h));
+            AMGCL_CALL_B200(b200_vec_upload(h, host, n));
+        }
+
+        template <class Vector>
+        b200_vector(const Vector &host, const b200_params &prm = b200_params(),
+                typename std::enable_if<!std::is_integral<Vector>::value, int>::type = 0)
+            : ctx(prm.context()), h(0), n(host.size())
+        {
+            AMGCL_CALL_B200(b200_vec_create(ctx, n, &h));
+            AMGCL_CALL_B200(b200_vec_upload(h, host.data(), n));
+        }
+
+        b200_vector(const b200_vector&) = delete;
+        b200_vector& operator=(const b200_vector&) = delete;
+
+        b200_vector(b200_vector &&o) : ctx(o.ctx), h(o.h), n(o.n) { o.h = 0; o.n = 0; }
+
+        ~b200_vector() { if (h) b200_vec_destroy(h); }
+
+        size_t size() const { return n; }
+        size_t bytes() const { return n * sizeof(real); }
+        b200_vec_t handle() const { return h; }
+        b200_ctx_t context() const { return ctx; }
+
+        /// Copy to a host container (resized by the caller).
+        void download(real *host) const { AMGCL_CALL_B200(b200_vec_download(h, host, n)); }
+        void upload(const real *host)   { AMGCL_CALL_B200(b200_vec_upload(h, host, n)); }
+
+    private:
+        b200_ctx_t ctx;
+        b200_vec_t h;
+        size_t     n;
+};
+
+/// Device CSR matrix (replaces cuda_matrix<real>, cuda.hpp:219-333).
+template <typename real>
+class b200_matrix {
+    static_assert(std::is_same<real, double>::value, "b200 backend is FP64");
+    public:
+        typedef real value_type;
+
+        template <class Col, class Ptr>
+        b200_matrix(const crs<real, Col, Ptr> &A, const b200_params &prm)
+            : ctx(prm.context()), h(0), nrows(A.nrows), ncols(A.ncols), nnz(A.nnz)
+        {
+            create(A.nrows, A.ncols, A.ptr, A.col, A.val);
+        }
+
+        b200_matrix(const b200_matrix&) = delete;
+        b200_matrix& operator=(const b200_matrix&) = delete;
+
+        ~b200_matrix() { if (h) b200_csr_destroy(h); }
+
+        size_t rows()     const { return nrows; }
+        size_t cols()     const { return ncols; }
+        size_t nonzeros() const { return nnz;   }
+        size_t bytes()    const { size_t b = 0; b200_csr_bytes(h, &b); return b; }
+        b200_csr_t handle()  const { return h; }
+        b200_ctx_t context() const { return ctx; }
+
+    private:
+        b200_ctx_t ctx;
+        b200_csr_t h;
+        size_t nrows, ncols, nnz;
+
+        void create(size_t n, size_t m, const int64_t *ptr, const int64_t *col, const real *val) {
+            AMGCL_CALL_B200(b200_csr_create_i64(ctx, n, m, ptr, col, val, &h));
+        }
+        void create(size_t n, size_t m, const int32_t *ptr, const int32_t *col, const real *val) {
+            AMGCL_CALL_B200(b200_csr_create_i32(ctx, n, m, ptr, col, val, &h));
+        }
+        // long / long long differ from int64_t on some ABIs: same width, reinterpret
+        template <class I>
+        typename std::enable_if<
+            sizeof(I) == 8 && !std::is_same<I, int64_t>::value, void>::type
+        create(size_t n, size_t m, const I *ptr, const I *col, const real *val) {
+            create(n, m, reinterpret_cast<const int64_t*>(ptr),
+                    reinterpret_cast<const int64_t*>(col), val);
+        }
+};
+
+} // namespace backend
+
+namespace solver {
+
+/// Coarsest-level direct solver that stays on the device (replaces
+/// solver::cuda_skyline_lu, cuda.hpp:61-84, which round-trips through the host
+/// every cycle): dense inverse formed once, applied as a GEMV.
+template <typename real>
+class b200_dense_inverse {
+    public:
+        typedef real value_type;
+
+        template <class Col, class Ptr>
+        b200_dense_inverse(const backend::crs<real, Col, Ptr> &A, const backend::b200_params &prm)
+            : ctx(prm.context()), h(0), n(A.nrows)
+        {
+            create(A.ptr, A.col, A.val);
+        }
+
+        b200_dense_inverse(const b200_dense_inverse&) = delete;
+        b200_dense_inverse& operator=(const b200_dense_inverse&) = delete;
+        ~b200_dense_inverse() { if (h) b200_coarse_destroy(h); }
+
+        /// Same threshold as solver::skyline_lu (skyline_lu.hpp:93-95), so the
+        /// hierarchy has exactly the levels the builtin backend would build.
+        static size_t coarse_enough() { return 3000; }
+
+        void operator()(const backend::b200_vector<real> &rhs, backend::b200_vector<real> &x) const {
+            AMGCL_CALL_B200(b200_coarse_solve(ctx, h, rhs.handle(), x.handle()));
+        }
+
+        size_t bytes() const { size_t b = 0; b200_coarse_bytes(h, &b); return b; }
+
+    private:
+        b200_ctx_t    ctx;
+        b200_coarse_t h;
+        size_t        n;
+
+        void create(const int64_t *ptr, const int64_t *col, const real *val) {
+            AMGCL_CALL_B200(b200_coarse_create_i64(ctx, n, ptr, col, val, &h));
+        }
+        void create(const int32_t *ptr, const int32_t *col, const real *val) {
+            AMGCL_CALL_B200(b200_coarse_create_i32(ctx, n, ptr, col, val, &h));
+        }
+        template <class I>
+        typename std::enable_if<
+            sizeof(I) == 8 && !std::is_same<I, int64_t>::value, void>::type
+        create(const I *ptr, const I *col, const real *val) {
+            create(reinterpret_cast<const int64_t*>(ptr), reinterpret_cast<const int64_t*>(col), val);
+        }
+};
+
+} // namespace solver
+
+namespace backend {
+
+/// B200 backend.
+/**
+ * Hand-written sm_100a kernels for every solve-phase primitive; the hierarchy
+ * is built on the host by AMGCL's own coarsening and uploaded once.
+ *
+ * \param real        Value type (double).
+ * \param ColumnType  Host column index type used during setup (ptrdiff_t as in
+ *                    backend::cuda, cuda.hpp:480-481; int halves setup memory).
+ */
+template <
+    typename real,
+    typename ColumnType  = ptrdiff_t,
+    typename PointerType = ColumnType,
+    class DirectSolver   = solver::b200_dense_inverse<real>
+    >
+struct b200 {
+    static_assert(std::is_same<real, double>::value,
+            "Unsupported value type for b200 backend (FP64 only)");
+
+    typedef real        value_type;
+    typedef ColumnType  col_type;
+    typedef PointerType ptr_type;
+
+    typedef b200_matrix<real> matrix;
+    typedef b200_vector<real> vector;
+    typedef b200_vector<real> matrix_diagonal;
+    typedef DirectSolver      direct_solver;
+
+    struct provides_row_iterator : std::false_type {};
+
+    typedef b200_params params;
+
+    static std::string name() { return "b200"; }
+
+    typedef typename builtin<real, col_type, ptr_type>::matrix host_matrix;
+
+    /// Copy matrix from builtin backend (deep copy; cf. cuda.hpp:512-518).
+    static std::shared_ptr<matrix>
+    copy_matrix(std::shared_ptr<host_matrix> A, const params &prm)
+    {
+        return std::make_shared<matrix>(*A, prm);
+    }
+
+    /// Copy vector from builtin backend (cf. cuda.hpp:521-533).
+    static std::shared_ptr<vector>
+    copy_vector(const numa_vector<real> &x, const params &prm)
+    {
+        return std::make_shared<vector>(x.data(), x.size(), prm);
+    }
+
+    static std::shared_ptr<vector>
+    copy_vector(const std::vector<real> &x, const params &prm)
+    {
+        return std::make_shared<vector>(x.data(), x.size(), prm);
+    }
+
+    static std::shared_ptr<vector>
+    copy_vector(std::shared_ptr< numa_vector<real> > x, const params &prm)
+    {
+        return copy_vector(*x, prm);
+    }
+
+    /// Create vector of the specified size (zero filled; cf. cuda.hpp:536-540).
+    static std::shared_ptr<vector>
+    create_vector(size_t size, const params &prm)
+    {
+        return std::make_shared<vector>(size, prm);
+    }
+
+    /// Create direct solver for coarse level (cf. cuda.hpp:543-547).
+    static std::shared_ptr<direct_solver>
+    create_solver(std::shared_ptr<host_matrix> A, const params &prm)
+    {
+        return std::make_shared<direct_solver>(*A, prm);
+    }
+};
+
+//---------------------------------------------------------------------------
+// Backend interface implementation
+//---------------------------------------------------------------------------
+template <typename V>
+struct bytes_impl< b200_vector<V> > {
+    static size_t get(const b200_vector<V> &v) { return v.bytes(); }
+};
+
+template <typename Alpha, typename Beta, typename V>
+struct spmv_impl<Alpha, b200_matrix<V>, b200_vector<V>, Beta, b200_vector<V> >
+{
+    static void apply(Alpha alpha, const b200_matrix<V> &A, const b200_vector<V> &x,
+            Beta beta, b200_vector<V> &y)
+    {
+        AMGCL_CALL_B200(b200_spmv(A.context(), static_cast<double>(alpha), A.handle(),
+                    x.handle(), static_cast<double>(beta), y.handle()));
+    }
+};
+
+template <typename V>
+struct residual_impl<b200_matrix<V>, b200_vector<V>, b200_vector<V>, b200_vector<V> >
+{
+    static void apply(const b200_vector<V> &rhs, const b200_matrix<V> &A,
+            const b200_vector<V> &x, b200_vector<V> &r)
+    {
+        AMGCL_CALL_B200(b200_residual(A.context(), rhs.handle(), A.handle(), x.handle(), r.handle()));
+    }
+};
+
+template <typename V>
+struct clear_impl< b200_vector<V> >
+{
+    static void apply(b200_vector<V> &x) {
+        AMGCL_CALL_B200(b200_clear(x.context(), x.handle()));
+    }
+};
+
+template <typename V>
+struct copy_impl<b200_vector<V>, b200_vector<V> >
+{
+    static void apply(const b200_vector<V> &x, b200_vector<V> &y) {
+        AMGCL_CALL_B200(b200_copy(x.context(), x.handle(), y.handle()));
+    }
+};
+
+/// host -> device
+template <class HostVec, typename V>
+struct copy_impl<HostVec, b200_vector<V>,
+    typename std::enable_if<is_builtin_vector<HostVec>::value>::type >
+{
+    static void apply(const HostVec &x, b200_vector<V> &y) {
+        precondition(x.size() == y.size(), "b200 copy: size mismatch");
+        y.upload(x.data());
+    }
+};
+
+/// device -> host
+template <typename V, class HostVec>
+struct copy_impl<b200_vector<V>, HostVec,
+    typename std::enable_if<is_builtin_vector<HostVec>::value>::type >
+{
+    static void apply(const b200_vector<V> &x, HostVec &y) {
+        precondition(x.size() == y.size(), "b200 copy: size mismatch");
+        x.download(y.data());
+    }
+};
+
+template <typename V>
+struct inner_product_impl<b200_vector<V>, b200_vector<V> >
+{
+    static V get(const b200_vector<V> &x, const b200_vector<V> &y) {
+        double r = 0;
+        AMGCL_CALL_B200(b200_dot(x.context(), x.handle(), y.handle(), &r));
+        return r;
+    }
+};
+
+template <typename A, typename B, typename V>
+struct axpby_impl<A, b200_vector<V>, B, b200_vector<V> >
+{
+    static void apply(A a, const b200_vector<V> &x, B b, b200_vector<V> &y) {
+        AMGCL_CALL_B200(b200_axpby(x.context(), static_cast<double>(a), x.handle(),
+                    static_cast<double>(b), y.handle()));
+    }
+};
+
+template <typename A, typename B, typename C, typename V>
+struct axpbypcz_impl<A, b200_vector<V>, B, b200_vector<V>, C, b200_vector<V> >
+{
+    static void apply(A a, const b200_vector<V> &x, B b, const b200_vector<V> &y,
+            C c, b200_vector<V> &z)
+    {
+        AMGCL_CALL_B200(b200_axpbypcz(x.context(), static_cast<double>(a), x.handle(),
+                    static_cast<double>(b), y.handle(), static_cast<double>(c), z.handle()));
+    }
+};
+
+template <typename A, typename B, typename V>
+struct vmul_impl<A, b200_vector<V>, b200_vector<V>, B, b200_vector<V> >
+{
+    static void apply(A a, const b200_vector<V> &x, const b200_vector<V> &y,
+            B b, b200_vector<V> &z)
+    {
+        AMGCL_CALL_B200(b200_vmul(x.context(), static_cast<double>(a), x.handle(), y.handle(),
+                    static_cast<double>(b), z.handle()));
+    }
+};
+
+} // namespace backend
+
+//---------------------------------------------------------------------------
+// Fused smoothers: same public API as the primary templates, one pass over A.
+//---------------------------------------------------------------------------
+namespace relaxation {
+
+/// damped_jacobi for the b200 backend (primary: relaxation/damped_jacobi.hpp:54-138)
+template <typename real, typename C, typename P, class DS>
+struct damped_jacobi< backend::b200<real, C, P, DS> > {
+    typedef backend::b200<real, C, P, DS>              Backend;
+    typedef typename Backend::value_type               value_type;
+    typedef typename math::scalar_of<value_type>::type scalar_type;
+
+    /// Relaxation parameters (identical to the primary template's).
+    struct params {
+        scalar_type damping;
+        params(scalar_type damping = 0.72) : damping(damping) {}
+
+#ifndef AMGCL_NO_BOOST
+        params(const boost::property_tree::ptree &p)
+            : AMGCL_PARAMS_IMPORT_VALUE(p, damping)
+        {
+            check_params(p, {"damping"});
+        }
+        void get(boost::property_tree::ptree &p, const std::string &path) const {
+            AMGCL_PARAMS_EXPORT_VALUE(p, path, damping);
+        }
+#endif
+    } prm;
+
+    std::shared_ptr<typename Backend::matrix_diagonal> dia;
+
+    template <class Matrix>
+    damped_jacobi(const Matrix &A, const params &prm,
+            const typename Backend::params &backend_prm)
+        : prm(prm), dia( Backend::copy_vector( diagonal(A, true), backend_prm ) )
+    { }
+
+    // x <- x + damping * D^-1 (rhs - A x), fused
+    void apply_pre(const typename Backend::matrix &A, const typename Backend::vector &rhs,
+            typename Backend::vector &x, typename Backend::vector &tmp) const
+    {
+        AMGCL_CALL_B200(b200_relax(A.context(), A.handle(), rhs.handle(), x.handle(),
+                    tmp.handle(), dia->handle(), prm.damping));
+    }
+
+    void apply_post(const typename Backend::matrix &A, const typename Backend::vector &rhs,
+            typename Backend::vector &x, typename Backend::vector &tmp) const
+    {
+        apply_pre(A, rhs, x, tmp);
+    }
+
+    template <class Matrix, class VectorRHS, class VectorX>
+    void apply(const Matrix&, const VectorRHS &rhs, VectorX &x) const
+    {
+        backend::vmul(math::identity<scalar_type>(), *dia, rhs, math::zero<scalar_type>(), x);
+    }
+
+    size_t bytes() const { return backend::bytes(*dia); }
+};
+
+/// spai0 for the b200 backend (primary: relaxation/spai0.hpp:50-117)
+template <typename real, typename C, typename P, class DS>
+struct spai0< backend::b200<real, C, P, DS> > {
+    typedef backend::b200<real, C, P, DS>              Backend;
+    typedef typename Backend::value_type               value_type;
+    typedef typename Backend::matrix_diagonal          matrix_diagonal;
+    typedef typename math::scalar_of<value_type>::type scalar_type;
+    typedef amgcl::detail::empty_params params;
+
+    /// SPAI-0 weights M_i = a_ii / sum_j a_ij^2 (same quantity the primary
+    /// template computes at spai0.hpp:60-82), evaluated here straight off the
+    /// raw CRS arrays of the host build matrix and uploaded once.
+    template <class HostCol, class HostPtr>
+    spai0(const backend::crs<value_type, HostCol, HostPtr> &A, const params &,
+            const typename Backend::params &backend_prm)
+    {
+        const ptrdiff_t n = static_cast<ptrdiff_t>(A.nrows);
+        std::vector<value_type> w(A.nrows);
+
+#pragma omp parallel for
+        for(ptrdiff_t row = 0; row < n; ++row) {
+            scalar_type sum_sq = 0;
+            value_type  on_diag = 0;
+            for(HostPtr e = A.ptr[row], stop = A.ptr[row + 1]; e < stop; ++e) {
+                const value_type a_ij = A.val[e];
+                sum_sq += a_ij * a_ij;
+                if (static_cast<ptrdiff_t>(A.col[e]) == row) on_diag += a_ij;
+            }
+            w[row] = (scalar_type(1) / sum_sq) * on_diag;
+        }
+
+        M = Backend::copy_vector(w, backend_prm);
+    }
+
+    // x <- x + M (rhs - A x), fused
+    void apply_pre(const typename Backend::matrix &A, const typename Backend::vector &rhs,
+            typename Backend::vector &x, typename Backend::vector &tmp) const
+    {
+        AMGCL_CALL_B200(b200_relax(A.context(), A.handle(), rhs.handle(), x.handle(),
+                    tmp.handle(), M->handle(), 1.0));
+    }
+
+    void apply_post(const typename Backend::matrix &A, const typename Backend::vector &rhs,
+            typename Backend::vector &x, typename Backend::vector &tmp) const
+    {
+        apply_pre(A, rhs, x, tmp);
+    }
+
+    template <class Matrix, class VectorRHS, class VectorX>
+    void apply(const Matrix&, const VectorRHS &rhs, VectorX &x) const
+    {
+        backend::vmul(math::identity<scalar_type>(), *M, rhs, math::zero<scalar_type>(), x);
+    }
+
+    size_t bytes() const { return backend::bytes(*M); }
+
+    std::shared_ptr<matrix_diagonal> M;
+};
+
+} // namespace relaxation
+} // namespace amgcl
+
+#endif

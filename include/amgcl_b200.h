@@ -1,0 +1,198 @@
+/*
+ * amgcl_b200.h -- C ABI of the B200-native solve-phase backend for AMGCL.
+ *
+ * This is the drop-in boundary.  Everything the AMGCL
+ * solve phase asks of a backend -- amgcl::backend::{spmv, residual, vmul,
+ * axpby, axpbypcz, inner_product, copy, clear} (reference:
+ * amgcl/backend/interface.hpp:312-405), the damped_jacobi / spai0 smoother
+ * sweeps (amgcl/relaxation/damped_jacobi.hpp:103-132, spai0.hpp:86-109) and
+ * the coarsest-level direct solve (amgcl/amg.hpp:521-524,
+ * amgcl/backend/cuda.hpp:61-84) -- is exported here as plain `extern "C"`
+ * functions over opaque handles, plain pointers and sizes.  No C++ or torch
+ * types cross this boundary.  The C++ header include/amgcl/backend/b200.hpp
+ * binds these symbols to the amgcl::backend template interface.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative B200_E* code otherwise;
+ *     b200_last_error() returns a thread-local, human readable message.
+ *   - all device work is issued on the context's stream (b200_ctx_set_stream)
+ *     and is asynchronous unless stated otherwise.
+ *   - values are FP64, device indices are int32 (nnz < 2^31 per matrix);
+ *     host CSR input may be int64 (ptrdiff_t, amgcl's default) or int32.
+ *   - there is NO CPU fallback: if no CUDA device is usable every call fails.
+ */
+#ifndef AMGCL_B200_H
+#define AMGCL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_OK            0
+#define B200_EINVAL       -1   /* bad argument (null handle, size mismatch ...)   */
+#define B200_ECUDA        -2   /* CUDA runtime error; see b200_last_error()      */
+#define B200_ENOMEM       -3   /* host or device allocation failed               */
+#define B200_ERANGE       -4   /* nnz or dimension does not fit int32            */
+#define B200_ESINGULAR    -5   /* coarse matrix is numerically singular          */
+#define B200_ENCCL        -6   /* NCCL error                                     */
+
+typedef struct b200_ctx_s    *b200_ctx_t;     /* device + stream + scratch            */
+typedef struct b200_csr_s    *b200_csr_t;     /* device CSR matrix (+ row-block plan) */
+typedef struct b200_vec_s    *b200_vec_t;     /* device FP64 vector                   */
+typedef struct b200_coarse_s *b200_coarse_t;  /* coarsest-level direct solver         */
+
+/* ---------------------------------------------------------------- context */
+
+/* Thread-local message describing the last failing call. */
+const char *b200_last_error(void);
+
+/* Library version string ("amgcl_b200 <semver> sm_100a"). */
+const char *b200_version(void);
+
+/* Number of usable CUDA devices (0 if none: every other call will fail). */
+int b200_device_count(void);
+
+/* Create a context on CUDA device `device` (replaces the cusparseHandle_t that
+ * amgcl::backend::cuda<>::params carries, amgcl/backend/cuda.hpp:490-507). */
+int b200_ctx_create(int device, b200_ctx_t *ctx);
+int b200_ctx_destroy(b200_ctx_t ctx);
+
+/* Process-wide default context on the current device (lazily created).  Used
+ * by the C++ shim when Backend::params is default constructed. */
+int b200_ctx_default(b200_ctx_t *ctx);
+
+/* Use an externally owned cudaStream_t (e.g. torch's current stream) for all
+ * subsequent work; NULL selects the context's own stream again. */
+int b200_ctx_set_stream(b200_ctx_t ctx, void *cuda_stream);
+int b200_ctx_get_stream(b200_ctx_t ctx, void **cuda_stream);
+int b200_ctx_device(b200_ctx_t ctx, int *device);
+
+/* Block the host until all work issued on the context's stream is done. */
+int b200_ctx_sync(b200_ctx_t ctx);
+
+/* Number of kernels launched through this context since creation / reset. */
+int b200_ctx_launch_count(b200_ctx_t ctx, uint64_t *count);
+int b200_ctx_reset_launch_count(b200_ctx_t ctx);
+
+/* Tuning knobs (all optional; defaults are chosen for B200).
+ *   "spmv_variant"     0 = one row block per CTA, 1 = persistent multi-stage
+ *   "fuse_relax"       1 = single-pass fused smoother sweep (default), 0 = two kernels
+ *   "zero_shortcut"    1 = skip the A-pass when x is known to be zero (default)
+ * Unknown keys return B200_EINVAL. */
+int b200_ctx_set_option(b200_ctx_t ctx, const char *key, int64_t value);
+int b200_ctx_get_option(b200_ctx_t ctx, const char *key, int64_t *value);
+
+/* ---------------------------------------------------------------- vectors */
+
+/* Replaces thrust::device_vector<double> (amgcl/backend/cuda.hpp:483-484) and
+ * Backend::create_vector / copy_vector (cuda.hpp:521-546). */
+int b200_vec_create(b200_ctx_t ctx, size_t n, b200_vec_t *v);        /* zero filled */
+int b200_vec_wrap(b200_ctx_t ctx, double *device_ptr, size_t n, b200_vec_t *v);
+int b200_vec_destroy(b200_vec_t v);
+int b200_vec_size(b200_vec_t v, size_t *n);
+int b200_vec_bytes(b200_vec_t v, size_t *bytes);
+/* Raw device pointer (materialises a pending lazy clear).  The pointer is
+ * invalidated by b200_relax(), which may swap storage between x and tmp. */
+int b200_vec_data(b200_vec_t v, double **device_ptr);
+/* Host <-> device copies, ordered on the context's stream; both block the host
+ * until the copy has completed (same semantics as thrust::copy, cuda.hpp:635-660). */
+int b200_vec_upload(b200_vec_t v, const double *host, size_t n);
+int b200_vec_download(b200_vec_t v, double *host, size_t n);
+
+/* ---------------------------------------------------------------- matrices */
+
+/* Upload a host CSR matrix (deep copy), narrowing indices to int32 and building
+ * the row-block plan used by the streaming kernels.  Replaces
+ * cuda_matrix<double>'s constructor (amgcl/backend/cuda.hpp:219-237,310-333)
+ * as called from Backend::copy_matrix (cuda.hpp:512-518). */
+int b200_csr_create_i64(b200_ctx_t ctx, int64_t nrows, int64_t ncols,
+                        const int64_t *ptr, const int64_t *col, const double *val,
+                        b200_csr_t *A);
+int b200_csr_create_i32(b200_ctx_t ctx, int64_t nrows, int64_t ncols,
+                        const int32_t *ptr, const int32_t *col, const double *val,
+                        b200_csr_t *A);
+int b200_csr_destroy(b200_csr_t A);
+int b200_csr_rows(b200_csr_t A, size_t *n);
+int b200_csr_cols(b200_csr_t A, size_t *n);
+int b200_csr_nonzeros(b200_csr_t A, size_t *n);
+int b200_csr_bytes(b200_csr_t A, size_t *bytes);
+/* Plan introspection for tests / DESIGN.md: lanes per row and row-block count. */
+int b200_csr_plan(b200_csr_t A, int *lanes_per_row, int64_t *n_blocks, int64_t *n_long_blocks);
+
+/* Pure host helper (no device needed): the row-block plan b200_csr_create_*
+ * would build for a matrix with these row pointers.  blk_out (may be NULL)
+ * receives nblocks+1 pairs {first row, first non-zero}; blk_capacity is its
+ * size in pairs.  lanes = 0 selects lanes-per-row from the average row length. */
+int b200_plan_i64(int64_t nrows, const int64_t *ptr, int lanes, int nnz_cap,
+                  int32_t *blk_out, int64_t blk_capacity, int64_t *nblocks,
+                  int *lanes_out, int *rows_cap_out, int64_t *nlong_out);
+
+/* ---------------------------------------------------------------- primitives */
+
+/* y = alpha*A*x + beta*y.  y is never read when beta == 0.
+ * (interface.hpp:312-323, builtin: backend/detail/matrix_ops.hpp:47-83) */
+int b200_spmv(b200_ctx_t ctx, double alpha, b200_csr_t A, b200_vec_t x,
+              double beta, b200_vec_t y);
+
+/* r = f - A*x, one kernel (interface.hpp:329-335, matrix_ops.hpp:85-115;
+ * the reference cuda backend needs copy + spmv, cuda.hpp:605-622). */
+int b200_residual(b200_ctx_t ctx, b200_vec_t f, b200_csr_t A, b200_vec_t x,
+                  b200_vec_t r);
+
+/* x = 0 (interface.hpp:338-344).  Lazy: marks x as zero; the memset is only
+ * issued if something later reads x element-wise. */
+int b200_clear(b200_ctx_t ctx, b200_vec_t x);
+
+/* y = x (interface.hpp:347-353). */
+int b200_copy(b200_ctx_t ctx, b200_vec_t x, b200_vec_t y);
+
+/* *result = sum_i x_i*y_i, compensated, deterministic summation order,
+ * synchronous (interface.hpp:356-371; builtin Kahan: builtin.hpp:1099-1183). */
+int b200_dot(b200_ctx_t ctx, b200_vec_t x, b200_vec_t y, double *result);
+
+/* y = a*x + b*y; y not read when b == 0 (interface.hpp:377-382, builtin.hpp:1185-1209). */
+int b200_axpby(b200_ctx_t ctx, double a, b200_vec_t x, double b, b200_vec_t y);
+
+/* z = a*x + b*y + c*z; z not read when c == 0 (interface.hpp:388-393, builtin.hpp:1211-1236). */
+int b200_axpbypcz(b200_ctx_t ctx, double a, b200_vec_t x, double b, b200_vec_t y,
+                  double c, b200_vec_t z);
+
+/* z = alpha*x.*y + beta*z; z not read when beta == 0 (interface.hpp:399-405, builtin.hpp:1238-1265). */
+int b200_vmul(b200_ctx_t ctx, double alpha, b200_vec_t x, b200_vec_t y,
+              double beta, b200_vec_t z);
+
+/* ---------------------------------------------------------------- smoothers */
+
+/* One diagonal-smoother sweep, fused into a single pass over A:
+ *     x <- x + (omega * diag) .* (rhs - A x)
+ * damped_jacobi: diag = D^-1, omega = damping (damped_jacobi.hpp:103-132);
+ * spai0:         diag = M,    omega = 1       (spai0.hpp:86-109).
+ * tmp is scratch of the same size as x; on return its contents are unspecified
+ * and x/tmp may have exchanged device storage.  If x is known to be zero
+ * (b200_clear() was the last writer) the A-pass is skipped: x = (omega*diag).*rhs,
+ * which is what the reference computes in that case (residual == rhs exactly). */
+int b200_relax(b200_ctx_t ctx, b200_csr_t A, b200_vec_t rhs, b200_vec_t x,
+               b200_vec_t tmp, b200_vec_t diag, double omega);
+
+/* ---------------------------------------------------------------- coarse solve */
+
+/* Coarsest-level direct solver (replaces solver::cuda_skyline_lu,
+ * cuda.hpp:61-84): the n x n inverse is formed on the device once
+ * (Gauss-Jordan, partial pivoting, FP64) and applied as a dense GEMV per
+ * cycle, so nothing leaves the device inside the V-cycle. */
+int b200_coarse_create_i64(b200_ctx_t ctx, int64_t n, const int64_t *ptr,
+                           const int64_t *col, const double *val, b200_coarse_t *S);
+int b200_coarse_create_i32(b200_ctx_t ctx, int64_t n, const int32_t *ptr,
+                           const int32_t *col, const double *val, b200_coarse_t *S);
+int b200_coarse_destroy(b200_coarse_t S);
+int b200_coarse_bytes(b200_coarse_t S, size_t *bytes);
+/* x = A^-1 rhs */
+int b200_coarse_solve(b200_ctx_t ctx, b200_coarse_t S, b200_vec_t rhs, b200_vec_t x);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AMGCL_B200_H */
