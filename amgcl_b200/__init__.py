@@ -36,6 +36,15 @@ class B200Error(RuntimeError):
     pass
 
 
+class ProfileEntry(_c.Structure):
+    """b200_profile_entry (include/amgcl_b200.h)."""
+    _fields_ = [("nrows", _i64), ("ncols", _i64), ("nnz", _i64), ("mode", _c.c_int),
+                ("launches", _i64), ("total_ms", _dbl), ("min_ms", _dbl)]
+
+
+MODE_NAMES = {0: "spmv", 1: "spmv_acc", 2: "residual", 3: "relax"}
+
+
 _lib = None
 _dropin = None
 
@@ -94,6 +103,8 @@ def lib():
         "b200_coarse_destroy": [_vp],
         "b200_coarse_bytes": [_vp, _P(_c.c_size_t)],
         "b200_coarse_solve": [_vp, _vp, _vp, _vp],
+        "b200_profile_begin": [_vp],
+        "b200_profile_end": [_vp, _vp, _i64, _P(_i64)],
     }
     for name, args in sigs.items():
         fn = getattr(L, name)
@@ -165,7 +176,14 @@ class Context:
             self.set_stream(stream)
 
     def set_stream(self, cuda_stream):
-        _check(lib().b200_ctx_set_stream(self.h, _vp(int(cuda_stream) if cuda_stream else 0)))
+        """cuda_stream: a cudaStream_t as int (torch: stream.cuda_stream).  0 means the
+        legacy default stream (what torch's default stream is); None selects the
+        context's own stream again."""
+        if cuda_stream is None:
+            handle = 0
+        else:
+            handle = int(cuda_stream) or 1     # (cudaStream_t)0x1 == cudaStreamLegacy
+        _check(lib().b200_ctx_set_stream(self.h, _vp(handle)))
 
     def sync(self):
         _check(lib().b200_ctx_sync(self.h), "b200_ctx_sync")
@@ -186,6 +204,23 @@ class Context:
 
     def reset_launches(self):
         _check(lib().b200_ctx_reset_launch_count(self.h))
+
+    def profile_begin(self):
+        _check(lib().b200_profile_begin(self.h), "b200_profile_begin")
+
+    def profile_end(self):
+        """Per (matrix shape, mode) device times of the CSR kernels since profile_begin()."""
+        cap = 256
+        buf = (ProfileEntry * cap)()
+        cnt = _i64()
+        _check(lib().b200_profile_end(self.h, buf, cap, _c.byref(cnt)), "b200_profile_end")
+        out = []
+        for i in range(min(cap, cnt.value)):
+            e = buf[i]
+            out.append({"nrows": e.nrows, "ncols": e.ncols, "nnz": e.nnz,
+                        "mode": MODE_NAMES.get(e.mode, str(e.mode)), "launches": e.launches,
+                        "total_ms": e.total_ms, "min_ms": e.min_ms})
+        return out
 
     def close(self):
         if self.h:

@@ -147,6 +147,7 @@ extern "C" int b200_ctx_destroy(b200_ctx_t ctx) {
     if (ctx->dot_ticket) cudaFree(ctx->dot_ticket);
     if (ctx->dot_result_h) cudaFreeHost(ctx->dot_result_h);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
     delete ctx;
     return B200_OK;
 }
@@ -203,6 +204,49 @@ extern "C" int b200_ctx_launch_count(b200_ctx_t ctx, uint64_t *count) {
 extern "C" int b200_ctx_reset_launch_count(b200_ctx_t ctx) {
     CHECK_CTX(ctx);
     ctx->launches = 0;
+    return B200_OK;
+}
+
+extern "C" int b200_profile_begin(b200_ctx_t ctx) {
+    CHECK_CTX(ctx);
+    ctx->prof_used = 0;
+    ctx->prof_recs.clear();
+    ctx->profiling = true;
+    return B200_OK;
+}
+
+extern "C" int b200_profile_end(b200_ctx_t ctx, b200_profile_entry *out, int64_t capacity,
+                                int64_t *count) {
+    CHECK_CTX(ctx);
+    B200_REQUIRE(count != nullptr, "null output pointer");
+    GUARD(ctx);
+    ctx->profiling = false;
+    B200_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::vector<b200_profile_entry> agg;
+    for (const auto &r : ctx->prof_recs) {
+        float ms = 0.f;
+        B200_CUDA(cudaEventElapsedTime(&ms, ctx->prof_events[r.ev], ctx->prof_events[r.ev + 1]));
+        b200_profile_entry *hit = nullptr;
+        for (auto &a : agg)
+            if (a.nrows == r.nrows && a.ncols == r.ncols && a.nnz == r.nnz && a.mode == r.mode) {
+                hit = &a;
+                break;
+            }
+        if (!hit) {
+            agg.push_back({r.nrows, r.ncols, r.nnz, r.mode, 0, 0.0, 1e30});
+            hit = &agg.back();
+        }
+        hit->launches += 1;
+        hit->total_ms += ms;
+        if (ms < hit->min_ms) hit->min_ms = ms;
+    }
+    ctx->prof_recs.clear();
+    ctx->prof_used = 0;
+    *count = (int64_t)agg.size();
+    if (out) {
+        const int64_t m = std::min<int64_t>(capacity, (int64_t)agg.size());
+        for (int64_t i = 0; i < m; ++i) out[i] = agg[(size_t)i];
+    }
     return B200_OK;
 }
 
@@ -532,8 +576,7 @@ static int launch_csr_L(b200_ctx_t ctx, b200_csr_t A, const CsrArgs &args) {
 }
 
 template <int MODE>
-static int launch_csr(b200_ctx_t ctx, b200_csr_t A, const CsrArgs &args) {
-    if (A->nblocks == 0) return B200_OK;
+static int launch_csr_dispatch(b200_ctx_t ctx, b200_csr_t A, const CsrArgs &args) {
     switch (A->lanes) {
     case 1:  return launch_csr_L<MODE, 1>(ctx, A, args);
     case 2:  return launch_csr_L<MODE, 2>(ctx, A, args);
@@ -542,6 +585,29 @@ static int launch_csr(b200_ctx_t ctx, b200_csr_t A, const CsrArgs &args) {
     case 16: return launch_csr_L<MODE, 16>(ctx, A, args);
     default: return launch_csr_L<MODE, 32>(ctx, A, args);
     }
+}
+
+constexpr size_t kProfMaxPairs = 1 << 16;
+
+template <int MODE>
+static int launch_csr(b200_ctx_t ctx, b200_csr_t A, const CsrArgs &args) {
+    if (A->nblocks == 0) return B200_OK;
+    if (!ctx->profiling || ctx->prof_recs.size() >= kProfMaxPairs)
+        return launch_csr_dispatch<MODE>(ctx, A, args);
+    // bracket the launch with a pair of events on the launching stream
+    while (ctx->prof_events.size() < ctx->prof_used + 2) {
+        cudaEvent_t e;
+        B200_CUDA(cudaEventCreate(&e));
+        ctx->prof_events.push_back(e);
+    }
+    const size_t ev = ctx->prof_used;
+    B200_CUDA(cudaEventRecord(ctx->prof_events[ev], ctx->stream));
+    int rc = launch_csr_dispatch<MODE>(ctx, A, args);
+    if (rc) return rc;
+    B200_CUDA(cudaEventRecord(ctx->prof_events[ev + 1], ctx->stream));
+    ctx->prof_used += 2;
+    ctx->prof_recs.push_back({A->nrows, A->ncols, A->nnz, MODE, ev});
+    return B200_OK;
 }
 
 static CsrArgs base_args(b200_csr_t A) {

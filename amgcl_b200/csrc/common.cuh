@@ -67,14 +67,21 @@ struct b200_ctx_s {
     double       *dot_result_h = nullptr; // pinned + mapped host scalar(s)
     double       *dot_result_d = nullptr; // device alias of dot_result_h
 
+    // optional per-launch timing of the CSR streaming kernels (b200_profile_*)
+    bool                      profiling = false;
+    std::vector<cudaEvent_t>  prof_events;      // pool, used pairwise
+    size_t                    prof_used = 0;
+    struct ProfRec { int64_t nrows, ncols, nnz; int mode; size_t ev; };
+    std::vector<ProfRec>      prof_recs;
+
     // tuning
-    int64_t opt_spmv_variant  = 0;
+    int64_t opt_spmv_variant  = 1;
     int64_t opt_fuse_relax    = 1;
     int64_t opt_zero_shortcut = 1;
     int64_t opt_nnz_cap       = 2048;
     int64_t opt_lanes         = 0;        // 0 = choose from average row length
-    int64_t opt_ctas_per_sm   = 2;        // persistent variant: CTAs per SM
-    int64_t opt_stages        = 4;        // persistent variant: ring depth
+    int64_t opt_ctas_per_sm   = 4;        // persistent variant: CTAs per SM
+    int64_t opt_stages        = 2;        // persistent variant: ring depth
 };
 
 struct b200_vec_s {

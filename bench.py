@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py -- solve-phase benchmark of the B200 backend (BASELINE.json metric).
+
+Workload (config #2 of BASELINE.json): 3-D 7-point Poisson 256^3 (16.8 M unknowns,
+117 M non-zeros), FP64, AMGCL smoothed_aggregation + damped_jacobi + CG with all
+reference defaults, hierarchy built on the host by AMGCL itself, solve phase on the
+B200 through amgcl::backend::b200 (the drop-in).  One "step" = one complete solve
+(rhs == 1, x0 == 0, tol 1e-8).  Metric: CG iterations per second (and solve seconds).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--n 256] [--impl b200|reference]
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "cg_iterations_per_second"
+UNIT = "iter/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=256, help="grid points per dimension")
+    ap.add_argument("--relax", default="damped_jacobi", choices=["damped_jacobi", "spai0"])
+    ap.add_argument("--krylov", default="cg", choices=["cg", "bicgstab"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-sample-iters", type=int, default=4,
+                    help="Krylov iterations per step of the CPU reference sample")
+    return ap.parse_args()
+
+
+def workload_name(args):
+    return "poisson3d_%d^3_fp64_sa_%s_%s" % (args.n, args.relax, args.krylov)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.QUERY,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+                power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, parts[4:8]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)),
+                "power_w_max": float(max(power)), "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------- reference arm
+def reference_arm(args, rank, world):
+    """The reference's own CPU implementation of the path: AMGCL builtin (OpenMP) backend
+    compiled from the reference sources (oracle/_ref), all host threads, same workload.
+    Each step is a bounded sample: the first `ref_sample_iters` Krylov iterations of the
+    solve (every iteration does the same work, so iterations/s is the same metric)."""
+    if rank != 0:
+        return
+    import oracle
+    from amgcl_b200 import poisson3d
+    if not oracle.have_ref():
+        print(json.dumps({"impl": "reference", "unavailable":
+                          "oracle/_ref/libamgcl_ref.so missing and /root/reference not present"}))
+        return
+    ref = oracle.ref()
+    cores = ref.threads
+    t0 = time.time()
+    ptr, col, val, rhs = poisson3d(args.n)
+    t_gen = time.time() - t0
+    t0 = time.time()
+    S = oracle.RefSolver(ptr, col, val, args.relax, args.krylov, maxiter=args.ref_sample_iters)
+    t_setup = time.time() - t0
+    for _ in range(args.warmup):
+        S.solve(rhs)
+    iters_total = 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        _, it, res = S.solve(rhs)
+        iters_total += it
+    dt = time.perf_counter() - t0
+    value = iters_total / dt
+    sample = "%d %s iterations of the %s solve per step, %d steps" % (
+        args.ref_sample_iters, args.krylov, workload_name(args), args.steps)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args), "backend": "amgcl::backend::builtin<double> (OpenMP)",
+                   "rows": int(ptr.size - 1), "nnz": int(ptr[-1]), "setup_s": t_setup,
+                   "generate_s": t_gen},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------- our arm
+def cpu_baseline_leg(args, ptr, col, val, rhs, full_iters):
+    """Reference builtin backend on the box's host cores, one full solve (bounded: the
+    whole 256^3 solve is a few seconds of CPU time on a many-core host)."""
+    import oracle
+    if not oracle.have_ref():
+        return None
+    ref = oracle.ref()
+    t0 = time.time()
+    S = oracle.RefSolver(ptr, col, val, args.relax, args.krylov)
+    t_setup = time.time() - t0
+    S.solve(rhs)                       # warm the caches / page in
+    t0 = time.perf_counter()
+    x, it, res = S.solve(rhs)
+    dt = time.perf_counter() - t0
+    S.close()
+    return {"value": it / dt, "unit": UNIT, "cores": ref.threads, "kind": "reference",
+            "sample": "one full %s solve (%d iterations, %.3f s) after one warm-up; setup %.1f s not timed"
+                      % (workload_name(args), it, dt, t_setup),
+            "iters": it, "resid": res, "solve_s": dt}, x
+
+
+def main_arm(args, rank, world, local_rank):
+    import torch
+    import amgcl_b200 as ab
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    device = local_rank
+    torch.cuda.set_device(device)
+    side = torch.cuda.Stream(device=device)
+    torch.cuda.set_stream(side)
+    ctx = ab.Context(device, stream=side.cuda_stream)
+
+    t0 = time.time()
+    ptr, col, val, rhs = ab.poisson3d(args.n)
+    t_gen = time.time() - t0
+    nrows, nnz = int(ptr.size - 1), int(ptr[-1])
+
+    t0 = time.time()
+    S = ab.DropinSolver(ptr, col, val, args.relax, args.krylov, ctx=ctx)
+    t_setup = time.time() - t0
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: rhs resident in HBM, x0 = 0, K complete solves ------------------------
+    S.upload_rhs(rhs)
+    for _ in range(max(args.warmup, 3)):
+        S.solve_resident()
+    sampler = ClockSampler(device)
+    barrier()
+    sampler.start()
+    ctx.reset_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(side)
+    iters_total = 0
+    for _ in range(args.steps):
+        it, res = S.solve_resident()
+        iters_total += it
+    e1.record(side)
+    barrier()
+    launches = ctx.launches
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    solve_s = ms * 1e-3 / args.steps
+    iters = iters_total // args.steps
+    # every rank solves its own replica of the system (see DESIGN.md "Multi-GPU")
+    value = world * iters_total / (ms * 1e-3)
+
+    # ---- roofline: same K steps again with the CSR launches bracketed by events ----------
+    ctx.profile_begin()
+    for _ in range(args.steps):
+        S.solve_resident()
+    prof = ctx.profile_end()
+    finest = [p for p in prof if p["nrows"] == nrows and p["ncols"] == nrows]
+    peak, peak_src = peaks()
+    roof = None
+    if finest:
+        def alg_bytes(p):
+            b = p["nnz"] * 12 + (p["nrows"] + 1) * 4 + p["ncols"] * 8 + p["nrows"] * 8
+            if p["mode"] in ("residual", "spmv_acc"):
+                b += p["nrows"] * 8
+            elif p["mode"] == "relax":
+                b += 2 * p["nrows"] * 8
+            return b
+        tot_b = sum(alg_bytes(p) * p["launches"] for p in finest)
+        tot_ms = sum(p["total_ms"] for p in finest)
+        tot_l = sum(p["launches"] for p in finest)
+        ach = tot_b / (tot_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "csr_ring_kernel (finest level A: spmv/residual/relax)",
+                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "peak_source": peak_src, "traffic": None,
+                "bytes_per_launch": tot_b / tot_l, "launches": tot_l,
+                "avg_launch_ms": tot_ms / tot_l,
+                "share_of_step": tot_ms / (args.steps * solve_s * 1e3),
+                "by_mode": {p["mode"]: {"launches": p["launches"],
+                                        "GBs": alg_bytes(p) * p["launches"] / (p["total_ms"] * 1e-3) / 1e9}
+                            for p in finest}}
+        ncu = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.isfile(ncu):
+            try:
+                with open(ncu) as f:
+                    roof["traffic"] = json.load(f).get("dram_bytes_per_launch")
+            except Exception:
+                pass
+    all_csr_ms = sum(p["total_ms"] for p in prof)
+
+    # ---- e2e: the user-facing call with pinned HOST buffers, copies inside the timed region --
+    rhs_pin = torch.empty(nrows, dtype=torch.float64, pin_memory=True)
+    x_pin = torch.empty(nrows, dtype=torch.float64, pin_memory=True)
+    rhs_h, x_h = rhs_pin.numpy(), x_pin.numpy()
+    rhs_h[:] = rhs
+    e2e_iters = 0
+    for _ in range(2):
+        x_h[:] = 0.0
+        S.solve_into(rhs_h, x_h)
+    barrier()
+    t_e2e = 0.0
+    for _ in range(args.steps):
+        x_h[:] = 0.0
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(side)
+        it, res_e2e = S.solve_into(rhs_h, x_h)
+        a1.record(side)
+        torch.cuda.synchronize()
+        t_e2e += a0.elapsed_time(a1) * 1e-3
+        e2e_iters += it
+    if dist is not None:
+        t = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_e2e = float(t.item())
+    e2e = {"value": world * e2e_iters / t_e2e, "unit": UNIT, "solve_s": t_e2e / args.steps,
+           "h2d_bytes_per_step": 2 * nrows * 8, "d2h_bytes_per_step": nrows * 8,
+           "api": "make_solver<amg<backend::b200<double>,...>, %s>::operator()(rhs, x) via dropin_solve "
+                  "(host rhs/x0 in, host x out)" % args.krylov}
+    x_gpu = x_h.copy()
+
+    # ---- cpu baseline (rank 0, N == 1) ---------------------------------------------------
+    cpu = None
+    parity = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        got = cpu_baseline_leg(args, ptr, col, val, rhs, iters)
+        if got is not None:
+            cpu, x_ref = got
+            parity = {"iters_gpu": iters, "iters_ref": cpu.pop("iters"),
+                      "resid_gpu": res, "resid_ref": cpu.pop("resid"),
+                      "x_rel_err_inf": float(np.abs(x_gpu - x_ref).max() / np.abs(x_ref).max())}
+            cpu.pop("solve_s", None)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": solve_s * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args), "rows": nrows, "nnz": nnz,
+                       "relax": args.relax, "krylov": args.krylov, "tol": 1e-8,
+                       "step": "one complete solve, rhs=1, x0=0",
+                       "l2": "inputs_exceed_l2 (finest matrix %.2f GB >> 126 MB)" % (nnz * 12 / 1e9),
+                       "parallelism": "single GPU" if world == 1 else
+                                      "%d independent replicas (one system per GPU)" % world,
+                       "setup_s": t_setup, "generate_s": t_gen, "hierarchy": "host (AMGCL smoothed_aggregation)"},
+            "solve_s": solve_s, "iters": iters, "resid": res,
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": roof, "csr_kernel_share_of_step": all_csr_ms / (args.steps * solve_s * 1e3),
+            "cpu_baseline": cpu, "parity": parity,
+        }
+        print(json.dumps(line))
+    S.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+    else:
+        main_arm(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -77,8 +77,28 @@ int b200_ctx_sync(b200_ctx_t ctx);
 int b200_ctx_launch_count(b200_ctx_t ctx, uint64_t *count);
 int b200_ctx_reset_launch_count(b200_ctx_t ctx);
 
+/* Per-launch device timing of the CSR streaming kernels (the reference's
+ * cuda_clock / AMGCL_TIC hooks, cuda.hpp:809-838, only see launch time): between
+ * begin and end every spmv / residual / relax launch is bracketed by a pair of
+ * CUDA events on the launching stream; end() aggregates them per (matrix shape,
+ * mode).  mode: 0 spmv(beta=0), 1 spmv(beta!=0), 2 residual, 3 fused relax. */
+typedef struct {
+    int64_t nrows, ncols, nnz;
+    int     mode;
+    int64_t launches;
+    double  total_ms;
+    double  min_ms;
+} b200_profile_entry;
+int b200_profile_begin(b200_ctx_t ctx);
+int b200_profile_end(b200_ctx_t ctx, b200_profile_entry *out, int64_t capacity, int64_t *count);
+
 /* Tuning knobs (all optional; defaults are chosen for B200).
- *   "spmv_variant"     0 = one row block per CTA, 1 = persistent multi-stage
+ *   "spmv_variant"     0 = one row block per CTA, 1 = persistent multi-stage ring (default)
+ *   "ctas_per_sm"      persistent variant: resident CTAs per SM (default 4)
+ *   "stages"           persistent variant: ring depth per CTA (default 2)
+ *   "nnz_cap"          non-zeros staged per row block (default 2048; applies to
+ *                      matrices created afterwards)
+ *   "lanes"            lanes per row, 0 = from the average row length (default)
  *   "fuse_relax"       1 = single-pass fused smoother sweep (default), 0 = two kernels
  *   "zero_shortcut"    1 = skip the A-pass when x is known to be zero (default)
  * Unknown keys return B200_EINVAL. */

@@ -1,0 +1,262 @@
+"""GPU parity tests proper: every C-ABI primitive against the oracle on identical
+inputs -- the committed golden vectors written by the real reference, and seeded
+random cases covering the edge cases the CSR kernels have to survive."""
+import numpy as np
+import pytest
+
+import amgcl_b200 as ab
+import oracle
+from conftest import rel_err, TOL_PRIMITIVE
+
+pytestmark = pytest.mark.gpu
+
+
+def up(ctx, A):
+    ptr, col, val = A
+    return ctx.csr(ptr.size - 1, int(col.max()) + 1 if col.size else 0, ptr, col, val)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_golden_level0_primitives(ctx, golden, variant):
+    ctx.set_option("spmv_variant", variant)
+    try:
+        g = golden
+        ptr, col, val = g.levels[0]["A"]
+        n = ptr.size - 1
+        A = ctx.csr(n, n, ptr, col, val)
+        a, b, c = g["in_a"], g["in_b"], g["in_c"]
+        va, vb, vc = ctx.vector(a), ctx.vector(b), ctx.vector(c)
+
+        ctx.spmv(2.0, A, va, 0.0, vb)
+        assert rel_err(vb.numpy(), g["spmv_2_a_0"]) < TOL_PRIMITIVE
+        vb.upload(b)
+        ctx.spmv(2.0, A, va, -0.5, vb)
+        assert rel_err(vb.numpy(), g["spmv_2_a_m05_b"]) < TOL_PRIMITIVE
+        vr = ctx.vector(n)
+        ctx.residual(vc, A, va, vr)
+        assert rel_err(vr.numpy(), g["residual_c_a"]) < TOL_PRIMITIVE
+        assert abs(ctx.dot(va, vc) - float(g["dot_a_c"])) < 1e-12
+        vb.upload(b)
+        ctx.axpby(0.3, va, 1.7, vb)
+        assert rel_err(vb.numpy(), g["axpby_03_a_17_b"]) < TOL_PRIMITIVE
+        vb.upload(b)
+        ctx.axpbypcz(0.3, va, 1.7, vb, -2.0, vc)
+        assert rel_err(vc.numpy(), g["axpbypcz"]) < TOL_PRIMITIVE
+        vc.upload(c)
+        ctx.vmul(0.72, va, vb, 1.0, vc)
+        assert rel_err(vc.numpy(), g["vmul_072_a_b_1_c"]) < TOL_PRIMITIVE
+        vc.upload(c)
+        ctx.vmul(1.0, va, vb, 0.0, vc)
+        assert rel_err(vc.numpy(), g["vmul_1_a_b_0_c"]) < TOL_PRIMITIVE
+    finally:
+        ctx.set_option("spmv_variant", 1)
+
+
+def test_golden_transfer_operators(ctx, golden):
+    g = golden
+    lv = g.levels[0]
+    n = lv["A"][0].size - 1
+    nc = lv["R"][0].size - 1
+    R = ctx.csr(nc, n, *lv["R"])
+    P = ctx.csr(n, nc, *lv["P"])
+    va, vu, vb = ctx.vector(g["in_a"]), ctx.vector(g["in_u"]), ctx.vector(g["in_b"])
+    vf = ctx.vector(nc)
+    ctx.spmv(1.0, R, va, 0.0, vf)                     # restriction  (amg.hpp:540)
+    assert rel_err(vf.numpy(), g["restrict_a"]) < TOL_PRIMITIVE
+    ctx.spmv(1.0, P, vu, 1.0, vb)                     # prolongation (amg.hpp:545)
+    assert rel_err(vb.numpy(), g["prolong_u_acc_b"]) < TOL_PRIMITIVE
+
+
+def test_zero_coefficient_never_reads_output(ctx, golden):
+    """Outputs whose coefficient is zero may hold NaNs (matrix_ops.hpp:65,73;
+    builtin.hpp:1197,1224,1253): the kernels must not touch them."""
+    g = golden
+    ptr, col, val = g.levels[0]["A"]
+    n = ptr.size - 1
+    A = ctx.csr(n, n, ptr, col, val)
+    nan = np.full(n, np.nan)
+    va, vb = ctx.vector(g["in_a"]), ctx.vector(g["in_b"])
+    out = ctx.vector(nan)
+    ctx.spmv(2.0, A, va, 0.0, out)
+    assert rel_err(out.numpy(), g["spmv_2_a_0"]) < TOL_PRIMITIVE
+    out.upload(nan)
+    ctx.axpby(0.3, va, 0.0, out)
+    assert rel_err(out.numpy(), g["axpby_03_a_0_b"]) < TOL_PRIMITIVE
+    out.upload(nan)
+    ctx.axpbypcz(0.3, va, 1.7, vb, 0.0, out)
+    assert rel_err(out.numpy(), g["axpbypcz_c0"]) < TOL_PRIMITIVE
+    out.upload(nan)
+    ctx.vmul(1.0, va, vb, 0.0, out)
+    assert rel_err(out.numpy(), g["vmul_1_a_b_0_c"]) < TOL_PRIMITIVE
+
+
+@pytest.mark.parametrize("fuse", [1, 0])
+def test_smoother_sweep_matches_oracle(ctx, golden, fuse):
+    """b200_relax == residual + vmul of the reference (damped_jacobi.hpp:108-109,
+    spai0.hpp:91-92), fused or not, and with the x == 0 shortcut."""
+    o = oracle.c()
+    ctx.set_option("fuse_relax", fuse)
+    try:
+        for lv in golden.levels:
+            ptr, col, val = lv["A"]
+            n = ptr.size - 1
+            rng = np.random.default_rng(n)
+            A = ctx.csr(n, n, ptr, col, val)
+            rhs, x0 = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
+            vr, vx, vt, vd = ctx.vector(rhs), ctx.vector(x0), ctx.vector(n), ctx.vector(lv["diag"])
+            ctx.relax(A, vr, vx, vt, vd, golden.omega)
+            want = o.relax(lv["A"], rhs, x0, lv["diag"], golden.omega)
+            assert rel_err(vx.numpy(), want) < TOL_PRIMITIVE
+            ctx.relax(A, vr, vx, vt, vd, golden.omega)            # second sweep (storage swapped)
+            want = o.relax(lv["A"], rhs, want, lv["diag"], golden.omega)
+            assert rel_err(vx.numpy(), want) < TOL_PRIMITIVE
+            ctx.clear(vx)                                          # lazy zero -> shortcut
+            ctx.relax(A, vr, vx, vt, vd, golden.omega)
+            want = o.relax(lv["A"], rhs, np.zeros(n), lv["diag"], golden.omega)
+            assert rel_err(vx.numpy(), want) < TOL_PRIMITIVE
+    finally:
+        ctx.set_option("fuse_relax", 1)
+
+
+def test_lazy_clear_semantics(ctx):
+    n = 1000
+    rng = np.random.default_rng(3)
+    a = rng.uniform(-1, 1, n)
+    va, vz = ctx.vector(a), ctx.vector(a)
+    ctx.clear(vz)
+    assert not vz.numpy().any()
+    assert ctx.dot(va, vz) == 0.0
+    ctx.axpby(2.0, va, 1.0, vz)           # z = 2a + 0
+    assert rel_err(vz.numpy(), 2 * a) < 1e-16
+    ctx.clear(vz)
+    ctx.copy(vz, va)                      # copies the zero
+    assert not va.numpy().any()
+    fresh = ctx.vector(n)                 # create_vector is zero filled
+    assert not fresh.numpy().any()
+    ctx.clear(vz)
+    assert vz.data_ptr() != 0 and not vz.numpy().any()
+
+
+def test_coarse_solver_matches_reference_lu(ctx, golden):
+    ptr, col, val = golden.coarse
+    n = ptr.size - 1
+    S = ctx.coarse(n, ptr, col, val)
+    vg, vx = ctx.vector(golden["in_g"]), ctx.vector(n)
+    ctx.coarse_solve(S, vg, vx)
+    assert rel_err(vx.numpy(), golden["coarse_solve_g"]) < 1e-11
+
+
+def test_coarse_solver_needs_pivoting(ctx):
+    # a system whose natural-order elimination hits a zero pivot
+    A = np.array([[0.0, 2.0, 1.0], [1.0, 0.0, 3.0], [4.0, 1.0, 0.0]])
+    import scipy.sparse as sp
+    M = sp.csr_matrix(A)
+    S = ctx.coarse(3, M.indptr, M.indices, M.data)
+    b = np.array([1.0, -2.0, 0.5])
+    vb, vx = ctx.vector(b), ctx.vector(3)
+    ctx.coarse_solve(S, vb, vx)
+    assert rel_err(vx.numpy(), np.linalg.solve(A, b)) < 1e-13
+    with pytest.raises(ab.B200Error):
+        ctx.coarse(2, np.array([0, 2, 4]), np.array([0, 1, 0, 1]), np.array([1.0, 2.0, 2.0, 4.0]))
+
+
+@pytest.mark.parametrize("lanes", [0, 1, 2, 4, 8, 16, 32])
+@pytest.mark.parametrize("variant", [0, 1])
+def test_ragged_matrix_all_lane_widths(ctx, lanes, variant):
+    """Empty rows, a row longer than a stage, a short last quad, rectangular shape."""
+    o = oracle.c()
+    rng = np.random.default_rng(lanes * 7 + variant)
+    nr, nc = 3001, 2500
+    lens = rng.integers(0, 40, nr)
+    lens[:9] = 0
+    lens[100] = 7000
+    lens[nr - 1] = 3
+    ptr = np.zeros(nr + 1, dtype=np.int64)
+    np.cumsum(lens, out=ptr[1:])
+    col = rng.integers(0, nc, ptr[-1])
+    val = rng.uniform(-1, 1, ptr[-1])
+    x, y, f = rng.uniform(-1, 1, nc), rng.uniform(-1, 1, nr), rng.uniform(-1, 1, nr)
+    ctx.set_option("lanes", lanes)
+    ctx.set_option("spmv_variant", variant)
+    try:
+        A = ctx.csr(nr, nc, ptr, col, val)
+        assert A.plan()["long_blocks"] >= 1
+        vx, vy, vf = ctx.vector(x), ctx.vector(y), ctx.vector(f)
+        ctx.spmv(1.5, A, vx, -0.25, vy)
+        assert rel_err(vy.numpy(), o.spmv(1.5, (ptr, col, val), x, -0.25, y)) < 1e-12
+        ctx.residual(vf, A, vx, vy)
+        assert rel_err(vy.numpy(), o.residual(f, (ptr, col, val), x)) < 1e-12
+    finally:
+        ctx.set_option("lanes", 0)
+        ctx.set_option("spmv_variant", 1)
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (3, 5), (4, 4), (5, 3), (257, 255), (1025, 64)])
+def test_small_and_odd_shapes(ctx, shape):
+    o = oracle.c()
+    nr, nc = shape
+    rng = np.random.default_rng(nr * 31 + nc)
+    import scipy.sparse as sp
+    M = sp.random(nr, nc, density=min(1.0, 6.0 / nc), random_state=1, format="csr")
+    M.sort_indices()
+    ptr, col, val = M.indptr.astype(np.int64), M.indices.astype(np.int64), M.data
+    x, y = rng.uniform(-1, 1, nc), rng.uniform(-1, 1, nr)
+    A = ctx.csr(nr, nc, ptr, col, val)
+    vx, vy = ctx.vector(x), ctx.vector(y)
+    ctx.spmv(1.0, A, vx, 2.0, vy)
+    assert rel_err(vy.numpy(), o.spmv(1.0, (ptr, col, val), x, 2.0, y)) < 1e-13 or not val.size
+    # int32 host indices take the other entry point
+    A32 = ctx.csr(nr, nc, ptr.astype(np.int32), col.astype(np.int32), val)
+    vy.upload(y)
+    ctx.spmv(1.0, A32, vx, 2.0, vy)
+    assert rel_err(vy.numpy(), o.spmv(1.0, (ptr, col, val), x, 2.0, y)) < 1e-13 or not val.size
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 255, 256, 257, 100003])
+def test_vector_ops_odd_lengths(ctx, n):
+    o = oracle.c()
+    rng = np.random.default_rng(n)
+    a, b, c = (rng.uniform(-1, 1, n) for _ in range(3))
+    va, vb, vc = ctx.vector(a), ctx.vector(b), ctx.vector(c)
+    ctx.axpby(-1.25, va, 0.5, vb)
+    want_b = o.axpby(-1.25, a, 0.5, b)
+    assert n == 0 or rel_err(vb.numpy(), want_b) < 1e-15
+    ctx.axpbypcz(2.0, va, -1.0, vb, 0.125, vc)
+    want_c = o.axpbypcz(2.0, a, -1.0, want_b, 0.125, c)
+    assert n == 0 or rel_err(vc.numpy(), want_c) < 1e-15
+    got = ctx.dot(va, vc)
+    want = o.inner_product(a, want_c)
+    assert abs(got - want) <= 1e-13 * max(1.0, np.abs(a * want_c).sum())
+    ctx.copy(vc, va)
+    assert n == 0 or np.array_equal(va.numpy(), vc.numpy())
+
+
+def test_argument_errors(ctx):
+    ptr, col, val, rhs = ab.poisson3d(4)
+    A = ctx.csr(64, 64, ptr, col, val)
+    good, bad = ctx.vector(64), ctx.vector(63)
+    with pytest.raises(ab.B200Error):
+        ctx.spmv(1.0, A, bad, 0.0, good)
+    with pytest.raises(ab.B200Error):
+        ctx.spmv(1.0, A, good, 0.0, good)          # aliasing
+    with pytest.raises(ab.B200Error):
+        ctx.axpby(1.0, good, 1.0, bad)
+    with pytest.raises(ab.B200Error):
+        ctx.csr(64, 10, ptr, col, val)              # column index out of range
+    with pytest.raises(ab.B200Error):
+        ctx.set_option("no_such_option", 1)
+
+
+def test_dot_is_deterministic_and_compensated(ctx):
+    n = 1 << 22
+    rng = np.random.default_rng(0)
+    a = rng.uniform(-1, 1, n) * 1e8
+    a[::2] = -a[1::2]                      # massive cancellation
+    a[0] += 1.0
+    ones = np.ones(n)
+    va, vo = ctx.vector(a), ctx.vector(ones)
+    r1 = ctx.dot(va, vo)
+    r2 = ctx.dot(va, vo)
+    assert r1 == r2
+    import math
+    assert abs(r1 - math.fsum(a)) < 1e-6

@@ -1,0 +1,133 @@
+"""GPU end-to-end parity: AMGCL's own make_solver<amg<...>, cg|bicgstab> running on
+backend::b200 (the drop-in) against the reference's builtin backend.
+
+Tolerances: equal iteration count, final relative residual within 1e-6
+relative, ||x - x_ref||_inf / ||x_ref||_inf <= 1e-8."""
+import numpy as np
+import pytest
+
+import amgcl_b200 as ab
+import oracle
+from conftest import rel_err, TOL_RESID_REL, TOL_SOLUTION
+
+pytestmark = pytest.mark.gpu
+
+CONFIGS = [("damped_jacobi", "cg"), ("spai0", "bicgstab"), ("spai0", "cg"),
+           ("damped_jacobi", "bicgstab")]
+
+
+def test_dropin_matches_golden_fixture(ctx, golden):
+    """Same hierarchy parameters as the fixture (coarse_enough=100 -> 3 levels)."""
+    ptr, col, val, rhs = ab.poisson3d(golden.n)
+    S = ab.DropinSolver(ptr, col, val, golden.relax, golden.krylov,
+                        coarse_enough=golden.coarse_enough, ctx=ctx)
+    x, iters, resid = S.solve(rhs)
+    assert iters == int(golden["iters"])
+    assert abs(resid - float(golden["resid"])) <= TOL_RESID_REL * float(golden["resid"])
+    assert rel_err(x, golden["x"]) < TOL_SOLUTION
+    # one V-cycle on a seeded vector
+    assert rel_err(S.apply_precond(golden["in_a"]), golden["precond_a"]) < 1e-11
+    rep = S.report()
+    assert "Number of levels:    %d" % golden.nlevels in rep
+    S.close()
+
+
+@pytest.mark.parametrize("n", [16, 32, 64])
+@pytest.mark.parametrize("relax,krylov", CONFIGS)
+def test_dropin_matches_known_answers(ctx, known_answers, n, relax, krylov):
+    """Configs #1 of BASELINE.json (64^3) and smaller: iterations / residual / solution
+    samples recorded from the reference (tests/golden/known_answers.json)."""
+    case = [c for c in known_answers["cases"]
+            if (c["n"], c["relax"], c["krylov"]) == (n, relax, krylov)][0]
+    ptr, col, val, rhs = ab.poisson3d(n)
+    S = ab.DropinSolver(ptr, col, val, relax, krylov, ctx=ctx)
+    x, iters, resid = S.solve(rhs)
+    assert iters == case["iters"]
+    assert abs(resid - case["resid"]) <= TOL_RESID_REL * case["resid"]
+    assert abs(x[0] - case["x_first"]) <= TOL_SOLUTION * abs(case["x_first"])
+    assert abs(x[x.size // 2] - case["x_mid"]) <= TOL_SOLUTION * abs(case["x_mid"])
+    assert abs(np.linalg.norm(x) - case["x_norm2"]) <= TOL_SOLUTION * case["x_norm2"]
+    # true residual of the returned solution (size-independent property)
+    r = rhs - oracle.c().spmv(1.0, (ptr, col, val), x, 0.0, np.zeros_like(x))
+    assert np.linalg.norm(r) / np.linalg.norm(rhs) < 2e-8
+    S.close()
+
+
+@pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not shipped")
+@pytest.mark.parametrize("relax,krylov", CONFIGS[:2])
+def test_dropin_vs_live_reference_random_rhs(ctx, relax, krylov):
+    n = 40
+    ptr, col, val, _ = ab.poisson3d(n)
+    rng = np.random.default_rng(7)
+    rhs = rng.uniform(-1, 1, ptr.size - 1)
+    x0 = rng.uniform(-1, 1, ptr.size - 1)
+    R = oracle.RefSolver(ptr, col, val, relax, krylov)
+    S = ab.DropinSolver(ptr, col, val, relax, krylov, ctx=ctx)
+    xr, itr, resr = R.solve(rhs, x0)
+    xg, itg, resg = S.solve(rhs, x0)
+    assert itg == itr
+    assert abs(resg - resr) <= TOL_RESID_REL * resr
+    assert rel_err(xg, xr) < TOL_SOLUTION
+    # the preconditioner alone
+    assert rel_err(S.apply_precond(rhs), R.apply_precond(rhs)) < 1e-10
+    S.close()
+    R.close()
+
+
+def test_zero_rhs(ctx):
+    ptr, col, val, rhs = ab.poisson3d(12)
+    S = ab.DropinSolver(ptr, col, val, ctx=ctx)
+    x, iters, resid = S.solve(np.zeros_like(rhs), x0=np.ones_like(rhs))
+    assert iters == 0 and resid == 0.0 and not x.any()      # cg.hpp:162-169
+    S.close()
+
+
+def test_resident_path_equals_host_path(ctx):
+    ptr, col, val, rhs = ab.poisson3d(24)
+    S = ab.DropinSolver(ptr, col, val, ctx=ctx)
+    x1, it1, r1 = S.solve(rhs)
+    S.upload_rhs(rhs)
+    it2, r2 = S.solve_resident()
+    assert (it1, r1) == (it2, r2)
+    assert np.array_equal(S.download_x(), x1)
+    S.close()
+
+
+def test_variants_and_fusion_agree(ctx):
+    """Kernel scheduling variants and the fused / unfused smoother give the same solve."""
+    ptr, col, val, rhs = ab.poisson3d(32)
+    results = []
+    try:
+        for variant, fuse, shortcut in ((1, 1, 1), (0, 1, 1), (1, 0, 1), (1, 1, 0)):
+            ctx.set_option("spmv_variant", variant)
+            ctx.set_option("fuse_relax", fuse)
+            ctx.set_option("zero_shortcut", shortcut)
+            S = ab.DropinSolver(ptr, col, val, ctx=ctx)
+            results.append(S.solve(rhs))
+            S.close()
+    finally:
+        ctx.set_option("spmv_variant", 1)
+        ctx.set_option("fuse_relax", 1)
+        ctx.set_option("zero_shortcut", 1)
+    x0, it0, r0 = results[0]
+    for x, it, r in results[1:]:
+        assert it == it0 and abs(r - r0) <= 1e-9 * r0 and rel_err(x, x0) < 1e-12
+
+
+def test_large_problem_size_independent_properties(ctx):
+    """128^3 (2.1M rows): survey iteration count, true residual, linearity of the V-cycle."""
+    n = 128
+    ptr, col, val, rhs = ab.poisson3d(n)
+    S = ab.DropinSolver(ptr, col, val, "damped_jacobi", "cg", ctx=ctx)
+    x, iters, resid = S.solve(rhs)
+    assert iters == 21
+    assert abs(resid - 6.07447143094944e-09) <= TOL_RESID_REL * 6.07447143094944e-09
+    A = ctx.csr(n ** 3, n ** 3, ptr, col, val)
+    vx, vf, vr = ctx.vector(x), ctx.vector(rhs), ctx.vector(n ** 3)
+    ctx.residual(vf, A, vx, vr)
+    assert np.sqrt(ctx.dot(vr, vr)) / np.sqrt(ctx.dot(vf, vf)) < 2e-8
+    rng = np.random.default_rng(5)
+    u, v = rng.uniform(-1, 1, n ** 3), rng.uniform(-1, 1, n ** 3)
+    Mu, Mv, Muv = S.apply_precond(u), S.apply_precond(v), S.apply_precond(2.0 * u - 3.0 * v)
+    assert rel_err(Muv, 2.0 * Mu - 3.0 * Mv) < 1e-12        # the V-cycle is a linear operator
+    S.close()

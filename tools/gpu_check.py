@@ -157,7 +157,9 @@ def cmd_parity():
 
 
 def cmd_spmv(n):
-    ctx = ab.Context(0, stream=torch.cuda.current_stream().cuda_stream)
+    side = torch.cuda.Stream()
+    torch.cuda.set_stream(side)
+    ctx = ab.Context(0, stream=side.cuda_stream)
     ptr, col, val, rhs = ab.poisson3d(n)
     nr = ptr.size - 1
     nnz = int(ptr[-1])
