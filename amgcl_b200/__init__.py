@@ -42,7 +42,8 @@ class ProfileEntry(_c.Structure):
                 ("launches", _i64), ("total_ms", _dbl), ("min_ms", _dbl)]
 
 
-MODE_NAMES = {0: "spmv", 1: "spmv_acc", 2: "residual", 3: "relax"}
+MODE_NAMES = {0: "spmv", 1: "spmv_acc", 2: "residual", 3: "relax", 10: "vec1", 11: "vec2",
+              12: "vec3", 20: "dot", 21: "relax_zero", 22: "coarse_gemv", 23: "memset"}
 
 
 _lib = None

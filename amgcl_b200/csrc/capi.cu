@@ -55,9 +55,39 @@ struct DeviceGuard {
 
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+constexpr size_t kProfMaxPairs = 1 << 17;
+
+// Bracket one launch with a pair of events on the launching stream (profiling only).
+struct ProfScope {
+    b200_ctx_t ctx;
+    bool on = false;
+    size_t ev = 0;
+    int64_t nrows, ncols, nnz;
+    int mode;
+    ProfScope(b200_ctx_t c, int mode_, int64_t nr, int64_t nc, int64_t nz)
+        : ctx(c), nrows(nr), ncols(nc), nnz(nz), mode(mode_) {
+        if (!ctx->profiling || ctx->prof_recs.size() >= kProfMaxPairs) return;
+        while (ctx->prof_events.size() < ctx->prof_used + 2) {
+            cudaEvent_t e;
+            if (cudaEventCreate(&e) != cudaSuccess) return;
+            ctx->prof_events.push_back(e);
+        }
+        ev = ctx->prof_used;
+        if (cudaEventRecord(ctx->prof_events[ev], ctx->stream) != cudaSuccess) return;
+        on = true;
+    }
+    ~ProfScope() {
+        if (!on) return;
+        if (cudaEventRecord(ctx->prof_events[ev + 1], ctx->stream) != cudaSuccess) return;
+        ctx->prof_used += 2;
+        ctx->prof_recs.push_back({nrows, ncols, nnz, mode, ev});
+    }
+};
+
 // Lazy clear bookkeeping ------------------------------------------------------
 static int materialize(b200_vec_t v) {
     if (v->zero_pending) {
+        ProfScope prof(v->ctx, B200_PROF_MEMSET, (int64_t)v->n, 1, 0);
         B200_CUDA(cudaMemsetAsync(v->ptr, 0, v->n * sizeof(double), v->ctx->stream));
         v->zero_pending = false;
     }
@@ -587,27 +617,11 @@ static int launch_csr_dispatch(b200_ctx_t ctx, b200_csr_t A, const CsrArgs &args
     }
 }
 
-constexpr size_t kProfMaxPairs = 1 << 16;
-
 template <int MODE>
 static int launch_csr(b200_ctx_t ctx, b200_csr_t A, const CsrArgs &args) {
     if (A->nblocks == 0) return B200_OK;
-    if (!ctx->profiling || ctx->prof_recs.size() >= kProfMaxPairs)
-        return launch_csr_dispatch<MODE>(ctx, A, args);
-    // bracket the launch with a pair of events on the launching stream
-    while (ctx->prof_events.size() < ctx->prof_used + 2) {
-        cudaEvent_t e;
-        B200_CUDA(cudaEventCreate(&e));
-        ctx->prof_events.push_back(e);
-    }
-    const size_t ev = ctx->prof_used;
-    B200_CUDA(cudaEventRecord(ctx->prof_events[ev], ctx->stream));
-    int rc = launch_csr_dispatch<MODE>(ctx, A, args);
-    if (rc) return rc;
-    B200_CUDA(cudaEventRecord(ctx->prof_events[ev + 1], ctx->stream));
-    ctx->prof_used += 2;
-    ctx->prof_recs.push_back({A->nrows, A->ncols, A->nnz, MODE, ev});
-    return B200_OK;
+    ProfScope prof(ctx, MODE, A->nrows, A->ncols, A->nnz);
+    return launch_csr_dispatch<MODE>(ctx, A, args);
 }
 
 static CsrArgs base_args(b200_csr_t A) {
@@ -627,6 +641,7 @@ static int launch_ew(b200_ctx_t ctx, size_t n, F f, const double *x, const doubl
     const bool vec_ok = aligned16(x) && aligned16(out) && (!RY || aligned16(y)) &&
                         (!RZ || aligned16(z));
     const int grid = grid_for(ctx, n, 4);
+    ProfScope prof(ctx, B200_PROF_VECTOR + (RY ? 1 : 0) + (RZ ? 1 : 0), (int64_t)n, 1, 0);
     ew_kernel<F, RY, RZ><<<grid, kThreads, 0, ctx->stream>>>(n, f, x, y, z, out, vec_ok);
     B200_CHECK_LAUNCH();
     ctx->launches++;
@@ -788,8 +803,11 @@ extern "C" int b200_dot(b200_ctx_t ctx, b200_vec_t x, b200_vec_t y, double *resu
     }
     const bool vec_ok = aligned16(x->ptr) && aligned16(y->ptr);
     int grid = std::min(grid_for(ctx, x->n, 8), kDotMaxBlocks);
-    dot_kernel<<<grid, kThreads, 0, ctx->stream>>>(x->n, x->ptr, y->ptr, ctx->dot_partial,
-                                                   ctx->dot_ticket, ctx->dot_result_d, vec_ok);
+    {
+        ProfScope prof(ctx, B200_PROF_DOT, (int64_t)x->n, 1, 0);
+        dot_kernel<<<grid, kThreads, 0, ctx->stream>>>(x->n, x->ptr, y->ptr, ctx->dot_partial,
+                                                       ctx->dot_ticket, ctx->dot_result_d, vec_ok);
+    }
     B200_CHECK_LAUNCH();
     ctx->launches++;
     B200_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -874,6 +892,7 @@ extern "C" int b200_relax(b200_ctx_t ctx, b200_csr_t A, b200_vec_t rhs, b200_vec
     if (x->zero_pending && ctx->opt_zero_shortcut) {
         // residual(rhs, A, 0) == rhs exactly, so the sweep reduces to a scaling
         const int grid = grid_for(ctx, x->n, 2);
+        ProfScope prof(ctx, B200_PROF_RELAX_ZERO, (int64_t)x->n, 1, 0);
         relax_zero_kernel<<<grid, kThreads, 0, ctx->stream>>>(x->n, omega, pd, pf, wr(x));
         B200_CHECK_LAUNCH();
         ctx->launches++;
@@ -1045,6 +1064,7 @@ extern "C" int b200_coarse_solve(b200_ctx_t ctx, b200_coarse_t S, b200_vec_t rhs
     if (rc) return rc;
     const int N = (int)S->n;
     const int warps_per_cta = kThreads / 32;
+    ProfScope prof(ctx, B200_PROF_COARSE, S->n, S->n, S->n * S->n);
     coarse_gemv_kernel<<<(N + warps_per_cta - 1) / warps_per_cta, kThreads, 0, ctx->stream>>>(
         N, S->Ainv, pr, wr(x));
     B200_CHECK_LAUNCH();

@@ -113,6 +113,24 @@ class ClockSampler:
                 "power_w_max": float(max(power)), "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def pick_threads(ref, step):
+    """Give the CPU reference its best OpenMP thread count on this host (memory-bound
+    kernels often peak below the hardware thread count): time one step per candidate."""
+    hw = os.cpu_count() or ref.threads
+    cands = sorted({c for c in (ref.threads, hw, hw // 2, hw // 4) if c and c >= 1}, reverse=True)
+    best, best_t = cands[0], None
+    for c in cands:
+        ref.set_threads(c)
+        step()                                   # settle
+        t0 = time.perf_counter()
+        step()
+        dt = time.perf_counter() - t0
+        if best_t is None or dt < best_t:
+            best, best_t = c, dt
+    ref.set_threads(best)
+    return best
+
+
 # --------------------------------------------------------------------------- reference arm
 def reference_arm(args, rank, world):
     """The reference's own CPU implementation of the path: AMGCL builtin (OpenMP) backend
@@ -128,13 +146,13 @@ def reference_arm(args, rank, world):
                           "oracle/_ref/libamgcl_ref.so missing and /root/reference not present"}))
         return
     ref = oracle.ref()
-    cores = ref.threads
     t0 = time.time()
     ptr, col, val, rhs = poisson3d(args.n)
     t_gen = time.time() - t0
     t0 = time.time()
     S = oracle.RefSolver(ptr, col, val, args.relax, args.krylov, maxiter=args.ref_sample_iters)
     t_setup = time.time() - t0
+    cores = pick_threads(ref, lambda: S.solve(rhs))
     for _ in range(args.warmup):
         S.solve(rhs)
     iters_total = 0
@@ -173,12 +191,15 @@ def cpu_baseline_leg(args, ptr, col, val, rhs, full_iters):
     t0 = time.time()
     S = oracle.RefSolver(ptr, col, val, args.relax, args.krylov)
     t_setup = time.time() - t0
+    Sq = oracle.RefSolver(ptr, col, val, args.relax, args.krylov, maxiter=2)
+    threads = pick_threads(ref, lambda: Sq.solve(rhs))
+    Sq.close()
     S.solve(rhs)                       # warm the caches / page in
     t0 = time.perf_counter()
     x, it, res = S.solve(rhs)
     dt = time.perf_counter() - t0
     S.close()
-    return {"value": it / dt, "unit": UNIT, "cores": ref.threads, "kind": "reference",
+    return {"value": it / dt, "unit": UNIT, "cores": threads, "kind": "reference",
             "sample": "one full %s solve (%d iterations, %.3f s) after one warm-up; setup %.1f s not timed"
                       % (workload_name(args), it, dt, t_setup),
             "iters": it, "resid": res, "solve_s": dt}, x
@@ -278,7 +299,25 @@ def main_arm(args, rank, world, local_rank):
                     roof["traffic"] = json.load(f).get("dram_bytes_per_launch")
             except Exception:
                 pass
-    all_csr_ms = sum(p["total_ms"] for p in prof)
+    all_csr_ms = sum(p["total_ms"] for p in prof if p["nnz"] > 0 and p["mode"] != "coarse_gemv")
+    streams = {"vec1": 2, "vec2": 3, "vec3": 4, "dot": 2, "relax_zero": 3, "memset": 1}
+    breakdown = []
+    for p in sorted(prof, key=lambda q: -q["total_ms"]):
+        if p["mode"] in streams:
+            b = streams[p["mode"]] * p["nrows"] * 8
+        elif p["mode"] == "coarse_gemv":
+            b = p["nnz"] * 8
+        else:
+            b = p["nnz"] * 12 + (p["nrows"] + 1) * 4 + p["ncols"] * 8 + p["nrows"] * 8
+            if p["mode"] in ("residual", "spmv_acc"):
+                b += p["nrows"] * 8
+            elif p["mode"] == "relax":
+                b += 2 * p["nrows"] * 8
+        breakdown.append({"rows": p["nrows"], "cols": p["ncols"], "nnz": p["nnz"], "kernel": p["mode"],
+                          "launches_per_step": p["launches"] / args.steps,
+                          "ms_per_step": round(p["total_ms"] / args.steps, 4),
+                          "GBs": round(b * p["launches"] / (p["total_ms"] * 1e-3) / 1e9, 1)})
+    kernels_ms_per_step = sum(p["total_ms"] for p in prof) / args.steps
 
     # ---- e2e: the user-facing call with pinned HOST buffers, copies inside the timed region --
     rhs_pin = torch.empty(nrows, dtype=torch.float64, pin_memory=True)
@@ -337,6 +376,7 @@ def main_arm(args, rank, world, local_rank):
             "solve_s": solve_s, "iters": iters, "resid": res,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "roofline": roof, "csr_kernel_share_of_step": all_csr_ms / (args.steps * solve_s * 1e3),
+            "kernels_ms_per_step": kernels_ms_per_step, "breakdown": breakdown,
             "cpu_baseline": cpu, "parity": parity,
         }
         print(json.dumps(line))

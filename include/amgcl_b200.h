@@ -81,7 +81,13 @@ int b200_ctx_reset_launch_count(b200_ctx_t ctx);
  * cuda_clock / AMGCL_TIC hooks, cuda.hpp:809-838, only see launch time): between
  * begin and end every spmv / residual / relax launch is bracketed by a pair of
  * CUDA events on the launching stream; end() aggregates them per (matrix shape,
- * mode).  mode: 0 spmv(beta=0), 1 spmv(beta!=0), 2 residual, 3 fused relax. */
+ * mode).  mode: 0 spmv(beta=0), 1 spmv(beta!=0), 2 residual, 3 fused relax; the
+ * vector kernels report nrows = n, ncols = 1, nnz = 0 and one of the modes below. */
+#define B200_PROF_VECTOR      10   /* element-wise, +1 per extra input stream (10..12) */
+#define B200_PROF_DOT         20
+#define B200_PROF_RELAX_ZERO  21   /* x = omega*diag.*rhs shortcut of the smoother     */
+#define B200_PROF_COARSE      22   /* dense GEMV of the coarsest-level solve           */
+#define B200_PROF_MEMSET      23   /* materialised lazy clear                          */
 typedef struct {
     int64_t nrows, ncols, nnz;
     int     mode;
