@@ -428,14 +428,16 @@ extern "C" int b200_vec_download(b200_vec_t v, double *host, size_t n) {
 namespace b200 {
 
 static int choose_lanes(double avg) {
+    // measured on the B200 with the operators of a 192^3 Poisson hierarchy
+    // (tools/gpu_check.py levels): few lanes per row keep many rows -- and so many
+    // independent x-gathers -- in flight per CTA; wide groups only pay off for long rows
     if (avg <= 12.0) return 1;
-    if (avg <= 24.0) return 2;
-    if (avg <= 48.0) return 4;
-    if (avg <= 96.0) return 8;
-    if (avg <= 192.0) return 16;
+    if (avg <= 40.0) return 2;
+    if (avg <= 64.0) return 4;
+    if (avg <= 160.0) return 8;
+    if (avg <= 320.0) return 16;
     return 32;
 }
-
 
 // Row-block plan (pure host logic, also exported as b200_plan_i64 for tests):
 // consecutive rows, starting at a multiple of four, are packed greedily while

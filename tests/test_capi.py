@@ -125,7 +125,7 @@ def test_plan_ragged(seed):
 
 
 def test_plan_lane_heuristic():
-    for avg, want in ((3, 1), (7, 1), (20, 2), (30, 4), (70, 8), (150, 16), (500, 32)):
+    for avg, want in ((3, 1), (7, 1), (20, 2), (30, 2), (50, 4), (70, 8), (200, 16), (500, 32)):
         ptr = np.arange(0, 1001, dtype=np.int64) * avg
         _, lanes, _, _ = plan(ptr)
         assert lanes == want

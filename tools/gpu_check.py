@@ -206,9 +206,57 @@ def cmd_spmv(n):
     print(json.dumps(rec), flush=True)
 
 
+def cmd_levels(n):
+    """Sweep lanes-per-row / stage size / ring shape on the REAL hierarchy operators
+    (A_l, P_l, R_l of every level, taken from the reference-built hierarchy)."""
+    import oracle
+    side = torch.cuda.Stream()
+    torch.cuda.set_stream(side)
+    ctx = ab.Context(0, stream=side.cuda_stream)
+    ptr, col, val, rhs = ab.poisson3d(n)
+    S = oracle.RefSolver(ptr, col, val, "damped_jacobi", "cg")
+    levels, coarse = S.hierarchy()
+    rng = np.random.default_rng(0)
+    ops = []
+    for l, lv in enumerate(levels):
+        for key in ("A", "P", "R"):
+            if l == 0 and key == "A":
+                continue
+            p_, c_, v_ = lv[key]
+            nr = p_.size - 1
+            nc = {"A": nr, "P": lv["R"][0].size - 1, "R": lv["A"][0].size - 1}[key]
+            ops.append(("L%d_%s" % (l, key), nr, nc, p_, c_, v_))
+    for name, nr, nc, p_, c_, v_ in ops:
+        nnz = int(p_[-1])
+        if nnz < 200000:
+            continue
+        x = rng.uniform(-1, 1, nc)
+        gb = algorithmic_bytes(nr, nc, nnz, "spmv") / 1e9
+        best = None
+        for lanes in (1, 2, 4, 8, 16, 32):
+            for nnz_cap, cps, stages in ((2048, 4, 2), (1024, 4, 4), (4096, 2, 2), (1024, 6, 2), (2048, 3, 3)):
+                ctx.set_option("lanes", lanes)
+                ctx.set_option("nnz_cap", nnz_cap)
+                ctx.set_option("ctas_per_sm", cps)
+                ctx.set_option("stages", stages)
+                A = ctx.csr(nr, nc, p_, c_, v_)
+                vx, vy = ctx.vector(x), ctx.vector(nr)
+                med, mn = time_op(lambda: ctx.spmv(1.0, A, vx, 0.0, vy), reps=10)
+                rec = {"op": name, "rows": nr, "cols": nc, "nnz": nnz, "avg": round(nnz / nr, 1),
+                       "lanes": lanes, "nnz_cap": nnz_cap, "cps": cps, "stages": stages,
+                       "ms": round(med, 4), "GBs": round(gb / (med * 1e-3), 1)}
+                print(json.dumps(rec), flush=True)
+                if best is None or rec["GBs"] > best["GBs"]:
+                    best = rec
+                del A, vx, vy
+        print(json.dumps({"BEST": best}), flush=True)
+
+
 if __name__ == "__main__":
     cmd = sys.argv[1] if len(sys.argv) > 1 else "parity"
     if cmd == "parity":
         cmd_parity()
     elif cmd == "spmv":
         cmd_spmv(int(sys.argv[2]) if len(sys.argv) > 2 else 128)
+    elif cmd == "levels":
+        cmd_levels(int(sys.argv[2]) if len(sys.argv) > 2 else 128)

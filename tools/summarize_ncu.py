@@ -1,0 +1,117 @@
+#!/usr/bin/env python
+"""Turn the ncu artefacts a gpurun call brought back into the tracked summaries under profiles/.
+
+    python tools/summarize_ncu.py <round-tag> <launches.csv> <full.ncu-rep>
+
+Writes profiles/<tag>_launches.csv (copy), profiles/<tag>_launch_shares.md,
+profiles/<tag>_csr_kernels.md (per-kernel metrics of the --set full capture) and
+profiles/traffic.json (DRAM bytes per launch of the dominant kernel, read by bench.py)."""
+import collections
+import csv
+import io
+import json
+import os
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PROF = os.path.join(ROOT, "profiles")
+
+
+def launch_shares(tag, path):
+    rows = list(csv.reader(open(path)))
+    hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
+    hdr = rows[hi]
+    data = [r for r in rows[hi + 1:] if len(r) == len(hdr)]
+    kn, mv = hdr.index("Kernel Name"), hdr.index("Metric Value")
+    agg = collections.OrderedDict()
+    tot = 0.0
+    for r in data:
+        key = r[kn].split("(")[0].replace("void ", "")
+        t = float(r[mv].replace(",", ""))
+        a = agg.setdefault(key, [0, 0.0])
+        a[0] += 1
+        a[1] += t
+        tot += t
+    out = ["# %s: ncu launch list (gpu__time_duration.sum, --clock-control none)" % tag, "",
+           "Command: `ncu --metrics gpu__time_duration.sum --clock-control none -s 900 -c 400 --csv "
+           "python tools/profile_target.py 256 1` (setup launches skipped; %d launches of the first "
+           "solve captured, %.2f ms of kernel time).  Per-launch times under ncu are cold-cache and "
+           "serialised: compare SHARES." % (len(data), tot / 1e6), "",
+           "Template arguments of csr_ring_kernel<MODE, L>: MODE 0 spmv(beta=0), 1 spmv(beta!=0), "
+           "2 residual, 3 fused relax; L = lanes per row (L=1 is the finest level A and P).", "",
+           "| kernel | launches | total us | share | avg us |", "|---|---:|---:|---:|---:|"]
+    for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        out.append("| `%s` | %d | %.1f | %.1f%% | %.2f |" % (k, n, t / 1e3, 100 * t / tot, t / n / 1e3))
+    finest = sum(t for k, (n, t) in agg.items() if k.startswith("csr_ring_kernel<") and
+                 k.endswith(", 1>") and not k.startswith("csr_ring_kernel<1"))
+    out += ["", "Finest-level A passes (`csr_ring_kernel<0|2|3, 1>`): %.1f%% of the captured kernel time."
+            % (100 * finest / tot)]
+    open(os.path.join(PROF, tag + "_launch_shares.md"), "w").write("\n".join(out) + "\n")
+    shutil.copy(path, os.path.join(PROF, tag + "_launches.csv"))
+
+
+WANT = [("gpu__time_duration.sum", "time"), ("launch__grid_size", "grid"),
+        ("launch__registers_per_thread", "regs"),
+        ("dram__bytes_read.sum", "dram read"), ("dram__bytes_write.sum", "dram write"),
+        ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram %"),
+        ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2 %"),
+        ("l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "L1TEX %"),
+        ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM %"),
+        ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps active %"),
+        ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem bank conflicts"),
+        ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smem wavefronts"),
+        ("lts__t_sector_hit_rate.pct", "L2 hit %"), ("l1tex__t_sector_hit_rate.pct", "L1 hit %")]
+
+
+def full_capture(tag, rep):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE,
+                         stderr=subprocess.DEVNULL, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    kn = hdr.index("Kernel Name")
+    out = ["# %s: ncu --set full capture of the CSR streaming kernels" % tag, "",
+           "Command: `ncu --set full --clock-control none --import-source on -k regex:csr_ring_kernel "
+           "-c 8 python tools/profile_target.py 256 1` (first 8 launches of the first solve: "
+           "residual on A0 twice, then R0, A1, R1, A2, ...).", "",
+           "| kernel | " + " | ".join(n for _, n in WANT) + " |",
+           "|---|" + "---:|" * len(WANT)]
+    traffic = None
+    for r in data:
+        cells = []
+        for key, _ in WANT:
+            if key in hdr:
+                i = hdr.index(key)
+                v = r[i]
+                try:
+                    v = "%.4g" % float(v.replace(",", ""))
+                except ValueError:
+                    pass
+                cells.append("%s %s" % (v, units[i]) if units[i] not in ("", "%") else v)
+            else:
+                cells.append("n/a")
+        name = r[kn].split("(")[0].replace("void ", "")
+        out.append("| `%s` | " % name + " | ".join(cells) + " |")
+        if traffic is None and name == "csr_ring_kernel<2, 1>":
+            def val(key):
+                i = hdr.index(key)
+                scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[units[i]]
+                return float(r[i].replace(",", "")) * scale
+            rd, wr = val("dram__bytes_read.sum"), val("dram__bytes_write.sum")
+            traffic = {"kernel": "csr_ring_kernel<2, 1> (residual r = f - A x on the finest level, 256^3)",
+                       "dram_bytes_read": rd, "dram_bytes_write": wr,
+                       "dram_bytes_per_launch": rd + wr,
+                       "algorithmic_bytes_per_launch": 117047296 * 12 + 16777217 * 4 + 3 * 16777216 * 8,
+                       "source": "profiles/%s_csr_kernels.md (ncu --set full, one launch)" % tag}
+    open(os.path.join(PROF, tag + "_csr_kernels.md"), "w").write("\n".join(out) + "\n")
+    if traffic:
+        json.dump(traffic, open(os.path.join(PROF, "traffic.json"), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    os.makedirs(PROF, exist_ok=True)
+    tag = sys.argv[1]
+    launch_shares(tag, sys.argv[2])
+    if len(sys.argv) > 3:
+        full_capture(tag, sys.argv[3])
