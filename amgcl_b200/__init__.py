@@ -20,7 +20,8 @@ import numpy as np
 from . import build as _build
 
 __all__ = ["lib", "dropin_lib", "Context", "Vector", "Csr", "Coarse", "DropinSolver",
-           "poisson3d", "B200Error", "RELAX", "KRYLOV"]
+           "poisson3d", "B200Error", "RELAX", "KRYLOV", "nccl_unique_id", "partition",
+           "dist_split"]
 
 _c = ctypes
 _i64 = _c.c_int64
@@ -104,6 +105,16 @@ def lib():
         "b200_coarse_destroy": [_vp],
         "b200_coarse_bytes": [_vp, _P(_c.c_size_t)],
         "b200_coarse_solve": [_vp, _vp, _vp, _vp],
+        "b200_nccl_unique_id": [_c.c_char_p, _c.c_size_t],
+        "b200_dist_init": [_vp, _c.c_char_p, _c.c_size_t, _c.c_int, _c.c_int, _i64],
+        "b200_dist_info": [_vp, _P(_c.c_int), _P(_c.c_int), _P(_i64)],
+        "b200_partition": [_i64, _c.c_int, _c.c_int, _P(_i64), _P(_i64), _P(_i64)],
+        "b200_dist_split_i64": [_c.c_int, _c.c_int, _c.c_int, _i64, _i64, _vp, _vp, _vp, _P(_vp)],
+        "b200_split_info": [_vp, _P(_i64), _P(_i64), _P(_i64), _P(_i64), _P(_i64), _P(_i64)],
+        "b200_split_copy": [_vp, _vp, _vp, _vp, _vp],
+        "b200_split_destroy": [_vp],
+        "b200_plan_i64": [_i64, _vp, _c.c_int, _c.c_int, _vp, _i64, _P(_i64), _P(_c.c_int),
+                          _P(_c.c_int), _P(_i64)],
         "b200_profile_begin": [_vp],
         "b200_profile_end": [_vp, _vp, _i64, _P(_i64)],
     }
@@ -205,6 +216,14 @@ class Context:
 
     def reset_launches(self):
         _check(lib().b200_ctx_reset_launch_count(self.h))
+
+    # -- multi-GPU ---------------------------------------------------------
+    def dist_init(self, unique_id, nranks, rank, dist_min_rows):
+        """Join the NCCL communicator (one process per GPU).  Dimensions >= dist_min_rows
+        are partitioned across the ranks from now on (see include/amgcl_b200.h)."""
+        buf = _c.create_string_buffer(bytes(unique_id), 128)
+        _check(lib().b200_dist_init(self.h, buf, 128, int(nranks), int(rank), int(dist_min_rows)),
+               "b200_dist_init")
 
     def profile_begin(self):
         _check(lib().b200_profile_begin(self.h), "b200_profile_begin")
@@ -453,6 +472,46 @@ class DropinSolver:
             self.close()
         except Exception:
             pass
+
+
+def nccl_unique_id():
+    """128-byte NCCL id (call on rank 0, ship to the other ranks, pass to Context.dist_init)."""
+    buf = _c.create_string_buffer(128)
+    _check(lib().b200_nccl_unique_id(buf, 128), "b200_nccl_unique_id")
+    return bytes(buf.raw)
+
+
+def partition(n, nranks, rank):
+    """(block, lo, hi) of the uniform row-block partition the library uses."""
+    b, lo, hi = _i64(), _i64(), _i64()
+    _check(lib().b200_partition(int(n), int(nranks), int(rank), _c.byref(b), _c.byref(lo),
+                                _c.byref(hi)), "b200_partition")
+    return b.value, lo.value, hi.value
+
+
+def dist_split(kind, nranks, rank, nrows, ncols, ptr, col, val):
+    """Host view of one rank's share of an operator (kind: 'square' | 'prolong' | 'restrict').
+    Returns dict(nrows, ncols, n_loc, slots, ptr, col, val, send_idx)."""
+    k = {"square": 1, "prolong": 2, "restrict": 3}[kind]
+    ptr = np.ascontiguousarray(ptr, dtype=np.int64)
+    col = np.ascontiguousarray(col, dtype=np.int64)
+    val = _f64(val)
+    h = _vp()
+    _check(lib().b200_dist_split_i64(k, int(nranks), int(rank), int(nrows), int(ncols), _ptr(ptr),
+                                     _ptr(col), _ptr(val), _c.byref(h)), "b200_dist_split_i64")
+    try:
+        nr, nc, nnz, nl, S, ns = (_i64() for _ in range(6))
+        _check(lib().b200_split_info(h, _c.byref(nr), _c.byref(nc), _c.byref(nnz), _c.byref(nl),
+                                     _c.byref(S), _c.byref(ns)))
+        p = np.zeros(nr.value + 1, dtype=np.int64)
+        c = np.zeros(nnz.value, dtype=np.int64)
+        v = np.zeros(nnz.value, dtype=np.float64)
+        si = np.zeros(ns.value, dtype=np.int64)
+        _check(lib().b200_split_copy(h, _ptr(p), _ptr(c), _ptr(v), _ptr(si)))
+    finally:
+        lib().b200_split_destroy(h)
+    return {"nrows": nr.value, "ncols": nc.value, "n_loc": nl.value, "slots": S.value,
+            "ptr": p, "col": c, "val": v, "send_idx": si}
 
 
 def poisson3d(n, dtype_index=np.int64):

@@ -7,6 +7,7 @@
 #include "csr_kernels.cuh"
 #include "vec_kernels.cuh"
 #include "coarse_kernels.cuh"
+#include "dist.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -87,8 +88,10 @@ struct ProfScope {
 // Lazy clear bookkeeping ------------------------------------------------------
 static int materialize(b200_vec_t v) {
     if (v->zero_pending) {
-        ProfScope prof(v->ctx, B200_PROF_MEMSET, (int64_t)v->n, 1, 0);
-        B200_CUDA(cudaMemsetAsync(v->ptr, 0, v->n * sizeof(double), v->ctx->stream));
+        if (v->len) {
+            ProfScope prof(v->ctx, B200_PROF_MEMSET, (int64_t)v->len, 1, 0);
+            B200_CUDA(cudaMemsetAsync(v->ptr, 0, v->len * sizeof(double), v->ctx->stream));
+        }
         v->zero_pending = false;
     }
     return B200_OK;
@@ -119,6 +122,17 @@ static int grid_for(const b200_ctx_t ctx, size_t n_items, int per_thread_items) 
 using namespace b200;
 
 #define CHECK_CTX(ctx) B200_REQUIRE((ctx) != nullptr, "null context")
+#define B200_NCCL(call)                                                        \
+    do {                                                                       \
+        ncclResult_t rc__ = (call);                                            \
+        if (rc__ != ncclSuccess)                                               \
+            return fail(B200_ENCCL, std::string("NCCL error in " #call ": ") + \
+                                        nccl().GetErrorString(rc__));          \
+    } while (0)
+static inline ncclComm_t comm_of(b200_ctx_t ctx) { return static_cast<ncclComm_t>(ctx->comm); }
+static inline bool same_layout(b200_vec_t a, b200_vec_t b) {
+    return a->n == b->n && a->kind == b->kind && a->len == b->len;
+}
 #define GUARD(ctx)                                                             \
     DeviceGuard guard__((ctx)->device);                                        \
     if (!guard__.ok) return fail(B200_ECUDA, "cudaSetDevice failed")
@@ -165,6 +179,7 @@ extern "C" int b200_ctx_create(int device, b200_ctx_t *out) {
     B200_CUDA(cudaMemset(ctx->dot_ticket, 0, sizeof(unsigned int)));
     B200_CUDA(cudaHostAlloc(&ctx->dot_result_h, 8 * sizeof(double), cudaHostAllocMapped));
     B200_CUDA(cudaHostGetDevicePointer(&ctx->dot_result_d, ctx->dot_result_h, 0));
+    B200_CUDA(cudaMalloc(&ctx->dot_dev, 2 * sizeof(double)));
     *out = ctx;
     return B200_OK;
 }
@@ -176,6 +191,8 @@ extern "C" int b200_ctx_destroy(b200_ctx_t ctx) {
     if (ctx->dot_partial) cudaFree(ctx->dot_partial);
     if (ctx->dot_ticket) cudaFree(ctx->dot_ticket);
     if (ctx->dot_result_h) cudaFreeHost(ctx->dot_result_h);
+    if (ctx->dot_dev) cudaFree(ctx->dot_dev);
+    if (ctx->comm && nccl().handle) nccl().CommDestroy(comm_of(ctx));
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
     delete ctx;
@@ -280,6 +297,116 @@ extern "C" int b200_profile_end(b200_ctx_t ctx, b200_profile_entry *out, int64_t
     return B200_OK;
 }
 
+// ---------------------------------------------------------------------------
+// multi-GPU
+// ---------------------------------------------------------------------------
+extern "C" int b200_nccl_unique_id(char *id, size_t size) {
+    B200_REQUIRE(id != nullptr && size >= sizeof(ncclUniqueId), "id buffer must hold 128 bytes");
+    if (!nccl().load()) return fail(B200_ENCCL, nccl().error);
+    ncclUniqueId uid;
+    B200_NCCL(nccl().GetUniqueId(&uid));
+    memset(id, 0, size);
+    memcpy(id, &uid, sizeof(uid));
+    return B200_OK;
+}
+
+extern "C" int b200_dist_init(b200_ctx_t ctx, const char *id, size_t size, int nranks, int rank,
+                              int64_t dist_min_rows) {
+    CHECK_CTX(ctx);
+    B200_REQUIRE(id != nullptr && size >= sizeof(ncclUniqueId), "id buffer must hold 128 bytes");
+    B200_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank / nranks");
+    B200_REQUIRE(dist_min_rows >= 1, "dist_min_rows must be positive");
+    B200_REQUIRE(!ctx->dist, "context is already distributed");
+    GUARD(ctx);
+    if (!nccl().load()) return fail(B200_ENCCL, nccl().error);
+    ncclUniqueId uid;
+    memcpy(&uid, id, sizeof(uid));
+    ncclComm_t comm = nullptr;
+    B200_NCCL(nccl().CommInitRank(&comm, nranks, uid, rank));
+    ctx->comm = comm;
+    ctx->rank = rank;
+    ctx->nranks = nranks;
+    ctx->dist_min_rows = dist_min_rows;
+    ctx->dist = true;
+    return B200_OK;
+}
+
+extern "C" int b200_dist_info(b200_ctx_t ctx, int *rank, int *nranks, int64_t *dist_min_rows) {
+    CHECK_CTX(ctx);
+    if (rank) *rank = ctx->rank;
+    if (nranks) *nranks = ctx->nranks;
+    if (dist_min_rows) *dist_min_rows = ctx->dist ? ctx->dist_min_rows : 0;
+    return B200_OK;
+}
+
+// ---- pure host view of the partitioning (no device, no NCCL): for CPU tests ------------
+struct b200_split_s {
+    SplitMatrix m;
+    std::vector<double> val;
+    int kind;
+};
+
+extern "C" int b200_dist_split_i64(int kind, int nranks, int rank, int64_t nrows, int64_t ncols,
+                                   const int64_t *ptr, const int64_t *col, const double *val,
+                                   b200_split_t *out) {
+    B200_REQUIRE(out != nullptr && ptr != nullptr, "null argument");
+    B200_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank / nranks");
+    B200_REQUIRE(kind >= 1 && kind <= 3, "kind must be 1 (square), 2 (prolong) or 3 (restrict)");
+    b200_split_s *sp = new (std::nothrow) b200_split_s();
+    if (!sp) return fail(B200_ENOMEM, "out of host memory");
+    sp->kind = kind;
+    if (kind == B200_CK_SQUARE) {
+        if (nrows != ncols) { delete sp; return fail(B200_EINVAL, "square operator expected"); }
+        split_square(Partition(nrows, nranks), rank, ptr, col, sp->m);
+    } else if (kind == B200_CK_PROLONG) {
+        split_prolong(Partition(nrows, nranks), rank, ncols, ptr, col, sp->m);
+    } else {
+        split_restrict(Partition(ncols, nranks), rank, nrows, ptr, col, val, sp->m);
+    }
+    const int64_t nnz = sp->m.ptr.back();
+    if (sp->m.val_contiguous) sp->val.assign(val + sp->m.val_offset, val + sp->m.val_offset + nnz);
+    else sp->val = sp->m.val;
+    *out = sp;
+    return B200_OK;
+}
+
+extern "C" int b200_split_info(b200_split_t sp, int64_t *nrows, int64_t *ncols, int64_t *nnz,
+                               int64_t *n_loc, int64_t *slots, int64_t *n_send) {
+    B200_REQUIRE(sp != nullptr, "null argument");
+    if (nrows) *nrows = sp->m.nrows;
+    if (ncols) *ncols = sp->m.ncols;
+    if (nnz) *nnz = sp->m.ptr.back();
+    if (n_loc) *n_loc = sp->m.n_loc;
+    if (slots) *slots = sp->m.S;
+    if (n_send) *n_send = (int64_t)sp->m.send_idx.size();
+    return B200_OK;
+}
+
+extern "C" int b200_split_copy(b200_split_t sp, int64_t *ptr, int64_t *col, double *val,
+                               int64_t *send_idx) {
+    B200_REQUIRE(sp != nullptr, "null argument");
+    if (ptr) memcpy(ptr, sp->m.ptr.data(), sp->m.ptr.size() * sizeof(int64_t));
+    if (col) memcpy(col, sp->m.col.data(), sp->m.col.size() * sizeof(int64_t));
+    if (val) memcpy(val, sp->val.data(), sp->val.size() * sizeof(double));
+    if (send_idx) memcpy(send_idx, sp->m.send_idx.data(), sp->m.send_idx.size() * sizeof(int64_t));
+    return B200_OK;
+}
+
+extern "C" int b200_split_destroy(b200_split_t sp) {
+    delete sp;
+    return B200_OK;
+}
+
+extern "C" int b200_partition(int64_t n, int nranks, int rank, int64_t *block, int64_t *lo,
+                              int64_t *hi) {
+    B200_REQUIRE(n >= 0 && nranks >= 1 && rank >= 0 && rank < nranks, "bad argument");
+    const Partition part(n, nranks);
+    if (block) *block = part.B;
+    if (lo) *lo = part.lo(rank);
+    if (hi) *hi = part.hi(rank);
+    return B200_OK;
+}
+
 static int64_t *option_slot(b200_ctx_t ctx, const char *key) {
     if (!key) return nullptr;
     if (!strcmp(key, "spmv_variant")) return &ctx->opt_spmv_variant;
@@ -335,11 +462,38 @@ extern "C" int b200_vec_create(b200_ctx_t ctx, size_t n, b200_vec_t *out) {
     v->ctx = ctx;
     v->n = n;
     v->owned = true;
+    if (ctx->dist && (int64_t)n >= ctx->dist_min_rows) {
+        const Partition part((int64_t)n, ctx->nranks);
+        v->kind = B200_VK_DIST;
+        v->off = (size_t)part.lo(ctx->rank);
+        v->len = (size_t)part.count(ctx->rank);
+        v->cap = (size_t)part.B;
+    } else if (ctx->dist && ctx->rank != 0) {
+        v->kind = B200_VK_GHOST;      // the object lives on rank 0; operations here are no-ops
+        v->len = 0;
+        v->cap = 0;
+        v->zero_pending = false;
+        *out = v;
+        return B200_OK;
+    } else {
+        v->kind = B200_VK_LOCAL;
+        v->len = n;
+        v->cap = n;
+    }
     // +2 doubles of padding so 16-byte vector accesses of the tail stay in bounds
-    cudaError_t rc = cudaMalloc(&v->ptr, (n + 2) * sizeof(double));
+    cudaError_t rc = cudaMalloc(&v->ptr, (v->cap + 2) * sizeof(double));
     if (rc != cudaSuccess) {
         delete v;
         return cuda_fail(rc, "cudaMalloc(vector)", __FILE__, __LINE__);
+    }
+    if (v->cap > v->len) {
+        // padding of a partial block takes part in collectives: keep it zero
+        rc = cudaMemsetAsync(v->ptr + v->len, 0, (v->cap - v->len) * sizeof(double), ctx->stream);
+        if (rc != cudaSuccess) {
+            cudaFree(v->ptr);
+            delete v;
+            return cuda_fail(rc, "cudaMemsetAsync(vector padding)", __FILE__, __LINE__);
+        }
     }
     v->zero_pending = true;   // logically zero; memset only if somebody looks
     *out = v;
@@ -351,10 +505,13 @@ extern "C" int b200_vec_wrap(b200_ctx_t ctx, double *device_ptr, size_t n, b200_
     B200_REQUIRE(out != nullptr, "null output pointer");
     B200_REQUIRE(device_ptr != nullptr || n == 0, "null device pointer");
     B200_REQUIRE((reinterpret_cast<uintptr_t>(device_ptr) & 7) == 0, "device pointer not 8-byte aligned");
+    B200_REQUIRE(!ctx->dist, "b200_vec_wrap is not available on a distributed context");
     b200_vec_s *v = new (std::nothrow) b200_vec_s();
     if (!v) return fail(B200_ENOMEM, "out of host memory");
     v->ctx = ctx;
     v->n = n;
+    v->len = n;
+    v->cap = n;
     v->ptr = device_ptr;
     v->owned = false;
     v->zero_pending = false;
@@ -381,7 +538,7 @@ extern "C" int b200_vec_size(b200_vec_t v, size_t *n) {
 
 extern "C" int b200_vec_bytes(b200_vec_t v, size_t *bytes) {
     B200_REQUIRE(v && bytes, "null argument");
-    *bytes = v->n * sizeof(double);
+    *bytes = v->len * sizeof(double);
     return B200_OK;
 }
 
@@ -397,9 +554,11 @@ extern "C" int b200_vec_upload(b200_vec_t v, const double *host, size_t n) {
     B200_REQUIRE(v && (host || n == 0), "null argument");
     B200_REQUIRE(n == v->n, "size mismatch in vector upload");
     GUARD(v->ctx);
-    if (n) {
-        B200_CUDA(cudaMemcpyAsync(wr(v), host, n * sizeof(double), cudaMemcpyHostToDevice,
-                                  v->ctx->stream));
+    if (v->kind == B200_VK_GHOST) return B200_OK;
+    if (v->len) {
+        // distributed: every rank is handed the full host vector and keeps its block
+        B200_CUDA(cudaMemcpyAsync(wr(v), host + v->off, v->len * sizeof(double),
+                                  cudaMemcpyHostToDevice, v->ctx->stream));
         B200_CUDA(cudaStreamSynchronize(v->ctx->stream));
     }
     v->zero_pending = false;
@@ -409,16 +568,37 @@ extern "C" int b200_vec_upload(b200_vec_t v, const double *host, size_t n) {
 extern "C" int b200_vec_download(b200_vec_t v, double *host, size_t n) {
     B200_REQUIRE(v && (host || n == 0), "null argument");
     B200_REQUIRE(n == v->n, "size mismatch in vector download");
-    GUARD(v->ctx);
+    b200_ctx_t ctx = v->ctx;
+    GUARD(ctx);
     if (!n) return B200_OK;
-    if (v->zero_pending) {          // nothing to fetch: the vector is zero
-        B200_CUDA(cudaStreamSynchronize(v->ctx->stream));
+    if (v->kind == B200_VK_GHOST) {          // lives on rank 0 only
         memset(host, 0, n * sizeof(double));
         return B200_OK;
     }
-    B200_CUDA(cudaMemcpyAsync(host, v->ptr, n * sizeof(double), cudaMemcpyDeviceToHost,
-                              v->ctx->stream));
-    B200_CUDA(cudaStreamSynchronize(v->ctx->stream));
+    if (v->kind == B200_VK_DIST) {
+        // every rank receives the complete vector: all-gather the blocks, then one D2H copy
+        int rc = materialize(v);
+        if (rc) return rc;
+        double *full = nullptr;
+        B200_CUDA(cudaMalloc(&full, (size_t)ctx->nranks * v->cap * sizeof(double)));
+        ncclResult_t nrc = nccl().AllGather(v->ptr, full, v->cap, ncclDouble, comm_of(ctx), ctx->stream);
+        if (nrc != ncclSuccess) {
+            cudaFree(full);
+            return fail(B200_ENCCL, std::string("ncclAllGather: ") + nccl().GetErrorString(nrc));
+        }
+        cudaError_t crc = cudaMemcpyAsync(host, full, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+        if (crc == cudaSuccess) crc = cudaStreamSynchronize(ctx->stream);
+        cudaFree(full);
+        if (crc != cudaSuccess) return cuda_fail(crc, "download(distributed)", __FILE__, __LINE__);
+        return B200_OK;
+    }
+    if (v->zero_pending) {          // nothing to fetch: the vector is zero
+        B200_CUDA(cudaStreamSynchronize(ctx->stream));
+        memset(host, 0, n * sizeof(double));
+        return B200_OK;
+    }
+    B200_CUDA(cudaMemcpyAsync(host, v->ptr, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA(cudaStreamSynchronize(ctx->stream));
     return B200_OK;
 }
 
@@ -486,8 +666,11 @@ static void build_plan(int64_t nrows, const Ptr *ptr, int lanes_opt, int nnz_cap
     plan.blk.push_back(make_int2((int)nrows, (int)nnz));
 }
 
+// Upload one CSR matrix exactly as the kernels will see it (indices narrowed to int32,
+// row-block plan built).  Single-GPU matrices come straight through here; the
+// distributed kinds hand in the local part produced by dist.cuh.
 template <class Ptr, class Col>
-static int csr_create(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *ptr,
+static int csr_upload(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *ptr,
                       const Col *col, const double *val, b200_csr_t *out) {
     CHECK_CTX(ctx);
     B200_REQUIRE(out != nullptr, "null output pointer");
@@ -528,6 +711,7 @@ static int csr_create(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *p
     b200_csr_s *A = new (std::nothrow) b200_csr_s();
     if (!A) return fail(B200_ENOMEM, "out of host memory");
     A->ctx = ctx; A->nrows = nrows; A->ncols = ncols; A->nnz = nnz;
+    A->gl_rows = nrows; A->gl_cols = ncols; A->gl_nnz = nnz;
     A->lanes = lanes; A->rows_cap = rows_cap; A->nnz_cap = nnz_cap;
     A->nblocks = nblocks; A->nlong = nlong;
     // padding: bulk copies round sizes up to 16 bytes
@@ -573,19 +757,116 @@ static int csr_create(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *p
     return B200_OK;
 }
 
+static void csr_free(b200_csr_t A) {
+    if (!A) return;
+    if (A->ptr) cudaFree(A->ptr);
+    if (A->col) cudaFree(A->col);
+    if (A->val) cudaFree(A->val);
+    if (A->blk) cudaFree(A->blk);
+    if (A->send_idx) cudaFree(A->send_idx);
+    if (A->halo) cudaFree(A->halo);
+    if (A->cbuf) cudaFree(A->cbuf);
+    delete A;
+}
+
+// The public constructor: on a distributed context decide from the shape which
+// kind of operator this is (see dist.cuh) and keep only this rank's share.
+template <class Ptr, class Col>
+static int csr_create(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *ptr,
+                      const Col *col, const double *val, b200_csr_t *out) {
+    CHECK_CTX(ctx);
+    B200_REQUIRE(out != nullptr, "null output pointer");
+    *out = nullptr;
+    if (!ctx->dist) return csr_upload(ctx, nrows, ncols, ptr, col, val, out);
+
+    B200_REQUIRE(nrows >= 0 && ncols >= 0 && ptr != nullptr && ptr[0] == 0, "bad CSR input");
+    const int64_t nnz = (int64_t)ptr[nrows];
+    B200_REQUIRE(nnz == 0 || (col != nullptr && val != nullptr), "null col/val array");
+    const int64_t T = ctx->dist_min_rows;
+    const bool rd = nrows >= T, cd = ncols >= T;
+    int kind = B200_CK_LOCAL;
+    if (rd && cd && nrows == ncols) kind = B200_CK_SQUARE;
+    else if (rd && (!cd || nrows > ncols)) kind = B200_CK_PROLONG;
+    else if (cd && (!rd || ncols > nrows)) kind = B200_CK_RESTRICT;
+
+    if (kind == B200_CK_LOCAL) {
+        if (ctx->rank == 0) return csr_upload(ctx, nrows, ncols, ptr, col, val, out);
+        b200_csr_s *G = new (std::nothrow) b200_csr_s();     // ghost: lives on rank 0
+        if (!G) return fail(B200_ENOMEM, "out of host memory");
+        G->ctx = ctx; G->kind = B200_CK_GHOST;
+        G->gl_rows = nrows; G->gl_cols = ncols; G->gl_nnz = nnz;
+        *out = G;
+        return B200_OK;
+    }
+    for (int64_t e = 0; e < nnz; ++e)
+        if ((int64_t)col[e] < 0 || (int64_t)col[e] >= ncols)
+            return fail(B200_EINVAL, "column index out of range");
+    GUARD(ctx);
+
+    SplitMatrix sp;
+    const int P = ctx->nranks, rank = ctx->rank;
+    if (kind == B200_CK_SQUARE) split_square(Partition(nrows, P), rank, ptr, col, sp);
+    else if (kind == B200_CK_PROLONG) split_prolong(Partition(nrows, P), rank, ncols, ptr, col, sp);
+    else split_restrict(Partition(ncols, P), rank, nrows, ptr, col, val, sp);
+
+    b200_csr_t A = nullptr;
+    const double *lval = sp.val_contiguous ? val + sp.val_offset : sp.val.data();
+    int64_t kernel_cols = sp.ncols;
+    if (kind == B200_CK_PROLONG && cd) kernel_cols = Partition(ncols, P).B * P;   // gathered blocks
+    int rc = csr_upload(ctx, sp.nrows, kernel_cols, sp.ptr.data(), sp.col.data(), lval, &A);
+    if (rc) return rc;
+    A->kind = kind;
+    A->gl_rows = nrows; A->gl_cols = ncols; A->gl_nnz = nnz;
+    A->n_loc = sp.n_loc;
+#define DCSR_CUDA(call)                                                        \
+    do {                                                                       \
+        cudaError_t rc__ = (call);                                             \
+        if (rc__ != cudaSuccess) {                                             \
+            csr_free(A);                                                       \
+            return cuda_fail(rc__, #call, __FILE__, __LINE__);                 \
+        }                                                                      \
+    } while (0)
+    if (kind == B200_CK_SQUARE) {
+        A->S = sp.S;
+        A->n_send = (int64_t)sp.send_idx.size();
+        std::vector<int32_t> idx(sp.send_idx.begin(), sp.send_idx.end());
+        DCSR_CUDA(cudaMalloc(&A->send_idx, std::max<size_t>(1, idx.size()) * sizeof(int)));
+        DCSR_CUDA(cudaMalloc(&A->halo, std::max<size_t>(2, (size_t)(P * sp.S)) * sizeof(double)));
+        DCSR_CUDA(cudaMemsetAsync(A->halo, 0, std::max<size_t>(2, (size_t)(P * sp.S)) * sizeof(double), ctx->stream));
+        if (!idx.empty())
+            DCSR_CUDA(cudaMemcpyAsync(A->send_idx, idx.data(), idx.size() * sizeof(int),
+                                      cudaMemcpyHostToDevice, ctx->stream));
+        A->bytes += idx.size() * sizeof(int) + (size_t)(P * sp.S) * sizeof(double);
+    } else {
+        // coarse-side buffer: gathered input of P, partial sums of R
+        const bool coarse_dist = (kind == B200_CK_PROLONG) ? cd : rd;
+        const int64_t nc = (kind == B200_CK_PROLONG) ? ncols : nrows;
+        A->coarse_dist = coarse_dist;
+        A->coarse_B = coarse_dist ? Partition(nc, P).B : nc;
+        A->cbuf_n = coarse_dist ? A->coarse_B * P : nc;
+        DCSR_CUDA(cudaMalloc(&A->cbuf, ((size_t)A->cbuf_n + 2) * sizeof(double)));
+        DCSR_CUDA(cudaMemsetAsync(A->cbuf, 0, ((size_t)A->cbuf_n + 2) * sizeof(double), ctx->stream));
+        A->bytes += (size_t)A->cbuf_n * sizeof(double);
+    }
+    DCSR_CUDA(cudaStreamSynchronize(ctx->stream));
+#undef DCSR_CUDA
+    *out = A;
+    return B200_OK;
+}
+
 // ---- launch one streaming pass over A ------------------------------------------------
-template <int MODE, int L>
-static int launch_csr_L(b200_ctx_t ctx, b200_csr_t A, const CsrArgs &args) {
+template <int MODE, int L, bool HALO>
+static int launch_csr_LH(b200_ctx_t ctx, b200_csr_t A, const CsrArgs &args) {
     const StageLayout lay = stage_layout(A->rows_cap, A->nnz_cap);
     if (ctx->opt_spmv_variant == 0) {
         const int smem = kHeaderBytes + lay.bytes;
         static bool attr_set[64] = {};   // per instantiation and device
         if (!attr_set[ctx->device & 63]) {
-            B200_CUDA(cudaFuncSetAttribute(csr_block_kernel<MODE, L>,
+            B200_CUDA(cudaFuncSetAttribute(csr_block_kernel<MODE, L, HALO>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             attr_set[ctx->device & 63] = true;
         }
-        csr_block_kernel<MODE, L><<<(unsigned)A->nblocks, kThreads, smem, ctx->stream>>>(args);
+        csr_block_kernel<MODE, L, HALO><<<(unsigned)A->nblocks, kThreads, smem, ctx->stream>>>(args);
     } else {
         int stages = (int)ctx->opt_stages;
         const int max_smem = 227 * 1024;
@@ -594,17 +875,23 @@ static int launch_csr_L(b200_ctx_t ctx, b200_csr_t A, const CsrArgs &args) {
         const int smem = kHeaderBytes + stages * lay.bytes;
         static bool attr_set[64] = {};
         if (!attr_set[ctx->device & 63]) {
-            B200_CUDA(cudaFuncSetAttribute(csr_ring_kernel<MODE, L>,
+            B200_CUDA(cudaFuncSetAttribute(csr_ring_kernel<MODE, L, HALO>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
             attr_set[ctx->device & 63] = true;
         }
         const int64_t cap = (int64_t)ctx->sm_count * ctx->opt_ctas_per_sm;
         const unsigned grid = (unsigned)std::min<int64_t>(A->nblocks, cap);
-        csr_ring_kernel<MODE, L><<<grid, kThreads, smem, ctx->stream>>>(args, stages);
+        csr_ring_kernel<MODE, L, HALO><<<grid, kThreads, smem, ctx->stream>>>(args, stages);
     }
     B200_CHECK_LAUNCH();
     ctx->launches++;
     return B200_OK;
+}
+
+template <int MODE, int L>
+static int launch_csr_L(b200_ctx_t ctx, b200_csr_t A, const CsrArgs &args) {
+    if (args.xh) return launch_csr_LH<MODE, L, true>(ctx, A, args);
+    return launch_csr_LH<MODE, L, false>(ctx, A, args);
 }
 
 template <int MODE>
@@ -652,6 +939,70 @@ static int launch_ew(b200_ctx_t ctx, size_t n, F f, const double *x, const doubl
 
 } // namespace b200
 
+namespace b200 {
+
+// SQUARE operators: make every rank's boundary values of x visible in A->halo.
+// One pack kernel + one in-place ncclAllGather (S doubles per rank) on the stream.
+static int halo_exchange(b200_ctx_t ctx, b200_csr_t A, const double *x) {
+    if (A->S == 0) return B200_OK;
+    ProfScope prof(ctx, B200_PROF_COMM, A->n_send, ctx->nranks, 0);
+    double *mine = A->halo + (size_t)ctx->rank * A->S;
+    if (A->n_send) {
+        const unsigned grid = (unsigned)((A->n_send + kThreads - 1) / kThreads);
+        halo_pack_kernel<<<grid, kThreads, 0, ctx->stream>>>(A->n_send, A->send_idx, x, mine);
+        B200_CHECK_LAUNCH();
+        ctx->launches++;
+    }
+    B200_NCCL(nccl().AllGather(mine, A->halo, (size_t)A->S, ncclDouble, comm_of(ctx), ctx->stream));
+    return B200_OK;
+}
+
+// PROLONG operators: bring the coarse vector to every rank; returns the pointer to gather from.
+static int coarse_to_all(b200_ctx_t ctx, b200_csr_t A, b200_vec_t xc, const double **px) {
+    ProfScope prof(ctx, B200_PROF_COMM, A->gl_cols, ctx->nranks, 1);
+    if (A->coarse_dist) {
+        B200_REQUIRE(xc->kind == B200_VK_DIST && (int64_t)xc->cap == A->coarse_B,
+                     "prolongation: coarse vector is not partitioned like the operator");
+        int rc = materialize(xc);
+        if (rc) return rc;
+        B200_NCCL(nccl().AllGather(xc->ptr, A->cbuf, (size_t)A->coarse_B, ncclDouble, comm_of(ctx), ctx->stream));
+        *px = A->cbuf;
+        return B200_OK;
+    }
+    if (ctx->rank == 0) {
+        B200_REQUIRE(xc->kind == B200_VK_LOCAL, "prolongation: coarse vector must live on rank 0");
+        int rc = materialize(xc);
+        if (rc) return rc;
+        B200_NCCL(nccl().Broadcast(xc->ptr, xc->ptr, (size_t)A->gl_cols, ncclDouble, 0, comm_of(ctx), ctx->stream));
+        *px = xc->ptr;
+    } else {
+        B200_NCCL(nccl().Broadcast(A->cbuf, A->cbuf, (size_t)A->gl_cols, ncclDouble, 0, comm_of(ctx), ctx->stream));
+        *px = A->cbuf;
+    }
+    return B200_OK;
+}
+
+// RESTRICT operators: combine the per-rank partial sums in A->cbuf into the coarse vector.
+static int partials_to_coarse(b200_ctx_t ctx, b200_csr_t A, b200_vec_t yc) {
+    ProfScope prof(ctx, B200_PROF_COMM, A->gl_rows, ctx->nranks, 2);
+    if (A->coarse_dist) {
+        B200_REQUIRE(yc->kind == B200_VK_DIST && (int64_t)yc->cap == A->coarse_B,
+                     "restriction: coarse vector is not partitioned like the operator");
+        B200_NCCL(nccl().ReduceScatter(A->cbuf, wr(yc), (size_t)A->coarse_B, ncclDouble, ncclSum,
+                                       comm_of(ctx), ctx->stream));
+        return B200_OK;
+    }
+    double *dst = A->cbuf;
+    if (ctx->rank == 0) {
+        B200_REQUIRE(yc->kind == B200_VK_LOCAL, "restriction: coarse vector must live on rank 0");
+        dst = wr(yc);
+    }
+    B200_NCCL(nccl().Reduce(A->cbuf, dst, (size_t)A->gl_rows, ncclDouble, ncclSum, 0, comm_of(ctx), ctx->stream));
+    return B200_OK;
+}
+
+} // namespace b200
+
 extern "C" int b200_csr_create_i64(b200_ctx_t ctx, int64_t nrows, int64_t ncols,
                                    const int64_t *ptr, const int64_t *col, const double *val,
                                    b200_csr_t *A) {
@@ -690,27 +1041,23 @@ extern "C" int b200_plan_i64(int64_t nrows, const int64_t *ptr, int lanes, int n
 extern "C" int b200_csr_destroy(b200_csr_t A) {
     if (!A) return B200_OK;
     GUARD(A->ctx);
-    if (A->ptr) cudaFree(A->ptr);
-    if (A->col) cudaFree(A->col);
-    if (A->val) cudaFree(A->val);
-    if (A->blk) cudaFree(A->blk);
-    delete A;
+    csr_free(A);
     return B200_OK;
 }
 
 extern "C" int b200_csr_rows(b200_csr_t A, size_t *n) {
     B200_REQUIRE(A && n, "null argument");
-    *n = (size_t)A->nrows;
+    *n = (size_t)A->gl_rows;
     return B200_OK;
 }
 extern "C" int b200_csr_cols(b200_csr_t A, size_t *n) {
     B200_REQUIRE(A && n, "null argument");
-    *n = (size_t)A->ncols;
+    *n = (size_t)A->gl_cols;
     return B200_OK;
 }
 extern "C" int b200_csr_nonzeros(b200_csr_t A, size_t *n) {
     B200_REQUIRE(A && n, "null argument");
-    *n = (size_t)A->nnz;
+    *n = (size_t)A->gl_nnz;
     return B200_OK;
 }
 extern "C" int b200_csr_bytes(b200_csr_t A, size_t *bytes) {
@@ -734,14 +1081,38 @@ extern "C" int b200_spmv(b200_ctx_t ctx, double alpha, b200_csr_t A, b200_vec_t 
                          b200_vec_t y) {
     CHECK_CTX(ctx);
     B200_REQUIRE(A && x && y, "null argument");
-    B200_REQUIRE((int64_t)x->n == A->ncols, "spmv: x size != matrix columns");
-    B200_REQUIRE((int64_t)y->n == A->nrows, "spmv: y size != matrix rows");
-    B200_REQUIRE(x != y && x->ptr != y->ptr, "spmv: x and y must not alias");
+    B200_REQUIRE((int64_t)x->n == A->gl_cols, "spmv: x size != matrix columns");
+    B200_REQUIRE((int64_t)y->n == A->gl_rows, "spmv: y size != matrix rows");
+    B200_REQUIRE(x != y && (x->ptr != y->ptr || !x->ptr), "spmv: x and y must not alias");
+    if (A->kind == B200_CK_GHOST) return B200_OK;          // operator lives on rank 0
     GUARD(ctx);
     CsrArgs a = base_args(A);
-    int rc = rd(x, &a.x);
-    if (rc) return rc;
     a.alpha = alpha; a.beta = beta;
+    int rc;
+    if (A->kind == B200_CK_PROLONG) {
+        B200_REQUIRE(y->kind == B200_VK_DIST, "prolongation: y must be a partitioned vector");
+        rc = coarse_to_all(ctx, A, x, &a.x);
+        if (rc) return rc;
+    } else if (A->kind == B200_CK_RESTRICT) {
+        B200_REQUIRE(beta == 0.0, "restriction on a distributed context needs beta == 0");
+        B200_REQUIRE(x->kind == B200_VK_DIST, "restriction: x must be a partitioned vector");
+        rc = rd(x, &a.x);
+        if (rc) return rc;
+        a.y = A->cbuf;
+        rc = launch_csr<MODE_SPMV>(ctx, A, a);
+        if (rc) return rc;
+        return partials_to_coarse(ctx, A, y);
+    } else {
+        rc = rd(x, &a.x);
+        if (rc) return rc;
+        if (A->kind == B200_CK_SQUARE) {
+            B200_REQUIRE(x->kind == B200_VK_DIST && y->kind == B200_VK_DIST,
+                         "spmv: vectors must be partitioned like the operator");
+            rc = halo_exchange(ctx, A, a.x);
+            if (rc) return rc;
+            a.xh = A->halo; a.nloc = (int)A->n_loc;
+        }
+    }
     if (beta == 0.0 || y->zero_pending) {
         a.y = wr(y);
         return launch_csr<MODE_SPMV>(ctx, A, a);
@@ -754,16 +1125,26 @@ extern "C" int b200_residual(b200_ctx_t ctx, b200_vec_t f, b200_csr_t A, b200_ve
                              b200_vec_t r) {
     CHECK_CTX(ctx);
     B200_REQUIRE(f && A && x && r, "null argument");
-    B200_REQUIRE((int64_t)x->n == A->ncols, "residual: x size != matrix columns");
-    B200_REQUIRE((int64_t)f->n == A->nrows && (int64_t)r->n == A->nrows,
+    B200_REQUIRE((int64_t)x->n == A->gl_cols, "residual: x size != matrix columns");
+    B200_REQUIRE((int64_t)f->n == A->gl_rows && (int64_t)r->n == A->gl_rows,
                  "residual: rhs/r size != matrix rows");
-    B200_REQUIRE(x != r && x->ptr != r->ptr, "residual: x and r must not alias");
+    B200_REQUIRE(x != r && (x->ptr != r->ptr || !x->ptr), "residual: x and r must not alias");
+    if (A->kind == B200_CK_GHOST) return B200_OK;
+    B200_REQUIRE(A->kind == B200_CK_LOCAL || A->kind == B200_CK_SQUARE,
+                 "residual: operator must be square");
     GUARD(ctx);
     CsrArgs a = base_args(A);
     int rc = rd(x, &a.x);
     if (rc) return rc;
     rc = rd(f, &a.f);
     if (rc) return rc;
+    if (A->kind == B200_CK_SQUARE) {
+        B200_REQUIRE(x->kind == B200_VK_DIST && f->kind == B200_VK_DIST && r->kind == B200_VK_DIST,
+                     "residual: vectors must be partitioned like the operator");
+        rc = halo_exchange(ctx, A, a.x);
+        if (rc) return rc;
+        a.xh = A->halo; a.nloc = (int)A->n_loc;
+    }
     a.y = (f == r) ? r->ptr : wr(r);   // r == f is fine: each row reads f[r] before writing
     return launch_csr<MODE_RESID>(ctx, A, a);
 }
@@ -771,6 +1152,7 @@ extern "C" int b200_residual(b200_ctx_t ctx, b200_vec_t f, b200_csr_t A, b200_ve
 extern "C" int b200_clear(b200_ctx_t ctx, b200_vec_t x) {
     CHECK_CTX(ctx);
     B200_REQUIRE(x, "null argument");
+    if (x->kind == B200_VK_GHOST) return B200_OK;
     if (ctx->opt_zero_shortcut) {
         x->zero_pending = true;
         return B200_OK;
@@ -783,35 +1165,58 @@ extern "C" int b200_clear(b200_ctx_t ctx, b200_vec_t x) {
 extern "C" int b200_copy(b200_ctx_t ctx, b200_vec_t x, b200_vec_t y) {
     CHECK_CTX(ctx);
     B200_REQUIRE(x && y, "null argument");
-    B200_REQUIRE(x->n == y->n, "copy: size mismatch");
-    if (x == y || x->ptr == y->ptr) return B200_OK;
+    B200_REQUIRE(same_layout(x, y), "copy: size mismatch");
+    if (x->kind == B200_VK_GHOST || x == y || x->ptr == y->ptr) return B200_OK;
     if (x->zero_pending) {
         y->zero_pending = true;
         return B200_OK;
     }
     GUARD(ctx);
-    return launch_ew<CopyF, false, false>(ctx, x->n, CopyF(), x->ptr, nullptr, nullptr, wr(y));
+    return launch_ew<CopyF, false, false>(ctx, x->len, CopyF(), x->ptr, nullptr, nullptr, wr(y));
 }
 
 extern "C" int b200_dot(b200_ctx_t ctx, b200_vec_t x, b200_vec_t y, double *result) {
     CHECK_CTX(ctx);
     B200_REQUIRE(x && y && result, "null argument");
-    B200_REQUIRE(x->n == y->n, "dot: size mismatch");
+    B200_REQUIRE(same_layout(x, y), "dot: size mismatch");
     GUARD(ctx);
-    if (x->n == 0 || x->zero_pending || y->zero_pending) {
+    const bool dist = x->kind == B200_VK_DIST;
+    const bool trivial = x->len == 0 || x->zero_pending || y->zero_pending || x->kind == B200_VK_GHOST;
+    if (!dist) {
+        if (trivial) {
+            B200_CUDA(cudaStreamSynchronize(ctx->stream));
+            *result = 0.0;
+            return B200_OK;
+        }
+        const bool vec_ok = aligned16(x->ptr) && aligned16(y->ptr);
+        int grid = std::min(grid_for(ctx, x->len, 8), kDotMaxBlocks);
+        {
+            ProfScope prof(ctx, B200_PROF_DOT, (int64_t)x->len, 1, 0);
+            dot_kernel<<<grid, kThreads, 0, ctx->stream>>>(x->len, x->ptr, y->ptr, ctx->dot_partial,
+                                                           ctx->dot_ticket, ctx->dot_result_d, vec_ok);
+        }
+        B200_CHECK_LAUNCH();
+        ctx->launches++;
         B200_CUDA(cudaStreamSynchronize(ctx->stream));
-        *result = 0.0;
+        *result = *reinterpret_cast<volatile double *>(ctx->dot_result_h);
         return B200_OK;
     }
-    const bool vec_ok = aligned16(x->ptr) && aligned16(y->ptr);
-    int grid = std::min(grid_for(ctx, x->n, 8), kDotMaxBlocks);
-    {
-        ProfScope prof(ctx, B200_PROF_DOT, (int64_t)x->n, 1, 0);
-        dot_kernel<<<grid, kThreads, 0, ctx->stream>>>(x->n, x->ptr, y->ptr, ctx->dot_partial,
-                                                       ctx->dot_ticket, ctx->dot_result_d, vec_ok);
+    // partitioned vectors: local partial -> device scalar -> ncclAllReduce -> host
+    // (mpi/inner_product.hpp:53-62 does the same with MPI_Allreduce on the host)
+    if (trivial) {
+        B200_CUDA(cudaMemsetAsync(ctx->dot_dev, 0, sizeof(double), ctx->stream));
+    } else {
+        const bool vec_ok = aligned16(x->ptr) && aligned16(y->ptr);
+        int grid = std::min(grid_for(ctx, x->len, 8), kDotMaxBlocks);
+        ProfScope prof(ctx, B200_PROF_DOT, (int64_t)x->len, 1, 0);
+        dot_kernel<<<grid, kThreads, 0, ctx->stream>>>(x->len, x->ptr, y->ptr, ctx->dot_partial,
+                                                       ctx->dot_ticket, ctx->dot_dev, vec_ok);
+        B200_CHECK_LAUNCH();
+        ctx->launches++;
     }
-    B200_CHECK_LAUNCH();
-    ctx->launches++;
+    B200_NCCL(nccl().AllReduce(ctx->dot_dev, ctx->dot_dev, 1, ncclDouble, ncclSum, comm_of(ctx), ctx->stream));
+    B200_CUDA(cudaMemcpyAsync(ctx->dot_result_h, ctx->dot_dev, sizeof(double), cudaMemcpyDeviceToHost,
+                              ctx->stream));
     B200_CUDA(cudaStreamSynchronize(ctx->stream));
     *result = *reinterpret_cast<volatile double *>(ctx->dot_result_h);
     return B200_OK;
@@ -820,24 +1225,26 @@ extern "C" int b200_dot(b200_ctx_t ctx, b200_vec_t x, b200_vec_t y, double *resu
 extern "C" int b200_axpby(b200_ctx_t ctx, double a, b200_vec_t x, double b, b200_vec_t y) {
     CHECK_CTX(ctx);
     B200_REQUIRE(x && y, "null argument");
-    B200_REQUIRE(x->n == y->n, "axpby: size mismatch");
+    B200_REQUIRE(same_layout(x, y), "axpby: size mismatch");
+    if (x->kind == B200_VK_GHOST) return B200_OK;
     GUARD(ctx);
     const double *px;
     int rc = rd(x, &px);
     if (rc) return rc;
     if (b == 0.0 || y->zero_pending) {
         AxF f{a};
-        return launch_ew<AxF, false, false>(ctx, x->n, f, px, nullptr, nullptr, wr(y));
+        return launch_ew<AxF, false, false>(ctx, x->len, f, px, nullptr, nullptr, wr(y));
     }
     AxpbyF f{a, b};
-    return launch_ew<AxpbyF, true, false>(ctx, x->n, f, px, y->ptr, nullptr, y->ptr);
+    return launch_ew<AxpbyF, true, false>(ctx, x->len, f, px, y->ptr, nullptr, y->ptr);
 }
 
 extern "C" int b200_axpbypcz(b200_ctx_t ctx, double a, b200_vec_t x, double b, b200_vec_t y,
                              double c, b200_vec_t z) {
     CHECK_CTX(ctx);
     B200_REQUIRE(x && y && z, "null argument");
-    B200_REQUIRE(x->n == y->n && x->n == z->n, "axpbypcz: size mismatch");
+    B200_REQUIRE(same_layout(x, y) && same_layout(x, z), "axpbypcz: size mismatch");
+    if (x->kind == B200_VK_GHOST) return B200_OK;
     GUARD(ctx);
     const double *px, *py;
     int rc = rd(x, &px);
@@ -846,17 +1253,18 @@ extern "C" int b200_axpbypcz(b200_ctx_t ctx, double a, b200_vec_t x, double b, b
     if (rc) return rc;
     if (c == 0.0 || z->zero_pending) {
         AxpbyZF f{a, b};
-        return launch_ew<AxpbyZF, true, false>(ctx, x->n, f, px, py, nullptr, wr(z));
+        return launch_ew<AxpbyZF, true, false>(ctx, x->len, f, px, py, nullptr, wr(z));
     }
     AxpbypczF f{a, b, c};
-    return launch_ew<AxpbypczF, true, true>(ctx, x->n, f, px, py, z->ptr, z->ptr);
+    return launch_ew<AxpbypczF, true, true>(ctx, x->len, f, px, py, z->ptr, z->ptr);
 }
 
 extern "C" int b200_vmul(b200_ctx_t ctx, double alpha, b200_vec_t x, b200_vec_t y, double beta,
                          b200_vec_t z) {
     CHECK_CTX(ctx);
     B200_REQUIRE(x && y && z, "null argument");
-    B200_REQUIRE(x->n == y->n && x->n == z->n, "vmul: size mismatch");
+    B200_REQUIRE(same_layout(x, y) && same_layout(x, z), "vmul: size mismatch");
+    if (x->kind == B200_VK_GHOST) return B200_OK;
     GUARD(ctx);
     const double *px, *py;
     int rc = rd(x, &px);
@@ -865,10 +1273,10 @@ extern "C" int b200_vmul(b200_ctx_t ctx, double alpha, b200_vec_t x, b200_vec_t 
     if (rc) return rc;
     if (beta == 0.0 || z->zero_pending) {
         VmulF f{alpha};
-        return launch_ew<VmulF, true, false>(ctx, x->n, f, px, py, nullptr, wr(z));
+        return launch_ew<VmulF, true, false>(ctx, x->len, f, px, py, nullptr, wr(z));
     }
     VmulAccF f{alpha, beta};
-    return launch_ew<VmulAccF, true, true>(ctx, x->n, f, px, py, z->ptr, z->ptr);
+    return launch_ew<VmulAccF, true, true>(ctx, x->len, f, px, py, z->ptr, z->ptr);
 }
 
 // ---------------------------------------------------------------------------
@@ -878,12 +1286,13 @@ extern "C" int b200_relax(b200_ctx_t ctx, b200_csr_t A, b200_vec_t rhs, b200_vec
                           b200_vec_t tmp, b200_vec_t diag, double omega) {
     CHECK_CTX(ctx);
     B200_REQUIRE(A && rhs && x && tmp && diag, "null argument");
-    B200_REQUIRE(A->nrows == A->ncols, "relax: matrix must be square");
-    B200_REQUIRE((int64_t)x->n == A->nrows && (int64_t)rhs->n == A->nrows &&
-                     (int64_t)diag->n == A->nrows && (int64_t)tmp->n == A->nrows,
+    B200_REQUIRE(A->gl_rows == A->gl_cols, "relax: matrix must be square");
+    B200_REQUIRE((int64_t)x->n == A->gl_rows && same_layout(x, rhs) && same_layout(x, diag) &&
+                     same_layout(x, tmp),
                  "relax: vector size != matrix rows");
-    B200_REQUIRE(x != tmp && x->ptr != tmp->ptr && x != rhs && tmp != rhs,
-                 "relax: x, tmp and rhs must be distinct vectors");
+    B200_REQUIRE(x != tmp && x != rhs && tmp != rhs, "relax: x, tmp and rhs must be distinct vectors");
+    if (A->kind == B200_CK_GHOST) return B200_OK;
+    B200_REQUIRE(x->ptr != tmp->ptr, "relax: x and tmp must not alias");
     GUARD(ctx);
     const double *pf, *pd;
     int rc = rd(rhs, &pf);
@@ -893,11 +1302,14 @@ extern "C" int b200_relax(b200_ctx_t ctx, b200_csr_t A, b200_vec_t rhs, b200_vec
 
     if (x->zero_pending && ctx->opt_zero_shortcut) {
         // residual(rhs, A, 0) == rhs exactly, so the sweep reduces to a scaling
-        const int grid = grid_for(ctx, x->n, 2);
-        ProfScope prof(ctx, B200_PROF_RELAX_ZERO, (int64_t)x->n, 1, 0);
-        relax_zero_kernel<<<grid, kThreads, 0, ctx->stream>>>(x->n, omega, pd, pf, wr(x));
-        B200_CHECK_LAUNCH();
-        ctx->launches++;
+        if (x->len) {
+            const int grid = grid_for(ctx, x->len, 2);
+            ProfScope prof(ctx, B200_PROF_RELAX_ZERO, (int64_t)x->len, 1, 0);
+            relax_zero_kernel<<<grid, kThreads, 0, ctx->stream>>>(x->len, omega, pd, pf, wr(x));
+            B200_CHECK_LAUNCH();
+            ctx->launches++;
+        }
+        x->zero_pending = false;
         return B200_OK;
     }
 
@@ -911,14 +1323,20 @@ extern "C" int b200_relax(b200_ctx_t ctx, b200_csr_t A, b200_vec_t rhs, b200_vec
     CsrArgs a = base_args(A);
     rc = rd(x, &a.x);
     if (rc) return rc;
+    if (A->kind == B200_CK_SQUARE) {
+        B200_REQUIRE(x->kind == B200_VK_DIST, "relax: vectors must be partitioned like the operator");
+        rc = halo_exchange(ctx, A, a.x);
+        if (rc) return rc;
+        a.xh = A->halo; a.nloc = (int)A->n_loc;
+    }
     a.f = pf; a.d = pd; a.alpha = omega;
     a.y = wr(tmp);
     rc = launch_csr<MODE_RELAX>(ctx, A, a);
     if (rc) return rc;
-    if (x->owned && tmp->owned) {
+    if (x->owned && tmp->owned && x->cap == tmp->cap) {
         std::swap(x->ptr, tmp->ptr);          // x now holds the new iterate
     } else {
-        B200_CUDA(cudaMemcpyAsync(x->ptr, tmp->ptr, x->n * sizeof(double),
+        B200_CUDA(cudaMemcpyAsync(x->ptr, tmp->ptr, x->len * sizeof(double),
                                   cudaMemcpyDeviceToDevice, ctx->stream));
     }
     return B200_OK;
@@ -940,6 +1358,13 @@ static int coarse_create(b200_ctx_t ctx, int64_t n, const Ptr *ptr, const Col *c
     const int64_t nnz = (int64_t)ptr[n];
     B200_REQUIRE(nnz >= 0 && (nnz == 0 || (col && val)), "bad col/val array");
     GUARD(ctx);
+    if (ctx->dist && ctx->rank != 0) {       // the coarsest level lives on rank 0
+        b200_coarse_s *G = new (std::nothrow) b200_coarse_s();
+        if (!G) return fail(B200_ENOMEM, "out of host memory");
+        G->ctx = ctx; G->n = n; G->ghost = true;
+        *out = G;
+        return B200_OK;
+    }
 
     std::vector<int32_t> hptr((size_t)n + 1), hcol((size_t)nnz);
     for (int64_t i = 0; i <= n; ++i) hptr[(size_t)i] = (int32_t)ptr[i];
@@ -1059,6 +1484,9 @@ extern "C" int b200_coarse_solve(b200_ctx_t ctx, b200_coarse_t S, b200_vec_t rhs
     CHECK_CTX(ctx);
     B200_REQUIRE(S && rhs && x, "null argument");
     B200_REQUIRE((int64_t)rhs->n == S->n && (int64_t)x->n == S->n, "coarse solve: size mismatch");
+    if (S->ghost) return B200_OK;
+    B200_REQUIRE(rhs->kind == B200_VK_LOCAL && x->kind == B200_VK_LOCAL,
+                 "coarse solve: vectors must live on this rank");
     B200_REQUIRE(rhs != x && rhs->ptr != x->ptr, "coarse solve: rhs and x must not alias");
     GUARD(ctx);
     const double *pr;

@@ -74,6 +74,14 @@ struct b200_ctx_s {
     struct ProfRec { int64_t nrows, ncols, nnz; int mode; size_t ev; };
     std::vector<ProfRec>      prof_recs;
 
+    // multi-GPU (dist.cuh): one process per GPU, this context's share of the job
+    bool     dist          = false;
+    int      rank          = 0;
+    int      nranks        = 1;
+    void    *comm          = nullptr;       // ncclComm_t
+    int64_t  dist_min_rows = 0;             // dimensions >= this are partitioned
+    double  *dot_dev       = nullptr;       // device scalar for the all-reduced dot product
+
     // tuning
     int64_t opt_spmv_variant  = 1;
     int64_t opt_fuse_relax    = 1;
@@ -84,10 +92,16 @@ struct b200_ctx_s {
     int64_t opt_stages        = 2;        // persistent variant: ring depth
 };
 
+enum { B200_VK_LOCAL = 0, B200_VK_DIST = 1, B200_VK_GHOST = 2 };
+
 struct b200_vec_s {
     b200_ctx_t ctx   = nullptr;
     double    *ptr   = nullptr;
-    size_t     n     = 0;
+    size_t     n     = 0;         // global length
+    size_t     len   = 0;         // elements stored on this rank (== n unless distributed)
+    size_t     off   = 0;         // global index of ptr[0]
+    size_t     cap   = 0;         // allocated elements (distributed: the uniform block)
+    int        kind  = B200_VK_LOCAL;
     bool       owned = true;
     // Lazy clear: the vector is logically zero but the memset has not been
     // issued.  Set by b200_clear, consumed by b200_relax (which then skips the
@@ -95,9 +109,24 @@ struct b200_vec_s {
     bool       zero_pending = false;
 };
 
+enum { B200_CK_LOCAL = 0, B200_CK_SQUARE = 1, B200_CK_PROLONG = 2, B200_CK_RESTRICT = 3,
+       B200_CK_GHOST = 4 };
+
 struct b200_csr_s {
     b200_ctx_t ctx   = nullptr;
-    int64_t    nrows = 0, ncols = 0, nnz = 0;
+    int64_t    nrows = 0, ncols = 0, nnz = 0;   // shape of the matrix the kernels see (local part)
+    // distributed operators (dist.cuh)
+    int        kind    = B200_CK_LOCAL;
+    int64_t    gl_rows = 0, gl_cols = 0, gl_nnz = 0;   // global shape (what the API reports)
+    int64_t    n_loc   = 0;       // SQUARE: owned rows == local columns
+    int64_t    S       = 0;       // SQUARE: halo slots per rank
+    int64_t    n_send  = 0;       // SQUARE: entries this rank contributes
+    int       *send_idx = nullptr;// SQUARE: [n_send] local indices to pack
+    double    *halo    = nullptr; // SQUARE: [nranks*S] all-gathered boundary values
+    double    *cbuf    = nullptr; // PROLONG: gathered coarse vector; RESTRICT: partial sums
+    int64_t    cbuf_n  = 0;
+    bool       coarse_dist = false;   // the coarse side of P/R is itself partitioned
+    int64_t    coarse_B = 0;          // its uniform block
     int       *ptr   = nullptr;   // [nrows+1] (+ padding) device
     int       *col   = nullptr;   // [nnz]     (+ padding) device
     double    *val   = nullptr;   // [nnz]     (+ padding) device
@@ -113,6 +142,7 @@ struct b200_csr_s {
 
 struct b200_coarse_s {
     b200_ctx_t ctx  = nullptr;
+    bool       ghost = false;     // multi-GPU: the coarsest level lives on rank 0
     int64_t    n    = 0;
     double    *Ainv = nullptr;    // [n*n] row-major device
     size_t     bytes = 0;

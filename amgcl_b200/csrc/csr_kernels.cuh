@@ -39,7 +39,9 @@ struct CsrArgs {
     int           nblocks;
     int           rows_cap;
     int           nnz_cap;
-    const double *x;      // gathered vector
+    const double *x;      // gathered vector (local columns)
+    const double *xh;     // halo values for columns >= nloc (multi-GPU), else nullptr
+    int           nloc;   // number of local columns when xh is set
     double       *y;      // output
     const double *f;      // rhs          (RESID, RELAX)
     const double *d;      // diagonal     (RELAX)
@@ -123,8 +125,18 @@ __device__ __forceinline__ void store_row(const CsrArgs &a, int r, double sum) {
     }
 }
 
+// ---- x[col]: local columns from the vector, remote ones from the all-gathered halo --
+template <bool HALO>
+__device__ __forceinline__ double gather(const CsrArgs &a, const double *__restrict__ x, int c) {
+    if (HALO) {
+        const double *p = (c < a.nloc) ? (x + c) : (a.xh + (c - a.nloc));
+        return __ldg(p);
+    }
+    return __ldg(x + c);
+}
+
 // ---- reduce the rows of a staged block out of shared memory ---------------------
-template <int MODE, int L>
+template <int MODE, int L, bool HALO>
 __device__ __forceinline__ void compute_staged(const CsrArgs &a, const BlockDesc &d,
                                                const char *stage, const StageLayout &lay) {
     const double *val_s = reinterpret_cast<const double *>(stage + lay.val_off);
@@ -156,10 +168,10 @@ __device__ __forceinline__ void compute_staged(const CsrArgs &a, const BlockDesc
                 const double v1 = p1 ? val_s[e1 - vo] : 0.0;
                 const double v2 = p2 ? val_s[e2 - vo] : 0.0;
                 const double v3 = p3 ? val_s[e3 - vo] : 0.0;
-                const double x0 = __ldg(x + c0);
-                const double x1 = __ldg(x + c1);
-                const double x2 = __ldg(x + c2);
-                const double x3 = __ldg(x + c3);
+                const double x0 = gather<HALO>(a, x, c0);
+                const double x1 = gather<HALO>(a, x, c1);
+                const double x2 = gather<HALO>(a, x, c2);
+                const double x3 = gather<HALO>(a, x, c3);
                 sum = fma(v0, x0, sum);
                 if (p1) sum = fma(v1, x1, sum);
                 if (p2) sum = fma(v2, x2, sum);
@@ -175,7 +187,7 @@ __device__ __forceinline__ void compute_staged(const CsrArgs &a, const BlockDesc
 }
 
 // ---- rows too long to stage: whole CTA strides over each row -----------------------
-template <int MODE>
+template <int MODE, bool HALO>
 __device__ __forceinline__ void compute_long(const CsrArgs &a, const BlockDesc &d,
                                              double *red_s /* >= 8 doubles */) {
     const double *__restrict__ x = a.x;
@@ -183,7 +195,7 @@ __device__ __forceinline__ void compute_long(const CsrArgs &a, const BlockDesc &
         const int beg = __ldg(a.ptr + r), end = __ldg(a.ptr + r + 1);
         double sum = 0.0;
         for (int e = beg + threadIdx.x; e < end; e += kThreads)
-            sum = fma(__ldg(a.val + e), __ldg(x + __ldg(a.col + e)), sum);
+            sum = fma(__ldg(a.val + e), gather<HALO>(a, x, __ldg(a.col + e)), sum);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
         __syncthreads();                       // red_s free from the previous row
@@ -199,7 +211,7 @@ __device__ __forceinline__ void compute_long(const CsrArgs &a, const BlockDesc &
 }
 
 // ---- variant 0: one row block per CTA -----------------------------------------------
-template <int MODE, int L>
+template <int MODE, int L, bool HALO>
 __global__ void __launch_bounds__(kThreads, 4) csr_block_kernel(const CsrArgs a) {
     extern __shared__ __align__(128) char smem[];
     uint64_t *bar   = reinterpret_cast<uint64_t *>(smem);
@@ -219,14 +231,14 @@ __global__ void __launch_bounds__(kThreads, 4) csr_block_kernel(const CsrArgs a)
         }
         __syncthreads();
         ptx::mbar_wait(bar, 0);
-        compute_staged<MODE, L>(a, d, stage, lay);
+        compute_staged<MODE, L, HALO>(a, d, stage, lay);
     } else {
-        compute_long<MODE>(a, d, red_s);
+        compute_long<MODE, HALO>(a, d, red_s);
     }
 }
 
 // ---- variant 1: persistent CTAs, S-deep ring of stages ----------------------------------
-template <int MODE, int L>
+template <int MODE, int L, bool HALO>
 __global__ void __launch_bounds__(kThreads, 2) csr_ring_kernel(const CsrArgs a, const int nstages) {
     extern __shared__ __align__(128) char smem[];
     uint64_t  *bars  = reinterpret_cast<uint64_t *>(smem);                 // [<=8]
@@ -258,9 +270,9 @@ __global__ void __launch_bounds__(kThreads, 2) csr_ring_kernel(const CsrArgs a, 
         ptx::mbar_wait(bars + s, parity);
         const BlockDesc d = descs[s];
         if ((d.e1 - d.e0) <= a.nnz_cap)
-            compute_staged<MODE, L>(a, d, stages + (size_t)s * lay.bytes, lay);
+            compute_staged<MODE, L, HALO>(a, d, stages + (size_t)s * lay.bytes, lay);
         else
-            compute_long<MODE>(a, d, red_s);
+            compute_long<MODE, HALO>(a, d, red_s);
         __syncthreads();                 // every thread is done with stage s (and descs[s])
         if (threadIdx.x == 0 && i + nstages < mine) {
             const BlockDesc n = load_desc(a, first + (i + nstages) * step);

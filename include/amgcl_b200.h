@@ -43,6 +43,7 @@ typedef struct b200_ctx_s    *b200_ctx_t;     /* device + stream + scratch      
 typedef struct b200_csr_s    *b200_csr_t;     /* device CSR matrix (+ row-block plan) */
 typedef struct b200_vec_s    *b200_vec_t;     /* device FP64 vector                   */
 typedef struct b200_coarse_s *b200_coarse_t;  /* coarsest-level direct solver         */
+typedef struct b200_split_s  *b200_split_t;   /* host view of one rank's operator share */
 
 /* ---------------------------------------------------------------- context */
 
@@ -88,6 +89,7 @@ int b200_ctx_reset_launch_count(b200_ctx_t ctx);
 #define B200_PROF_RELAX_ZERO  21   /* x = omega*diag.*rhs shortcut of the smoother     */
 #define B200_PROF_COARSE      22   /* dense GEMV of the coarsest-level solve           */
 #define B200_PROF_MEMSET      23   /* materialised lazy clear                          */
+#define B200_PROF_COMM        30   /* multi-GPU exchange (pack + NCCL collective)      */
 typedef struct {
     int64_t nrows, ncols, nnz;
     int     mode;
@@ -97,6 +99,43 @@ typedef struct {
 } b200_profile_entry;
 int b200_profile_begin(b200_ctx_t ctx);
 int b200_profile_end(b200_ctx_t ctx, b200_profile_entry *out, int64_t capacity, int64_t *count);
+
+/* ---------------------------------------------------------------- multi-GPU */
+
+/* One process per GPU (SPMD): every rank runs the same AMGCL program on the same
+ * host hierarchy; after b200_dist_init every vector / matrix dimension >=
+ * dist_min_rows is partitioned in uniform contiguous row blocks across the ranks,
+ * everything smaller lives on rank 0 (other ranks get no-op ghost handles).
+ * Replaces amgcl::mpi::distributed_matrix / comm_pattern / mpi::inner_product
+ * (amgcl/mpi/distributed_matrix.hpp:51-557, amgcl/mpi/inner_product.hpp:53-62)
+ * with NCCL collectives on device buffers:
+ *   A_l x        halo = one in-place ncclAllGather of packed boundary values
+ *   P_l u        ncclAllGather / ncclBroadcast of the coarse vector, local rows
+ *   R_l t        local columns, ncclReduceScatter / ncclReduce of partial sums
+ *   <x, y>       local kernel + ncclAllReduce of one double
+ * With dist_min_rows = rows of the finest matrix only the finest level is
+ * partitioned (the north-star configuration).  The id comes from
+ * b200_nccl_unique_id on rank 0 and is distributed by the caller (e.g. with
+ * torch.distributed). */
+int b200_nccl_unique_id(char *id, size_t size /* >= 128 */);
+int b200_dist_init(b200_ctx_t ctx, const char *id, size_t size, int nranks, int rank,
+                   int64_t dist_min_rows);
+int b200_dist_info(b200_ctx_t ctx, int *rank, int *nranks, int64_t *dist_min_rows);
+
+/* Pure host helpers (no device, no NCCL) exposing the partition logic to tests.
+ * b200_partition: uniform block size and this rank's [lo, hi) for a dimension.
+ * b200_dist_split_i64: rank's share of an operator; kind 1 = square (columns
+ * remapped to [local | halo slots]), 2 = prolongation (own rows), 3 = restriction
+ * (own columns).  slots = halo slots per rank, send_idx = local indices this rank
+ * contributes to the all-gathered halo, in slot order. */
+int b200_partition(int64_t n, int nranks, int rank, int64_t *block, int64_t *lo, int64_t *hi);
+int b200_dist_split_i64(int kind, int nranks, int rank, int64_t nrows, int64_t ncols,
+                        const int64_t *ptr, const int64_t *col, const double *val,
+                        b200_split_t *out);
+int b200_split_info(b200_split_t sp, int64_t *nrows, int64_t *ncols, int64_t *nnz,
+                    int64_t *n_loc, int64_t *slots, int64_t *n_send);
+int b200_split_copy(b200_split_t sp, int64_t *ptr, int64_t *col, double *val, int64_t *send_idx);
+int b200_split_destroy(b200_split_t sp);
 
 /* Tuning knobs (all optional; defaults are chosen for B200).
  *   "spmv_variant"     0 = one row block per CTA, 1 = persistent multi-stage ring (default)

@@ -1,0 +1,84 @@
+#!/usr/bin/env python
+"""Multi-GPU parity check (run under torchrun, one rank per GPU):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29511 tools/dist_check.py [n ...]
+
+Every rank runs the same AMGCL program (drop-in) on a distributed context; rank 0 compares
+iterations / residual / solution with the reference's known answers and, when shipped, with
+the live reference."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+rank = int(os.environ.get("RANK", "0"))
+world = int(os.environ.get("WORLD_SIZE", "1"))
+local = int(os.environ.get("LOCAL_RANK", "0"))
+os.environ.setdefault("OMP_NUM_THREADS", str(max(1, (os.cpu_count() or 8) // max(world, 1))))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import amgcl_b200 as ab  # noqa: E402
+
+
+def make_ctx(min_rows):
+    torch.cuda.set_device(local)
+    ctx = ab.Context(local)
+    if world > 1:
+        box = [ab.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        ctx.dist_init(box[0], world, rank, min_rows)
+    return ctx
+
+
+def main():
+    sizes = [int(a) for a in sys.argv[1:]] or [32, 64]
+    if world > 1:
+        dist.init_process_group("gloo")     # plumbing only: id exchange + barriers
+    known = json.load(open(os.path.join(ROOT, "tests", "golden", "known_answers.json")))["cases"]
+    ok = True
+    for n in sizes:
+        ptr, col, val, rhs = ab.poisson3d(n)
+        nrows = ptr.size - 1
+        for mode, min_rows in (("finest", nrows), ("all>=2000", 2000)):
+            for relax, krylov in (("damped_jacobi", "cg"), ("spai0", "bicgstab")):
+                ctx = make_ctx(min_rows)
+                S = ab.DropinSolver(ptr, col, val, relax, krylov, ctx=ctx)
+                x, it, res = S.solve(rhs)
+                case = [c for c in known if (c["n"], c["relax"], c["krylov"]) == (n, relax, krylov)]
+                rec = {"n": n, "world": world, "partitioned": mode, "relax": relax, "krylov": krylov,
+                       "iters": it, "resid": res}
+                if case:
+                    c = case[0]
+                    rec["ref_iters"] = c["iters"]
+                    rec["resid_rel_diff"] = abs(res - c["resid"]) / c["resid"]
+                    rec["x_norm_rel_diff"] = abs(np.linalg.norm(x) - c["x_norm2"]) / c["x_norm2"]
+                    good = (it == c["iters"] and rec["resid_rel_diff"] < 1e-6 and
+                            rec["x_norm_rel_diff"] < 1e-8)
+                    rec["ok"] = bool(good)
+                    ok = ok and good
+                # true residual computed on the host
+                import oracle
+                r = rhs - oracle.c().spmv(1.0, (ptr, col, val), x, 0.0, np.zeros_like(x))
+                rec["true_resid"] = float(np.linalg.norm(r) / np.linalg.norm(rhs))
+                ok = ok and rec["true_resid"] < 2e-8
+                if rank == 0:
+                    print(json.dumps(rec), flush=True)
+                S.close()
+                ctx.close()
+                if world > 1:
+                    dist.barrier()
+    if rank == 0:
+        print("DIST_CHECK", "PASS" if ok else "FAIL", flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
