@@ -44,7 +44,8 @@ class ProfileEntry(_c.Structure):
 
 
 MODE_NAMES = {0: "spmv", 1: "spmv_acc", 2: "residual", 3: "relax", 10: "vec1", 11: "vec2",
-              12: "vec3", 20: "dot", 21: "relax_zero", 22: "coarse_gemv", 23: "memset"}
+              12: "vec3", 20: "dot", 21: "relax_zero", 22: "coarse_gemv", 23: "memset",
+              30: "comm"}
 
 
 _lib = None
@@ -156,6 +157,9 @@ def dropin_lib():
     D.dropin_report.restype = _i64
     D.dropin_bytes.argtypes = [_vp]
     D.dropin_bytes.restype = _i64
+    D.dropin_set_num_threads.argtypes = [_c.c_int]
+    D.dropin_set_num_threads.restype = None
+    D.dropin_num_threads.restype = _c.c_int
     _dropin = D
     return D
 
@@ -472,6 +476,11 @@ class DropinSolver:
             self.close()
         except Exception:
             pass
+
+
+def set_setup_threads(n):
+    """OpenMP threads for AMGCL's host-side hierarchy setup inside the drop-in library."""
+    dropin_lib().dropin_set_num_threads(int(n))
 
 
 def nccl_unique_id():

@@ -1358,7 +1358,8 @@ static int coarse_create(b200_ctx_t ctx, int64_t n, const Ptr *ptr, const Col *c
     const int64_t nnz = (int64_t)ptr[n];
     B200_REQUIRE(nnz >= 0 && (nnz == 0 || (col && val)), "bad col/val array");
     GUARD(ctx);
-    if (ctx->dist && ctx->rank != 0) {       // the coarsest level lives on rank 0
+    const bool replicated = ctx->dist && n >= ctx->dist_min_rows;
+    if (ctx->dist && ctx->rank != 0 && !replicated) {       // the coarsest level lives on rank 0
         b200_coarse_s *G = new (std::nothrow) b200_coarse_s();
         if (!G) return fail(B200_ENOMEM, "out of host memory");
         G->ctx = ctx; G->n = n; G->ghost = true;
@@ -1451,6 +1452,19 @@ static int coarse_create(b200_ctx_t ctx, int64_t n, const Ptr *ptr, const Col *c
         return fail(B200_ENOMEM, "out of host memory");
     }
     S->ctx = ctx; S->n = n; S->Ainv = Ainv; S->bytes = (size_t)N * N * sizeof(double);
+    if (replicated) {
+        // the coarsest level is itself partitioned: every rank keeps the inverse and
+        // applies its own rows to the all-gathered right-hand side
+        S->replicated = true;
+        S->block = Partition(n, ctx->nranks).B;
+        cudaError_t rc = cudaMalloc(&S->gbuf, ((size_t)S->block * ctx->nranks + 2) * sizeof(double));
+        if (rc != cudaSuccess) {
+            cudaFree(Ainv);
+            delete S;
+            return cuda_fail(rc, "cudaMalloc(coarse gather buffer)", __FILE__, __LINE__);
+        }
+        S->bytes += (size_t)S->block * ctx->nranks * sizeof(double);
+    }
     *out = S;
     return B200_OK;
 }
@@ -1470,6 +1484,7 @@ extern "C" int b200_coarse_destroy(b200_coarse_t S) {
     if (!S) return B200_OK;
     GUARD(S->ctx);
     if (S->Ainv) cudaFree(S->Ainv);
+    if (S->gbuf) cudaFree(S->gbuf);
     delete S;
     return B200_OK;
 }
@@ -1485,18 +1500,36 @@ extern "C" int b200_coarse_solve(b200_ctx_t ctx, b200_coarse_t S, b200_vec_t rhs
     B200_REQUIRE(S && rhs && x, "null argument");
     B200_REQUIRE((int64_t)rhs->n == S->n && (int64_t)x->n == S->n, "coarse solve: size mismatch");
     if (S->ghost) return B200_OK;
+    GUARD(ctx);
+    const int N = (int)S->n;
+    const int warps_per_cta = kThreads / 32;
+    if (S->replicated) {
+        B200_REQUIRE(rhs->kind == B200_VK_DIST && x->kind == B200_VK_DIST &&
+                         (int64_t)rhs->cap == S->block && rhs != x,
+                     "coarse solve: vectors must be partitioned like the coarsest level");
+        int rc = materialize(rhs);
+        if (rc) return rc;
+        B200_NCCL(nccl().AllGather(rhs->ptr, S->gbuf, (size_t)S->block, ncclDouble, comm_of(ctx), ctx->stream));
+        const int nloc = (int)x->len;
+        if (nloc) {
+            ProfScope prof(ctx, B200_PROF_COARSE, nloc, S->n, (int64_t)nloc * S->n);
+            coarse_gemv_kernel<<<(nloc + warps_per_cta - 1) / warps_per_cta, kThreads, 0, ctx->stream>>>(
+                N, (int)x->off, nloc, S->Ainv, S->gbuf, wr(x));
+            B200_CHECK_LAUNCH();
+            ctx->launches++;
+        }
+        x->zero_pending = false;
+        return B200_OK;
+    }
     B200_REQUIRE(rhs->kind == B200_VK_LOCAL && x->kind == B200_VK_LOCAL,
                  "coarse solve: vectors must live on this rank");
     B200_REQUIRE(rhs != x && rhs->ptr != x->ptr, "coarse solve: rhs and x must not alias");
-    GUARD(ctx);
     const double *pr;
     int rc = rd(rhs, &pr);
     if (rc) return rc;
-    const int N = (int)S->n;
-    const int warps_per_cta = kThreads / 32;
     ProfScope prof(ctx, B200_PROF_COARSE, S->n, S->n, S->n * S->n);
     coarse_gemv_kernel<<<(N + warps_per_cta - 1) / warps_per_cta, kThreads, 0, ctx->stream>>>(
-        N, S->Ainv, pr, wr(x));
+        N, 0, N, S->Ainv, pr, wr(x));
     B200_CHECK_LAUNCH();
     ctx->launches++;
     return B200_OK;

@@ -108,14 +108,16 @@ __global__ void coarse_extract_kernel(int n, const double *__restrict__ M, doubl
     Ainv[idx] = M[r * 2 * n + n + c];
 }
 
-// x = Ainv * rhs : one warp per row, coalesced row reads, shuffle reduction
+// x[0:nloc) = Ainv[row0 : row0+nloc, :] * rhs : one warp per row, coalesced row reads,
+// shuffle reduction.  (row0, nloc) select this rank's rows when the coarsest level is
+// itself partitioned; single GPU: row0 = 0, nloc = n.
 __global__ void __launch_bounds__(kThreads)
-coarse_gemv_kernel(int n, const double *__restrict__ Ainv, const double *__restrict__ rhs,
-                   double *__restrict__ x) {
+coarse_gemv_kernel(int n, int row0, int nloc, const double *__restrict__ Ainv,
+                   const double *__restrict__ rhs, double *__restrict__ x) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (warp >= n) return;
-    const double *row = Ainv + (size_t)warp * n;
+    if (warp >= nloc) return;
+    const double *row = Ainv + (size_t)(row0 + warp) * n;
     double s = 0.0;
     for (int j = lane; j < n; j += 32) s = fma(row[j], rhs[j], s);
 #pragma unroll

@@ -143,6 +143,9 @@ struct b200_csr_s {
 struct b200_coarse_s {
     b200_ctx_t ctx  = nullptr;
     bool       ghost = false;     // multi-GPU: the coarsest level lives on rank 0
+    bool       replicated = false;// multi-GPU: coarsest level partitioned -> inverse on every rank
+    double    *gbuf = nullptr;    // replicated: all-gathered right-hand side [nranks * block]
+    int64_t    block = 0;
     int64_t    n    = 0;
     double    *Ainv = nullptr;    // [n*n] row-major device
     size_t     bytes = 0;

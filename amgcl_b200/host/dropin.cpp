@@ -17,6 +17,8 @@
 #include <tuple>
 #include <vector>
 
+#include <omp.h>
+
 #include <amgcl/backend/b200.hpp>
 #include <amgcl/adapter/crs_tuple.hpp>
 #include <amgcl/make_solver.hpp>
@@ -91,6 +93,11 @@ struct Handle {
 extern "C" {
 
 const char *dropin_last_error() { return g_error.c_str(); }
+
+// OpenMP threads used by AMGCL's host-side setup (launchers such as torchrun export
+// OMP_NUM_THREADS=1, which would serialise the coarsening).
+void dropin_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+int dropin_num_threads() { return omp_get_max_threads(); }
 
 // relax: 0 = damped_jacobi, 1 = spai0 ; krylov: 0 = cg, 1 = bicgstab
 // ctx: a b200_ctx_t or NULL for the library default

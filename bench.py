@@ -39,6 +39,10 @@ def parse_args():
     ap.add_argument("--relax", default="damped_jacobi", choices=["damped_jacobi", "spai0"])
     ap.add_argument("--krylov", default="cg", choices=["cg", "bicgstab"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--partition", default="all", choices=["finest", "all"],
+                    help="N>1: partition only the finest level (north star) or every level "
+                         "with at least --partition-min-rows rows")
+    ap.add_argument("--partition-min-rows", type=int, default=100000)
     ap.add_argument("--ref-sample-iters", type=int, default=4,
                     help="Krylov iterations per step of the CPU reference sample")
     return ap.parse_args()
@@ -220,11 +224,22 @@ def main_arm(args, rank, world, local_rank):
     side = torch.cuda.Stream(device=device)
     torch.cuda.set_stream(side)
     ctx = ab.Context(device, stream=side.cuda_stream)
+    # host-side setup threads: share the box between the ranks (torchrun exports 1)
+    ab.set_setup_threads(max(1, (os.cpu_count() or 8) // world))
 
     t0 = time.time()
     ptr, col, val, rhs = ab.poisson3d(args.n)
     t_gen = time.time() - t0
     nrows, nnz = int(ptr.size - 1), int(ptr[-1])
+
+    dist_min_rows = nrows
+    if world > 1:
+        # one system, row-partitioned across the GPUs: NCCL id from rank 0
+        box = [ab.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        if args.partition == "all":
+            dist_min_rows = args.partition_min_rows
+        ctx.dist_init(box[0], world, rank, dist_min_rows)
 
     t0 = time.time()
     S = ab.DropinSolver(ptr, col, val, args.relax, args.krylov, ctx=ctx)
@@ -260,15 +275,18 @@ def main_arm(args, rank, world, local_rank):
         ms = float(t.item())
     solve_s = ms * 1e-3 / args.steps
     iters = iters_total // args.steps
-    # every rank solves its own replica of the system (see DESIGN.md "Multi-GPU")
-    value = world * iters_total / (ms * 1e-3)
+    # N > 1: ONE system, row-partitioned across the GPUs -> strong scaling
+    value = iters_total / (ms * 1e-3)
 
     # ---- roofline: same K steps again with the CSR launches bracketed by events ----------
     ctx.profile_begin()
     for _ in range(args.steps):
         S.solve_resident()
     prof = ctx.profile_end()
-    finest = [p for p in prof if p["nrows"] == nrows and p["ncols"] == nrows]
+    # the finest-level operator (this rank's share of it when partitioned) = most non-zeros
+    csr_prof = [p for p in prof if p["mode"] in ("spmv", "spmv_acc", "residual", "relax")]
+    big = max([p["nnz"] for p in csr_prof if p["nrows"] * 2 > p["ncols"]] or [0])
+    finest = [p for p in csr_prof if p["nnz"] == big and p["mode"] != "spmv_acc"]
     peak, peak_src = peaks()
     roof = None
     if finest:
@@ -300,7 +318,7 @@ def main_arm(args, rank, world, local_rank):
             except Exception:
                 pass
     all_csr_ms = sum(p["total_ms"] for p in prof if p["nnz"] > 0 and p["mode"] != "coarse_gemv")
-    streams = {"vec1": 2, "vec2": 3, "vec3": 4, "dot": 2, "relax_zero": 3, "memset": 1}
+    streams = {"vec1": 2, "vec2": 3, "vec3": 4, "dot": 2, "relax_zero": 3, "memset": 1, "comm": 1}
     breakdown = []
     for p in sorted(prof, key=lambda q: -q["total_ms"]):
         if p["mode"] in streams:
@@ -343,8 +361,9 @@ def main_arm(args, rank, world, local_rank):
         t = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_e2e = float(t.item())
-    e2e = {"value": world * e2e_iters / t_e2e, "unit": UNIT, "solve_s": t_e2e / args.steps,
-           "h2d_bytes_per_step": 2 * nrows * 8, "d2h_bytes_per_step": nrows * 8,
+    per_rank_rows = (nrows + world - 1) // world
+    e2e = {"value": e2e_iters / t_e2e, "unit": UNIT, "solve_s": t_e2e / args.steps,
+           "h2d_bytes_per_step": 2 * per_rank_rows * 8 * world, "d2h_bytes_per_step": nrows * 8 * world,
            "api": "make_solver<amg<backend::b200<double>,...>, %s>::operator()(rhs, x) via dropin_solve "
                   "(host rhs/x0 in, host x out)" % args.krylov}
     x_gpu = x_h.copy()
@@ -365,13 +384,15 @@ def main_arm(args, rank, world, local_rank):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": solve_s * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
             "config": {"workload": workload_name(args), "rows": nrows, "nnz": nnz,
                        "relax": args.relax, "krylov": args.krylov, "tol": 1e-8,
                        "step": "one complete solve, rhs=1, x0=0",
                        "l2": "inputs_exceed_l2 (finest matrix %.2f GB >> 126 MB)" % (nnz * 12 / 1e9),
                        "parallelism": "single GPU" if world == 1 else
-                                      "%d independent replicas (one system per GPU)" % world,
+                                      "one system row-partitioned over %d GPUs (levels with >= %d rows; "
+                                      "NCCL halo all-gather / reduce / all-reduce)" % (world, dist_min_rows),
                        "setup_s": t_setup, "generate_s": t_gen, "hierarchy": "host (AMGCL smoothed_aggregation)"},
             "solve_s": solve_s, "iters": iters, "resid": res,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
