@@ -146,8 +146,8 @@ def reference_arm(args, rank, world):
     import oracle
     from amgcl_b200 import poisson3d
     if not oracle.have_ref():
-        print(json.dumps({"impl": "reference", "unavailable":
-                          "oracle/_ref/libamgcl_ref.so missing and /root/reference not present"}))
+        emit({"impl": "reference", "unavailable":
+              "oracle/_ref/libamgcl_ref.so missing and /root/reference not present"})
         return
     ref = oracle.ref()
     t0 = time.time()
@@ -181,7 +181,7 @@ def reference_arm(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # --------------------------------------------------------------------------- our arm
@@ -400,13 +400,31 @@ def main_arm(args, rank, world, local_rank):
             "kernels_ms_per_step": kernels_ms_per_step, "breakdown": breakdown,
             "cpu_baseline": cpu, "parity": parity,
         }
-        print(json.dumps(line))
+        emit(line)
     S.close()
     if dist is not None:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The one JSON line goes to the real stdout; everything else (NCCL banners, library
+    chatter) was redirected to stderr in main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)            # fd 1 -> stderr for native libraries (NCCL prints its version there)
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
