@@ -108,7 +108,7 @@ def lib():
         "b200_coarse_solve": [_vp, _vp, _vp, _vp],
         "b200_nccl_unique_id": [_c.c_char_p, _c.c_size_t],
         "b200_dist_init": [_vp, _c.c_char_p, _c.c_size_t, _c.c_int, _c.c_int, _i64],
-        "b200_dist_info": [_vp, _P(_c.c_int), _P(_c.c_int), _P(_i64)],
+        "b200_dist_info": [_vp, _P(_c.c_int), _P(_c.c_int), _P(_i64), _P(_c.c_int)],
         "b200_partition": [_i64, _c.c_int, _c.c_int, _P(_i64), _P(_i64), _P(_i64)],
         "b200_dist_split_i64": [_c.c_int, _c.c_int, _c.c_int, _i64, _i64, _vp, _vp, _vp, _P(_vp)],
         "b200_split_info": [_vp, _P(_i64), _P(_i64), _P(_i64), _P(_i64), _P(_i64), _P(_i64)],
@@ -228,6 +228,12 @@ class Context:
         buf = _c.create_string_buffer(bytes(unique_id), 128)
         _check(lib().b200_dist_init(self.h, buf, 128, int(nranks), int(rank), int(dist_min_rows)),
                "b200_dist_init")
+
+    def dist_info(self):
+        r, n, p = _c.c_int(), _c.c_int(), _c.c_int()
+        m = _i64()
+        _check(lib().b200_dist_info(self.h, _c.byref(r), _c.byref(n), _c.byref(m), _c.byref(p)))
+        return {"rank": r.value, "nranks": n.value, "dist_min_rows": m.value, "p2p": bool(p.value)}
 
     def profile_begin(self):
         _check(lib().b200_profile_begin(self.h), "b200_profile_begin")

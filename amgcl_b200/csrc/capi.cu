@@ -8,6 +8,7 @@
 #include "vec_kernels.cuh"
 #include "coarse_kernels.cuh"
 #include "dist.cuh"
+#include "peer.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -21,6 +22,9 @@
 // error plumbing
 // ---------------------------------------------------------------------------
 namespace b200 {
+
+static void peer_release(b200_ctx_t ctx, void *local, void **peers);
+static int peer_alloc(b200_ctx_t ctx, size_t bytes, void **local, void **peers);
 
 static thread_local std::string g_last_error;
 
@@ -192,6 +196,14 @@ extern "C" int b200_ctx_destroy(b200_ctx_t ctx) {
     if (ctx->dot_ticket) cudaFree(ctx->dot_ticket);
     if (ctx->dot_result_h) cudaFreeHost(ctx->dot_result_h);
     if (ctx->dot_dev) cudaFree(ctx->dot_dev);
+    if (ctx->push_ticket) cudaFree(ctx->push_ticket);
+    if (ctx->ipc_dev) cudaFree(ctx->ipc_dev);
+    if (ctx->dot_pb_local) {
+        for (int q = 0; q < ctx->nranks; ++q)
+            if (q != ctx->rank && ctx->dot_pb_peer[q]) cudaIpcCloseMemHandle(ctx->dot_pb_peer[q]);
+        cudaFree(ctx->dot_pb_local);
+    }
+    for (void *ptr : ctx->deferred_free) cudaFree(ptr);
     if (ctx->comm && nccl().handle) nccl().CommDestroy(comm_of(ctx));
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
@@ -328,14 +340,32 @@ extern "C" int b200_dist_init(b200_ctx_t ctx, const char *id, size_t size, int n
     ctx->nranks = nranks;
     ctx->dist_min_rows = dist_min_rows;
     ctx->dist = true;
+    B200_CUDA(cudaMalloc(&ctx->push_ticket, sizeof(unsigned int)));
+    B200_CUDA(cudaMemset(ctx->push_ticket, 0, sizeof(unsigned int)));
+    B200_CUDA(cudaMalloc(&ctx->ipc_dev, (size_t)kMaxRanks * sizeof(cudaIpcMemHandle_t)));
+
+    // peer-memory exchange: try to map a small buffer of every peer; agree collectively
+    ctx->p2p = false;
+    if (ctx->opt_p2p && nranks > 1 && nranks <= kMaxRanks) {
+        int ok = peer_alloc(ctx, kFlagBytes + 2 * 256, &ctx->dot_pb_local, ctx->dot_pb_peer) == B200_OK;
+        int *flag_d = reinterpret_cast<int *>(ctx->ipc_dev);
+        B200_CUDA(cudaMemcpy(flag_d, &ok, sizeof(int), cudaMemcpyHostToDevice));
+        B200_NCCL(nccl().AllReduce(flag_d, flag_d, 1, ncclInt, ncclMin, comm, ctx->stream));
+        B200_CUDA(cudaMemcpyAsync(&ok, flag_d, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        B200_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->p2p = ok != 0;
+        if (!ctx->p2p) cudaGetLastError();
+    }
     return B200_OK;
 }
 
-extern "C" int b200_dist_info(b200_ctx_t ctx, int *rank, int *nranks, int64_t *dist_min_rows) {
+extern "C" int b200_dist_info(b200_ctx_t ctx, int *rank, int *nranks, int64_t *dist_min_rows,
+                              int *p2p) {
     CHECK_CTX(ctx);
     if (rank) *rank = ctx->rank;
     if (nranks) *nranks = ctx->nranks;
     if (dist_min_rows) *dist_min_rows = ctx->dist ? ctx->dist_min_rows : 0;
+    if (p2p) *p2p = ctx->p2p ? 1 : 0;
     return B200_OK;
 }
 
@@ -416,6 +446,7 @@ static int64_t *option_slot(b200_ctx_t ctx, const char *key) {
     if (!strcmp(key, "lanes")) return &ctx->opt_lanes;
     if (!strcmp(key, "ctas_per_sm")) return &ctx->opt_ctas_per_sm;
     if (!strcmp(key, "stages")) return &ctx->opt_stages;
+    if (!strcmp(key, "p2p")) return &ctx->opt_p2p;
     return nullptr;
 }
 
@@ -764,8 +795,9 @@ static void csr_free(b200_csr_t A) {
     if (A->val) cudaFree(A->val);
     if (A->blk) cudaFree(A->blk);
     if (A->send_idx) cudaFree(A->send_idx);
-    if (A->halo) cudaFree(A->halo);
+    if (A->halo_owned) cudaFree(A->halo_owned);
     if (A->cbuf) cudaFree(A->cbuf);
+    if (A->pb_local) peer_release(A->ctx, A->pb_local, A->pb_peer);
     delete A;
 }
 
@@ -831,7 +863,8 @@ static int csr_create(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *p
         A->n_send = (int64_t)sp.send_idx.size();
         std::vector<int32_t> idx(sp.send_idx.begin(), sp.send_idx.end());
         DCSR_CUDA(cudaMalloc(&A->send_idx, std::max<size_t>(1, idx.size()) * sizeof(int)));
-        DCSR_CUDA(cudaMalloc(&A->halo, std::max<size_t>(2, (size_t)(P * sp.S)) * sizeof(double)));
+        DCSR_CUDA(cudaMalloc(&A->halo_owned, std::max<size_t>(2, (size_t)(P * sp.S)) * sizeof(double)));
+        A->halo = A->halo_owned;
         DCSR_CUDA(cudaMemsetAsync(A->halo, 0, std::max<size_t>(2, (size_t)(P * sp.S)) * sizeof(double), ctx->stream));
         if (!idx.empty())
             DCSR_CUDA(cudaMemcpyAsync(A->send_idx, idx.data(), idx.size() * sizeof(int),
@@ -850,6 +883,69 @@ static int csr_create(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *p
     }
     DCSR_CUDA(cudaStreamSynchronize(ctx->stream));
 #undef DCSR_CUDA
+
+    // who exchanges with whom (identical on every rank: derived from the global matrix)
+    {
+        std::vector<unsigned char> dep;
+        const int me = rank;
+        if (kind == B200_CK_SQUARE) {
+            const Partition part(nrows, P);
+            dependency_matrix(part, part, ptr, col, dep);
+            for (int q = 0; q < P; ++q) {
+                A->need_from[q] = q != me && dep[(size_t)me * P + q];
+                A->needed_by[q] = q != me && dep[(size_t)q * P + me];
+            }
+        } else if (kind == B200_CK_PROLONG) {
+            // consumer p (fine rows) needs the coarse entries owned by o
+            const Partition fine(nrows, P);
+            const Partition coarse = A->coarse_dist ? Partition(ncols, P) : Partition(ncols, 1);
+            if (A->coarse_dist) {
+                dependency_matrix(fine, coarse, ptr, col, dep);
+                for (int q = 0; q < P; ++q) {
+                    A->need_from[q] = dep[(size_t)me * P + q];
+                    A->needed_by[q] = dep[(size_t)q * P + me];
+                }
+            } else {
+                for (int q = 0; q < P; ++q) {
+                    const bool has = (int64_t)ptr[fine.hi(q)] > (int64_t)ptr[fine.lo(q)];
+                    if (me == 0) A->needed_by[q] = q != 0 && has;
+                    if (q == 0) A->need_from[0] = me != 0 && (int64_t)ptr[fine.hi(me)] > (int64_t)ptr[fine.lo(me)];
+                }
+            }
+        } else {
+            // producer r (fine columns) contributes to the coarse rows owned by o
+            const Partition fine(ncols, P);
+            if (A->coarse_dist) {
+                const Partition coarse(nrows, P);
+                dependency_matrix(coarse, fine, ptr, col, dep);     // dep[o][r]
+                for (int q = 0; q < P; ++q) {
+                    A->need_from[q] = dep[(size_t)me * P + q];       // r = q contributes to me
+                    A->needed_by[q] = dep[(size_t)q * P + me];       // I contribute to owner q
+                }
+            } else {
+                std::vector<unsigned char> has((size_t)P, 0);
+                for (int64_t e = 0; e < nnz; ++e) has[(size_t)fine.owner((int64_t)col[e])] = 1;
+                A->needed_by[0] = has[(size_t)me];
+                if (me == 0)
+                    for (int q = 0; q < P; ++q) A->need_from[q] = has[(size_t)q];
+            }
+        }
+    }
+    if (ctx->p2p) {
+        size_t half = 16;
+        if (kind == B200_CK_SQUARE) half = (size_t)P * (size_t)A->S * sizeof(double);
+        else if (kind == B200_CK_PROLONG) half = (size_t)A->cbuf_n * sizeof(double);
+        else if (A->coarse_dist) half = (size_t)P * (size_t)A->coarse_B * sizeof(double);
+        else if (rank == 0) half = (size_t)P * (size_t)nrows * sizeof(double);
+        half = (half + 255) & ~size_t(255);
+        A->pb_half = half;
+        int rc2 = peer_alloc(ctx, kFlagBytes + 2 * half, &A->pb_local, A->pb_peer);
+        if (rc2) {
+            csr_free(A);
+            return rc2;
+        }
+        A->bytes += kFlagBytes + 2 * half;
+    }
     *out = A;
     return B200_OK;
 }
@@ -941,11 +1037,85 @@ static int launch_ew(b200_ctx_t ctx, size_t n, F f, const double *x, const doubl
 
 namespace b200 {
 
+// Collective: every rank allocates `bytes` (zero filled) and maps the allocations of all
+// its peers through CUDA IPC.  peers[rank] is the local pointer.
+static int peer_alloc(b200_ctx_t ctx, size_t bytes, void **local, void **peers) {
+    bytes = (bytes + 255) & ~size_t(255);
+    B200_CUDA(cudaMalloc(local, bytes));
+    B200_CUDA(cudaMemsetAsync(*local, 0, bytes, ctx->stream));
+    cudaIpcMemHandle_t mine;
+    B200_CUDA(cudaIpcGetMemHandle(&mine, *local));
+    char *stage = static_cast<char *>(ctx->ipc_dev);
+    const size_t hs = sizeof(cudaIpcMemHandle_t);
+    B200_CUDA(cudaMemcpyAsync(stage + ctx->rank * hs, &mine, hs, cudaMemcpyHostToDevice, ctx->stream));
+    B200_NCCL(nccl().AllGather(stage + ctx->rank * hs, stage, hs, ncclChar, comm_of(ctx), ctx->stream));
+    std::vector<cudaIpcMemHandle_t> all((size_t)ctx->nranks);
+    B200_CUDA(cudaMemcpyAsync(all.data(), stage, hs * ctx->nranks, cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int q = 0; q < ctx->nranks; ++q) {
+        if (q == ctx->rank) { peers[q] = *local; continue; }
+        B200_CUDA(cudaIpcOpenMemHandle(&peers[q], all[(size_t)q], cudaIpcMemLazyEnablePeerAccess));
+    }
+    return B200_OK;
+}
+
+static void peer_release(b200_ctx_t ctx, void *local, void **peers) {
+    if (!local) return;
+    for (int q = 0; q < ctx->nranks; ++q)
+        if (q != ctx->rank && peers[q]) cudaIpcCloseMemHandle(peers[q]);
+    // peers may still have this allocation mapped: keep it until the context dies
+    ctx->deferred_free.push_back(local);
+}
+
+static inline unsigned long long *flag_at(void *base, int parity, int slot) {
+    return reinterpret_cast<unsigned long long *>(base) + parity * kFlagStride + slot;
+}
+static inline double *data_at(void *base, int parity, size_t half_bytes) {
+    return reinterpret_cast<double *>(static_cast<char *>(base) + kFlagBytes + (size_t)parity * half_bytes);
+}
+
+static int launch_push(b200_ctx_t ctx, int64_t count, const double *src, const int *idx,
+                       const PeerTargets &tgt, int64_t seg_stride, unsigned long long seq) {
+    const unsigned grid = (unsigned)std::max<int64_t>(1, (count + kThreads - 1) / kThreads);
+    push_kernel<<<grid, kThreads, 0, ctx->stream>>>(count, src, idx, tgt, ctx->nranks, seg_stride,
+                                                    ctx->push_ticket, seq);
+    B200_CHECK_LAUNCH();
+    ctx->launches++;
+    return B200_OK;
+}
+
 // SQUARE operators: make every rank's boundary values of x visible in A->halo.
 // One pack kernel + one in-place ncclAllGather (S doubles per rank) on the stream.
 static int halo_exchange(b200_ctx_t ctx, b200_csr_t A, const double *x) {
     if (A->S == 0) return B200_OK;
     ProfScope prof(ctx, B200_PROF_COMM, A->n_send, ctx->nranks, 0);
+    if (ctx->p2p) {
+        // push my boundary values straight into the halo buffers of the ranks that gather
+        // them, release their flags, then wait for the ranks I gather from
+        const int par = (int)(A->seq & 1);
+        const unsigned long long seq = ++A->seq;
+        PeerTargets tgt;
+        WaitList w;
+        bool any_wait = false;
+        for (int q = 0; q < kMaxRanks; ++q) { tgt.data[q] = nullptr; tgt.flag[q] = nullptr; w.flag[q] = nullptr; }
+        for (int q = 0; q < ctx->nranks; ++q) {
+            if (q == ctx->rank) continue;
+            if (A->needed_by[q]) {
+                tgt.data[q] = data_at(A->pb_peer[q], par, A->pb_half) + (size_t)ctx->rank * A->S;
+                tgt.flag[q] = flag_at(A->pb_peer[q], par, ctx->rank);
+            }
+            if (A->need_from[q]) { w.flag[q] = flag_at(A->pb_local, par, q); any_wait = true; }
+        }
+        int rc = launch_push(ctx, A->n_send, x, A->send_idx, tgt, 0, seq);
+        if (rc) return rc;
+        if (any_wait) {
+            wait_kernel<<<1, 32, 0, ctx->stream>>>(w, ctx->nranks, seq);
+            B200_CHECK_LAUNCH();
+            ctx->launches++;
+        }
+        A->halo = data_at(A->pb_local, par, A->pb_half);   // what the kernel gathers from
+        return B200_OK;
+    }
     double *mine = A->halo + (size_t)ctx->rank * A->S;
     if (A->n_send) {
         const unsigned grid = (unsigned)((A->n_send + kThreads - 1) / kThreads);
@@ -960,6 +1130,55 @@ static int halo_exchange(b200_ctx_t ctx, b200_csr_t A, const double *x) {
 // PROLONG operators: bring the coarse vector to every rank; returns the pointer to gather from.
 static int coarse_to_all(b200_ctx_t ctx, b200_csr_t A, b200_vec_t xc, const double **px) {
     ProfScope prof(ctx, B200_PROF_COMM, A->gl_cols, ctx->nranks, 1);
+    if (ctx->p2p) {
+        const int par = (int)(A->seq & 1);
+        const unsigned long long seq = ++A->seq;
+        PeerTargets tgt;
+        WaitList w;
+        bool any_wait = false;
+        for (int q = 0; q < kMaxRanks; ++q) { tgt.data[q] = nullptr; tgt.flag[q] = nullptr; w.flag[q] = nullptr; }
+        if (A->coarse_dist) {
+            B200_REQUIRE(xc->kind == B200_VK_DIST && (int64_t)xc->cap == A->coarse_B,
+                         "prolongation: coarse vector is not partitioned like the operator");
+            int rc = materialize(xc);
+            if (rc) return rc;
+            for (int q = 0; q < ctx->nranks; ++q) {
+                if (A->needed_by[q]) {
+                    tgt.data[q] = data_at(A->pb_peer[q], par, A->pb_half) + (size_t)ctx->rank * A->coarse_B;
+                    tgt.flag[q] = flag_at(A->pb_peer[q], par, ctx->rank);
+                }
+                if (A->need_from[q]) { w.flag[q] = flag_at(A->pb_local, par, q); any_wait = true; }
+            }
+            rc = launch_push(ctx, A->coarse_B, xc->ptr, nullptr, tgt, 0, seq);
+            if (rc) return rc;
+            *px = data_at(A->pb_local, par, A->pb_half);
+        } else if (ctx->rank == 0) {
+            B200_REQUIRE(xc->kind == B200_VK_LOCAL, "prolongation: coarse vector must live on rank 0");
+            int rc = materialize(xc);
+            if (rc) return rc;
+            bool any = false;
+            for (int q = 1; q < ctx->nranks; ++q)
+                if (A->needed_by[q]) {
+                    tgt.data[q] = data_at(A->pb_peer[q], par, A->pb_half);
+                    tgt.flag[q] = flag_at(A->pb_peer[q], par, 0);
+                    any = true;
+                }
+            if (any) {
+                rc = launch_push(ctx, A->gl_cols, xc->ptr, nullptr, tgt, 0, seq);
+                if (rc) return rc;
+            }
+            *px = xc->ptr;
+        } else {
+            if (A->need_from[0]) { w.flag[0] = flag_at(A->pb_local, par, 0); any_wait = true; }
+            *px = data_at(A->pb_local, par, A->pb_half);
+        }
+        if (any_wait) {
+            wait_kernel<<<1, 32, 0, ctx->stream>>>(w, ctx->nranks, seq);
+            B200_CHECK_LAUNCH();
+            ctx->launches++;
+        }
+        return B200_OK;
+    }
     if (A->coarse_dist) {
         B200_REQUIRE(xc->kind == B200_VK_DIST && (int64_t)xc->cap == A->coarse_B,
                      "prolongation: coarse vector is not partitioned like the operator");
@@ -985,6 +1204,48 @@ static int coarse_to_all(b200_ctx_t ctx, b200_csr_t A, b200_vec_t xc, const doub
 // RESTRICT operators: combine the per-rank partial sums in A->cbuf into the coarse vector.
 static int partials_to_coarse(b200_ctx_t ctx, b200_csr_t A, b200_vec_t yc) {
     ProfScope prof(ctx, B200_PROF_COMM, A->gl_rows, ctx->nranks, 2);
+    if (ctx->p2p) {
+        // every rank stores its partial sums for owner q directly into q's staging area;
+        // the owner adds the staged partials in rank order (deterministic)
+        const int par = (int)(A->seq & 1);
+        const unsigned long long seq = ++A->seq;
+        PeerTargets tgt;
+        WaitList w;
+        for (int q = 0; q < kMaxRanks; ++q) { tgt.data[q] = nullptr; tgt.flag[q] = nullptr; w.flag[q] = nullptr; }
+        const int64_t seg = A->coarse_dist ? A->coarse_B : A->gl_rows;     // staged entries per source
+        const int nowners = A->coarse_dist ? ctx->nranks : 1;
+        bool any = false;
+        for (int q = 0; q < nowners; ++q)
+            if (A->needed_by[q]) {
+                tgt.data[q] = data_at(A->pb_peer[q], par, A->pb_half) + (size_t)ctx->rank * seg;
+                tgt.flag[q] = flag_at(A->pb_peer[q], par, ctx->rank);
+                any = true;
+            }
+        if (any) {
+            int rc = launch_push(ctx, seg, A->cbuf, nullptr, tgt, A->coarse_dist ? seg : 0, seq);
+            if (rc) return rc;
+        }
+        const bool owner = A->coarse_dist || ctx->rank == 0;
+        if (owner) {
+            if (A->coarse_dist)
+                B200_REQUIRE(yc->kind == B200_VK_DIST && (int64_t)yc->cap == A->coarse_B,
+                             "restriction: coarse vector is not partitioned like the operator");
+            else
+                B200_REQUIRE(yc->kind == B200_VK_LOCAL, "restriction: coarse vector must live on rank 0");
+            for (int q = 0; q < ctx->nranks; ++q)
+                if (A->need_from[q]) w.flag[q] = flag_at(A->pb_local, par, q);
+            const int64_t count = (int64_t)yc->len;
+            if (count) {
+                const unsigned grid = (unsigned)((count + kThreads - 1) / kThreads);
+                reduce_sum_kernel<<<grid, kThreads, 0, ctx->stream>>>(
+                    count, data_at(A->pb_local, par, A->pb_half), seg, ctx->nranks, w, seq, wr(yc), nullptr);
+                B200_CHECK_LAUNCH();
+                ctx->launches++;
+            }
+            yc->zero_pending = false;
+        }
+        return B200_OK;
+    }
     if (A->coarse_dist) {
         B200_REQUIRE(yc->kind == B200_VK_DIST && (int64_t)yc->cap == A->coarse_B,
                      "restriction: coarse vector is not partitioned like the operator");
@@ -1213,6 +1474,30 @@ extern "C" int b200_dot(b200_ctx_t ctx, b200_vec_t x, b200_vec_t y, double *resu
                                                        ctx->dot_ticket, ctx->dot_dev, vec_ok);
         B200_CHECK_LAUNCH();
         ctx->launches++;
+    }
+    if (ctx->p2p) {
+        // every rank stores its partial into slot `rank` of every peer; each rank then adds
+        // the P partials in rank order (bitwise identical on all ranks) straight into
+        // mapped host memory
+        const int par = (int)(ctx->dot_seq & 1);
+        const unsigned long long seq = ++ctx->dot_seq;
+        PeerTargets tgt;
+        WaitList w;
+        for (int q = 0; q < kMaxRanks; ++q) { tgt.data[q] = nullptr; tgt.flag[q] = nullptr; w.flag[q] = nullptr; }
+        for (int q = 0; q < ctx->nranks; ++q) {
+            tgt.data[q] = data_at(ctx->dot_pb_peer[q], par, 256) + ctx->rank;
+            tgt.flag[q] = flag_at(ctx->dot_pb_peer[q], par, ctx->rank);
+            w.flag[q] = flag_at(ctx->dot_pb_local, par, q);
+        }
+        int rc = launch_push(ctx, 1, ctx->dot_dev, nullptr, tgt, 0, seq);
+        if (rc) return rc;
+        reduce_sum_kernel<<<1, 32, 0, ctx->stream>>>(1, data_at(ctx->dot_pb_local, par, 256), 1, ctx->nranks,
+                                                      w, seq, ctx->dot_dev + 1, ctx->dot_result_d);
+        B200_CHECK_LAUNCH();
+        ctx->launches++;
+        B200_CUDA(cudaStreamSynchronize(ctx->stream));
+        *result = *reinterpret_cast<volatile double *>(ctx->dot_result_h);
+        return B200_OK;
     }
     B200_NCCL(nccl().AllReduce(ctx->dot_dev, ctx->dot_dev, 1, ncclDouble, ncclSum, comm_of(ctx), ctx->stream));
     B200_CUDA(cudaMemcpyAsync(ctx->dot_result_h, ctx->dot_dev, sizeof(double), cudaMemcpyDeviceToHost,

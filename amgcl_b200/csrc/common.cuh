@@ -81,6 +81,14 @@ struct b200_ctx_s {
     void    *comm          = nullptr;       // ncclComm_t
     int64_t  dist_min_rows = 0;             // dimensions >= this are partitioned
     double  *dot_dev       = nullptr;       // device scalar for the all-reduced dot product
+    // peer-memory exchange (peer.cuh): enabled when CUDA IPC between the ranks works
+    bool     p2p           = false;
+    unsigned int *push_ticket = nullptr;    // device, self-resetting
+    void    *ipc_dev       = nullptr;       // device staging for IPC handle exchange
+    void    *dot_pb_local  = nullptr;       // [flags | 2 x 16 doubles] shared with the peers
+    void    *dot_pb_peer[16] = {};
+    unsigned long long dot_seq = 0;
+    std::vector<void *> deferred_free;      // IPC-exported allocations, freed with the context
 
     // tuning
     int64_t opt_spmv_variant  = 1;
@@ -90,6 +98,7 @@ struct b200_ctx_s {
     int64_t opt_lanes         = 0;        // 0 = choose from average row length
     int64_t opt_ctas_per_sm   = 4;        // persistent variant: CTAs per SM
     int64_t opt_stages        = 2;        // persistent variant: ring depth
+    int64_t opt_p2p           = 1;        // multi-GPU: exchange through mapped peer memory
 };
 
 enum { B200_VK_LOCAL = 0, B200_VK_DIST = 1, B200_VK_GHOST = 2 };
@@ -122,11 +131,19 @@ struct b200_csr_s {
     int64_t    S       = 0;       // SQUARE: halo slots per rank
     int64_t    n_send  = 0;       // SQUARE: entries this rank contributes
     int       *send_idx = nullptr;// SQUARE: [n_send] local indices to pack
-    double    *halo    = nullptr; // SQUARE: [nranks*S] all-gathered boundary values
+    double    *halo    = nullptr; // SQUARE: [nranks*S] boundary values the kernel gathers from
+    double    *halo_owned = nullptr; //       NCCL path: private buffer (peer path: inside pb)
     double    *cbuf    = nullptr; // PROLONG: gathered coarse vector; RESTRICT: partial sums
     int64_t    cbuf_n  = 0;
     bool       coarse_dist = false;   // the coarse side of P/R is itself partitioned
     int64_t    coarse_B = 0;          // its uniform block
+    // peer-memory exchange state (peer.cuh); layout: [flags 256 B | parity 0 | parity 1]
+    void      *pb_local = nullptr;
+    void      *pb_peer[16] = {};
+    size_t     pb_half  = 0;          // bytes of one parity buffer
+    unsigned long long seq = 0;       // exchanges done so far (same on every rank)
+    bool       need_from[16] = {};    // ranks whose data this rank consumes
+    bool       needed_by[16] = {};    // ranks that consume this rank's data
     int       *ptr   = nullptr;   // [nrows+1] (+ padding) device
     int       *col   = nullptr;   // [nnz]     (+ padding) device
     double    *val   = nullptr;   // [nnz]     (+ padding) device

@@ -221,6 +221,21 @@ static void split_restrict(const Partition &fine, int rank, int64_t nrows, const
         }
 }
 
+// dep[p][o] = rows owned by p (row partition) reference columns owned by o (column
+// partition), p != o for square operators.  Identical on every rank (global matrix).
+template <class Ptr, class Col>
+static void dependency_matrix(const Partition &rows, const Partition &cols, const Ptr *ptr,
+                              const Col *col, std::vector<unsigned char> &dep) {
+    const int P = rows.P;
+    dep.assign((size_t)P * P, 0);
+    for (int p = 0; p < P; ++p) {
+        unsigned char *row = dep.data() + (size_t)p * P;
+        for (int64_t r = rows.lo(p); r < rows.hi(p); ++r)
+            for (int64_t e = (int64_t)ptr[r]; e < (int64_t)ptr[r + 1]; ++e)
+                row[cols.owner((int64_t)col[e])] = 1;
+    }
+}
+
 // ---- device helper: pack this rank's boundary values into its halo segment ----------
 __global__ void __launch_bounds__(kThreads)
 halo_pack_kernel(int64_t count, const int *__restrict__ send_idx, const double *__restrict__ x,

@@ -43,6 +43,8 @@ def parse_args():
                     help="N>1: partition only the finest level (north star) or every level "
                          "with at least --partition-min-rows rows")
     ap.add_argument("--partition-min-rows", type=int, default=100000)
+    ap.add_argument("--p2p", type=int, default=1, choices=[0, 1],
+                    help="N>1: 1 = peer-memory exchange kernels over NVLink, 0 = NCCL collectives")
     ap.add_argument("--ref-sample-iters", type=int, default=4,
                     help="Krylov iterations per step of the CPU reference sample")
     return ap.parse_args()
@@ -239,7 +241,12 @@ def main_arm(args, rank, world, local_rank):
         dist.broadcast_object_list(box, src=0)
         if args.partition == "all":
             dist_min_rows = args.partition_min_rows
+        ctx.set_option("p2p", args.p2p)
         ctx.dist_init(box[0], world, rank, dist_min_rows)
+    transport = "n/a"
+    if world > 1:
+        transport = "peer-memory push/wait/reduce kernels (CUDA IPC over NVLink)" \
+            if ctx.dist_info()["p2p"] else "NCCL collectives"
 
     t0 = time.time()
     S = ab.DropinSolver(ptr, col, val, args.relax, args.krylov, ctx=ctx)
@@ -392,7 +399,7 @@ def main_arm(args, rank, world, local_rank):
                        "l2": "inputs_exceed_l2 (finest matrix %.2f GB >> 126 MB)" % (nnz * 12 / 1e9),
                        "parallelism": "single GPU" if world == 1 else
                                       "one system row-partitioned over %d GPUs (levels with >= %d rows; "
-                                      "NCCL halo all-gather / reduce / all-reduce)" % (world, dist_min_rows),
+                                      "exchange: %s)" % (world, dist_min_rows, transport),
                        "setup_s": t_setup, "generate_s": t_gen, "hierarchy": "host (AMGCL smoothed_aggregation)"},
             "solve_s": solve_s, "iters": iters, "resid": res,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,

@@ -120,7 +120,10 @@ int b200_profile_end(b200_ctx_t ctx, b200_profile_entry *out, int64_t capacity, 
 int b200_nccl_unique_id(char *id, size_t size /* >= 128 */);
 int b200_dist_init(b200_ctx_t ctx, const char *id, size_t size, int nranks, int rank,
                    int64_t dist_min_rows);
-int b200_dist_info(b200_ctx_t ctx, int *rank, int *nranks, int64_t *dist_min_rows);
+/* p2p: 1 if the exchanges run through CUDA-IPC mapped peer memory with our own push /
+ * wait / reduce kernels over NVLink (default when every rank could map its peers; option
+ * "p2p" = 0 before b200_dist_init forces the NCCL collectives), 0 for NCCL. */
+int b200_dist_info(b200_ctx_t ctx, int *rank, int *nranks, int64_t *dist_min_rows, int *p2p);
 
 /* Pure host helpers (no device, no NCCL) exposing the partition logic to tests.
  * b200_partition: uniform block size and this rank's [lo, hi) for a dimension.
@@ -144,6 +147,7 @@ int b200_split_destroy(b200_split_t sp);
  *   "nnz_cap"          non-zeros staged per row block (default 2048; applies to
  *                      matrices created afterwards)
  *   "lanes"            lanes per row, 0 = from the average row length (default)
+ *   "p2p"              multi-GPU: 1 = peer-memory exchange kernels (default), 0 = NCCL
  *   "fuse_relax"       1 = single-pass fused smoother sweep (default), 0 = two kernels
  *   "zero_shortcut"    1 = skip the A-pass when x is known to be zero (default)
  * Unknown keys return B200_EINVAL. */

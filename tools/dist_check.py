@@ -26,12 +26,13 @@ import torch.distributed as dist  # noqa: E402
 import amgcl_b200 as ab  # noqa: E402
 
 
-def make_ctx(min_rows):
+def make_ctx(min_rows, p2p=1):
     torch.cuda.set_device(local)
     ctx = ab.Context(local)
     if world > 1:
         box = [ab.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
+        ctx.set_option("p2p", p2p)
         ctx.dist_init(box[0], world, rank, min_rows)
     return ctx
 
@@ -45,14 +46,17 @@ def main():
     for n in sizes:
         ptr, col, val, rhs = ab.poisson3d(n)
         nrows = ptr.size - 1
-        for mode, min_rows in (("finest", nrows), ("all>=2000", 2000)):
+        for mode, min_rows, p2p in (("finest", nrows, 1), ("all>=2000", 2000, 1),
+                                    ("finest", nrows, 0), ("all>=2000", 2000, 0)):
+            if world == 1 and p2p == 0:
+                continue
             for relax, krylov in (("damped_jacobi", "cg"), ("spai0", "bicgstab")):
-                ctx = make_ctx(min_rows)
+                ctx = make_ctx(min_rows, p2p)
                 S = ab.DropinSolver(ptr, col, val, relax, krylov, ctx=ctx)
                 x, it, res = S.solve(rhs)
                 case = [c for c in known if (c["n"], c["relax"], c["krylov"]) == (n, relax, krylov)]
                 rec = {"n": n, "world": world, "partitioned": mode, "relax": relax, "krylov": krylov,
-                       "iters": it, "resid": res}
+                       "p2p": ctx.dist_info()["p2p"], "iters": it, "resid": res}
                 if case:
                     c = case[0]
                     rec["ref_iters"] = c["iters"]
