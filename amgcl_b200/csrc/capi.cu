@@ -939,6 +939,11 @@ static int csr_create(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *p
         else if (rank == 0) half = (size_t)P * (size_t)nrows * sizeof(double);
         half = (half + 255) & ~size_t(255);
         A->pb_half = half;
+        // layout of the buffer a producer writes INTO (the owner's): equal to mine except for
+        // a restriction onto a rank-0-only level, where only rank 0 holds the staging area
+        A->pb_half_owner = half;
+        if (kind == B200_CK_RESTRICT && !A->coarse_dist)
+            A->pb_half_owner = (((size_t)P * (size_t)nrows * sizeof(double)) + 255) & ~size_t(255);
         int rc2 = peer_alloc(ctx, kFlagBytes + 2 * half, &A->pb_local, A->pb_peer);
         if (rc2) {
             csr_free(A);
@@ -1217,7 +1222,7 @@ static int partials_to_coarse(b200_ctx_t ctx, b200_csr_t A, b200_vec_t yc) {
         bool any = false;
         for (int q = 0; q < nowners; ++q)
             if (A->needed_by[q]) {
-                tgt.data[q] = data_at(A->pb_peer[q], par, A->pb_half) + (size_t)ctx->rank * seg;
+                tgt.data[q] = data_at(A->pb_peer[q], par, A->pb_half_owner) + (size_t)ctx->rank * seg;
                 tgt.flag[q] = flag_at(A->pb_peer[q], par, ctx->rank);
                 any = true;
             }

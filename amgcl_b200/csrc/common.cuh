@@ -140,7 +140,8 @@ struct b200_csr_s {
     // peer-memory exchange state (peer.cuh); layout: [flags 256 B | parity 0 | parity 1]
     void      *pb_local = nullptr;
     void      *pb_peer[16] = {};
-    size_t     pb_half  = 0;          // bytes of one parity buffer
+    size_t     pb_half  = 0;          // bytes of one parity buffer (mine)
+    size_t     pb_half_owner = 0;     // ... of the buffer my contributions are written into
     unsigned long long seq = 0;       // exchanges done so far (same on every rank)
     bool       need_from[16] = {};    // ranks whose data this rank consumes
     bool       needed_by[16] = {};    // ranks that consume this rank's data
