@@ -1081,7 +1081,11 @@ static inline double *data_at(void *base, int parity, size_t half_bytes) {
 
 static int launch_push(b200_ctx_t ctx, int64_t count, const double *src, const int *idx,
                        const PeerTargets &tgt, int64_t seg_stride, unsigned long long seq) {
-    const unsigned grid = (unsigned)std::max<int64_t>(1, (count + kThreads - 1) / kThreads);
+    // indexed (halo) pushes: one value per thread; contiguous ones: 8 doubles per thread;
+    // never more than 4 CTAs per SM -- the grid-stride loops cover the rest
+    const int64_t per_cta = idx ? kThreads : (int64_t)kThreads * 8;
+    const int64_t want = std::max<int64_t>(1, (count + per_cta - 1) / per_cta);
+    const unsigned grid = (unsigned)std::min<int64_t>(want, (int64_t)ctx->sm_count * 4);
     push_kernel<<<grid, kThreads, 0, ctx->stream>>>(count, src, idx, tgt, ctx->nranks, seg_stride,
                                                     ctx->push_ticket, seq);
     B200_CHECK_LAUNCH();

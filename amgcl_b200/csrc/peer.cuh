@@ -49,22 +49,37 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 }
 
 // Push `count` doubles (src[idx[i]] if idx, else src[i]) to every target; per target the
-// source window may be shifted: target q receives src[shift[q] + i] (reduce-scatter).
+// source window may be shifted: target q receives src[q*seg_stride + i] (reduce-scatter).
+// Contiguous sources move as 16-byte stores, four per thread in flight (NVLink stores are
+// posted; what matters is bytes in flight per SM).  grid-stride: any grid size works.
 __global__ void __launch_bounds__(kThreads)
 push_kernel(int64_t count, const double *__restrict__ src, const int *__restrict__ idx,
             PeerTargets tgt, int nranks, int64_t seg_stride /* 0: same window for all */,
             unsigned int *ticket, unsigned long long seq) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < count) {
-        if (seg_stride == 0) {
-            const double v = idx ? src[idx[i]] : src[i];
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
+    if (idx) {
+        for (int64_t i = tid; i < count; i += nthr) {
+            const double v = src[idx[i]];
 #pragma unroll 1
             for (int q = 0; q < nranks; ++q)
                 if (tgt.data[q]) tgt.data[q][i] = v;
-        } else {
+        }
+    } else {
+        const int64_t n2 = count >> 1;            // all windows and targets are 16-byte aligned
 #pragma unroll 1
-            for (int q = 0; q < nranks; ++q)
-                if (tgt.data[q]) tgt.data[q][i] = src[(int64_t)q * seg_stride + i];
+        for (int q = 0; q < nranks; ++q) {
+            if (!tgt.data[q]) continue;
+            const double2 *s2 = reinterpret_cast<const double2 *>(src + (int64_t)q * seg_stride);
+            double2 *d2 = reinterpret_cast<double2 *>(tgt.data[q]);
+            int64_t i = tid;
+            for (; i + 3 * nthr < n2; i += 4 * nthr) {
+                const double2 a = s2[i], b = s2[i + nthr], c = s2[i + 2 * nthr], d = s2[i + 3 * nthr];
+                d2[i] = a; d2[i + nthr] = b; d2[i + 2 * nthr] = c; d2[i + 3 * nthr] = d;
+            }
+            for (; i < n2; i += nthr) d2[i] = s2[i];
+            if ((count & 1) && tid == 0)
+                tgt.data[q][count - 1] = src[(int64_t)q * seg_stride + count - 1];
         }
     }
     __threadfence_system();                  // my peer stores are visible system-wide ...

@@ -42,7 +42,7 @@ def parse_args():
     ap.add_argument("--partition", default="all", choices=["finest", "all"],
                     help="N>1: partition only the finest level (north star) or every level "
                          "with at least --partition-min-rows rows")
-    ap.add_argument("--partition-min-rows", type=int, default=100000)
+    ap.add_argument("--partition-min-rows", type=int, default=1000000)
     ap.add_argument("--p2p", type=int, default=1, choices=[0, 1],
                     help="N>1: 1 = peer-memory exchange kernels over NVLink, 0 = NCCL collectives")
     ap.add_argument("--ref-sample-iters", type=int, default=4,

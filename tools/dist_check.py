@@ -37,10 +37,48 @@ def make_ctx(min_rows, p2p=1):
     return ctx
 
 
+def latency():
+    """Per-call device time of the exchange primitives (tiny local work): halo exchange inside
+    spmv on a partitioned 48^3 operator, and the all-reduced dot product."""
+    ptr, col, val, rhs = ab.poisson3d(48)
+    n = ptr.size - 1
+    for p2p in (1, 0):
+        torch.cuda.set_device(local)
+        side = torch.cuda.Stream()
+        torch.cuda.set_stream(side)
+        ctx = make_ctx(n, p2p)
+        ctx.set_stream(side.cuda_stream)
+        A = ctx.csr(n, n, ptr, col, val)
+        x, y = ctx.vector(rhs), ctx.vector(n)
+        out = {"world": world, "p2p": ctx.dist_info()["p2p"]}
+        for name, fn, reps in (("spmv_with_halo_us", lambda: ctx.spmv(1.0, A, x, 0.0, y), 300),
+                               ("dot_us", lambda: ctx.dot(x, x), 300)):
+            for _ in range(20):
+                fn()
+            dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(side)
+            for _ in range(reps):
+                fn()
+            e1.record(side)
+            torch.cuda.synchronize()
+            out[name] = round(1e3 * e0.elapsed_time(e1) / reps, 2)
+        if rank == 0:
+            print(json.dumps(out), flush=True)
+        del A, x, y
+        ctx.close()
+        dist.barrier()
+
+
 def main():
-    sizes = [int(a) for a in sys.argv[1:]] or [32, 64]
     if world > 1:
         dist.init_process_group("gloo")     # plumbing only: id exchange + barriers
+    if "--latency" in sys.argv:
+        latency()
+        dist.destroy_process_group()
+        return
+    sizes = [int(a) for a in sys.argv[1:]] or [32, 64]
     known = json.load(open(os.path.join(ROOT, "tests", "golden", "known_answers.json")))["cases"]
     ok = True
     for n in sizes:
