@@ -66,12 +66,19 @@ push_kernel(int64_t count, const double *__restrict__ src, const int *__restrict
                 if (tgt.data[q]) tgt.data[q][i] = v;
         }
     } else {
-        const int64_t n2 = count >> 1;            // all windows and targets are 16-byte aligned
+        const int64_t n2 = count >> 1;
 #pragma unroll 1
         for (int q = 0; q < nranks; ++q) {
             if (!tgt.data[q]) continue;
-            const double2 *s2 = reinterpret_cast<const double2 *>(src + (int64_t)q * seg_stride);
-            double2 *d2 = reinterpret_cast<double2 *>(tgt.data[q]);
+            const double *sq = src + (int64_t)q * seg_stride;
+            double *dq = tgt.data[q];
+            if ((reinterpret_cast<uintptr_t>(sq) | reinterpret_cast<uintptr_t>(dq)) & 15) {
+                // a window that starts on an odd element (e.g. rank * n_coarse): 8-byte stores
+                for (int64_t i = tid; i < count; i += nthr) dq[i] = sq[i];
+                continue;
+            }
+            const double2 *s2 = reinterpret_cast<const double2 *>(sq);
+            double2 *d2 = reinterpret_cast<double2 *>(dq);
             int64_t i = tid;
             for (; i + 3 * nthr < n2; i += 4 * nthr) {
                 const double2 a = s2[i], b = s2[i + nthr], c = s2[i + 2 * nthr], d = s2[i + 3 * nthr];
