@@ -29,8 +29,8 @@ _dbl = _c.c_double
 _vp = _c.c_void_p
 _P = _c.POINTER
 
-RELAX = {"damped_jacobi": 0, "spai0": 1}
-KRYLOV = {"cg": 0, "bicgstab": 1}
+RELAX = {"damped_jacobi": 0, "spai0": 1, "chebyshev": 2}
+KRYLOV = {"cg": 0, "bicgstab": 1, "gmres": 2, "bicgstabl": 3}
 
 
 class B200Error(RuntimeError):

@@ -88,13 +88,17 @@ dot_kernel(size_t n, const double *__restrict__ x, const double *__restrict__ y,
         const double2 *x2 = reinterpret_cast<const double2 *>(x);
         const double2 *y2 = reinterpret_cast<const double2 *>(y);
         size_t i = tid;
-        for (; i + stride < n2; i += 2 * stride) {
+        for (; i + 3 * stride < n2; i += 4 * stride) {
             const double2 xa = x2[i], ya = y2[i];
             const double2 xb = x2[i + stride], yb = y2[i + stride];
+            const double2 xc = x2[i + 2 * stride], yc = y2[i + 2 * stride];
+            const double2 xd = x2[i + 3 * stride], yd = y2[i + 3 * stride];
             acc(xa.x * ya.x); acc(xa.y * ya.y);
             acc(xb.x * yb.x); acc(xb.y * yb.y);
+            acc(xc.x * yc.x); acc(xc.y * yc.y);
+            acc(xd.x * yd.x); acc(xd.y * yd.y);
         }
-        if (i < n2) {
+        for (; i < n2; i += stride) {
             const double2 xa = x2[i], ya = y2[i];
             acc(xa.x * ya.x); acc(xa.y * ya.y);
         }

@@ -214,8 +214,8 @@ def c():
 # ---------------------------------------------------------------------------
 # the real reference (AMGCL builtin backend)
 # ---------------------------------------------------------------------------
-RELAX = {"damped_jacobi": 0, "spai0": 1}
-KRYLOV = {"cg": 0, "bicgstab": 1}
+RELAX = {"damped_jacobi": 0, "spai0": 1, "chebyshev": 2}
+KRYLOV = {"cg": 0, "bicgstab": 1, "gmres": 2, "bicgstabl": 3}
 
 
 def have_ref():

@@ -31,6 +31,9 @@
 #include <amgcl/relaxation/spai0.hpp>
 #include <amgcl/solver/cg.hpp>
 #include <amgcl/solver/bicgstab.hpp>
+#include <amgcl/relaxation/chebyshev.hpp>
+#include <amgcl/solver/gmres.hpp>
+#include <amgcl/solver/bicgstabl.hpp>
 #include <amgcl/solver/skyline_lu.hpp>
 
 namespace {
@@ -170,6 +173,12 @@ int ref_create(int64_t n, const int64_t *ptr, const int64_t *col, const double *
             h->solver.reset(new SolverImpl<relaxation::spai0, solver::cg>(n, ptr, col, val, tol, maxiter, coarse_enough, bprm));
         else if (relax == 1 && krylov == 1)
             h->solver.reset(new SolverImpl<relaxation::spai0, solver::bicgstab>(n, ptr, col, val, tol, maxiter, coarse_enough, bprm));
+        else if (relax == 2 && krylov == 0)
+            h->solver.reset(new SolverImpl<relaxation::chebyshev, solver::cg>(n, ptr, col, val, tol, maxiter, coarse_enough, bprm));
+        else if (relax == 0 && krylov == 2)
+            h->solver.reset(new SolverImpl<relaxation::damped_jacobi, solver::gmres>(n, ptr, col, val, tol, maxiter, coarse_enough, bprm));
+        else if (relax == 1 && krylov == 3)
+            h->solver.reset(new SolverImpl<relaxation::spai0, solver::bicgstabl>(n, ptr, col, val, tol, maxiter, coarse_enough, bprm));
         else { g_error = "unknown relax/krylov selector"; return -1; }
         *out = h.release();
         return 0;

@@ -107,6 +107,19 @@ def main():
                 "level_nnz": [int(l["A"][0][-1]) for l in levels] + [int(coarse[0][-1])]})
             print(known["cases"][-1])
             S.close()
+    # components that reach the backend only through its primitives
+    known["primitive_only"] = []
+    for n in (16, 32, 48):
+        ptr, col, val, rhs = poisson3d(n)
+        for relax, krylov in (("chebyshev", "cg"), ("damped_jacobi", "gmres"), ("spai0", "bicgstabl")):
+            S = oracle.RefSolver(ptr, col, val, relax, krylov)
+            x, iters, resid = S.solve(rhs)
+            known["primitive_only"].append({
+                "n": n, "relax": relax, "krylov": krylov, "iters": iters, "resid": resid,
+                "x_first": float(x[0]), "x_mid": float(x[x.size // 2]),
+                "x_norm2": float(np.linalg.norm(x))})
+            print(known["primitive_only"][-1])
+            S.close()
     # BASELINE.md section 2 (measured by the survey with the same reference build)
     known["survey"] = [
         {"n": 128, "relax": "damped_jacobi", "krylov": "cg", "iters": 21, "resid": 6.07447143094944e-09},
