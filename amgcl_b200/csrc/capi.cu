@@ -795,6 +795,7 @@ static void csr_free(b200_csr_t A) {
     if (A->val) cudaFree(A->val);
     if (A->blk) cudaFree(A->blk);
     if (A->send_idx) cudaFree(A->send_idx);
+    if (A->blk_halo) cudaFree(A->blk_halo);
     if (A->halo_owned) cudaFree(A->halo_owned);
     if (A->cbuf) cudaFree(A->cbuf);
     if (A->pb_local) peer_release(A->ctx, A->pb_local, A->pb_peer);
@@ -870,6 +871,22 @@ static int csr_create(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *p
             DCSR_CUDA(cudaMemcpyAsync(A->send_idx, idx.data(), idx.size() * sizeof(int),
                                       cudaMemcpyHostToDevice, ctx->stream));
         A->bytes += idx.size() * sizeof(int) + (size_t)(P * sp.S) * sizeof(double);
+        // which row blocks touch the halo (the same plan csr_upload just built)
+        RowBlockPlan plan;
+        build_plan(sp.nrows, sp.ptr.data(), A->lanes, A->nnz_cap, plan);
+        std::vector<unsigned char> bh((size_t)std::max<int64_t>(1, A->nblocks), 0);
+        if ((int64_t)plan.blk.size() - 1 == A->nblocks) {
+            for (int64_t b = 0; b < A->nblocks; ++b) {
+                const int64_t e0 = plan.blk[(size_t)b].y, e1 = plan.blk[(size_t)b + 1].y;
+                for (int64_t e = e0; e < e1 && !bh[(size_t)b]; ++e)
+                    if (sp.col[(size_t)e] >= sp.n_loc) bh[(size_t)b] = 1;
+            }
+        } else {
+            std::fill(bh.begin(), bh.end(), 1);      // cannot happen; be safe: every block waits
+        }
+        DCSR_CUDA(cudaMalloc(&A->blk_halo, bh.size()));
+        DCSR_CUDA(cudaMemcpyAsync(A->blk_halo, bh.data(), bh.size(), cudaMemcpyHostToDevice, ctx->stream));
+        DCSR_CUDA(cudaStreamSynchronize(ctx->stream));
     } else {
         // coarse-side buffer: gathered input of P, partial sums of R
         const bool coarse_dist = (kind == B200_CK_PROLONG) ? cd : rd;
@@ -1095,7 +1112,8 @@ static int launch_push(b200_ctx_t ctx, int64_t count, const double *src, const i
 
 // SQUARE operators: make every rank's boundary values of x visible in A->halo.
 // One pack kernel + one in-place ncclAllGather (S doubles per rank) on the stream.
-static int halo_exchange(b200_ctx_t ctx, b200_csr_t A, const double *x) {
+static int halo_exchange(b200_ctx_t ctx, b200_csr_t A, const double *x, CsrArgs &a) {
+    a.xh = A->halo; a.nloc = (int)A->n_loc;
     if (A->S == 0) return B200_OK;
     ProfScope prof(ctx, B200_PROF_COMM, A->n_send, ctx->nranks, 0);
     if (ctx->p2p) {
@@ -1117,12 +1135,19 @@ static int halo_exchange(b200_ctx_t ctx, b200_csr_t A, const double *x) {
         }
         int rc = launch_push(ctx, A->n_send, x, A->send_idx, tgt, 0, seq);
         if (rc) return rc;
-        if (any_wait) {
-            wait_kernel<<<1, 32, 0, ctx->stream>>>(w, ctx->nranks, seq);
-            B200_CHECK_LAUNCH();
-            ctx->launches++;
-        }
         A->halo = data_at(A->pb_local, par, A->pb_half);   // what the kernel gathers from
+        a.xh = A->halo;
+        if (any_wait) {
+            // no separate wait launch: the consumer kernel starts on its interior rows at
+            // once and only blocks that gather remote columns poll the flags
+            unsigned int mask = 0;
+            for (int q = 0; q < ctx->nranks; ++q)
+                if (w.flag[q]) mask |= 1u << q;
+            a.blk_halo = A->blk_halo;
+            a.wait_flags = flag_at(A->pb_local, par, 0);
+            a.wait_mask = mask;
+            a.wait_seq = seq;
+        }
         return B200_OK;
     }
     double *mine = A->halo + (size_t)ctx->rank * A->S;
@@ -1378,9 +1403,8 @@ extern "C" int b200_spmv(b200_ctx_t ctx, double alpha, b200_csr_t A, b200_vec_t 
         if (A->kind == B200_CK_SQUARE) {
             B200_REQUIRE(x->kind == B200_VK_DIST && y->kind == B200_VK_DIST,
                          "spmv: vectors must be partitioned like the operator");
-            rc = halo_exchange(ctx, A, a.x);
+            rc = halo_exchange(ctx, A, a.x, a);
             if (rc) return rc;
-            a.xh = A->halo; a.nloc = (int)A->n_loc;
         }
     }
     if (beta == 0.0 || y->zero_pending) {
@@ -1411,9 +1435,8 @@ extern "C" int b200_residual(b200_ctx_t ctx, b200_vec_t f, b200_csr_t A, b200_ve
     if (A->kind == B200_CK_SQUARE) {
         B200_REQUIRE(x->kind == B200_VK_DIST && f->kind == B200_VK_DIST && r->kind == B200_VK_DIST,
                      "residual: vectors must be partitioned like the operator");
-        rc = halo_exchange(ctx, A, a.x);
+        rc = halo_exchange(ctx, A, a.x, a);
         if (rc) return rc;
-        a.xh = A->halo; a.nloc = (int)A->n_loc;
     }
     a.y = (f == r) ? r->ptr : wr(r);   // r == f is fine: each row reads f[r] before writing
     return launch_csr<MODE_RESID>(ctx, A, a);
@@ -1619,9 +1642,8 @@ extern "C" int b200_relax(b200_ctx_t ctx, b200_csr_t A, b200_vec_t rhs, b200_vec
     if (rc) return rc;
     if (A->kind == B200_CK_SQUARE) {
         B200_REQUIRE(x->kind == B200_VK_DIST, "relax: vectors must be partitioned like the operator");
-        rc = halo_exchange(ctx, A, a.x);
+        rc = halo_exchange(ctx, A, a.x, a);
         if (rc) return rc;
-        a.xh = A->halo; a.nloc = (int)A->n_loc;
     }
     a.f = pf; a.d = pd; a.alpha = omega;
     a.y = wr(tmp);

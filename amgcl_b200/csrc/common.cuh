@@ -143,6 +143,7 @@ struct b200_csr_s {
     size_t     pb_half  = 0;          // bytes of one parity buffer (mine)
     size_t     pb_half_owner = 0;     // ... of the buffer my contributions are written into
     unsigned long long seq = 0;       // exchanges done so far (same on every rank)
+    unsigned char *blk_halo = nullptr;  // SQUARE: [nblocks] block gathers remote columns
     bool       need_from[16] = {};    // ranks whose data this rank consumes
     bool       needed_by[16] = {};    // ranks that consume this rank's data
     int       *ptr   = nullptr;   // [nrows+1] (+ padding) device

@@ -42,6 +42,13 @@ struct CsrArgs {
     const double *x;      // gathered vector (local columns)
     const double *xh;     // halo values for columns >= nloc (multi-GPU), else nullptr
     int           nloc;   // number of local columns when xh is set
+    // multi-GPU, peer-memory transport: the halo is pushed by the peers while this kernel
+    // already works on interior rows; a block that gathers remote columns first waits for
+    // the flags of the ranks in wait_mask to reach wait_seq (csrc/peer.cuh protocol)
+    const unsigned char      *blk_halo;    // [nblocks] 1 = block references the halo
+    const unsigned long long *wait_flags;  // flag row of the current parity (16 slots)
+    unsigned int              wait_mask;
+    unsigned long long        wait_seq;
     double       *y;      // output
     const double *f;      // rhs          (RESID, RELAX)
     const double *d;      // diagonal     (RELAX)
@@ -129,10 +136,31 @@ __device__ __forceinline__ void store_row(const CsrArgs &a, int r, double sum) {
 template <bool HALO>
 __device__ __forceinline__ double gather(const CsrArgs &a, const double *__restrict__ x, int c) {
     if (HALO) {
-        const double *p = (c < a.nloc) ? (x + c) : (a.xh + (c - a.nloc));
-        return __ldg(p);
+        // halo values may arrive while the kernel runs: read them through L2 (ld.cg)
+        if (c < a.nloc) return __ldg(x + c);
+        return __ldcg(a.xh + (c - a.nloc));
     }
     return __ldg(x + c);
+}
+
+// Block until the peers' halo pushes for this exchange have landed (thread 0 polls the
+// flags with acquire semantics, the CTA follows through the barrier).
+template <bool HALO>
+__device__ __forceinline__ void wait_for_halo(const CsrArgs &a, int b) {
+    if (!HALO) return;
+    if (a.blk_halo == nullptr || !a.blk_halo[b]) return;      // uniform per CTA
+    if (threadIdx.x == 0) {
+        unsigned int m = a.wait_mask;
+        while (m) {
+            const int q = __ffs(m) - 1;
+            m &= m - 1;
+            unsigned long long v;
+            do {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a.wait_flags + q) : "memory");
+            } while (v < a.wait_seq);
+        }
+    }
+    __syncthreads();
 }
 
 // ---- reduce the rows of a staged block out of shared memory ---------------------
@@ -231,8 +259,10 @@ __global__ void __launch_bounds__(kThreads, 4) csr_block_kernel(const CsrArgs a)
         }
         __syncthreads();
         ptx::mbar_wait(bar, 0);
+        wait_for_halo<HALO>(a, b);
         compute_staged<MODE, L, HALO>(a, d, stage, lay);
     } else {
+        wait_for_halo<HALO>(a, b);
         compute_long<MODE, HALO>(a, d, red_s);
     }
 }
@@ -269,6 +299,7 @@ __global__ void __launch_bounds__(kThreads, 2) csr_ring_kernel(const CsrArgs a, 
     for (int i = 0; i < mine; ++i) {
         ptx::mbar_wait(bars + s, parity);
         const BlockDesc d = descs[s];
+        wait_for_halo<HALO>(a, first + i * step);
         if ((d.e1 - d.e0) <= a.nnz_cap)
             compute_staged<MODE, L, HALO>(a, d, stages + (size_t)s * lay.bytes, lay);
         else
