@@ -57,7 +57,7 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB_CUDA
+    path = os.environ.get("B200_LIB") or _build.LIB_CUDA     # B200_LIB: experimental builds
     if not os.path.isfile(path):
         path = _build.build_cuda()
     L = _c.CDLL(path, mode=_c.RTLD_GLOBAL)
@@ -141,6 +141,8 @@ def dropin_lib():
     D.dropin_create.argtypes = [_vp, _i64, _vp, _vp, _vp, _c.c_int, _c.c_int, _dbl, _c.c_int,
                                 _c.c_int, _P(_vp)]
     D.dropin_create.restype = _c.c_int
+    D.dropin_create_mixed.argtypes = D.dropin_create.argtypes
+    D.dropin_create_mixed.restype = _c.c_int
     D.dropin_destroy.argtypes = [_vp]
     D.dropin_destroy.restype = None
     D.dropin_solve.argtypes = [_vp, _vp, _vp, _P(_i64), _P(_dbl)]
@@ -406,7 +408,9 @@ class DropinSolver:
     -- the reference's own templates running on the B200 backend."""
 
     def __init__(self, ptr, col, val, relax="damped_jacobi", krylov="cg", tol=1e-8,
-                 maxiter=100, coarse_enough=-1, ctx=None):
+                 maxiter=100, coarse_enough=-1, ctx=None, precision="f64"):
+        """precision: 'f64' (FP64 throughout) or 'mixed' (amg<backend::b200<float>> hierarchy
+        under an FP64 Krylov solver, the reference's mixed-precision composition)."""
         D = dropin_lib()
         self.ptr = np.ascontiguousarray(ptr, dtype=np.int64)
         self.col = np.ascontiguousarray(col, dtype=np.int64)
@@ -414,7 +418,8 @@ class DropinSolver:
         self.n = self.ptr.size - 1
         self.ctx = ctx
         self.h = _vp()
-        rc = D.dropin_create(ctx.h if ctx is not None else None, self.n, _ptr(self.ptr),
+        create = D.dropin_create_mixed if precision == "mixed" else D.dropin_create
+        rc = create(ctx.h if ctx is not None else None, self.n, _ptr(self.ptr),
                              _ptr(self.col), _ptr(self.val), RELAX[relax], KRYLOV[krylov],
                              float(tol), int(maxiter), int(coarse_enough), _c.byref(self.h))
         if rc != 0:

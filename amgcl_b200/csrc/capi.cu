@@ -94,7 +94,7 @@ static int materialize(b200_vec_t v) {
     if (v->zero_pending) {
         if (v->len) {
             ProfScope prof(v->ctx, B200_PROF_MEMSET, (int64_t)v->len, 1, 0);
-            B200_CUDA(cudaMemsetAsync(v->ptr, 0, v->len * sizeof(double), v->ctx->stream));
+            B200_CUDA(cudaMemsetAsync(v->ptr, 0, v->len * v->esz, v->ctx->stream));
         }
         v->zero_pending = false;
     }
@@ -110,6 +110,17 @@ static int rd(b200_vec_t v, const double **p) {
 static double *wr(b200_vec_t v) {
     v->zero_pending = false;
     return v->ptr;
+}
+// typed views (FP32 vectors keep their floats behind the same pointer)
+template <class T> static inline T *tp(double *p) { return reinterpret_cast<T *>(p); }
+template <class T> static inline const T *tp(const double *p) { return reinterpret_cast<const T *>(p); }
+static inline bool all64(std::initializer_list<b200_vec_t> vs) {
+    for (b200_vec_t v : vs) if (v->dtype != B200_F64) return false;
+    return true;
+}
+static inline bool all32(std::initializer_list<b200_vec_t> vs) {
+    for (b200_vec_t v : vs) if (v->dtype != B200_F32) return false;
+    return true;
 }
 
 static int grid_for(const b200_ctx_t ctx, size_t n_items, int per_thread_items) {
@@ -137,6 +148,8 @@ static inline ncclComm_t comm_of(b200_ctx_t ctx) { return static_cast<ncclComm_t
 static inline bool same_layout(b200_vec_t a, b200_vec_t b) {
     return a->n == b->n && a->kind == b->kind && a->len == b->len;
 }
+#define B200_REQUIRE_F64_DIST(ctx, what)                                                    \
+    B200_REQUIRE(!(ctx)->dist, what ": FP32 objects are not supported on a distributed context")
 #define GUARD(ctx)                                                             \
     DeviceGuard guard__((ctx)->device);                                        \
     if (!guard__.ok) return fail(B200_ECUDA, "cudaSetDevice failed")
@@ -483,16 +496,19 @@ extern "C" int b200_ctx_get_option(b200_ctx_t ctx, const char *key, int64_t *val
 // ---------------------------------------------------------------------------
 // vectors
 // ---------------------------------------------------------------------------
-extern "C" int b200_vec_create(b200_ctx_t ctx, size_t n, b200_vec_t *out) {
+static int vec_create_typed(b200_ctx_t ctx, size_t n, int dtype, b200_vec_t *out) {
     CHECK_CTX(ctx);
     B200_REQUIRE(out != nullptr, "null output pointer");
     *out = nullptr;
+    if (dtype == B200_F32) B200_REQUIRE_F64_DIST(ctx, "b200_vec_create_f32");
     GUARD(ctx);
     b200_vec_s *v = new (std::nothrow) b200_vec_s();
     if (!v) return fail(B200_ENOMEM, "out of host memory");
     v->ctx = ctx;
     v->n = n;
     v->owned = true;
+    v->dtype = dtype;
+    v->esz = dtype == B200_F32 ? sizeof(float) : sizeof(double);
     if (ctx->dist && (int64_t)n >= ctx->dist_min_rows) {
         const Partition part((int64_t)n, ctx->nranks);
         v->kind = B200_VK_DIST;
@@ -512,7 +528,7 @@ extern "C" int b200_vec_create(b200_ctx_t ctx, size_t n, b200_vec_t *out) {
         v->cap = n;
     }
     // +2 doubles of padding so 16-byte vector accesses of the tail stay in bounds
-    cudaError_t rc = cudaMalloc(&v->ptr, (v->cap + 2) * sizeof(double));
+    cudaError_t rc = cudaMalloc(&v->ptr, (v->cap + 4) * v->esz);
     if (rc != cudaSuccess) {
         delete v;
         return cuda_fail(rc, "cudaMalloc(vector)", __FILE__, __LINE__);
@@ -528,6 +544,20 @@ extern "C" int b200_vec_create(b200_ctx_t ctx, size_t n, b200_vec_t *out) {
     }
     v->zero_pending = true;   // logically zero; memset only if somebody looks
     *out = v;
+    return B200_OK;
+}
+
+extern "C" int b200_vec_create(b200_ctx_t ctx, size_t n, b200_vec_t *out) {
+    return vec_create_typed(ctx, n, B200_F64, out);
+}
+
+extern "C" int b200_vec_create_f32(b200_ctx_t ctx, size_t n, b200_vec_t *out) {
+    return vec_create_typed(ctx, n, B200_F32, out);
+}
+
+extern "C" int b200_vec_dtype(b200_vec_t v, int *dtype) {
+    B200_REQUIRE(v && dtype, "null argument");
+    *dtype = v->dtype;
     return B200_OK;
 }
 
@@ -569,21 +599,49 @@ extern "C" int b200_vec_size(b200_vec_t v, size_t *n) {
 
 extern "C" int b200_vec_bytes(b200_vec_t v, size_t *bytes) {
     B200_REQUIRE(v && bytes, "null argument");
-    *bytes = v->len * sizeof(double);
+    *bytes = v->len * v->esz;
     return B200_OK;
 }
 
 extern "C" int b200_vec_data(b200_vec_t v, double **device_ptr) {
     B200_REQUIRE(v && device_ptr, "null argument");
+    B200_REQUIRE(v->dtype == B200_F64, "b200_vec_data: FP64 vectors only");
     GUARD(v->ctx);
     int rc = materialize(v);
     *device_ptr = v->ptr;
     return rc;
 }
 
+extern "C" int b200_vec_upload_f32(b200_vec_t v, const float *host, size_t n) {
+    B200_REQUIRE(v && (host || n == 0), "null argument");
+    B200_REQUIRE(n == v->n, "size mismatch in vector upload");
+    B200_REQUIRE(v->dtype == B200_F32 && v->kind == B200_VK_LOCAL, "upload_f32: FP32 local vector expected");
+    GUARD(v->ctx);
+    if (n) {
+        B200_CUDA(cudaMemcpyAsync(wr(v), host, n * sizeof(float), cudaMemcpyHostToDevice, v->ctx->stream));
+        B200_CUDA(cudaStreamSynchronize(v->ctx->stream));
+    }
+    v->zero_pending = false;
+    return B200_OK;
+}
+
+extern "C" int b200_vec_download_f32(b200_vec_t v, float *host, size_t n) {
+    B200_REQUIRE(v && (host || n == 0), "null argument");
+    B200_REQUIRE(n == v->n, "size mismatch in vector download");
+    B200_REQUIRE(v->dtype == B200_F32 && v->kind == B200_VK_LOCAL, "download_f32: FP32 local vector expected");
+    GUARD(v->ctx);
+    if (!n) return B200_OK;
+    int rc = materialize(v);
+    if (rc) return rc;
+    B200_CUDA(cudaMemcpyAsync(host, v->ptr, n * sizeof(float), cudaMemcpyDeviceToHost, v->ctx->stream));
+    B200_CUDA(cudaStreamSynchronize(v->ctx->stream));
+    return B200_OK;
+}
+
 extern "C" int b200_vec_upload(b200_vec_t v, const double *host, size_t n) {
     B200_REQUIRE(v && (host || n == 0), "null argument");
     B200_REQUIRE(n == v->n, "size mismatch in vector upload");
+    B200_REQUIRE(v->dtype == B200_F64, "b200_vec_upload: FP64 vector expected (use _f32)");
     GUARD(v->ctx);
     if (v->kind == B200_VK_GHOST) return B200_OK;
     if (v->len) {
@@ -599,6 +657,7 @@ extern "C" int b200_vec_upload(b200_vec_t v, const double *host, size_t n) {
 extern "C" int b200_vec_download(b200_vec_t v, double *host, size_t n) {
     B200_REQUIRE(v && (host || n == 0), "null argument");
     B200_REQUIRE(n == v->n, "size mismatch in vector download");
+    B200_REQUIRE(v->dtype == B200_F64, "b200_vec_download: FP64 vector expected (use _f32)");
     b200_ctx_t ctx = v->ctx;
     GUARD(ctx);
     if (!n) return B200_OK;
@@ -700,9 +759,9 @@ static void build_plan(int64_t nrows, const Ptr *ptr, int lanes_opt, int nnz_cap
 // Upload one CSR matrix exactly as the kernels will see it (indices narrowed to int32,
 // row-block plan built).  Single-GPU matrices come straight through here; the
 // distributed kinds hand in the local part produced by dist.cuh.
-template <class Ptr, class Col>
+template <class Ptr, class Col, class Val>
 static int csr_upload(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *ptr,
-                      const Col *col, const double *val, b200_csr_t *out) {
+                      const Col *col, const Val *val, b200_csr_t *out) {
     CHECK_CTX(ctx);
     B200_REQUIRE(out != nullptr, "null output pointer");
     *out = nullptr;
@@ -743,12 +802,13 @@ static int csr_upload(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *p
     if (!A) return fail(B200_ENOMEM, "out of host memory");
     A->ctx = ctx; A->nrows = nrows; A->ncols = ncols; A->nnz = nnz;
     A->gl_rows = nrows; A->gl_cols = ncols; A->gl_nnz = nnz;
+    A->dtype = std::is_same<Val, float>::value ? B200_F32 : B200_F64;
     A->lanes = lanes; A->rows_cap = rows_cap; A->nnz_cap = nnz_cap;
     A->nblocks = nblocks; A->nlong = nlong;
     // padding: bulk copies round sizes up to 16 bytes
     const size_t ptr_bytes = ((size_t)nrows + 1 + 8) * sizeof(int);
     const size_t col_bytes = ((size_t)nnz + 8) * sizeof(int);
-    const size_t val_bytes = ((size_t)nnz + 4) * sizeof(double);
+    const size_t val_bytes = ((size_t)nnz + 8) * sizeof(Val);
     const size_t blk_bytes = ((size_t)nblocks + 1) * sizeof(int2);
     auto cleanup = [&]() {
         if (A->ptr) cudaFree(A->ptr);
@@ -777,7 +837,7 @@ static int csr_upload(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *p
     if (nnz) {
         CSR_CUDA(cudaMemcpyAsync(A->col, hcol.data(), (size_t)nnz * sizeof(int),
                                  cudaMemcpyHostToDevice, ctx->stream));
-        CSR_CUDA(cudaMemcpyAsync(A->val, val, (size_t)nnz * sizeof(double),
+        CSR_CUDA(cudaMemcpyAsync(A->val, val, (size_t)nnz * sizeof(Val),
                                  cudaMemcpyHostToDevice, ctx->stream));
     }
     CSR_CUDA(cudaMemcpyAsync(A->blk, blk.data(), blk_bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -798,12 +858,21 @@ static void csr_free(b200_csr_t A) {
     if (A->blk_halo) cudaFree(A->blk_halo);
     if (A->halo_owned) cudaFree(A->halo_owned);
     if (A->cbuf) cudaFree(A->cbuf);
+    if (A->scratch64) cudaFree(A->scratch64);
     if (A->pb_local) peer_release(A->ctx, A->pb_local, A->pb_peer);
     delete A;
 }
 
 // The public constructor: on a distributed context decide from the shape which
 // kind of operator this is (see dist.cuh) and keep only this rank's share.
+template <class Ptr, class Col>
+static int csr_create_f32(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *ptr,
+                          const Col *col, const float *val, b200_csr_t *out) {
+    CHECK_CTX(ctx);
+    B200_REQUIRE_F64_DIST(ctx, "b200_csr_create_*_f32");
+    return csr_upload(ctx, nrows, ncols, ptr, col, val, out);
+}
+
 template <class Ptr, class Col>
 static int csr_create(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *ptr,
                       const Col *col, const double *val, b200_csr_t *out) {
@@ -973,18 +1042,24 @@ static int csr_create(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *p
 }
 
 // ---- launch one streaming pass over A ------------------------------------------------
-template <int MODE, int L, bool HALO>
-static int launch_csr_LH(b200_ctx_t ctx, b200_csr_t A, const CsrArgs &args) {
-    const StageLayout lay = stage_layout(A->rows_cap, A->nnz_cap);
-    if (ctx->opt_spmv_variant == 0) {
+// P = precision combination (csr_kernels.cuh).  Only FP64 carries the multi-GPU halo path
+// and the one-block-per-CTA cross-check variant; the mixed-precision combinations use the
+// persistent ring only.
+template <int MODE, int L, bool HALO, class P>
+static int launch_csr_LH(b200_ctx_t ctx, b200_csr_t A, const CsrArgsT<P> &args) {
+    constexpr bool fp64 = std::is_same<P, PrecDD>::value;
+    const StageLayout lay = stage_layout(A->rows_cap, A->nnz_cap, (int)sizeof(typename P::TV));
+    if (fp64 && ctx->opt_spmv_variant == 0) {
         const int smem = kHeaderBytes + lay.bytes;
         static bool attr_set[64] = {};   // per instantiation and device
         if (!attr_set[ctx->device & 63]) {
-            B200_CUDA(cudaFuncSetAttribute(csr_block_kernel<MODE, L, HALO>,
+            B200_CUDA(cudaFuncSetAttribute(csr_block_kernel<MODE, L, HALO, PrecDD>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             attr_set[ctx->device & 63] = true;
         }
-        csr_block_kernel<MODE, L, HALO><<<(unsigned)A->nblocks, kThreads, smem, ctx->stream>>>(args);
+        // (only reachable with P == PrecDD)
+        csr_block_kernel<MODE, L, HALO, PrecDD><<<(unsigned)A->nblocks, kThreads, smem, ctx->stream>>>(
+            *reinterpret_cast<const CsrArgsT<PrecDD> *>(&args));
     } else {
         int stages = (int)ctx->opt_stages;
         const int max_smem = 227 * 1024;
@@ -993,27 +1068,30 @@ static int launch_csr_LH(b200_ctx_t ctx, b200_csr_t A, const CsrArgs &args) {
         const int smem = kHeaderBytes + stages * lay.bytes;
         static bool attr_set[64] = {};
         if (!attr_set[ctx->device & 63]) {
-            B200_CUDA(cudaFuncSetAttribute(csr_ring_kernel<MODE, L, HALO>,
+            B200_CUDA(cudaFuncSetAttribute(csr_ring_kernel<MODE, L, HALO, P>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
             attr_set[ctx->device & 63] = true;
         }
         const int64_t cap = (int64_t)ctx->sm_count * ctx->opt_ctas_per_sm;
         const unsigned grid = (unsigned)std::min<int64_t>(A->nblocks, cap);
-        csr_ring_kernel<MODE, L, HALO><<<grid, kThreads, smem, ctx->stream>>>(args, stages);
+        csr_ring_kernel<MODE, L, HALO, P><<<grid, kThreads, smem, ctx->stream>>>(args, stages);
     }
     B200_CHECK_LAUNCH();
     ctx->launches++;
     return B200_OK;
 }
 
-template <int MODE, int L>
-static int launch_csr_L(b200_ctx_t ctx, b200_csr_t A, const CsrArgs &args) {
-    if (args.xh) return launch_csr_LH<MODE, L, true>(ctx, A, args);
-    return launch_csr_LH<MODE, L, false>(ctx, A, args);
+template <int MODE, int L, class P>
+static int launch_csr_L(b200_ctx_t ctx, b200_csr_t A, const CsrArgsT<P> &args) {
+    if (std::is_same<P, PrecDD>::value && args.xh)
+        return launch_csr_LH<MODE, L, true, PrecDD>(ctx, A, *reinterpret_cast<const CsrArgsT<PrecDD> *>(&args));
+    return launch_csr_LH<MODE, L, false, P>(ctx, A, args);
 }
 
-template <int MODE>
-static int launch_csr_dispatch(b200_ctx_t ctx, b200_csr_t A, const CsrArgs &args) {
+template <int MODE, class P>
+static int launch_csr(b200_ctx_t ctx, b200_csr_t A, const CsrArgsT<P> &args) {
+    if (A->nblocks == 0) return B200_OK;
+    ProfScope prof(ctx, MODE, A->nrows, A->ncols, A->nnz);
     switch (A->lanes) {
     case 1:  return launch_csr_L<MODE, 1>(ctx, A, args);
     case 2:  return launch_csr_L<MODE, 2>(ctx, A, args);
@@ -1024,32 +1102,39 @@ static int launch_csr_dispatch(b200_ctx_t ctx, b200_csr_t A, const CsrArgs &args
     }
 }
 
-template <int MODE>
-static int launch_csr(b200_ctx_t ctx, b200_csr_t A, const CsrArgs &args) {
-    if (A->nblocks == 0) return B200_OK;
-    ProfScope prof(ctx, MODE, A->nrows, A->ncols, A->nnz);
-    return launch_csr_dispatch<MODE>(ctx, A, args);
-}
-
-static CsrArgs base_args(b200_csr_t A) {
-    CsrArgs a;
+template <class P>
+static CsrArgsT<P> base_args_t(b200_csr_t A) {
+    CsrArgsT<P> a;
     memset(&a, 0, sizeof(a));
-    a.ptr = A->ptr; a.col = A->col; a.val = A->val; a.blk = A->blk;
+    a.ptr = A->ptr; a.col = A->col; a.val = static_cast<const typename P::TV *>(A->val); a.blk = A->blk;
     a.nrows = (int)A->nrows; a.nblocks = (int)A->nblocks;
     a.rows_cap = A->rows_cap; a.nnz_cap = A->nnz_cap;
     return a;
 }
+static CsrArgs base_args(b200_csr_t A) { return base_args_t<PrecDD>(A); }
 
-// ---- element-wise launch helper ---------------------------------------------------------
-template <class F, bool RY, bool RZ>
-static int launch_ew(b200_ctx_t ctx, size_t n, F f, const double *x, const double *y,
-                     const double *z, double *out) {
+// ---- element-wise launch helpers ----------------------------------------------------------
+// all streams of one element type T: 16-byte vector path when aligned
+template <class F, bool RY, bool RZ, class T>
+static int launch_ew(b200_ctx_t ctx, size_t n, F f, const T *x, const T *y, const T *z, T *out) {
     if (n == 0) return B200_OK;
     const bool vec_ok = aligned16(x) && aligned16(out) && (!RY || aligned16(y)) &&
                         (!RZ || aligned16(z));
-    const int grid = grid_for(ctx, n, 4);
+    const int grid = grid_for(ctx, n, 16 / (int)sizeof(T) * 2);
     ProfScope prof(ctx, B200_PROF_VECTOR + (RY ? 1 : 0) + (RZ ? 1 : 0), (int64_t)n, 1, 0);
-    ew_kernel<F, RY, RZ><<<grid, kThreads, 0, ctx->stream>>>(n, f, x, y, z, out, vec_ok);
+    ew_kernel_same<F, RY, RZ, T><<<grid, kThreads, 0, ctx->stream>>>(n, f, x, y, z, out, vec_ok);
+    B200_CHECK_LAUNCH();
+    ctx->launches++;
+    return B200_OK;
+}
+// mixed element types (FP32 inputs accumulated into an FP64 vector, precision-changing copy)
+template <class F, bool RY, bool RZ, class TX, class TY, class TZ, class TO>
+static int launch_ew_mixed(b200_ctx_t ctx, size_t n, F f, const TX *x, const TY *y, const TZ *z,
+                           TO *out) {
+    if (n == 0) return B200_OK;
+    const int grid = grid_for(ctx, n, 2);
+    ProfScope prof(ctx, B200_PROF_VECTOR + (RY ? 1 : 0) + (RZ ? 1 : 0), (int64_t)n, 1, 0);
+    ew_kernel<F, RY, RZ, TX, TY, TZ, TO><<<grid, kThreads, 0, ctx->stream>>>(n, f, x, y, z, out, false);
     B200_CHECK_LAUNCH();
     ctx->launches++;
     return B200_OK;
@@ -1310,6 +1395,24 @@ extern "C" int b200_csr_create_i32(b200_ctx_t ctx, int64_t nrows, int64_t ncols,
     return csr_create(ctx, nrows, ncols, ptr, col, val, A);
 }
 
+extern "C" int b200_csr_create_i64_f32(b200_ctx_t ctx, int64_t nrows, int64_t ncols,
+                                       const int64_t *ptr, const int64_t *col, const float *val,
+                                       b200_csr_t *A) {
+    return csr_create_f32(ctx, nrows, ncols, ptr, col, val, A);
+}
+
+extern "C" int b200_csr_create_i32_f32(b200_ctx_t ctx, int64_t nrows, int64_t ncols,
+                                       const int32_t *ptr, const int32_t *col, const float *val,
+                                       b200_csr_t *A) {
+    return csr_create_f32(ctx, nrows, ncols, ptr, col, val, A);
+}
+
+extern "C" int b200_csr_dtype(b200_csr_t A, int *dtype) {
+    B200_REQUIRE(A && dtype, "null argument");
+    *dtype = A->dtype;
+    return B200_OK;
+}
+
 extern "C" int b200_plan_i64(int64_t nrows, const int64_t *ptr, int lanes, int nnz_cap,
                              int32_t *blk_out, int64_t blk_capacity, int64_t *nblocks,
                              int *lanes_out, int *rows_cap_out, int64_t *nlong_out) {
@@ -1372,6 +1475,43 @@ extern "C" int b200_csr_plan(b200_csr_t A, int *lanes_per_row, int64_t *n_blocks
 // ---------------------------------------------------------------------------
 // primitives
 // ---------------------------------------------------------------------------
+namespace b200 {
+
+template <class P>
+static int spmv_local(b200_ctx_t ctx, double alpha, b200_csr_t A, b200_vec_t x, double beta,
+                      b200_vec_t y) {
+    CsrArgsT<P> a = base_args_t<P>(A);
+    const double *px;
+    int rc = rd(x, &px);
+    if (rc) return rc;
+    a.x = tp<typename P::TX>(px);
+    a.alpha = alpha; a.beta = beta;
+    if (beta == 0.0 || y->zero_pending) {
+        a.y = tp<typename P::TY>(wr(y));
+        return launch_csr<MODE_SPMV>(ctx, A, a);
+    }
+    a.y = tp<typename P::TY>(y->ptr);
+    return launch_csr<MODE_SPMV_ACC>(ctx, A, a);
+}
+
+template <class P>
+static int residual_local(b200_ctx_t ctx, b200_vec_t f, b200_csr_t A, b200_vec_t x, b200_vec_t r) {
+    CsrArgsT<P> a = base_args_t<P>(A);
+    const double *px, *pf;
+    int rc = rd(x, &px);
+    if (rc) return rc;
+    rc = rd(f, &pf);
+    if (rc) return rc;
+    a.x = tp<typename P::TX>(px);
+    a.f = tp<typename P::TF>(pf);
+    a.y = tp<typename P::TY>((f == r) ? r->ptr : wr(r));
+    return launch_csr<MODE_RESID>(ctx, A, a);
+}
+
+#define B200_BAD_MIX(what) fail(B200_EINVAL, what ": unsupported precision combination")
+
+} // namespace b200
+
 extern "C" int b200_spmv(b200_ctx_t ctx, double alpha, b200_csr_t A, b200_vec_t x, double beta,
                          b200_vec_t y) {
     CHECK_CTX(ctx);
@@ -1381,6 +1521,15 @@ extern "C" int b200_spmv(b200_ctx_t ctx, double alpha, b200_csr_t A, b200_vec_t 
     B200_REQUIRE(x != y && (x->ptr != y->ptr || !x->ptr), "spmv: x and y must not alias");
     if (A->kind == B200_CK_GHOST) return B200_OK;          // operator lives on rank 0
     GUARD(ctx);
+    if (A->dtype == B200_F32) {
+        // FP32 operator (mixed-precision hierarchy): single GPU, persistent ring kernels
+        if (all32({x, y})) return spmv_local<PrecFF>(ctx, alpha, A, x, beta, y);
+        if (all64({x, y})) return spmv_local<PrecFD>(ctx, alpha, A, x, beta, y);
+        if (x->dtype == B200_F32 && y->dtype == B200_F64)
+            return spmv_local<PrecFFD>(ctx, alpha, A, x, beta, y);
+        return B200_BAD_MIX("spmv");
+    }
+    if (!all64({x, y})) return B200_BAD_MIX("spmv");
     CsrArgs a = base_args(A);
     a.alpha = alpha; a.beta = beta;
     int rc;
@@ -1427,6 +1576,13 @@ extern "C" int b200_residual(b200_ctx_t ctx, b200_vec_t f, b200_csr_t A, b200_ve
     B200_REQUIRE(A->kind == B200_CK_LOCAL || A->kind == B200_CK_SQUARE,
                  "residual: operator must be square");
     GUARD(ctx);
+    if (A->dtype == B200_F32) {
+        if (all32({f, x, r})) return residual_local<PrecFF>(ctx, f, A, x, r);
+        if (all64({f, x, r})) return residual_local<PrecFD>(ctx, f, A, x, r);
+        if (all64({f, x}) && r->dtype == B200_F32) return residual_local<PrecFDF>(ctx, f, A, x, r);
+        return B200_BAD_MIX("residual");
+    }
+    if (!all64({f, x, r})) return B200_BAD_MIX("residual");
     CsrArgs a = base_args(A);
     int rc = rd(x, &a.x);
     if (rc) return rc;
@@ -1465,13 +1621,31 @@ extern "C" int b200_copy(b200_ctx_t ctx, b200_vec_t x, b200_vec_t y) {
         return B200_OK;
     }
     GUARD(ctx);
-    return launch_ew<CopyF, false, false>(ctx, x->len, CopyF(), x->ptr, nullptr, nullptr, wr(y));
+    if (all64({x, y}))
+        return launch_ew<CopyF<double>, false, false, double>(ctx, x->len, CopyF<double>(), x->ptr, nullptr, nullptr, wr(y));
+    if (all32({x, y}))
+        return launch_ew<CopyF<float>, false, false, float>(ctx, x->len, CopyF<float>(), tp<float>(x->ptr), nullptr, nullptr, tp<float>(wr(y)));
+    if (x->dtype == B200_F64)      // precision-changing copies
+        return launch_ew_mixed<CopyF<float>, false, false>(ctx, x->len, CopyF<float>(), x->ptr, (const float *)nullptr, (const float *)nullptr, tp<float>(wr(y)));
+    return launch_ew_mixed<CopyF<double>, false, false>(ctx, x->len, CopyF<double>(), tp<float>(x->ptr), (const double *)nullptr, (const double *)nullptr, wr(y));
 }
+
+namespace b200 {
+template <class T>
+static void launch_dot_kernel(b200_ctx_t ctx, b200_vec_t x, b200_vec_t y, double *result_dev) {
+    const bool vec_ok = aligned16(x->ptr) && aligned16(y->ptr);
+    const int grid = std::min(grid_for(ctx, x->len, 32 / (int)sizeof(T) * 2), kDotMaxBlocks);
+    ProfScope prof(ctx, B200_PROF_DOT, (int64_t)x->len, 1, 0);
+    dot_kernel<T><<<grid, kThreads, 0, ctx->stream>>>(x->len, tp<T>(x->ptr), tp<T>(y->ptr), ctx->dot_partial,
+                                                      ctx->dot_ticket, result_dev, vec_ok);
+}
+} // namespace b200
 
 extern "C" int b200_dot(b200_ctx_t ctx, b200_vec_t x, b200_vec_t y, double *result) {
     CHECK_CTX(ctx);
     B200_REQUIRE(x && y && result, "null argument");
     B200_REQUIRE(same_layout(x, y), "dot: size mismatch");
+    if (x->dtype != y->dtype) return B200_BAD_MIX("dot");
     GUARD(ctx);
     const bool dist = x->kind == B200_VK_DIST;
     const bool trivial = x->len == 0 || x->zero_pending || y->zero_pending || x->kind == B200_VK_GHOST;
@@ -1481,29 +1655,20 @@ extern "C" int b200_dot(b200_ctx_t ctx, b200_vec_t x, b200_vec_t y, double *resu
             *result = 0.0;
             return B200_OK;
         }
-        const bool vec_ok = aligned16(x->ptr) && aligned16(y->ptr);
-        int grid = std::min(grid_for(ctx, x->len, 8), kDotMaxBlocks);
-        {
-            ProfScope prof(ctx, B200_PROF_DOT, (int64_t)x->len, 1, 0);
-            dot_kernel<<<grid, kThreads, 0, ctx->stream>>>(x->len, x->ptr, y->ptr, ctx->dot_partial,
-                                                           ctx->dot_ticket, ctx->dot_result_d, vec_ok);
-        }
+        if (x->dtype == B200_F64) launch_dot_kernel<double>(ctx, x, y, ctx->dot_result_d);
+        else launch_dot_kernel<float>(ctx, x, y, ctx->dot_result_d);
         B200_CHECK_LAUNCH();
         ctx->launches++;
         B200_CUDA(cudaStreamSynchronize(ctx->stream));
         *result = *reinterpret_cast<volatile double *>(ctx->dot_result_h);
         return B200_OK;
     }
-    // partitioned vectors: local partial -> device scalar -> ncclAllReduce -> host
+    // partitioned vectors: local partial -> device scalar -> all-reduce -> host
     // (mpi/inner_product.hpp:53-62 does the same with MPI_Allreduce on the host)
     if (trivial) {
         B200_CUDA(cudaMemsetAsync(ctx->dot_dev, 0, sizeof(double), ctx->stream));
     } else {
-        const bool vec_ok = aligned16(x->ptr) && aligned16(y->ptr);
-        int grid = std::min(grid_for(ctx, x->len, 8), kDotMaxBlocks);
-        ProfScope prof(ctx, B200_PROF_DOT, (int64_t)x->len, 1, 0);
-        dot_kernel<<<grid, kThreads, 0, ctx->stream>>>(x->len, x->ptr, y->ptr, ctx->dot_partial,
-                                                       ctx->dot_ticket, ctx->dot_dev, vec_ok);
+        launch_dot_kernel<double>(ctx, x, y, ctx->dot_dev);
         B200_CHECK_LAUNCH();
         ctx->launches++;
     }
@@ -1539,21 +1704,58 @@ extern "C" int b200_dot(b200_ctx_t ctx, b200_vec_t x, b200_vec_t y, double *resu
     return B200_OK;
 }
 
+namespace b200 {
+template <class T>
+static int axpby_t(b200_ctx_t ctx, double a, b200_vec_t x, double b, b200_vec_t y) {
+    const double *px;
+    int rc = rd(x, &px);
+    if (rc) return rc;
+    if (b == 0.0 || y->zero_pending) {
+        AxF<T> f{(T)a};
+        return launch_ew<AxF<T>, false, false, T>(ctx, x->len, f, tp<T>(px), nullptr, nullptr, tp<T>(wr(y)));
+    }
+    AxpbyF<T> f{(T)a, (T)b};
+    return launch_ew<AxpbyF<T>, true, false, T>(ctx, x->len, f, tp<T>(px), tp<T>(y->ptr), nullptr, tp<T>(y->ptr));
+}
+template <class T>
+static int axpbypcz_t(b200_ctx_t ctx, double a, b200_vec_t x, double b, b200_vec_t y, double c, b200_vec_t z) {
+    const double *px, *py;
+    int rc = rd(x, &px);
+    if (rc) return rc;
+    rc = rd(y, &py);
+    if (rc) return rc;
+    if (c == 0.0 || z->zero_pending) {
+        AxpbyF<T> f{(T)a, (T)b};
+        return launch_ew<AxpbyF<T>, true, false, T>(ctx, x->len, f, tp<T>(px), tp<T>(py), nullptr, tp<T>(wr(z)));
+    }
+    AxpbypczF<T> f{(T)a, (T)b, (T)c};
+    return launch_ew<AxpbypczF<T>, true, true, T>(ctx, x->len, f, tp<T>(px), tp<T>(py), tp<T>(z->ptr), tp<T>(z->ptr));
+}
+template <class T>
+static int vmul_t(b200_ctx_t ctx, double alpha, b200_vec_t x, b200_vec_t y, double beta, b200_vec_t z) {
+    const double *px, *py;
+    int rc = rd(x, &px);
+    if (rc) return rc;
+    rc = rd(y, &py);
+    if (rc) return rc;
+    if (beta == 0.0 || z->zero_pending) {
+        VmulF<T> f{(T)alpha};
+        return launch_ew<VmulF<T>, true, false, T>(ctx, x->len, f, tp<T>(px), tp<T>(py), nullptr, tp<T>(wr(z)));
+    }
+    VmulAccF<T> f{(T)alpha, (T)beta};
+    return launch_ew<VmulAccF<T>, true, true, T>(ctx, x->len, f, tp<T>(px), tp<T>(py), tp<T>(z->ptr), tp<T>(z->ptr));
+}
+} // namespace b200
+
 extern "C" int b200_axpby(b200_ctx_t ctx, double a, b200_vec_t x, double b, b200_vec_t y) {
     CHECK_CTX(ctx);
     B200_REQUIRE(x && y, "null argument");
     B200_REQUIRE(same_layout(x, y), "axpby: size mismatch");
     if (x->kind == B200_VK_GHOST) return B200_OK;
     GUARD(ctx);
-    const double *px;
-    int rc = rd(x, &px);
-    if (rc) return rc;
-    if (b == 0.0 || y->zero_pending) {
-        AxF f{a};
-        return launch_ew<AxF, false, false>(ctx, x->len, f, px, nullptr, nullptr, wr(y));
-    }
-    AxpbyF f{a, b};
-    return launch_ew<AxpbyF, true, false>(ctx, x->len, f, px, y->ptr, nullptr, y->ptr);
+    if (all64({x, y})) return axpby_t<double>(ctx, a, x, b, y);
+    if (all32({x, y})) return axpby_t<float>(ctx, a, x, b, y);
+    return B200_BAD_MIX("axpby");
 }
 
 extern "C" int b200_axpbypcz(b200_ctx_t ctx, double a, b200_vec_t x, double b, b200_vec_t y,
@@ -1563,17 +1765,9 @@ extern "C" int b200_axpbypcz(b200_ctx_t ctx, double a, b200_vec_t x, double b, b
     B200_REQUIRE(same_layout(x, y) && same_layout(x, z), "axpbypcz: size mismatch");
     if (x->kind == B200_VK_GHOST) return B200_OK;
     GUARD(ctx);
-    const double *px, *py;
-    int rc = rd(x, &px);
-    if (rc) return rc;
-    rc = rd(y, &py);
-    if (rc) return rc;
-    if (c == 0.0 || z->zero_pending) {
-        AxpbyZF f{a, b};
-        return launch_ew<AxpbyZF, true, false>(ctx, x->len, f, px, py, nullptr, wr(z));
-    }
-    AxpbypczF f{a, b, c};
-    return launch_ew<AxpbypczF, true, true>(ctx, x->len, f, px, py, z->ptr, z->ptr);
+    if (all64({x, y, z})) return axpbypcz_t<double>(ctx, a, x, b, y, c, z);
+    if (all32({x, y, z})) return axpbypcz_t<float>(ctx, a, x, b, y, c, z);
+    return B200_BAD_MIX("axpbypcz");
 }
 
 extern "C" int b200_vmul(b200_ctx_t ctx, double alpha, b200_vec_t x, b200_vec_t y, double beta,
@@ -1583,22 +1777,48 @@ extern "C" int b200_vmul(b200_ctx_t ctx, double alpha, b200_vec_t x, b200_vec_t 
     B200_REQUIRE(same_layout(x, y) && same_layout(x, z), "vmul: size mismatch");
     if (x->kind == B200_VK_GHOST) return B200_OK;
     GUARD(ctx);
-    const double *px, *py;
-    int rc = rd(x, &px);
-    if (rc) return rc;
-    rc = rd(y, &py);
-    if (rc) return rc;
-    if (beta == 0.0 || z->zero_pending) {
-        VmulF f{alpha};
-        return launch_ew<VmulF, true, false>(ctx, x->len, f, px, py, nullptr, wr(z));
+    if (all64({x, y, z})) return vmul_t<double>(ctx, alpha, x, y, beta, z);
+    if (all32({x, y, z})) return vmul_t<float>(ctx, alpha, x, y, beta, z);
+    if (all32({x, y}) && z->dtype == B200_F64) {
+        // FP32 smoother diagonal and residual accumulated into an FP64 iterate
+        const double *px, *py;
+        int rc = rd(x, &px);
+        if (rc) return rc;
+        rc = rd(y, &py);
+        if (rc) return rc;
+        if (beta == 0.0 || z->zero_pending) {
+            VmulF<double> f{alpha};
+            return launch_ew_mixed<VmulF<double>, true, false>(ctx, x->len, f, tp<float>(px), tp<float>(py),
+                                                               (const double *)nullptr, wr(z));
+        }
+        VmulAccF<double> f{alpha, beta};
+        return launch_ew_mixed<VmulAccF<double>, true, true>(ctx, x->len, f, tp<float>(px), tp<float>(py),
+                                                            (const double *)z->ptr, z->ptr);
     }
-    VmulAccF f{alpha, beta};
-    return launch_ew<VmulAccF, true, true>(ctx, x->len, f, px, py, z->ptr, z->ptr);
+    return B200_BAD_MIX("vmul");
 }
 
 // ---------------------------------------------------------------------------
 // smoother sweep
 // ---------------------------------------------------------------------------
+namespace b200 {
+
+template <class TD, class TF, class TX>
+static int relax_zero_t(b200_ctx_t ctx, double omega, const double *pd, const double *pf, b200_vec_t x) {
+    if (x->len) {
+        const int grid = grid_for(ctx, x->len, 2);
+        ProfScope prof(ctx, B200_PROF_RELAX_ZERO, (int64_t)x->len, 1, 0);
+        relax_zero_kernel<TD, TF, TX><<<grid, kThreads, 0, ctx->stream>>>(x->len, omega, tp<TD>(pd), tp<TF>(pf),
+                                                                          tp<TX>(wr(x)));
+        B200_CHECK_LAUNCH();
+        ctx->launches++;
+    }
+    x->zero_pending = false;
+    return B200_OK;
+}
+
+} // namespace b200
+
 extern "C" int b200_relax(b200_ctx_t ctx, b200_csr_t A, b200_vec_t rhs, b200_vec_t x,
                           b200_vec_t tmp, b200_vec_t diag, double omega) {
     CHECK_CTX(ctx);
@@ -1611,6 +1831,16 @@ extern "C" int b200_relax(b200_ctx_t ctx, b200_csr_t A, b200_vec_t rhs, b200_vec
     if (A->kind == B200_CK_GHOST) return B200_OK;
     B200_REQUIRE(x->ptr != tmp->ptr, "relax: x and tmp must not alias");
     GUARD(ctx);
+
+    // precision combination: 0 = FP64 throughout, 1 = FP32 throughout,
+    // 2 = FP32 operator + diagonal sweeping an FP64 iterate (finest level of a mixed hierarchy;
+    //     tmp is that level's FP32 scratch)
+    int mix = -1;
+    if (A->dtype == B200_F64 && all64({rhs, x, tmp, diag})) mix = 0;
+    else if (A->dtype == B200_F32 && all32({rhs, x, tmp, diag})) mix = 1;
+    else if (A->dtype == B200_F32 && all64({rhs, x}) && all32({tmp, diag})) mix = 2;
+    if (mix < 0) return B200_BAD_MIX("relax");
+
     const double *pf, *pd;
     int rc = rd(rhs, &pf);
     if (rc) return rc;
@@ -1619,15 +1849,9 @@ extern "C" int b200_relax(b200_ctx_t ctx, b200_csr_t A, b200_vec_t rhs, b200_vec
 
     if (x->zero_pending && ctx->opt_zero_shortcut) {
         // residual(rhs, A, 0) == rhs exactly, so the sweep reduces to a scaling
-        if (x->len) {
-            const int grid = grid_for(ctx, x->len, 2);
-            ProfScope prof(ctx, B200_PROF_RELAX_ZERO, (int64_t)x->len, 1, 0);
-            relax_zero_kernel<<<grid, kThreads, 0, ctx->stream>>>(x->len, omega, pd, pf, wr(x));
-            B200_CHECK_LAUNCH();
-            ctx->launches++;
-        }
-        x->zero_pending = false;
-        return B200_OK;
+        if (mix == 0) return relax_zero_t<double, double, double>(ctx, omega, pd, pf, x);
+        if (mix == 1) return relax_zero_t<float, float, float>(ctx, omega, pd, pf, x);
+        return relax_zero_t<float, double, double>(ctx, omega, pd, pf, x);
     }
 
     if (!ctx->opt_fuse_relax) {
@@ -1635,6 +1859,37 @@ extern "C" int b200_relax(b200_ctx_t ctx, b200_csr_t A, b200_vec_t rhs, b200_vec
         rc = b200_residual(ctx, rhs, A, x, tmp);
         if (rc) return rc;
         return b200_vmul(ctx, omega, diag, tmp, 1.0, x);
+    }
+
+    if (mix == 1) {
+        CsrArgsT<PrecFF> a = base_args_t<PrecFF>(A);
+        const double *px;
+        rc = rd(x, &px);
+        if (rc) return rc;
+        a.x = tp<float>(px); a.f = tp<float>(pf); a.d = tp<float>(pd); a.alpha = omega;
+        a.y = tp<float>(wr(tmp));
+        rc = launch_csr<MODE_RELAX>(ctx, A, a);
+        if (rc) return rc;
+        if (x->owned && tmp->owned && x->cap == tmp->cap) std::swap(x->ptr, tmp->ptr);
+        else B200_CUDA(cudaMemcpyAsync(x->ptr, tmp->ptr, x->len * x->esz, cudaMemcpyDeviceToDevice, ctx->stream));
+        return B200_OK;
+    }
+    if (mix == 2) {
+        // the new FP64 iterate cannot live in the level's FP32 scratch: the operator owns an
+        // FP64 buffer that trades places with x exactly like tmp does in the uniform case
+        if (!A->scratch64)
+            B200_CUDA(cudaMalloc(&A->scratch64, ((size_t)A->nrows + 4) * sizeof(double)));
+        CsrArgsT<PrecFD> a = base_args_t<PrecFD>(A);
+        const double *px;
+        rc = rd(x, &px);
+        if (rc) return rc;
+        a.x = px; a.f = pf; a.d = tp<float>(pd); a.alpha = omega;
+        a.y = A->scratch64;
+        rc = launch_csr<MODE_RELAX>(ctx, A, a);
+        if (rc) return rc;
+        if (x->owned && x->cap == (size_t)A->nrows) std::swap(x->ptr, A->scratch64);
+        else B200_CUDA(cudaMemcpyAsync(x->ptr, A->scratch64, x->len * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        return B200_OK;
     }
 
     CsrArgs a = base_args(A);
@@ -1663,9 +1918,9 @@ extern "C" int b200_relax(b200_ctx_t ctx, b200_csr_t A, b200_vec_t rhs, b200_vec
 // ---------------------------------------------------------------------------
 namespace b200 {
 
-template <class Ptr, class Col>
+template <class Ptr, class Col, class Val>
 static int coarse_create(b200_ctx_t ctx, int64_t n, const Ptr *ptr, const Col *col,
-                         const double *val, b200_coarse_t *out) {
+                         const Val *val, b200_coarse_t *out) {
     CHECK_CTX(ctx);
     B200_REQUIRE(out != nullptr, "null output pointer");
     *out = nullptr;
@@ -1691,6 +1946,9 @@ static int coarse_create(b200_ctx_t ctx, int64_t n, const Ptr *ptr, const Col *c
         hcol[(size_t)e] = (int32_t)c;
     }
 
+    // the inverse is always formed and kept in FP64, whatever the hierarchy's precision
+    std::vector<double> hval((size_t)nnz);
+    for (int64_t e = 0; e < nnz; ++e) hval[(size_t)e] = (double)val[e];
     const int N = (int)n;
     int *dptr = nullptr, *dcol = nullptr, *dpiv = nullptr;
     double *dval = nullptr, *M = nullptr, *colk = nullptr, *pivval = nullptr, *Ainv = nullptr;
@@ -1720,7 +1978,7 @@ static int coarse_create(b200_ctx_t ctx, int64_t n, const Ptr *ptr, const Col *c
     CO_CUDA(cudaMemcpyAsync(dptr, hptr.data(), ((size_t)N + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
     if (nnz) {
         CO_CUDA(cudaMemcpyAsync(dcol, hcol.data(), (size_t)nnz * sizeof(int), cudaMemcpyHostToDevice, st));
-        CO_CUDA(cudaMemcpyAsync(dval, val, (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice, st));
+        CO_CUDA(cudaMemcpyAsync(dval, hval.data(), (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice, st));
     }
     CO_CUDA(cudaMemsetAsync(M, 0, Mbytes, st));
     coarse_scatter_kernel<<<(N + 127) / 128, 128, 0, st>>>(N, dptr, dcol, dval, M);
@@ -1768,6 +2026,7 @@ static int coarse_create(b200_ctx_t ctx, int64_t n, const Ptr *ptr, const Col *c
         return fail(B200_ENOMEM, "out of host memory");
     }
     S->ctx = ctx; S->n = n; S->Ainv = Ainv; S->bytes = (size_t)N * N * sizeof(double);
+    S->dtype = std::is_same<Val, float>::value ? B200_F32 : B200_F64;
     if (replicated) {
         // the coarsest level is itself partitioned: every rank keeps the inverse and
         // applies its own rows to the all-gathered right-hand side
@@ -1793,6 +2052,19 @@ extern "C" int b200_coarse_create_i64(b200_ctx_t ctx, int64_t n, const int64_t *
 }
 extern "C" int b200_coarse_create_i32(b200_ctx_t ctx, int64_t n, const int32_t *ptr,
                                       const int32_t *col, const double *val, b200_coarse_t *S) {
+    return coarse_create(ctx, n, ptr, col, val, S);
+}
+
+extern "C" int b200_coarse_create_i64_f32(b200_ctx_t ctx, int64_t n, const int64_t *ptr,
+                                          const int64_t *col, const float *val, b200_coarse_t *S) {
+    CHECK_CTX(ctx);
+    B200_REQUIRE_F64_DIST(ctx, "b200_coarse_create_*_f32");
+    return coarse_create(ctx, n, ptr, col, val, S);
+}
+extern "C" int b200_coarse_create_i32_f32(b200_ctx_t ctx, int64_t n, const int32_t *ptr,
+                                          const int32_t *col, const float *val, b200_coarse_t *S) {
+    CHECK_CTX(ctx);
+    B200_REQUIRE_F64_DIST(ctx, "b200_coarse_create_*_f32");
     return coarse_create(ctx, n, ptr, col, val, S);
 }
 
@@ -1829,7 +2101,7 @@ extern "C" int b200_coarse_solve(b200_ctx_t ctx, b200_coarse_t S, b200_vec_t rhs
         const int nloc = (int)x->len;
         if (nloc) {
             ProfScope prof(ctx, B200_PROF_COARSE, nloc, S->n, (int64_t)nloc * S->n);
-            coarse_gemv_kernel<<<(nloc + warps_per_cta - 1) / warps_per_cta, kThreads, 0, ctx->stream>>>(
+            coarse_gemv_kernel<double><<<(nloc + warps_per_cta - 1) / warps_per_cta, kThreads, 0, ctx->stream>>>(
                 N, (int)x->off, nloc, S->Ainv, S->gbuf, wr(x));
             B200_CHECK_LAUNCH();
             ctx->launches++;
@@ -1840,11 +2112,16 @@ extern "C" int b200_coarse_solve(b200_ctx_t ctx, b200_coarse_t S, b200_vec_t rhs
     B200_REQUIRE(rhs->kind == B200_VK_LOCAL && x->kind == B200_VK_LOCAL,
                  "coarse solve: vectors must live on this rank");
     B200_REQUIRE(rhs != x && rhs->ptr != x->ptr, "coarse solve: rhs and x must not alias");
+    if (rhs->dtype != x->dtype) return B200_BAD_MIX("coarse solve");
     const double *pr;
     int rc = rd(rhs, &pr);
     if (rc) return rc;
     ProfScope prof(ctx, B200_PROF_COARSE, S->n, S->n, S->n * S->n);
-    coarse_gemv_kernel<<<(N + warps_per_cta - 1) / warps_per_cta, kThreads, 0, ctx->stream>>>(
+    if (rhs->dtype == B200_F32)
+        coarse_gemv_kernel<float><<<(N + warps_per_cta - 1) / warps_per_cta, kThreads, 0, ctx->stream>>>(
+            N, 0, N, S->Ainv, tp<float>(pr), tp<float>(wr(x)));
+    else
+    coarse_gemv_kernel<double><<<(N + warps_per_cta - 1) / warps_per_cta, kThreads, 0, ctx->stream>>>(
         N, 0, N, S->Ainv, pr, wr(x));
     B200_CHECK_LAUNCH();
     ctx->launches++;

@@ -111,18 +111,19 @@ __global__ void coarse_extract_kernel(int n, const double *__restrict__ M, doubl
 // x[0:nloc) = Ainv[row0 : row0+nloc, :] * rhs : one warp per row, coalesced row reads,
 // shuffle reduction.  (row0, nloc) select this rank's rows when the coarsest level is
 // itself partitioned; single GPU: row0 = 0, nloc = n.
+template <class T>
 __global__ void __launch_bounds__(kThreads)
 coarse_gemv_kernel(int n, int row0, int nloc, const double *__restrict__ Ainv,
-                   const double *__restrict__ rhs, double *__restrict__ x) {
+                   const T *__restrict__ rhs, T *__restrict__ x) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= nloc) return;
     const double *row = Ainv + (size_t)(row0 + warp) * n;
     double s = 0.0;
-    for (int j = lane; j < n; j += 32) s = fma(row[j], rhs[j], s);
+    for (int j = lane; j < n; j += 32) s = fma(row[j], (double)rhs[j], s);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) x[warp] = s;
+    if (lane == 0) x[warp] = (T)s;
 }
 
 } // namespace b200

@@ -105,7 +105,9 @@ enum { B200_VK_LOCAL = 0, B200_VK_DIST = 1, B200_VK_GHOST = 2 };
 
 struct b200_vec_s {
     b200_ctx_t ctx   = nullptr;
-    double    *ptr   = nullptr;
+    double    *ptr   = nullptr;   // device storage; holds floats when dtype == B200_F32
+    int        dtype = B200_F64;
+    size_t     esz   = sizeof(double);
     size_t     n     = 0;         // global length
     size_t     len   = 0;         // elements stored on this rank (== n unless distributed)
     size_t     off   = 0;         // global index of ptr[0]
@@ -148,7 +150,9 @@ struct b200_csr_s {
     bool       needed_by[16] = {};    // ranks that consume this rank's data
     int       *ptr   = nullptr;   // [nrows+1] (+ padding) device
     int       *col   = nullptr;   // [nnz]     (+ padding) device
-    double    *val   = nullptr;   // [nnz]     (+ padding) device
+    void      *val   = nullptr;   // [nnz]     (+ padding) device, FP64 or FP32
+    int        dtype = B200_F64;
+    double    *scratch64 = nullptr;   // FP32 operator swept on FP64 vectors: new iterate
     // row-block plan
     int        lanes    = 1;      // lanes cooperating on one row (power of two <= 32)
     int        rows_cap = 256;    // rows per block   (multiple of kThreads / lanes)
@@ -161,6 +165,7 @@ struct b200_csr_s {
 
 struct b200_coarse_s {
     b200_ctx_t ctx  = nullptr;
+    int        dtype = B200_F64;  // element type of the vectors it is applied to
     bool       ghost = false;     // multi-GPU: the coarsest level lives on rank 0
     bool       replicated = false;// multi-GPU: coarsest level partitioned -> inverse on every rank
     double    *gbuf = nullptr;    // replicated: all-gathered right-hand side [nranks * block]

@@ -23,6 +23,14 @@
 //   variant 0: one row block per CTA, latency hidden by several CTAs per SM;
 //   variant 1: persistent CTAs walking the block list with an S-deep ring of
 //              stages, so S*CTAs/SM bulk copies are always in flight per SM.
+//
+// Precision.  Every kernel is a template over the element types of the matrix
+// values, the gathered vector, the right-hand side, the output and the smoother
+// diagonal (struct Prec).  FP64 throughout is the default; the other
+// combinations are the ones AMGCL's mixed-precision composition produces (FP32
+// hierarchy under an FP64 Krylov solver, tutorial/1.poisson3Db/poisson3Db.cpp:45-51):
+// as in the reference (matrix_ops.hpp:57) a row sum is accumulated in the value
+// type of the OUTPUT vector.
 #pragma once
 #include "common.cuh"
 
@@ -30,17 +38,37 @@ namespace b200 {
 
 enum { MODE_SPMV = 0, MODE_SPMV_ACC = 1, MODE_RESID = 2, MODE_RELAX = 3 };
 
-struct CsrArgs {
+#ifndef B200_GATHER_BATCH
+#define B200_GATHER_BATCH 4
+#endif
+constexpr int kGatherBatch = B200_GATHER_BATCH;   // x-gathers issued back to back per lane
+
+template <class TV_, class TX_, class TF_, class TY_, class TD_>
+struct Prec {
+    typedef TV_ TV;   // matrix values
+    typedef TX_ TX;   // gathered vector x
+    typedef TF_ TF;   // right-hand side f
+    typedef TY_ TY;   // output y (and accumulation type of a row sum)
+    typedef TD_ TD;   // smoother diagonal
+};
+typedef Prec<double, double, double, double, double> PrecDD;   // FP64 throughout
+typedef Prec<float, float, float, float, float>      PrecFF;   // FP32 level of a mixed hierarchy
+typedef Prec<float, double, double, double, float>   PrecFD;   // FP32 operator on FP64 vectors
+typedef Prec<float, double, double, float, float>    PrecFDF;  // finest residual into FP32 scratch
+typedef Prec<float, float, float, double, float>     PrecFFD;  // prolongation into an FP64 iterate
+
+template <class P>
+struct CsrArgsT {
     const int    *ptr;
     const int    *col;
-    const double *val;
+    const typename P::TV *val;
     const int2   *blk;    // [nblocks+1]: {first row, first non-zero} of each block
     int           nrows;
     int           nblocks;
     int           rows_cap;
     int           nnz_cap;
-    const double *x;      // gathered vector (local columns)
-    const double *xh;     // halo values for columns >= nloc (multi-GPU), else nullptr
+    const typename P::TX *x;      // gathered vector (local columns)
+    const typename P::TX *xh;     // halo values for columns >= nloc (multi-GPU), else nullptr
     int           nloc;   // number of local columns when xh is set
     // multi-GPU, peer-memory transport: the halo is pushed by the peers while this kernel
     // already works on interior rows; a block that gathers remote columns first waits for
@@ -49,21 +77,22 @@ struct CsrArgs {
     const unsigned long long *wait_flags;  // flag row of the current parity (16 slots)
     unsigned int              wait_mask;
     unsigned long long        wait_seq;
-    double       *y;      // output
-    const double *f;      // rhs          (RESID, RELAX)
-    const double *d;      // diagonal     (RELAX)
+    typename P::TY       *y;      // output
+    const typename P::TF *f;      // rhs          (RESID, RELAX)
+    const typename P::TD *d;      // diagonal     (RELAX)
     double        alpha;  // SPMV: alpha; RELAX: omega
     double        beta;   // SPMV_ACC
 };
+typedef CsrArgsT<PrecDD> CsrArgs;
 
 // ---- shared memory layout of one stage --------------------------------------
 struct StageLayout {
     int val_off, col_off, ptr_off, bytes;
 };
-__host__ __device__ inline StageLayout stage_layout(int rows_cap, int nnz_cap) {
+__host__ __device__ inline StageLayout stage_layout(int rows_cap, int nnz_cap, int val_size) {
     StageLayout s;
     s.val_off = 0;
-    int val_bytes = (nnz_cap + 2) * 8;             // +2: source aligned down to 16 B
+    int val_bytes = nnz_cap * val_size + 16;       // source aligned down to 16 B
     val_bytes = (val_bytes + 15) & ~15;
     s.col_off = s.val_off + val_bytes;
     int col_bytes = (nnz_cap + 8) * 4;             // +3 align down, +3 round up
@@ -82,7 +111,8 @@ struct BlockDesc {      // written by the producer thread, read by everyone afte
 };
 
 // ---- issue the bulk copies of one row block ----------------------------------
-__device__ __forceinline__ BlockDesc load_desc(const CsrArgs &a, int b) {
+template <class P>
+__device__ __forceinline__ BlockDesc load_desc(const CsrArgsT<P> &a, int b) {
     const int2 lo = __ldg(a.blk + b);
     const int2 hi = __ldg(a.blk + b + 1);
     BlockDesc d;
@@ -92,9 +122,12 @@ __device__ __forceinline__ BlockDesc load_desc(const CsrArgs &a, int b) {
 }
 
 // Returns true if the block was staged (false: too long, use the strided path).
-__device__ __forceinline__ bool issue_block(const CsrArgs &a, const BlockDesc &d, char *stage,
+template <class P>
+__device__ __forceinline__ bool issue_block(const CsrArgsT<P> &a, const BlockDesc &d, char *stage,
                                             const StageLayout &lay, uint64_t *bar,
                                             uint64_t policy) {
+    typedef typename P::TV TV;
+    constexpr int VA = 16 / (int)sizeof(TV);        // values per 16 bytes
     const int nnz = d.e1 - d.e0;
     if (nnz > a.nnz_cap) {
         // nothing to stage: complete the phase with a plain arrive
@@ -102,39 +135,42 @@ __device__ __forceinline__ bool issue_block(const CsrArgs &a, const BlockDesc &d
                      : "memory");
         return false;
     }
-    const int a0 = d.e0 & ~1;                       // val source aligned to 16 B
-    const int nval = ((d.e1 - a0) + 1) & ~1;
+    const int a0 = d.e0 & ~(VA - 1);                // val source aligned to 16 B
+    const int nval = ((d.e1 - a0) + VA - 1) & ~(VA - 1);
     const int c0 = d.e0 & ~3;                       // col source aligned to 16 B
     const int ncol = ((d.e1 - c0) + 3) & ~3;
     const int nptr = ((d.r1 - d.r0 + 1) + 3) & ~3;  // r0 is a multiple of 4
-    const uint32_t bytes = nval * 8 + ncol * 4 + nptr * 4;
+    const uint32_t bytes = nval * (int)sizeof(TV) + ncol * 4 + nptr * 4;
     ptx::mbar_expect_tx(bar, bytes);
-    if (nval) ptx::bulk_g2s(stage + lay.val_off, a.val + a0, nval * 8, bar, policy);
+    if (nval) ptx::bulk_g2s(stage + lay.val_off, a.val + a0, nval * (int)sizeof(TV), bar, policy);
     if (ncol) ptx::bulk_g2s(stage + lay.col_off, a.col + c0, ncol * 4, bar, policy);
     ptx::bulk_g2s(stage + lay.ptr_off, a.ptr + d.r0, nptr * 4, bar, policy);
     return true;
 }
 
 // ---- per-row epilogue ----------------------------------------------------------
-template <int MODE>
-__device__ __forceinline__ void store_row(const CsrArgs &a, int r, double sum) {
+template <int MODE, class P>
+__device__ __forceinline__ void store_row(const CsrArgsT<P> &a, int r, typename P::TY sum) {
+    typedef typename P::TY TY;
     if (MODE == MODE_SPMV) {
-        a.y[r] = a.alpha * sum;
+        a.y[r] = (TY)(a.alpha * sum);
     } else if (MODE == MODE_SPMV_ACC) {
-        a.y[r] = a.alpha * sum + a.beta * a.y[r];
+        a.y[r] = (TY)(a.alpha * sum + a.beta * a.y[r]);
     } else if (MODE == MODE_RESID) {
-        a.y[r] = a.f[r] - sum;
+        a.y[r] = (TY)(a.f[r] - sum);
     } else {
         // x_new = (omega*d)*t + x with t = f - A x; same association as the
         // reference's vmul  z = a*x*y + b*z  (builtin.hpp:1238-1265)
-        const double t = a.f[r] - sum;
-        a.y[r] = fma(a.alpha * a.d[r], t, a.x[r]);
+        const TY t = (TY)(a.f[r] - sum);
+        const TY w = (TY)(a.alpha * a.d[r]);
+        a.y[r] = fma(w, t, (TY)a.x[r]);
     }
 }
 
 // ---- x[col]: local columns from the vector, remote ones from the all-gathered halo --
-template <bool HALO>
-__device__ __forceinline__ double gather(const CsrArgs &a, const double *__restrict__ x, int c) {
+template <bool HALO, class P>
+__device__ __forceinline__ typename P::TX gather(const CsrArgsT<P> &a,
+                                                 const typename P::TX *__restrict__ x, int c) {
     if (HALO) {
         // halo values may arrive while the kernel runs: read them through L2 (ld.cg)
         if (c < a.nloc) return __ldg(x + c);
@@ -145,8 +181,8 @@ __device__ __forceinline__ double gather(const CsrArgs &a, const double *__restr
 
 // Block until the peers' halo pushes for this exchange have landed (thread 0 polls the
 // flags with acquire semantics, the CTA follows through the barrier).
-template <bool HALO>
-__device__ __forceinline__ void wait_for_halo(const CsrArgs &a, int b) {
+template <bool HALO, class P>
+__device__ __forceinline__ void wait_for_halo(const CsrArgsT<P> &a, int b) {
     if (!HALO) return;
     if (a.blk_halo == nullptr || !a.blk_halo[b]) return;      // uniform per CTA
     if (threadIdx.x == 0) {
@@ -164,46 +200,50 @@ __device__ __forceinline__ void wait_for_halo(const CsrArgs &a, int b) {
 }
 
 // ---- reduce the rows of a staged block out of shared memory ---------------------
-template <int MODE, int L, bool HALO>
-__device__ __forceinline__ void compute_staged(const CsrArgs &a, const BlockDesc &d,
+template <int MODE, int L, bool HALO, class P>
+__device__ __forceinline__ void compute_staged(const CsrArgsT<P> &a, const BlockDesc &d,
                                                const char *stage, const StageLayout &lay) {
-    const double *val_s = reinterpret_cast<const double *>(stage + lay.val_off);
+    typedef typename P::TV TV;
+    typedef typename P::TX TX;
+    typedef typename P::TY TS;                       // row sums live in the output's type
+    constexpr int VA = 16 / (int)sizeof(TV);
+    const TV *val_s = reinterpret_cast<const TV *>(stage + lay.val_off);
     const int    *col_s = reinterpret_cast<const int *>(stage + lay.col_off);
     const int    *ptr_s = reinterpret_cast<const int *>(stage + lay.ptr_off);
-    const int vo = d.e0 & ~1;
+    const int vo = d.e0 & ~(VA - 1);
     const int co = d.e0 & ~3;
     constexpr int G = kThreads / L;
     const int g    = threadIdx.x / L;
     const int lane = threadIdx.x % L;
     const int nr   = d.r1 - d.r0;
-    const double *__restrict__ x = a.x;
+    const TX *__restrict__ x = a.x;
 
     for (int base = 0; base < nr; base += G) {
         const int  rr    = base + g;
         const bool valid = rr < nr;
-        double sum = 0.0;
+        TS sum = 0;
         if (valid) {
             const int beg = ptr_s[rr];
             const int end = ptr_s[rr + 1];
-            for (int e = beg + lane; e < end; e += 4 * L) {
-                const int  e1 = e + L, e2 = e + 2 * L, e3 = e + 3 * L;
-                const bool p1 = e1 < end, p2 = e2 < end, p3 = e3 < end;
-                const int  c0 = col_s[e - co];
-                const int  c1 = p1 ? col_s[e1 - co] : c0;
-                const int  c2 = p2 ? col_s[e2 - co] : c0;
-                const int  c3 = p3 ? col_s[e3 - co] : c0;
-                const double v0 = val_s[e - vo];
-                const double v1 = p1 ? val_s[e1 - vo] : 0.0;
-                const double v2 = p2 ? val_s[e2 - vo] : 0.0;
-                const double v3 = p3 ? val_s[e3 - vo] : 0.0;
-                const double x0 = gather<HALO>(a, x, c0);
-                const double x1 = gather<HALO>(a, x, c1);
-                const double x2 = gather<HALO>(a, x, c2);
-                const double x3 = gather<HALO>(a, x, c3);
-                sum = fma(v0, x0, sum);
-                if (p1) sum = fma(v1, x1, sum);
-                if (p2) sum = fma(v2, x2, sum);
-                if (p3) sum = fma(v3, x3, sum);
+            // U independent gathers in flight per lane, then the FMAs in entry order
+            constexpr int U = kGatherBatch;
+            for (int e = beg + lane; e < end; e += U * L) {
+                int  c[U];
+                TV   v[U];
+                TX   xv[U];
+                bool p[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int eu = e + u * L;
+                    p[u] = eu < end;
+                    c[u] = p[u] ? col_s[eu - co] : col_s[e - co];
+                    v[u] = p[u] ? val_s[eu - vo] : (TV)0;
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) xv[u] = gather<HALO>(a, x, c[u]);
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (p[u]) sum = fma((TS)v[u], (TS)xv[u], sum);
             }
         }
         if (L > 1) {
@@ -215,37 +255,39 @@ __device__ __forceinline__ void compute_staged(const CsrArgs &a, const BlockDesc
 }
 
 // ---- rows too long to stage: whole CTA strides over each row -----------------------
-template <int MODE, bool HALO>
-__device__ __forceinline__ void compute_long(const CsrArgs &a, const BlockDesc &d,
+template <int MODE, bool HALO, class P>
+__device__ __forceinline__ void compute_long(const CsrArgsT<P> &a, const BlockDesc &d,
                                              double *red_s /* >= 8 doubles */) {
-    const double *__restrict__ x = a.x;
+    typedef typename P::TX TX;
+    typedef typename P::TY TS;
+    const TX *__restrict__ x = a.x;
     for (int r = d.r0; r < d.r1; ++r) {
         const int beg = __ldg(a.ptr + r), end = __ldg(a.ptr + r + 1);
-        double sum = 0.0;
+        TS sum = 0;
         for (int e = beg + threadIdx.x; e < end; e += kThreads)
-            sum = fma(__ldg(a.val + e), gather<HALO>(a, x, __ldg(a.col + e)), sum);
+            sum = fma((TS)__ldg(a.val + e), (TS)gather<HALO>(a, x, __ldg(a.col + e)), sum);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
         __syncthreads();                       // red_s free from the previous row
-        if ((threadIdx.x & 31) == 0) red_s[threadIdx.x >> 5] = sum;
+        if ((threadIdx.x & 31) == 0) red_s[threadIdx.x >> 5] = (double)sum;
         __syncthreads();
         if (threadIdx.x == 0) {
-            double tot = 0.0;
+            TS tot = 0;
 #pragma unroll
-            for (int w = 0; w < kThreads / 32; ++w) tot += red_s[w];
+            for (int w = 0; w < kThreads / 32; ++w) tot += (TS)red_s[w];
             store_row<MODE>(a, r, tot);
         }
     }
 }
 
 // ---- variant 0: one row block per CTA -----------------------------------------------
-template <int MODE, int L, bool HALO>
-__global__ void __launch_bounds__(kThreads, 4) csr_block_kernel(const CsrArgs a) {
+template <int MODE, int L, bool HALO, class P>
+__global__ void __launch_bounds__(kThreads, 4) csr_block_kernel(const CsrArgsT<P> a) {
     extern __shared__ __align__(128) char smem[];
     uint64_t *bar   = reinterpret_cast<uint64_t *>(smem);
     double   *red_s = reinterpret_cast<double *>(smem + 64);
     char     *stage = smem + kHeaderBytes;
-    const StageLayout lay = stage_layout(a.rows_cap, a.nnz_cap);
+    const StageLayout lay = stage_layout(a.rows_cap, a.nnz_cap, (int)sizeof(typename P::TV));
 
     const int b = blockIdx.x;
     const BlockDesc d = load_desc(a, b);          // broadcast loads, uniform
@@ -268,13 +310,13 @@ __global__ void __launch_bounds__(kThreads, 4) csr_block_kernel(const CsrArgs a)
 }
 
 // ---- variant 1: persistent CTAs, S-deep ring of stages ----------------------------------
-template <int MODE, int L, bool HALO>
-__global__ void __launch_bounds__(kThreads, 2) csr_ring_kernel(const CsrArgs a, const int nstages) {
+template <int MODE, int L, bool HALO, class P>
+__global__ void __launch_bounds__(kThreads, 2) csr_ring_kernel(const CsrArgsT<P> a, const int nstages) {
     extern __shared__ __align__(128) char smem[];
     uint64_t  *bars  = reinterpret_cast<uint64_t *>(smem);                 // [<=8]
     double    *red_s = reinterpret_cast<double *>(smem + 64);              // [8]
     BlockDesc *descs = reinterpret_cast<BlockDesc *>(smem + 128);          // [<=8]
-    const StageLayout lay = stage_layout(a.rows_cap, a.nnz_cap);
+    const StageLayout lay = stage_layout(a.rows_cap, a.nnz_cap, (int)sizeof(typename P::TV));
     char *stages = smem + kHeaderBytes;
 
     const int first = blockIdx.x;
@@ -315,14 +357,15 @@ __global__ void __launch_bounds__(kThreads, 2) csr_ring_kernel(const CsrArgs a, 
 }
 
 // ---- x == 0 shortcut of the smoother sweep: x = (omega*d).*rhs ---------------------------
+template <class TD, class TF, class TX>
 __global__ void __launch_bounds__(kThreads) relax_zero_kernel(size_t n, double omega,
-                                                              const double *__restrict__ d,
-                                                              const double *__restrict__ f,
-                                                              double *__restrict__ x) {
+                                                              const TD *__restrict__ d,
+                                                              const TF *__restrict__ f,
+                                                              TX *__restrict__ x) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         // (omega*d)*(f - 0) + 0, written as the reference evaluates it
-        x[i] = fma(omega * d[i], f[i], 0.0);
+        x[i] = fma((TX)(omega * d[i]), (TX)f[i], (TX)0);
     }
 }
 

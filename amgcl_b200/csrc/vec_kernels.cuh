@@ -9,70 +9,109 @@
 // vector loads in flight per stream per thread, grid sized to a multiple of the
 // SM count.  As in the reference, an output whose coefficient is zero is never
 // read (it may hold uninitialised memory, i.e. NaNs).
+//
+// Templated over the element types (FP64 default; FP32 and the FP32->FP64 mixes of
+// AMGCL's mixed-precision composition).  Arithmetic is done in the OUTPUT's type,
+// as the reference's templates do.
 #pragma once
 #include "common.cuh"
 
 namespace b200 {
 
+template <class T> struct Vec16;
+template <> struct Vec16<double> { typedef double2 type; static constexpr int N = 2; };
+template <> struct Vec16<float>  { typedef float4  type; static constexpr int N = 4; };
+
+__device__ __forceinline__ double vec_elem(const double2 &v, int i) { return i ? v.y : v.x; }
+__device__ __forceinline__ float  vec_elem(const float4 &v, int i) {
+    return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w;
+}
+__device__ __forceinline__ void vec_set(double2 &v, int i, double s) { if (i) v.y = s; else v.x = s; }
+__device__ __forceinline__ void vec_set(float4 &v, int i, float s) {
+    if (i == 0) v.x = s; else if (i == 1) v.y = s; else if (i == 2) v.z = s; else v.w = s;
+}
+
+// 16-byte path: all streams share the output's element type (decided on the host)
+template <class F, bool READ_Y, bool READ_Z, class T>
+__device__ __forceinline__ void ew_vector_path(size_t n, F f, const T *x, const T *y, const T *z_in,
+                                               T *out, size_t tid, size_t stride) {
+    typedef typename Vec16<T>::type V;
+    constexpr int N = Vec16<T>::N;
+    const size_t nv = n / N;
+    const V *xv = reinterpret_cast<const V *>(x);
+    const V *yv = reinterpret_cast<const V *>(y);
+    const V *zv = reinterpret_cast<const V *>(z_in);
+    V *ov = reinterpret_cast<V *>(out);
+    size_t i = tid;
+    for (; i + stride < nv; i += 2 * stride) {
+        const size_t j = i + stride;
+        V xa = xv[i], xb = xv[j];
+        V ya = xa, yb = xb, za = xa, zb = xb, oa, ob;
+        if (READ_Y) { ya = yv[i]; yb = yv[j]; }
+        if (READ_Z) { za = zv[i]; zb = zv[j]; }
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            vec_set(oa, k, f(vec_elem(xa, k), vec_elem(ya, k), vec_elem(za, k)));
+            vec_set(ob, k, f(vec_elem(xb, k), vec_elem(yb, k), vec_elem(zb, k)));
+        }
+        ov[i] = oa;
+        ov[j] = ob;
+    }
+    if (i < nv) {
+        V xa = xv[i];
+        V ya = xa, za = xa, oa;
+        if (READ_Y) ya = yv[i];
+        if (READ_Z) za = zv[i];
+#pragma unroll
+        for (int k = 0; k < N; ++k)
+            vec_set(oa, k, f(vec_elem(xa, k), vec_elem(ya, k), vec_elem(za, k)));
+        ov[i] = oa;
+    }
+    // tail (n not a multiple of the vector width)
+    for (size_t k = nv * N + tid; k < n; k += stride)
+        out[k] = f(x[k], READ_Y ? y[k] : (T)0, READ_Z ? z_in[k] : (T)0);
+}
+
 // ---- generic element-wise driver ---------------------------------------------
-// F: double operator()(double x, double y, double z) ; NIN = streams read (1..3);
-// the output aliases the last input stream when RMW is set.
-template <class F, bool READ_Y, bool READ_Z>
+// F: TO operator()(TO x, TO y, TO z); mixed element types take the scalar loop.
+template <class F, bool READ_Y, bool READ_Z, class TX, class TY, class TZ, class TO>
 __global__ void __launch_bounds__(kThreads)
-ew_kernel(size_t n, F f, const double *x, const double *y, const double *z_in,
-          double *out, bool vec_ok) {
+ew_kernel(size_t n, F f, const TX *x, const TY *y, const TZ *z_in, TO *out, bool vec_ok) {
+    const size_t tid    = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = tid; i < n; i += stride)
+        out[i] = f((TO)x[i], READ_Y ? (TO)y[i] : (TO)0, READ_Z ? (TO)z_in[i] : (TO)0);
+}
+template <class F, bool READ_Y, bool READ_Z, class T>
+__global__ void __launch_bounds__(kThreads)
+ew_kernel_same(size_t n, F f, const T *x, const T *y, const T *z_in, T *out, bool vec_ok) {
     const size_t tid    = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     if (vec_ok) {
-        const size_t n2 = n >> 1;
-        const double2 *x2 = reinterpret_cast<const double2 *>(x);
-        const double2 *y2 = reinterpret_cast<const double2 *>(y);
-        const double2 *z2 = reinterpret_cast<const double2 *>(z_in);
-        double2 *o2 = reinterpret_cast<double2 *>(out);
-        size_t i = tid;
-        for (; i + stride < n2; i += 2 * stride) {
-            const size_t j = i + stride;
-            double2 xa = x2[i], xb = x2[j];
-            double2 ya = make_double2(0, 0), yb = ya, za = ya, zb = ya;
-            if (READ_Y) { ya = y2[i]; yb = y2[j]; }
-            if (READ_Z) { za = z2[i]; zb = z2[j]; }
-            o2[i] = make_double2(f(xa.x, ya.x, za.x), f(xa.y, ya.y, za.y));
-            o2[j] = make_double2(f(xb.x, yb.x, zb.x), f(xb.y, yb.y, zb.y));
-        }
-        if (i < n2) {
-            double2 xa = x2[i];
-            double2 ya = make_double2(0, 0), za = ya;
-            if (READ_Y) ya = y2[i];
-            if (READ_Z) za = z2[i];
-            o2[i] = make_double2(f(xa.x, ya.x, za.x), f(xa.y, ya.y, za.y));
-        }
-        if ((n & 1) && tid == 0) {
-            const size_t k = n - 1;
-            out[k] = f(x[k], READ_Y ? y[k] : 0.0, READ_Z ? z_in[k] : 0.0);
-        }
+        ew_vector_path<F, READ_Y, READ_Z, T>(n, f, x, y, z_in, out, tid, stride);
     } else {
         for (size_t i = tid; i < n; i += stride)
-            out[i] = f(x[i], READ_Y ? y[i] : 0.0, READ_Z ? z_in[i] : 0.0);
+            out[i] = f(x[i], READ_Y ? y[i] : (T)0, READ_Z ? z_in[i] : (T)0);
     }
 }
 
-// functors: arithmetic written with the reference's association
-struct AxF      { double a;       __device__ double operator()(double x, double, double) const { return a * x; } };
-struct AxpbyF   { double a, b;    __device__ double operator()(double x, double y, double) const { return a * x + b * y; } };
-struct AxpbyZF  { double a, b;    __device__ double operator()(double x, double y, double) const { return a * x + b * y; } };
-struct AxpbypczF{ double a, b, c; __device__ double operator()(double x, double y, double z) const { return a * x + b * y + c * z; } };
-struct VmulF    { double a;       __device__ double operator()(double x, double y, double) const { return a * x * y; } };
-struct VmulAccF { double a, b;    __device__ double operator()(double x, double y, double z) const { return a * x * y + b * z; } };
-struct CopyF    {                 __device__ double operator()(double x, double, double) const { return x; } };
+// functors: arithmetic written with the reference's association, in the output's type
+template <class T> struct AxF       { T a;       __device__ T operator()(T x, T, T) const { return a * x; } };
+template <class T> struct AxpbyF    { T a, b;    __device__ T operator()(T x, T y, T) const { return a * x + b * y; } };
+template <class T> struct AxpbypczF { T a, b, c; __device__ T operator()(T x, T y, T z) const { return a * x + b * y + c * z; } };
+template <class T> struct VmulF     { T a;       __device__ T operator()(T x, T y, T) const { return a * x * y; } };
+template <class T> struct VmulAccF  { T a, b;    __device__ T operator()(T x, T y, T z) const { return a * x * y + b * z; } };
+template <class T> struct CopyF     {            __device__ T operator()(T x, T, T) const { return x; } };
 
 // ---- dot product: one kernel, deterministic, compensated -----------------------
-// Each thread accumulates its grid-strided products with Kahan compensation
+// Each thread accumulates its grid-strided products with Kahan compensation in FP64
 // (the reference's builtin backend does the same per OpenMP thread,
 // builtin.hpp:1143-1181); the CTA reduces through warp shuffles and shared
 // memory; the last CTA to finish (ticket counter) adds the per-CTA partials in
 // index order and writes the scalar straight into mapped pinned host memory.
+template <class T>
 __global__ void __launch_bounds__(kThreads)
-dot_kernel(size_t n, const double *__restrict__ x, const double *__restrict__ y,
+dot_kernel(size_t n, const T *__restrict__ x, const T *__restrict__ y,
            double *partial, unsigned int *ticket, double *result, bool vec_ok) {
     const size_t tid    = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -84,27 +123,34 @@ dot_kernel(size_t n, const double *__restrict__ x, const double *__restrict__ y,
         s = t;
     };
     if (vec_ok) {
-        const size_t n2 = n >> 1;
-        const double2 *x2 = reinterpret_cast<const double2 *>(x);
-        const double2 *y2 = reinterpret_cast<const double2 *>(y);
+        typedef typename Vec16<T>::type V;
+        constexpr int N = Vec16<T>::N;
+        const size_t nv = n / N;
+        const V *xv = reinterpret_cast<const V *>(x);
+        const V *yv = reinterpret_cast<const V *>(y);
         size_t i = tid;
-        for (; i + 3 * stride < n2; i += 4 * stride) {
-            const double2 xa = x2[i], ya = y2[i];
-            const double2 xb = x2[i + stride], yb = y2[i + stride];
-            const double2 xc = x2[i + 2 * stride], yc = y2[i + 2 * stride];
-            const double2 xd = x2[i + 3 * stride], yd = y2[i + 3 * stride];
-            acc(xa.x * ya.x); acc(xa.y * ya.y);
-            acc(xb.x * yb.x); acc(xb.y * yb.y);
-            acc(xc.x * yc.x); acc(xc.y * yc.y);
-            acc(xd.x * yd.x); acc(xd.y * yd.y);
+        for (; i + 3 * stride < nv; i += 4 * stride) {
+            const V xa = xv[i], ya = yv[i];
+            const V xb = xv[i + stride], yb = yv[i + stride];
+            const V xc = xv[i + 2 * stride], yc = yv[i + 2 * stride];
+            const V xd = xv[i + 3 * stride], yd = yv[i + 3 * stride];
+#pragma unroll
+            for (int k = 0; k < N; ++k) acc((double)vec_elem(xa, k) * (double)vec_elem(ya, k));
+#pragma unroll
+            for (int k = 0; k < N; ++k) acc((double)vec_elem(xb, k) * (double)vec_elem(yb, k));
+#pragma unroll
+            for (int k = 0; k < N; ++k) acc((double)vec_elem(xc, k) * (double)vec_elem(yc, k));
+#pragma unroll
+            for (int k = 0; k < N; ++k) acc((double)vec_elem(xd, k) * (double)vec_elem(yd, k));
         }
-        for (; i < n2; i += stride) {
-            const double2 xa = x2[i], ya = y2[i];
-            acc(xa.x * ya.x); acc(xa.y * ya.y);
+        for (; i < nv; i += stride) {
+            const V xa = xv[i], ya = yv[i];
+#pragma unroll
+            for (int k = 0; k < N; ++k) acc((double)vec_elem(xa, k) * (double)vec_elem(ya, k));
         }
-        if ((n & 1) && tid == 0) acc(x[n - 1] * y[n - 1]);
+        for (size_t k = nv * N + tid; k < n; k += stride) acc((double)x[k] * (double)y[k]);
     } else {
-        for (size_t i = tid; i < n; i += stride) acc(x[i] * y[i]);
+        for (size_t i = tid; i < n; i += stride) acc((double)x[i] * (double)y[i]);
     }
 
     __shared__ double warp_sum[kThreads / 32];

@@ -46,10 +46,12 @@ struct SolverBase {
     virtual size_t bytes() const = 0;
 };
 
-template <template <class> class Relax, template <class, class> class Krylov>
+typedef amgcl::backend::b200<float> BackendF32;   // hierarchy of a mixed-precision solver
+
+template <template <class> class Relax, template <class, class> class Krylov, class PBackend = Backend>
 struct SolverImpl : SolverBase {
     typedef amgcl::make_solver<
-        amgcl::amg<Backend, amgcl::coarsening::smoothed_aggregation, Relax>,
+        amgcl::amg<PBackend, amgcl::coarsening::smoothed_aggregation, Relax>,
         Krylov<Backend, amgcl::solver::detail::default_inner_product>
         > Solver;
 
@@ -127,6 +129,38 @@ int dropin_create(void *ctx, int64_t n, const int64_t *ptr, const int64_t *col, 
             h->solver.reset(new SolverImpl<relaxation::damped_jacobi, solver::gmres>(n, ptr, col, val, tol, maxiter, coarse_enough, h->bprm));
         else if (relax == 1 && krylov == 3)
             h->solver.reset(new SolverImpl<relaxation::spai0, solver::bicgstabl>(n, ptr, col, val, tol, maxiter, coarse_enough, h->bprm));
+        else {
+            g_error = "unknown relax/krylov selector";
+            return -1;
+        }
+        h->f = Backend::create_vector(n, h->bprm);
+        h->x = Backend::create_vector(n, h->bprm);
+        *out = h.release();
+        return 0;
+    } catch (const std::exception &e) {
+        g_error = e.what();
+        return -1;
+    }
+}
+
+// Mixed precision (tutorial/1.poisson3Db/poisson3Db.cpp:45-51): FP32 hierarchy
+// (amg<backend::b200<float>>) under an FP64 Krylov solver (backend::b200<double>).
+int dropin_create_mixed(void *ctx, int64_t n, const int64_t *ptr, const int64_t *col, const double *val,
+                        int relax, int krylov, double tol, int maxiter, int coarse_enough, void **out)
+{
+    try {
+        std::unique_ptr<Handle> h(new Handle());
+        h->n = (size_t)n;
+        h->bprm = Backend::params(static_cast<b200_ctx_t>(ctx));
+        using namespace amgcl;
+        if (relax == 0 && krylov == 0)
+            h->solver.reset(new SolverImpl<relaxation::damped_jacobi, solver::cg, BackendF32>(n, ptr, col, val, tol, maxiter, coarse_enough, h->bprm));
+        else if (relax == 1 && krylov == 1)
+            h->solver.reset(new SolverImpl<relaxation::spai0, solver::bicgstab, BackendF32>(n, ptr, col, val, tol, maxiter, coarse_enough, h->bprm));
+        else if (relax == 1 && krylov == 0)
+            h->solver.reset(new SolverImpl<relaxation::spai0, solver::cg, BackendF32>(n, ptr, col, val, tol, maxiter, coarse_enough, h->bprm));
+        else if (relax == 0 && krylov == 1)
+            h->solver.reset(new SolverImpl<relaxation::damped_jacobi, solver::bicgstab, BackendF32>(n, ptr, col, val, tol, maxiter, coarse_enough, h->bprm));
         else {
             g_error = "unknown relax/krylov selector";
             return -1;

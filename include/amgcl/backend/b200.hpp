@@ -76,10 +76,22 @@ struct b200_params {
     b200_ctx_t context() const { return ctx ? ctx : detail::b200_default_ctx(); }
 };
 
+namespace detail {
+// element-type dispatch onto the typed C entry points
+inline int b200_vec_new(b200_ctx_t c, size_t n, b200_vec_t *h, double*) { return b200_vec_create(c, n, h); }
+inline int b200_vec_new(b200_ctx_t c, size_t n, b200_vec_t *h, float*)  { return b200_vec_create_f32(c, n, h); }
+inline int b200_vec_put(b200_vec_t h, const double *p, size_t n) { return b200_vec_upload(h, p, n); }
+inline int b200_vec_put(b200_vec_t h, const float  *p, size_t n) { return b200_vec_upload_f32(h, p, n); }
+inline int b200_vec_get(b200_vec_t h, double *p, size_t n) { return b200_vec_download(h, p, n); }
+inline int b200_vec_get(b200_vec_t h, float  *p, size_t n) { return b200_vec_download_f32(h, p, n); }
+template <class T> struct b200_is_real : std::integral_constant<bool,
+    std::is_same<T, double>::value || std::is_same<T, float>::value> {};
+} // namespace detail
+
 /// Device vector (replaces thrust::device_vector<real>, cuda.hpp:483).
 template <typename real>
 class b200_vector {
-    static_assert(std::is_same<real, double>::value, "b200 backend is FP64");
+    static_assert(detail::b200_is_real<real>::value, "b200 vectors are FP64 or FP32");
     public:
         typedef real value_type;
 
@@ -88,23 +100,24 @@ class b200_vector {
         b200_vector(size_t n, const b200_params &prm = b200_params())
             : ctx(prm.context()), h(0), n(n)
         {
-            AMGCL_CALL_B200(b200_vec_create(ctx, n, &h));
+            AMGCL_CALL_B200(detail::b200_vec_new(ctx, n, &h, (real*)0));
         }
 
         b200_vector(const real *host, size_t n, const b200_params &prm = b200_params())
             : ctx(prm.context()), h(0), n(n)
         {
-            AMGCL_CALL_B200(b200_vec_create(ctx, n, &h));
-            AMGCL_CALL_B200(b200_vec_upload(h, host, n));
+            AMGCL_CALL_B200(detail::b200_vec_new(ctx, n, &h, (real*)0));
+            AMGCL_CALL_B200(detail::b200_vec_put(h, host, n));
         }
 
+        /// From a host container (std::vector / numa_vector of the same element type).
         template <class Vector>
-        b200_vector(const Vector &host, const b200_params &prm = b200_params(),
-                typename std::enable_if<!std::is_integral<Vector>::value, int>::type = 0)
+        explicit b200_vector(const Vector &host, const b200_params &prm = b200_params(),
+                typename std::enable_if<is_builtin_vector<Vector>::value, int>::type = 0)
             : ctx(prm.context()), h(0), n(host.size())
         {
-            AMGCL_CALL_B200(b200_vec_create(ctx, n, &h));
-            AMGCL_CALL_B200(b200_vec_upload(h, host.data(), n));
+            AMGCL_CALL_B200(detail::b200_vec_new(ctx, n, &h, (real*)0));
+            AMGCL_CALL_B200(detail::b200_vec_put(h, host.data(), n));
         }
 
         b200_vector(const b200_vector&) = delete;
@@ -120,8 +133,8 @@ class b200_vector {
         b200_ctx_t context() const { return ctx; }
 
         /// Copy to a host container (resized by the caller).
-        void download(real *host) const { AMGCL_CALL_B200(b200_vec_download(h, host, n)); }
-        void upload(const real *host)   { AMGCL_CALL_B200(b200_vec_upload(h, host, n)); }
+        void download(real *host) const { AMGCL_CALL_B200(detail::b200_vec_get(h, host, n)); }
+        void upload(const real *host)   { AMGCL_CALL_B200(detail::b200_vec_put(h, host, n)); }
 
     private:
         b200_ctx_t ctx;
@@ -132,7 +145,7 @@ class b200_vector {
 /// Device CSR matrix (replaces cuda_matrix<real>, cuda.hpp:219-333).
 template <typename real>
 class b200_matrix {
-    static_assert(std::is_same<real, double>::value, "b200 backend is FP64");
+    static_assert(detail::b200_is_real<real>::value, "b200 matrices are FP64 or FP32");
     public:
         typedef real value_type;
 
@@ -160,11 +173,17 @@ class b200_matrix {
         b200_csr_t h;
         size_t nrows, ncols, nnz;
 
-        void create(size_t n, size_t m, const int64_t *ptr, const int64_t *col, const real *val) {
+        void create(size_t n, size_t m, const int64_t *ptr, const int64_t *col, const double *val) {
             AMGCL_CALL_B200(b200_csr_create_i64(ctx, n, m, ptr, col, val, &h));
         }
-        void create(size_t n, size_t m, const int32_t *ptr, const int32_t *col, const real *val) {
+        void create(size_t n, size_t m, const int32_t *ptr, const int32_t *col, const double *val) {
             AMGCL_CALL_B200(b200_csr_create_i32(ctx, n, m, ptr, col, val, &h));
+        }
+        void create(size_t n, size_t m, const int64_t *ptr, const int64_t *col, const float *val) {
+            AMGCL_CALL_B200(b200_csr_create_i64_f32(ctx, n, m, ptr, col, val, &h));
+        }
+        void create(size_t n, size_t m, const int32_t *ptr, const int32_t *col, const float *val) {
+            AMGCL_CALL_B200(b200_csr_create_i32_f32(ctx, n, m, ptr, col, val, &h));
         }
         // long / long long differ from int64_t on some ABIs: same width, reinterpret
         template <class I>
@@ -203,7 +222,10 @@ class b200_dense_inverse {
         /// hierarchy has exactly the levels the builtin backend would build.
         static size_t coarse_enough() { return 3000; }
 
-        void operator()(const backend::b200_vector<real> &rhs, backend::b200_vector<real> &x) const {
+        /// amg::cycle is a template over the vector types it is handed, so this call is
+        /// instantiated for the outer solver's vectors as well (single-level hierarchies).
+        template <typename V1, typename V2>
+        void operator()(const backend::b200_vector<V1> &rhs, backend::b200_vector<V2> &x) const {
             AMGCL_CALL_B200(b200_coarse_solve(ctx, h, rhs.handle(), x.handle()));
         }
 
@@ -214,11 +236,17 @@ class b200_dense_inverse {
         b200_coarse_t h;
         size_t        n;
 
-        void create(const int64_t *ptr, const int64_t *col, const real *val) {
+        void create(const int64_t *ptr, const int64_t *col, const double *val) {
             AMGCL_CALL_B200(b200_coarse_create_i64(ctx, n, ptr, col, val, &h));
         }
-        void create(const int32_t *ptr, const int32_t *col, const real *val) {
+        void create(const int32_t *ptr, const int32_t *col, const double *val) {
             AMGCL_CALL_B200(b200_coarse_create_i32(ctx, n, ptr, col, val, &h));
+        }
+        void create(const int64_t *ptr, const int64_t *col, const float *val) {
+            AMGCL_CALL_B200(b200_coarse_create_i64_f32(ctx, n, ptr, col, val, &h));
+        }
+        void create(const int32_t *ptr, const int32_t *col, const float *val) {
+            AMGCL_CALL_B200(b200_coarse_create_i32_f32(ctx, n, ptr, col, val, &h));
         }
         template <class I>
         typename std::enable_if<
@@ -248,8 +276,9 @@ template <
     class DirectSolver   = solver::b200_dense_inverse<real>
     >
 struct b200 {
-    static_assert(std::is_same<real, double>::value,
-            "Unsupported value type for b200 backend (FP64 only)");
+    static_assert(detail::b200_is_real<real>::value,
+            "Unsupported value type for b200 backend (double, or float for the hierarchy of a "
+            "mixed-precision solver)");
 
     typedef real        value_type;
     typedef ColumnType  col_type;
@@ -309,30 +338,37 @@ struct b200 {
     }
 };
 
+/// An FP64 Krylov solver may drive an FP32 hierarchy (mixed precision, as
+/// builtin<double> / builtin<float> allow: builtin.hpp:1014-1015,
+/// tutorial/1.poisson3Db/poisson3Db.cpp:45-51).
+template <typename V1, typename V2, typename C, typename P, class DS1, class DS2>
+struct backends_compatible< b200<V1, C, P, DS1>, b200<V2, C, P, DS2> > : std::true_type {};
+
 //---------------------------------------------------------------------------
-// Backend interface implementation
+// Backend interface implementation.  The C ABI dispatches on the element types of
+// the handles, so every customisation point is a thin template over them.
 //---------------------------------------------------------------------------
 template <typename V>
 struct bytes_impl< b200_vector<V> > {
     static size_t get(const b200_vector<V> &v) { return v.bytes(); }
 };
 
-template <typename Alpha, typename Beta, typename V>
-struct spmv_impl<Alpha, b200_matrix<V>, b200_vector<V>, Beta, b200_vector<V> >
+template <typename Alpha, typename Beta, typename VM, typename V1, typename V2>
+struct spmv_impl<Alpha, b200_matrix<VM>, b200_vector<V1>, Beta, b200_vector<V2> >
 {
-    static void apply(Alpha alpha, const b200_matrix<V> &A, const b200_vector<V> &x,
-            Beta beta, b200_vector<V> &y)
+    static void apply(Alpha alpha, const b200_matrix<VM> &A, const b200_vector<V1> &x,
+            Beta beta, b200_vector<V2> &y)
     {
         AMGCL_CALL_B200(b200_spmv(A.context(), static_cast<double>(alpha), A.handle(),
                     x.handle(), static_cast<double>(beta), y.handle()));
     }
 };
 
-template <typename V>
-struct residual_impl<b200_matrix<V>, b200_vector<V>, b200_vector<V>, b200_vector<V> >
+template <typename VM, typename V1, typename V2, typename V3>
+struct residual_impl<b200_matrix<VM>, b200_vector<V1>, b200_vector<V2>, b200_vector<V3> >
 {
-    static void apply(const b200_vector<V> &rhs, const b200_matrix<V> &A,
-            const b200_vector<V> &x, b200_vector<V> &r)
+    static void apply(const b200_vector<V1> &rhs, const b200_matrix<VM> &A,
+            const b200_vector<V2> &x, b200_vector<V3> &r)
     {
         AMGCL_CALL_B200(b200_residual(A.context(), rhs.handle(), A.handle(), x.handle(), r.handle()));
     }
@@ -346,10 +382,10 @@ struct clear_impl< b200_vector<V> >
     }
 };
 
-template <typename V>
-struct copy_impl<b200_vector<V>, b200_vector<V> >
+template <typename V1, typename V2>
+struct copy_impl<b200_vector<V1>, b200_vector<V2> >
 {
-    static void apply(const b200_vector<V> &x, b200_vector<V> &y) {
+    static void apply(const b200_vector<V1> &x, b200_vector<V2> &y) {
         AMGCL_CALL_B200(b200_copy(x.context(), x.handle(), y.handle()));
     }
 };
@@ -382,35 +418,35 @@ struct inner_product_impl<b200_vector<V>, b200_vector<V> >
     static V get(const b200_vector<V> &x, const b200_vector<V> &y) {
         double r = 0;
         AMGCL_CALL_B200(b200_dot(x.context(), x.handle(), y.handle(), &r));
-        return r;
+        return static_cast<V>(r);
     }
 };
 
-template <typename A, typename B, typename V>
-struct axpby_impl<A, b200_vector<V>, B, b200_vector<V> >
+template <typename A, typename B, typename V1, typename V2>
+struct axpby_impl<A, b200_vector<V1>, B, b200_vector<V2> >
 {
-    static void apply(A a, const b200_vector<V> &x, B b, b200_vector<V> &y) {
+    static void apply(A a, const b200_vector<V1> &x, B b, b200_vector<V2> &y) {
         AMGCL_CALL_B200(b200_axpby(x.context(), static_cast<double>(a), x.handle(),
                     static_cast<double>(b), y.handle()));
     }
 };
 
-template <typename A, typename B, typename C, typename V>
-struct axpbypcz_impl<A, b200_vector<V>, B, b200_vector<V>, C, b200_vector<V> >
+template <typename A, typename B, typename C, typename V1, typename V2, typename V3>
+struct axpbypcz_impl<A, b200_vector<V1>, B, b200_vector<V2>, C, b200_vector<V3> >
 {
-    static void apply(A a, const b200_vector<V> &x, B b, const b200_vector<V> &y,
-            C c, b200_vector<V> &z)
+    static void apply(A a, const b200_vector<V1> &x, B b, const b200_vector<V2> &y,
+            C c, b200_vector<V3> &z)
     {
         AMGCL_CALL_B200(b200_axpbypcz(x.context(), static_cast<double>(a), x.handle(),
                     static_cast<double>(b), y.handle(), static_cast<double>(c), z.handle()));
     }
 };
 
-template <typename A, typename B, typename V>
-struct vmul_impl<A, b200_vector<V>, b200_vector<V>, B, b200_vector<V> >
+template <typename A, typename B, typename V1, typename V2, typename V3>
+struct vmul_impl<A, b200_vector<V1>, b200_vector<V2>, B, b200_vector<V3> >
 {
-    static void apply(A a, const b200_vector<V> &x, const b200_vector<V> &y,
-            B b, b200_vector<V> &z)
+    static void apply(A a, const b200_vector<V1> &x, const b200_vector<V2> &y,
+            B b, b200_vector<V3> &z)
     {
         AMGCL_CALL_B200(b200_vmul(x.context(), static_cast<double>(a), x.handle(), y.handle(),
                     static_cast<double>(b), z.handle()));
@@ -456,16 +492,19 @@ struct damped_jacobi< backend::b200<real, C, P, DS> > {
         : prm(prm), dia( Backend::copy_vector( diagonal(A, true), backend_prm ) )
     { }
 
-    // x <- x + damping * D^-1 (rhs - A x), fused
-    void apply_pre(const typename Backend::matrix &A, const typename Backend::vector &rhs,
-            typename Backend::vector &x, typename Backend::vector &tmp) const
+    // x <- x + damping * D^-1 (rhs - A x), fused.  rhs / x may be FP64 vectors of the outer
+    // solver while A, D^-1 and tmp are this (FP32) hierarchy's: mixed precision, finest level.
+    template <typename VR, typename VX, typename VT>
+    void apply_pre(const typename Backend::matrix &A, const backend::b200_vector<VR> &rhs,
+            backend::b200_vector<VX> &x, backend::b200_vector<VT> &tmp) const
     {
         AMGCL_CALL_B200(b200_relax(A.context(), A.handle(), rhs.handle(), x.handle(),
                     tmp.handle(), dia->handle(), prm.damping));
     }
 
-    void apply_post(const typename Backend::matrix &A, const typename Backend::vector &rhs,
-            typename Backend::vector &x, typename Backend::vector &tmp) const
+    template <typename VR, typename VX, typename VT>
+    void apply_post(const typename Backend::matrix &A, const backend::b200_vector<VR> &rhs,
+            backend::b200_vector<VX> &x, backend::b200_vector<VT> &tmp) const
     {
         apply_pre(A, rhs, x, tmp);
     }
@@ -513,16 +552,18 @@ struct spai0< backend::b200<real, C, P, DS> > {
         M = Backend::copy_vector(w, backend_prm);
     }
 
-    // x <- x + M (rhs - A x), fused
-    void apply_pre(const typename Backend::matrix &A, const typename Backend::vector &rhs,
-            typename Backend::vector &x, typename Backend::vector &tmp) const
+    // x <- x + M (rhs - A x), fused (vector element types as for damped_jacobi above)
+    template <typename VR, typename VX, typename VT>
+    void apply_pre(const typename Backend::matrix &A, const backend::b200_vector<VR> &rhs,
+            backend::b200_vector<VX> &x, backend::b200_vector<VT> &tmp) const
     {
         AMGCL_CALL_B200(b200_relax(A.context(), A.handle(), rhs.handle(), x.handle(),
                     tmp.handle(), M->handle(), 1.0));
     }
 
-    void apply_post(const typename Backend::matrix &A, const typename Backend::vector &rhs,
-            typename Backend::vector &x, typename Backend::vector &tmp) const
+    template <typename VR, typename VX, typename VT>
+    void apply_post(const typename Backend::matrix &A, const backend::b200_vector<VR> &rhs,
+            backend::b200_vector<VX> &x, backend::b200_vector<VT> &tmp) const
     {
         apply_pre(A, rhs, x, tmp);
     }

@@ -39,6 +39,12 @@ extern "C" {
 #define B200_ESINGULAR    -5   /* coarse matrix is numerically singular          */
 #define B200_ENCCL        -6   /* NCCL error                                     */
 
+/* element types: FP64 is the default everywhere; FP32 objects exist for AMGCL's mixed
+ * precision composition (FP32 hierarchy under an FP64 Krylov solver,
+ * tutorial/1.poisson3Db/poisson3Db.cpp:45-51, docs/tutorial/poisson3Db.rst:259-292) */
+#define B200_F64           0
+#define B200_F32           1
+
 typedef struct b200_ctx_s    *b200_ctx_t;     /* device + stream + scratch            */
 typedef struct b200_csr_s    *b200_csr_t;     /* device CSR matrix (+ row-block plan) */
 typedef struct b200_vec_s    *b200_vec_t;     /* device FP64 vector                   */
@@ -170,6 +176,14 @@ int b200_vec_data(b200_vec_t v, double **device_ptr);
  * until the copy has completed (same semantics as thrust::copy, cuda.hpp:635-660). */
 int b200_vec_upload(b200_vec_t v, const double *host, size_t n);
 int b200_vec_download(b200_vec_t v, double *host, size_t n);
+/* FP32 vectors (single GPU only).  Every primitive below accepts the precision
+ * combinations AMGCL's mixed-precision composition produces -- all FP64, all FP32, and an
+ * FP32 matrix / diagonal applied to FP64 vectors (see DESIGN.md "Mixed precision") -- and
+ * returns B200_EINVAL for any other mix. */
+int b200_vec_create_f32(b200_ctx_t ctx, size_t n, b200_vec_t *v);
+int b200_vec_upload_f32(b200_vec_t v, const float *host, size_t n);
+int b200_vec_download_f32(b200_vec_t v, float *host, size_t n);
+int b200_vec_dtype(b200_vec_t v, int *dtype);
 
 /* ---------------------------------------------------------------- matrices */
 
@@ -183,6 +197,13 @@ int b200_csr_create_i64(b200_ctx_t ctx, int64_t nrows, int64_t ncols,
 int b200_csr_create_i32(b200_ctx_t ctx, int64_t nrows, int64_t ncols,
                         const int32_t *ptr, const int32_t *col, const double *val,
                         b200_csr_t *A);
+int b200_csr_create_i64_f32(b200_ctx_t ctx, int64_t nrows, int64_t ncols,
+                            const int64_t *ptr, const int64_t *col, const float *val,
+                            b200_csr_t *A);
+int b200_csr_create_i32_f32(b200_ctx_t ctx, int64_t nrows, int64_t ncols,
+                            const int32_t *ptr, const int32_t *col, const float *val,
+                            b200_csr_t *A);
+int b200_csr_dtype(b200_csr_t A, int *dtype);
 int b200_csr_destroy(b200_csr_t A);
 int b200_csr_rows(b200_csr_t A, size_t *n);
 int b200_csr_cols(b200_csr_t A, size_t *n);
@@ -256,6 +277,12 @@ int b200_coarse_create_i64(b200_ctx_t ctx, int64_t n, const int64_t *ptr,
                            const int64_t *col, const double *val, b200_coarse_t *S);
 int b200_coarse_create_i32(b200_ctx_t ctx, int64_t n, const int32_t *ptr,
                            const int32_t *col, const double *val, b200_coarse_t *S);
+/* FP32 hierarchy: the coarse matrix arrives in FP32, the inverse is formed and kept in
+ * FP64, and it is applied to FP32 vectors. */
+int b200_coarse_create_i64_f32(b200_ctx_t ctx, int64_t n, const int64_t *ptr,
+                               const int64_t *col, const float *val, b200_coarse_t *S);
+int b200_coarse_create_i32_f32(b200_ctx_t ctx, int64_t n, const int32_t *ptr,
+                               const int32_t *col, const float *val, b200_coarse_t *S);
 int b200_coarse_destroy(b200_coarse_t S);
 int b200_coarse_bytes(b200_coarse_t S, size_t *bytes);
 /* x = A^-1 rhs */

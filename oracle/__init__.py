@@ -241,6 +241,7 @@ class _Ref:
         R.ref_set_num_threads.restype = None
         R.ref_create.argtypes = [_i64, _vp, _vp, _vp, _c.c_int, _c.c_int, _dbl, _c.c_int,
                                  _c.c_int, _P(_vp)]
+        R.ref_create_mixed.argtypes = R.ref_create.argtypes
         R.ref_destroy.argtypes = [_vp]
         R.ref_destroy.restype = None
         R.ref_solve.argtypes = [_vp, _vp, _vp, _P(_i64), _P(_dbl)]
@@ -327,14 +328,16 @@ class RefSolver:
     """make_solver<amg<builtin<double>, smoothed_aggregation, RELAX>, KRYLOV> (the reference)."""
 
     def __init__(self, ptr, col, val, relax="damped_jacobi", krylov="cg", tol=1e-8,
-                 maxiter=100, coarse_enough=-1):
+                 maxiter=100, coarse_enough=-1, precision="f64"):
+        """precision 'mixed': amg<builtin<float>> under a builtin<double> Krylov solver."""
         self.r = ref()
         self.ptr = _arr(ptr, np.int64)
         self.col = _arr(col, np.int64)
         self.val = _arr(val, np.float64)
         self.n = self.ptr.size - 1
         self.h = _vp()
-        rc = self.r.R.ref_create(self.n, _p(self.ptr), _p(self.col), _p(self.val), RELAX[relax],
+        create = self.r.R.ref_create_mixed if precision == "mixed" else self.r.R.ref_create
+        rc = create(self.n, _p(self.ptr), _p(self.col), _p(self.val), RELAX[relax],
                                  KRYLOV[krylov], tol, maxiter, coarse_enough, _c.byref(self.h))
         if rc != 0:
             raise RuntimeError("ref_create: " + self.r.R.ref_last_error().decode())

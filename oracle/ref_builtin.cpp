@@ -91,6 +91,32 @@ struct SolverBase {
 };
 
 template <template <class> class Relax, template <class, class> class Krylov>
+struct MixedImpl : SolverBase {
+    // the reference's mixed-precision composition (tutorial/1.poisson3Db/poisson3Db.cpp:45-51)
+    typedef amgcl::make_solver<
+        amgcl::amg<amgcl::backend::builtin<float>, amgcl::coarsening::smoothed_aggregation, Relax>,
+        Krylov<amgcl::backend::builtin<double>, amgcl::solver::detail::default_inner_product>
+        > Solver;
+    std::unique_ptr<Solver> S;
+    MixedImpl(size_t n, const int64_t *ptr, const int64_t *col, const double *val, double tol,
+              int maxiter, int coarse_enough)
+    {
+        typename Solver::params prm;
+        prm.solver.tol = tol;
+        prm.solver.maxiter = maxiter;
+        if (coarse_enough >= 0) prm.precond.coarse_enough = coarse_enough;
+        auto A = std::make_tuple(n,
+                amgcl::make_iterator_range(ptr, ptr + n + 1),
+                amgcl::make_iterator_range(col, col + ptr[n]),
+                amgcl::make_iterator_range(val, val + ptr[n]));
+        S.reset(new Solver(A, prm));
+    }
+    std::tuple<size_t, double> solve(const HostVector &f, HostVector &x) override { return (*S)(f, x); }
+    void apply_precond(const HostVector &f, HostVector &x) override { S->precond().apply(f, x); }
+    std::string report() const override { std::ostringstream os; os << *S; return os.str(); }
+};
+
+template <template <class> class Relax, template <class, class> class Krylov>
 struct SolverImpl : SolverBase {
     typedef amgcl::make_solver<
         amgcl::amg<RecBackend, amgcl::coarsening::smoothed_aggregation, Relax>,
@@ -179,6 +205,27 @@ int ref_create(int64_t n, const int64_t *ptr, const int64_t *col, const double *
             h->solver.reset(new SolverImpl<relaxation::damped_jacobi, solver::gmres>(n, ptr, col, val, tol, maxiter, coarse_enough, bprm));
         else if (relax == 1 && krylov == 3)
             h->solver.reset(new SolverImpl<relaxation::spai0, solver::bicgstabl>(n, ptr, col, val, tol, maxiter, coarse_enough, bprm));
+        else { g_error = "unknown relax/krylov selector"; return -1; }
+        *out = h.release();
+        return 0;
+    } catch (const std::exception &e) { g_error = e.what(); return -1; }
+}
+
+int ref_create_mixed(int64_t n, const int64_t *ptr, const int64_t *col, const double *val, int relax,
+                     int krylov, double tol, int maxiter, int coarse_enough, void **out)
+{
+    try {
+        std::unique_ptr<Handle> h(new Handle());
+        h->n = (size_t)n;
+        using namespace amgcl;
+        if (relax == 0 && krylov == 0)
+            h->solver.reset(new MixedImpl<relaxation::damped_jacobi, solver::cg>(n, ptr, col, val, tol, maxiter, coarse_enough));
+        else if (relax == 1 && krylov == 1)
+            h->solver.reset(new MixedImpl<relaxation::spai0, solver::bicgstab>(n, ptr, col, val, tol, maxiter, coarse_enough));
+        else if (relax == 1 && krylov == 0)
+            h->solver.reset(new MixedImpl<relaxation::spai0, solver::cg>(n, ptr, col, val, tol, maxiter, coarse_enough));
+        else if (relax == 0 && krylov == 1)
+            h->solver.reset(new MixedImpl<relaxation::damped_jacobi, solver::bicgstab>(n, ptr, col, val, tol, maxiter, coarse_enough));
         else { g_error = "unknown relax/krylov selector"; return -1; }
         *out = h.release();
         return 0;

@@ -120,6 +120,19 @@ def main():
                 "x_norm2": float(np.linalg.norm(x))})
             print(known["primitive_only"][-1])
             S.close()
+    # the reference's mixed-precision composition: amg<builtin<float>> under a builtin<double> solver
+    known["mixed"] = []
+    for n in (16, 32, 48, 64):
+        ptr, col, val, rhs = poisson3d(n)
+        for relax, krylov in CONFIGS:
+            S = oracle.RefSolver(ptr, col, val, relax, krylov, precision="mixed")
+            x, iters, resid = S.solve(rhs)
+            known["mixed"].append({
+                "n": n, "relax": relax, "krylov": krylov, "iters": iters, "resid": resid,
+                "x_first": float(x[0]), "x_mid": float(x[x.size // 2]),
+                "x_norm2": float(np.linalg.norm(x))})
+            print("mixed", known["mixed"][-1])
+            S.close()
     # BASELINE.md section 2 (measured by the survey with the same reference build)
     known["survey"] = [
         {"n": 128, "relax": "damped_jacobi", "krylov": "cg", "iters": 21, "resid": 6.07447143094944e-09},

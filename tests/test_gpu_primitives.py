@@ -260,3 +260,111 @@ def test_dot_is_deterministic_and_compensated(ctx):
     assert r1 == r2
     import math
     assert abs(r1 - math.fsum(a)) < 1e-6
+
+
+def _f32vec(ctx, a):
+    """FP32 device vector from a numpy array (C ABI: b200_vec_create_f32 / upload_f32)."""
+    import ctypes
+    L = ab.lib()
+    L.b200_vec_create_f32.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]
+    L.b200_vec_upload_f32.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
+    L.b200_vec_download_f32.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
+    v = ab.Vector.__new__(ab.Vector)
+    v.ctx, v.h = ctx, ctypes.c_void_p()
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    v.n = a.size
+    assert L.b200_vec_create_f32(ctx.h, v.n, ctypes.byref(v.h)) == 0
+    assert L.b200_vec_upload_f32(v.h, a.ctypes.data, v.n) == 0
+
+    def numpy32():
+        out = np.empty(v.n, dtype=np.float32)
+        assert L.b200_vec_download_f32(v.h, out.ctypes.data, v.n) == 0, L.b200_last_error()
+        return out
+    v.numpy32 = numpy32
+    return v
+
+
+def _f32csr(ctx, nrows, ncols, ptr, col, val):
+    import ctypes
+    L = ab.lib()
+    L.b200_csr_create_i64_f32.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
+                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]
+    A = ab.Csr.__new__(ab.Csr)
+    A.ctx, A.h = ctx, ctypes.c_void_p()
+    ptr = np.ascontiguousarray(ptr, dtype=np.int64)
+    col = np.ascontiguousarray(col, dtype=np.int64)
+    val = np.ascontiguousarray(val, dtype=np.float32)
+    assert L.b200_csr_create_i64_f32(ctx.h, nrows, ncols, ptr.ctypes.data, col.ctypes.data,
+                                     val.ctypes.data, ctypes.byref(A.h)) == 0, L.b200_last_error()
+    A.nrows, A.ncols, A.nnz = nrows, ncols, int(ptr[-1])
+    return A
+
+
+def test_mixed_precision_primitives(ctx, golden):
+    """Every precision combination the mixed composition produces, against a numpy model that
+    rounds where the kernels round (row sums live in the output's element type)."""
+    g = golden
+    ptr, col, val = g.levels[0]["A"]
+    n = ptr.size - 1
+    import scipy.sparse as sp
+    A64 = sp.csr_matrix((val, col, ptr), shape=(n, n))
+    A32 = _f32csr(ctx, n, n, ptr, col, val)
+    a, b, c = g["in_a"], g["in_b"], g["in_c"]
+    a32, b32 = a.astype(np.float32), b.astype(np.float32)
+    Af = sp.csr_matrix((val.astype(np.float32), col, ptr), shape=(n, n))
+    scale = np.abs(A64).dot(np.abs(a)).max()
+
+    # FP32 operator on FP64 vectors (the Krylov solver's q = A p and r = f - A x)
+    va, vy = ctx.vector(a), ctx.vector(n)
+    ctx.spmv(1.0, A32, va, 0.0, vy)
+    assert np.abs(vy.numpy() - Af.astype(np.float64).dot(a)).max() < 1e-13 * scale
+    vc, vr = ctx.vector(c), ctx.vector(n)
+    ctx.residual(vc, A32, va, vr)
+    assert np.abs(vr.numpy() - (c - Af.astype(np.float64).dot(a))).max() < 1e-13 * scale
+
+    # all FP32 (levels below the finest)
+    fa, fy = _f32vec(ctx, a32), _f32vec(ctx, np.zeros(n))
+    ctx.spmv(1.0, A32, fa, 0.0, fy)
+    want = Af.astype(np.float64).dot(a32.astype(np.float64))
+    assert np.abs(fy.numpy32() - want).max() < 5e-6 * scale
+
+    # finest-level residual: FP64 rhs and x, FP32 result
+    ft = _f32vec(ctx, np.zeros(n))
+    ctx.residual(vc, A32, va, ft)
+    assert np.abs(ft.numpy32() - (c - Af.astype(np.float64).dot(a))).max() < 5e-6 * scale
+
+    # prolongation of an FP32 correction into the FP64 iterate
+    lv = g.levels[0]
+    nc = lv["R"][0].size - 1
+    P32 = _f32csr(ctx, n, nc, *lv["P"])
+    fu = _f32vec(ctx, g["in_u"])
+    vb = ctx.vector(b)
+    ctx.spmv(1.0, P32, fu, 1.0, vb)
+    Pf = sp.csr_matrix((lv["P"][2].astype(np.float32), lv["P"][1], lv["P"][0]), shape=(n, nc))
+    want = b + Pf.astype(np.float64).dot(g["in_u"].astype(np.float32).astype(np.float64))
+    assert np.abs(vb.numpy() - want).max() < 1e-13 * max(1.0, np.abs(want).max())
+
+    # smoother sweep: FP32 operator + diagonal + scratch, FP64 rhs and iterate (fused and not)
+    d32 = lv["diag"].astype(np.float32)
+    for fuse in (1, 0):
+        ctx.set_option("fuse_relax", fuse)
+        try:
+            vx, vrhs = ctx.vector(a), ctx.vector(c)
+            fd, ftmp = _f32vec(ctx, d32), _f32vec(ctx, np.zeros(n))
+            ctx.relax(A32, vrhs, vx, ftmp, fd, g.omega)
+            t = c - Af.astype(np.float64).dot(a)
+            want = a + (g.omega * d32.astype(np.float64)) * t
+            assert np.abs(vx.numpy() - want).max() < 2e-6 * max(1.0, np.abs(want).max())
+            ctx.clear(vx)
+            ctx.relax(A32, vrhs, vx, ftmp, fd, g.omega)       # x == 0 shortcut, mixed
+            want0 = (g.omega * d32.astype(np.float64)) * c
+            assert np.abs(vx.numpy() - want0).max() < 2e-6 * max(1.0, np.abs(want0).max())
+        finally:
+            ctx.set_option("fuse_relax", 1)
+
+    # unsupported mixes are refused, not silently converted
+    with pytest.raises(ab.B200Error):
+        ctx.axpby(1.0, fa, 1.0, va)
+    A64d = ctx.csr(n, n, ptr, col, val)
+    with pytest.raises(ab.B200Error):
+        ctx.spmv(1.0, A64d, fa, 0.0, vy)

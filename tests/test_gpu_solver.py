@@ -168,3 +168,25 @@ def test_multi_gpu_parity_when_two_devices_are_present():
                           "29541", os.path.join(root, "tools", "dist_check.py"), "32"],
                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert "DIST_CHECK PASS" in out.stdout, out.stdout[-2000:]
+
+
+@pytest.mark.parametrize("n", [16, 32, 64])
+@pytest.mark.parametrize("relax,krylov", CONFIGS)
+def test_mixed_precision_matches_reference_mixed(ctx, known_answers, n, relax, krylov):
+    """SURVEY 8f rank 2: FP32 hierarchy (amg<backend::b200<float>>) under an FP64 Krylov solver,
+    against the reference's own mixed composition amg<builtin<float>> + builtin<double>
+    (tutorial/1.poisson3Db/poisson3Db.cpp:45-51).  FP32 rounding differs between the two
+    (summation order, FMA), so the tolerance is FP32-sized: same iteration count (+-1),
+    solution within 1e-6 of the reference's, true FP64 residual below 2e-8."""
+    case = [c for c in known_answers["mixed"]
+            if (c["n"], c["relax"], c["krylov"]) == (n, relax, krylov)][0]
+    ptr, col, val, rhs = ab.poisson3d(n)
+    S = ab.DropinSolver(ptr, col, val, relax, krylov, ctx=ctx, precision="mixed")
+    x, iters, resid = S.solve(rhs)
+    assert abs(iters - case["iters"]) <= 1
+    assert resid < 1e-8
+    assert abs(np.linalg.norm(x) - case["x_norm2"]) <= 1e-6 * case["x_norm2"]
+    assert abs(x[0] - case["x_first"]) <= 1e-6 * abs(case["x_first"])
+    r = rhs - oracle.c().spmv(1.0, (ptr, col, val), x, 0.0, np.zeros_like(x))
+    assert np.linalg.norm(r) / np.linalg.norm(rhs) < 2e-8
+    S.close()

@@ -168,9 +168,8 @@ def cmd_spmv(n):
     d = np.full(nr, 1.0 / 6.0)
     configs = []
     for variant, nnz_cap, cps, stages in (
-            (0, 2048, 0, 0), (0, 1024, 0, 0), (0, 4096, 0, 0),
-            (1, 2048, 2, 4), (1, 2048, 2, 3), (1, 2048, 4, 2), (1, 1024, 4, 4),
-            (1, 4096, 1, 4), (1, 4096, 2, 2), (1, 2048, 1, 8), (1, 2048, 3, 3)):
+            (0, 2048, 0, 0), (1, 2048, 4, 2), (1, 2048, 5, 2), (1, 1536, 5, 2), (1, 2048, 3, 3),
+            (1, 1536, 6, 2), (1, 2048, 4, 3)):
         configs.append((variant, nnz_cap, cps, stages))
     for variant, nnz_cap, cps, stages in configs:
         ctx.set_option("nnz_cap", nnz_cap)
@@ -233,8 +232,8 @@ def cmd_levels(n):
         x = rng.uniform(-1, 1, nc)
         gb = algorithmic_bytes(nr, nc, nnz, "spmv") / 1e9
         best = None
-        for lanes in (1, 2, 4, 8, 16, 32):
-            for nnz_cap, cps, stages in ((2048, 4, 2), (1024, 4, 4), (4096, 2, 2), (1024, 6, 2), (2048, 3, 3)):
+        for lanes in (1, 2, 4, 8, 16):
+            for nnz_cap, cps, stages in ((2048, 4, 2), (2048, 5, 2), (4096, 2, 2), (1536, 5, 2)):
                 ctx.set_option("lanes", lanes)
                 ctx.set_option("nnz_cap", nnz_cap)
                 ctx.set_option("ctas_per_sm", cps)
