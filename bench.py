@@ -39,6 +39,9 @@ def parse_args():
     ap.add_argument("--relax", default="damped_jacobi", choices=["damped_jacobi", "spai0"])
     ap.add_argument("--krylov", default="cg", choices=["cg", "bicgstab"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="f64", choices=["f64", "mixed"],
+                    help="f64 (BASELINE config, default) or mixed = FP32 hierarchy under an FP64 "
+                         "Krylov solver (the reference's mixed-precision composition; not the headline)")
     ap.add_argument("--partition", default="all", choices=["finest", "all"],
                     help="N>1: partition only the finest level (north star) or every level "
                          "with at least --partition-min-rows rows")
@@ -51,7 +54,8 @@ def parse_args():
 
 
 def workload_name(args):
-    return "poisson3d_%d^3_fp64_sa_%s_%s" % (args.n, args.relax, args.krylov)
+    prec = "fp64" if args.precision == "f64" else "mixed_fp64krylov_fp32amg"
+    return "poisson3d_%d^3_%s_sa_%s_%s" % (args.n, prec, args.relax, args.krylov)
 
 
 def peaks():
@@ -156,7 +160,8 @@ def reference_arm(args, rank, world):
     ptr, col, val, rhs = poisson3d(args.n)
     t_gen = time.time() - t0
     t0 = time.time()
-    S = oracle.RefSolver(ptr, col, val, args.relax, args.krylov, maxiter=args.ref_sample_iters)
+    S = oracle.RefSolver(ptr, col, val, args.relax, args.krylov, maxiter=args.ref_sample_iters,
+                         precision=args.precision)
     t_setup = time.time() - t0
     cores = pick_threads(ref, lambda: S.solve(rhs))
     for _ in range(args.warmup):
@@ -173,7 +178,8 @@ def reference_arm(args, rank, world):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64" if args.precision == "f64" else "f64 krylov + f32 hierarchy",
         "data": "synthetic",
         "config": {"workload": workload_name(args), "backend": "amgcl::backend::builtin<double> (OpenMP)",
                    "rows": int(ptr.size - 1), "nnz": int(ptr[-1]), "setup_s": t_setup,
@@ -195,9 +201,9 @@ def cpu_baseline_leg(args, ptr, col, val, rhs, full_iters):
         return None
     ref = oracle.ref()
     t0 = time.time()
-    S = oracle.RefSolver(ptr, col, val, args.relax, args.krylov)
+    S = oracle.RefSolver(ptr, col, val, args.relax, args.krylov, precision=args.precision)
     t_setup = time.time() - t0
-    Sq = oracle.RefSolver(ptr, col, val, args.relax, args.krylov, maxiter=2)
+    Sq = oracle.RefSolver(ptr, col, val, args.relax, args.krylov, maxiter=2, precision=args.precision)
     threads = pick_threads(ref, lambda: Sq.solve(rhs))
     Sq.close()
     S.solve(rhs)                       # warm the caches / page in
@@ -249,7 +255,7 @@ def main_arm(args, rank, world, local_rank):
             if ctx.dist_info()["p2p"] else "NCCL collectives"
 
     t0 = time.time()
-    S = ab.DropinSolver(ptr, col, val, args.relax, args.krylov, ctx=ctx)
+    S = ab.DropinSolver(ptr, col, val, args.relax, args.krylov, ctx=ctx, precision=args.precision)
     t_setup = time.time() - t0
 
     def barrier():
@@ -296,7 +302,7 @@ def main_arm(args, rank, world, local_rank):
     finest = [p for p in csr_prof if p["nnz"] == big and p["mode"] != "spmv_acc"]
     peak, peak_src = peaks()
     roof = None
-    if finest:
+    if finest and args.precision == "f64":
         def alg_bytes(p):
             b = p["nnz"] * 12 + (p["nrows"] + 1) * 4 + p["ncols"] * 8 + p["nrows"] * 8
             if p["mode"] in ("residual", "spmv_acc"):
@@ -391,7 +397,8 @@ def main_arm(args, rank, world, local_rank):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": solve_s * 1e3, "higher_is_better": True,
-            "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "f64",
+            "scaling": "weak" if world == 1 else "strong", "vs_baseline": None,
+            "dtype": "f64" if args.precision == "f64" else "f64 krylov + f32 hierarchy",
             "data": "synthetic",
             "config": {"workload": workload_name(args), "rows": nrows, "nnz": nnz,
                        "relax": args.relax, "krylov": args.krylov, "tol": 1e-8,
