@@ -323,11 +323,16 @@ def main_arm(args, rank, world, local_rank):
                 "by_mode": {p["mode"]: {"launches": p["launches"],
                                         "GBs": alg_bytes(p) * p["launches"] / (p["total_ms"] * 1e-3) / 1e9}
                             for p in finest}}
+        # DRAM bytes per launch from the committed ncu --set full capture (only valid for the
+        # workload it was captured on: single GPU, same operator)
         ncu = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.isfile(ncu):
+        if os.path.isfile(ncu) and world == 1:
             try:
                 with open(ncu) as f:
-                    roof["traffic"] = json.load(f).get("dram_bytes_per_launch")
+                    tj = json.load(f)
+                if int(tj.get("nnz", -1)) == nnz:
+                    roof["traffic"] = tj.get("dram_bytes_per_launch")
+                    roof["traffic_kernel"] = tj.get("kernel")
             except Exception:
                 pass
     all_csr_ms = sum(p["total_ms"] for p in prof if p["nnz"] > 0 and p["mode"] != "coarse_gemv")

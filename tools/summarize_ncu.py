@@ -100,7 +100,7 @@ def full_capture(tag, rep):
                 return float(r[i].replace(",", "")) * scale
             rd, wr = val("dram__bytes_read.sum"), val("dram__bytes_write.sum")
             traffic = {"kernel": "csr_ring_kernel<2, 1> (residual r = f - A x on the finest level, 256^3)",
-                       "dram_bytes_read": rd, "dram_bytes_write": wr,
+                       "nnz": 117047296, "dram_bytes_read": rd, "dram_bytes_write": wr,
                        "dram_bytes_per_launch": rd + wr,
                        "algorithmic_bytes_per_launch": 117047296 * 12 + 16777217 * 4 + 3 * 16777216 * 8,
                        "source": "profiles/%s_csr_kernels.md (ncu --set full, one launch)" % tag}
