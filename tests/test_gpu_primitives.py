@@ -368,3 +368,44 @@ def test_mixed_precision_primitives(ctx, golden):
     A64d = ctx.csr(n, n, ptr, col, val)
     with pytest.raises(ab.B200Error):
         ctx.spmv(1.0, A64d, fa, 0.0, vy)
+
+
+def test_wrapping_torch_memory(ctx):
+    """b200_vec_wrap: the primitives run on caller-owned device memory (here torch tensors on
+    torch's current stream); the fused sweep copies back instead of swapping storage."""
+    import ctypes
+    import torch
+    o = oracle.c()
+    ptr, col, val, rhs = ab.poisson3d(10)
+    n = ptr.size - 1
+    rng = np.random.default_rng(11)
+    xh, fh = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
+    dev = torch.device("cuda", 0)
+    tx = torch.tensor(xh, device=dev)
+    tf = torch.tensor(fh, device=dev)
+    ty = torch.zeros(n, dtype=torch.float64, device=dev)
+    L = ab.lib()
+
+    def wrap(t):
+        v = ab.Vector.__new__(ab.Vector)
+        v.ctx, v.h, v.n = ctx, ctypes.c_void_p(), t.numel()
+        assert L.b200_vec_wrap(ctx.h, ctypes.c_void_p(t.data_ptr()), v.n, ctypes.byref(v.h)) == 0
+        return v
+
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    try:
+        A = ctx.csr(n, n, ptr, col, val)
+        vx, vf, vy = wrap(tx), wrap(tf), wrap(ty)
+        ctx.residual(vf, A, vx, vy)
+        torch.cuda.synchronize()
+        assert rel_err(ty.cpu().numpy(), o.residual(fh, (ptr, col, val), xh)) < TOL_PRIMITIVE
+        d = o.relax_diag((ptr, col, val), "damped_jacobi")
+        vd = ctx.vector(d)
+        before = tx.data_ptr()
+        ctx.relax(A, vf, vx, vy, vd, 0.72)             # x is external: result must land in tx
+        torch.cuda.synchronize()
+        assert tx.data_ptr() == before
+        assert rel_err(tx.cpu().numpy(), o.relax((ptr, col, val), fh, xh, d, 0.72)) < TOL_PRIMITIVE
+        assert abs(ctx.dot(vx, vx) - float((tx * tx).sum().item())) < 1e-9
+    finally:
+        ctx.set_stream(None)

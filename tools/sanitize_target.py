@@ -1,0 +1,39 @@
+#!/usr/bin/env python
+"""Small workload for compute-sanitizer: every kernel family once, tiny sizes."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import amgcl_b200 as ab  # noqa: E402
+
+ctx = ab.Context(0)
+rng = np.random.default_rng(0)
+for variant in (1, 0):
+    ctx.set_option("spmv_variant", variant)
+    for lanes in (0, 2, 8, 32):
+        ctx.set_option("lanes", lanes)
+        nr, nc = 1500, 1300
+        lens = rng.integers(0, 30, nr)
+        lens[5] = 4000
+        ptr = np.zeros(nr + 1, dtype=np.int64)
+        np.cumsum(lens, out=ptr[1:])
+        col = rng.integers(0, nc, ptr[-1])
+        val = rng.uniform(-1, 1, ptr[-1])
+        A = ctx.csr(nr, nc, ptr, col, val)
+        x, y, f = ctx.vector(rng.uniform(-1, 1, nc)), ctx.vector(nr), ctx.vector(rng.uniform(-1, 1, nr))
+        ctx.spmv(1.0, A, x, 0.0, y)
+        ctx.spmv(1.0, A, x, 0.5, y)
+        ctx.residual(f, A, x, y)
+ctx.set_option("lanes", 0)
+ctx.set_option("spmv_variant", 1)
+for relax, krylov, prec in (("damped_jacobi", "cg", "f64"), ("spai0", "bicgstab", "f64"),
+                            ("damped_jacobi", "cg", "mixed")):
+    ptr, col, val, rhs = ab.poisson3d(14)
+    S = ab.DropinSolver(ptr, col, val, relax, krylov, coarse_enough=200, ctx=ctx, precision=prec)
+    x, it, res = S.solve(rhs)
+    print(relax, krylov, prec, it, res)
+    S.close()
+print("SANITIZE_TARGET_DONE")
