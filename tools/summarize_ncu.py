@@ -7,6 +7,7 @@ Writes profiles/<tag>_launches.csv (copy), profiles/<tag>_launch_shares.md,
 profiles/<tag>_csr_kernels.md (per-kernel metrics of the --set full capture) and
 profiles/traffic.json (DRAM bytes per launch of the dominant kernel, read by bench.py)."""
 import collections
+import re
 import csv
 import io
 import json
@@ -19,6 +20,19 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PROF = os.path.join(ROOT, "profiles")
 
 
+def short_name(full):
+    """'void b200::csr_ring_kernel<3, 1, 0, Prec<double, ...>>(args)' -> 'csr_ring_kernel<3, 1> f64'."""
+    name = full.split("(")[0].replace("void ", "").replace("b200::", "")
+    m = re.match(r"(csr_\w+_kernel)<(\d+), (\d+), (\d+), Prec<([^>]*)>>", name)
+    if m:
+        types = [t.strip() for t in m.group(5).split(",")]
+        prec = "f64" if all(t == "double" for t in types) else \
+               "f32" if all(t == "float" for t in types) else "mixed"
+        return "%s<%s, %s>%s %s" % (m.group(1), m.group(2), m.group(3),
+                                    " halo" if m.group(4) == "1" else "", prec)
+    return name
+
+
 def launch_shares(tag, path):
     rows = list(csv.reader(open(path)))
     hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
@@ -28,7 +42,7 @@ def launch_shares(tag, path):
     agg = collections.OrderedDict()
     tot = 0.0
     for r in data:
-        key = r[kn].split("(")[0].replace("void ", "")
+        key = short_name(r[kn])
         t = float(r[mv].replace(",", ""))
         a = agg.setdefault(key, [0, 0.0])
         a[0] += 1
@@ -44,8 +58,7 @@ def launch_shares(tag, path):
            "| kernel | launches | total us | share | avg us |", "|---|---:|---:|---:|---:|"]
     for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         out.append("| `%s` | %d | %.1f | %.1f%% | %.2f |" % (k, n, t / 1e3, 100 * t / tot, t / n / 1e3))
-    finest = sum(t for k, (n, t) in agg.items() if k.startswith("csr_ring_kernel<") and
-                 k.endswith(", 1>") and not k.startswith("csr_ring_kernel<1"))
+    finest = sum(t for k, (n, t) in agg.items() if re.match(r"csr_ring_kernel<[023], 1>", k))
     out += ["", "Finest-level A passes (`csr_ring_kernel<0|2|3, 1>`): %.1f%% of the captured kernel time."
             % (100 * finest / tot)]
     open(os.path.join(PROF, tag + "_launch_shares.md"), "w").write("\n".join(out) + "\n")
@@ -91,9 +104,9 @@ def full_capture(tag, rep):
                 cells.append("%s %s" % (v, units[i]) if units[i] not in ("", "%") else v)
             else:
                 cells.append("n/a")
-        name = r[kn].split("(")[0].replace("void ", "")
+        name = short_name(r[kn])
         out.append("| `%s` | " % name + " | ".join(cells) + " |")
-        if traffic is None and name == "csr_ring_kernel<2, 1>":
+        if traffic is None and name.startswith("csr_ring_kernel<2, 1>"):
             def val(key):
                 i = hdr.index(key)
                 scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[units[i]]
