@@ -20,8 +20,8 @@ import numpy as np
 from . import build as _build
 
 __all__ = ["lib", "dropin_lib", "Context", "Vector", "Csr", "Coarse", "DropinSolver",
-           "poisson3d", "B200Error", "RELAX", "KRYLOV", "nccl_unique_id", "partition",
-           "dist_split"]
+           "poisson3d", "unstructured3d", "B200Error", "RELAX", "KRYLOV", "nccl_unique_id",
+           "partition", "dist_split"]
 
 _c = ctypes
 _i64 = _c.c_int64
@@ -532,6 +532,32 @@ def dist_split(kind, nranks, rank, nrows, ncols, ptr, col, val):
         lib().b200_split_destroy(h)
     return {"nrows": nr.value, "ncols": nc.value, "n_loc": nl.value, "slots": S.value,
             "ptr": p, "col": c, "val": v, "send_idx": si}
+
+
+def unstructured3d(n, k=24, seed=0):
+    """Synthetic stand-in for BASELINE.json config #4 (poisson3Db.mtx is not available offline):
+    an SPD weighted graph Laplacian (+ small diagonal shift) on n random points of the unit
+    cube, each connected to its k nearest neighbours with weight 1/d^2 (finite-element-like:
+    near neighbours are strongly coupled), symmetrised -- an unstructured CSR with the row
+    statistics of poisson3Db (85,623 rows, ~28 nnz/row at n = 85623, k = 24), rows in random
+    (point) order.  Returns (ptr, col, val, rhs)."""
+    import scipy.sparse as sp
+    from scipy.spatial import cKDTree
+    rng = np.random.default_rng(seed)
+    pts = rng.uniform(0.0, 1.0, (int(n), 3))
+    dist, nbr = cKDTree(pts).query(pts, k=k + 1)
+    rows = np.repeat(np.arange(n), k)
+    cols = nbr[:, 1:].reshape(-1)
+    h2 = float(np.median(dist[:, 1])) ** 2
+    w = h2 / (dist[:, 1:].reshape(-1) ** 2 + 1e-3 * h2)
+    W = sp.coo_matrix((w, (rows, cols)), shape=(n, n)).tocsr()
+    W = W.maximum(W.T)                                 # symmetric weights
+    deg = np.asarray(W.sum(axis=1)).ravel()
+    A = (sp.diags(deg * (1.0 + 1e-3)) - W).tocsr()
+    A.sort_indices()
+    rhs = np.ones(n)
+    return (A.indptr.astype(np.int64), A.indices.astype(np.int64),
+            np.ascontiguousarray(A.data, dtype=np.float64), rhs)
 
 
 def poisson3d(n, dtype_index=np.int64):

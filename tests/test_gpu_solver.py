@@ -190,3 +190,22 @@ def test_mixed_precision_matches_reference_mixed(ctx, known_answers, n, relax, k
     r = rhs - oracle.c().spmv(1.0, (ptr, col, val), x, 0.0, np.zeros_like(x))
     assert np.linalg.norm(r) / np.linalg.norm(rhs) < 2e-8
     S.close()
+
+
+@pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not shipped")
+@pytest.mark.parametrize("relax,krylov", CONFIGS[:2])
+def test_unstructured_matrix_vs_live_reference(ctx, relax, krylov):
+    """BASELINE.json config #4 class of input (poisson3Db.mtx itself is not available offline):
+    an unstructured SPD matrix with ~28 non-zeros per row in random row order.  Irregular rows
+    exercise the multi-lane reduction and scattered gathers on every level."""
+    ptr, col, val, rhs = ab.unstructured3d(30000)
+    R = oracle.RefSolver(ptr, col, val, relax, krylov)
+    S = ab.DropinSolver(ptr, col, val, relax, krylov, ctx=ctx)
+    xr, itr, resr = R.solve(rhs)
+    xg, itg, resg = S.solve(rhs)
+    assert R.nlevels >= 3
+    assert itg == itr
+    assert abs(resg - resr) <= 1e-5 * resr
+    assert rel_err(xg, xr) < TOL_SOLUTION
+    S.close()
+    R.close()

@@ -251,11 +251,59 @@ def cmd_levels(n):
         print(json.dumps({"BEST": best}), flush=True)
 
 
+def cmd_unstructured():
+    """BASELINE.json config #4 stand-in (poisson3Db.mtx is not available offline): synthetic
+    unstructured SPD matrices with poisson3Db's row statistics; AMG + Krylov parity against the
+    reference and an SpMV GB/s sweep over sizes from L2-resident to HBM-resident."""
+    import oracle
+    side = torch.cuda.Stream()
+    torch.cuda.set_stream(side)
+    ctx = ab.Context(0, stream=side.cuda_stream)
+    rng = np.random.default_rng(3)
+    for mult in (1, 4, 16, 64):
+        n = 85623 * mult
+        t0 = time.time()
+        ptr, col, val, rhs = ab.unstructured3d(n)
+        nnz = int(ptr[-1])
+        rec = {"matrix": "unstructured3d(n=%d, k=24) [synthetic stand-in for poisson3Db]" % n,
+               "rows": n, "nnz": nnz, "nnz_per_row": round(nnz / n, 2), "generate_s": round(time.time() - t0, 1)}
+        A = ctx.csr(n, n, ptr, col, val)
+        x = rng.uniform(-1, 1, n)
+        vx, vy, vf = ctx.vector(x), ctx.vector(n), ctx.vector(rhs)
+        rec["plan"] = A.plan()
+        for mode, fn in (("spmv", lambda: ctx.spmv(1.0, A, vx, 0.0, vy)),
+                         ("residual", lambda: ctx.residual(vf, A, vx, vy))):
+            med, best = time_op(fn)
+            gb = algorithmic_bytes(n, n, nnz, mode) / 1e9
+            rec[mode] = {"ms": round(med, 4), "GBs": round(gb / (med * 1e-3), 1)}
+        rec["fits_l2"] = bool(nnz * 12 < 100e6)
+        if mult <= 4:
+            for relax, kry in (("spai0", "bicgstab"), ("damped_jacobi", "cg")):
+                D = ab.DropinSolver(ptr, col, val, relax, kry, ctx=ctx)
+                t1 = time.time()
+                xg, itg, resg = D.solve(rhs)
+                key = "%s_%s" % (relax, kry)
+                rec[key] = {"gpu_iters": itg, "gpu_resid": resg, "gpu_solve_s": round(time.time() - t1, 4)}
+                if oracle.have_ref():
+                    R = oracle.RefSolver(ptr, col, val, relax, kry)
+                    t1 = time.time()
+                    xr, itr, resr = R.solve(rhs)
+                    rec[key].update({"ref_iters": itr, "ref_resid": resr,
+                                     "ref_solve_s": round(time.time() - t1, 4),
+                                     "x_rel_err": float(np.abs(xg - xr).max() / np.abs(xr).max())})
+                    R.close()
+                D.close()
+        print(json.dumps(rec), flush=True)
+        del A, vx, vy, vf
+
+
 if __name__ == "__main__":
     cmd = sys.argv[1] if len(sys.argv) > 1 else "parity"
     if cmd == "parity":
         cmd_parity()
     elif cmd == "spmv":
         cmd_spmv(int(sys.argv[2]) if len(sys.argv) > 2 else 128)
+    elif cmd == "unstructured":
+        cmd_unstructured()
     elif cmd == "levels":
         cmd_levels(int(sys.argv[2]) if len(sys.argv) > 2 else 128)
