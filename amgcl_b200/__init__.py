@@ -534,17 +534,31 @@ def dist_split(kind, nranks, rank, nrows, ncols, ptr, col, val):
             "ptr": p, "col": c, "val": v, "send_idx": si}
 
 
-def unstructured3d(n, k=24, seed=0):
+def _morton_order(pts, bits=10):
+    """Indices that sort 3-D points along a Z-order (Morton) curve: the locality a mesh
+    generator's numbering typically has."""
+    q = np.minimum((pts * (1 << bits)).astype(np.uint64), (1 << bits) - 1)
+    code = np.zeros(pts.shape[0], dtype=np.uint64)
+    for b in range(bits):
+        for d in range(3):
+            code |= ((q[:, d] >> np.uint64(b)) & np.uint64(1)) << np.uint64(3 * b + d)
+    return np.argsort(code, kind="stable")
+
+
+def unstructured3d(n, k=24, seed=0, order="morton"):
     """Synthetic stand-in for BASELINE.json config #4 (poisson3Db.mtx is not available offline):
     an SPD weighted graph Laplacian (+ small diagonal shift) on n random points of the unit
     cube, each connected to its k nearest neighbours with weight 1/d^2 (finite-element-like:
     near neighbours are strongly coupled), symmetrised -- an unstructured CSR with the row
-    statistics of poisson3Db (85,623 rows, ~28 nnz/row at n = 85623, k = 24), rows in random
-    (point) order.  Returns (ptr, col, val, rhs)."""
+    statistics of poisson3Db (85,623 rows, ~28 nnz/row at n = 85623, k = 24).  order="morton"
+    numbers the points along a space-filling curve (mesh-like locality); order="random" keeps
+    the random point order (worst case for the x-gathers).  Returns (ptr, col, val, rhs)."""
     import scipy.sparse as sp
     from scipy.spatial import cKDTree
     rng = np.random.default_rng(seed)
     pts = rng.uniform(0.0, 1.0, (int(n), 3))
+    if order == "morton":
+        pts = pts[_morton_order(pts)]
     dist, nbr = cKDTree(pts).query(pts, k=k + 1)
     rows = np.repeat(np.arange(n), k)
     cols = nbr[:, 1:].reshape(-1)

@@ -198,7 +198,7 @@ def test_unstructured_matrix_vs_live_reference(ctx, relax, krylov):
     """BASELINE.json config #4 class of input (poisson3Db.mtx itself is not available offline):
     an unstructured SPD matrix with ~28 non-zeros per row in random row order.  Irregular rows
     exercise the multi-lane reduction and scattered gathers on every level."""
-    ptr, col, val, rhs = ab.unstructured3d(30000)
+    ptr, col, val, rhs = ab.unstructured3d(20000, order="random" if krylov == "cg" else "morton")
     R = oracle.RefSolver(ptr, col, val, relax, krylov)
     S = ab.DropinSolver(ptr, col, val, relax, krylov, ctx=ctx)
     xr, itr, resr = R.solve(rhs)
