@@ -232,8 +232,14 @@ def cmd_levels(n):
         x = rng.uniform(-1, 1, nc)
         gb = algorithmic_bytes(nr, nc, nnz, "spmv") / 1e9
         best = None
-        for lanes in (1, 2, 4, 8, 16):
-            for nnz_cap, cps, stages in ((2048, 4, 2), (2048, 5, 2), (4096, 2, 2), (1536, 5, 2)):
+        cfgs = ((2048, 4, 2), (2048, 5, 2), (4096, 2, 2), (1536, 5, 2))
+        lane_set = (1, 2, 4, 8, 16)
+        if os.environ.get("B200_SWEEP"):          # e.g. "1024:4:2,1024:2:2;2,4"
+            c, l = os.environ["B200_SWEEP"].split(";")
+            cfgs = tuple(tuple(int(v) for v in t.split(":")) for t in c.split(","))
+            lane_set = tuple(int(v) for v in l.split(","))
+        for lanes in lane_set:
+            for nnz_cap, cps, stages in cfgs:
                 ctx.set_option("lanes", lanes)
                 ctx.set_option("nnz_cap", nnz_cap)
                 ctx.set_option("ctas_per_sm", cps)
