@@ -147,6 +147,8 @@ def dropin_lib():
     D.dropin_destroy.restype = None
     D.dropin_solve.argtypes = [_vp, _vp, _vp, _P(_i64), _P(_dbl)]
     D.dropin_solve.restype = _c.c_int
+    D.dropin_solve_zero_guess.argtypes = [_vp, _vp, _vp, _P(_i64), _P(_dbl)]
+    D.dropin_solve_zero_guess.restype = _c.c_int
     D.dropin_upload_rhs.argtypes = [_vp, _vp]
     D.dropin_upload_rhs.restype = _c.c_int
     D.dropin_solve_resident.argtypes = [_vp, _P(_i64), _P(_dbl)]
@@ -444,6 +446,16 @@ class DropinSolver:
         res = _dbl()
         if dropin_lib().dropin_solve(self.h, _ptr(rhs), _ptr(x), _c.byref(it), _c.byref(res)):
             self._err("dropin_solve")
+        return it.value, res.value
+
+    def solve_zero_guess_into(self, rhs, x_out):
+        """Host rhs in, host solution out, x0 = 0 created on the device (the tutorial's call
+        pattern): one H2D and one D2H copy per solve."""
+        it = _i64()
+        res = _dbl()
+        if dropin_lib().dropin_solve_zero_guess(self.h, _ptr(rhs), _ptr(x_out), _c.byref(it),
+                                                _c.byref(res)):
+            self._err("dropin_solve_zero_guess")
         return it.value, res.value
 
     def upload_rhs(self, rhs):

@@ -195,6 +195,27 @@ int dropin_solve(void *handle, const double *rhs_host, double *x_host, int64_t *
     }
 }
 
+// End-to-end call as the reference's tutorial does it (poisson3Db_cuda.cu:83-87): the
+// right-hand side comes from the host, the initial guess x0 = 0 is created on the device,
+// the solution goes back to the host.
+int dropin_solve_zero_guess(void *handle, const double *rhs_host, double *x_host, int64_t *iters,
+                            double *resid)
+{
+    Handle *h = static_cast<Handle *>(handle);
+    try {
+        h->f->upload(rhs_host);
+        amgcl::backend::clear(*h->x);
+        size_t it; double r;
+        std::tie(it, r) = h->solver->solve(*h->f, *h->x);
+        h->x->download(x_host);
+        *iters = (int64_t)it; *resid = r;
+        return 0;
+    } catch (const std::exception &e) {
+        g_error = e.what();
+        return -1;
+    }
+}
+
 // Device-resident variant: rhs uploaded beforehand, x0 = 0, x stays on the device.
 int dropin_upload_rhs(void *handle, const double *rhs_host)
 {
