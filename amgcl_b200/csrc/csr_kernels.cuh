@@ -218,6 +218,54 @@ __device__ __forceinline__ void compute_staged(const CsrArgsT<P> &a, const Block
     const int nr   = d.r1 - d.r0;
     const TX *__restrict__ x = a.x;
 
+    if (L >= 16) {
+        // Wide groups (a half or a full warp per row): consecutive lanes read consecutive
+        // entries, so the shared-memory reads are bank-conflict free and the gathers of one
+        // row coalesce.  Memory-level parallelism comes from working on RU rows at once
+        // instead of batching along one (short) row.
+        constexpr int RU = kGatherBatch;
+        for (int base = 0; base < nr; base += G * RU) {
+            int  beg[RU], end[RU], c[RU];
+            TV   v[RU];
+            TX   xv[RU];
+            TS   sum[RU];
+            bool rowok[RU], p[RU];
+#pragma unroll
+            for (int u = 0; u < RU; ++u) {
+                const int rr = base + u * G + g;
+                rowok[u] = rr < nr;
+                beg[u] = rowok[u] ? ptr_s[rr] : 0;
+                end[u] = rowok[u] ? ptr_s[rr + 1] : 0;
+                sum[u] = 0;
+            }
+            // first L entries of each of the RU rows: all loads first, then the gathers
+#pragma unroll
+            for (int u = 0; u < RU; ++u) {
+                const int e = beg[u] + lane;
+                p[u] = e < end[u];
+                c[u] = p[u] ? col_s[e - co] : 0;
+                v[u] = p[u] ? val_s[e - vo] : (TV)0;
+            }
+#pragma unroll
+            for (int u = 0; u < RU; ++u) xv[u] = p[u] ? gather<HALO>(a, x, c[u]) : (TX)0;
+#pragma unroll
+            for (int u = 0; u < RU; ++u)
+                if (p[u]) sum[u] = (TS)v[u] * (TS)xv[u];
+            // rows longer than L: the rest, row by row
+#pragma unroll
+            for (int u = 0; u < RU; ++u)
+                for (int e = beg[u] + lane + L; e < end[u]; e += L)
+                    sum[u] = fma((TS)val_s[e - vo], (TS)gather<HALO>(a, x, col_s[e - co]), sum[u]);
+#pragma unroll
+            for (int o = L / 2; o > 0; o >>= 1) {
+#pragma unroll
+                for (int u = 0; u < RU; ++u) sum[u] += __shfl_xor_sync(0xffffffffu, sum[u], o);
+            }
+#pragma unroll
+            for (int u = 0; u < RU; ++u)
+                if (rowok[u] && lane == 0) store_row<MODE>(a, d.r0 + base + u * G + g, sum[u]);
+        }
+    } else
     for (int base = 0; base < nr; base += G) {
         const int  rr    = base + g;
         const bool valid = rr < nr;

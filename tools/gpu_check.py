@@ -233,7 +233,7 @@ def cmd_levels(n):
         gb = algorithmic_bytes(nr, nc, nnz, "spmv") / 1e9
         best = None
         cfgs = ((2048, 4, 2), (2048, 5, 2), (4096, 2, 2), (1536, 5, 2))
-        lane_set = (1, 2, 4, 8, 16)
+        lane_set = (1, 2, 4, 8, 16, 32)
         if os.environ.get("B200_SWEEP"):          # e.g. "1024:4:2,1024:2:2;2,4"
             c, l = os.environ["B200_SWEEP"].split(";")
             cfgs = tuple(tuple(int(v) for v in t.split(":")) for t in c.split(","))
