@@ -92,7 +92,6 @@ def lib():
         "b200_csr_nonzeros": [_vp, _P(_c.c_size_t)],
         "b200_csr_bytes": [_vp, _P(_c.c_size_t)],
         "b200_csr_plan": [_vp, _P(_c.c_int), _P(_i64), _P(_i64)],
-        "b200_csr_dict": [_vp, _P(_c.c_int), _P(_dbl)],
         "b200_spmv": [_vp, _dbl, _vp, _vp, _dbl, _vp],
         "b200_residual": [_vp, _vp, _vp, _vp, _vp],
         "b200_clear": [_vp, _vp],
@@ -368,10 +367,7 @@ class Csr:
         nb = _i64()
         nl = _i64()
         _check(lib().b200_csr_plan(self.h, _c.byref(lanes), _c.byref(nb), _c.byref(nl)))
-        en, reuse = _c.c_int(), _dbl()
-        _check(lib().b200_csr_dict(self.h, _c.byref(en), _c.byref(reuse)))
-        return {"lanes": lanes.value, "blocks": nb.value, "long_blocks": nl.value,
-                "dict": bool(en.value), "reuse": round(reuse.value, 2)}
+        return {"lanes": lanes.value, "blocks": nb.value, "long_blocks": nl.value}
 
     def bytes(self):
         b = _c.c_size_t()

@@ -460,7 +460,6 @@ static int64_t *option_slot(b200_ctx_t ctx, const char *key) {
     if (!strcmp(key, "ctas_per_sm")) return &ctx->opt_ctas_per_sm;
     if (!strcmp(key, "stages")) return &ctx->opt_stages;
     if (!strcmp(key, "p2p")) return &ctx->opt_p2p;
-    if (!strcmp(key, "dict")) return &ctx->opt_dict;
     return nullptr;
 }
 
@@ -757,59 +756,6 @@ static void build_plan(int64_t nrows, const Ptr *ptr, int lanes_opt, int nnz_cap
     plan.blk.push_back(make_int2((int)nrows, (int)nnz));
 }
 
-// Column dictionary (pure host): per row block the sorted distinct columns and, per
-// non-zero, the 16-bit position of its column in that list.  Blocks with more than `ucap`
-// distinct columns are split at quad-aligned midpoints.  Returns false (leave the matrix on
-// the plain kernels) if a single quad still exceeds the cap or if rows share too few columns
-// for the dictionary to pay off.
-struct ColumnDict {
-    std::vector<int2> blk;
-    std::vector<unsigned short> lcol;
-    std::vector<int> ucol, ublk;
-    double reuse = 0.0;
-};
-
-static bool build_dict(int64_t nrows, const int32_t *ptr, const int32_t *col, const std::vector<int2> &blk0,
-                       int ucap, ColumnDict &out) {
-    const int64_t nnz = ptr[nrows];
-    out.blk.clear(); out.ucol.clear(); out.ublk.clear();
-    out.lcol.assign((size_t)nnz, 0);
-    std::vector<std::pair<int, int>> todo;           // row ranges, processed in order
-    std::vector<int> u;
-    int64_t distinct = 0;
-    for (size_t b = 0; b + 1 < blk0.size(); ++b) {
-        todo.clear();
-        todo.push_back({blk0[b].x, blk0[b + 1].x});
-        while (!todo.empty()) {
-            const std::pair<int, int> rg = todo.back();
-            todo.pop_back();
-            const int e0 = ptr[rg.first], e1 = ptr[rg.second];
-            u.assign(col + e0, col + e1);
-            std::sort(u.begin(), u.end());
-            u.erase(std::unique(u.begin(), u.end()), u.end());
-            if ((int)u.size() > ucap) {
-                const int rows = rg.second - rg.first;
-                if (rows <= 4) return false;
-                const int mid = rg.first + (((rows / 2) + 3) & ~3);
-                todo.push_back({mid, rg.second});    // second half later
-                todo.push_back({rg.first, mid});     // first half next (keeps row order)
-                continue;
-            }
-            out.blk.push_back(make_int2(rg.first, e0));
-            out.ublk.push_back((int)out.ucol.size());
-            for (int e = e0; e < e1; ++e)
-                out.lcol[(size_t)e] = (unsigned short)(std::lower_bound(u.begin(), u.end(), col[e]) - u.begin());
-            out.ucol.insert(out.ucol.end(), u.begin(), u.end());
-            while (out.ucol.size() & 3) out.ucol.push_back(u.empty() ? 0 : u.back());   // TMA: 16-byte units
-            distinct += (int64_t)u.size();
-        }
-    }
-    out.blk.push_back(make_int2((int)nrows, (int)nnz));
-    out.ublk.push_back((int)out.ucol.size());
-    out.reuse = distinct ? (double)nnz / (double)distinct : 0.0;
-    return out.reuse >= 1.5;
-}
-
 // Upload one CSR matrix exactly as the kernels will see it (indices narrowed to int32,
 // row-block plan built).  Single-GPU matrices come straight through here; the
 // distributed kinds hand in the local part produced by dist.cuh.
@@ -846,24 +792,6 @@ static int csr_upload(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *p
     // ---- row-block plan -------------------------------------------------------
     RowBlockPlan plan;
     build_plan(nrows, hptr.data(), (int)ctx->opt_lanes, (int)ctx->opt_nnz_cap, plan);
-    // operators whose rows share columns (coarse stencils, restrictions): column dictionary
-    ColumnDict cd;
-    bool use_dict = false;
-    const double avg_row = nrows ? (double)nnz / (double)nrows : 0.0;
-    if (ctx->opt_dict && avg_row > 12.0 && nnz > 0 && ncols > 0) {
-        RowBlockPlan dp;
-        const int cap_d = std::min<int>((int)ctx->opt_nnz_cap, 1792) & ~7;
-        // as many row groups as a block has rows: every warp of the CTA has work
-        int ld = 1;
-        while (ld < 32 && (double)kThreads / (ld * 2) >= (double)cap_d / avg_row) ld *= 2;
-        if (ctx->opt_lanes) ld = (int)ctx->opt_lanes;
-        build_plan(nrows, hptr.data(), ld, cap_d, dp);
-        if (dp.nlong == 0 && build_dict(nrows, hptr.data(), hcol.data(), dp.blk, cap_d / 2, cd)) {
-            use_dict = true;
-            plan.lanes = dp.lanes; plan.rows_cap = dp.rows_cap; plan.nnz_cap = cap_d; plan.nlong = 0;
-            plan.blk = cd.blk;
-        }
-    }
     const int lanes = plan.lanes, rows_cap = plan.rows_cap, nnz_cap = plan.nnz_cap;
     const int64_t nlong = plan.nlong;
     std::vector<int2> &blk = plan.blk;
@@ -877,7 +805,6 @@ static int csr_upload(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *p
     A->dtype = std::is_same<Val, float>::value ? B200_F32 : B200_F64;
     A->lanes = lanes; A->rows_cap = rows_cap; A->nnz_cap = nnz_cap;
     A->nblocks = nblocks; A->nlong = nlong;
-    A->h_blk = blk;
     // padding: bulk copies round sizes up to 16 bytes
     const size_t ptr_bytes = ((size_t)nrows + 1 + 8) * sizeof(int);
     const size_t col_bytes = ((size_t)nnz + 8) * sizeof(int);
@@ -888,9 +815,6 @@ static int csr_upload(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *p
         if (A->col) cudaFree(A->col);
         if (A->val) cudaFree(A->val);
         if (A->blk) cudaFree(A->blk);
-        if (A->lcol) cudaFree(A->lcol);
-        if (A->ucol) cudaFree(A->ucol);
-        if (A->ublk) cudaFree(A->ublk);
         delete A;
     };
 #define CSR_CUDA(call)                                                         \
@@ -917,29 +841,9 @@ static int csr_upload(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *p
                                  cudaMemcpyHostToDevice, ctx->stream));
     }
     CSR_CUDA(cudaMemcpyAsync(A->blk, blk.data(), blk_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    size_t dict_bytes = 0;
-    if (use_dict) {
-        const size_t lb = ((size_t)nnz + 16) * sizeof(unsigned short);
-        const size_t ub = (cd.ucol.size() + 8) * sizeof(int);
-        const size_t bb = cd.ublk.size() * sizeof(int);
-        CSR_CUDA(cudaMalloc(&A->lcol, lb));
-        CSR_CUDA(cudaMalloc(&A->ucol, ub));
-        CSR_CUDA(cudaMalloc(&A->ublk, bb));
-        CSR_CUDA(cudaMemsetAsync(A->lcol, 0, lb, ctx->stream));
-        CSR_CUDA(cudaMemsetAsync(A->ucol, 0, ub, ctx->stream));
-        CSR_CUDA(cudaMemcpyAsync(A->lcol, cd.lcol.data(), (size_t)nnz * sizeof(unsigned short),
-                                 cudaMemcpyHostToDevice, ctx->stream));
-        CSR_CUDA(cudaMemcpyAsync(A->ucol, cd.ucol.data(), cd.ucol.size() * sizeof(int),
-                                 cudaMemcpyHostToDevice, ctx->stream));
-        CSR_CUDA(cudaMemcpyAsync(A->ublk, cd.ublk.data(), bb, cudaMemcpyHostToDevice, ctx->stream));
-        A->dict = true;
-        A->ucap = nnz_cap / 2;
-        A->dict_reuse = cd.reuse;
-        dict_bytes = lb + ub + bb;
-    }
     CSR_CUDA(cudaStreamSynchronize(ctx->stream));   // host staging buffers die here
 #undef CSR_CUDA
-    A->bytes = ptr_bytes + col_bytes + val_bytes + blk_bytes + dict_bytes;
+    A->bytes = ptr_bytes + col_bytes + val_bytes + blk_bytes;
     *out = A;
     return B200_OK;
 }
@@ -950,9 +854,6 @@ static void csr_free(b200_csr_t A) {
     if (A->col) cudaFree(A->col);
     if (A->val) cudaFree(A->val);
     if (A->blk) cudaFree(A->blk);
-    if (A->lcol) cudaFree(A->lcol);
-    if (A->ucol) cudaFree(A->ucol);
-    if (A->ublk) cudaFree(A->ublk);
     if (A->send_idx) cudaFree(A->send_idx);
     if (A->blk_halo) cudaFree(A->blk_halo);
     if (A->halo_owned) cudaFree(A->halo_owned);
@@ -1039,12 +940,18 @@ static int csr_create(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *p
             DCSR_CUDA(cudaMemcpyAsync(A->send_idx, idx.data(), idx.size() * sizeof(int),
                                       cudaMemcpyHostToDevice, ctx->stream));
         A->bytes += idx.size() * sizeof(int) + (size_t)(P * sp.S) * sizeof(double);
-        // which row blocks touch the halo
+        // which row blocks touch the halo (the same plan csr_upload just built)
+        RowBlockPlan plan;
+        build_plan(sp.nrows, sp.ptr.data(), A->lanes, A->nnz_cap, plan);
         std::vector<unsigned char> bh((size_t)std::max<int64_t>(1, A->nblocks), 0);
-        for (int64_t b = 0; b < A->nblocks; ++b) {
-            const int64_t e0 = A->h_blk[(size_t)b].y, e1 = A->h_blk[(size_t)b + 1].y;
-            for (int64_t e = e0; e < e1 && !bh[(size_t)b]; ++e)
-                if (sp.col[(size_t)e] >= sp.n_loc) bh[(size_t)b] = 1;
+        if ((int64_t)plan.blk.size() - 1 == A->nblocks) {
+            for (int64_t b = 0; b < A->nblocks; ++b) {
+                const int64_t e0 = plan.blk[(size_t)b].y, e1 = plan.blk[(size_t)b + 1].y;
+                for (int64_t e = e0; e < e1 && !bh[(size_t)b]; ++e)
+                    if (sp.col[(size_t)e] >= sp.n_loc) bh[(size_t)b] = 1;
+            }
+        } else {
+            std::fill(bh.begin(), bh.end(), 1);      // cannot happen; be safe: every block waits
         }
         DCSR_CUDA(cudaMalloc(&A->blk_halo, bh.size()));
         DCSR_CUDA(cudaMemcpyAsync(A->blk_halo, bh.data(), bh.size(), cudaMemcpyHostToDevice, ctx->stream));
@@ -1142,7 +1049,7 @@ template <int MODE, int L, bool HALO, class P>
 static int launch_csr_LH(b200_ctx_t ctx, b200_csr_t A, const CsrArgsT<P> &args) {
     constexpr bool fp64 = std::is_same<P, PrecDD>::value;
     const StageLayout lay = stage_layout(A->rows_cap, A->nnz_cap, (int)sizeof(typename P::TV));
-    if (fp64 && ctx->opt_spmv_variant == 0 && !A->dict) {
+    if (fp64 && ctx->opt_spmv_variant == 0) {
         const int smem = kHeaderBytes + lay.bytes;
         static bool attr_set[64] = {};   // per instantiation and device
         if (!attr_set[ctx->device & 63]) {
@@ -1153,23 +1060,6 @@ static int launch_csr_LH(b200_ctx_t ctx, b200_csr_t A, const CsrArgsT<P> &args) 
         // (only reachable with P == PrecDD)
         csr_block_kernel<MODE, L, HALO, PrecDD><<<(unsigned)A->nblocks, kThreads, smem, ctx->stream>>>(
             *reinterpret_cast<const CsrArgsT<PrecDD> *>(&args));
-    } else if (A->dict) {
-        const DictLayout dl = dict_layout(A->rows_cap, A->nnz_cap, A->ucap, (int)sizeof(typename P::TV));
-        const int xs_bytes = ((A->ucap + 4) * (int)sizeof(typename P::TX) + 15) & ~15;
-        int stages = (int)std::min<int64_t>(ctx->opt_stages, 4);
-        const int max_smem = 227 * 1024;
-        const int per_cta_budget = max_smem / (int)ctx->opt_ctas_per_sm - 1024;
-        while (stages > 1 && kHeaderBytes + stages * dl.bytes + xs_bytes > per_cta_budget) --stages;
-        const int smem = kHeaderBytes + stages * dl.bytes + xs_bytes;
-        static bool attr_set[64] = {};
-        if (!attr_set[ctx->device & 63]) {
-            B200_CUDA(cudaFuncSetAttribute(csr_dict_kernel<MODE, L, HALO, P>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-            attr_set[ctx->device & 63] = true;
-        }
-        const int64_t cap = (int64_t)ctx->sm_count * ctx->opt_ctas_per_sm;
-        const unsigned grid = (unsigned)std::min<int64_t>(A->nblocks, cap);
-        csr_dict_kernel<MODE, L, HALO, P><<<grid, kThreads, smem, ctx->stream>>>(args, stages);
     } else {
         int stages = (int)ctx->opt_stages;
         const int max_smem = 227 * 1024;
@@ -1219,7 +1109,6 @@ static CsrArgsT<P> base_args_t(b200_csr_t A) {
     a.ptr = A->ptr; a.col = A->col; a.val = static_cast<const typename P::TV *>(A->val); a.blk = A->blk;
     a.nrows = (int)A->nrows; a.nblocks = (int)A->nblocks;
     a.rows_cap = A->rows_cap; a.nnz_cap = A->nnz_cap;
-    a.lcol = A->lcol; a.ucol = A->ucol; a.ublk = A->ublk; a.ucap = A->ucap;
     return a;
 }
 static CsrArgs base_args(b200_csr_t A) { return base_args_t<PrecDD>(A); }
@@ -1574,13 +1463,6 @@ extern "C" int b200_csr_bytes(b200_csr_t A, size_t *bytes) {
     *bytes = A->bytes;
     return B200_OK;
 }
-extern "C" int b200_csr_dict(b200_csr_t A, int *enabled, double *reuse) {
-    B200_REQUIRE(A, "null argument");
-    if (enabled) *enabled = A->dict ? 1 : 0;
-    if (reuse) *reuse = A->dict_reuse;
-    return B200_OK;
-}
-
 extern "C" int b200_csr_plan(b200_csr_t A, int *lanes_per_row, int64_t *n_blocks,
                              int64_t *n_long_blocks) {
     B200_REQUIRE(A, "null argument");

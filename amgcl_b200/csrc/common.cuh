@@ -99,7 +99,6 @@ struct b200_ctx_s {
     int64_t opt_ctas_per_sm   = 4;        // persistent variant: CTAs per SM
     int64_t opt_stages        = 2;        // persistent variant: ring depth
     int64_t opt_p2p           = 1;        // multi-GPU: exchange through mapped peer memory
-    int64_t opt_dict          = 1;        // column dictionary for operators with >12 nnz/row
 };
 
 enum { B200_VK_LOCAL = 0, B200_VK_DIST = 1, B200_VK_GHOST = 2 };
@@ -161,14 +160,6 @@ struct b200_csr_s {
     int64_t    nblocks  = 0;
     int64_t    nlong    = 0;      // blocks too long to stage (handled by the strided path)
     int2      *blk      = nullptr;// [nblocks+1] device: {first row, first nnz} per block
-    std::vector<int2> h_blk;      // host copy of blk
-    // column dictionary (csr_dict_kernel): enabled when rows of a block share columns
-    bool            dict  = false;
-    unsigned short *lcol  = nullptr;  // [nnz] position of the column in the block's distinct list
-    int            *ucol  = nullptr;  // distinct columns per block, padded to multiples of 4
-    int            *ublk  = nullptr;  // [nblocks+1] offsets into ucol
-    int             ucap  = 0;
-    double          dict_reuse = 0.0; // non-zeros per distinct column (average over blocks)
     size_t     bytes    = 0;
 };
 

@@ -82,12 +82,6 @@ struct CsrArgsT {
     const typename P::TD *d;      // diagonal     (RELAX)
     double        alpha;  // SPMV: alpha; RELAX: omega
     double        beta;   // SPMV_ACC
-    // column dictionary (csr_dict_kernel): per row block the sorted list of distinct
-    // columns it references and 16-bit positions into that list instead of 32-bit columns
-    const unsigned short *lcol;   // [nnz]       position of the entry's column in its block's list
-    const int            *ucol;   // distinct global columns, block after block (each padded to 4)
-    const int            *ublk;   // [nblocks+1] offsets into ucol
-    int                   ucap;   // most distinct columns a block may have
 };
 typedef CsrArgsT<PrecDD> CsrArgs;
 
@@ -205,30 +199,10 @@ __device__ __forceinline__ void wait_for_halo(const CsrArgsT<P> &a, int b) {
     __syncthreads();
 }
 
-// ---- where an entry's x value comes from ------------------------------------------
-// plain CSR: 32-bit column from the stage, value gathered from global memory (L1/L2);
-// dictionary: 16-bit position from the stage, value from the block's x window in shared
-// memory (filled once per block from the distinct-column list).
-template <bool DICT, bool HALO, class P>
-struct XSource {
-    typedef typename P::TX TX;
-    const CsrArgsT<P> &a;
-    const int *col_s; int co;
-    const unsigned short *lcol_s; int lo;
-    const TX *x_s;
-    __device__ __forceinline__ int index(int e) const {
-        return DICT ? (int)lcol_s[e - lo] : col_s[e - co];
-    }
-    __device__ __forceinline__ TX load(int c) const {
-        return DICT ? x_s[c] : gather<HALO>(a, a.x, c);
-    }
-};
-
 // ---- reduce the rows of a staged block out of shared memory ---------------------
-template <int MODE, int L, bool HALO, bool DICT, class P>
+template <int MODE, int L, bool HALO, class P>
 __device__ __forceinline__ void compute_staged(const CsrArgsT<P> &a, const BlockDesc &d,
-                                               const char *stage, const StageLayout &lay,
-                                               const typename P::TX *x_s) {
+                                               const char *stage, const StageLayout &lay) {
     typedef typename P::TV TV;
     typedef typename P::TX TX;
     typedef typename P::TY TS;                       // row sums live in the output's type
@@ -238,13 +212,11 @@ __device__ __forceinline__ void compute_staged(const CsrArgsT<P> &a, const Block
     const int    *ptr_s = reinterpret_cast<const int *>(stage + lay.ptr_off);
     const int vo = d.e0 & ~(VA - 1);
     const int co = d.e0 & ~3;
-    const XSource<DICT, HALO, P> xs = {a, col_s, co,
-                                       reinterpret_cast<const unsigned short *>(stage + lay.col_off),
-                                       d.e0 & ~7, x_s};
     constexpr int G = kThreads / L;
     const int g    = threadIdx.x / L;
     const int lane = threadIdx.x % L;
     const int nr   = d.r1 - d.r0;
+    const TX *__restrict__ x = a.x;
 
     if (L >= 16) {
         // Wide groups (a half or a full warp per row): consecutive lanes read consecutive
@@ -271,11 +243,11 @@ __device__ __forceinline__ void compute_staged(const CsrArgsT<P> &a, const Block
             for (int u = 0; u < RU; ++u) {
                 const int e = beg[u] + lane;
                 p[u] = e < end[u];
-                c[u] = p[u] ? xs.index(e) : 0;
+                c[u] = p[u] ? col_s[e - co] : 0;
                 v[u] = p[u] ? val_s[e - vo] : (TV)0;
             }
 #pragma unroll
-            for (int u = 0; u < RU; ++u) xv[u] = p[u] ? xs.load(c[u]) : (TX)0;
+            for (int u = 0; u < RU; ++u) xv[u] = p[u] ? gather<HALO>(a, x, c[u]) : (TX)0;
 #pragma unroll
             for (int u = 0; u < RU; ++u)
                 if (p[u]) sum[u] = (TS)v[u] * (TS)xv[u];
@@ -283,7 +255,7 @@ __device__ __forceinline__ void compute_staged(const CsrArgsT<P> &a, const Block
 #pragma unroll
             for (int u = 0; u < RU; ++u)
                 for (int e = beg[u] + lane + L; e < end[u]; e += L)
-                    sum[u] = fma((TS)val_s[e - vo], (TS)xs.load(xs.index(e)), sum[u]);
+                    sum[u] = fma((TS)val_s[e - vo], (TS)gather<HALO>(a, x, col_s[e - co]), sum[u]);
 #pragma unroll
             for (int o = L / 2; o > 0; o >>= 1) {
 #pragma unroll
@@ -312,11 +284,11 @@ __device__ __forceinline__ void compute_staged(const CsrArgsT<P> &a, const Block
                 for (int u = 0; u < U; ++u) {
                     const int eu = e + u * L;
                     p[u] = eu < end;
-                    c[u] = p[u] ? xs.index(eu) : xs.index(e);
+                    c[u] = p[u] ? col_s[eu - co] : col_s[e - co];
                     v[u] = p[u] ? val_s[eu - vo] : (TV)0;
                 }
 #pragma unroll
-                for (int u = 0; u < U; ++u) xv[u] = xs.load(c[u]);
+                for (int u = 0; u < U; ++u) xv[u] = gather<HALO>(a, x, c[u]);
 #pragma unroll
                 for (int u = 0; u < U; ++u)
                     if (p[u]) sum = fma((TS)v[u], (TS)xv[u], sum);
@@ -378,7 +350,7 @@ __global__ void __launch_bounds__(kThreads, 4) csr_block_kernel(const CsrArgsT<P
         __syncthreads();
         ptx::mbar_wait(bar, 0);
         wait_for_halo<HALO>(a, b);
-        compute_staged<MODE, L, HALO, false>(a, d, stage, lay, nullptr);
+        compute_staged<MODE, L, HALO>(a, d, stage, lay);
     } else {
         wait_for_halo<HALO>(a, b);
         compute_long<MODE, HALO>(a, d, red_s);
@@ -419,7 +391,7 @@ __global__ void __launch_bounds__(kThreads, 2) csr_ring_kernel(const CsrArgsT<P>
         const BlockDesc d = descs[s];
         wait_for_halo<HALO>(a, first + i * step);
         if ((d.e1 - d.e0) <= a.nnz_cap)
-            compute_staged<MODE, L, HALO, false>(a, d, stages + (size_t)s * lay.bytes, lay, nullptr);
+            compute_staged<MODE, L, HALO>(a, d, stages + (size_t)s * lay.bytes, lay);
         else
             compute_long<MODE, HALO>(a, d, red_s);
         __syncthreads();                 // every thread is done with stage s (and descs[s])
@@ -427,124 +399,6 @@ __global__ void __launch_bounds__(kThreads, 2) csr_ring_kernel(const CsrArgsT<P>
             const BlockDesc n = load_desc(a, first + (i + nstages) * step);
             descs[s] = n;
             issue_block(a, n, stages + (size_t)s * lay.bytes, lay, bars + s, policy);
-        }
-        if (++s == nstages) { s = 0; parity ^= 1; }
-    }
-}
-
-// ---- variant 2: persistent ring with a per-block column dictionary -------------------------
-// For operators whose rows gather scattered columns (coarse-level stencils, restrictions) the
-// 32-byte sectors fetched for 8-byte x values, not the matrix stream, saturate the L2->SM path
-// (DESIGN.md section 8).  Here a block's distinct columns are fetched ONCE, in sorted order,
-// into shared memory, and the rows then read x from there through 16-bit positions: the
-// index stream shrinks from 4 to 2 bytes per non-zero and every x sector is fetched once per
-// block instead of once per referencing row.
-struct DictLayout {
-    int val_off, col_off, ptr_off, ucol_off, bytes;     // col_off holds the 16-bit positions
-};
-__host__ __device__ inline DictLayout dict_layout(int rows_cap, int nnz_cap, int ucap, int val_size) {
-    DictLayout s;
-    s.val_off = 0;
-    int b = nnz_cap * val_size + 16;
-    b = (b + 15) & ~15;
-    s.col_off = b;
-    b = (nnz_cap + 16) * 2;                          // +7 align down, +7 round up
-    b = (b + 15) & ~15;
-    s.ptr_off = s.col_off + b;
-    b = (rows_cap + 4) * 4;
-    b = (b + 15) & ~15;
-    s.ucol_off = s.ptr_off + b;
-    b = (ucap + 4) * 4;
-    b = (b + 15) & ~15;
-    s.bytes = s.ucol_off + b;
-    return s;
-}
-
-struct DictDesc {
-    int r0, r1, e0, e1, u0, u1;
-};
-
-template <class P>
-__device__ __forceinline__ DictDesc load_dict_desc(const CsrArgsT<P> &a, int b) {
-    const int2 lo = __ldg(a.blk + b);
-    const int2 hi = __ldg(a.blk + b + 1);
-    DictDesc d;
-    d.r0 = lo.x; d.e0 = lo.y;
-    d.r1 = hi.x; d.e1 = hi.y;
-    d.u0 = __ldg(a.ublk + b);
-    d.u1 = __ldg(a.ublk + b + 1);
-    return d;
-}
-
-template <class P>
-__device__ __forceinline__ void issue_dict_block(const CsrArgsT<P> &a, const DictDesc &d, char *stage,
-                                                 const DictLayout &lay, uint64_t *bar, uint64_t policy) {
-    typedef typename P::TV TV;
-    constexpr int VA = 16 / (int)sizeof(TV);
-    const int a0 = d.e0 & ~(VA - 1);
-    const int nval = ((d.e1 - a0) + VA - 1) & ~(VA - 1);
-    const int c0 = d.e0 & ~7;                       // 16-bit positions: 8 per 16 bytes
-    const int ncol = ((d.e1 - c0) + 7) & ~7;
-    const int nptr = ((d.r1 - d.r0 + 1) + 3) & ~3;
-    const int nu = d.u1 - d.u0;                     // already a multiple of 4
-    const uint32_t bytes = nval * (int)sizeof(TV) + ncol * 2 + nptr * 4 + nu * 4;
-    ptx::mbar_expect_tx(bar, bytes);
-    if (nval) ptx::bulk_g2s(stage + lay.val_off, a.val + a0, nval * (int)sizeof(TV), bar, policy);
-    if (ncol) ptx::bulk_g2s(stage + lay.col_off, a.lcol + c0, ncol * 2, bar, policy);
-    ptx::bulk_g2s(stage + lay.ptr_off, a.ptr + d.r0, nptr * 4, bar, policy);
-    if (nu) ptx::bulk_g2s(stage + lay.ucol_off, a.ucol + d.u0, nu * 4, bar, policy);
-}
-
-template <int MODE, int L, bool HALO, class P>
-__global__ void __launch_bounds__(kThreads, 2) csr_dict_kernel(const CsrArgsT<P> a, const int nstages) {
-    typedef typename P::TX TX;
-    extern __shared__ __align__(128) char smem[];
-    uint64_t *bars  = reinterpret_cast<uint64_t *>(smem);                 // [<=4]
-    DictDesc *descs = reinterpret_cast<DictDesc *>(smem + 64);            // [<=4] x 24 B
-    const DictLayout lay = dict_layout(a.rows_cap, a.nnz_cap, a.ucap, (int)sizeof(typename P::TV));
-    char *stages = smem + kHeaderBytes;
-    TX   *x_s    = reinterpret_cast<TX *>(stages + (size_t)nstages * lay.bytes);   // [ucap]
-
-    const int first = blockIdx.x;
-    const int step  = gridDim.x;
-    const int mine  = (a.nblocks - first + step - 1) / step;
-    uint64_t policy = 0;
-
-    if (threadIdx.x == 0) {
-        policy = ptx::policy_evict_first();
-        for (int s = 0; s < nstages; ++s) ptx::mbar_init(bars + s, 1);
-        ptx::fence_mbar_init();
-        const int pre = mine < nstages ? mine : nstages;
-        for (int i = 0; i < pre; ++i) {
-            const DictDesc d = load_dict_desc(a, first + i * step);
-            descs[i] = d;
-            issue_dict_block(a, d, stages + (size_t)i * lay.bytes, lay, bars + i, policy);
-        }
-    }
-    __syncthreads();
-
-    int s = 0, parity = 0;
-    for (int i = 0; i < mine; ++i) {
-        ptx::mbar_wait(bars + s, parity);
-        const DictDesc d = descs[s];
-        char *stage = stages + (size_t)s * lay.bytes;
-        wait_for_halo<HALO>(a, first + i * step);
-        // phase 1: the block's x window, one coalesced pass over its sorted distinct columns
-        const int *ucol_s = reinterpret_cast<const int *>(stage + lay.ucol_off);
-        const int nu = d.u1 - d.u0;
-        for (int k = threadIdx.x; k < nu; k += kThreads) x_s[k] = gather<HALO>(a, a.x, ucol_s[k]);
-        __syncthreads();
-        // phase 2: rows out of shared memory
-        StageLayout sl;
-        sl.val_off = lay.val_off; sl.col_off = lay.col_off; sl.ptr_off = lay.ptr_off; sl.bytes = lay.bytes;
-        BlockDesc bd;
-        bd.r0 = d.r0; bd.r1 = d.r1; bd.e0 = d.e0; bd.e1 = d.e1;
-        compute_staged<MODE, L, HALO, true>(a, bd, stage, sl, x_s);
-        __syncthreads();                 // stage s and x_s are free again
-        if (threadIdx.x == 0 && i + nstages < mine) {
-            const DictDesc n = load_dict_desc(a, first + (i + nstages) * step);
-            descs[s] = n;
-            issue_dict_block(a, n, stage, lay, bars + s, policy);
         }
         if (++s == nstages) { s = 0; parity ^= 1; }
     }

@@ -154,7 +154,6 @@ int b200_split_destroy(b200_split_t sp);
  *                      matrices created afterwards)
  *   "lanes"            lanes per row, 0 = from the average row length (default)
  *   "p2p"              multi-GPU: 1 = peer-memory exchange kernels (default), 0 = NCCL
- *   "dict"             1 = column dictionary for operators with > 12 nnz/row (default)
  *   "fuse_relax"       1 = single-pass fused smoother sweep (default), 0 = two kernels
  *   "zero_shortcut"    1 = skip the A-pass when x is known to be zero (default)
  * Unknown keys return B200_EINVAL. */
@@ -212,14 +211,6 @@ int b200_csr_nonzeros(b200_csr_t A, size_t *n);
 int b200_csr_bytes(b200_csr_t A, size_t *bytes);
 /* Plan introspection for tests / DESIGN.md: lanes per row and row-block count. */
 int b200_csr_plan(b200_csr_t A, int *lanes_per_row, int64_t *n_blocks, int64_t *n_long_blocks);
-
-/* Column dictionary: for operators with more than 12 non-zeros per row whose rows share
- * columns (coarse-level stencils, restrictions) the upload also stores, per row block, the
- * sorted distinct columns and 16-bit positions into that list; the kernels then fetch every
- * x value once per block into shared memory (csr_dict_kernel).  enabled = 0 if the matrix
- * stayed on the plain kernels; reuse = non-zeros per distinct column.  Option "dict" = 0
- * (before the matrix is created) disables it. */
-int b200_csr_dict(b200_csr_t A, int *enabled, double *reuse);
 
 /* Pure host helper (no device needed): the row-block plan b200_csr_create_*
  * would build for a matrix with these row pointers.  blk_out (may be NULL)

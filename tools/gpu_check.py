@@ -244,12 +244,11 @@ def cmd_levels(n):
                 ctx.set_option("nnz_cap", nnz_cap)
                 ctx.set_option("ctas_per_sm", cps)
                 ctx.set_option("stages", stages)
-                ctx.set_option("dict", int(os.environ.get("B200_DICT", "1")))
                 A = ctx.csr(nr, nc, p_, c_, v_)
                 vx, vy = ctx.vector(x), ctx.vector(nr)
                 med, mn = time_op(lambda: ctx.spmv(1.0, A, vx, 0.0, vy), reps=10)
                 rec = {"op": name, "rows": nr, "cols": nc, "nnz": nnz, "avg": round(nnz / nr, 1),
-                       "plan": A.plan(), "lanes": lanes, "nnz_cap": nnz_cap, "cps": cps, "stages": stages,
+                       "lanes": lanes, "nnz_cap": nnz_cap, "cps": cps, "stages": stages,
                        "ms": round(med, 4), "GBs": round(gb / (med * 1e-3), 1)}
                 print(json.dumps(rec), flush=True)
                 if best is None or rec["GBs"] > best["GBs"]:
