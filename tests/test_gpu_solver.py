@@ -205,7 +205,12 @@ def test_unstructured_matrix_vs_live_reference(ctx, relax, krylov):
     xg, itg, resg = S.solve(rhs)
     assert R.nlevels >= 3
     assert itg == itr
-    assert abs(resg - resr) <= 1e-5 * resr
+    # CG's residual norm is a smooth function of the rounding; BiCGStab's final value is not
+    # (the reference itself moves in the 2nd-3rd digit with the OpenMP thread count on these
+    # irregular matrices), so for it the solution and the true residual carry the check
+    assert abs(resg - resr) <= (1e-5 if krylov == "cg" else 5e-2) * resr
     assert rel_err(xg, xr) < TOL_SOLUTION
+    r = rhs - oracle.c().spmv(1.0, (ptr, col, val), xg, 0.0, np.zeros_like(xg))
+    assert np.linalg.norm(r) / np.linalg.norm(rhs) < 2e-8
     S.close()
     R.close()
