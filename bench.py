@@ -48,7 +48,7 @@ def parse_args():
     ap.add_argument("--partition-min-rows", type=int, default=1000000)
     ap.add_argument("--p2p", type=int, default=1, choices=[0, 1],
                     help="N>1: 1 = peer-memory exchange kernels over NVLink, 0 = NCCL collectives")
-    ap.add_argument("--ref-sample-iters", type=int, default=4,
+    ap.add_argument("--ref-sample-iters", type=int, default=8,
                     help="Krylov iterations per step of the CPU reference sample")
     return ap.parse_args()
 
