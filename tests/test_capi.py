@@ -154,3 +154,30 @@ def test_poisson_generator_matches_reference_counts():
     ptr, col, val, _ = ab.poisson3d(6)
     A = sp.csr_matrix((val, col, ptr))
     assert abs(A - A.T).max() == 0
+
+
+def test_product_code_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing that ships (package, headers, native sources)
+    may import, include, link or execute it, and there is no CPU fallback to route through."""
+    offenders = []
+    for base in ("amgcl_b200", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, base)):
+            for f in files:
+                if not f.endswith((".py", ".cpp", ".cu", ".cuh", ".h", ".hpp")):
+                    continue
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                for lineno, line in enumerate(text.splitlines(), 1):
+                    code = line.split("//")[0].split("#")[0] if not f.endswith(".py") else line.split("#")[0]
+                    if re.search(r"\boracle\b|liboracle|libamgcl_ref|_ref/", code):
+                        offenders.append("%s:%d: %s" % (os.path.join(dirpath, f), lineno, line.strip()))
+    assert not offenders, "\n".join(offenders)
+
+
+def test_every_header_entry_point_cites_the_reference():
+    """include/amgcl_b200.h: the primitives name the reference interface they replace."""
+    text = open(os.path.join(ROOT, "include", "amgcl_b200.h")).read()
+    for needle in ("interface.hpp:312-323", "interface.hpp:329-335", "interface.hpp:356-371",
+                   "interface.hpp:377-382", "interface.hpp:388-393", "interface.hpp:399-405",
+                   "damped_jacobi.hpp:103-132", "spai0.hpp:86-109", "cuda.hpp:61-84",
+                   "mpi/distributed_matrix.hpp:51-557"):
+        assert needle in text, needle
