@@ -182,6 +182,7 @@ extern "C" int b200_ctx_create(int device, b200_ctx_t *out) {
     b200_ctx_s *ctx = new (std::nothrow) b200_ctx_s();
     if (!ctx) return fail(B200_ENOMEM, "out of host memory");
     ctx->device = device;
+    if (const char *e = getenv("B200_PDL")) ctx->opt_pdl = atoi(e) ? 1 : 0;
     cudaDeviceProp prop;
     B200_CUDA(cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
@@ -460,6 +461,7 @@ static int64_t *option_slot(b200_ctx_t ctx, const char *key) {
     if (!strcmp(key, "ctas_per_sm")) return &ctx->opt_ctas_per_sm;
     if (!strcmp(key, "stages")) return &ctx->opt_stages;
     if (!strcmp(key, "p2p")) return &ctx->opt_p2p;
+    if (!strcmp(key, "pdl")) return &ctx->opt_pdl;
     return nullptr;
 }
 
@@ -1041,6 +1043,25 @@ static int csr_create(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *p
     return B200_OK;
 }
 
+// Launch with programmatic stream serialization (PDL) when enabled: the kernel may be
+// scheduled while its predecessor drains and orders itself with griddepcontrol.wait.
+template <class... KArgs, class... Args>
+static cudaError_t launch_pdl(b200_ctx_t ctx, void (*kernel)(KArgs...), dim3 grid, dim3 block,
+                              size_t smem, Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = ctx->opt_pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 // ---- launch one streaming pass over A ------------------------------------------------
 // P = precision combination (csr_kernels.cuh).  Only FP64 carries the multi-GPU halo path
 // and the one-block-per-CTA cross-check variant; the mixed-precision combinations use the
@@ -1074,7 +1095,8 @@ static int launch_csr_LH(b200_ctx_t ctx, b200_csr_t A, const CsrArgsT<P> &args) 
         }
         const int64_t cap = (int64_t)ctx->sm_count * ctx->opt_ctas_per_sm;
         const unsigned grid = (unsigned)std::min<int64_t>(A->nblocks, cap);
-        csr_ring_kernel<MODE, L, HALO, P><<<grid, kThreads, smem, ctx->stream>>>(args, stages);
+        B200_CUDA(launch_pdl(ctx, csr_ring_kernel<MODE, L, HALO, P>, dim3(grid), dim3(kThreads), (size_t)smem,
+                             args, stages));
     }
     B200_CHECK_LAUNCH();
     ctx->launches++;
@@ -1122,7 +1144,8 @@ static int launch_ew(b200_ctx_t ctx, size_t n, F f, const T *x, const T *y, cons
                         (!RZ || aligned16(z));
     const int grid = grid_for(ctx, n, 16 / (int)sizeof(T) * 2);
     ProfScope prof(ctx, B200_PROF_VECTOR + (RY ? 1 : 0) + (RZ ? 1 : 0), (int64_t)n, 1, 0);
-    ew_kernel_same<F, RY, RZ, T><<<grid, kThreads, 0, ctx->stream>>>(n, f, x, y, z, out, vec_ok);
+    B200_CUDA(launch_pdl(ctx, ew_kernel_same<F, RY, RZ, T>, dim3(grid), dim3(kThreads), 0, n, f, x, y, z, out,
+                         vec_ok));
     B200_CHECK_LAUNCH();
     ctx->launches++;
     return B200_OK;
@@ -1134,7 +1157,8 @@ static int launch_ew_mixed(b200_ctx_t ctx, size_t n, F f, const TX *x, const TY 
     if (n == 0) return B200_OK;
     const int grid = grid_for(ctx, n, 2);
     ProfScope prof(ctx, B200_PROF_VECTOR + (RY ? 1 : 0) + (RZ ? 1 : 0), (int64_t)n, 1, 0);
-    ew_kernel<F, RY, RZ, TX, TY, TZ, TO><<<grid, kThreads, 0, ctx->stream>>>(n, f, x, y, z, out, false);
+    B200_CUDA(launch_pdl(ctx, ew_kernel<F, RY, RZ, TX, TY, TZ, TO>, dim3(grid), dim3(kThreads), 0, n, f, x, y,
+                         z, out, false));
     B200_CHECK_LAUNCH();
     ctx->launches++;
     return B200_OK;
@@ -1636,8 +1660,10 @@ static void launch_dot_kernel(b200_ctx_t ctx, b200_vec_t x, b200_vec_t y, double
     const bool vec_ok = aligned16(x->ptr) && aligned16(y->ptr);
     const int grid = std::min(grid_for(ctx, x->len, 32 / (int)sizeof(T) * 2), kDotMaxBlocks);
     ProfScope prof(ctx, B200_PROF_DOT, (int64_t)x->len, 1, 0);
-    dot_kernel<T><<<grid, kThreads, 0, ctx->stream>>>(x->len, tp<T>(x->ptr), tp<T>(y->ptr), ctx->dot_partial,
-                                                      ctx->dot_ticket, result_dev, vec_ok);
+    const cudaError_t rc = launch_pdl(ctx, dot_kernel<T>, dim3(grid), dim3(kThreads), 0, x->len,
+                                      (const T *)tp<T>(x->ptr), (const T *)tp<T>(y->ptr), ctx->dot_partial,
+                                      ctx->dot_ticket, result_dev, vec_ok);
+    if (rc != cudaSuccess) cuda_fail(rc, "dot_kernel launch", __FILE__, __LINE__);
 }
 } // namespace b200
 
@@ -1808,8 +1834,8 @@ static int relax_zero_t(b200_ctx_t ctx, double omega, const double *pd, const do
     if (x->len) {
         const int grid = grid_for(ctx, x->len, 2);
         ProfScope prof(ctx, B200_PROF_RELAX_ZERO, (int64_t)x->len, 1, 0);
-        relax_zero_kernel<TD, TF, TX><<<grid, kThreads, 0, ctx->stream>>>(x->len, omega, tp<TD>(pd), tp<TF>(pf),
-                                                                          tp<TX>(wr(x)));
+        B200_CUDA(launch_pdl(ctx, relax_zero_kernel<TD, TF, TX>, dim3(grid), dim3(kThreads), 0, x->len, omega,
+                             tp<TD>(pd), tp<TF>(pf), tp<TX>(wr(x))));
         B200_CHECK_LAUNCH();
         ctx->launches++;
     }
@@ -2118,11 +2144,12 @@ extern "C" int b200_coarse_solve(b200_ctx_t ctx, b200_coarse_t S, b200_vec_t rhs
     if (rc) return rc;
     ProfScope prof(ctx, B200_PROF_COARSE, S->n, S->n, S->n * S->n);
     if (rhs->dtype == B200_F32)
-        coarse_gemv_kernel<float><<<(N + warps_per_cta - 1) / warps_per_cta, kThreads, 0, ctx->stream>>>(
-            N, 0, N, S->Ainv, tp<float>(pr), tp<float>(wr(x)));
+        B200_CUDA(launch_pdl(ctx, coarse_gemv_kernel<float>, dim3((N + warps_per_cta - 1) / warps_per_cta),
+                             dim3(kThreads), 0, N, 0, N, (const double *)S->Ainv, tp<float>(pr),
+                             tp<float>(wr(x))));
     else
-    coarse_gemv_kernel<double><<<(N + warps_per_cta - 1) / warps_per_cta, kThreads, 0, ctx->stream>>>(
-        N, 0, N, S->Ainv, pr, wr(x));
+        B200_CUDA(launch_pdl(ctx, coarse_gemv_kernel<double>, dim3((N + warps_per_cta - 1) / warps_per_cta),
+                             dim3(kThreads), 0, N, 0, N, (const double *)S->Ainv, pr, wr(x)));
     B200_CHECK_LAUNCH();
     ctx->launches++;
     return B200_OK;

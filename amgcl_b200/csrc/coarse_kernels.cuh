@@ -115,6 +115,7 @@ template <class T>
 __global__ void __launch_bounds__(kThreads)
 coarse_gemv_kernel(int n, int row0, int nloc, const double *__restrict__ Ainv,
                    const T *__restrict__ rhs, T *__restrict__ x) {
+    ptx::pdl_wait();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= nloc) return;

@@ -372,6 +372,8 @@ __global__ void __launch_bounds__(kThreads, 2) csr_ring_kernel(const CsrArgsT<P>
     const int mine  = (a.nblocks - first + step - 1) / step;   // blocks this CTA owns
     uint64_t policy = 0;
 
+    // PDL: the prologue below only reads matrix data (never written by a kernel), so it may
+    // run before the predecessor's writes are visible
     if (threadIdx.x == 0) {
         policy = ptx::policy_evict_first();
         for (int s = 0; s < nstages; ++s) ptx::mbar_init(bars + s, 1);
@@ -384,6 +386,7 @@ __global__ void __launch_bounds__(kThreads, 2) csr_ring_kernel(const CsrArgsT<P>
         }
     }
     __syncthreads();
+    ptx::pdl_wait();         // vectors (x, f, d, y) come from earlier kernels: from here on
 
     int s = 0, parity = 0;
     for (int i = 0; i < mine; ++i) {
@@ -410,6 +413,7 @@ __global__ void __launch_bounds__(kThreads) relax_zero_kernel(size_t n, double o
                                                               const TD *__restrict__ d,
                                                               const TF *__restrict__ f,
                                                               TX *__restrict__ x) {
+    ptx::pdl_wait();
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         // (omega*d)*(f - 0) + 0, written as the reference evaluates it

@@ -77,6 +77,7 @@ __device__ __forceinline__ void ew_vector_path(size_t n, F f, const T *x, const 
 template <class F, bool READ_Y, bool READ_Z, class TX, class TY, class TZ, class TO>
 __global__ void __launch_bounds__(kThreads)
 ew_kernel(size_t n, F f, const TX *x, const TY *y, const TZ *z_in, TO *out, bool vec_ok) {
+    ptx::pdl_wait();
     const size_t tid    = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = tid; i < n; i += stride)
@@ -85,6 +86,7 @@ ew_kernel(size_t n, F f, const TX *x, const TY *y, const TZ *z_in, TO *out, bool
 template <class F, bool READ_Y, bool READ_Z, class T>
 __global__ void __launch_bounds__(kThreads)
 ew_kernel_same(size_t n, F f, const T *x, const T *y, const T *z_in, T *out, bool vec_ok) {
+    ptx::pdl_wait();
     const size_t tid    = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     if (vec_ok) {
@@ -113,6 +115,7 @@ template <class T>
 __global__ void __launch_bounds__(kThreads)
 dot_kernel(size_t n, const T *__restrict__ x, const T *__restrict__ y,
            double *partial, unsigned int *ticket, double *result, bool vec_ok) {
+    ptx::pdl_wait();
     const size_t tid    = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     double s = 0.0, c = 0.0;

@@ -154,6 +154,8 @@ int b200_split_destroy(b200_split_t sp);
  *                      matrices created afterwards)
  *   "lanes"            lanes per row, 0 = from the average row length (default)
  *   "p2p"              multi-GPU: 1 = peer-memory exchange kernels (default), 0 = NCCL
+ *   "pdl"              1 = programmatic dependent launch of the solve kernels (default;
+ *                      environment variable B200_PDL overrides the default), 0 = plain launches
  *   "fuse_relax"       1 = single-pass fused smoother sweep (default), 0 = two kernels
  *   "zero_shortcut"    1 = skip the A-pass when x is known to be zero (default)
  * Unknown keys return B200_EINVAL. */

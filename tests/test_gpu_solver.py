@@ -116,6 +116,27 @@ def test_variants_and_fusion_agree(ctx):
         assert it == it0 and abs(r - r0) <= 1e-9 * r0 and rel_err(x, x0) < 1e-12
 
 
+def test_dependent_launch_is_bit_transparent(ctx):
+    """Programmatic dependent launch only changes when kernels are scheduled: the solve with
+    and without it must be bit-identical (same arithmetic, same order)."""
+    ptr, col, val, rhs = ab.poisson3d(48)
+    out = []
+    try:
+        for pdl in (1, 0, 1):
+            ctx.set_option("pdl", pdl)
+            for relax, krylov in (("damped_jacobi", "cg"), ("spai0", "bicgstab")):
+                S = ab.DropinSolver(ptr, col, val, relax, krylov, ctx=ctx)
+                for _ in range(3):           # repeated solves: back-to-back kernel chains
+                    out.append((pdl, relax, S.solve(rhs)))
+                S.close()
+    finally:
+        ctx.set_option("pdl", 1)
+    base = {r: (x, it, res) for p, r, (x, it, res) in out if p == 0}
+    for p, r, (x, it, res) in out:
+        x0, it0, res0 = base[r]
+        assert it == it0 and res == res0 and np.array_equal(x, x0), (p, r)
+
+
 def test_large_problem_size_independent_properties(ctx):
     """128^3 (2.1M rows): survey iteration count, true residual, linearity of the V-cycle."""
     n = 128
