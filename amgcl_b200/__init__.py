@@ -29,7 +29,7 @@ _dbl = _c.c_double
 _vp = _c.c_void_p
 _P = _c.POINTER
 
-RELAX = {"damped_jacobi": 0, "spai0": 1, "chebyshev": 2}
+RELAX = {"damped_jacobi": 0, "spai0": 1, "chebyshev": 2, "ilu0": 3}
 KRYLOV = {"cg": 0, "bicgstab": 1, "gmres": 2, "bicgstabl": 3}
 
 
@@ -116,6 +116,12 @@ def lib():
         "b200_split_destroy": [_vp],
         "b200_plan_i64": [_i64, _vp, _c.c_int, _c.c_int, _vp, _i64, _P(_i64), _P(_c.c_int),
                           _P(_c.c_int), _P(_i64)],
+        "b200_graph_begin": [_vp, _P(_c.c_int)],
+        "b200_graph_end": [_vp, _P(_vp)],
+        "b200_graph_abort": [_vp],
+        "b200_graph_launch": [_vp, _vp, _P(_c.c_int)],
+        "b200_graph_info": [_vp, _P(_i64), _P(_i64), _P(_i64), _P(_c.c_int)],
+        "b200_graph_destroy": [_vp],
         "b200_profile_begin": [_vp],
         "b200_profile_end": [_vp, _vp, _i64, _P(_i64)],
     }
@@ -143,6 +149,11 @@ def dropin_lib():
     D.dropin_create.restype = _c.c_int
     D.dropin_create_mixed.argtypes = D.dropin_create.argtypes
     D.dropin_create_mixed.restype = _c.c_int
+    D.dropin_create_graph.argtypes = [_vp, _i64, _vp, _vp, _vp, _c.c_int, _c.c_int, _c.c_int, _dbl,
+                                      _c.c_int, _c.c_int, _P(_vp)]
+    D.dropin_create_graph.restype = _c.c_int
+    D.dropin_graph_stats.argtypes = [_vp, _P(_i64), _P(_i64), _P(_i64)]
+    D.dropin_graph_stats.restype = _c.c_int
     D.dropin_destroy.argtypes = [_vp]
     D.dropin_destroy.restype = None
     D.dropin_solve.argtypes = [_vp, _vp, _vp, _P(_i64), _P(_dbl)]
@@ -298,6 +309,21 @@ class Context:
     def vmul(self, alpha, x, y, beta, z):
         _check(lib().b200_vmul(self.h, alpha, x.h, y.h, beta, z.h), "b200_vmul")
 
+    # -- recorded call sequences (b200_graph_*) --
+    def graph_begin(self):
+        """Start recording; False when this context cannot record right now."""
+        rec = _c.c_int(0)
+        _check(lib().b200_graph_begin(self.h, _c.byref(rec)), "b200_graph_begin")
+        return bool(rec.value)
+
+    def graph_end(self):
+        g = _vp()
+        _check(lib().b200_graph_end(self.h, _c.byref(g)), "b200_graph_end")
+        return Graph(self, g)
+
+    def graph_abort(self):
+        _check(lib().b200_graph_abort(self.h), "b200_graph_abort")
+
     def relax(self, A, rhs, x, tmp, diag, omega):
         _check(lib().b200_relax(self.h, A.h, rhs.h, x.h, tmp.h, diag.h, omega), "b200_relax")
 
@@ -405,14 +431,47 @@ class Coarse:
             pass
 
 
+class Graph:
+    """A recorded call sequence (b200_graph_t)."""
+
+    def __init__(self, ctx, h):
+        self.ctx = ctx
+        self.h = h
+
+    def launch(self):
+        """Replay; False (and nothing done) when the vector state differs from recording time."""
+        ok = _c.c_int(0)
+        _check(lib().b200_graph_launch(self.ctx.h, self.h, _c.byref(ok)), "b200_graph_launch")
+        return bool(ok.value)
+
+    def info(self):
+        k, n, r, st = _i64(), _i64(), _i64(), _c.c_int(0)
+        _check(lib().b200_graph_info(self.h, _c.byref(k), _c.byref(n), _c.byref(r), _c.byref(st)))
+        return {"kernels": k.value, "nodes": n.value, "replays": r.value, "stale": bool(st.value)}
+
+    def close(self):
+        if self.h:
+            lib().b200_graph_destroy(self.h)
+            self.h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class DropinSolver:
     """amgcl::make_solver<amg<backend::b200<double>, smoothed_aggregation, RELAX>, KRYLOV>
     -- the reference's own templates running on the B200 backend."""
 
     def __init__(self, ptr, col, val, relax="damped_jacobi", krylov="cg", tol=1e-8,
-                 maxiter=100, coarse_enough=-1, ctx=None, precision="f64"):
+                 maxiter=100, coarse_enough=-1, ctx=None, precision="f64", graph=False):
         """precision: 'f64' (FP64 throughout) or 'mixed' (amg<backend::b200<float>> hierarchy
-        under an FP64 Krylov solver, the reference's mixed-precision composition)."""
+        under an FP64 Krylov solver, the reference's mixed-precision composition).
+        graph: wrap the hierarchy in amgcl::preconditioner::b200_cycle_graph (every V-cycle
+        is one CUDA graph launch); available for damped_jacobi|spai0 x cg|bicgstab and
+        damped_jacobi + gmres."""
         D = dropin_lib()
         self.ptr = np.ascontiguousarray(ptr, dtype=np.int64)
         self.col = np.ascontiguousarray(col, dtype=np.int64)
@@ -420,10 +479,16 @@ class DropinSolver:
         self.n = self.ptr.size - 1
         self.ctx = ctx
         self.h = _vp()
-        create = D.dropin_create_mixed if precision == "mixed" else D.dropin_create
-        rc = create(ctx.h if ctx is not None else None, self.n, _ptr(self.ptr),
-                             _ptr(self.col), _ptr(self.val), RELAX[relax], KRYLOV[krylov],
-                             float(tol), int(maxiter), int(coarse_enough), _c.byref(self.h))
+        if graph:
+            rc = D.dropin_create_graph(ctx.h if ctx is not None else None, self.n, _ptr(self.ptr),
+                                       _ptr(self.col), _ptr(self.val), RELAX[relax], KRYLOV[krylov],
+                                       1 if precision == "mixed" else 0, float(tol), int(maxiter),
+                                       int(coarse_enough), _c.byref(self.h))
+        else:
+            create = D.dropin_create_mixed if precision == "mixed" else D.dropin_create
+            rc = create(ctx.h if ctx is not None else None, self.n, _ptr(self.ptr),
+                        _ptr(self.col), _ptr(self.val), RELAX[relax], KRYLOV[krylov],
+                        float(tol), int(maxiter), int(coarse_enough), _c.byref(self.h))
         if rc != 0:
             raise B200Error("dropin_create: " + D.dropin_last_error().decode(errors="replace"))
 
@@ -482,6 +547,12 @@ class DropinSolver:
         if dropin_lib().dropin_apply_precond(self.h, _ptr(f), _ptr(x)):
             self._err("dropin_apply_precond")
         return x
+
+    def graph_stats(self):
+        """(recorded graphs, kernels per replay, replays so far); zeros without graph=True."""
+        g, k, r = _i64(), _i64(), _i64()
+        dropin_lib().dropin_graph_stats(self.h, _c.byref(g), _c.byref(k), _c.byref(r))
+        return g.value, k.value, r.value
 
     def report(self):
         need = dropin_lib().dropin_report(self.h, None, 0)

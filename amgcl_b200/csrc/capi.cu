@@ -123,6 +123,48 @@ static inline bool all32(std::initializer_list<b200_vec_t> vs) {
     return true;
 }
 
+// CUDA-graph recording -----------------------------------------------------------
+// The library keeps two pieces of host-side state per vector that decide WHICH kernels run and
+// on WHICH addresses: the storage pointer (b200_relax trades x's storage with tmp's) and the
+// lazy-clear flag.  A recorded graph bakes both in, so it remembers the state every object it
+// touched had on entry (the graph may only be replayed from exactly that state) and the state
+// the recorded calls left behind (applied after each replay).
+struct GraphSlot {
+    double **slot;      // &vec->ptr or &csr->scratch64
+    bool    *zp;        // &vec->zero_pending (nullptr for operator scratch)
+    double  *p0; bool z0;   // on entry
+    double  *p1; bool z1;   // on exit
+};
+} // namespace b200
+
+struct b200_graph_s {
+    b200_ctx_t ctx = nullptr;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    std::vector<b200::GraphSlot> slots;
+    uint64_t destroy_epoch = 0, option_epoch = 0;
+    uint64_t launches0 = 0;     // ctx->launches when recording started
+    uint64_t launches = 0;      // kernels in the graph
+    size_t   nodes = 0;
+    uint64_t replays = 0;
+};
+
+namespace b200 {
+
+static void touch_slot(b200_ctx_t ctx, double **slot, bool *zp) {
+    b200_graph_s *g = ctx->recording;
+    for (const GraphSlot &s : g->slots)
+        if (s.slot == slot) return;
+    g->slots.push_back({slot, zp, *slot, zp ? *zp : false, nullptr, false});
+}
+static inline void touch(b200_ctx_t ctx, std::initializer_list<b200_vec_t> vs) {
+    if (!ctx->recording) return;
+    for (b200_vec_t v : vs) {
+        touch_slot(ctx, &v->ptr, &v->zero_pending);
+        v->in_graph = true;
+    }
+}
+
 static int grid_for(const b200_ctx_t ctx, size_t n_items, int per_thread_items) {
     // enough CTAs to cover the range once, capped at 8 CTAs per SM (2048 threads)
     size_t want = (n_items + (size_t)kThreads * per_thread_items - 1) /
@@ -150,6 +192,8 @@ static inline bool same_layout(b200_vec_t a, b200_vec_t b) {
 }
 #define B200_REQUIRE_F64_DIST(ctx, what)                                                    \
     B200_REQUIRE(!(ctx)->dist, what ": FP32 objects are not supported on a distributed context")
+#define NOT_RECORDING(ctx, what)                                                        \
+    B200_REQUIRE(!(ctx)->recording, what ": not allowed while a graph is being recorded")
 #define GUARD(ctx)                                                             \
     DeviceGuard guard__((ctx)->device);                                        \
     if (!guard__.ok) return fail(B200_ECUDA, "cudaSetDevice failed")
@@ -183,6 +227,8 @@ extern "C" int b200_ctx_create(int device, b200_ctx_t *out) {
     if (!ctx) return fail(B200_ENOMEM, "out of host memory");
     ctx->device = device;
     if (const char *e = getenv("B200_PDL")) ctx->opt_pdl = atoi(e) ? 1 : 0;
+    if (const char *e = getenv("B200_CYCLE_GRAPH")) ctx->opt_cycle_graph = atoi(e) ? 1 : 0;
+    if (const char *e = getenv("B200_GRAPH_PDL")) ctx->opt_graph_pdl = atoi(e) ? 1 : 0;
     cudaDeviceProp prop;
     B200_CUDA(cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
@@ -242,6 +288,8 @@ extern "C" int b200_ctx_default(b200_ctx_t *out) {
 
 extern "C" int b200_ctx_set_stream(b200_ctx_t ctx, void *cuda_stream) {
     CHECK_CTX(ctx);
+    NOT_RECORDING(ctx, "stream change");
+    ctx->option_epoch++;
     ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
     return B200_OK;
 }
@@ -262,6 +310,7 @@ extern "C" int b200_ctx_device(b200_ctx_t ctx, int *device) {
 
 extern "C" int b200_ctx_sync(b200_ctx_t ctx) {
     CHECK_CTX(ctx);
+    NOT_RECORDING(ctx, "sync");
     GUARD(ctx);
     B200_CUDA(cudaStreamSynchronize(ctx->stream));
     return B200_OK;
@@ -282,6 +331,7 @@ extern "C" int b200_ctx_reset_launch_count(b200_ctx_t ctx) {
 
 extern "C" int b200_profile_begin(b200_ctx_t ctx) {
     CHECK_CTX(ctx);
+    NOT_RECORDING(ctx, "profiling");
     ctx->prof_used = 0;
     ctx->prof_recs.clear();
     ctx->profiling = true;
@@ -462,6 +512,8 @@ static int64_t *option_slot(b200_ctx_t ctx, const char *key) {
     if (!strcmp(key, "stages")) return &ctx->opt_stages;
     if (!strcmp(key, "p2p")) return &ctx->opt_p2p;
     if (!strcmp(key, "pdl")) return &ctx->opt_pdl;
+    if (!strcmp(key, "cycle_graph")) return &ctx->opt_cycle_graph;
+    if (!strcmp(key, "graph_pdl")) return &ctx->opt_graph_pdl;
     return nullptr;
 }
 
@@ -482,6 +534,8 @@ extern "C" int b200_ctx_set_option(b200_ctx_t ctx, const char *key, int64_t valu
     } else if (slot == &ctx->opt_spmv_variant) {
         if (value < 0 || value > 1) return fail(B200_EINVAL, "spmv_variant must be 0 or 1");
     }
+    B200_REQUIRE(!ctx->recording, "options cannot change while a graph is being recorded");
+    if (*slot != value) ctx->option_epoch++;      // recorded graphs were built with the old value
     *slot = value;
     return B200_OK;
 }
@@ -500,6 +554,7 @@ extern "C" int b200_ctx_get_option(b200_ctx_t ctx, const char *key, int64_t *val
 // ---------------------------------------------------------------------------
 static int vec_create_typed(b200_ctx_t ctx, size_t n, int dtype, b200_vec_t *out) {
     CHECK_CTX(ctx);
+    NOT_RECORDING(ctx, "vector creation");
     B200_REQUIRE(out != nullptr, "null output pointer");
     *out = nullptr;
     if (dtype == B200_F32) B200_REQUIRE_F64_DIST(ctx, "b200_vec_create_f32");
@@ -584,6 +639,17 @@ extern "C" int b200_vec_wrap(b200_ctx_t ctx, double *device_ptr, size_t n, b200_
 
 extern "C" int b200_vec_destroy(b200_vec_t v) {
     if (!v) return B200_OK;
+    if (v->in_graph) v->ctx->destroy_epoch++;      // recorded graphs that refer to it are dead
+    if (b200_graph_s *g = v->ctx->recording) {
+        // (e.g. a garbage-collected handle of the host language)  The recording may already
+        // use the storage: it is released after the recorded calls have run.
+        for (size_t i = 0; i < g->slots.size();)
+            if (g->slots[i].slot == &v->ptr) g->slots.erase(g->slots.begin() + i);
+            else ++i;
+        if (v->owned && v->ptr) v->ctx->graph_deferred.push_back(v->ptr);
+        delete v;
+        return B200_OK;
+    }
     GUARD(v->ctx);
     if (v->owned && v->ptr) {
         // cudaFree synchronises the device, so no kernel can still be using it
@@ -616,6 +682,7 @@ extern "C" int b200_vec_data(b200_vec_t v, double **device_ptr) {
 
 extern "C" int b200_vec_upload_f32(b200_vec_t v, const float *host, size_t n) {
     B200_REQUIRE(v && (host || n == 0), "null argument");
+    NOT_RECORDING(v->ctx, "host transfer");
     B200_REQUIRE(n == v->n, "size mismatch in vector upload");
     B200_REQUIRE(v->dtype == B200_F32 && v->kind == B200_VK_LOCAL, "upload_f32: FP32 local vector expected");
     GUARD(v->ctx);
@@ -629,6 +696,7 @@ extern "C" int b200_vec_upload_f32(b200_vec_t v, const float *host, size_t n) {
 
 extern "C" int b200_vec_download_f32(b200_vec_t v, float *host, size_t n) {
     B200_REQUIRE(v && (host || n == 0), "null argument");
+    NOT_RECORDING(v->ctx, "host transfer");
     B200_REQUIRE(n == v->n, "size mismatch in vector download");
     B200_REQUIRE(v->dtype == B200_F32 && v->kind == B200_VK_LOCAL, "download_f32: FP32 local vector expected");
     GUARD(v->ctx);
@@ -642,6 +710,7 @@ extern "C" int b200_vec_download_f32(b200_vec_t v, float *host, size_t n) {
 
 extern "C" int b200_vec_upload(b200_vec_t v, const double *host, size_t n) {
     B200_REQUIRE(v && (host || n == 0), "null argument");
+    NOT_RECORDING(v->ctx, "host transfer");
     B200_REQUIRE(n == v->n, "size mismatch in vector upload");
     B200_REQUIRE(v->dtype == B200_F64, "b200_vec_upload: FP64 vector expected (use _f32)");
     GUARD(v->ctx);
@@ -658,6 +727,7 @@ extern "C" int b200_vec_upload(b200_vec_t v, const double *host, size_t n) {
 
 extern "C" int b200_vec_download(b200_vec_t v, double *host, size_t n) {
     B200_REQUIRE(v && (host || n == 0), "null argument");
+    NOT_RECORDING(v->ctx, "host transfer");
     B200_REQUIRE(n == v->n, "size mismatch in vector download");
     B200_REQUIRE(v->dtype == B200_F64, "b200_vec_download: FP64 vector expected (use _f32)");
     b200_ctx_t ctx = v->ctx;
@@ -871,6 +941,7 @@ template <class Ptr, class Col>
 static int csr_create_f32(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *ptr,
                           const Col *col, const float *val, b200_csr_t *out) {
     CHECK_CTX(ctx);
+    NOT_RECORDING(ctx, "matrix creation");
     B200_REQUIRE_F64_DIST(ctx, "b200_csr_create_*_f32");
     return csr_upload(ctx, nrows, ncols, ptr, col, val, out);
 }
@@ -879,6 +950,7 @@ template <class Ptr, class Col>
 static int csr_create(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *ptr,
                       const Col *col, const double *val, b200_csr_t *out) {
     CHECK_CTX(ctx);
+    NOT_RECORDING(ctx, "matrix creation");
     B200_REQUIRE(out != nullptr, "null output pointer");
     *out = nullptr;
     if (!ctx->dist) return csr_upload(ctx, nrows, ncols, ptr, col, val, out);
@@ -1056,7 +1128,8 @@ static cudaError_t launch_pdl(b200_ctx_t ctx, void (*kernel)(KArgs...), dim3 gri
     cfg.stream = ctx->stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = ctx->opt_pdl ? 1 : 0;
+    attr[0].val.programmaticStreamSerializationAllowed =
+        (ctx->opt_pdl && (!ctx->recording || ctx->opt_graph_pdl)) ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, args...);
@@ -1113,6 +1186,7 @@ static int launch_csr_L(b200_ctx_t ctx, b200_csr_t A, const CsrArgsT<P> &args) {
 template <int MODE, class P>
 static int launch_csr(b200_ctx_t ctx, b200_csr_t A, const CsrArgsT<P> &args) {
     if (A->nblocks == 0) return B200_OK;
+    if (ctx->recording) A->in_graph = true;
     ProfScope prof(ctx, MODE, A->nrows, A->ncols, A->nnz);
     switch (A->lanes) {
     case 1:  return launch_csr_L<MODE, 1>(ctx, A, args);
@@ -1462,6 +1536,8 @@ extern "C" int b200_plan_i64(int64_t nrows, const int64_t *ptr, int lanes, int n
 
 extern "C" int b200_csr_destroy(b200_csr_t A) {
     if (!A) return B200_OK;
+    NOT_RECORDING(A->ctx, "matrix destruction");
+    if (A->in_graph) A->ctx->destroy_epoch++;
     GUARD(A->ctx);
     csr_free(A);
     return B200_OK;
@@ -1540,6 +1616,7 @@ extern "C" int b200_spmv(b200_ctx_t ctx, double alpha, b200_csr_t A, b200_vec_t 
                          b200_vec_t y) {
     CHECK_CTX(ctx);
     B200_REQUIRE(A && x && y, "null argument");
+    touch(ctx, {x, y});
     B200_REQUIRE((int64_t)x->n == A->gl_cols, "spmv: x size != matrix columns");
     B200_REQUIRE((int64_t)y->n == A->gl_rows, "spmv: y size != matrix rows");
     B200_REQUIRE(x != y && (x->ptr != y->ptr || !x->ptr), "spmv: x and y must not alias");
@@ -1592,6 +1669,7 @@ extern "C" int b200_residual(b200_ctx_t ctx, b200_vec_t f, b200_csr_t A, b200_ve
                              b200_vec_t r) {
     CHECK_CTX(ctx);
     B200_REQUIRE(f && A && x && r, "null argument");
+    touch(ctx, {f, x, r});
     B200_REQUIRE((int64_t)x->n == A->gl_cols, "residual: x size != matrix columns");
     B200_REQUIRE((int64_t)f->n == A->gl_rows && (int64_t)r->n == A->gl_rows,
                  "residual: rhs/r size != matrix rows");
@@ -1625,6 +1703,7 @@ extern "C" int b200_residual(b200_ctx_t ctx, b200_vec_t f, b200_csr_t A, b200_ve
 extern "C" int b200_clear(b200_ctx_t ctx, b200_vec_t x) {
     CHECK_CTX(ctx);
     B200_REQUIRE(x, "null argument");
+    touch(ctx, {x});
     if (x->kind == B200_VK_GHOST) return B200_OK;
     if (ctx->opt_zero_shortcut) {
         x->zero_pending = true;
@@ -1638,6 +1717,7 @@ extern "C" int b200_clear(b200_ctx_t ctx, b200_vec_t x) {
 extern "C" int b200_copy(b200_ctx_t ctx, b200_vec_t x, b200_vec_t y) {
     CHECK_CTX(ctx);
     B200_REQUIRE(x && y, "null argument");
+    touch(ctx, {x, y});
     B200_REQUIRE(same_layout(x, y), "copy: size mismatch");
     if (x->kind == B200_VK_GHOST || x == y || x->ptr == y->ptr) return B200_OK;
     if (x->zero_pending) {
@@ -1670,6 +1750,7 @@ static void launch_dot_kernel(b200_ctx_t ctx, b200_vec_t x, b200_vec_t y, double
 extern "C" int b200_dot(b200_ctx_t ctx, b200_vec_t x, b200_vec_t y, double *result) {
     CHECK_CTX(ctx);
     B200_REQUIRE(x && y && result, "null argument");
+    NOT_RECORDING(ctx, "dot (host-synchronous)");
     B200_REQUIRE(same_layout(x, y), "dot: size mismatch");
     if (x->dtype != y->dtype) return B200_BAD_MIX("dot");
     GUARD(ctx);
@@ -1776,6 +1857,7 @@ static int vmul_t(b200_ctx_t ctx, double alpha, b200_vec_t x, b200_vec_t y, doub
 extern "C" int b200_axpby(b200_ctx_t ctx, double a, b200_vec_t x, double b, b200_vec_t y) {
     CHECK_CTX(ctx);
     B200_REQUIRE(x && y, "null argument");
+    touch(ctx, {x, y});
     B200_REQUIRE(same_layout(x, y), "axpby: size mismatch");
     if (x->kind == B200_VK_GHOST) return B200_OK;
     GUARD(ctx);
@@ -1788,6 +1870,7 @@ extern "C" int b200_axpbypcz(b200_ctx_t ctx, double a, b200_vec_t x, double b, b
                              double c, b200_vec_t z) {
     CHECK_CTX(ctx);
     B200_REQUIRE(x && y && z, "null argument");
+    touch(ctx, {x, y, z});
     B200_REQUIRE(same_layout(x, y) && same_layout(x, z), "axpbypcz: size mismatch");
     if (x->kind == B200_VK_GHOST) return B200_OK;
     GUARD(ctx);
@@ -1800,6 +1883,7 @@ extern "C" int b200_vmul(b200_ctx_t ctx, double alpha, b200_vec_t x, b200_vec_t 
                          b200_vec_t z) {
     CHECK_CTX(ctx);
     B200_REQUIRE(x && y && z, "null argument");
+    touch(ctx, {x, y, z});
     B200_REQUIRE(same_layout(x, y) && same_layout(x, z), "vmul: size mismatch");
     if (x->kind == B200_VK_GHOST) return B200_OK;
     GUARD(ctx);
@@ -1849,6 +1933,7 @@ extern "C" int b200_relax(b200_ctx_t ctx, b200_csr_t A, b200_vec_t rhs, b200_vec
                           b200_vec_t tmp, b200_vec_t diag, double omega) {
     CHECK_CTX(ctx);
     B200_REQUIRE(A && rhs && x && tmp && diag, "null argument");
+    touch(ctx, {rhs, x, tmp, diag});
     B200_REQUIRE(A->gl_rows == A->gl_cols, "relax: matrix must be square");
     B200_REQUIRE((int64_t)x->n == A->gl_rows && same_layout(x, rhs) && same_layout(x, diag) &&
                      same_layout(x, tmp),
@@ -1905,6 +1990,7 @@ extern "C" int b200_relax(b200_ctx_t ctx, b200_csr_t A, b200_vec_t rhs, b200_vec
         // FP64 buffer that trades places with x exactly like tmp does in the uniform case
         if (!A->scratch64)
             B200_CUDA(cudaMalloc(&A->scratch64, ((size_t)A->nrows + 4) * sizeof(double)));
+        if (ctx->recording) touch_slot(ctx, &A->scratch64, nullptr);
         CsrArgsT<PrecFD> a = base_args_t<PrecFD>(A);
         const double *px;
         rc = rd(x, &px);
@@ -1948,6 +2034,7 @@ template <class Ptr, class Col, class Val>
 static int coarse_create(b200_ctx_t ctx, int64_t n, const Ptr *ptr, const Col *col,
                          const Val *val, b200_coarse_t *out) {
     CHECK_CTX(ctx);
+    NOT_RECORDING(ctx, "coarse solver creation");
     B200_REQUIRE(out != nullptr, "null output pointer");
     *out = nullptr;
     B200_REQUIRE(n > 0 && n <= 16384, "coarse solver: n must be in [1, 16384]");
@@ -2096,6 +2183,8 @@ extern "C" int b200_coarse_create_i32_f32(b200_ctx_t ctx, int64_t n, const int32
 
 extern "C" int b200_coarse_destroy(b200_coarse_t S) {
     if (!S) return B200_OK;
+    NOT_RECORDING(S->ctx, "coarse solver destruction");
+    if (S->in_graph) S->ctx->destroy_epoch++;
     GUARD(S->ctx);
     if (S->Ainv) cudaFree(S->Ainv);
     if (S->gbuf) cudaFree(S->gbuf);
@@ -2112,6 +2201,8 @@ extern "C" int b200_coarse_bytes(b200_coarse_t S, size_t *bytes) {
 extern "C" int b200_coarse_solve(b200_ctx_t ctx, b200_coarse_t S, b200_vec_t rhs, b200_vec_t x) {
     CHECK_CTX(ctx);
     B200_REQUIRE(S && rhs && x, "null argument");
+    touch(ctx, {rhs, x});
+    if (ctx->recording) S->in_graph = true;
     B200_REQUIRE((int64_t)rhs->n == S->n && (int64_t)x->n == S->n, "coarse solve: size mismatch");
     if (S->ghost) return B200_OK;
     GUARD(ctx);
@@ -2152,5 +2243,143 @@ extern "C" int b200_coarse_solve(b200_ctx_t ctx, b200_coarse_t S, b200_vec_t rhs
                              dim3(kThreads), 0, N, 0, N, (const double *)S->Ainv, pr, wr(x)));
     B200_CHECK_LAUNCH();
     ctx->launches++;
+    return B200_OK;
+}
+
+// ---------------------------------------------------------------------------
+// CUDA-graph recording of a call sequence (the V-cycle)
+// ---------------------------------------------------------------------------
+namespace b200 {
+static void graph_free(b200_graph_s *g) {
+    if (!g) return;
+    if (g->exec) cudaGraphExecDestroy(g->exec);
+    if (g->graph) cudaGraphDestroy(g->graph);
+    delete g;
+}
+// put every touched object back into the state it had when recording started (nothing that
+// was recorded has run)
+static void graph_release_deferred(b200_ctx_t ctx) {
+    for (void *p : ctx->graph_deferred) cudaFree(p);     // cudaFree waits for the device
+    ctx->graph_deferred.clear();
+}
+static void graph_rollback(b200_graph_s *g) {
+    for (const GraphSlot &s : g->slots) {
+        *s.slot = s.p0;
+        if (s.zp) *s.zp = s.z0;
+    }
+}
+} // namespace b200
+
+extern "C" int b200_graph_begin(b200_ctx_t ctx, int *recording) {
+    CHECK_CTX(ctx);
+    B200_REQUIRE(recording != nullptr, "null output pointer");
+    B200_REQUIRE(!ctx->recording, "graph_begin: already recording");
+    *recording = 0;
+    // not recordable: per-launch event timing, multi-GPU exchanges (host-side sequence
+    // numbers and NCCL calls), the legacy default stream
+    if (ctx->profiling || ctx->dist || !ctx->opt_cycle_graph) return B200_OK;
+    if (ctx->stream == nullptr || ctx->stream == cudaStreamLegacy) return B200_OK;
+    GUARD(ctx);
+    b200_graph_s *g = new (std::nothrow) b200_graph_s();
+    if (!g) return fail(B200_ENOMEM, "out of host memory");
+    g->ctx = ctx;
+    g->destroy_epoch = ctx->destroy_epoch;
+    g->option_epoch = ctx->option_epoch;
+    g->launches0 = ctx->launches;
+    const cudaError_t rc = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed);
+    if (rc != cudaSuccess) {
+        delete g;
+        return cuda_fail(rc, "cudaStreamBeginCapture", __FILE__, __LINE__);
+    }
+    ctx->recording = g;
+    *recording = 1;
+    return B200_OK;
+}
+
+extern "C" int b200_graph_abort(b200_ctx_t ctx) {
+    CHECK_CTX(ctx);
+    b200_graph_s *g = ctx->recording;
+    if (!g) return B200_OK;
+    GUARD(ctx);
+    cudaGraph_t junk = nullptr;
+    cudaStreamEndCapture(ctx->stream, &junk);      // may itself report the capture as invalidated
+    if (junk) cudaGraphDestroy(junk);
+    cudaGetLastError();
+    graph_rollback(g);
+    ctx->launches = g->launches0;
+    ctx->recording = nullptr;
+    graph_free(g);
+    graph_release_deferred(ctx);
+    return B200_OK;
+}
+
+extern "C" int b200_graph_end(b200_ctx_t ctx, b200_graph_t *out) {
+    CHECK_CTX(ctx);
+    B200_REQUIRE(out != nullptr, "null output pointer");
+    *out = nullptr;
+    b200_graph_s *g = ctx->recording;
+    B200_REQUIRE(g != nullptr, "graph_end: not recording");
+    GUARD(ctx);
+    ctx->recording = nullptr;
+    cudaError_t rc = cudaStreamEndCapture(ctx->stream, &g->graph);
+    if (rc == cudaSuccess) rc = cudaGraphInstantiate(&g->exec, g->graph, 0);
+    if (rc == cudaSuccess) rc = cudaGraphGetNodes(g->graph, nullptr, &g->nodes);
+    if (rc == cudaSuccess) rc = cudaGraphLaunch(g->exec, ctx->stream);     // the recorded calls run now
+    if (rc != cudaSuccess) {
+        cudaGetLastError();
+        graph_rollback(g);
+        ctx->launches = g->launches0;
+        graph_free(g);
+        graph_release_deferred(ctx);
+        return cuda_fail(rc, "graph_end (capture / instantiate / launch)", __FILE__, __LINE__);
+    }
+    graph_release_deferred(ctx);
+    for (GraphSlot &s : g->slots) {
+        s.p1 = *s.slot;
+        s.z1 = s.zp ? *s.zp : false;
+    }
+    g->launches = ctx->launches - g->launches0;
+    *out = g;
+    return B200_OK;
+}
+
+extern "C" int b200_graph_launch(b200_ctx_t ctx, b200_graph_t g, int *launched) {
+    CHECK_CTX(ctx);
+    B200_REQUIRE(g && launched, "null argument");
+    *launched = 0;
+    B200_REQUIRE(g->ctx == ctx, "graph belongs to another context");
+    B200_REQUIRE(!ctx->recording, "graph_launch: a graph is being recorded");
+    if (ctx->profiling || !ctx->opt_cycle_graph) return B200_OK;
+    if (g->destroy_epoch != ctx->destroy_epoch || g->option_epoch != ctx->option_epoch)
+        return B200_OK;                      // stale: the caller records a new one
+    for (const GraphSlot &s : g->slots)
+        if (*s.slot != s.p0 || (s.zp && *s.zp != s.z0)) return B200_OK;
+    GUARD(ctx);
+    B200_CUDA(cudaGraphLaunch(g->exec, ctx->stream));
+    for (const GraphSlot &s : g->slots) {
+        *s.slot = s.p1;
+        if (s.zp) *s.zp = s.z1;
+    }
+    ctx->launches += g->launches;
+    g->replays++;
+    *launched = 1;
+    return B200_OK;
+}
+
+extern "C" int b200_graph_info(b200_graph_t g, int64_t *kernels, int64_t *nodes, int64_t *replays,
+                               int *stale) {
+    B200_REQUIRE(g != nullptr, "null argument");
+    if (kernels) *kernels = (int64_t)g->launches;
+    if (nodes) *nodes = (int64_t)g->nodes;
+    if (replays) *replays = (int64_t)g->replays;
+    if (stale)
+        *stale = (g->destroy_epoch != g->ctx->destroy_epoch || g->option_epoch != g->ctx->option_epoch);
+    return B200_OK;
+}
+
+extern "C" int b200_graph_destroy(b200_graph_t g) {
+    if (!g) return B200_OK;
+    GUARD(g->ctx);
+    graph_free(g);
     return B200_OK;
 }

@@ -54,6 +54,8 @@ constexpr int kDotMaxBlocks = 2048;   // upper bound on partial sums of one dot 
 // ---------------------------------------------------------------------------
 // objects behind the opaque handles
 // ---------------------------------------------------------------------------
+struct b200_graph_s;
+
 struct b200_ctx_s {
     int          device      = 0;
     int          sm_count    = 148;
@@ -100,6 +102,14 @@ struct b200_ctx_s {
     int64_t opt_stages        = 2;        // persistent variant: ring depth
     int64_t opt_p2p           = 1;        // multi-GPU: exchange through mapped peer memory
     int64_t opt_pdl           = 1;        // programmatic dependent launch of the solve kernels
+    int64_t opt_cycle_graph   = 1;        // the shim's preconditioner wrapper may record CUDA graphs
+    int64_t opt_graph_pdl     = 1;        // keep the PDL attribute on launches recorded into a graph
+
+    // CUDA-graph recording of a call sequence (b200_graph_*)
+    b200_graph_s *recording   = nullptr;  // non-null between b200_graph_begin and _end / _abort
+    std::vector<void *> graph_deferred;   // storage of vectors destroyed while recording
+    uint64_t     destroy_epoch = 0;       // bumped when an object a graph refers to is destroyed
+    uint64_t     option_epoch  = 0;       // bumped by b200_ctx_set_option / set_stream
 };
 
 enum { B200_VK_LOCAL = 0, B200_VK_DIST = 1, B200_VK_GHOST = 2 };
@@ -119,6 +129,7 @@ struct b200_vec_s {
     // issued.  Set by b200_clear, consumed by b200_relax (which then skips the
     // A-pass), dropped by any full overwrite, materialised by any other read.
     bool       zero_pending = false;
+    bool       in_graph     = false;   // some recorded graph refers to this vector
 };
 
 enum { B200_CK_LOCAL = 0, B200_CK_SQUARE = 1, B200_CK_PROLONG = 2, B200_CK_RESTRICT = 3,
@@ -154,6 +165,7 @@ struct b200_csr_s {
     void      *val   = nullptr;   // [nnz]     (+ padding) device, FP64 or FP32
     int        dtype = B200_F64;
     double    *scratch64 = nullptr;   // FP32 operator swept on FP64 vectors: new iterate
+    bool       in_graph  = false;     // some recorded graph refers to this operator
     // row-block plan
     int        lanes    = 1;      // lanes cooperating on one row (power of two <= 32)
     int        rows_cap = 256;    // rows per block   (multiple of kThreads / lanes)
@@ -174,6 +186,7 @@ struct b200_coarse_s {
     int64_t    n    = 0;
     double    *Ainv = nullptr;    // [n*n] row-major device
     size_t     bytes = 0;
+    bool       in_graph = false;
 };
 
 // ---------------------------------------------------------------------------

@@ -29,6 +29,7 @@
 #include <amgcl/solver/cg.hpp>
 #include <amgcl/solver/bicgstab.hpp>
 #include <amgcl/relaxation/chebyshev.hpp>
+#include <amgcl/relaxation/ilu0.hpp>
 #include <amgcl/solver/gmres.hpp>
 #include <amgcl/solver/bicgstabl.hpp>
 
@@ -44,14 +45,28 @@ struct SolverBase {
     virtual void apply_precond(const Backend::vector &f, Backend::vector &x) = 0;
     virtual std::string report() const = 0;
     virtual size_t bytes() const = 0;
+    virtual void graph_stats(size_t &ngraphs, size_t &kernels, size_t &replays) const {
+        ngraphs = kernels = replays = 0;
+    }
 };
 
 typedef amgcl::backend::b200<float> BackendF32;   // hierarchy of a mixed-precision solver
 
-template <template <class> class Relax, template <class, class> class Krylov, class PBackend = Backend>
+// Graph = true wraps the hierarchy in preconditioner::b200_cycle_graph (one CUDA graph launch
+// per V-cycle); Graph = false is the unmodified reference composition.
+template <class AMG, bool Graph> struct precond_of { typedef AMG type; };
+template <class AMG> struct precond_of<AMG, true> { typedef amgcl::preconditioner::b200_cycle_graph<AMG> type; };
+
+template <class P> void stats_of(const P &, size_t &g, size_t &k, size_t &r) { g = k = r = 0; }
+template <class AMG> void stats_of(const amgcl::preconditioner::b200_cycle_graph<AMG> &p,
+                                   size_t &g, size_t &k, size_t &r) { p.graph_stats(g, k, r); }
+
+template <template <class> class Relax, template <class, class> class Krylov, class PBackend = Backend,
+          bool Graph = false>
 struct SolverImpl : SolverBase {
+    typedef amgcl::amg<PBackend, amgcl::coarsening::smoothed_aggregation, Relax> AMG;
     typedef amgcl::make_solver<
-        amgcl::amg<PBackend, amgcl::coarsening::smoothed_aggregation, Relax>,
+        typename precond_of<AMG, Graph>::type,
         Krylov<Backend, amgcl::solver::detail::default_inner_product>
         > Solver;
 
@@ -84,7 +99,25 @@ struct SolverImpl : SolverBase {
         return os.str();
     }
     size_t bytes() const override { return amgcl::backend::bytes(*S); }
+    void graph_stats(size_t &g, size_t &k, size_t &r) const override { stats_of(S->precond(), g, k, r); }
 };
+
+// the four BASELINE.json combinations with the V-cycle replayed as a CUDA graph
+template <class PBackend>
+SolverBase *make_graphed(int relax, int krylov, size_t n, const int64_t *ptr, const int64_t *col,
+                         const double *val, double tol, int maxiter, int coarse_enough,
+                         const Backend::params &bprm) {
+    using namespace amgcl;
+    if (relax == 0 && krylov == 0)
+        return new SolverImpl<relaxation::damped_jacobi, solver::cg, PBackend, true>(n, ptr, col, val, tol, maxiter, coarse_enough, bprm);
+    if (relax == 0 && krylov == 1)
+        return new SolverImpl<relaxation::damped_jacobi, solver::bicgstab, PBackend, true>(n, ptr, col, val, tol, maxiter, coarse_enough, bprm);
+    if (relax == 1 && krylov == 0)
+        return new SolverImpl<relaxation::spai0, solver::cg, PBackend, true>(n, ptr, col, val, tol, maxiter, coarse_enough, bprm);
+    if (relax == 1 && krylov == 1)
+        return new SolverImpl<relaxation::spai0, solver::bicgstab, PBackend, true>(n, ptr, col, val, tol, maxiter, coarse_enough, bprm);
+    return nullptr;
+}
 
 struct Handle {
     size_t n;
@@ -129,6 +162,12 @@ int dropin_create(void *ctx, int64_t n, const int64_t *ptr, const int64_t *col, 
             h->solver.reset(new SolverImpl<relaxation::damped_jacobi, solver::gmres>(n, ptr, col, val, tol, maxiter, coarse_enough, h->bprm));
         else if (relax == 1 && krylov == 3)
             h->solver.reset(new SolverImpl<relaxation::spai0, solver::bicgstabl>(n, ptr, col, val, tol, maxiter, coarse_enough, h->bprm));
+        // ILU(0): setup on the host, triangular solves as damped Jacobi sweeps built from
+        // residual / axpby / vmul (relaxation/detail/ilu_solve.hpp:97-113)
+        else if (relax == 3 && krylov == 1)
+            h->solver.reset(new SolverImpl<relaxation::ilu0, solver::bicgstab>(n, ptr, col, val, tol, maxiter, coarse_enough, h->bprm));
+        else if (relax == 3 && krylov == 0)
+            h->solver.reset(new SolverImpl<relaxation::ilu0, solver::cg>(n, ptr, col, val, tol, maxiter, coarse_enough, h->bprm));
         else {
             g_error = "unknown relax/krylov selector";
             return -1;
@@ -173,6 +212,50 @@ int dropin_create_mixed(void *ctx, int64_t n, const int64_t *ptr, const int64_t 
         g_error = e.what();
         return -1;
     }
+}
+
+// As dropin_create / dropin_create_mixed (mixed != 0), with the hierarchy wrapped in
+// amgcl::preconditioner::b200_cycle_graph.  GMRES exercises many (rhs, x) pairs per solve.
+int dropin_create_graph(void *ctx, int64_t n, const int64_t *ptr, const int64_t *col, const double *val,
+                        int relax, int krylov, int mixed, double tol, int maxiter, int coarse_enough,
+                        void **out)
+{
+    try {
+        std::unique_ptr<Handle> h(new Handle());
+        h->n = (size_t)n;
+        h->bprm = Backend::params(static_cast<b200_ctx_t>(ctx));
+        SolverBase *sb = nullptr;
+        if (!mixed && relax == 0 && krylov == 2)
+            sb = new SolverImpl<amgcl::relaxation::damped_jacobi, amgcl::solver::gmres, Backend, true>(n, ptr, col, val, tol, maxiter, coarse_enough, h->bprm);
+        else if (mixed)
+            sb = make_graphed<BackendF32>(relax, krylov, n, ptr, col, val, tol, maxiter, coarse_enough, h->bprm);
+        else
+            sb = make_graphed<Backend>(relax, krylov, n, ptr, col, val, tol, maxiter, coarse_enough, h->bprm);
+        if (!sb) {
+            g_error = "unknown relax/krylov selector";
+            return -1;
+        }
+        h->solver.reset(sb);
+        h->f = Backend::create_vector(n, h->bprm);
+        h->x = Backend::create_vector(n, h->bprm);
+        *out = h.release();
+        return 0;
+    } catch (const std::exception &e) {
+        g_error = e.what();
+        return -1;
+    }
+}
+
+// recorded graphs, kernels per replay (first graph), replays so far
+int dropin_graph_stats(void *handle, int64_t *ngraphs, int64_t *kernels, int64_t *replays)
+{
+    Handle *h = static_cast<Handle *>(handle);
+    size_t g, k, r;
+    h->solver->graph_stats(g, k, r);
+    if (ngraphs) *ngraphs = (int64_t)g;
+    if (kernels) *kernels = (int64_t)k;
+    if (replays) *replays = (int64_t)r;
+    return 0;
 }
 
 void dropin_destroy(void *handle) { delete static_cast<Handle *>(handle); }

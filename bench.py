@@ -48,6 +48,9 @@ def parse_args():
     ap.add_argument("--partition-min-rows", type=int, default=1000000)
     ap.add_argument("--p2p", type=int, default=1, choices=[0, 1],
                     help="N>1: 1 = peer-memory exchange kernels over NVLink, 0 = NCCL collectives")
+    ap.add_argument("--graph", type=int, default=0, choices=[0, 1],
+                    help="1: amgcl::preconditioner::b200_cycle_graph<amg<...>> -- every V-cycle is one "
+                         "CUDA graph launch (single GPU)")
     ap.add_argument("--ref-sample-iters", type=int, default=8,
                     help="Krylov iterations per step of the CPU reference sample")
     return ap.parse_args()
@@ -255,7 +258,8 @@ def main_arm(args, rank, world, local_rank):
             if ctx.dist_info()["p2p"] else "NCCL collectives"
 
     t0 = time.time()
-    S = ab.DropinSolver(ptr, col, val, args.relax, args.krylov, ctx=ctx, precision=args.precision)
+    S = ab.DropinSolver(ptr, col, val, args.relax, args.krylov, ctx=ctx, precision=args.precision,
+                        graph=bool(args.graph) and world == 1)
     t_setup = time.time() - t0
 
     def barrier():
@@ -411,6 +415,8 @@ def main_arm(args, rank, world, local_rank):
                        "parallelism": "single GPU" if world == 1 else
                                       "one system row-partitioned over %d GPUs (levels with >= %d rows; "
                                       "exchange: %s)" % (world, dist_min_rows, transport),
+                       "cycle_graph": {"on": bool(args.graph) and world == 1,
+                                       "graphs_kernels_replays": list(S.graph_stats())},
                        "setup_s": t_setup, "generate_s": t_gen, "hierarchy": "host (AMGCL smoothed_aggregation)"},
             "solve_s": solve_s, "iters": iters, "resid": res,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,

@@ -32,6 +32,7 @@
  * residual + vmul (damped_jacobi.hpp:108-109, spai0.hpp:91-92).
  */
 
+#include <iostream>
 #include <memory>
 #include <string>
 #include <vector>
@@ -580,6 +581,134 @@ struct spai0< backend::b200<real, C, P, DS> > {
 };
 
 } // namespace relaxation
+
+//---------------------------------------------------------------------------
+// Whole-cycle CUDA graph (opt-in wrapper)
+//---------------------------------------------------------------------------
+namespace preconditioner {
+
+/// Wraps a preconditioner that runs on backend::b200 (normally amgcl::amg<...>) and replays
+/// its apply() as ONE CUDA graph launch:
+///
+/// \code
+///   typedef amgcl::amg<Backend, coarsening::smoothed_aggregation, relaxation::damped_jacobi> AMG;
+///   typedef amgcl::make_solver<amgcl::preconditioner::b200_cycle_graph<AMG>,
+///                              amgcl::solver::cg<Backend>> Solver;
+/// \endcode
+///
+/// amg::apply (amg.hpp:289-297) issues clear + cycle (amg.hpp:514-553) as a fixed sequence of
+/// backend calls with no host-visible result, so the sequence is recorded once per distinct
+/// (rhs, x, vector-state) combination through b200_graph_begin / _end and replayed afterwards.
+/// The first application runs directly (it also performs one-off allocations); applications
+/// the C library declines to replay (state mismatch, profiling, multi-GPU context) fall back
+/// to recording another graph or to the direct path, so results are always those of P.apply.
+template <class Precond>
+class b200_cycle_graph {
+    public:
+        typedef typename Precond::backend_type backend_type;
+        typedef typename backend_type::matrix  matrix;
+        typedef typename backend_type::value_type value_type;
+        typedef typename backend_type::col_type col_type;
+        typedef typename backend_type::ptr_type ptr_type;
+        typedef typename backend::builtin<value_type, col_type, ptr_type>::matrix build_matrix;
+        typedef typename Precond::params params;
+        typedef typename backend_type::params backend_params;
+
+        template <class Matrix>
+        b200_cycle_graph(const Matrix &M, const params &prm = params(),
+                const backend_params &bprm = backend_params())
+            : P(M, prm, bprm), ctx(bprm.context()), applied(0), enabled(true) {}
+
+        b200_cycle_graph(std::shared_ptr<build_matrix> M, const params &prm = params(),
+                const backend_params &bprm = backend_params())
+            : P(M, prm, bprm), ctx(bprm.context()), applied(0), enabled(true) {}
+
+        ~b200_cycle_graph() {
+            for (size_t i = 0; i < graphs.size(); ++i) b200_graph_destroy(graphs[i]);
+        }
+
+        template <class Vec1, class Vec2>
+        void apply(const Vec1 &rhs, Vec2 &&x) const {
+            if (!enabled) { P.apply(rhs, x); return; }
+
+            for (size_t i = 0; i < graphs.size(); ++i) {
+                int launched = 0;
+                AMGCL_CALL_B200(b200_graph_launch(ctx, graphs[i], &launched));
+                if (launched) return;
+            }
+
+            // the first application always runs directly: lazily allocated scratch must exist
+            // before anything is recorded
+            if (applied++ == 0) { P.apply(rhs, x); return; }
+            drop_stale();
+            if (graphs.size() >= max_graphs) { P.apply(rhs, x); return; }
+
+            int recording = 0;
+            AMGCL_CALL_B200(b200_graph_begin(ctx, &recording));
+            if (!recording) { P.apply(rhs, x); return; }
+            try {
+                P.apply(rhs, x);
+            } catch (...) {
+                // something in this preconditioner cannot be recorded (e.g. an inner product in
+                // a nested Krylov solver): restore the state and use the direct path from now on
+                b200_graph_abort(ctx);
+                enabled = false;
+                P.apply(rhs, x);
+                return;
+            }
+            b200_graph_t g = 0;
+            if (b200_graph_end(ctx, &g) != B200_OK) {     // state was rolled back
+                enabled = false;
+                P.apply(rhs, x);
+                return;
+            }
+            graphs.push_back(g);
+        }
+
+        const Precond& base() const { return P; }
+        Precond&       base()       { return P; }
+
+        std::shared_ptr<matrix> system_matrix_ptr() const { return P.system_matrix_ptr(); }
+        const matrix& system_matrix() const { return P.system_matrix(); }
+        size_t bytes() const { return backend::bytes(P); }
+
+        /// Recorded graphs, kernels per replay of the first one, replays over all of them.
+        void graph_stats(size_t &ngraphs, size_t &kernels, size_t &replays) const {
+            ngraphs = graphs.size(); kernels = 0; replays = 0;
+            for (size_t i = 0; i < graphs.size(); ++i) {
+                int64_t k = 0, n = 0, r = 0; int stale = 0;
+                b200_graph_info(graphs[i], &k, &n, &r, &stale);
+                if (i == 0) kernels = (size_t)k;
+                replays += (size_t)r;
+            }
+        }
+
+    private:
+        static const size_t max_graphs = 64;
+
+        void drop_stale() const {
+            size_t keep = 0;
+            for (size_t i = 0; i < graphs.size(); ++i) {
+                int stale = 0;
+                b200_graph_info(graphs[i], 0, 0, 0, &stale);
+                if (stale) b200_graph_destroy(graphs[i]);
+                else graphs[keep++] = graphs[i];
+            }
+            graphs.resize(keep);
+        }
+
+        Precond P;
+        b200_ctx_t ctx;
+        mutable size_t applied;
+        mutable bool enabled;
+        mutable std::vector<b200_graph_t> graphs;
+
+        friend std::ostream& operator<<(std::ostream &os, const b200_cycle_graph &p) {
+            return os << p.P;
+        }
+};
+
+} // namespace preconditioner
 } // namespace amgcl
 
 #endif

@@ -50,6 +50,7 @@ typedef struct b200_csr_s    *b200_csr_t;     /* device CSR matrix (+ row-block 
 typedef struct b200_vec_s    *b200_vec_t;     /* device FP64 vector                   */
 typedef struct b200_coarse_s *b200_coarse_t;  /* coarsest-level direct solver         */
 typedef struct b200_split_s  *b200_split_t;   /* host view of one rank's operator share */
+typedef struct b200_graph_s  *b200_graph_t;   /* recorded call sequence (CUDA graph)    */
 
 /* ---------------------------------------------------------------- context */
 
@@ -156,6 +157,10 @@ int b200_split_destroy(b200_split_t sp);
  *   "p2p"              multi-GPU: 1 = peer-memory exchange kernels (default), 0 = NCCL
  *   "pdl"              1 = programmatic dependent launch of the solve kernels (default;
  *                      environment variable B200_PDL overrides the default), 0 = plain launches
+ *   "cycle_graph"      1 = b200_graph_begin records (default; env B200_CYCLE_GRAPH), 0 = it
+ *                      reports "not recording" and existing graphs are not replayed
+ *   "graph_pdl"        1 = launches recorded into a graph keep the PDL attribute (default;
+ *                      env B200_GRAPH_PDL)
  *   "fuse_relax"       1 = single-pass fused smoother sweep (default), 0 = two kernels
  *   "zero_shortcut"    1 = skip the A-pass when x is known to be zero (default)
  * Unknown keys return B200_EINVAL. */
@@ -289,6 +294,36 @@ int b200_coarse_destroy(b200_coarse_t S);
 int b200_coarse_bytes(b200_coarse_t S, size_t *bytes);
 /* x = A^-1 rhs */
 int b200_coarse_solve(b200_ctx_t ctx, b200_coarse_t S, b200_vec_t rhs, b200_vec_t x);
+
+/* ---------------------------------------------------------------- recorded call sequences */
+
+/* CUDA-graph recording of a sequence of the calls above ("whole-cycle
+ * CUDA graph").  The reference issues the V-cycle (amg.hpp:514-553) as ~10 library calls per
+ * level from the host on every preconditioner application; between b200_graph_begin and
+ * b200_graph_end the same calls are recorded instead of executed, b200_graph_end runs them once
+ * and returns a graph that b200_graph_launch replays with a single launch.
+ *
+ * The library's host-side vector state (storage exchanged by b200_relax, pending lazy clears)
+ * is part of what was recorded: b200_graph_launch compares the current state of every vector
+ * the graph touches with the state at recording time and sets *launched = 0 WITHOUT doing
+ * anything when they differ (or when an object the graph refers to has been destroyed, an
+ * option or the stream changed, or profiling is on); the caller then records another graph or
+ * issues the calls directly.  Scalars (alpha, beta, omega) are baked in.
+ *
+ * While recording, host-synchronous and allocating calls (b200_dot, uploads / downloads,
+ * b200_ctx_sync, object creation / destruction) fail with B200_EINVAL; after any failure call
+ * b200_graph_abort, which drops the recording and restores the vector state of
+ * b200_graph_begin (nothing recorded has run).  *recording = 0 from b200_graph_begin means the
+ * context cannot record right now (profiling, multi-GPU context, legacy default stream, option
+ * "cycle_graph" = 0): issue the calls directly. */
+int b200_graph_begin(b200_ctx_t ctx, int *recording);
+int b200_graph_end(b200_ctx_t ctx, b200_graph_t *graph);     /* instantiate + run once */
+int b200_graph_abort(b200_ctx_t ctx);
+int b200_graph_launch(b200_ctx_t ctx, b200_graph_t graph, int *launched);
+/* kernels per replay, graph nodes (kernels + memsets + copies), replays so far, staleness */
+int b200_graph_info(b200_graph_t graph, int64_t *kernels, int64_t *nodes, int64_t *replays,
+                    int *stale);
+int b200_graph_destroy(b200_graph_t graph);
 
 #ifdef __cplusplus
 }

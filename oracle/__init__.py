@@ -214,7 +214,7 @@ def c():
 # ---------------------------------------------------------------------------
 # the real reference (AMGCL builtin backend)
 # ---------------------------------------------------------------------------
-RELAX = {"damped_jacobi": 0, "spai0": 1, "chebyshev": 2}
+RELAX = {"damped_jacobi": 0, "spai0": 1, "chebyshev": 2, "ilu0": 3}
 KRYLOV = {"cg": 0, "bicgstab": 1, "gmres": 2, "bicgstabl": 3}
 
 
@@ -267,7 +267,74 @@ class _Ref:
         R.ref_vmul.restype = None
         R.ref_relax_diag.argtypes = [_i64, _vp, _vp, _vp, _c.c_int, _vp]
         R.ref_relax_diag.restype = None
+        R.ref_mm_read_crs.argtypes = [_c.c_char_p, _i64, _i64, _P(_i64), _P(_i64), _P(_i64), _vp, _vp, _vp]
+        R.ref_mm_read_dense.argtypes = [_c.c_char_p, _i64, _i64, _P(_i64), _P(_i64), _vp]
+        R.ref_mm_write_crs.argtypes = [_c.c_char_p, _i64, _i64, _vp, _vp, _vp]
+        R.ref_mm_write_dense.argtypes = [_c.c_char_p, _vp, _i64, _i64]
+        R.ref_bin_read_crs.argtypes = [_c.c_char_p, _i64, _i64, _P(_i64), _P(_i64), _vp, _vp, _vp]
+        R.ref_bin_write_crs.argtypes = [_c.c_char_p, _i64, _vp, _vp, _vp]
+        R.ref_bin_read_dense.argtypes = [_c.c_char_p, _i64, _i64, _P(_i64), _P(_i64), _vp]
         self.R = R
+
+    # file formats (io/mm.hpp, io/binary.hpp) -------------------------------
+    def _io_fail(self, what):
+        raise RuntimeError(what + ": " + self.R.ref_last_error().decode(errors="replace"))
+
+    def mm_read_crs(self, path, rows=(-1, -1)):
+        n, m, nnz = _i64(), _i64(), _i64()
+        b = str(path).encode()
+        if self.R.ref_mm_read_crs(b, rows[0], rows[1], _c.byref(n), _c.byref(m), _c.byref(nnz), None, None, None):
+            self._io_fail("mm_read_crs")
+        ptr, col, val = np.empty(n.value + 1, np.int64), np.empty(nnz.value, np.int64), np.empty(nnz.value)
+        if self.R.ref_mm_read_crs(b, rows[0], rows[1], _c.byref(n), _c.byref(m), _c.byref(nnz), _p(ptr), _p(col), _p(val)):
+            self._io_fail("mm_read_crs")
+        return n.value, m.value, ptr, col, val
+
+    def mm_read_dense(self, path, rows=(-1, -1)):
+        n, m = _i64(), _i64()
+        b = str(path).encode()
+        if self.R.ref_mm_read_dense(b, rows[0], rows[1], _c.byref(n), _c.byref(m), None):
+            self._io_fail("mm_read_dense")
+        out = np.empty((n.value, m.value))
+        if self.R.ref_mm_read_dense(b, rows[0], rows[1], _c.byref(n), _c.byref(m), _p(out)):
+            self._io_fail("mm_read_dense")
+        return out
+
+    def mm_write_crs(self, path, ncols, ptr, col, val):
+        ptr, col, val = _arr(ptr, np.int64), _arr(col, np.int64), _arr(val, np.float64)
+        if self.R.ref_mm_write_crs(str(path).encode(), ptr.size - 1, ncols, _p(ptr), _p(col), _p(val)):
+            self._io_fail("mm_write_crs")
+
+    def mm_write_dense(self, path, a):
+        a = _arr(a, np.float64)
+        a2 = a.reshape(a.shape[0], -1)
+        if self.R.ref_mm_write_dense(str(path).encode(), _p(a2), a2.shape[0], a2.shape[1]):
+            self._io_fail("mm_write_dense")
+
+    def bin_read_crs(self, path, rows=(-1, -1)):
+        n, nnz = _i64(), _i64()
+        b = str(path).encode()
+        if self.R.ref_bin_read_crs(b, rows[0], rows[1], _c.byref(n), _c.byref(nnz), None, None, None):
+            self._io_fail("bin_read_crs")
+        ptr, col, val = np.empty(n.value + 1, np.int64), np.empty(nnz.value, np.int64), np.empty(nnz.value)
+        if self.R.ref_bin_read_crs(b, rows[0], rows[1], _c.byref(n), _c.byref(nnz), _p(ptr), _p(col), _p(val)):
+            self._io_fail("bin_read_crs")
+        return n.value, ptr, col, val
+
+    def bin_write_crs(self, path, ptr, col, val):
+        ptr, col, val = _arr(ptr, np.int64), _arr(col, np.int64), _arr(val, np.float64)
+        if self.R.ref_bin_write_crs(str(path).encode(), ptr.size - 1, _p(ptr), _p(col), _p(val)):
+            self._io_fail("bin_write_crs")
+
+    def bin_read_dense(self, path, rows=(-1, -1)):
+        n, m = _i64(), _i64()
+        b = str(path).encode()
+        if self.R.ref_bin_read_dense(b, rows[0], rows[1], _c.byref(n), _c.byref(m), None):
+            self._io_fail("bin_read_dense")
+        out = np.empty((n.value, m.value))
+        if self.R.ref_bin_read_dense(b, rows[0], rows[1], _c.byref(n), _c.byref(m), _p(out)):
+            self._io_fail("bin_read_dense")
+        return out
 
     @property
     def threads(self):

@@ -32,9 +32,12 @@
 #include <amgcl/solver/cg.hpp>
 #include <amgcl/solver/bicgstab.hpp>
 #include <amgcl/relaxation/chebyshev.hpp>
+#include <amgcl/relaxation/ilu0.hpp>
 #include <amgcl/solver/gmres.hpp>
 #include <amgcl/solver/bicgstabl.hpp>
 #include <amgcl/solver/skyline_lu.hpp>
+#include <amgcl/io/mm.hpp>
+#include <amgcl/io/binary.hpp>
 
 namespace {
 
@@ -205,6 +208,12 @@ int ref_create(int64_t n, const int64_t *ptr, const int64_t *col, const double *
             h->solver.reset(new SolverImpl<relaxation::damped_jacobi, solver::gmres>(n, ptr, col, val, tol, maxiter, coarse_enough, bprm));
         else if (relax == 1 && krylov == 3)
             h->solver.reset(new SolverImpl<relaxation::spai0, solver::bicgstabl>(n, ptr, col, val, tol, maxiter, coarse_enough, bprm));
+        // ILU(0) smoother: on a non-builtin backend (RecBackend here, backend::cuda / b200 on the
+        // GPU) its triangular solves are damped Jacobi sweeps (relaxation/detail/ilu_solve.hpp:97-113)
+        else if (relax == 3 && krylov == 1)
+            h->solver.reset(new SolverImpl<relaxation::ilu0, solver::bicgstab>(n, ptr, col, val, tol, maxiter, coarse_enough, bprm));
+        else if (relax == 3 && krylov == 0)
+            h->solver.reset(new SolverImpl<relaxation::ilu0, solver::cg>(n, ptr, col, val, tol, maxiter, coarse_enough, bprm));
         else { g_error = "unknown relax/krylov selector"; return -1; }
         *out = h.release();
         return 0;
@@ -385,6 +394,103 @@ void ref_relax_diag(int64_t n, const int64_t *ptr, const int64_t *col, const dou
         amgcl::relaxation::spai0<Builtin> S(A, amgcl::relaxation::spai0<Builtin>::params(), Builtin::params());
         std::memcpy(d, S.M->data(), (size_t)n * sizeof(double));
     }
+}
+
+// ---- the reference's file readers / writers (io/mm.hpp, io/binary.hpp) --------------------
+// Two-phase reads: call with null arrays for the sizes, then with buffers.
+int ref_mm_read_crs(const char *path, int64_t row_beg, int64_t row_end, int64_t *rows, int64_t *cols,
+                    int64_t *nnz, int64_t *ptr, int64_t *col, double *val)
+{
+    try {
+        amgcl::io::mm_reader mm(path);
+        if (!mm.is_sparse()) { g_error = "not a sparse file"; return -1; }
+        std::vector<ptrdiff_t> p, c;
+        std::vector<double> v;
+        size_t n, m;
+        std::tie(n, m) = mm(p, c, v, row_beg, row_end);
+        *rows = (int64_t)n; *cols = (int64_t)m; *nnz = (int64_t)c.size();
+        if (ptr) std::copy(p.begin(), p.end(), ptr);
+        if (col) std::copy(c.begin(), c.end(), col);
+        if (val) std::copy(v.begin(), v.end(), val);
+        return 0;
+    } catch (const std::exception &e) { g_error = e.what(); return -1; }
+}
+
+int ref_mm_read_dense(const char *path, int64_t row_beg, int64_t row_end, int64_t *rows, int64_t *cols,
+                      double *data)
+{
+    try {
+        amgcl::io::mm_reader mm(path);
+        if (mm.is_sparse()) { g_error = "not a dense file"; return -1; }
+        std::vector<double> v;
+        size_t n, m;
+        std::tie(n, m) = mm(v, row_beg, row_end);
+        *rows = (int64_t)n; *cols = (int64_t)m;
+        if (data) std::copy(v.begin(), v.end(), data);
+        return 0;
+    } catch (const std::exception &e) { g_error = e.what(); return -1; }
+}
+
+int ref_mm_write_crs(const char *path, int64_t n, int64_t m, const int64_t *ptr, const int64_t *col,
+                     const double *val)
+{
+    try {
+        HostMatrix A = view(n, m, ptr, col, val);
+        amgcl::io::mm_write(path, A);
+        return 0;
+    } catch (const std::exception &e) { g_error = e.what(); return -1; }
+}
+
+int ref_mm_write_dense(const char *path, const double *data, int64_t rows, int64_t cols)
+{
+    try {
+        amgcl::io::mm_write(path, data, (size_t)rows, (size_t)cols);
+        return 0;
+    } catch (const std::exception &e) { g_error = e.what(); return -1; }
+}
+
+int ref_bin_read_crs(const char *path, int64_t row_beg, int64_t row_end, int64_t *rows, int64_t *nnz,
+                     int64_t *ptr, int64_t *col, double *val)
+{
+    try {
+        size_t n;
+        std::vector<ptrdiff_t> p, c;
+        std::vector<double> v;
+        amgcl::io::read_crs(path, n, p, c, v, row_beg, row_end);
+        *rows = (int64_t)p.size() - 1; *nnz = (int64_t)c.size();
+        if (ptr) std::copy(p.begin(), p.end(), ptr);
+        if (col) std::copy(c.begin(), c.end(), col);
+        if (val) std::copy(v.begin(), v.end(), val);
+        return 0;
+    } catch (const std::exception &e) { g_error = e.what(); return -1; }
+}
+
+// the writer of examples/mm2bin.cpp:22-31 / :37-44
+int ref_bin_write_crs(const char *path, int64_t n, const int64_t *ptr, const int64_t *col, const double *val)
+{
+    try {
+        std::ofstream f(path, std::ios::binary);
+        size_t rows = (size_t)n;
+        std::vector<ptrdiff_t> p(ptr, ptr + n + 1), c(col, col + ptr[n]);
+        std::vector<double> v(val, val + ptr[n]);
+        bool ok = amgcl::io::write(f, rows) && amgcl::io::write(f, p) && amgcl::io::write(f, c) &&
+                  amgcl::io::write(f, v);
+        if (!ok) { g_error = "File I/O error"; return -1; }
+        return 0;
+    } catch (const std::exception &e) { g_error = e.what(); return -1; }
+}
+
+int ref_bin_read_dense(const char *path, int64_t row_beg, int64_t row_end, int64_t *rows, int64_t *cols,
+                       double *data)
+{
+    try {
+        size_t n, m;
+        std::vector<double> v;
+        amgcl::io::read_dense(path, n, m, v, row_beg, row_end);
+        *rows = (int64_t)(m ? v.size() / m : 0); *cols = (int64_t)m;
+        if (data) std::copy(v.begin(), v.end(), data);
+        return 0;
+    } catch (const std::exception &e) { g_error = e.what(); return -1; }
 }
 
 } // extern "C"

@@ -111,7 +111,8 @@ def main():
     known["primitive_only"] = []
     for n in (16, 32, 48):
         ptr, col, val, rhs = poisson3d(n)
-        for relax, krylov in (("chebyshev", "cg"), ("damped_jacobi", "gmres"), ("spai0", "bicgstabl")):
+        for relax, krylov in (("chebyshev", "cg"), ("damped_jacobi", "gmres"), ("spai0", "bicgstabl"),
+                              ("ilu0", "bicgstab"), ("ilu0", "cg")):
             S = oracle.RefSolver(ptr, col, val, relax, krylov)
             x, iters, resid = S.solve(rhs)
             known["primitive_only"].append({
@@ -142,6 +143,12 @@ def main():
     ]
     with open(os.path.join(HERE, "known_answers.json"), "w") as f:
         json.dump(known, f, indent=1)
+    # files written by the reference's own writers (io/mm.hpp:349-420, io/binary.hpp:158-168)
+    R = oracle.ref()
+    ptr, col, val, rhs = poisson3d(5)
+    R.mm_write_crs(os.path.join(HERE, "io_poisson5.mtx"), 125, ptr, col, val)
+    R.bin_write_crs(os.path.join(HERE, "io_poisson5.bin"), ptr, col, val)
+    R.mm_write_dense(os.path.join(HERE, "io_vec5.mtx"), np.sin(np.arange(125.0)))
 
 
 if __name__ == "__main__":

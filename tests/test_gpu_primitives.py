@@ -409,3 +409,110 @@ def test_wrapping_torch_memory(ctx):
         assert abs(ctx.dot(vx, vx) - float((tx * tx).sum().item())) < 1e-9
     finally:
         ctx.set_stream(None)
+
+
+# ---------------------------------------------------------------------------
+# recorded call sequences (b200_graph_*)
+# ---------------------------------------------------------------------------
+def _two_grid_sequence(ctx, A, vr, vx, vt, vd, vy, omega):
+    """clear -> sweep (x == 0 shortcut) -> sweep (storage swap) -> residual -> axpby: the
+    pieces of a V-cycle that carry host-side state."""
+    ctx.clear(vx)
+    ctx.relax(A, vr, vx, vt, vd, omega)
+    ctx.relax(A, vr, vx, vt, vd, omega)
+    ctx.residual(vr, A, vx, vy)
+    ctx.axpby(0.5, vx, 2.0, vy)
+
+
+def test_graph_replay_matches_direct_execution(ctx, golden):
+    """A recorded sequence replays bit-identically, only from the vector state it was
+    recorded in, and leaves the same state behind as the direct calls."""
+    lv = golden.levels[0]
+    ptr, col, val = lv["A"]
+    n = ptr.size - 1
+    rng = np.random.default_rng(11)
+    A = ctx.csr(n, n, ptr, col, val)
+    rhs = rng.uniform(-1, 1, n)
+    vr, vx, vt, vd, vy = ctx.vector(rhs), ctx.vector(n), ctx.vector(n), ctx.vector(lv["diag"]), ctx.vector(n)
+
+    _two_grid_sequence(ctx, A, vr, vx, vt, vd, vy, golden.omega)        # direct
+    want_x, want_y = vx.numpy(), vy.numpy()
+
+    launches0 = ctx.launches
+    assert ctx.graph_begin()
+    _two_grid_sequence(ctx, A, vr, vx, vt, vd, vy, golden.omega)        # recorded, runs at graph_end
+    g = ctx.graph_end()
+    per_run = ctx.launches - launches0
+    assert np.array_equal(vx.numpy(), want_x) and np.array_equal(vy.numpy(), want_y)
+    info = g.info()
+    assert info["kernels"] == per_run >= 4 and info["nodes"] >= info["kernels"] and not info["stale"]
+
+    # the sequence swapped x <-> tmp once: the state differs from the recorded one, so the
+    # graph must refuse; one direct run swaps back, then it replays
+    assert not g.launch()
+    assert np.array_equal(vx.numpy(), want_x)
+    _two_grid_sequence(ctx, A, vr, vx, vt, vd, vy, golden.omega)
+    for _ in range(2):
+        vy.upload(np.full(n, np.nan))
+        launches1 = ctx.launches
+        assert g.launch()
+        assert ctx.launches - launches1 == per_run
+        assert np.array_equal(vx.numpy(), want_x) and np.array_equal(vy.numpy(), want_y)
+        assert not g.launch()                                          # parity flipped again
+        _two_grid_sequence(ctx, A, vr, vx, vt, vd, vy, golden.omega)
+    assert g.info()["replays"] == 2
+
+    # a new right-hand side flows through the replay (pointers are baked in, data is not)
+    rhs2 = rng.uniform(-1, 1, n)
+    vr.upload(rhs2)
+    assert g.launch()
+    got_x, got_y = vx.numpy(), vy.numpy()
+    _two_grid_sequence(ctx, A, vr, vx, vt, vd, vy, golden.omega)        # parity back
+    _two_grid_sequence(ctx, A, vr, vx, vt, vd, vy, golden.omega)        # same state as the replay had
+    assert np.array_equal(vx.numpy(), got_x) and np.array_equal(vy.numpy(), got_y)
+
+    # option changes and destroyed operands make the graph stale
+    ctx.set_option("fuse_relax", 0)
+    try:
+        assert g.info()["stale"] and not g.launch()
+    finally:
+        ctx.set_option("fuse_relax", 1)
+    g.close()
+
+
+def test_graph_recording_rejects_host_synchronous_calls_and_aborts_cleanly(ctx, golden):
+    lv = golden.levels[0]
+    ptr, col, val = lv["A"]
+    n = ptr.size - 1
+    rng = np.random.default_rng(12)
+    A = ctx.csr(n, n, ptr, col, val)
+    rhs, x0 = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
+    vr, vx, vt, vd = ctx.vector(rhs), ctx.vector(x0), ctx.vector(n), ctx.vector(lv["diag"])
+    launches0 = ctx.launches
+    assert ctx.graph_begin()
+    ctx.relax(A, vr, vx, vt, vd, golden.omega)          # swaps storage on the host side
+    ctx.clear(vt)
+    for bad in (lambda: ctx.dot(vr, vx), lambda: vx.numpy(), lambda: ctx.vector(n), lambda: ctx.sync()):
+        with pytest.raises(ab.B200Error, match="recorded"):
+            bad()
+    with pytest.raises(ab.B200Error):
+        ctx.graph_begin()                               # no nesting
+    ctx.graph_abort()
+    assert ctx.launches == launches0
+    # nothing ran and the state is the one before graph_begin
+    assert np.array_equal(vx.numpy(), x0)
+    ctx.relax(A, vr, vx, vt, vd, golden.omega)
+    want = oracle.c().relax(lv["A"], rhs, x0, lv["diag"], golden.omega)
+    assert rel_err(vx.numpy(), want) < TOL_PRIMITIVE
+
+    # contexts that cannot record say so instead of failing
+    ctx.set_option("cycle_graph", 0)
+    try:
+        assert not ctx.graph_begin()
+    finally:
+        ctx.set_option("cycle_graph", 1)
+    ctx.profile_begin()
+    try:
+        assert not ctx.graph_begin()
+    finally:
+        ctx.profile_end()

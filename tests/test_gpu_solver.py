@@ -137,6 +137,44 @@ def test_dependent_launch_is_bit_transparent(ctx):
         assert it == it0 and res == res0 and np.array_equal(x, x0), (p, r)
 
 
+@pytest.mark.parametrize("relax,krylov,precision", [
+    ("damped_jacobi", "cg", "f64"), ("spai0", "bicgstab", "f64"), ("spai0", "cg", "f64"),
+    ("damped_jacobi", "bicgstab", "f64"), ("damped_jacobi", "cg", "mixed"),
+    ("spai0", "bicgstab", "mixed"), ("damped_jacobi", "gmres", "f64")])
+def test_cycle_graph_wrapper_is_bit_transparent(ctx, relax, krylov, precision):
+    """amgcl::preconditioner::b200_cycle_graph<amg<...>> (every V-cycle one CUDA graph launch)
+    gives the very same iterates as the unwrapped hierarchy: same kernels, same arguments."""
+    ptr, col, val, rhs = ab.poisson3d(40)
+    rng = np.random.default_rng(5)
+    rhs2 = rng.uniform(-1, 1, rhs.size)
+    plain = ab.DropinSolver(ptr, col, val, relax, krylov, ctx=ctx, precision=precision)
+    graphed = ab.DropinSolver(ptr, col, val, relax, krylov, ctx=ctx, precision=precision, graph=True)
+    assert plain.graph_stats() == (0, 0, 0)
+    for b in (rhs, rhs2, rhs):
+        l0 = ctx.launches
+        x0, it0, r0 = plain.solve(b)
+        l1 = ctx.launches
+        x1, it1, r1 = graphed.solve(b)
+        l2 = ctx.launches
+        assert (it1, r1) == (it0, r0) and np.array_equal(x1, x0)
+        assert l2 - l1 == l1 - l0                   # replays count the kernels they contain
+    ngraphs, kernels, replays = graphed.graph_stats()
+    assert 1 <= ngraphs <= 64 and kernels > 20
+    if krylov != "gmres":                           # GMRES permutes its basis storage: few hits
+        assert replays >= it0
+    # the preconditioner alone, and the wrapper switched off at run time
+    f = rng.uniform(-1, 1, rhs.size)
+    assert np.array_equal(graphed.apply_precond(f), plain.apply_precond(f))
+    ctx.set_option("cycle_graph", 0)
+    try:
+        x2, it2, r2 = graphed.solve(rhs)
+    finally:
+        ctx.set_option("cycle_graph", 1)
+    assert (it2, r2) == (it0, r0) and np.array_equal(x2, x0)
+    plain.close()
+    graphed.close()
+
+
 def test_large_problem_size_independent_properties(ctx):
     """128^3 (2.1M rows): survey iteration count, true residual, linearity of the V-cycle."""
     n = 128
@@ -158,11 +196,14 @@ def test_large_problem_size_independent_properties(ctx):
 
 @pytest.mark.parametrize("n", [16, 32, 48])
 @pytest.mark.parametrize("relax,krylov", [("chebyshev", "cg"), ("damped_jacobi", "gmres"),
-                                          ("spai0", "bicgstabl")])
+                                          ("spai0", "bicgstabl"), ("ilu0", "bicgstab"), ("ilu0", "cg")])
 def test_components_that_only_use_the_primitives(ctx, known_answers, n, relax, krylov):
     """AMGCL's Chebyshev smoother (relaxation/chebyshev.hpp), GMRES
-    (solver/gmres.hpp, via lin_comb -> axpby/axpbypcz) and BiCGStab(L) run unmodified on the
-    backend through spmv / residual / vmul / axpby / axpbypcz / inner_product alone."""
+    (solver/gmres.hpp, via lin_comb -> axpby/axpbypcz), BiCGStab(L) and the ILU(0) smoother
+    (relaxation/ilu0.hpp; triangular solves as damped Jacobi sweeps,
+    relaxation/detail/ilu_solve.hpp:97-113 -- the goldens come from the same generic code
+    path on a non-builtin CPU backend) run unmodified on the backend through spmv / residual /
+    vmul / axpby / axpbypcz / inner_product alone."""
     case = [c for c in known_answers["primitive_only"]
             if (c["n"], c["relax"], c["krylov"]) == (n, relax, krylov)][0]
     ptr, col, val, rhs = ab.poisson3d(n)
