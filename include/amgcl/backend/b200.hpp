@@ -624,16 +624,21 @@ class b200_cycle_graph {
             : P(M, prm, bprm), ctx(bprm.context()), applied(0), enabled(true) {}
 
         ~b200_cycle_graph() {
-            for (size_t i = 0; i < graphs.size(); ++i) b200_graph_destroy(graphs[i]);
+            for (size_t i = 0; i < graphs.size(); ++i) b200_graph_destroy(graphs[i].g);
         }
 
         template <class Vec1, class Vec2>
         void apply(const Vec1 &rhs, Vec2 &&x) const {
             if (!enabled) { P.apply(rhs, x); return; }
 
+            // a graph replays the recorded calls on the recorded handles: only graphs recorded
+            // for this very (rhs, x) pair are candidates (BiCGStab and GMRES apply the
+            // preconditioner to several pairs)
+            const b200_vec_t hr = rhs.handle(), hx = x.handle();
             for (size_t i = 0; i < graphs.size(); ++i) {
+                if (graphs[i].rhs != hr || graphs[i].x != hx) continue;
                 int launched = 0;
-                AMGCL_CALL_B200(b200_graph_launch(ctx, graphs[i], &launched));
+                AMGCL_CALL_B200(b200_graph_launch(ctx, graphs[i].g, &launched));
                 if (launched) return;
             }
 
@@ -662,7 +667,8 @@ class b200_cycle_graph {
                 P.apply(rhs, x);
                 return;
             }
-            graphs.push_back(g);
+            entry e = {hr, hx, g};
+            graphs.push_back(e);
         }
 
         const Precond& base() const { return P; }
@@ -677,7 +683,7 @@ class b200_cycle_graph {
             ngraphs = graphs.size(); kernels = 0; replays = 0;
             for (size_t i = 0; i < graphs.size(); ++i) {
                 int64_t k = 0, n = 0, r = 0; int stale = 0;
-                b200_graph_info(graphs[i], &k, &n, &r, &stale);
+                b200_graph_info(graphs[i].g, &k, &n, &r, &stale);
                 if (i == 0) kernels = (size_t)k;
                 replays += (size_t)r;
             }
@@ -690,8 +696,8 @@ class b200_cycle_graph {
             size_t keep = 0;
             for (size_t i = 0; i < graphs.size(); ++i) {
                 int stale = 0;
-                b200_graph_info(graphs[i], 0, 0, 0, &stale);
-                if (stale) b200_graph_destroy(graphs[i]);
+                b200_graph_info(graphs[i].g, 0, 0, 0, &stale);
+                if (stale) b200_graph_destroy(graphs[i].g);
                 else graphs[keep++] = graphs[i];
             }
             graphs.resize(keep);
@@ -701,7 +707,8 @@ class b200_cycle_graph {
         b200_ctx_t ctx;
         mutable size_t applied;
         mutable bool enabled;
-        mutable std::vector<b200_graph_t> graphs;
+        struct entry { b200_vec_t rhs, x; b200_graph_t g; };
+        mutable std::vector<entry> graphs;
 
         friend std::ostream& operator<<(std::ostream &os, const b200_cycle_graph &p) {
             return os << p.P;

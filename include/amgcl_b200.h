@@ -308,7 +308,9 @@ int b200_coarse_solve(b200_ctx_t ctx, b200_coarse_t S, b200_vec_t rhs, b200_vec_
  * the graph touches with the state at recording time and sets *launched = 0 WITHOUT doing
  * anything when they differ (or when an object the graph refers to has been destroyed, an
  * option or the stream changed, or profiling is on); the caller then records another graph or
- * issues the calls directly.  Scalars (alpha, beta, omega) are baked in.
+ * issues the calls directly.  Scalars (alpha, beta, omega) and the handles passed to the recorded
+ * calls are baked in: a graph recorded for apply(r, s) computes on r and s, so a caller that
+ * applies the same sequence to several vector pairs keeps one graph per pair.
  *
  * While recording, host-synchronous and allocating calls (b200_dot, uploads / downloads,
  * b200_ctx_sync, object creation / destruction) fail with B200_EINVAL; after any failure call

@@ -159,7 +159,7 @@ def test_cycle_graph_wrapper_is_bit_transparent(ctx, relax, krylov, precision):
         assert (it1, r1) == (it0, r0) and np.array_equal(x1, x0)
         assert l2 - l1 == l1 - l0                   # replays count the kernels they contain
     ngraphs, kernels, replays = graphed.graph_stats()
-    assert 1 <= ngraphs <= 64 and kernels > 20
+    assert 1 <= ngraphs <= 64 and kernels >= 6
     if krylov != "gmres":                           # GMRES permutes its basis storage: few hits
         assert replays >= it0
     # the preconditioner alone, and the wrapper switched off at run time
