@@ -657,11 +657,14 @@ def unstructured3d(n, k=24, seed=0, order="morton"):
             np.ascontiguousarray(A.data, dtype=np.float64), rhs)
 
 
-def poisson3d(n, dtype_index=np.int64):
+def poisson3d(n, dtype_index=np.int64, anisotropy=1.0, convection=0.0):
     """3-D 7-point Poisson problem on an n^3 grid, natural ordering (i fastest),
-    Dirichlet by truncation, diag 6, off-diag -1, rhs == 1: the same system the
-    reference's tests generate (tests/sample_problem.hpp:11-82, anisotropy 1),
-    built here with numpy.  Returns (ptr, col, val, rhs)."""
+    Dirichlet by truncation, rhs == 1: the same system the reference's tests generate
+    (tests/sample_problem.hpp:11-82; hx = 1, hy = anisotropy, hz = anisotropy^2, so the
+    default is diag 6, off-diag -1), built here with numpy.  convection > 0 adds a first-order
+    upwind transport term with velocity (c, c/2, c/4) -- not in the reference's generator --
+    which makes the matrix non-symmetric (for the BiCGStab / GMRES parity cases).
+    Returns (ptr, col, val, rhs)."""
     n = int(n)
     n3 = n * n * n
     idx = np.arange(n3, dtype=np.int64)
@@ -683,7 +686,15 @@ def poisson3d(n, dtype_index=np.int64):
     ptr = np.zeros(n3 + 1, dtype=np.int64)
     np.cumsum(counts, out=ptr[1:])
     cols = (idx[:, None] + offs[None, :])[mask]
-    vals = np.broadcast_to(np.array([-1.0, -1.0, -1.0, 6.0, -1.0, -1.0, -1.0]), (n3, 7))[mask]
+    hx = 1.0
+    hy = hx * float(anisotropy)
+    hz = hy * float(anisotropy)
+    ax, ay, az = 1.0 / (hx * hx), 1.0 / (hy * hy), 1.0 / (hz * hz)
+    c = float(convection)
+    stencil = np.array([-az - c / 4, -ay - c / 2, -ax - c,
+                        (2 / (hx * hx) + 2 / (hy * hy) + 2 / (hz * hz)) + (c + c / 2 + c / 4),
+                        -ax, -ay, -az])
+    vals = np.broadcast_to(stencil, (n3, 7))[mask]
     rhs = np.ones(n3)
     return (ptr.astype(dtype_index), np.ascontiguousarray(cols, dtype=dtype_index),
             np.ascontiguousarray(vals, dtype=np.float64), rhs)

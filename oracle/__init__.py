@@ -274,7 +274,17 @@ class _Ref:
         R.ref_bin_read_crs.argtypes = [_c.c_char_p, _i64, _i64, _P(_i64), _P(_i64), _vp, _vp, _vp]
         R.ref_bin_write_crs.argtypes = [_c.c_char_p, _i64, _vp, _vp, _vp]
         R.ref_bin_read_dense.argtypes = [_c.c_char_p, _i64, _i64, _P(_i64), _P(_i64), _vp]
+        R.ref_sample_problem.argtypes = [_i64, _dbl, _vp, _vp, _vp, _vp]
+        R.ref_sample_problem.restype = _i64
         self.R = R
+
+    def sample_problem(self, n, anisotropy=1.0):
+        """tests/sample_problem.hpp:11-82 -> (ptr, col, val, rhs)."""
+        nnz = self.R.ref_sample_problem(n, anisotropy, None, None, None, None)
+        ptr, col = np.empty(n ** 3 + 1, np.int64), np.empty(nnz, np.int64)
+        val, rhs = np.empty(nnz), np.empty(n ** 3)
+        self.R.ref_sample_problem(n, anisotropy, _p(ptr), _p(col), _p(val), _p(rhs))
+        return ptr, col, val, rhs
 
     # file formats (io/mm.hpp, io/binary.hpp) -------------------------------
     def _io_fail(self, what):

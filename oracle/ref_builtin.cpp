@@ -38,6 +38,7 @@
 #include <amgcl/solver/skyline_lu.hpp>
 #include <amgcl/io/mm.hpp>
 #include <amgcl/io/binary.hpp>
+#include "tests/sample_problem.hpp"
 
 namespace {
 
@@ -491,6 +492,19 @@ int ref_bin_read_dense(const char *path, int64_t row_beg, int64_t row_end, int64
         if (data) std::copy(v.begin(), v.end(), data);
         return 0;
     } catch (const std::exception &e) { g_error = e.what(); return -1; }
+}
+
+// the reference's own test-matrix generator (tests/sample_problem.hpp:11-82); two-phase
+int64_t ref_sample_problem(int64_t n, double anisotropy, int64_t *ptr, int64_t *col, double *val, double *rhs)
+{
+    std::vector<double> v, f;
+    std::vector<int64_t> c, p;
+    sample_problem((ptrdiff_t)n, v, c, p, f, anisotropy);
+    if (ptr) std::copy(p.begin(), p.end(), ptr);
+    if (col) std::copy(c.begin(), c.end(), col);
+    if (val) std::copy(v.begin(), v.end(), val);
+    if (rhs) std::copy(f.begin(), f.end(), rhs);
+    return (int64_t)c.size();
 }
 
 } // extern "C"

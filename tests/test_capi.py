@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 import amgcl_b200 as ab
+import oracle
 from amgcl_b200 import build
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -154,6 +155,26 @@ def test_poisson_generator_matches_reference_counts():
     ptr, col, val, _ = ab.poisson3d(6)
     A = sp.csr_matrix((val, col, ptr))
     assert abs(A - A.T).max() == 0
+
+
+@pytest.mark.skipif(not oracle.have_ref(), reason="reference build (oracle/_ref) not available")
+def test_poisson_generator_equals_the_reference_generator():
+    """bit-for-bit against tests/sample_problem.hpp compiled from the reference, including
+    its anisotropy parameter."""
+    R = oracle.ref()
+    for n, a in ((1, 1.0), (4, 1.0), (7, 0.5), (6, 2.0), (9, 0.1)):
+        want = R.sample_problem(n, a)
+        got = ab.poisson3d(n, anisotropy=a)
+        assert all(np.array_equal(g, w) for g, w in zip(got, want)), (n, a)
+    # the transport term (not in the reference's generator) keeps the sparsity pattern and
+    # an M-matrix, and breaks symmetry
+    ptr, col, val, _ = ab.poisson3d(5, convection=0.7)
+    p0, c0, v0, _ = ab.poisson3d(5)
+    assert np.array_equal(ptr, p0) and np.array_equal(col, c0)
+    import scipy.sparse as sp
+    A = sp.csr_matrix((val, col, ptr))
+    assert abs(A - A.T).max() > 0 and np.all(A.diagonal() > 0) and (A - sp.diags(A.diagonal())).max() <= 0
+    assert np.all(np.asarray(A.sum(axis=1)).ravel() >= -1e-12)
 
 
 def test_product_code_never_touches_the_oracle():

@@ -76,6 +76,35 @@ def test_dropin_vs_live_reference_random_rhs(ctx, relax, krylov):
     R.close()
 
 
+@pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not shipped")
+@pytest.mark.parametrize("anisotropy,convection,relax,krylov", [
+    (0.5, 0.0, "damped_jacobi", "cg"), (0.5, 0.0, "spai0", "bicgstab"),
+    (1.0, 0.7, "spai0", "bicgstab"), (1.0, 0.7, "damped_jacobi", "gmres"),
+    (2.0, 0.3, "spai0", "bicgstab")])
+def test_anisotropic_and_nonsymmetric_systems_vs_live_reference(ctx, anisotropy, convection, relax, krylov):
+    """tests/sample_problem.hpp's anisotropy parameter (different strength-of-connection
+    pattern, hence different aggregates and coarse stencils) and a non-symmetric
+    convection-diffusion operator: hierarchy shape, iteration count, residual and solution
+    against the reference running on the same host."""
+    n = 32
+    ptr, col, val, rhs = ab.poisson3d(n, anisotropy=anisotropy, convection=convection)
+    R = oracle.RefSolver(ptr, col, val, relax, krylov)
+    S = ab.DropinSolver(ptr, col, val, relax, krylov, ctx=ctx)
+    xr, itr, resr = R.solve(rhs)
+    xg, itg, resg = S.solve(rhs)
+    assert itg == itr
+    tol = 1e-4 if krylov == "bicgstab" else TOL_RESID_REL      # BiCGStab amplifies rounding
+    assert abs(resg - resr) <= tol * resr
+    assert rel_err(xg, xr) < TOL_SOLUTION
+    true_res = np.linalg.norm(rhs - oracle.c().spmv(1.0, (ptr, col, val), xg, 0.0, np.zeros_like(rhs)))
+    assert true_res <= 2e-8 * np.linalg.norm(rhs)
+    rng = np.random.default_rng(3)
+    f = rng.uniform(-1, 1, rhs.size)
+    assert rel_err(S.apply_precond(f), R.apply_precond(f)) < 1e-10
+    S.close()
+    R.close()
+
+
 def test_zero_rhs(ctx):
     ptr, col, val, rhs = ab.poisson3d(12)
     S = ab.DropinSolver(ptr, col, val, ctx=ctx)
