@@ -5,6 +5,8 @@
                            instantiated on backend::b200 (g++; needs the AMGCL
                            headers, i.e. only buildable where /root/reference or
                            $AMGCL_ROOT exists -- the prebuilt .so travels to the GPU box)
+  poisson_b200             examples/poisson_b200.cpp: the reference tutorial program with the
+                           backend typedef switched (plain g++, links libamgcl_b200.so)
 """
 import os
 import shutil
@@ -19,6 +21,8 @@ INCLUDE = os.path.join(ROOT, "include")
 
 LIB_CUDA = os.path.join(LIBDIR, "libamgcl_b200.so")
 LIB_DROPIN = os.path.join(LIBDIR, "libamgcl_b200_dropin.so")
+EXAMPLE = os.path.join(LIBDIR, "poisson_b200")
+EXAMPLE_SRC = os.path.join(ROOT, "examples", "poisson_b200.cpp")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -96,9 +100,27 @@ def build_dropin(force=False):
     return LIB_DROPIN
 
 
+def build_example(force=False):
+    """Compile the tutorial-style user program exactly as INTEGRATION.md section 1 says a user would."""
+    sources = [EXAMPLE_SRC, os.path.join(INCLUDE, "amgcl", "backend", "b200.hpp"),
+               os.path.join(INCLUDE, "amgcl_b200.h")]
+    if not force and not _newer(EXAMPLE, sources):
+        return EXAMPLE
+    root = amgcl_root()
+    if root is None:
+        if os.path.isfile(EXAMPLE):
+            return EXAMPLE
+        raise RuntimeError("AMGCL headers not found (set AMGCL_ROOT) and no prebuilt example")
+    _run(["g++", "-std=c++17", "-O2", "-mavx2", "-mfma", "-fopenmp", "-DAMGCL_NO_BOOST",
+          "-I", root, "-I", INCLUDE, EXAMPLE_SRC, "-o", EXAMPLE,
+          "-L", LIBDIR, "-lamgcl_b200", "-Wl,-rpath,$ORIGIN"])
+    return EXAMPLE
+
+
 def build_all(force=False, verbose=False):
     build_cuda(force=force, verbose=verbose)
     build_dropin(force=force)
+    build_example(force=force)
 
 
 if __name__ == "__main__":

@@ -177,6 +177,17 @@ def test_poisson_generator_equals_the_reference_generator():
     assert np.all(np.asarray(A.sum(axis=1)).ravel() >= -1e-12)
 
 
+@pytest.mark.skipif(build.amgcl_root() is None, reason="AMGCL headers not available")
+def test_tutorial_program_compiles_without_nvcc():
+    """user code is plain C++ against the AMGCL headers and
+    include/amgcl/backend/b200.hpp, linked with libamgcl_b200.so only."""
+    exe = build.build_example(force=True)
+    assert os.path.isfile(exe) and os.access(exe, os.X_OK)
+    import subprocess
+    needed = subprocess.run(["readelf", "-d", exe], stdout=subprocess.PIPE, text=True).stdout
+    assert "libamgcl_b200.so" in needed and "libcudart" not in needed and "libcusparse" not in needed
+
+
 def test_product_code_never_touches_the_oracle():
     """oracle/ is test infrastructure: nothing that ships (package, headers, native sources)
     may import, include, link or execute it, and there is no CPU fallback to route through."""

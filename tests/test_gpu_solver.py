@@ -105,6 +105,24 @@ def test_anisotropic_and_nonsymmetric_systems_vs_live_reference(ctx, anisotropy,
     R.close()
 
 
+@pytest.mark.parametrize("krylov,graph,iters", [("cg", "", 14), ("bicgstab", "", 8), ("bicgstab", "graph", 8)])
+def test_tutorial_program_runs(known_answers, krylov, graph, iters):
+    """examples/poisson_b200.cpp (the reference tutorial with the backend typedef switched,
+    compiled with plain g++) on 64^3: the iteration counts of the reference."""
+    import subprocess
+    from amgcl_b200 import build
+    exe = build.build_example()
+    case = [c for c in known_answers["cases"]
+            if (c["n"], c["relax"], c["krylov"]) == (64, "spai0", krylov)]
+    if case:
+        assert case[0]["iters"] == iters
+    out = subprocess.run([exe, "64", krylov] + ([graph] if graph else []), stdout=subprocess.PIPE,
+                         stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:]
+    assert "Iterations: %d" % iters in out.stdout, out.stdout[-2000:]
+    assert "Number of levels" in out.stdout          # the reference's own hierarchy report
+
+
 def test_zero_rhs(ctx):
     ptr, col, val, rhs = ab.poisson3d(12)
     S = ab.DropinSolver(ptr, col, val, ctx=ctx)
