@@ -1120,8 +1120,7 @@ static int csr_create(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *p
 template <class... KArgs, class... Args>
 static cudaError_t launch_pdl(b200_ctx_t ctx, void (*kernel)(KArgs...), dim3 grid, dim3 block,
                               size_t smem, Args... args) {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;

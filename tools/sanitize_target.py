@@ -36,4 +36,13 @@ for relax, krylov, prec in (("damped_jacobi", "cg", "f64"), ("spai0", "bicgstab"
     x, it, res = S.solve(rhs)
     print(relax, krylov, prec, it, res)
     S.close()
+# recorded V-cycles (CUDA graph replays) and the ILU(0) sweeps built from the primitives
+ptr, col, val, rhs = ab.poisson3d(14)
+for relax, krylov, prec, graph in (("spai0", "bicgstab", "f64", True), ("damped_jacobi", "cg", "mixed", True),
+                                   ("ilu0", "bicgstab", "f64", False)):
+    S = ab.DropinSolver(ptr, col, val, relax, krylov, coarse_enough=200, ctx=ctx, precision=prec, graph=graph)
+    for _ in range(2):
+        x, it, res = S.solve(rhs)
+    print(relax, krylov, prec, "graph" if graph else "", it, res, S.graph_stats())
+    S.close()
 print("SANITIZE_TARGET_DONE")
