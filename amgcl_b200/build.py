@@ -1,6 +1,6 @@
 """Build recipes for the native parts of amgcl_b200 (all in-tree, no JIT cache).
 
-  libamgcl_b200.so         CUDA kernels + C ABI (nvcc, sm_100a only)
+  libamgcl_b200.so         CUDA kernels + C ABI (nvcc, sm_100a only; csrc/api_*.cu)
   libamgcl_b200_dropin.so  AMGCL's own make_solver/amg/cg/bicgstab templates
                            instantiated on backend::b200 (g++; needs the AMGCL
                            headers, i.e. only buildable where /root/reference or
@@ -24,10 +24,10 @@ LIB_DROPIN = os.path.join(LIBDIR, "libamgcl_b200_dropin.so")
 EXAMPLE = os.path.join(LIBDIR, "poisson_b200")
 EXAMPLE_SRC = os.path.join(ROOT, "examples", "poisson_b200.cpp")
 
-NVCC_FLAGS = [
+NVCC_COMPILE = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC", "-I", INCLUDE,
 ]
 # portable x86-64 flags: the GPU box may have a different CPU than the build box
 CXX_FLAGS = ["-O2", "-mavx2", "-mfma", "-std=c++17", "-fopenmp", "-fPIC", "-shared", "-DAMGCL_NO_BOOST"]
@@ -62,21 +62,44 @@ def nvcc_path():
     return None
 
 
+def cuda_sources():
+    """The translation units of libamgcl_b200.so (api_*.cu) and everything they include."""
+    units = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
+    headers = sorted(f for f in os.listdir(CSRC) if f.endswith(".cuh"))
+    return units, headers
+
+
 def build_cuda(force=False, verbose=False):
-    """Compile the CUDA kernels + C ABI for sm_100a into libamgcl_b200.so."""
+    """Compile the CUDA kernels + C ABI for sm_100a into libamgcl_b200.so (one object per
+    api_*.cu, compiled concurrently, objects kept under lib/obj/)."""
     os.makedirs(LIBDIR, exist_ok=True)
-    sources = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))]
-    sources.append(os.path.join(INCLUDE, "amgcl_b200.h"))
-    if not force and not _newer(LIB_CUDA, sources):
+    units, headers = cuda_sources()
+    deps = [os.path.join(CSRC, f) for f in headers] + [os.path.join(INCLUDE, "amgcl_b200.h")]
+    if not force and not _newer(LIB_CUDA, deps + [os.path.join(CSRC, u) for u in units]):
         return LIB_CUDA
     nvcc = nvcc_path()
     if nvcc is None:
         raise RuntimeError("nvcc not found: cannot build libamgcl_b200.so")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
-        "-o", LIB_CUDA, os.path.join(CSRC, "capi.cu")]
-    out = _run(cmd)
-    if verbose:
-        print(out)
+    objdir = os.path.join(LIBDIR, "obj")
+    os.makedirs(objdir, exist_ok=True)
+    jobs = []
+    for u in units:
+        src = os.path.join(CSRC, u)
+        obj = os.path.join(objdir, u[:-3] + ".o")
+        if force or _newer(obj, deps + [src]):
+            cmd = [nvcc] + NVCC_COMPILE + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+            jobs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = []
+    for cmd, proc in jobs:
+        out = proc.communicate()[0]
+        if proc.returncode != 0:
+            failed.append("build failed: %s\n%s" % (" ".join(cmd), out))
+        elif verbose:
+            print(out)
+    if failed:
+        raise RuntimeError("\n".join(failed))
+    objs = [os.path.join(objdir, u[:-3] + ".o") for u in units]
+    _run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_CUDA] + objs)
     return LIB_CUDA
 
 

@@ -1,0 +1,407 @@
+// api_exchange.cu -- multi-GPU: NCCL / peer-memory set-up, partition views, the exchange steps
+//
+// Part of the implementation of the C ABI declared in include/amgcl_b200.h (host-side logic
+// only: argument checking, bookkeeping, kernel launches; no CPU fallback anywhere).
+#include "internal.cuh"
+#include "peer.cuh"
+
+using namespace b200;
+
+// ---------------------------------------------------------------------------
+// multi-GPU
+// ---------------------------------------------------------------------------
+extern "C" int b200_nccl_unique_id(char *id, size_t size) {
+    B200_REQUIRE(id != nullptr && size >= sizeof(ncclUniqueId), "id buffer must hold 128 bytes");
+    if (!nccl().load()) return fail(B200_ENCCL, nccl().error);
+    ncclUniqueId uid;
+    B200_NCCL(nccl().GetUniqueId(&uid));
+    memset(id, 0, size);
+    memcpy(id, &uid, sizeof(uid));
+    return B200_OK;
+}
+
+extern "C" int b200_dist_init(b200_ctx_t ctx, const char *id, size_t size, int nranks, int rank,
+                              int64_t dist_min_rows) {
+    CHECK_CTX(ctx);
+    B200_REQUIRE(id != nullptr && size >= sizeof(ncclUniqueId), "id buffer must hold 128 bytes");
+    B200_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank / nranks");
+    B200_REQUIRE(dist_min_rows >= 1, "dist_min_rows must be positive");
+    B200_REQUIRE(!ctx->dist, "context is already distributed");
+    GUARD(ctx);
+    if (!nccl().load()) return fail(B200_ENCCL, nccl().error);
+    ncclUniqueId uid;
+    memcpy(&uid, id, sizeof(uid));
+    ncclComm_t comm = nullptr;
+    B200_NCCL(nccl().CommInitRank(&comm, nranks, uid, rank));
+    ctx->comm = comm;
+    ctx->rank = rank;
+    ctx->nranks = nranks;
+    ctx->dist_min_rows = dist_min_rows;
+    ctx->dist = true;
+    B200_CUDA(cudaMalloc(&ctx->push_ticket, sizeof(unsigned int)));
+    B200_CUDA(cudaMemset(ctx->push_ticket, 0, sizeof(unsigned int)));
+    B200_CUDA(cudaMalloc(&ctx->ipc_dev, (size_t)kMaxRanks * sizeof(cudaIpcMemHandle_t)));
+
+    // peer-memory exchange: try to map a small buffer of every peer; agree collectively
+    ctx->p2p = false;
+    if (ctx->opt_p2p && nranks > 1 && nranks <= kMaxRanks) {
+        int ok = peer_alloc(ctx, kFlagBytes + 2 * 256, &ctx->dot_pb_local, ctx->dot_pb_peer) == B200_OK;
+        int *flag_d = reinterpret_cast<int *>(ctx->ipc_dev);
+        B200_CUDA(cudaMemcpy(flag_d, &ok, sizeof(int), cudaMemcpyHostToDevice));
+        B200_NCCL(nccl().AllReduce(flag_d, flag_d, 1, ncclInt, ncclMin, comm, ctx->stream));
+        B200_CUDA(cudaMemcpyAsync(&ok, flag_d, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        B200_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->p2p = ok != 0;
+        if (!ctx->p2p) cudaGetLastError();
+    }
+    return B200_OK;
+}
+
+extern "C" int b200_dist_info(b200_ctx_t ctx, int *rank, int *nranks, int64_t *dist_min_rows,
+                              int *p2p) {
+    CHECK_CTX(ctx);
+    if (rank) *rank = ctx->rank;
+    if (nranks) *nranks = ctx->nranks;
+    if (dist_min_rows) *dist_min_rows = ctx->dist ? ctx->dist_min_rows : 0;
+    if (p2p) *p2p = ctx->p2p ? 1 : 0;
+    return B200_OK;
+}
+
+// ---- pure host view of the partitioning (no device, no NCCL): for CPU tests ------------
+struct b200_split_s {
+    SplitMatrix m;
+    std::vector<double> val;
+    int kind;
+};
+
+extern "C" int b200_dist_split_i64(int kind, int nranks, int rank, int64_t nrows, int64_t ncols,
+                                   const int64_t *ptr, const int64_t *col, const double *val,
+                                   b200_split_t *out) {
+    B200_REQUIRE(out != nullptr && ptr != nullptr, "null argument");
+    B200_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank / nranks");
+    B200_REQUIRE(kind >= 1 && kind <= 3, "kind must be 1 (square), 2 (prolong) or 3 (restrict)");
+    b200_split_s *sp = new (std::nothrow) b200_split_s();
+    if (!sp) return fail(B200_ENOMEM, "out of host memory");
+    sp->kind = kind;
+    if (kind == B200_CK_SQUARE) {
+        if (nrows != ncols) { delete sp; return fail(B200_EINVAL, "square operator expected"); }
+        split_square(Partition(nrows, nranks), rank, ptr, col, sp->m);
+    } else if (kind == B200_CK_PROLONG) {
+        split_prolong(Partition(nrows, nranks), rank, ncols, ptr, col, sp->m);
+    } else {
+        split_restrict(Partition(ncols, nranks), rank, nrows, ptr, col, val, sp->m);
+    }
+    const int64_t nnz = sp->m.ptr.back();
+    if (sp->m.val_contiguous) sp->val.assign(val + sp->m.val_offset, val + sp->m.val_offset + nnz);
+    else sp->val = sp->m.val;
+    *out = sp;
+    return B200_OK;
+}
+
+extern "C" int b200_split_info(b200_split_t sp, int64_t *nrows, int64_t *ncols, int64_t *nnz,
+                               int64_t *n_loc, int64_t *slots, int64_t *n_send) {
+    B200_REQUIRE(sp != nullptr, "null argument");
+    if (nrows) *nrows = sp->m.nrows;
+    if (ncols) *ncols = sp->m.ncols;
+    if (nnz) *nnz = sp->m.ptr.back();
+    if (n_loc) *n_loc = sp->m.n_loc;
+    if (slots) *slots = sp->m.S;
+    if (n_send) *n_send = (int64_t)sp->m.send_idx.size();
+    return B200_OK;
+}
+
+extern "C" int b200_split_copy(b200_split_t sp, int64_t *ptr, int64_t *col, double *val,
+                               int64_t *send_idx) {
+    B200_REQUIRE(sp != nullptr, "null argument");
+    if (ptr) memcpy(ptr, sp->m.ptr.data(), sp->m.ptr.size() * sizeof(int64_t));
+    if (col) memcpy(col, sp->m.col.data(), sp->m.col.size() * sizeof(int64_t));
+    if (val) memcpy(val, sp->val.data(), sp->val.size() * sizeof(double));
+    if (send_idx) memcpy(send_idx, sp->m.send_idx.data(), sp->m.send_idx.size() * sizeof(int64_t));
+    return B200_OK;
+}
+
+extern "C" int b200_split_destroy(b200_split_t sp) {
+    delete sp;
+    return B200_OK;
+}
+
+extern "C" int b200_partition(int64_t n, int nranks, int rank, int64_t *block, int64_t *lo,
+                              int64_t *hi) {
+    B200_REQUIRE(n >= 0 && nranks >= 1 && rank >= 0 && rank < nranks, "bad argument");
+    const Partition part(n, nranks);
+    if (block) *block = part.B;
+    if (lo) *lo = part.lo(rank);
+    if (hi) *hi = part.hi(rank);
+    return B200_OK;
+}
+
+namespace b200 {
+
+// Collective: every rank allocates `bytes` (zero filled) and maps the allocations of all
+// its peers through CUDA IPC.  peers[rank] is the local pointer.
+int peer_alloc(b200_ctx_t ctx, size_t bytes, void **local, void **peers) {
+    bytes = (bytes + 255) & ~size_t(255);
+    B200_CUDA(cudaMalloc(local, bytes));
+    B200_CUDA(cudaMemsetAsync(*local, 0, bytes, ctx->stream));
+    cudaIpcMemHandle_t mine;
+    B200_CUDA(cudaIpcGetMemHandle(&mine, *local));
+    char *stage = static_cast<char *>(ctx->ipc_dev);
+    const size_t hs = sizeof(cudaIpcMemHandle_t);
+    B200_CUDA(cudaMemcpyAsync(stage + ctx->rank * hs, &mine, hs, cudaMemcpyHostToDevice, ctx->stream));
+    B200_NCCL(nccl().AllGather(stage + ctx->rank * hs, stage, hs, ncclChar, comm_of(ctx), ctx->stream));
+    std::vector<cudaIpcMemHandle_t> all((size_t)ctx->nranks);
+    B200_CUDA(cudaMemcpyAsync(all.data(), stage, hs * ctx->nranks, cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int q = 0; q < ctx->nranks; ++q) {
+        if (q == ctx->rank) { peers[q] = *local; continue; }
+        B200_CUDA(cudaIpcOpenMemHandle(&peers[q], all[(size_t)q], cudaIpcMemLazyEnablePeerAccess));
+    }
+    return B200_OK;
+}
+
+void peer_release(b200_ctx_t ctx, void *local, void **peers) {
+    if (!local) return;
+    for (int q = 0; q < ctx->nranks; ++q)
+        if (q != ctx->rank && peers[q]) cudaIpcCloseMemHandle(peers[q]);
+    // peers may still have this allocation mapped: keep it until the context dies
+    ctx->deferred_free.push_back(local);
+}
+
+
+static int launch_push(b200_ctx_t ctx, int64_t count, const double *src, const int *idx,
+                       const PeerTargets &tgt, int64_t seg_stride, unsigned long long seq) {
+    // indexed (halo) pushes: one value per thread; contiguous ones: 8 doubles per thread;
+    // never more than 4 CTAs per SM -- the grid-stride loops cover the rest
+    const int64_t per_cta = idx ? kThreads : (int64_t)kThreads * 8;
+    const int64_t want = std::max<int64_t>(1, (count + per_cta - 1) / per_cta);
+    const unsigned grid = (unsigned)std::min<int64_t>(want, (int64_t)ctx->sm_count * 4);
+    push_kernel<<<grid, kThreads, 0, ctx->stream>>>(count, src, idx, tgt, ctx->nranks, seg_stride,
+                                                    ctx->push_ticket, seq);
+    B200_CHECK_LAUNCH();
+    ctx->launches++;
+    return B200_OK;
+}
+
+// SQUARE operators: make every rank's boundary values of x visible in A->halo.
+// One pack kernel + one in-place ncclAllGather (S doubles per rank) on the stream.
+int halo_exchange(b200_ctx_t ctx, b200_csr_t A, const double *x, HaloArgs &a) {
+    a.xh = A->halo; a.nloc = (int)A->n_loc;
+    if (A->S == 0) return B200_OK;
+    ProfScope prof(ctx, B200_PROF_COMM, A->n_send, ctx->nranks, 0);
+    if (ctx->p2p) {
+        // push my boundary values straight into the halo buffers of the ranks that gather
+        // them, release their flags, then wait for the ranks I gather from
+        const int par = (int)(A->seq & 1);
+        const unsigned long long seq = ++A->seq;
+        PeerTargets tgt;
+        WaitList w;
+        bool any_wait = false;
+        for (int q = 0; q < kMaxRanks; ++q) { tgt.data[q] = nullptr; tgt.flag[q] = nullptr; w.flag[q] = nullptr; }
+        for (int q = 0; q < ctx->nranks; ++q) {
+            if (q == ctx->rank) continue;
+            if (A->needed_by[q]) {
+                tgt.data[q] = data_at(A->pb_peer[q], par, A->pb_half) + (size_t)ctx->rank * A->S;
+                tgt.flag[q] = flag_at(A->pb_peer[q], par, ctx->rank);
+            }
+            if (A->need_from[q]) { w.flag[q] = flag_at(A->pb_local, par, q); any_wait = true; }
+        }
+        int rc = launch_push(ctx, A->n_send, x, A->send_idx, tgt, 0, seq);
+        if (rc) return rc;
+        A->halo = data_at(A->pb_local, par, A->pb_half);   // what the kernel gathers from
+        a.xh = A->halo;
+        if (any_wait) {
+            // no separate wait launch: the consumer kernel starts on its interior rows at
+            // once and only blocks that gather remote columns poll the flags
+            unsigned int mask = 0;
+            for (int q = 0; q < ctx->nranks; ++q)
+                if (w.flag[q]) mask |= 1u << q;
+            a.blk_halo = A->blk_halo;
+            a.wait_flags = flag_at(A->pb_local, par, 0);
+            a.wait_mask = mask;
+            a.wait_seq = seq;
+        }
+        return B200_OK;
+    }
+    double *mine = A->halo + (size_t)ctx->rank * A->S;
+    if (A->n_send) {
+        const unsigned grid = (unsigned)((A->n_send + kThreads - 1) / kThreads);
+        halo_pack_kernel<<<grid, kThreads, 0, ctx->stream>>>(A->n_send, A->send_idx, x, mine);
+        B200_CHECK_LAUNCH();
+        ctx->launches++;
+    }
+    B200_NCCL(nccl().AllGather(mine, A->halo, (size_t)A->S, ncclDouble, comm_of(ctx), ctx->stream));
+    return B200_OK;
+}
+
+// PROLONG operators: bring the coarse vector to every rank; returns the pointer to gather from.
+int coarse_to_all(b200_ctx_t ctx, b200_csr_t A, b200_vec_t xc, const double **px) {
+    ProfScope prof(ctx, B200_PROF_COMM, A->gl_cols, ctx->nranks, 1);
+    if (ctx->p2p) {
+        const int par = (int)(A->seq & 1);
+        const unsigned long long seq = ++A->seq;
+        PeerTargets tgt;
+        WaitList w;
+        bool any_wait = false;
+        for (int q = 0; q < kMaxRanks; ++q) { tgt.data[q] = nullptr; tgt.flag[q] = nullptr; w.flag[q] = nullptr; }
+        if (A->coarse_dist) {
+            B200_REQUIRE(xc->kind == B200_VK_DIST && (int64_t)xc->cap == A->coarse_B,
+                         "prolongation: coarse vector is not partitioned like the operator");
+            int rc = materialize(xc);
+            if (rc) return rc;
+            for (int q = 0; q < ctx->nranks; ++q) {
+                if (A->needed_by[q]) {
+                    tgt.data[q] = data_at(A->pb_peer[q], par, A->pb_half) + (size_t)ctx->rank * A->coarse_B;
+                    tgt.flag[q] = flag_at(A->pb_peer[q], par, ctx->rank);
+                }
+                if (A->need_from[q]) { w.flag[q] = flag_at(A->pb_local, par, q); any_wait = true; }
+            }
+            rc = launch_push(ctx, A->coarse_B, xc->ptr, nullptr, tgt, 0, seq);
+            if (rc) return rc;
+            *px = data_at(A->pb_local, par, A->pb_half);
+        } else if (ctx->rank == 0) {
+            B200_REQUIRE(xc->kind == B200_VK_LOCAL, "prolongation: coarse vector must live on rank 0");
+            int rc = materialize(xc);
+            if (rc) return rc;
+            bool any = false;
+            for (int q = 1; q < ctx->nranks; ++q)
+                if (A->needed_by[q]) {
+                    tgt.data[q] = data_at(A->pb_peer[q], par, A->pb_half);
+                    tgt.flag[q] = flag_at(A->pb_peer[q], par, 0);
+                    any = true;
+                }
+            if (any) {
+                rc = launch_push(ctx, A->gl_cols, xc->ptr, nullptr, tgt, 0, seq);
+                if (rc) return rc;
+            }
+            *px = xc->ptr;
+        } else {
+            if (A->need_from[0]) { w.flag[0] = flag_at(A->pb_local, par, 0); any_wait = true; }
+            *px = data_at(A->pb_local, par, A->pb_half);
+        }
+        if (any_wait) {
+            wait_kernel<<<1, 32, 0, ctx->stream>>>(w, ctx->nranks, seq);
+            B200_CHECK_LAUNCH();
+            ctx->launches++;
+        }
+        return B200_OK;
+    }
+    if (A->coarse_dist) {
+        B200_REQUIRE(xc->kind == B200_VK_DIST && (int64_t)xc->cap == A->coarse_B,
+                     "prolongation: coarse vector is not partitioned like the operator");
+        int rc = materialize(xc);
+        if (rc) return rc;
+        B200_NCCL(nccl().AllGather(xc->ptr, A->cbuf, (size_t)A->coarse_B, ncclDouble, comm_of(ctx), ctx->stream));
+        *px = A->cbuf;
+        return B200_OK;
+    }
+    if (ctx->rank == 0) {
+        B200_REQUIRE(xc->kind == B200_VK_LOCAL, "prolongation: coarse vector must live on rank 0");
+        int rc = materialize(xc);
+        if (rc) return rc;
+        B200_NCCL(nccl().Broadcast(xc->ptr, xc->ptr, (size_t)A->gl_cols, ncclDouble, 0, comm_of(ctx), ctx->stream));
+        *px = xc->ptr;
+    } else {
+        B200_NCCL(nccl().Broadcast(A->cbuf, A->cbuf, (size_t)A->gl_cols, ncclDouble, 0, comm_of(ctx), ctx->stream));
+        *px = A->cbuf;
+    }
+    return B200_OK;
+}
+
+// RESTRICT operators: combine the per-rank partial sums in A->cbuf into the coarse vector.
+int partials_to_coarse(b200_ctx_t ctx, b200_csr_t A, b200_vec_t yc) {
+    ProfScope prof(ctx, B200_PROF_COMM, A->gl_rows, ctx->nranks, 2);
+    if (ctx->p2p) {
+        // every rank stores its partial sums for owner q directly into q's staging area;
+        // the owner adds the staged partials in rank order (deterministic)
+        const int par = (int)(A->seq & 1);
+        const unsigned long long seq = ++A->seq;
+        PeerTargets tgt;
+        WaitList w;
+        for (int q = 0; q < kMaxRanks; ++q) { tgt.data[q] = nullptr; tgt.flag[q] = nullptr; w.flag[q] = nullptr; }
+        const int64_t seg = A->coarse_dist ? A->coarse_B : A->gl_rows;     // staged entries per source
+        const int nowners = A->coarse_dist ? ctx->nranks : 1;
+        bool any = false;
+        for (int q = 0; q < nowners; ++q)
+            if (A->needed_by[q]) {
+                tgt.data[q] = data_at(A->pb_peer[q], par, A->pb_half_owner) + (size_t)ctx->rank * seg;
+                tgt.flag[q] = flag_at(A->pb_peer[q], par, ctx->rank);
+                any = true;
+            }
+        if (any) {
+            int rc = launch_push(ctx, seg, A->cbuf, nullptr, tgt, A->coarse_dist ? seg : 0, seq);
+            if (rc) return rc;
+        }
+        const bool owner = A->coarse_dist || ctx->rank == 0;
+        if (owner) {
+            if (A->coarse_dist)
+                B200_REQUIRE(yc->kind == B200_VK_DIST && (int64_t)yc->cap == A->coarse_B,
+                             "restriction: coarse vector is not partitioned like the operator");
+            else
+                B200_REQUIRE(yc->kind == B200_VK_LOCAL, "restriction: coarse vector must live on rank 0");
+            for (int q = 0; q < ctx->nranks; ++q)
+                if (A->need_from[q]) w.flag[q] = flag_at(A->pb_local, par, q);
+            const int64_t count = (int64_t)yc->len;
+            if (count) {
+                const unsigned grid = (unsigned)((count + kThreads - 1) / kThreads);
+                reduce_sum_kernel<<<grid, kThreads, 0, ctx->stream>>>(
+                    count, data_at(A->pb_local, par, A->pb_half), seg, ctx->nranks, w, seq, wr(yc), nullptr);
+                B200_CHECK_LAUNCH();
+                ctx->launches++;
+            }
+            yc->zero_pending = false;
+        }
+        return B200_OK;
+    }
+    if (A->coarse_dist) {
+        B200_REQUIRE(yc->kind == B200_VK_DIST && (int64_t)yc->cap == A->coarse_B,
+                     "restriction: coarse vector is not partitioned like the operator");
+        B200_NCCL(nccl().ReduceScatter(A->cbuf, wr(yc), (size_t)A->coarse_B, ncclDouble, ncclSum,
+                                       comm_of(ctx), ctx->stream));
+        return B200_OK;
+    }
+    double *dst = A->cbuf;
+    if (ctx->rank == 0) {
+        B200_REQUIRE(yc->kind == B200_VK_LOCAL, "restriction: coarse vector must live on rank 0");
+        dst = wr(yc);
+    }
+    B200_NCCL(nccl().Reduce(A->cbuf, dst, (size_t)A->gl_rows, ncclDouble, ncclSum, 0, comm_of(ctx), ctx->stream));
+    return B200_OK;
+}
+
+// Partitioned inner product: the local partial sum is in ctx->dot_dev; combine the ranks'
+// partials and hand the result to the host (mpi/inner_product.hpp:53-62 does the same with
+// MPI_Allreduce on the host).
+int dist_dot_finish(b200_ctx_t ctx, double *result) {
+    if (ctx->p2p) {
+        // every rank stores its partial into slot `rank` of every peer; each rank then adds
+        // the P partials in rank order (bitwise identical on all ranks) straight into
+        // mapped host memory
+        const int par = (int)(ctx->dot_seq & 1);
+        const unsigned long long seq = ++ctx->dot_seq;
+        PeerTargets tgt;
+        WaitList w;
+        for (int q = 0; q < kMaxRanks; ++q) { tgt.data[q] = nullptr; tgt.flag[q] = nullptr; w.flag[q] = nullptr; }
+        for (int q = 0; q < ctx->nranks; ++q) {
+            tgt.data[q] = data_at(ctx->dot_pb_peer[q], par, 256) + ctx->rank;
+            tgt.flag[q] = flag_at(ctx->dot_pb_peer[q], par, ctx->rank);
+            w.flag[q] = flag_at(ctx->dot_pb_local, par, q);
+        }
+        int rc = launch_push(ctx, 1, ctx->dot_dev, nullptr, tgt, 0, seq);
+        if (rc) return rc;
+        reduce_sum_kernel<<<1, 32, 0, ctx->stream>>>(1, data_at(ctx->dot_pb_local, par, 256), 1, ctx->nranks,
+                                                      w, seq, ctx->dot_dev + 1, ctx->dot_result_d);
+        B200_CHECK_LAUNCH();
+        ctx->launches++;
+        B200_CUDA(cudaStreamSynchronize(ctx->stream));
+        *result = *reinterpret_cast<volatile double *>(ctx->dot_result_h);
+        return B200_OK;
+    }
+    B200_NCCL(nccl().AllReduce(ctx->dot_dev, ctx->dot_dev, 1, ncclDouble, ncclSum, comm_of(ctx), ctx->stream));
+    B200_CUDA(cudaMemcpyAsync(ctx->dot_result_h, ctx->dot_dev, sizeof(double), cudaMemcpyDeviceToHost,
+                              ctx->stream));
+    B200_CUDA(cudaStreamSynchronize(ctx->stream));
+    *result = *reinterpret_cast<volatile double *>(ctx->dot_result_h);
+    return B200_OK;
+}
+
+} // namespace b200

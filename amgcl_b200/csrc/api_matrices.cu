@@ -1,0 +1,782 @@
+// api_matrices.cu -- CSR operators: row-block plan, upload, the streaming passes (spmv, residual, smoother sweep)
+//
+// Part of the implementation of the C ABI declared in include/amgcl_b200.h (host-side logic
+// only: argument checking, bookkeeping, kernel launches; no CPU fallback anywhere).
+#include "internal.cuh"
+#include "csr_kernels.cuh"
+
+using namespace b200;
+
+// ---------------------------------------------------------------------------
+// matrices
+// ---------------------------------------------------------------------------
+namespace b200 {
+
+static int choose_lanes(double avg) {
+    // measured on the B200 with the operators of a 192^3 Poisson hierarchy
+    // (tools/gpu_check.py levels): few lanes per row keep many rows -- and so many
+    // independent x-gathers -- in flight per CTA; wide groups only pay off for long rows
+    if (avg <= 12.0) return 1;
+    if (avg <= 40.0) return 2;
+    if (avg <= 64.0) return 4;
+    if (avg <= 160.0) return 8;
+    if (avg <= 320.0) return 16;
+    return 32;
+}
+
+// Row-block plan (pure host logic, also exported as b200_plan_i64 for tests):
+// consecutive rows, starting at a multiple of four, are packed greedily while
+// they fit `rows_cap` rows and `nnz_cap` non-zeros.  A block that still exceeds
+// nnz_cap (a single quad of very long rows) is counted as "long" and is handled
+// by the strided path of the kernels.
+struct RowBlockPlan {
+    int lanes = 1, rows_cap = 256, nnz_cap = 2048;
+    int64_t nlong = 0;
+    std::vector<int2> blk;   // {first row, first non-zero}; last entry = {nrows, nnz}
+};
+
+template <class Ptr>
+static void build_plan(int64_t nrows, const Ptr *ptr, int lanes_opt, int nnz_cap,
+                       RowBlockPlan &plan) {
+    const int64_t nnz = nrows ? (int64_t)ptr[nrows] : 0;
+    const double avg = nrows ? (double)nnz / (double)nrows : 0.0;
+    const int lanes = lanes_opt ? lanes_opt : choose_lanes(avg);
+    const int groups = kThreads / lanes;
+    // rows per block: a multiple of the number of row groups, sized so a typical
+    // block fills the stage
+    int k = 1;
+    if (avg > 0.0) k = (int)std::floor((double)nnz_cap / (avg * groups));
+    k = std::max(1, std::min(k, kRowsCapMax / groups));
+    int rows_cap = std::min(kRowsCapMax, groups * k);
+    rows_cap = std::max(4, rows_cap & ~3);
+    plan.lanes = lanes; plan.rows_cap = rows_cap; plan.nnz_cap = nnz_cap; plan.nlong = 0;
+    plan.blk.clear();
+    plan.blk.reserve((size_t)(nnz / std::max(1, nnz_cap / 2) + nrows / rows_cap + 16));
+    int64_t r = 0;
+    while (r < nrows) {
+        const int64_t r0 = r;
+        const int64_t e0 = (int64_t)ptr[r0];
+        // always take the first quad, then grow quad by quad while it fits
+        int64_t r1 = std::min<int64_t>(nrows, r0 + 4);
+        while (r1 < nrows) {
+            const int64_t rn = std::min<int64_t>(nrows, r1 + 4);
+            if (rn - r0 > rows_cap) break;
+            if ((int64_t)ptr[rn] - e0 > nnz_cap) break;
+            r1 = rn;
+        }
+        if ((int64_t)ptr[r1] - e0 > nnz_cap) ++plan.nlong;
+        plan.blk.push_back(make_int2((int)r0, (int)e0));
+        r = r1;
+    }
+    plan.blk.push_back(make_int2((int)nrows, (int)nnz));
+}
+
+// Upload one CSR matrix exactly as the kernels will see it (indices narrowed to int32,
+// row-block plan built).  Single-GPU matrices come straight through here; the
+// distributed kinds hand in the local part produced by dist.cuh.
+template <class Ptr, class Col, class Val>
+static int csr_upload(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *ptr,
+                      const Col *col, const Val *val, b200_csr_t *out) {
+    CHECK_CTX(ctx);
+    B200_REQUIRE(out != nullptr, "null output pointer");
+    *out = nullptr;
+    B200_REQUIRE(nrows >= 0 && ncols >= 0, "negative matrix dimension");
+    B200_REQUIRE(ptr != nullptr, "null row pointer array");
+    const int64_t imax = std::numeric_limits<int32_t>::max();
+    if (nrows >= imax - 8 || ncols >= imax) return fail(B200_ERANGE, "matrix dimension exceeds int32");
+    B200_REQUIRE(ptr[0] == 0, "ptr[0] must be 0");
+    const int64_t nnz = (int64_t)ptr[nrows];
+    if (nnz < 0) return fail(B200_EINVAL, "negative number of non-zeros");
+    if (nnz >= imax - 8) return fail(B200_ERANGE, "number of non-zeros exceeds int32");
+    B200_REQUIRE(nnz == 0 || (col != nullptr && val != nullptr), "null col/val array");
+    GUARD(ctx);
+
+    // ---- narrow indices, validate ------------------------------------------
+    std::vector<int32_t> hptr((size_t)nrows + 1), hcol((size_t)nnz);
+    for (int64_t i = 0; i <= nrows; ++i) {
+        const int64_t p = (int64_t)ptr[i];
+        if (i && p < (int64_t)ptr[i - 1]) return fail(B200_EINVAL, "row pointers not monotone");
+        hptr[(size_t)i] = (int32_t)p;
+    }
+    for (int64_t e = 0; e < nnz; ++e) {
+        const int64_t c = (int64_t)col[e];
+        if (c < 0 || c >= ncols) return fail(B200_EINVAL, "column index out of range");
+        hcol[(size_t)e] = (int32_t)c;
+    }
+
+    // ---- row-block plan -------------------------------------------------------
+    RowBlockPlan plan;
+    build_plan(nrows, hptr.data(), (int)ctx->opt_lanes, (int)ctx->opt_nnz_cap, plan);
+    const int lanes = plan.lanes, rows_cap = plan.rows_cap, nnz_cap = plan.nnz_cap;
+    const int64_t nlong = plan.nlong;
+    std::vector<int2> &blk = plan.blk;
+    const int64_t nblocks = (int64_t)blk.size() - 1;
+
+    // ---- upload ---------------------------------------------------------------------
+    b200_csr_s *A = new (std::nothrow) b200_csr_s();
+    if (!A) return fail(B200_ENOMEM, "out of host memory");
+    A->ctx = ctx; A->nrows = nrows; A->ncols = ncols; A->nnz = nnz;
+    A->gl_rows = nrows; A->gl_cols = ncols; A->gl_nnz = nnz;
+    A->dtype = std::is_same<Val, float>::value ? B200_F32 : B200_F64;
+    A->lanes = lanes; A->rows_cap = rows_cap; A->nnz_cap = nnz_cap;
+    A->nblocks = nblocks; A->nlong = nlong;
+    // padding: bulk copies round sizes up to 16 bytes
+    const size_t ptr_bytes = ((size_t)nrows + 1 + 8) * sizeof(int);
+    const size_t col_bytes = ((size_t)nnz + 8) * sizeof(int);
+    const size_t val_bytes = ((size_t)nnz + 8) * sizeof(Val);
+    const size_t blk_bytes = ((size_t)nblocks + 1) * sizeof(int2);
+    auto cleanup = [&]() {
+        if (A->ptr) cudaFree(A->ptr);
+        if (A->col) cudaFree(A->col);
+        if (A->val) cudaFree(A->val);
+        if (A->blk) cudaFree(A->blk);
+        delete A;
+    };
+#define CSR_CUDA(call)                                                         \
+    do {                                                                       \
+        cudaError_t rc__ = (call);                                             \
+        if (rc__ != cudaSuccess) {                                             \
+            cleanup();                                                         \
+            return cuda_fail(rc__, #call, __FILE__, __LINE__);                 \
+        }                                                                      \
+    } while (0)
+    CSR_CUDA(cudaMalloc(&A->ptr, ptr_bytes));
+    CSR_CUDA(cudaMalloc(&A->col, col_bytes));
+    CSR_CUDA(cudaMalloc(&A->val, val_bytes));
+    CSR_CUDA(cudaMalloc(&A->blk, blk_bytes));
+    CSR_CUDA(cudaMemsetAsync(A->ptr, 0, ptr_bytes, ctx->stream));
+    CSR_CUDA(cudaMemsetAsync(A->col, 0, col_bytes, ctx->stream));
+    CSR_CUDA(cudaMemsetAsync(A->val, 0, val_bytes, ctx->stream));
+    CSR_CUDA(cudaMemcpyAsync(A->ptr, hptr.data(), ((size_t)nrows + 1) * sizeof(int),
+                             cudaMemcpyHostToDevice, ctx->stream));
+    if (nnz) {
+        CSR_CUDA(cudaMemcpyAsync(A->col, hcol.data(), (size_t)nnz * sizeof(int),
+                                 cudaMemcpyHostToDevice, ctx->stream));
+        CSR_CUDA(cudaMemcpyAsync(A->val, val, (size_t)nnz * sizeof(Val),
+                                 cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CSR_CUDA(cudaMemcpyAsync(A->blk, blk.data(), blk_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CSR_CUDA(cudaStreamSynchronize(ctx->stream));   // host staging buffers die here
+#undef CSR_CUDA
+    A->bytes = ptr_bytes + col_bytes + val_bytes + blk_bytes;
+    *out = A;
+    return B200_OK;
+}
+
+static void csr_free(b200_csr_t A) {
+    if (!A) return;
+    if (A->ptr) cudaFree(A->ptr);
+    if (A->col) cudaFree(A->col);
+    if (A->val) cudaFree(A->val);
+    if (A->blk) cudaFree(A->blk);
+    if (A->send_idx) cudaFree(A->send_idx);
+    if (A->blk_halo) cudaFree(A->blk_halo);
+    if (A->halo_owned) cudaFree(A->halo_owned);
+    if (A->cbuf) cudaFree(A->cbuf);
+    if (A->scratch64) cudaFree(A->scratch64);
+    if (A->pb_local) peer_release(A->ctx, A->pb_local, A->pb_peer);
+    delete A;
+}
+
+// The public constructor: on a distributed context decide from the shape which
+// kind of operator this is (see dist.cuh) and keep only this rank's share.
+template <class Ptr, class Col>
+static int csr_create_f32(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *ptr,
+                          const Col *col, const float *val, b200_csr_t *out) {
+    CHECK_CTX(ctx);
+    NOT_RECORDING(ctx, "matrix creation");
+    B200_REQUIRE_F64_DIST(ctx, "b200_csr_create_*_f32");
+    return csr_upload(ctx, nrows, ncols, ptr, col, val, out);
+}
+
+template <class Ptr, class Col>
+static int csr_create(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *ptr,
+                      const Col *col, const double *val, b200_csr_t *out) {
+    CHECK_CTX(ctx);
+    NOT_RECORDING(ctx, "matrix creation");
+    B200_REQUIRE(out != nullptr, "null output pointer");
+    *out = nullptr;
+    if (!ctx->dist) return csr_upload(ctx, nrows, ncols, ptr, col, val, out);
+
+    B200_REQUIRE(nrows >= 0 && ncols >= 0 && ptr != nullptr && ptr[0] == 0, "bad CSR input");
+    const int64_t nnz = (int64_t)ptr[nrows];
+    B200_REQUIRE(nnz == 0 || (col != nullptr && val != nullptr), "null col/val array");
+    const int64_t T = ctx->dist_min_rows;
+    const bool rd = nrows >= T, cd = ncols >= T;
+    int kind = B200_CK_LOCAL;
+    if (rd && cd && nrows == ncols) kind = B200_CK_SQUARE;
+    else if (rd && (!cd || nrows > ncols)) kind = B200_CK_PROLONG;
+    else if (cd && (!rd || ncols > nrows)) kind = B200_CK_RESTRICT;
+
+    if (kind == B200_CK_LOCAL) {
+        if (ctx->rank == 0) return csr_upload(ctx, nrows, ncols, ptr, col, val, out);
+        b200_csr_s *G = new (std::nothrow) b200_csr_s();     // ghost: lives on rank 0
+        if (!G) return fail(B200_ENOMEM, "out of host memory");
+        G->ctx = ctx; G->kind = B200_CK_GHOST;
+        G->gl_rows = nrows; G->gl_cols = ncols; G->gl_nnz = nnz;
+        *out = G;
+        return B200_OK;
+    }
+    for (int64_t e = 0; e < nnz; ++e)
+        if ((int64_t)col[e] < 0 || (int64_t)col[e] >= ncols)
+            return fail(B200_EINVAL, "column index out of range");
+    GUARD(ctx);
+
+    SplitMatrix sp;
+    const int P = ctx->nranks, rank = ctx->rank;
+    if (kind == B200_CK_SQUARE) split_square(Partition(nrows, P), rank, ptr, col, sp);
+    else if (kind == B200_CK_PROLONG) split_prolong(Partition(nrows, P), rank, ncols, ptr, col, sp);
+    else split_restrict(Partition(ncols, P), rank, nrows, ptr, col, val, sp);
+
+    b200_csr_t A = nullptr;
+    const double *lval = sp.val_contiguous ? val + sp.val_offset : sp.val.data();
+    int64_t kernel_cols = sp.ncols;
+    if (kind == B200_CK_PROLONG && cd) kernel_cols = Partition(ncols, P).B * P;   // gathered blocks
+    int rc = csr_upload(ctx, sp.nrows, kernel_cols, sp.ptr.data(), sp.col.data(), lval, &A);
+    if (rc) return rc;
+    A->kind = kind;
+    A->gl_rows = nrows; A->gl_cols = ncols; A->gl_nnz = nnz;
+    A->n_loc = sp.n_loc;
+#define DCSR_CUDA(call)                                                        \
+    do {                                                                       \
+        cudaError_t rc__ = (call);                                             \
+        if (rc__ != cudaSuccess) {                                             \
+            csr_free(A);                                                       \
+            return cuda_fail(rc__, #call, __FILE__, __LINE__);                 \
+        }                                                                      \
+    } while (0)
+    if (kind == B200_CK_SQUARE) {
+        A->S = sp.S;
+        A->n_send = (int64_t)sp.send_idx.size();
+        std::vector<int32_t> idx(sp.send_idx.begin(), sp.send_idx.end());
+        DCSR_CUDA(cudaMalloc(&A->send_idx, std::max<size_t>(1, idx.size()) * sizeof(int)));
+        DCSR_CUDA(cudaMalloc(&A->halo_owned, std::max<size_t>(2, (size_t)(P * sp.S)) * sizeof(double)));
+        A->halo = A->halo_owned;
+        DCSR_CUDA(cudaMemsetAsync(A->halo, 0, std::max<size_t>(2, (size_t)(P * sp.S)) * sizeof(double), ctx->stream));
+        if (!idx.empty())
+            DCSR_CUDA(cudaMemcpyAsync(A->send_idx, idx.data(), idx.size() * sizeof(int),
+                                      cudaMemcpyHostToDevice, ctx->stream));
+        A->bytes += idx.size() * sizeof(int) + (size_t)(P * sp.S) * sizeof(double);
+        // which row blocks touch the halo (the same plan csr_upload just built)
+        RowBlockPlan plan;
+        build_plan(sp.nrows, sp.ptr.data(), A->lanes, A->nnz_cap, plan);
+        std::vector<unsigned char> bh((size_t)std::max<int64_t>(1, A->nblocks), 0);
+        if ((int64_t)plan.blk.size() - 1 == A->nblocks) {
+            for (int64_t b = 0; b < A->nblocks; ++b) {
+                const int64_t e0 = plan.blk[(size_t)b].y, e1 = plan.blk[(size_t)b + 1].y;
+                for (int64_t e = e0; e < e1 && !bh[(size_t)b]; ++e)
+                    if (sp.col[(size_t)e] >= sp.n_loc) bh[(size_t)b] = 1;
+            }
+        } else {
+            std::fill(bh.begin(), bh.end(), 1);      // cannot happen; be safe: every block waits
+        }
+        DCSR_CUDA(cudaMalloc(&A->blk_halo, bh.size()));
+        DCSR_CUDA(cudaMemcpyAsync(A->blk_halo, bh.data(), bh.size(), cudaMemcpyHostToDevice, ctx->stream));
+        DCSR_CUDA(cudaStreamSynchronize(ctx->stream));
+    } else {
+        // coarse-side buffer: gathered input of P, partial sums of R
+        const bool coarse_dist = (kind == B200_CK_PROLONG) ? cd : rd;
+        const int64_t nc = (kind == B200_CK_PROLONG) ? ncols : nrows;
+        A->coarse_dist = coarse_dist;
+        A->coarse_B = coarse_dist ? Partition(nc, P).B : nc;
+        A->cbuf_n = coarse_dist ? A->coarse_B * P : nc;
+        DCSR_CUDA(cudaMalloc(&A->cbuf, ((size_t)A->cbuf_n + 2) * sizeof(double)));
+        DCSR_CUDA(cudaMemsetAsync(A->cbuf, 0, ((size_t)A->cbuf_n + 2) * sizeof(double), ctx->stream));
+        A->bytes += (size_t)A->cbuf_n * sizeof(double);
+    }
+    DCSR_CUDA(cudaStreamSynchronize(ctx->stream));
+#undef DCSR_CUDA
+
+    // who exchanges with whom (identical on every rank: derived from the global matrix)
+    {
+        std::vector<unsigned char> dep;
+        const int me = rank;
+        if (kind == B200_CK_SQUARE) {
+            const Partition part(nrows, P);
+            dependency_matrix(part, part, ptr, col, dep);
+            for (int q = 0; q < P; ++q) {
+                A->need_from[q] = q != me && dep[(size_t)me * P + q];
+                A->needed_by[q] = q != me && dep[(size_t)q * P + me];
+            }
+        } else if (kind == B200_CK_PROLONG) {
+            // consumer p (fine rows) needs the coarse entries owned by o
+            const Partition fine(nrows, P);
+            const Partition coarse = A->coarse_dist ? Partition(ncols, P) : Partition(ncols, 1);
+            if (A->coarse_dist) {
+                dependency_matrix(fine, coarse, ptr, col, dep);
+                for (int q = 0; q < P; ++q) {
+                    A->need_from[q] = dep[(size_t)me * P + q];
+                    A->needed_by[q] = dep[(size_t)q * P + me];
+                }
+            } else {
+                for (int q = 0; q < P; ++q) {
+                    const bool has = (int64_t)ptr[fine.hi(q)] > (int64_t)ptr[fine.lo(q)];
+                    if (me == 0) A->needed_by[q] = q != 0 && has;
+                    if (q == 0) A->need_from[0] = me != 0 && (int64_t)ptr[fine.hi(me)] > (int64_t)ptr[fine.lo(me)];
+                }
+            }
+        } else {
+            // producer r (fine columns) contributes to the coarse rows owned by o
+            const Partition fine(ncols, P);
+            if (A->coarse_dist) {
+                const Partition coarse(nrows, P);
+                dependency_matrix(coarse, fine, ptr, col, dep);     // dep[o][r]
+                for (int q = 0; q < P; ++q) {
+                    A->need_from[q] = dep[(size_t)me * P + q];       // r = q contributes to me
+                    A->needed_by[q] = dep[(size_t)q * P + me];       // I contribute to owner q
+                }
+            } else {
+                std::vector<unsigned char> has((size_t)P, 0);
+                for (int64_t e = 0; e < nnz; ++e) has[(size_t)fine.owner((int64_t)col[e])] = 1;
+                A->needed_by[0] = has[(size_t)me];
+                if (me == 0)
+                    for (int q = 0; q < P; ++q) A->need_from[q] = has[(size_t)q];
+            }
+        }
+    }
+    if (ctx->p2p) {
+        size_t half = 16;
+        if (kind == B200_CK_SQUARE) half = (size_t)P * (size_t)A->S * sizeof(double);
+        else if (kind == B200_CK_PROLONG) half = (size_t)A->cbuf_n * sizeof(double);
+        else if (A->coarse_dist) half = (size_t)P * (size_t)A->coarse_B * sizeof(double);
+        else if (rank == 0) half = (size_t)P * (size_t)nrows * sizeof(double);
+        half = (half + 255) & ~size_t(255);
+        A->pb_half = half;
+        // layout of the buffer a producer writes INTO (the owner's): equal to mine except for
+        // a restriction onto a rank-0-only level, where only rank 0 holds the staging area
+        A->pb_half_owner = half;
+        if (kind == B200_CK_RESTRICT && !A->coarse_dist)
+            A->pb_half_owner = (((size_t)P * (size_t)nrows * sizeof(double)) + 255) & ~size_t(255);
+        int rc2 = peer_alloc(ctx, kFlagBytes + 2 * half, &A->pb_local, A->pb_peer);
+        if (rc2) {
+            csr_free(A);
+            return rc2;
+        }
+        A->bytes += kFlagBytes + 2 * half;
+    }
+    *out = A;
+    return B200_OK;
+}
+
+// ---- launch one streaming pass over A ------------------------------------------------
+// P = precision combination (csr_kernels.cuh).  Only FP64 carries the multi-GPU halo path
+// and the one-block-per-CTA cross-check variant; the mixed-precision combinations use the
+// persistent ring only.
+template <int MODE, int L, bool HALO, class P>
+static int launch_csr_LH(b200_ctx_t ctx, b200_csr_t A, const CsrArgsT<P> &args) {
+    constexpr bool fp64 = std::is_same<P, PrecDD>::value;
+    const StageLayout lay = stage_layout(A->rows_cap, A->nnz_cap, (int)sizeof(typename P::TV));
+    if (fp64 && ctx->opt_spmv_variant == 0) {
+        const int smem = kHeaderBytes + lay.bytes;
+        static bool attr_set[64] = {};   // per instantiation and device
+        if (!attr_set[ctx->device & 63]) {
+            B200_CUDA(cudaFuncSetAttribute(csr_block_kernel<MODE, L, HALO, PrecDD>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_set[ctx->device & 63] = true;
+        }
+        // (only reachable with P == PrecDD)
+        csr_block_kernel<MODE, L, HALO, PrecDD><<<(unsigned)A->nblocks, kThreads, smem, ctx->stream>>>(
+            *reinterpret_cast<const CsrArgsT<PrecDD> *>(&args));
+    } else {
+        int stages = (int)ctx->opt_stages;
+        const int max_smem = 227 * 1024;
+        const int per_cta_budget = max_smem / (int)ctx->opt_ctas_per_sm - 1024;
+        while (stages > 1 && kHeaderBytes + stages * lay.bytes > per_cta_budget) --stages;
+        const int smem = kHeaderBytes + stages * lay.bytes;
+        static bool attr_set[64] = {};
+        if (!attr_set[ctx->device & 63]) {
+            B200_CUDA(cudaFuncSetAttribute(csr_ring_kernel<MODE, L, HALO, P>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+            attr_set[ctx->device & 63] = true;
+        }
+        const int64_t cap = (int64_t)ctx->sm_count * ctx->opt_ctas_per_sm;
+        const unsigned grid = (unsigned)std::min<int64_t>(A->nblocks, cap);
+        B200_CUDA(launch_pdl(ctx, csr_ring_kernel<MODE, L, HALO, P>, dim3(grid), dim3(kThreads), (size_t)smem,
+                             args, stages));
+    }
+    B200_CHECK_LAUNCH();
+    ctx->launches++;
+    return B200_OK;
+}
+
+template <int MODE, int L, class P>
+static int launch_csr_L(b200_ctx_t ctx, b200_csr_t A, const CsrArgsT<P> &args) {
+    if (std::is_same<P, PrecDD>::value && args.xh)
+        return launch_csr_LH<MODE, L, true, PrecDD>(ctx, A, *reinterpret_cast<const CsrArgsT<PrecDD> *>(&args));
+    return launch_csr_LH<MODE, L, false, P>(ctx, A, args);
+}
+
+template <int MODE, class P>
+static int launch_csr(b200_ctx_t ctx, b200_csr_t A, const CsrArgsT<P> &args) {
+    if (A->nblocks == 0) return B200_OK;
+    if (ctx->recording) A->in_graph = true;
+    ProfScope prof(ctx, MODE, A->nrows, A->ncols, A->nnz);
+    switch (A->lanes) {
+    case 1:  return launch_csr_L<MODE, 1>(ctx, A, args);
+    case 2:  return launch_csr_L<MODE, 2>(ctx, A, args);
+    case 4:  return launch_csr_L<MODE, 4>(ctx, A, args);
+    case 8:  return launch_csr_L<MODE, 8>(ctx, A, args);
+    case 16: return launch_csr_L<MODE, 16>(ctx, A, args);
+    default: return launch_csr_L<MODE, 32>(ctx, A, args);
+    }
+}
+
+template <class P>
+static CsrArgsT<P> base_args_t(b200_csr_t A) {
+    CsrArgsT<P> a;
+    memset(&a, 0, sizeof(a));
+    a.ptr = A->ptr; a.col = A->col; a.val = static_cast<const typename P::TV *>(A->val); a.blk = A->blk;
+    a.nrows = (int)A->nrows; a.nblocks = (int)A->nblocks;
+    a.rows_cap = A->rows_cap; a.nnz_cap = A->nnz_cap;
+    return a;
+}
+static CsrArgs base_args(b200_csr_t A) { return base_args_t<PrecDD>(A); }
+
+// multi-GPU: make the boundary values of a.x visible and tell the kernel where they are
+static int halo_into(b200_ctx_t ctx, b200_csr_t A, CsrArgs &a) {
+    HaloArgs h;
+    const int rc = halo_exchange(ctx, A, a.x, h);
+    if (rc) return rc;
+    a.xh = h.xh; a.nloc = h.nloc;
+    a.blk_halo = h.blk_halo; a.wait_flags = h.wait_flags; a.wait_mask = h.wait_mask; a.wait_seq = h.wait_seq;
+    return B200_OK;
+}
+
+
+} // namespace b200
+
+extern "C" int b200_csr_create_i64(b200_ctx_t ctx, int64_t nrows, int64_t ncols,
+                                   const int64_t *ptr, const int64_t *col, const double *val,
+                                   b200_csr_t *A) {
+    return csr_create(ctx, nrows, ncols, ptr, col, val, A);
+}
+
+extern "C" int b200_csr_create_i32(b200_ctx_t ctx, int64_t nrows, int64_t ncols,
+                                   const int32_t *ptr, const int32_t *col, const double *val,
+                                   b200_csr_t *A) {
+    return csr_create(ctx, nrows, ncols, ptr, col, val, A);
+}
+
+extern "C" int b200_csr_create_i64_f32(b200_ctx_t ctx, int64_t nrows, int64_t ncols,
+                                       const int64_t *ptr, const int64_t *col, const float *val,
+                                       b200_csr_t *A) {
+    return csr_create_f32(ctx, nrows, ncols, ptr, col, val, A);
+}
+
+extern "C" int b200_csr_create_i32_f32(b200_ctx_t ctx, int64_t nrows, int64_t ncols,
+                                       const int32_t *ptr, const int32_t *col, const float *val,
+                                       b200_csr_t *A) {
+    return csr_create_f32(ctx, nrows, ncols, ptr, col, val, A);
+}
+
+extern "C" int b200_csr_dtype(b200_csr_t A, int *dtype) {
+    B200_REQUIRE(A && dtype, "null argument");
+    *dtype = A->dtype;
+    return B200_OK;
+}
+
+extern "C" int b200_plan_i64(int64_t nrows, const int64_t *ptr, int lanes, int nnz_cap,
+                             int32_t *blk_out, int64_t blk_capacity, int64_t *nblocks,
+                             int *lanes_out, int *rows_cap_out, int64_t *nlong_out) {
+    B200_REQUIRE(nrows >= 0 && ptr != nullptr && nblocks != nullptr, "bad argument");
+    B200_REQUIRE(nnz_cap >= 256 && nnz_cap <= kNnzCapMax && nnz_cap % 8 == 0, "bad nnz_cap");
+    B200_REQUIRE(lanes == 0 || (lanes >= 1 && lanes <= 32 && !(lanes & (lanes - 1))), "bad lanes");
+    RowBlockPlan plan;
+    build_plan(nrows, ptr, lanes, nnz_cap, plan);
+    *nblocks = (int64_t)plan.blk.size() - 1;
+    if (lanes_out) *lanes_out = plan.lanes;
+    if (rows_cap_out) *rows_cap_out = plan.rows_cap;
+    if (nlong_out) *nlong_out = plan.nlong;
+    if (blk_out) {
+        if ((int64_t)plan.blk.size() > blk_capacity)
+            return fail(B200_EINVAL, "plan output buffer too small");
+        for (size_t i = 0; i < plan.blk.size(); ++i) {
+            blk_out[2 * i] = plan.blk[i].x;
+            blk_out[2 * i + 1] = plan.blk[i].y;
+        }
+    }
+    return B200_OK;
+}
+
+extern "C" int b200_csr_destroy(b200_csr_t A) {
+    if (!A) return B200_OK;
+    NOT_RECORDING(A->ctx, "matrix destruction");
+    if (A->in_graph) A->ctx->destroy_epoch++;
+    GUARD(A->ctx);
+    csr_free(A);
+    return B200_OK;
+}
+
+extern "C" int b200_csr_rows(b200_csr_t A, size_t *n) {
+    B200_REQUIRE(A && n, "null argument");
+    *n = (size_t)A->gl_rows;
+    return B200_OK;
+}
+extern "C" int b200_csr_cols(b200_csr_t A, size_t *n) {
+    B200_REQUIRE(A && n, "null argument");
+    *n = (size_t)A->gl_cols;
+    return B200_OK;
+}
+extern "C" int b200_csr_nonzeros(b200_csr_t A, size_t *n) {
+    B200_REQUIRE(A && n, "null argument");
+    *n = (size_t)A->gl_nnz;
+    return B200_OK;
+}
+extern "C" int b200_csr_bytes(b200_csr_t A, size_t *bytes) {
+    B200_REQUIRE(A && bytes, "null argument");
+    *bytes = A->bytes;
+    return B200_OK;
+}
+extern "C" int b200_csr_plan(b200_csr_t A, int *lanes_per_row, int64_t *n_blocks,
+                             int64_t *n_long_blocks) {
+    B200_REQUIRE(A, "null argument");
+    if (lanes_per_row) *lanes_per_row = A->lanes;
+    if (n_blocks) *n_blocks = A->nblocks;
+    if (n_long_blocks) *n_long_blocks = A->nlong;
+    return B200_OK;
+}
+
+// ---------------------------------------------------------------------------
+// primitives
+// ---------------------------------------------------------------------------
+namespace b200 {
+
+template <class P>
+static int spmv_local(b200_ctx_t ctx, double alpha, b200_csr_t A, b200_vec_t x, double beta,
+                      b200_vec_t y) {
+    CsrArgsT<P> a = base_args_t<P>(A);
+    const double *px;
+    int rc = rd(x, &px);
+    if (rc) return rc;
+    a.x = tp<typename P::TX>(px);
+    a.alpha = alpha; a.beta = beta;
+    if (beta == 0.0 || y->zero_pending) {
+        a.y = tp<typename P::TY>(wr(y));
+        return launch_csr<MODE_SPMV>(ctx, A, a);
+    }
+    a.y = tp<typename P::TY>(y->ptr);
+    return launch_csr<MODE_SPMV_ACC>(ctx, A, a);
+}
+
+template <class P>
+static int residual_local(b200_ctx_t ctx, b200_vec_t f, b200_csr_t A, b200_vec_t x, b200_vec_t r) {
+    CsrArgsT<P> a = base_args_t<P>(A);
+    const double *px, *pf;
+    int rc = rd(x, &px);
+    if (rc) return rc;
+    rc = rd(f, &pf);
+    if (rc) return rc;
+    a.x = tp<typename P::TX>(px);
+    a.f = tp<typename P::TF>(pf);
+    a.y = tp<typename P::TY>((f == r) ? r->ptr : wr(r));
+    return launch_csr<MODE_RESID>(ctx, A, a);
+}
+
+
+} // namespace b200
+
+extern "C" int b200_spmv(b200_ctx_t ctx, double alpha, b200_csr_t A, b200_vec_t x, double beta,
+                         b200_vec_t y) {
+    CHECK_CTX(ctx);
+    B200_REQUIRE(A && x && y, "null argument");
+    touch(ctx, {x, y});
+    B200_REQUIRE((int64_t)x->n == A->gl_cols, "spmv: x size != matrix columns");
+    B200_REQUIRE((int64_t)y->n == A->gl_rows, "spmv: y size != matrix rows");
+    B200_REQUIRE(x != y && (x->ptr != y->ptr || !x->ptr), "spmv: x and y must not alias");
+    if (A->kind == B200_CK_GHOST) return B200_OK;          // operator lives on rank 0
+    GUARD(ctx);
+    if (A->dtype == B200_F32) {
+        // FP32 operator (mixed-precision hierarchy): single GPU, persistent ring kernels
+        if (all32({x, y})) return spmv_local<PrecFF>(ctx, alpha, A, x, beta, y);
+        if (all64({x, y})) return spmv_local<PrecFD>(ctx, alpha, A, x, beta, y);
+        if (x->dtype == B200_F32 && y->dtype == B200_F64)
+            return spmv_local<PrecFFD>(ctx, alpha, A, x, beta, y);
+        return B200_BAD_MIX("spmv");
+    }
+    if (!all64({x, y})) return B200_BAD_MIX("spmv");
+    CsrArgs a = base_args(A);
+    a.alpha = alpha; a.beta = beta;
+    int rc;
+    if (A->kind == B200_CK_PROLONG) {
+        B200_REQUIRE(y->kind == B200_VK_DIST, "prolongation: y must be a partitioned vector");
+        rc = coarse_to_all(ctx, A, x, &a.x);
+        if (rc) return rc;
+    } else if (A->kind == B200_CK_RESTRICT) {
+        B200_REQUIRE(beta == 0.0, "restriction on a distributed context needs beta == 0");
+        B200_REQUIRE(x->kind == B200_VK_DIST, "restriction: x must be a partitioned vector");
+        rc = rd(x, &a.x);
+        if (rc) return rc;
+        a.y = A->cbuf;
+        rc = launch_csr<MODE_SPMV>(ctx, A, a);
+        if (rc) return rc;
+        return partials_to_coarse(ctx, A, y);
+    } else {
+        rc = rd(x, &a.x);
+        if (rc) return rc;
+        if (A->kind == B200_CK_SQUARE) {
+            B200_REQUIRE(x->kind == B200_VK_DIST && y->kind == B200_VK_DIST,
+                         "spmv: vectors must be partitioned like the operator");
+            rc = halo_into(ctx, A, a);
+            if (rc) return rc;
+        }
+    }
+    if (beta == 0.0 || y->zero_pending) {
+        a.y = wr(y);
+        return launch_csr<MODE_SPMV>(ctx, A, a);
+    }
+    a.y = y->ptr;
+    return launch_csr<MODE_SPMV_ACC>(ctx, A, a);
+}
+
+extern "C" int b200_residual(b200_ctx_t ctx, b200_vec_t f, b200_csr_t A, b200_vec_t x,
+                             b200_vec_t r) {
+    CHECK_CTX(ctx);
+    B200_REQUIRE(f && A && x && r, "null argument");
+    touch(ctx, {f, x, r});
+    B200_REQUIRE((int64_t)x->n == A->gl_cols, "residual: x size != matrix columns");
+    B200_REQUIRE((int64_t)f->n == A->gl_rows && (int64_t)r->n == A->gl_rows,
+                 "residual: rhs/r size != matrix rows");
+    B200_REQUIRE(x != r && (x->ptr != r->ptr || !x->ptr), "residual: x and r must not alias");
+    if (A->kind == B200_CK_GHOST) return B200_OK;
+    B200_REQUIRE(A->kind == B200_CK_LOCAL || A->kind == B200_CK_SQUARE,
+                 "residual: operator must be square");
+    GUARD(ctx);
+    if (A->dtype == B200_F32) {
+        if (all32({f, x, r})) return residual_local<PrecFF>(ctx, f, A, x, r);
+        if (all64({f, x, r})) return residual_local<PrecFD>(ctx, f, A, x, r);
+        if (all64({f, x}) && r->dtype == B200_F32) return residual_local<PrecFDF>(ctx, f, A, x, r);
+        return B200_BAD_MIX("residual");
+    }
+    if (!all64({f, x, r})) return B200_BAD_MIX("residual");
+    CsrArgs a = base_args(A);
+    int rc = rd(x, &a.x);
+    if (rc) return rc;
+    rc = rd(f, &a.f);
+    if (rc) return rc;
+    if (A->kind == B200_CK_SQUARE) {
+        B200_REQUIRE(x->kind == B200_VK_DIST && f->kind == B200_VK_DIST && r->kind == B200_VK_DIST,
+                     "residual: vectors must be partitioned like the operator");
+        rc = halo_into(ctx, A, a);
+        if (rc) return rc;
+    }
+    a.y = (f == r) ? r->ptr : wr(r);   // r == f is fine: each row reads f[r] before writing
+    return launch_csr<MODE_RESID>(ctx, A, a);
+}
+
+// ---------------------------------------------------------------------------
+// smoother sweep
+// ---------------------------------------------------------------------------
+namespace b200 {
+
+template <class TD, class TF, class TX>
+static int relax_zero_t(b200_ctx_t ctx, double omega, const double *pd, const double *pf, b200_vec_t x) {
+    if (x->len) {
+        const int grid = grid_for(ctx, x->len, 2);
+        ProfScope prof(ctx, B200_PROF_RELAX_ZERO, (int64_t)x->len, 1, 0);
+        B200_CUDA(launch_pdl(ctx, relax_zero_kernel<TD, TF, TX>, dim3(grid), dim3(kThreads), 0, x->len, omega,
+                             tp<TD>(pd), tp<TF>(pf), tp<TX>(wr(x))));
+        B200_CHECK_LAUNCH();
+        ctx->launches++;
+    }
+    x->zero_pending = false;
+    return B200_OK;
+}
+
+} // namespace b200
+
+extern "C" int b200_relax(b200_ctx_t ctx, b200_csr_t A, b200_vec_t rhs, b200_vec_t x,
+                          b200_vec_t tmp, b200_vec_t diag, double omega) {
+    CHECK_CTX(ctx);
+    B200_REQUIRE(A && rhs && x && tmp && diag, "null argument");
+    touch(ctx, {rhs, x, tmp, diag});
+    B200_REQUIRE(A->gl_rows == A->gl_cols, "relax: matrix must be square");
+    B200_REQUIRE((int64_t)x->n == A->gl_rows && same_layout(x, rhs) && same_layout(x, diag) &&
+                     same_layout(x, tmp),
+                 "relax: vector size != matrix rows");
+    B200_REQUIRE(x != tmp && x != rhs && tmp != rhs, "relax: x, tmp and rhs must be distinct vectors");
+    if (A->kind == B200_CK_GHOST) return B200_OK;
+    B200_REQUIRE(x->ptr != tmp->ptr, "relax: x and tmp must not alias");
+    GUARD(ctx);
+
+    // precision combination: 0 = FP64 throughout, 1 = FP32 throughout,
+    // 2 = FP32 operator + diagonal sweeping an FP64 iterate (finest level of a mixed hierarchy;
+    //     tmp is that level's FP32 scratch)
+    int mix = -1;
+    if (A->dtype == B200_F64 && all64({rhs, x, tmp, diag})) mix = 0;
+    else if (A->dtype == B200_F32 && all32({rhs, x, tmp, diag})) mix = 1;
+    else if (A->dtype == B200_F32 && all64({rhs, x}) && all32({tmp, diag})) mix = 2;
+    if (mix < 0) return B200_BAD_MIX("relax");
+
+    const double *pf, *pd;
+    int rc = rd(rhs, &pf);
+    if (rc) return rc;
+    rc = rd(diag, &pd);
+    if (rc) return rc;
+
+    if (x->zero_pending && ctx->opt_zero_shortcut) {
+        // residual(rhs, A, 0) == rhs exactly, so the sweep reduces to a scaling
+        if (mix == 0) return relax_zero_t<double, double, double>(ctx, omega, pd, pf, x);
+        if (mix == 1) return relax_zero_t<float, float, float>(ctx, omega, pd, pf, x);
+        return relax_zero_t<float, double, double>(ctx, omega, pd, pf, x);
+    }
+
+    if (!ctx->opt_fuse_relax) {
+        // the literal reference sequence: tmp = rhs - A x ; x = omega*diag.*tmp + x
+        rc = b200_residual(ctx, rhs, A, x, tmp);
+        if (rc) return rc;
+        return b200_vmul(ctx, omega, diag, tmp, 1.0, x);
+    }
+
+    if (mix == 1) {
+        CsrArgsT<PrecFF> a = base_args_t<PrecFF>(A);
+        const double *px;
+        rc = rd(x, &px);
+        if (rc) return rc;
+        a.x = tp<float>(px); a.f = tp<float>(pf); a.d = tp<float>(pd); a.alpha = omega;
+        a.y = tp<float>(wr(tmp));
+        rc = launch_csr<MODE_RELAX>(ctx, A, a);
+        if (rc) return rc;
+        if (x->owned && tmp->owned && x->cap == tmp->cap) std::swap(x->ptr, tmp->ptr);
+        else B200_CUDA(cudaMemcpyAsync(x->ptr, tmp->ptr, x->len * x->esz, cudaMemcpyDeviceToDevice, ctx->stream));
+        return B200_OK;
+    }
+    if (mix == 2) {
+        // the new FP64 iterate cannot live in the level's FP32 scratch: the operator owns an
+        // FP64 buffer that trades places with x exactly like tmp does in the uniform case
+        if (!A->scratch64)
+            B200_CUDA(cudaMalloc(&A->scratch64, ((size_t)A->nrows + 4) * sizeof(double)));
+        if (ctx->recording) touch_slot(ctx, &A->scratch64, nullptr);
+        CsrArgsT<PrecFD> a = base_args_t<PrecFD>(A);
+        const double *px;
+        rc = rd(x, &px);
+        if (rc) return rc;
+        a.x = px; a.f = pf; a.d = tp<float>(pd); a.alpha = omega;
+        a.y = A->scratch64;
+        rc = launch_csr<MODE_RELAX>(ctx, A, a);
+        if (rc) return rc;
+        if (x->owned && x->cap == (size_t)A->nrows) std::swap(x->ptr, A->scratch64);
+        else B200_CUDA(cudaMemcpyAsync(x->ptr, A->scratch64, x->len * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        return B200_OK;
+    }
+
+    CsrArgs a = base_args(A);
+    rc = rd(x, &a.x);
+    if (rc) return rc;
+    if (A->kind == B200_CK_SQUARE) {
+        B200_REQUIRE(x->kind == B200_VK_DIST, "relax: vectors must be partitioned like the operator");
+        rc = halo_into(ctx, A, a);
+        if (rc) return rc;
+    }
+    a.f = pf; a.d = pd; a.alpha = omega;
+    a.y = wr(tmp);
+    rc = launch_csr<MODE_RELAX>(ctx, A, a);
+    if (rc) return rc;
+    if (x->owned && tmp->owned && x->cap == tmp->cap) {
+        std::swap(x->ptr, tmp->ptr);          // x now holds the new iterate
+    } else {
+        B200_CUDA(cudaMemcpyAsync(x->ptr, tmp->ptr, x->len * sizeof(double),
+                                  cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    return B200_OK;
+}
+

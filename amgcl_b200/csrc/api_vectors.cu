@@ -1,0 +1,436 @@
+// api_vectors.cu -- vectors, element-wise kernels, inner product
+//
+// Part of the implementation of the C ABI declared in include/amgcl_b200.h (host-side logic
+// only: argument checking, bookkeeping, kernel launches; no CPU fallback anywhere).
+#include "internal.cuh"
+#include "vec_kernels.cuh"
+
+using namespace b200;
+
+// ---------------------------------------------------------------------------
+// vectors
+// ---------------------------------------------------------------------------
+static int vec_create_typed(b200_ctx_t ctx, size_t n, int dtype, b200_vec_t *out) {
+    CHECK_CTX(ctx);
+    NOT_RECORDING(ctx, "vector creation");
+    B200_REQUIRE(out != nullptr, "null output pointer");
+    *out = nullptr;
+    if (dtype == B200_F32) B200_REQUIRE_F64_DIST(ctx, "b200_vec_create_f32");
+    GUARD(ctx);
+    b200_vec_s *v = new (std::nothrow) b200_vec_s();
+    if (!v) return fail(B200_ENOMEM, "out of host memory");
+    v->ctx = ctx;
+    v->n = n;
+    v->owned = true;
+    v->dtype = dtype;
+    v->esz = dtype == B200_F32 ? sizeof(float) : sizeof(double);
+    if (ctx->dist && (int64_t)n >= ctx->dist_min_rows) {
+        const Partition part((int64_t)n, ctx->nranks);
+        v->kind = B200_VK_DIST;
+        v->off = (size_t)part.lo(ctx->rank);
+        v->len = (size_t)part.count(ctx->rank);
+        v->cap = (size_t)part.B;
+    } else if (ctx->dist && ctx->rank != 0) {
+        v->kind = B200_VK_GHOST;      // the object lives on rank 0; operations here are no-ops
+        v->len = 0;
+        v->cap = 0;
+        v->zero_pending = false;
+        *out = v;
+        return B200_OK;
+    } else {
+        v->kind = B200_VK_LOCAL;
+        v->len = n;
+        v->cap = n;
+    }
+    // +2 doubles of padding so 16-byte vector accesses of the tail stay in bounds
+    cudaError_t rc = cudaMalloc(&v->ptr, (v->cap + 4) * v->esz);
+    if (rc != cudaSuccess) {
+        delete v;
+        return cuda_fail(rc, "cudaMalloc(vector)", __FILE__, __LINE__);
+    }
+    if (v->cap > v->len) {
+        // padding of a partial block takes part in collectives: keep it zero
+        rc = cudaMemsetAsync(v->ptr + v->len, 0, (v->cap - v->len) * sizeof(double), ctx->stream);
+        if (rc != cudaSuccess) {
+            cudaFree(v->ptr);
+            delete v;
+            return cuda_fail(rc, "cudaMemsetAsync(vector padding)", __FILE__, __LINE__);
+        }
+    }
+    v->zero_pending = true;   // logically zero; memset only if somebody looks
+    *out = v;
+    return B200_OK;
+}
+
+extern "C" int b200_vec_create(b200_ctx_t ctx, size_t n, b200_vec_t *out) {
+    return vec_create_typed(ctx, n, B200_F64, out);
+}
+
+extern "C" int b200_vec_create_f32(b200_ctx_t ctx, size_t n, b200_vec_t *out) {
+    return vec_create_typed(ctx, n, B200_F32, out);
+}
+
+extern "C" int b200_vec_dtype(b200_vec_t v, int *dtype) {
+    B200_REQUIRE(v && dtype, "null argument");
+    *dtype = v->dtype;
+    return B200_OK;
+}
+
+extern "C" int b200_vec_wrap(b200_ctx_t ctx, double *device_ptr, size_t n, b200_vec_t *out) {
+    CHECK_CTX(ctx);
+    B200_REQUIRE(out != nullptr, "null output pointer");
+    B200_REQUIRE(device_ptr != nullptr || n == 0, "null device pointer");
+    B200_REQUIRE((reinterpret_cast<uintptr_t>(device_ptr) & 7) == 0, "device pointer not 8-byte aligned");
+    B200_REQUIRE(!ctx->dist, "b200_vec_wrap is not available on a distributed context");
+    b200_vec_s *v = new (std::nothrow) b200_vec_s();
+    if (!v) return fail(B200_ENOMEM, "out of host memory");
+    v->ctx = ctx;
+    v->n = n;
+    v->len = n;
+    v->cap = n;
+    v->ptr = device_ptr;
+    v->owned = false;
+    v->zero_pending = false;
+    *out = v;
+    return B200_OK;
+}
+
+extern "C" int b200_vec_destroy(b200_vec_t v) {
+    if (!v) return B200_OK;
+    if (v->in_graph) v->ctx->destroy_epoch++;      // recorded graphs that refer to it are dead
+    if (b200_graph_s *g = v->ctx->recording) {
+        // (e.g. a garbage-collected handle of the host language)  The recording may already
+        // use the storage: it is released after the recorded calls have run.
+        for (size_t i = 0; i < g->slots.size();)
+            if (g->slots[i].slot == &v->ptr) g->slots.erase(g->slots.begin() + i);
+            else ++i;
+        if (v->owned && v->ptr) v->ctx->graph_deferred.push_back(v->ptr);
+        delete v;
+        return B200_OK;
+    }
+    GUARD(v->ctx);
+    if (v->owned && v->ptr) {
+        // cudaFree synchronises the device, so no kernel can still be using it
+        cudaFree(v->ptr);
+    }
+    delete v;
+    return B200_OK;
+}
+
+extern "C" int b200_vec_size(b200_vec_t v, size_t *n) {
+    B200_REQUIRE(v && n, "null argument");
+    *n = v->n;
+    return B200_OK;
+}
+
+extern "C" int b200_vec_bytes(b200_vec_t v, size_t *bytes) {
+    B200_REQUIRE(v && bytes, "null argument");
+    *bytes = v->len * v->esz;
+    return B200_OK;
+}
+
+extern "C" int b200_vec_data(b200_vec_t v, double **device_ptr) {
+    B200_REQUIRE(v && device_ptr, "null argument");
+    B200_REQUIRE(v->dtype == B200_F64, "b200_vec_data: FP64 vectors only");
+    GUARD(v->ctx);
+    int rc = materialize(v);
+    *device_ptr = v->ptr;
+    return rc;
+}
+
+extern "C" int b200_vec_upload_f32(b200_vec_t v, const float *host, size_t n) {
+    B200_REQUIRE(v && (host || n == 0), "null argument");
+    NOT_RECORDING(v->ctx, "host transfer");
+    B200_REQUIRE(n == v->n, "size mismatch in vector upload");
+    B200_REQUIRE(v->dtype == B200_F32 && v->kind == B200_VK_LOCAL, "upload_f32: FP32 local vector expected");
+    GUARD(v->ctx);
+    if (n) {
+        B200_CUDA(cudaMemcpyAsync(wr(v), host, n * sizeof(float), cudaMemcpyHostToDevice, v->ctx->stream));
+        B200_CUDA(cudaStreamSynchronize(v->ctx->stream));
+    }
+    v->zero_pending = false;
+    return B200_OK;
+}
+
+extern "C" int b200_vec_download_f32(b200_vec_t v, float *host, size_t n) {
+    B200_REQUIRE(v && (host || n == 0), "null argument");
+    NOT_RECORDING(v->ctx, "host transfer");
+    B200_REQUIRE(n == v->n, "size mismatch in vector download");
+    B200_REQUIRE(v->dtype == B200_F32 && v->kind == B200_VK_LOCAL, "download_f32: FP32 local vector expected");
+    GUARD(v->ctx);
+    if (!n) return B200_OK;
+    int rc = materialize(v);
+    if (rc) return rc;
+    B200_CUDA(cudaMemcpyAsync(host, v->ptr, n * sizeof(float), cudaMemcpyDeviceToHost, v->ctx->stream));
+    B200_CUDA(cudaStreamSynchronize(v->ctx->stream));
+    return B200_OK;
+}
+
+extern "C" int b200_vec_upload(b200_vec_t v, const double *host, size_t n) {
+    B200_REQUIRE(v && (host || n == 0), "null argument");
+    NOT_RECORDING(v->ctx, "host transfer");
+    B200_REQUIRE(n == v->n, "size mismatch in vector upload");
+    B200_REQUIRE(v->dtype == B200_F64, "b200_vec_upload: FP64 vector expected (use _f32)");
+    GUARD(v->ctx);
+    if (v->kind == B200_VK_GHOST) return B200_OK;
+    if (v->len) {
+        // distributed: every rank is handed the full host vector and keeps its block
+        B200_CUDA(cudaMemcpyAsync(wr(v), host + v->off, v->len * sizeof(double),
+                                  cudaMemcpyHostToDevice, v->ctx->stream));
+        B200_CUDA(cudaStreamSynchronize(v->ctx->stream));
+    }
+    v->zero_pending = false;
+    return B200_OK;
+}
+
+extern "C" int b200_vec_download(b200_vec_t v, double *host, size_t n) {
+    B200_REQUIRE(v && (host || n == 0), "null argument");
+    NOT_RECORDING(v->ctx, "host transfer");
+    B200_REQUIRE(n == v->n, "size mismatch in vector download");
+    B200_REQUIRE(v->dtype == B200_F64, "b200_vec_download: FP64 vector expected (use _f32)");
+    b200_ctx_t ctx = v->ctx;
+    GUARD(ctx);
+    if (!n) return B200_OK;
+    if (v->kind == B200_VK_GHOST) {          // lives on rank 0 only
+        memset(host, 0, n * sizeof(double));
+        return B200_OK;
+    }
+    if (v->kind == B200_VK_DIST) {
+        // every rank receives the complete vector: all-gather the blocks, then one D2H copy
+        int rc = materialize(v);
+        if (rc) return rc;
+        double *full = nullptr;
+        B200_CUDA(cudaMalloc(&full, (size_t)ctx->nranks * v->cap * sizeof(double)));
+        ncclResult_t nrc = nccl().AllGather(v->ptr, full, v->cap, ncclDouble, comm_of(ctx), ctx->stream);
+        if (nrc != ncclSuccess) {
+            cudaFree(full);
+            return fail(B200_ENCCL, std::string("ncclAllGather: ") + nccl().GetErrorString(nrc));
+        }
+        cudaError_t crc = cudaMemcpyAsync(host, full, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+        if (crc == cudaSuccess) crc = cudaStreamSynchronize(ctx->stream);
+        cudaFree(full);
+        if (crc != cudaSuccess) return cuda_fail(crc, "download(distributed)", __FILE__, __LINE__);
+        return B200_OK;
+    }
+    if (v->zero_pending) {          // nothing to fetch: the vector is zero
+        B200_CUDA(cudaStreamSynchronize(ctx->stream));
+        memset(host, 0, n * sizeof(double));
+        return B200_OK;
+    }
+    B200_CUDA(cudaMemcpyAsync(host, v->ptr, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA(cudaStreamSynchronize(ctx->stream));
+    return B200_OK;
+}
+
+namespace b200 {
+
+// ---- element-wise launch helpers ----------------------------------------------------------
+// all streams of one element type T: 16-byte vector path when aligned
+template <class F, bool RY, bool RZ, class T>
+static int launch_ew(b200_ctx_t ctx, size_t n, F f, const T *x, const T *y, const T *z, T *out) {
+    if (n == 0) return B200_OK;
+    const bool vec_ok = aligned16(x) && aligned16(out) && (!RY || aligned16(y)) &&
+                        (!RZ || aligned16(z));
+    const int grid = grid_for(ctx, n, 16 / (int)sizeof(T) * 2);
+    ProfScope prof(ctx, B200_PROF_VECTOR + (RY ? 1 : 0) + (RZ ? 1 : 0), (int64_t)n, 1, 0);
+    B200_CUDA(launch_pdl(ctx, ew_kernel_same<F, RY, RZ, T>, dim3(grid), dim3(kThreads), 0, n, f, x, y, z, out,
+                         vec_ok));
+    B200_CHECK_LAUNCH();
+    ctx->launches++;
+    return B200_OK;
+}
+// mixed element types (FP32 inputs accumulated into an FP64 vector, precision-changing copy)
+template <class F, bool RY, bool RZ, class TX, class TY, class TZ, class TO>
+static int launch_ew_mixed(b200_ctx_t ctx, size_t n, F f, const TX *x, const TY *y, const TZ *z,
+                           TO *out) {
+    if (n == 0) return B200_OK;
+    const int grid = grid_for(ctx, n, 2);
+    ProfScope prof(ctx, B200_PROF_VECTOR + (RY ? 1 : 0) + (RZ ? 1 : 0), (int64_t)n, 1, 0);
+    B200_CUDA(launch_pdl(ctx, ew_kernel<F, RY, RZ, TX, TY, TZ, TO>, dim3(grid), dim3(kThreads), 0, n, f, x, y,
+                         z, out, false));
+    B200_CHECK_LAUNCH();
+    ctx->launches++;
+    return B200_OK;
+}
+
+} // namespace b200
+
+extern "C" int b200_clear(b200_ctx_t ctx, b200_vec_t x) {
+    CHECK_CTX(ctx);
+    B200_REQUIRE(x, "null argument");
+    touch(ctx, {x});
+    if (x->kind == B200_VK_GHOST) return B200_OK;
+    if (ctx->opt_zero_shortcut) {
+        x->zero_pending = true;
+        return B200_OK;
+    }
+    GUARD(ctx);
+    x->zero_pending = true;
+    return materialize(x);
+}
+
+extern "C" int b200_copy(b200_ctx_t ctx, b200_vec_t x, b200_vec_t y) {
+    CHECK_CTX(ctx);
+    B200_REQUIRE(x && y, "null argument");
+    touch(ctx, {x, y});
+    B200_REQUIRE(same_layout(x, y), "copy: size mismatch");
+    if (x->kind == B200_VK_GHOST || x == y || x->ptr == y->ptr) return B200_OK;
+    if (x->zero_pending) {
+        y->zero_pending = true;
+        return B200_OK;
+    }
+    GUARD(ctx);
+    if (all64({x, y}))
+        return launch_ew<CopyF<double>, false, false, double>(ctx, x->len, CopyF<double>(), x->ptr, nullptr, nullptr, wr(y));
+    if (all32({x, y}))
+        return launch_ew<CopyF<float>, false, false, float>(ctx, x->len, CopyF<float>(), tp<float>(x->ptr), nullptr, nullptr, tp<float>(wr(y)));
+    if (x->dtype == B200_F64)      // precision-changing copies
+        return launch_ew_mixed<CopyF<float>, false, false>(ctx, x->len, CopyF<float>(), x->ptr, (const float *)nullptr, (const float *)nullptr, tp<float>(wr(y)));
+    return launch_ew_mixed<CopyF<double>, false, false>(ctx, x->len, CopyF<double>(), tp<float>(x->ptr), (const double *)nullptr, (const double *)nullptr, wr(y));
+}
+
+namespace b200 {
+template <class T>
+static void launch_dot_kernel(b200_ctx_t ctx, b200_vec_t x, b200_vec_t y, double *result_dev) {
+    const bool vec_ok = aligned16(x->ptr) && aligned16(y->ptr);
+    const int grid = std::min(grid_for(ctx, x->len, 32 / (int)sizeof(T) * 2), kDotMaxBlocks);
+    ProfScope prof(ctx, B200_PROF_DOT, (int64_t)x->len, 1, 0);
+    const cudaError_t rc = launch_pdl(ctx, dot_kernel<T>, dim3(grid), dim3(kThreads), 0, x->len,
+                                      (const T *)tp<T>(x->ptr), (const T *)tp<T>(y->ptr), ctx->dot_partial,
+                                      ctx->dot_ticket, result_dev, vec_ok);
+    if (rc != cudaSuccess) cuda_fail(rc, "dot_kernel launch", __FILE__, __LINE__);
+}
+} // namespace b200
+
+extern "C" int b200_dot(b200_ctx_t ctx, b200_vec_t x, b200_vec_t y, double *result) {
+    CHECK_CTX(ctx);
+    B200_REQUIRE(x && y && result, "null argument");
+    NOT_RECORDING(ctx, "dot (host-synchronous)");
+    B200_REQUIRE(same_layout(x, y), "dot: size mismatch");
+    if (x->dtype != y->dtype) return B200_BAD_MIX("dot");
+    GUARD(ctx);
+    const bool dist = x->kind == B200_VK_DIST;
+    const bool trivial = x->len == 0 || x->zero_pending || y->zero_pending || x->kind == B200_VK_GHOST;
+    if (!dist) {
+        if (trivial) {
+            B200_CUDA(cudaStreamSynchronize(ctx->stream));
+            *result = 0.0;
+            return B200_OK;
+        }
+        if (x->dtype == B200_F64) launch_dot_kernel<double>(ctx, x, y, ctx->dot_result_d);
+        else launch_dot_kernel<float>(ctx, x, y, ctx->dot_result_d);
+        B200_CHECK_LAUNCH();
+        ctx->launches++;
+        B200_CUDA(cudaStreamSynchronize(ctx->stream));
+        *result = *reinterpret_cast<volatile double *>(ctx->dot_result_h);
+        return B200_OK;
+    }
+    // partitioned vectors: local partial -> device scalar -> all-reduce -> host
+    // (mpi/inner_product.hpp:53-62 does the same with MPI_Allreduce on the host)
+    if (trivial) {
+        B200_CUDA(cudaMemsetAsync(ctx->dot_dev, 0, sizeof(double), ctx->stream));
+    } else {
+        launch_dot_kernel<double>(ctx, x, y, ctx->dot_dev);
+        B200_CHECK_LAUNCH();
+        ctx->launches++;
+    }
+    return dist_dot_finish(ctx, result);
+}
+
+namespace b200 {
+template <class T>
+static int axpby_t(b200_ctx_t ctx, double a, b200_vec_t x, double b, b200_vec_t y) {
+    const double *px;
+    int rc = rd(x, &px);
+    if (rc) return rc;
+    if (b == 0.0 || y->zero_pending) {
+        AxF<T> f{(T)a};
+        return launch_ew<AxF<T>, false, false, T>(ctx, x->len, f, tp<T>(px), nullptr, nullptr, tp<T>(wr(y)));
+    }
+    AxpbyF<T> f{(T)a, (T)b};
+    return launch_ew<AxpbyF<T>, true, false, T>(ctx, x->len, f, tp<T>(px), tp<T>(y->ptr), nullptr, tp<T>(y->ptr));
+}
+template <class T>
+static int axpbypcz_t(b200_ctx_t ctx, double a, b200_vec_t x, double b, b200_vec_t y, double c, b200_vec_t z) {
+    const double *px, *py;
+    int rc = rd(x, &px);
+    if (rc) return rc;
+    rc = rd(y, &py);
+    if (rc) return rc;
+    if (c == 0.0 || z->zero_pending) {
+        AxpbyF<T> f{(T)a, (T)b};
+        return launch_ew<AxpbyF<T>, true, false, T>(ctx, x->len, f, tp<T>(px), tp<T>(py), nullptr, tp<T>(wr(z)));
+    }
+    AxpbypczF<T> f{(T)a, (T)b, (T)c};
+    return launch_ew<AxpbypczF<T>, true, true, T>(ctx, x->len, f, tp<T>(px), tp<T>(py), tp<T>(z->ptr), tp<T>(z->ptr));
+}
+template <class T>
+static int vmul_t(b200_ctx_t ctx, double alpha, b200_vec_t x, b200_vec_t y, double beta, b200_vec_t z) {
+    const double *px, *py;
+    int rc = rd(x, &px);
+    if (rc) return rc;
+    rc = rd(y, &py);
+    if (rc) return rc;
+    if (beta == 0.0 || z->zero_pending) {
+        VmulF<T> f{(T)alpha};
+        return launch_ew<VmulF<T>, true, false, T>(ctx, x->len, f, tp<T>(px), tp<T>(py), nullptr, tp<T>(wr(z)));
+    }
+    VmulAccF<T> f{(T)alpha, (T)beta};
+    return launch_ew<VmulAccF<T>, true, true, T>(ctx, x->len, f, tp<T>(px), tp<T>(py), tp<T>(z->ptr), tp<T>(z->ptr));
+}
+} // namespace b200
+
+extern "C" int b200_axpby(b200_ctx_t ctx, double a, b200_vec_t x, double b, b200_vec_t y) {
+    CHECK_CTX(ctx);
+    B200_REQUIRE(x && y, "null argument");
+    touch(ctx, {x, y});
+    B200_REQUIRE(same_layout(x, y), "axpby: size mismatch");
+    if (x->kind == B200_VK_GHOST) return B200_OK;
+    GUARD(ctx);
+    if (all64({x, y})) return axpby_t<double>(ctx, a, x, b, y);
+    if (all32({x, y})) return axpby_t<float>(ctx, a, x, b, y);
+    return B200_BAD_MIX("axpby");
+}
+
+extern "C" int b200_axpbypcz(b200_ctx_t ctx, double a, b200_vec_t x, double b, b200_vec_t y,
+                             double c, b200_vec_t z) {
+    CHECK_CTX(ctx);
+    B200_REQUIRE(x && y && z, "null argument");
+    touch(ctx, {x, y, z});
+    B200_REQUIRE(same_layout(x, y) && same_layout(x, z), "axpbypcz: size mismatch");
+    if (x->kind == B200_VK_GHOST) return B200_OK;
+    GUARD(ctx);
+    if (all64({x, y, z})) return axpbypcz_t<double>(ctx, a, x, b, y, c, z);
+    if (all32({x, y, z})) return axpbypcz_t<float>(ctx, a, x, b, y, c, z);
+    return B200_BAD_MIX("axpbypcz");
+}
+
+extern "C" int b200_vmul(b200_ctx_t ctx, double alpha, b200_vec_t x, b200_vec_t y, double beta,
+                         b200_vec_t z) {
+    CHECK_CTX(ctx);
+    B200_REQUIRE(x && y && z, "null argument");
+    touch(ctx, {x, y, z});
+    B200_REQUIRE(same_layout(x, y) && same_layout(x, z), "vmul: size mismatch");
+    if (x->kind == B200_VK_GHOST) return B200_OK;
+    GUARD(ctx);
+    if (all64({x, y, z})) return vmul_t<double>(ctx, alpha, x, y, beta, z);
+    if (all32({x, y, z})) return vmul_t<float>(ctx, alpha, x, y, beta, z);
+    if (all32({x, y}) && z->dtype == B200_F64) {
+        // FP32 smoother diagonal and residual accumulated into an FP64 iterate
+        const double *px, *py;
+        int rc = rd(x, &px);
+        if (rc) return rc;
+        rc = rd(y, &py);
+        if (rc) return rc;
+        if (beta == 0.0 || z->zero_pending) {
+            VmulF<double> f{alpha};
+            return launch_ew_mixed<VmulF<double>, true, false>(ctx, x->len, f, tp<float>(px), tp<float>(py),
+                                                               (const double *)nullptr, wr(z));
+        }
+        VmulAccF<double> f{alpha, beta};
+        return launch_ew_mixed<VmulAccF<double>, true, true>(ctx, x->len, f, tp<float>(px), tp<float>(py),
+                                                            (const double *)z->ptr, z->ptr);
+    }
+    return B200_BAD_MIX("vmul");
+}
+

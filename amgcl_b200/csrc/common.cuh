@@ -49,6 +49,11 @@ constexpr int kRowsCapMax   = 1024;   // most rows a row block may hold
 constexpr int kNnzCapMax    = 6144;   // most non-zeros a staged row block may hold
 constexpr int kDotMaxBlocks = 2048;   // upper bound on partial sums of one dot product
 
+// multi-GPU peer-memory exchange buffers (peer.cuh): [flags 256 B | parity 0 | parity 1]
+constexpr int kMaxRanks   = 16;
+constexpr int kFlagStride = 16;                 // flag slots per parity (>= kMaxRanks)
+constexpr size_t kFlagBytes = 2 * kFlagStride * sizeof(unsigned long long);   // 256 B header
+
 } // namespace b200
 
 // ---------------------------------------------------------------------------

@@ -236,12 +236,4 @@ static void dependency_matrix(const Partition &rows, const Partition &cols, cons
     }
 }
 
-// ---- device helper: pack this rank's boundary values into its halo segment ----------
-__global__ void __launch_bounds__(kThreads)
-halo_pack_kernel(int64_t count, const int *__restrict__ send_idx, const double *__restrict__ x,
-                 double *__restrict__ segment) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < count) segment[i] = x[send_idx[i]];
-}
-
 } // namespace b200

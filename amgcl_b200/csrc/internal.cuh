@@ -1,0 +1,219 @@
+// internal.cuh -- host-side plumbing shared by the api_*.cu translation units: error
+// reporting, the device guard, per-launch profiling brackets, lazy-clear bookkeeping, graph
+// recording state, the launch helper and the functions one unit calls in another.
+#pragma once
+#include "common.cuh"
+#include "dist.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <initializer_list>
+#include <limits>
+#include <new>
+#include <string>
+#include <vector>
+
+namespace b200 {
+
+// device guard: every entry point runs with the context's device current
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; }
+        if (prev != dev) ok = (cudaSetDevice(dev) == cudaSuccess);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+constexpr size_t kProfMaxPairs = 1 << 17;
+
+// Bracket one launch with a pair of events on the launching stream (profiling only).
+struct ProfScope {
+    b200_ctx_t ctx;
+    bool on = false;
+    size_t ev = 0;
+    int64_t nrows, ncols, nnz;
+    int mode;
+    ProfScope(b200_ctx_t c, int mode_, int64_t nr, int64_t nc, int64_t nz)
+        : ctx(c), nrows(nr), ncols(nc), nnz(nz), mode(mode_) {
+        if (!ctx->profiling || ctx->prof_recs.size() >= kProfMaxPairs) return;
+        while (ctx->prof_events.size() < ctx->prof_used + 2) {
+            cudaEvent_t e;
+            if (cudaEventCreate(&e) != cudaSuccess) return;
+            ctx->prof_events.push_back(e);
+        }
+        ev = ctx->prof_used;
+        if (cudaEventRecord(ctx->prof_events[ev], ctx->stream) != cudaSuccess) return;
+        on = true;
+    }
+    ~ProfScope() {
+        if (!on) return;
+        if (cudaEventRecord(ctx->prof_events[ev + 1], ctx->stream) != cudaSuccess) return;
+        ctx->prof_used += 2;
+        ctx->prof_recs.push_back({nrows, ncols, nnz, mode, ev});
+    }
+};
+
+// Lazy clear bookkeeping ------------------------------------------------------
+inline int materialize(b200_vec_t v) {
+    if (v->zero_pending) {
+        if (v->len) {
+            ProfScope prof(v->ctx, B200_PROF_MEMSET, (int64_t)v->len, 1, 0);
+            B200_CUDA(cudaMemsetAsync(v->ptr, 0, v->len * v->esz, v->ctx->stream));
+        }
+        v->zero_pending = false;
+    }
+    return B200_OK;
+}
+// pointer for reading (or read-modify-write)
+inline int rd(b200_vec_t v, const double **p) {
+    int rc = materialize(v);
+    *p = v->ptr;
+    return rc;
+}
+// pointer for a full overwrite
+inline double *wr(b200_vec_t v) {
+    v->zero_pending = false;
+    return v->ptr;
+}
+// typed views (FP32 vectors keep their floats behind the same pointer)
+template <class T> inline T *tp(double *p) { return reinterpret_cast<T *>(p); }
+template <class T> inline const T *tp(const double *p) { return reinterpret_cast<const T *>(p); }
+inline bool all64(std::initializer_list<b200_vec_t> vs) {
+    for (b200_vec_t v : vs) if (v->dtype != B200_F64) return false;
+    return true;
+}
+inline bool all32(std::initializer_list<b200_vec_t> vs) {
+    for (b200_vec_t v : vs) if (v->dtype != B200_F32) return false;
+    return true;
+}
+
+// CUDA-graph recording -----------------------------------------------------------
+// The library keeps two pieces of host-side state per vector that decide WHICH kernels run and
+// on WHICH addresses: the storage pointer (b200_relax trades x's storage with tmp's) and the
+// lazy-clear flag.  A recorded graph bakes both in, so it remembers the state every object it
+// touched had on entry (the graph may only be replayed from exactly that state) and the state
+// the recorded calls left behind (applied after each replay).
+struct GraphSlot {
+    double **slot;      // &vec->ptr or &csr->scratch64
+    bool    *zp;        // &vec->zero_pending (nullptr for operator scratch)
+    double  *p0; bool z0;   // on entry
+    double  *p1; bool z1;   // on exit
+};
+} // namespace b200
+
+struct b200_graph_s {
+    b200_ctx_t ctx = nullptr;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    std::vector<b200::GraphSlot> slots;
+    uint64_t destroy_epoch = 0, option_epoch = 0;
+    uint64_t launches0 = 0;     // ctx->launches when recording started
+    uint64_t launches = 0;      // kernels in the graph
+    size_t   nodes = 0;
+    uint64_t replays = 0;
+};
+
+namespace b200 {
+
+inline void touch_slot(b200_ctx_t ctx, double **slot, bool *zp) {
+    b200_graph_s *g = ctx->recording;
+    for (const GraphSlot &s : g->slots)
+        if (s.slot == slot) return;
+    g->slots.push_back({slot, zp, *slot, zp ? *zp : false, nullptr, false});
+}
+inline void touch(b200_ctx_t ctx, std::initializer_list<b200_vec_t> vs) {
+    if (!ctx->recording) return;
+    for (b200_vec_t v : vs) {
+        touch_slot(ctx, &v->ptr, &v->zero_pending);
+        v->in_graph = true;
+    }
+}
+
+inline int grid_for(const b200_ctx_t ctx, size_t n_items, int per_thread_items) {
+    // enough CTAs to cover the range once, capped at 8 CTAs per SM (2048 threads)
+    size_t want = (n_items + (size_t)kThreads * per_thread_items - 1) /
+                  ((size_t)kThreads * per_thread_items);
+    size_t cap = (size_t)ctx->sm_count * 8;
+    if (want < 1) want = 1;
+    return (int)std::min(want, cap);
+}
+
+} // namespace b200
+
+namespace b200 {
+
+// ---- peer-memory exchange buffers (layout: [flags 256 B | parity 0 | parity 1]) ------------
+inline unsigned long long *flag_at(void *base, int parity, int slot) {
+    return reinterpret_cast<unsigned long long *>(base) + parity * kFlagStride + slot;
+}
+inline double *data_at(void *base, int parity, size_t half_bytes) {
+    return reinterpret_cast<double *>(static_cast<char *>(base) + kFlagBytes + (size_t)parity * half_bytes);
+}
+
+// Launch with programmatic stream serialization (PDL) when enabled: the kernel may be
+// scheduled while its predecessor drains and orders itself with griddepcontrol.wait.
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(b200_ctx_t ctx, void (*kernel)(KArgs...), dim3 grid, dim3 block,
+                              size_t smem, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed =
+        (ctx->opt_pdl && (!ctx->recording || ctx->opt_graph_pdl)) ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
+// ---- implemented in api_exchange.cu (multi-GPU) ----------------------------------------------
+int  peer_alloc(b200_ctx_t ctx, size_t bytes, void **local, void **peers);
+void peer_release(b200_ctx_t ctx, void *local, void **peers);
+// what halo_exchange hands to the consumer kernel (copied into its CsrArgs)
+struct HaloArgs {
+    const double             *xh = nullptr;         // halo values for columns >= nloc
+    int                       nloc = 0;
+    const unsigned char      *blk_halo = nullptr;   // peer transport: blocks that must wait
+    const unsigned long long *wait_flags = nullptr;
+    unsigned int              wait_mask = 0;
+    unsigned long long        wait_seq = 0;
+};
+int  halo_exchange(b200_ctx_t ctx, b200_csr_t A, const double *x, HaloArgs &a);
+int  coarse_to_all(b200_ctx_t ctx, b200_csr_t A, b200_vec_t xc, const double **px);
+int  partials_to_coarse(b200_ctx_t ctx, b200_csr_t A, b200_vec_t yc);
+int  dist_dot_finish(b200_ctx_t ctx, double *result);
+
+} // namespace b200
+
+#define CHECK_CTX(ctx) B200_REQUIRE((ctx) != nullptr, "null context")
+#define B200_NCCL(call)                                                        \
+    do {                                                                       \
+        ncclResult_t rc__ = (call);                                            \
+        if (rc__ != ncclSuccess)                                               \
+            return fail(B200_ENCCL, std::string("NCCL error in " #call ": ") + \
+                                        nccl().GetErrorString(rc__));          \
+    } while (0)
+inline ncclComm_t comm_of(b200_ctx_t ctx) { return static_cast<ncclComm_t>(ctx->comm); }
+inline bool same_layout(b200_vec_t a, b200_vec_t b) {
+    return a->n == b->n && a->kind == b->kind && a->len == b->len;
+}
+#define B200_REQUIRE_F64_DIST(ctx, what)                                                    \
+    B200_REQUIRE(!(ctx)->dist, what ": FP32 objects are not supported on a distributed context")
+#define NOT_RECORDING(ctx, what)                                                        \
+    B200_REQUIRE(!(ctx)->recording, what ": not allowed while a graph is being recorded")
+#define GUARD(ctx)                                                             \
+    DeviceGuard guard__((ctx)->device);                                        \
+    if (!guard__.ok) return fail(B200_ECUDA, "cudaSetDevice failed")
+#define B200_BAD_MIX(what) ::b200::fail(B200_EINVAL, what ": unsupported precision combination")

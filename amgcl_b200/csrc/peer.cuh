@@ -26,9 +26,7 @@
 
 namespace b200 {
 
-constexpr int kMaxRanks   = 16;
-constexpr int kFlagStride = 16;                 // flag slots per parity (>= kMaxRanks)
-constexpr size_t kFlagBytes = 2 * kFlagStride * sizeof(unsigned long long);   // 256 B header
+// (kMaxRanks, kFlagStride, kFlagBytes: common.cuh)
 
 struct PeerTargets {
     double             *data[kMaxRanks];   // where my contribution goes in peer q (nullptr: skip)
@@ -129,6 +127,15 @@ reduce_sum_kernel(int64_t count, const double *staged, int64_t stride, int nrank
         dst[i] = s;
         if (host_out && i == 0) *host_out = s;
     }
+}
+
+
+// ---- device helper: pack this rank's boundary values into its halo segment ----------
+__global__ void __launch_bounds__(kThreads)
+halo_pack_kernel(int64_t count, const int *__restrict__ send_idx, const double *__restrict__ x,
+                 double *__restrict__ segment) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) segment[i] = x[send_idx[i]];
 }
 
 } // namespace b200
