@@ -116,6 +116,12 @@ def lib():
         "b200_split_destroy": [_vp],
         "b200_plan_i64": [_i64, _vp, _c.c_int, _c.c_int, _vp, _i64, _P(_i64), _P(_c.c_int),
                           _P(_c.c_int), _P(_i64)],
+        "b200_index_create_i64": [_vp, _vp, _c.c_size_t, _c.c_size_t, _P(_vp)],
+        "b200_index_destroy": [_vp],
+        "b200_index_size": [_vp, _P(_c.c_size_t)],
+        "b200_gather": [_vp, _vp, _vp, _vp],
+        "b200_gather_host": [_vp, _vp, _vp, _vp],
+        "b200_scatter": [_vp, _vp, _vp, _vp],
         "b200_graph_begin": [_vp, _P(_c.c_int)],
         "b200_graph_end": [_vp, _P(_vp)],
         "b200_graph_abort": [_vp],
@@ -154,6 +160,8 @@ def dropin_lib():
     D.dropin_create_graph.restype = _c.c_int
     D.dropin_graph_stats.argtypes = [_vp, _P(_i64), _P(_i64), _P(_i64)]
     D.dropin_graph_stats.restype = _c.c_int
+    D.dropin_gather_scatter.argtypes = [_vp, _i64, _vp, _i64, _vp, _dbl, _vp, _vp, _vp]
+    D.dropin_gather_scatter.restype = _c.c_int
     D.dropin_destroy.argtypes = [_vp]
     D.dropin_destroy.restype = None
     D.dropin_solve.argtypes = [_vp, _vp, _vp, _P(_i64), _P(_dbl)]
@@ -309,6 +317,22 @@ class Context:
     def vmul(self, alpha, x, y, beta, z):
         _check(lib().b200_vmul(self.h, alpha, x.h, y.h, beta, z.h), "b200_vmul")
 
+    # -- index lists (Backend::gather / scatter) --
+    def index(self, idx, size):
+        """Device index list into a vector of `size` elements."""
+        return Index(self, idx, size)
+
+    def gather(self, I, src, dst):
+        _check(lib().b200_gather(self.h, I.h, src.h, dst.h), "b200_gather")
+
+    def gather_host(self, I, src):
+        out = np.empty(I.n, dtype=np.float64)
+        _check(lib().b200_gather_host(self.h, I.h, src.h, _ptr(out)), "b200_gather_host")
+        return out
+
+    def scatter(self, I, src, dst):
+        _check(lib().b200_scatter(self.h, I.h, src.h, dst.h), "b200_scatter")
+
     # -- recorded call sequences (b200_graph_*) --
     def graph_begin(self):
         """Start recording; False when this context cannot record right now."""
@@ -426,6 +450,26 @@ class Coarse:
         try:
             if self.h:
                 lib().b200_coarse_destroy(self.h)
+                self.h = _vp()
+        except Exception:
+            pass
+
+
+class Index:
+    """Device index list (b200_index_t)."""
+
+    def __init__(self, ctx, idx, size):
+        idx = np.ascontiguousarray(idx, dtype=np.int64)
+        self.ctx = ctx
+        self.n = idx.size
+        self.h = _vp()
+        _check(lib().b200_index_create_i64(ctx.h, _ptr(idx), idx.size, int(size), _c.byref(self.h)),
+               "b200_index_create_i64")
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().b200_index_destroy(self.h)
                 self.h = _vp()
         except Exception:
             pass

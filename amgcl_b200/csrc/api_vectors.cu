@@ -434,3 +434,133 @@ extern "C" int b200_vmul(b200_ctx_t ctx, double alpha, b200_vec_t x, b200_vec_t 
     return B200_BAD_MIX("vmul");
 }
 
+
+// ---------------------------------------------------------------------------
+// index lists: gather / scatter
+// ---------------------------------------------------------------------------
+extern "C" int b200_index_create_i64(b200_ctx_t ctx, const int64_t *idx, size_t n, size_t range,
+                                     b200_index_t *out) {
+    CHECK_CTX(ctx);
+    NOT_RECORDING(ctx, "index list creation");
+    B200_REQUIRE(out != nullptr, "null output pointer");
+    *out = nullptr;
+    B200_REQUIRE(idx != nullptr || n == 0, "null index array");
+    B200_REQUIRE(!ctx->dist, "index lists are not supported on a distributed context");
+    B200_REQUIRE(range < ((size_t)1 << 31), "index range must be below 2^31");
+    std::vector<int> narrow(n);
+    for (size_t k = 0; k < n; ++k) {
+        if (idx[k] < 0 || (size_t)idx[k] >= range) return fail(B200_ERANGE, "index out of range");
+        narrow[k] = (int)idx[k];
+    }
+    GUARD(ctx);
+    b200_index_s *I = new (std::nothrow) b200_index_s();
+    if (!I) return fail(B200_ENOMEM, "out of host memory");
+    I->ctx = ctx; I->n = n; I->range = range;
+    cudaError_t rc = cudaMalloc(&I->idx, (n + 4) * sizeof(int));
+    if (rc == cudaSuccess) rc = cudaMalloc(&I->stage_d, (n + 4) * sizeof(double));
+    if (rc == cudaSuccess && n)
+        rc = cudaMemcpyAsync(I->idx, narrow.data(), n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
+    if (rc == cudaSuccess) rc = cudaStreamSynchronize(ctx->stream);     // `narrow` dies here
+    if (rc != cudaSuccess) {
+        if (I->idx) cudaFree(I->idx);
+        if (I->stage_d) cudaFree(I->stage_d);
+        delete I;
+        return cuda_fail(rc, "index list upload", __FILE__, __LINE__);
+    }
+    *out = I;
+    return B200_OK;
+}
+
+extern "C" int b200_index_destroy(b200_index_t I) {
+    if (!I) return B200_OK;
+    NOT_RECORDING(I->ctx, "index list destruction");
+    if (I->in_graph) I->ctx->destroy_epoch++;
+    GUARD(I->ctx);
+    if (I->idx) cudaFree(I->idx);
+    if (I->stage_d) cudaFree(I->stage_d);
+    delete I;
+    return B200_OK;
+}
+
+extern "C" int b200_index_size(b200_index_t I, size_t *n) {
+    B200_REQUIRE(I && n, "null argument");
+    *n = I->n;
+    return B200_OK;
+}
+
+namespace b200 {
+template <class T>
+static int gather_launch(b200_ctx_t ctx, b200_index_t I, const double *src, double *dst) {
+    if (!I->n) return B200_OK;
+    const int grid = grid_for(ctx, I->n, 2);
+    ProfScope prof(ctx, B200_PROF_VECTOR + 1, (int64_t)I->n, 1, 0);
+    B200_CUDA(launch_pdl(ctx, gather_kernel<T>, dim3(grid), dim3(kThreads), 0, I->n, (const int *)I->idx,
+                         (const T *)tp<T>(src), tp<T>(dst)));
+    B200_CHECK_LAUNCH();
+    ctx->launches++;
+    return B200_OK;
+}
+} // namespace b200
+
+extern "C" int b200_gather(b200_ctx_t ctx, b200_index_t I, b200_vec_t src, b200_vec_t dst) {
+    CHECK_CTX(ctx);
+    B200_REQUIRE(I && src && dst, "null argument");
+    touch(ctx, {src, dst});
+    if (ctx->recording) I->in_graph = true;
+    B200_REQUIRE(src->n == I->range && dst->n == I->n, "gather: vector sizes do not match the index list");
+    B200_REQUIRE(src != dst && src->ptr != dst->ptr, "gather: src and dst must not alias");
+    if (src->dtype != dst->dtype) return B200_BAD_MIX("gather");
+    GUARD(ctx);
+    const double *ps;
+    int rc = rd(src, &ps);
+    if (rc) return rc;
+    return src->dtype == B200_F64 ? gather_launch<double>(ctx, I, ps, wr(dst))
+                                  : gather_launch<float>(ctx, I, ps, wr(dst));
+}
+
+// gather into a host array (the reference's second overload, cuda.hpp:560-563): host-synchronous
+extern "C" int b200_gather_host(b200_ctx_t ctx, b200_index_t I, b200_vec_t src, void *host) {
+    CHECK_CTX(ctx);
+    B200_REQUIRE(I && src && (host || I->n == 0), "null argument");
+    NOT_RECORDING(ctx, "gather to the host");
+    B200_REQUIRE(src->n == I->range, "gather: vector size does not match the index list");
+    GUARD(ctx);
+    if (!I->n) return B200_OK;
+    const double *ps;
+    int rc = rd(src, &ps);
+    if (rc) return rc;
+    rc = src->dtype == B200_F64 ? gather_launch<double>(ctx, I, ps, static_cast<double *>(I->stage_d))
+                                : gather_launch<float>(ctx, I, ps, static_cast<double *>(I->stage_d));
+    if (rc) return rc;
+    B200_CUDA(cudaMemcpyAsync(host, I->stage_d, I->n * src->esz, cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA(cudaStreamSynchronize(ctx->stream));
+    return B200_OK;
+}
+
+extern "C" int b200_scatter(b200_ctx_t ctx, b200_index_t I, b200_vec_t src, b200_vec_t dst) {
+    CHECK_CTX(ctx);
+    B200_REQUIRE(I && src && dst, "null argument");
+    touch(ctx, {src, dst});
+    if (ctx->recording) I->in_graph = true;
+    B200_REQUIRE(dst->n == I->range && src->n == I->n, "scatter: vector sizes do not match the index list");
+    B200_REQUIRE(src != dst && src->ptr != dst->ptr, "scatter: src and dst must not alias");
+    if (src->dtype != dst->dtype) return B200_BAD_MIX("scatter");
+    GUARD(ctx);
+    if (!I->n) return B200_OK;
+    const double *ps, *pd;
+    int rc = rd(src, &ps);
+    if (rc) return rc;
+    rc = rd(dst, &pd);                  // partial overwrite: a pending clear must land first
+    if (rc) return rc;
+    const int grid = grid_for(ctx, I->n, 2);
+    ProfScope prof(ctx, B200_PROF_VECTOR + 1, (int64_t)I->n, 1, 0);
+    if (src->dtype == B200_F64)
+        B200_CUDA(launch_pdl(ctx, scatter_kernel<double>, dim3(grid), dim3(kThreads), 0, I->n,
+                             (const int *)I->idx, ps, dst->ptr));
+    else
+        B200_CUDA(launch_pdl(ctx, scatter_kernel<float>, dim3(grid), dim3(kThreads), 0, I->n,
+                             (const int *)I->idx, (const float *)tp<float>(ps), tp<float>(dst->ptr)));
+    B200_CHECK_LAUNCH();
+    ctx->launches++;
+    return B200_OK;
+}

@@ -181,6 +181,15 @@ struct b200_csr_s {
     size_t     bytes    = 0;
 };
 
+struct b200_index_s {
+    b200_ctx_t ctx  = nullptr;
+    size_t     n    = 0;          // number of indices
+    size_t     range = 0;         // every index is < range (size of the indexed vector)
+    int       *idx  = nullptr;    // [n] device
+    void      *stage_d = nullptr; // [n] device staging for gathers that end on the host
+    bool       in_graph = false;
+};
+
 struct b200_coarse_s {
     b200_ctx_t ctx  = nullptr;
     int        dtype = B200_F64;  // element type of the vectors it is applied to

@@ -193,4 +193,25 @@ dot_kernel(size_t n, const T *__restrict__ x, const T *__restrict__ y,
     }
 }
 
+// ---- index lists (Backend::gather / Backend::scatter, cuda.hpp:548-577) --------------------
+// dst[k] = src[idx[k]]: the index stream and the output are coalesced, the gathered side goes
+// through the read-only path
+template <class T>
+__global__ void __launch_bounds__(kThreads)
+gather_kernel(size_t n, const int *__restrict__ idx, const T *__restrict__ src, T *__restrict__ dst) {
+    ptx::pdl_wait();
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride)
+        dst[k] = __ldg(src + idx[k]);
+}
+// dst[idx[k]] = src[k] (indices are expected to be distinct, as thrust::scatter requires)
+template <class T>
+__global__ void __launch_bounds__(kThreads)
+scatter_kernel(size_t n, const int *__restrict__ idx, const T *__restrict__ src, T *__restrict__ dst) {
+    ptx::pdl_wait();
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride)
+        dst[idx[k]] = src[k];
+}
+
 } // namespace b200

@@ -359,4 +359,33 @@ int64_t dropin_report(void *handle, char *buf, int64_t size)
 
 int64_t dropin_bytes(void *handle) { return (int64_t)static_cast<Handle *>(handle)->solver->bytes(); }
 
+// Backend::gather / Backend::scatter exercised through the C++ binding (cuda.hpp:548-577):
+// g[k] = src[I[k]] on the device and straight to the host; then dst (size n, pre-filled with
+// `fill`) receives dst[I[k]] = g[k].
+int dropin_gather_scatter(void *ctx, int64_t n, const double *src_host, int64_t m, const int64_t *I,
+                          double fill, double *gathered_dev_path, double *gathered_host_path,
+                          double *scattered)
+{
+    try {
+        Backend::params bprm(static_cast<b200_ctx_t>(ctx));
+        std::vector<ptrdiff_t> idx(I, I + m);
+        Backend::gather G((size_t)n, idx, bprm);
+        Backend::scatter S((size_t)n, idx, bprm);
+        Backend::vector src(src_host, (size_t)n, bprm), g((size_t)m, bprm);
+        G(src, g);
+        g.download(gathered_dev_path);
+        std::vector<double> vals((size_t)m);
+        G(src, vals);
+        std::copy(vals.begin(), vals.end(), gathered_host_path);
+        std::vector<double> init((size_t)n, fill);
+        Backend::vector dst(init.data(), (size_t)n, bprm);
+        S(g, dst);
+        dst.download(scattered);
+        return 0;
+    } catch (const std::exception &e) {
+        g_error = e.what();
+        return -1;
+    }
+}
+
 } // extern "C"

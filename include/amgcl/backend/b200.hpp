@@ -337,6 +337,52 @@ struct b200 {
     {
         return std::make_shared<direct_solver>(*A, prm);
     }
+
+    /// dst[k] = src[I[k]] (cuda.hpp:548-564).
+    struct gather {
+        gather(size_t src_size, const std::vector<ptrdiff_t> &I, const params &prm)
+            : idx(0), n(I.size())
+        {
+            std::vector<int64_t> I64(I.begin(), I.end());
+            AMGCL_CALL_B200(b200_index_create_i64(prm.context(), I64.data(), n, src_size, &idx));
+            ctx = prm.context();
+        }
+        gather(const gather&) = delete;
+        gather& operator=(const gather&) = delete;
+        ~gather() { if (idx) b200_index_destroy(idx); }
+
+        void operator()(const vector &src, vector &dst) const {
+            AMGCL_CALL_B200(b200_gather(ctx, idx, src.handle(), dst.handle()));
+        }
+        void operator()(const vector &vec, std::vector<value_type> &vals) const {
+            AMGCL_CALL_B200(b200_gather_host(ctx, idx, vec.handle(), vals.data()));
+        }
+
+        b200_ctx_t ctx;
+        b200_index_t idx;
+        size_t n;
+    };
+
+    /// dst[I[k]] = src[k] (cuda.hpp:566-577).
+    struct scatter {
+        scatter(size_t size, const std::vector<ptrdiff_t> &I, const params &prm)
+            : idx(0)
+        {
+            std::vector<int64_t> I64(I.begin(), I.end());
+            AMGCL_CALL_B200(b200_index_create_i64(prm.context(), I64.data(), I.size(), size, &idx));
+            ctx = prm.context();
+        }
+        scatter(const scatter&) = delete;
+        scatter& operator=(const scatter&) = delete;
+        ~scatter() { if (idx) b200_index_destroy(idx); }
+
+        void operator()(const vector &src, vector &dst) const {
+            AMGCL_CALL_B200(b200_scatter(ctx, idx, src.handle(), dst.handle()));
+        }
+
+        b200_ctx_t ctx;
+        b200_index_t idx;
+    };
 };
 
 /// An FP64 Krylov solver may drive an FP32 hierarchy (mixed precision, as

@@ -51,6 +51,7 @@ typedef struct b200_vec_s    *b200_vec_t;     /* device FP64 vector             
 typedef struct b200_coarse_s *b200_coarse_t;  /* coarsest-level direct solver         */
 typedef struct b200_split_s  *b200_split_t;   /* host view of one rank's operator share */
 typedef struct b200_graph_s  *b200_graph_t;   /* recorded call sequence (CUDA graph)    */
+typedef struct b200_index_s  *b200_index_t;   /* device index list (gather / scatter)   */
 
 /* ---------------------------------------------------------------- context */
 
@@ -260,6 +261,21 @@ int b200_axpbypcz(b200_ctx_t ctx, double a, b200_vec_t x, double b, b200_vec_t y
 /* z = alpha*x.*y + beta*z; z not read when beta == 0 (interface.hpp:399-405, builtin.hpp:1238-1265). */
 int b200_vmul(b200_ctx_t ctx, double alpha, b200_vec_t x, b200_vec_t y,
               double beta, b200_vec_t z);
+
+/* Index lists (Backend::gather / Backend::scatter, cuda.hpp:548-577; used by components that
+ * move sub-vectors, e.g. the boundary exchange of mpi/distributed_matrix.hpp:300).  `range` is
+ * the size of the vector the indices point into; indices are narrowed to int32 and checked
+ * (B200_ERANGE).  Single-GPU contexts only. */
+int b200_index_create_i64(b200_ctx_t ctx, const int64_t *idx, size_t n, size_t range, b200_index_t *I);
+int b200_index_destroy(b200_index_t I);
+int b200_index_size(b200_index_t I, size_t *n);
+/* dst[k] = src[I[k]], k < n (thrust::gather, cuda.hpp:556-558) */
+int b200_gather(b200_ctx_t ctx, b200_index_t I, b200_vec_t src, b200_vec_t dst);
+/* host[k] = src[I[k]]: n elements of src's type; synchronous (cuda.hpp:560-563) */
+int b200_gather_host(b200_ctx_t ctx, b200_index_t I, b200_vec_t src, void *host);
+/* dst[I[k]] = src[k]; the other entries of dst are kept; indices must be distinct
+ * (thrust::scatter, cuda.hpp:573-575) */
+int b200_scatter(b200_ctx_t ctx, b200_index_t I, b200_vec_t src, b200_vec_t dst);
 
 /* ---------------------------------------------------------------- smoothers */
 

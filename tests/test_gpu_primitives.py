@@ -516,3 +516,59 @@ def test_graph_recording_rejects_host_synchronous_calls_and_aborts_cleanly(ctx, 
         assert not ctx.graph_begin()
     finally:
         ctx.profile_end()
+
+
+# ---------------------------------------------------------------------------
+# index lists: Backend::gather / Backend::scatter (cuda.hpp:548-577)
+# ---------------------------------------------------------------------------
+def test_gather_scatter(ctx):
+    rng = np.random.default_rng(21)
+    n, m = 10007, 3001
+    src = rng.uniform(-1, 1, n)
+    idx = rng.permutation(n)[:m]                      # distinct, unordered
+    I = ctx.index(idx, n)
+    vs, vg = ctx.vector(src), ctx.vector(m)
+    ctx.gather(I, vs, vg)
+    assert np.array_equal(vg.numpy(), src[idx])
+    assert np.array_equal(ctx.gather_host(I, vs), src[idx])
+    base = rng.uniform(-1, 1, n)
+    vd = ctx.vector(base)
+    ctx.scatter(I, vg, vd)
+    want = base.copy()
+    want[idx] = src[idx]
+    assert np.array_equal(vd.numpy(), want)
+    # a lazily cleared destination is materialised before the partial overwrite
+    ctx.clear(vd)
+    ctx.scatter(I, vg, vd)
+    want = np.zeros(n)
+    want[idx] = src[idx]
+    assert np.array_equal(vd.numpy(), want)
+    # ... and a cleared source gathers zeros
+    ctx.clear(vs)
+    ctx.gather(I, vs, vg)
+    assert not vg.numpy().any()
+    # empty list, bad index, size mismatch
+    E = ctx.index(np.zeros(0, dtype=np.int64), n)
+    ctx.gather(E, vs, ctx.vector(0))
+    with pytest.raises(ab.B200Error, match="out of range"):
+        ctx.index([0, n], n)
+    with pytest.raises(ab.B200Error, match="sizes"):
+        ctx.gather(I, vg, vs)
+
+
+def test_gather_scatter_through_the_cpp_backend(ctx):
+    """Backend::gather / Backend::scatter of include/amgcl/backend/b200.hpp."""
+    import ctypes
+    D = ab.dropin_lib()
+    rng = np.random.default_rng(22)
+    n, m = 5000, 777
+    src = rng.uniform(-1, 1, n)
+    idx = np.ascontiguousarray(rng.permutation(n)[:m], dtype=np.int64)
+    g1, g2, sc = np.empty(m), np.empty(m), np.empty(n)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    rc = D.dropin_gather_scatter(ctx.h, n, p(src), m, p(idx), -7.0, p(g1), p(g2), p(sc))
+    assert rc == 0, D.dropin_last_error()
+    assert np.array_equal(g1, src[idx]) and np.array_equal(g2, src[idx])
+    want = np.full(n, -7.0)
+    want[idx] = src[idx]
+    assert np.array_equal(sc, want)
