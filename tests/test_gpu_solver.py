@@ -123,6 +123,12 @@ def test_tutorial_program_runs(known_answers, krylov, graph, iters):
     assert "Number of levels" in out.stdout          # the reference's own hierarchy report
 
 
+def test_driver_smoke_entry_point():
+    """__graft_entry__.smoke(): the call the driver makes on the GPU box before the bench."""
+    import __graft_entry__
+    __graft_entry__.smoke()
+
+
 def test_zero_rhs(ctx):
     ptr, col, val, rhs = ab.poisson3d(12)
     S = ab.DropinSolver(ptr, col, val, ctx=ctx)
