@@ -1,0 +1,187 @@
+"""Property-based tests (hypothesis) of the host-side logic behind the C ABI: the row-block
+plan every CSR kernel walks, the multi-GPU partition / operator splitting, and the file
+formats.  Pure CPU: nothing here needs a device."""
+import os
+
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st, HealthCheck
+
+import amgcl_b200 as ab
+from amgcl_b200 import io as bio
+from test_capi import plan, check_plan
+
+SETTINGS = dict(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+
+
+def csr_mv(ptr, col, val, x):
+    y = np.zeros(ptr.size - 1)
+    row = np.repeat(np.arange(ptr.size - 1), np.diff(ptr))
+    np.add.at(y, row, val * x[col])
+    return y
+
+
+@st.composite
+def row_lengths(draw):
+    n = draw(st.integers(0, 600))
+    kind = draw(st.sampled_from(["short", "mixed", "long_tail", "empty_rows"]))
+    seed = draw(st.integers(0, 2 ** 31 - 1))
+    rng = np.random.default_rng(seed)
+    if kind == "short":
+        lens = rng.integers(0, 9, n)
+    elif kind == "mixed":
+        lens = rng.integers(0, 200, n)
+    elif kind == "long_tail":
+        lens = rng.integers(0, 30, n)
+        for _ in range(min(n, 3)):
+            lens[rng.integers(0, n)] = rng.integers(500, 9000)
+    else:
+        lens = rng.integers(0, 40, n) * (rng.uniform(size=n) < 0.3)
+    return lens.astype(np.int64)
+
+
+@settings(**SETTINGS)
+@given(row_lengths(), st.sampled_from([0, 1, 2, 4, 8, 16, 32]), st.sampled_from([256, 512, 2048, 6144]))
+def test_row_block_plan_invariants(lens, lanes, cap):
+    """b200_plan_i64: the blocks tile the rows exactly once in order, every block starts on a
+    multiple of four rows (16-byte aligned ptr slice for the TMA copy), holds at most rows_cap
+    rows and at most nnz_cap non-zeros unless it is a single over-long quad, and the block's
+    first non-zero is ptr[first row]."""
+    ptr = np.zeros(lens.size + 1, dtype=np.int64)
+    np.cumsum(lens, out=ptr[1:])
+    blk, ln, rows_cap, nlong = plan(ptr, lanes, cap)
+    assert ln in (1, 2, 4, 8, 16, 32) and (lanes == 0 or ln == lanes)
+    assert rows_cap % 4 == 0 and 4 <= rows_cap <= 1024
+    if lens.size == 0:
+        assert blk.shape[0] == 1 and nlong == 0
+        return
+    assert nlong == check_plan(ptr, blk, rows_cap, cap)
+    # greedy packing: a block could not have taken the next quad as well
+    rows = blk[:, 0].astype(np.int64)
+    for b in range(rows.size - 2):
+        nxt_end = min(rows[b + 1] + 4, lens.size)
+        fits_rows = nxt_end - rows[b] <= rows_cap
+        fits_nnz = ptr[nxt_end] - ptr[rows[b]] <= cap
+        assert not (fits_rows and fits_nnz), "block %d stopped early" % b
+
+
+@settings(**SETTINGS)
+@given(st.integers(0, 5000), st.integers(1, 16))
+def test_partition_is_a_uniform_block_cover(n, P):
+    """b200_partition: one uniform block size (multiple of 4) for every rank, contiguous,
+    covering [0, n) exactly; trailing ranks may be short or empty."""
+    parts = [ab.partition(n, P, r) for r in range(P)]
+    B = parts[0][0]
+    assert B % 4 == 0 and B * P >= n and (n == 0 or B >= 4)
+    assert all(p[0] == B for p in parts)
+    assert parts[0][1] == 0 and parts[-1][2] == n
+    for r in range(P):
+        _, lo, hi = parts[r]
+        assert lo == min(r * B, n) and hi == min((r + 1) * B, n)
+
+
+@st.composite
+def sparse_matrix(draw, square=False):
+    nr = draw(st.integers(1, 60))
+    nc = nr if square else draw(st.integers(1, 60))
+    seed = draw(st.integers(0, 2 ** 31 - 1))
+    dens = draw(st.sampled_from([0.02, 0.1, 0.4]))
+    rng = np.random.default_rng(seed)
+    mask = rng.uniform(size=(nr, nc)) < dens
+    if square:
+        mask |= np.eye(nr, dtype=bool)
+    dense = np.where(mask, rng.uniform(-1, 1, (nr, nc)), 0.0)
+    ptr = np.zeros(nr + 1, dtype=np.int64)
+    np.cumsum(mask.sum(axis=1), out=ptr[1:])
+    col = np.nonzero(mask)[1].astype(np.int64)
+    val = dense[mask]
+    return nr, nc, ptr, col, val, dense
+
+
+@settings(**SETTINGS)
+@given(sparse_matrix(square=True), st.integers(1, 6), st.integers(0, 2 ** 31 - 1))
+def test_split_square_reproduces_the_global_product(m, P, seed):
+    """b200_dist_split_i64(kind=square): local columns first, remote columns renumbered into
+    the halo (rank-major slots); owner ranks publish x[send_idx]; the pieces together give A x."""
+    n, _, ptr, col, val, dense = m
+    x = np.random.default_rng(seed).uniform(-1, 1, n)
+    parts = [ab.dist_split("square", P, r, n, n, ptr, col, val) for r in range(P)]
+    bounds = [ab.partition(n, P, r) for r in range(P)]
+    S = parts[0]["slots"]
+    assert all(p["slots"] == S for p in parts)
+    halo = np.zeros(P * S)
+    for r, p in enumerate(parts):
+        lo, hi = bounds[r][1], bounds[r][2]
+        assert p["send_idx"].size <= S and (p["send_idx"].size == 0 or p["send_idx"].max() < hi - lo)
+        halo[r * S:r * S + p["send_idx"].size] = x[lo + p["send_idx"]]
+    got = np.zeros(n)
+    for r, p in enumerate(parts):
+        _, lo, hi = bounds[r]
+        assert p["nrows"] == hi - lo and p["n_loc"] == hi - lo
+        if hi > lo:
+            got[lo:hi] = csr_mv(p["ptr"], p["col"], p["val"], np.concatenate([x[lo:hi], halo]))
+    assert np.allclose(got, dense @ x, rtol=0, atol=1e-12)
+
+
+@settings(**SETTINGS)
+@given(sparse_matrix(), st.integers(1, 6), st.integers(0, 2 ** 31 - 1))
+def test_split_prolong_and_restrict(m, P, seed):
+    """prolong: rank r owns the fine rows of its block and reads the whole coarse vector;
+    restrict: rank r owns the fine COLUMNS of its block and produces partial sums over all
+    coarse rows that add up to R t."""
+    nr, nc, ptr, col, val, dense = m
+    rng = np.random.default_rng(seed)
+    # P_h (fine rows = nr) applied to a coarse vector of nc entries
+    u = rng.uniform(-1, 1, nc)
+    fine = [ab.partition(nr, P, r) for r in range(P)]
+    got = np.zeros(nr)
+    for r in range(P):
+        p = ab.dist_split("prolong", P, r, nr, nc, ptr, col, val)
+        _, lo, hi = fine[r]
+        assert p["nrows"] == hi - lo and p["ncols"] == nc
+        if hi > lo:
+            got[lo:hi] = csr_mv(p["ptr"], p["col"], p["val"], u)
+    assert np.allclose(got, dense @ u, rtol=0, atol=1e-12)
+    # R (coarse rows = nr) applied to a fine vector of nc entries partitioned by columns
+    t = rng.uniform(-1, 1, nc)
+    finec = [ab.partition(nc, P, r) for r in range(P)]
+    total = np.zeros(nr)
+    for r in range(P):
+        p = ab.dist_split("restrict", P, r, nr, nc, ptr, col, val)
+        _, lo, hi = finec[r]
+        assert p["nrows"] == nr and p["ncols"] == hi - lo
+        if p["col"].size:
+            assert p["col"].max() < hi - lo
+        total += csr_mv(p["ptr"], p["col"], p["val"], t[lo:hi]) if hi > lo else 0.0
+    assert np.allclose(total, dense @ t, rtol=0, atol=1e-12)
+
+
+@settings(max_examples=30, deadline=None, suppress_health_check=[HealthCheck.too_slow,
+                                                                   HealthCheck.function_scoped_fixture])
+@given(sparse_matrix(), st.integers(0, 2 ** 31 - 1))
+def test_file_formats_round_trip(tmp_path_factory, m, seed):
+    nr, nc, ptr, col, val, dense = m
+    d = tmp_path_factory.mktemp("io")
+    # MatrixMarket keeps 20 significant digits: exact for doubles
+    pm = str(d / "a.mtx")
+    bio.write_mm(pm, nc, ptr, col, val)
+    n2, m2, p2, c2, v2 = bio.read_mm(pm)
+    assert (n2, m2) == (nr, nc)
+    assert np.array_equal(p2, ptr) and np.array_equal(c2, col) and np.array_equal(v2, val)
+    # a random strip of rows
+    rng = np.random.default_rng(seed)
+    lo = int(rng.integers(0, nr + 1))
+    hi = int(rng.integers(lo, nr + 1))
+    n3, m3, p3, c3, v3 = bio.read_mm(pm, rows=(lo, hi))
+    assert n3 == hi - lo and np.array_equal(p3, ptr[lo:hi + 1] - ptr[lo])
+    assert np.array_equal(c3, col[ptr[lo]:ptr[hi]]) and np.array_equal(v3, val[ptr[lo]:ptr[hi]])
+    pb = str(d / "a.bin")
+    bio.write_crs_binary(pb, ptr, col, val)
+    n4, p4, c4, v4 = bio.read_crs_binary(pb, rows=(lo, hi))
+    assert n4 == hi - lo and np.array_equal(p4, p3) and np.array_equal(c4, c3) and np.array_equal(v4, v3)
+    pd = str(d / "d.bin")
+    bio.write_dense_binary(pd, dense)
+    assert np.array_equal(bio.read_dense_binary(pd, rows=(lo, hi)), dense[lo:hi])
+    pdm = str(d / "d.mtx")
+    bio.write_mm(pdm, dense)
+    assert np.array_equal(bio.read_mm(pdm), dense)
