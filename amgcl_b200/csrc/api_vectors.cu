@@ -97,17 +97,20 @@ extern "C" int b200_vec_wrap(b200_ctx_t ctx, double *device_ptr, size_t n, b200_
 
 extern "C" int b200_vec_destroy(b200_vec_t v) {
     if (!v) return B200_OK;
-    if (v->in_graph) v->ctx->destroy_epoch++;      // recorded graphs that refer to it are dead
     if (b200_graph_s *g = v->ctx->recording) {
-        // (e.g. a garbage-collected handle of the host language)  The recording may already
-        // use the storage: it is released after the recorded calls have run.
-        for (size_t i = 0; i < g->slots.size();)
-            if (g->slots[i].slot == &v->ptr) g->slots.erase(g->slots.begin() + i);
-            else ++i;
+        // Typically a garbage-collected handle of the host language that has nothing to do with
+        // the recording: its storage is released once the recording is over (cudaFree would
+        // synchronise the device in the middle of a capture).  A vector the recording itself
+        // uses cannot go away underneath it.
+        for (const GraphSlot &s : g->slots)
+            if (s.slot == &v->ptr)
+                return fail(B200_EINVAL, "vector is used by the graph being recorded");
+        if (v->in_graph) v->ctx->destroy_epoch++;
         if (v->owned && v->ptr) v->ctx->graph_deferred.push_back(v->ptr);
         delete v;
         return B200_OK;
     }
+    if (v->in_graph) v->ctx->destroy_epoch++;      // recorded graphs that refer to it are dead
     GUARD(v->ctx);
     if (v->owned && v->ptr) {
         // cudaFree synchronises the device, so no kernel can still be using it

@@ -329,7 +329,9 @@ int b200_coarse_solve(b200_ctx_t ctx, b200_coarse_t S, b200_vec_t rhs, b200_vec_
  * applies the same sequence to several vector pairs keeps one graph per pair.
  *
  * While recording, host-synchronous and allocating calls (b200_dot, uploads / downloads,
- * b200_ctx_sync, object creation / destruction) fail with B200_EINVAL; after any failure call
+ * b200_ctx_sync, object creation / destruction) fail with B200_EINVAL -- except b200_vec_destroy
+ * of a vector the recording does not use (a garbage-collected handle, say), whose storage is
+ * released when the recording ends; after any failure call
  * b200_graph_abort, which drops the recording and restores the vector state of
  * b200_graph_begin (nothing recorded has run).  *recording = 0 from b200_graph_begin means the
  * context cannot record right now (profiling, multi-GPU context, legacy default stream, option
