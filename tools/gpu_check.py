@@ -266,12 +266,29 @@ def cmd_unstructured():
     torch.cuda.set_stream(side)
     ctx = ab.Context(0, stream=side.cuda_stream)
     rng = np.random.default_rng(3)
-    for mult, order in ((1, "morton"), (4, "morton"), (16, "morton"), (64, "morton"), (16, "random")):
-        n = 85623 * mult
+    cases = [(1, "morton"), (4, "morton"), (16, "morton"), (64, "morton"), (16, "random")]
+    # a real MatrixMarket / AMGCL-binary file (e.g. tutorial/1.poisson3Db's poisson3Db.mtx and
+    # poisson3Db_b.mtx) when one is supplied: B200_MATRIX=path [B200_RHS=path]
+    if os.environ.get("B200_MATRIX"):
+        cases = [(None, os.environ["B200_MATRIX"])] + cases
+    for mult, order in cases:
         t0 = time.time()
-        ptr, col, val, rhs = ab.unstructured3d(n, order=order)
+        if mult is None:
+            from amgcl_b200 import io as bio
+            if order.endswith(".bin"):
+                n, ptr, col, val = bio.read_crs_binary(order)
+            else:
+                n, _, ptr, col, val = bio.read_mm(order)
+            rp = os.environ.get("B200_RHS")
+            rhs = (bio.read_dense_binary(rp) if rp and rp.endswith(".bin") else bio.read_mm(rp))[:, 0] \
+                if rp else np.ones(n)
+            name = "file %s" % os.path.basename(order)
+        else:
+            n = 85623 * mult
+            ptr, col, val, rhs = ab.unstructured3d(n, order=order)
+            name = "unstructured3d(n=%d, k=24, order=%s) [synthetic stand-in for poisson3Db]" % (n, order)
         nnz = int(ptr[-1])
-        rec = {"matrix": "unstructured3d(n=%d, k=24, order=%s) [synthetic stand-in for poisson3Db]" % (n, order),
+        rec = {"matrix": name,
                "rows": n, "nnz": nnz, "nnz_per_row": round(nnz / n, 2), "generate_s": round(time.time() - t0, 1)}
         A = ctx.csr(n, n, ptr, col, val)
         x = rng.uniform(-1, 1, n)
@@ -283,7 +300,7 @@ def cmd_unstructured():
             gb = algorithmic_bytes(n, n, nnz, mode) / 1e9
             rec[mode] = {"ms": round(med, 4), "GBs": round(gb / (med * 1e-3), 1)}
         rec["fits_l2"] = bool(nnz * 12 < 100e6)
-        if mult <= 4:
+        if mult is None or mult <= 4:
             for relax, kry in (("spai0", "bicgstab"),):
                 D = ab.DropinSolver(ptr, col, val, relax, kry, ctx=ctx)
                 t1 = time.time()
