@@ -84,6 +84,16 @@ def lib():
         "b200_vec_data": [_vp, _P(_vp)],
         "b200_vec_upload": [_vp, _vp, _c.c_size_t],
         "b200_vec_download": [_vp, _vp, _c.c_size_t],
+        # FP32 objects of the mixed-precision composition (b200<float> hierarchy)
+        "b200_vec_create_f32": [_vp, _c.c_size_t, _P(_vp)],
+        "b200_vec_upload_f32": [_vp, _vp, _c.c_size_t],
+        "b200_vec_download_f32": [_vp, _vp, _c.c_size_t],
+        "b200_vec_dtype": [_vp, _P(_c.c_int)],
+        "b200_csr_create_i64_f32": [_vp, _i64, _i64, _vp, _vp, _vp, _P(_vp)],
+        "b200_csr_create_i32_f32": [_vp, _i64, _i64, _vp, _vp, _vp, _P(_vp)],
+        "b200_csr_dtype": [_vp, _P(_c.c_int)],
+        "b200_coarse_create_i64_f32": [_vp, _i64, _vp, _vp, _vp, _P(_vp)],
+        "b200_coarse_create_i32_f32": [_vp, _i64, _vp, _vp, _vp, _P(_vp)],
         "b200_csr_create_i64": [_vp, _i64, _i64, _vp, _vp, _vp, _P(_vp)],
         "b200_csr_create_i32": [_vp, _i64, _i64, _vp, _vp, _vp, _P(_vp)],
         "b200_csr_destroy": [_vp],
