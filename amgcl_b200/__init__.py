@@ -19,7 +19,7 @@ import numpy as np
 
 from . import build as _build
 
-__all__ = ["lib", "dropin_lib", "Context", "Vector", "Csr", "Coarse", "DropinSolver",
+__all__ = ["lib", "dropin_lib", "Context", "Vector", "Csr", "Coarse", "Krylov", "DropinSolver",
            "poisson3d", "unstructured3d", "B200Error", "RELAX", "KRYLOV", "nccl_unique_id",
            "partition", "dist_split"]
 
@@ -43,8 +43,10 @@ class ProfileEntry(_c.Structure):
                 ("launches", _i64), ("total_ms", _dbl), ("min_ms", _dbl)]
 
 
+# vecK: element-wise pass over K+1 vector streams (reads + writes)
 MODE_NAMES = {0: "spmv", 1: "spmv_acc", 2: "residual", 3: "relax", 10: "vec1", 11: "vec2",
-              12: "vec3", 20: "dot", 21: "relax_zero", 22: "coarse_gemv", 23: "memset",
+              12: "vec3", 13: "vec4", 14: "vec5", 15: "vec6", 16: "vec7",
+              20: "dot", 21: "relax_zero", 22: "coarse_gemv", 23: "memset", 24: "coarse_tail",
               30: "comm"}
 
 
@@ -138,6 +140,17 @@ def lib():
         "b200_graph_launch": [_vp, _vp, _P(_c.c_int)],
         "b200_graph_info": [_vp, _P(_i64), _P(_i64), _P(_i64), _P(_c.c_int)],
         "b200_graph_destroy": [_vp],
+        # fused Krylov steps (device-resident scalars)
+        "b200_krylov_create": [_vp, _c.c_size_t, _P(_vp)],
+        "b200_krylov_destroy": [_vp],
+        "b200_krylov_residual": [_vp, _vp, _vp, _vp, _vp, _P(_dbl)],
+        "b200_krylov_scalars": [_vp, _vp, _c.c_int],
+        "b200_cg_direction": [_vp, _vp, _vp, _vp],
+        "b200_cg_step": [_vp, _vp, _vp, _vp, _vp, _vp, _P(_dbl)],
+        "b200_bicg_start": [_vp, _vp, _vp],
+        "b200_bicg_direction": [_vp, _vp, _vp, _vp],
+        "b200_bicg_step_s": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _P(_dbl)],
+        "b200_bicg_step_r": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _P(_dbl)],
         "b200_profile_begin": [_vp],
         "b200_profile_end": [_vp, _vp, _i64, _P(_i64)],
     }
@@ -363,6 +376,64 @@ class Context:
 
     def coarse_solve(self, S, rhs, x):
         _check(lib().b200_coarse_solve(self.h, S.h, rhs.h, x.h), "b200_coarse_solve")
+
+
+class Krylov:
+    """Device-resident scalars of one Krylov solver (b200_krylov_t) + the fused steps."""
+
+    SCALARS = ("rho", "qp", "alpha", "ts", "tt", "omega", "rr", "ss", "rho_next")
+
+    def __init__(self, ctx, n):
+        self.ctx = ctx
+        self.h = _vp()
+        _check(lib().b200_krylov_create(ctx.h, int(n), _c.byref(self.h)), "b200_krylov_create")
+
+    def residual(self, rhs, A, x, r):
+        out = _dbl()
+        _check(lib().b200_krylov_residual(self.h, rhs.h, A.h, x.h, r.h, _c.byref(out)), "b200_krylov_residual")
+        return out.value
+
+    def scalars(self):
+        buf = (_dbl * 9)()
+        _check(lib().b200_krylov_scalars(self.h, buf, 9), "b200_krylov_scalars")
+        return dict(zip(self.SCALARS, list(buf)))
+
+    def cg_direction(self, r, s, p):
+        _check(lib().b200_cg_direction(self.h, r.h, s.h, p.h), "b200_cg_direction")
+
+    def cg_step(self, A, p, q, x, r):
+        out = _dbl()
+        _check(lib().b200_cg_step(self.h, A.h, p.h, q.h, x.h, r.h, _c.byref(out)), "b200_cg_step")
+        return out.value
+
+    def bicg_start(self, r, rh):
+        _check(lib().b200_bicg_start(self.h, r.h, rh.h), "b200_bicg_start")
+
+    def bicg_direction(self, r, v, p):
+        _check(lib().b200_bicg_direction(self.h, r.h, v.h, p.h), "b200_bicg_direction")
+
+    def bicg_step_s(self, A, rh, T, v, r, s, x):
+        out = _dbl()
+        _check(lib().b200_bicg_step_s(self.h, A.h, rh.h, T.h, v.h, r.h, s.h, x.h, _c.byref(out)),
+               "b200_bicg_step_s")
+        return out.value
+
+    def bicg_step_r(self, A, rh, T, t, s, r, x):
+        out = _dbl()
+        _check(lib().b200_bicg_step_r(self.h, A.h, rh.h, T.h, t.h, s.h, r.h, x.h, _c.byref(out)),
+               "b200_bicg_step_r")
+        return out.value
+
+    def close(self):
+        if self.h:
+            lib().b200_krylov_destroy(self.h)
+            self.h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Vector:

@@ -49,6 +49,22 @@ extern "C" int b200_device_count(void) {
     return n;
 }
 
+static int ctx_init(b200_ctx_t ctx, int device) {
+    cudaDeviceProp prop;
+    B200_CUDA(cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    if (prop.major < 10) return fail(B200_ECUDA, "amgcl_b200 needs an sm_100a (Blackwell B200) device");
+    B200_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
+    B200_CUDA(cudaMalloc(&ctx->dot_partial, kDotMaxBlocks * sizeof(double)));
+    B200_CUDA(cudaMalloc(&ctx->dot_ticket, sizeof(unsigned int)));
+    B200_CUDA(cudaMemset(ctx->dot_ticket, 0, sizeof(unsigned int)));
+    B200_CUDA(cudaHostAlloc(&ctx->dot_result_h, 8 * sizeof(double), cudaHostAllocMapped));
+    B200_CUDA(cudaHostGetDevicePointer(&ctx->dot_result_d, ctx->dot_result_h, 0));
+    B200_CUDA(cudaMalloc(&ctx->dot_dev, 2 * sizeof(double)));
+    return scal_create(ctx);
+}
+
 extern "C" int b200_ctx_create(int device, b200_ctx_t *out) {
     B200_REQUIRE(out != nullptr, "null output pointer");
     *out = nullptr;
@@ -64,21 +80,15 @@ extern "C" int b200_ctx_create(int device, b200_ctx_t *out) {
     if (const char *e = getenv("B200_PDL")) ctx->opt_pdl = atoi(e) ? 1 : 0;
     if (const char *e = getenv("B200_CYCLE_GRAPH")) ctx->opt_cycle_graph = atoi(e) ? 1 : 0;
     if (const char *e = getenv("B200_GRAPH_PDL")) ctx->opt_graph_pdl = atoi(e) ? 1 : 0;
-    cudaDeviceProp prop;
-    B200_CUDA(cudaGetDeviceProperties(&prop, device));
-    ctx->sm_count = prop.multiProcessorCount;
-    if (prop.major < 10) {
-        delete ctx;
-        return fail(B200_ECUDA, "amgcl_b200 needs an sm_100a (Blackwell B200) device");
+    if (const char *e = getenv("B200_FUSED_KRYLOV")) ctx->opt_fused_krylov = atoi(e) ? 1 : 0;
+    // any failure below releases what was created so far (b200_ctx_destroy null-checks every member)
+    const int rc = ctx_init(ctx, device);
+    if (rc != B200_OK) {
+        const std::string msg = g_last_error;
+        b200_ctx_destroy(ctx);
+        g_last_error = msg;
+        return rc;
     }
-    B200_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
-    ctx->stream = ctx->own_stream;
-    B200_CUDA(cudaMalloc(&ctx->dot_partial, kDotMaxBlocks * sizeof(double)));
-    B200_CUDA(cudaMalloc(&ctx->dot_ticket, sizeof(unsigned int)));
-    B200_CUDA(cudaMemset(ctx->dot_ticket, 0, sizeof(unsigned int)));
-    B200_CUDA(cudaHostAlloc(&ctx->dot_result_h, 8 * sizeof(double), cudaHostAllocMapped));
-    B200_CUDA(cudaHostGetDevicePointer(&ctx->dot_result_d, ctx->dot_result_h, 0));
-    B200_CUDA(cudaMalloc(&ctx->dot_dev, 2 * sizeof(double)));
     *out = ctx;
     return B200_OK;
 }
@@ -86,7 +96,13 @@ extern "C" int b200_ctx_create(int device, b200_ctx_t *out) {
 extern "C" int b200_ctx_destroy(b200_ctx_t ctx) {
     if (!ctx) return B200_OK;
     GUARD(ctx);
-    cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    scal_destroy(ctx);
+    if (ctx->scal_x_local) {
+        for (int q = 0; q < ctx->nranks; ++q)
+            if (q != ctx->rank && ctx->scal_x_peer[q]) cudaIpcCloseMemHandle(ctx->scal_x_peer[q]);
+        cudaFree(ctx->scal_x_local);
+    }
     if (ctx->dot_partial) cudaFree(ctx->dot_partial);
     if (ctx->dot_ticket) cudaFree(ctx->dot_ticket);
     if (ctx->dot_result_h) cudaFreeHost(ctx->dot_result_h);
@@ -222,6 +238,7 @@ static int64_t *option_slot(b200_ctx_t ctx, const char *key) {
     if (!strcmp(key, "pdl")) return &ctx->opt_pdl;
     if (!strcmp(key, "cycle_graph")) return &ctx->opt_cycle_graph;
     if (!strcmp(key, "graph_pdl")) return &ctx->opt_graph_pdl;
+    if (!strcmp(key, "fused_krylov")) return &ctx->opt_fused_krylov;
     return nullptr;
 }
 
@@ -370,7 +387,10 @@ extern "C" int b200_graph_launch(b200_ctx_t ctx, b200_graph_t g, int *launched) 
     for (const GraphSlot &s : g->slots) {
         *s.slot = s.p1;
         if (s.zp) *s.zp = s.z1;
+        if (s.gen) ++*s.gen;                 // the replay wrote (or may have written) the vector
     }
+    // products the recorded kernels leave in the scalar table (smoother sweep -> <rhs, x>)
+    for (const GraphProduct &p : g->products) product_record(ctx, p.a, p.b, p.slot);
     ctx->launches += g->launches;
     g->replays++;
     *launched = 1;

@@ -54,6 +54,16 @@ extern "C" int b200_dist_init(b200_ctx_t ctx, const char *id, size_t size, int n
         ctx->p2p = ok != 0;
         if (!ctx->p2p) cudaGetLastError();
     }
+    if (ctx->p2p) {
+        // exchange buffers of the device scalar table: in-kernel all-reduce (reduce.cuh)
+        void *local = nullptr;
+        int rc = peer_alloc(ctx, sizeof(ScalExchange), &local, ctx->scal_x_peer);
+        if (rc) return rc;
+        ctx->scal_x_local = static_cast<ScalExchange *>(local);
+        B200_CUDA(cudaMalloc(&ctx->scal_x_table, kMaxRanks * sizeof(ScalExchange *)));
+        B200_CUDA(cudaMemcpy(ctx->scal_x_table, ctx->scal_x_peer, kMaxRanks * sizeof(void *),
+                             cudaMemcpyHostToDevice));
+    }
     return B200_OK;
 }
 
@@ -372,30 +382,8 @@ int partials_to_coarse(b200_ctx_t ctx, b200_csr_t A, b200_vec_t yc) {
 // partials and hand the result to the host (mpi/inner_product.hpp:53-62 does the same with
 // MPI_Allreduce on the host).
 int dist_dot_finish(b200_ctx_t ctx, double *result) {
-    if (ctx->p2p) {
-        // every rank stores its partial into slot `rank` of every peer; each rank then adds
-        // the P partials in rank order (bitwise identical on all ranks) straight into
-        // mapped host memory
-        const int par = (int)(ctx->dot_seq & 1);
-        const unsigned long long seq = ++ctx->dot_seq;
-        PeerTargets tgt;
-        WaitList w;
-        for (int q = 0; q < kMaxRanks; ++q) { tgt.data[q] = nullptr; tgt.flag[q] = nullptr; w.flag[q] = nullptr; }
-        for (int q = 0; q < ctx->nranks; ++q) {
-            tgt.data[q] = data_at(ctx->dot_pb_peer[q], par, 256) + ctx->rank;
-            tgt.flag[q] = flag_at(ctx->dot_pb_peer[q], par, ctx->rank);
-            w.flag[q] = flag_at(ctx->dot_pb_local, par, q);
-        }
-        int rc = launch_push(ctx, 1, ctx->dot_dev, nullptr, tgt, 0, seq);
-        if (rc) return rc;
-        reduce_sum_kernel<<<1, 32, 0, ctx->stream>>>(1, data_at(ctx->dot_pb_local, par, 256), 1, ctx->nranks,
-                                                      w, seq, ctx->dot_dev + 1, ctx->dot_result_d);
-        B200_CHECK_LAUNCH();
-        ctx->launches++;
-        B200_CUDA(cudaStreamSynchronize(ctx->stream));
-        *result = *reinterpret_cast<volatile double *>(ctx->dot_result_h);
-        return B200_OK;
-    }
+    // (NCCL transport; with the peer-memory transport the all-reduce happens inside the
+    // reducing kernel, reduce.cuh)
     B200_NCCL(nccl().AllReduce(ctx->dot_dev, ctx->dot_dev, 1, ncclDouble, ncclSum, comm_of(ctx), ctx->stream));
     B200_CUDA(cudaMemcpyAsync(ctx->dot_result_h, ctx->dot_dev, sizeof(double), cudaMemcpyDeviceToHost,
                               ctx->stream));

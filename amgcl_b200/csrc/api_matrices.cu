@@ -541,26 +541,49 @@ extern "C" int b200_csr_plan(b200_csr_t A, int *lanes_per_row, int64_t *n_blocks
 // ---------------------------------------------------------------------------
 namespace b200 {
 
+// what a caller wants reduced while the rows are in registers (reduce.cuh); slots == nullptr: nothing
+struct DotReq {
+    int           ndot  = 0;
+    const double *w     = nullptr;     // second operand of the first product (nullptr: see CsrArgsT)
+    const int    *slots = nullptr;
+    bool          done  = false;       // set when the launch produced the scalars
+};
+template <class P>
+static void apply_req(b200_ctx_t ctx, b200_csr_t A, CsrArgsT<P> &a, DotReq *req) {
+    if (!req || !req->ndot || ctx->opt_spmv_variant != 1 || a.nblocks == 0) return;
+    if (!std::is_same<typename P::TY, double>::value) return;
+    // partitioned operator: every rank launches, the finishing CTAs all-reduce over the peers
+    const bool across = A->kind == B200_CK_SQUARE;
+    if (across && !ctx->scal_x_table) return;       // NCCL transport: separate reduction instead
+    a.ndot = req->ndot;
+    a.w = req->w;
+    red_out(ctx, req->ndot, req->slots, a.red, across);
+    req->done = true;
+}
+
 template <class P>
 static int spmv_local(b200_ctx_t ctx, double alpha, b200_csr_t A, b200_vec_t x, double beta,
-                      b200_vec_t y) {
+                      b200_vec_t y, DotReq *req = nullptr) {
     CsrArgsT<P> a = base_args_t<P>(A);
     const double *px;
     int rc = rd(x, &px);
     if (rc) return rc;
     a.x = tp<typename P::TX>(px);
     a.alpha = alpha; a.beta = beta;
+    apply_req(ctx, A, a, req);
     if (beta == 0.0 || y->zero_pending) {
         a.y = tp<typename P::TY>(wr(y));
         return launch_csr<MODE_SPMV>(ctx, A, a);
     }
-    a.y = tp<typename P::TY>(y->ptr);
+    a.y = tp<typename P::TY>(mut(y));
     return launch_csr<MODE_SPMV_ACC>(ctx, A, a);
 }
 
 template <class P>
-static int residual_local(b200_ctx_t ctx, b200_vec_t f, b200_csr_t A, b200_vec_t x, b200_vec_t r) {
+static int residual_local(b200_ctx_t ctx, b200_vec_t f, b200_csr_t A, b200_vec_t x, b200_vec_t r,
+                          DotReq *req = nullptr) {
     CsrArgsT<P> a = base_args_t<P>(A);
+    apply_req(ctx, A, a, req);
     const double *px, *pf;
     int rc = rd(x, &px);
     if (rc) return rc;
@@ -568,15 +591,16 @@ static int residual_local(b200_ctx_t ctx, b200_vec_t f, b200_csr_t A, b200_vec_t
     if (rc) return rc;
     a.x = tp<typename P::TX>(px);
     a.f = tp<typename P::TF>(pf);
-    a.y = tp<typename P::TY>((f == r) ? r->ptr : wr(r));
+    a.y = tp<typename P::TY>((f == r) ? mut(r) : wr(r));
     return launch_csr<MODE_RESID>(ctx, A, a);
 }
 
 
 } // namespace b200
 
-extern "C" int b200_spmv(b200_ctx_t ctx, double alpha, b200_csr_t A, b200_vec_t x, double beta,
-                         b200_vec_t y) {
+namespace b200 {
+static int spmv_impl(b200_ctx_t ctx, double alpha, b200_csr_t A, b200_vec_t x, double beta,
+                     b200_vec_t y, DotReq *req) {
     CHECK_CTX(ctx);
     B200_REQUIRE(A && x && y, "null argument");
     touch(ctx, {x, y});
@@ -588,7 +612,7 @@ extern "C" int b200_spmv(b200_ctx_t ctx, double alpha, b200_csr_t A, b200_vec_t 
     if (A->dtype == B200_F32) {
         // FP32 operator (mixed-precision hierarchy): single GPU, persistent ring kernels
         if (all32({x, y})) return spmv_local<PrecFF>(ctx, alpha, A, x, beta, y);
-        if (all64({x, y})) return spmv_local<PrecFD>(ctx, alpha, A, x, beta, y);
+        if (all64({x, y})) return spmv_local<PrecFD>(ctx, alpha, A, x, beta, y, req);
         if (x->dtype == B200_F32 && y->dtype == B200_F64)
             return spmv_local<PrecFFD>(ctx, alpha, A, x, beta, y);
         return B200_BAD_MIX("spmv");
@@ -620,16 +644,17 @@ extern "C" int b200_spmv(b200_ctx_t ctx, double alpha, b200_csr_t A, b200_vec_t 
             if (rc) return rc;
         }
     }
+    if (A->kind == B200_CK_LOCAL || A->kind == B200_CK_SQUARE) apply_req(ctx, A, a, req);
     if (beta == 0.0 || y->zero_pending) {
         a.y = wr(y);
         return launch_csr<MODE_SPMV>(ctx, A, a);
     }
-    a.y = y->ptr;
+    a.y = mut(y);
     return launch_csr<MODE_SPMV_ACC>(ctx, A, a);
 }
 
-extern "C" int b200_residual(b200_ctx_t ctx, b200_vec_t f, b200_csr_t A, b200_vec_t x,
-                             b200_vec_t r) {
+static int residual_impl(b200_ctx_t ctx, b200_vec_t f, b200_csr_t A, b200_vec_t x, b200_vec_t r,
+                         DotReq *req) {
     CHECK_CTX(ctx);
     B200_REQUIRE(f && A && x && r, "null argument");
     touch(ctx, {f, x, r});
@@ -643,7 +668,7 @@ extern "C" int b200_residual(b200_ctx_t ctx, b200_vec_t f, b200_csr_t A, b200_ve
     GUARD(ctx);
     if (A->dtype == B200_F32) {
         if (all32({f, x, r})) return residual_local<PrecFF>(ctx, f, A, x, r);
-        if (all64({f, x, r})) return residual_local<PrecFD>(ctx, f, A, x, r);
+        if (all64({f, x, r})) return residual_local<PrecFD>(ctx, f, A, x, r, req);
         if (all64({f, x}) && r->dtype == B200_F32) return residual_local<PrecFDF>(ctx, f, A, x, r);
         return B200_BAD_MIX("residual");
     }
@@ -659,8 +684,46 @@ extern "C" int b200_residual(b200_ctx_t ctx, b200_vec_t f, b200_csr_t A, b200_ve
         rc = halo_into(ctx, A, a);
         if (rc) return rc;
     }
-    a.y = (f == r) ? r->ptr : wr(r);   // r == f is fine: each row reads f[r] before writing
+    a.y = (f == r) ? mut(r) : wr(r);   // r == f is fine: each row reads f[r] before writing
+    apply_req(ctx, A, a, req);
     return launch_csr<MODE_RESID>(ctx, A, a);
+}
+
+// y = A x (alpha = 1, beta = 0) leaving <y, w> (and <y, y> when ndot == 2) in the table slots;
+// falls back to a separate reduction launch where the streaming kernel cannot produce them.
+int spmv_with_dots(b200_ctx_t ctx, b200_csr_t A, b200_vec_t x, b200_vec_t y, b200_vec_t w, int ndot,
+                   const int *slots) {
+    DotReq req;
+    req.ndot = ndot; req.slots = slots;
+    const double *pw = nullptr;
+    if (w != y) {
+        int rc = rd(w, &pw);
+        if (rc) return rc;
+    }
+    req.w = pw;
+    int rc = spmv_impl(ctx, 1.0, A, x, 0.0, y, &req);
+    if (rc || req.done || A->kind == B200_CK_GHOST) return rc;
+    return launch_dot_slots(ctx, y, w, ndot == 2 ? y : nullptr, slots);
+}
+
+// r = f - A x leaving <r, r> in the table slot
+int residual_with_norm(b200_ctx_t ctx, b200_vec_t f, b200_csr_t A, b200_vec_t x, b200_vec_t r, int slot) {
+    DotReq req;
+    req.ndot = 1; req.slots = &slot;
+    int rc = residual_impl(ctx, f, A, x, r, &req);
+    if (rc || req.done || A->kind == B200_CK_GHOST) return rc;
+    return launch_dot_slots(ctx, r, r, nullptr, &slot);
+}
+} // namespace b200
+
+extern "C" int b200_spmv(b200_ctx_t ctx, double alpha, b200_csr_t A, b200_vec_t x, double beta,
+                         b200_vec_t y) {
+    return spmv_impl(ctx, alpha, A, x, beta, y, nullptr);
+}
+
+extern "C" int b200_residual(b200_ctx_t ctx, b200_vec_t f, b200_csr_t A, b200_vec_t x,
+                             b200_vec_t r) {
+    return residual_impl(ctx, f, A, x, r, nullptr);
 }
 
 // ---------------------------------------------------------------------------
@@ -736,6 +799,7 @@ extern "C" int b200_relax(b200_ctx_t ctx, b200_csr_t A, b200_vec_t rhs, b200_vec
         a.y = tp<float>(wr(tmp));
         rc = launch_csr<MODE_RELAX>(ctx, A, a);
         if (rc) return rc;
+        x->gen++; tmp->gen++;
         if (x->owned && tmp->owned && x->cap == tmp->cap) std::swap(x->ptr, tmp->ptr);
         else B200_CUDA(cudaMemcpyAsync(x->ptr, tmp->ptr, x->len * x->esz, cudaMemcpyDeviceToDevice, ctx->stream));
         return B200_OK;
@@ -752,10 +816,20 @@ extern "C" int b200_relax(b200_ctx_t ctx, b200_csr_t A, b200_vec_t rhs, b200_vec
         if (rc) return rc;
         a.x = px; a.f = pf; a.d = tp<float>(pd); a.alpha = omega;
         a.y = A->scratch64;
+        // a Krylov solver of this size is alive: leave <rhs, x_new> behind (cg.hpp:184)
+        DotReq req;
+        int pslot = -1;
+        if (product_wanted(ctx, (size_t)A->gl_rows)) {
+            pslot = product_take_slot(ctx);
+            req.ndot = 1; req.slots = &pslot;
+            apply_req(ctx, A, a, &req);
+        }
         rc = launch_csr<MODE_RELAX>(ctx, A, a);
         if (rc) return rc;
+        x->gen++;
         if (x->owned && x->cap == (size_t)A->nrows) std::swap(x->ptr, A->scratch64);
         else B200_CUDA(cudaMemcpyAsync(x->ptr, A->scratch64, x->len * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        if (req.done) product_record(ctx, rhs, x, pslot);
         return B200_OK;
     }
 
@@ -769,14 +843,25 @@ extern "C" int b200_relax(b200_ctx_t ctx, b200_csr_t A, b200_vec_t rhs, b200_vec
     }
     a.f = pf; a.d = pd; a.alpha = omega;
     a.y = wr(tmp);
+    // a Krylov solver of this size is alive: leave <rhs, x_new> behind (cg.hpp:184 asks for
+    // exactly this product right after the V-cycle's last sweep)
+    DotReq req;
+    int pslot = -1;
+    if (product_wanted(ctx, (size_t)A->gl_rows)) {
+        pslot = product_take_slot(ctx);
+        req.ndot = 1; req.slots = &pslot;
+        apply_req(ctx, A, a, &req);
+    }
     rc = launch_csr<MODE_RELAX>(ctx, A, a);
     if (rc) return rc;
+    x->gen++;
     if (x->owned && tmp->owned && x->cap == tmp->cap) {
         std::swap(x->ptr, tmp->ptr);          // x now holds the new iterate
     } else {
         B200_CUDA(cudaMemcpyAsync(x->ptr, tmp->ptr, x->len * sizeof(double),
                                   cudaMemcpyDeviceToDevice, ctx->stream));
     }
+    if (req.done) product_record(ctx, rhs, x, pslot);
     return B200_OK;
 }
 

@@ -90,6 +90,7 @@ extern "C" int b200_vec_wrap(b200_ctx_t ctx, double *device_ptr, size_t n, b200_
     v->cap = n;
     v->ptr = device_ptr;
     v->owned = false;
+    v->escaped = true;
     v->zero_pending = false;
     *out = v;
     return B200_OK;
@@ -138,6 +139,8 @@ extern "C" int b200_vec_data(b200_vec_t v, double **device_ptr) {
     GUARD(v->ctx);
     int rc = materialize(v);
     *device_ptr = v->ptr;
+    v->escaped = true;          // the caller may write through the raw pointer
+    v->gen++;
     return rc;
 }
 
@@ -294,36 +297,34 @@ extern "C" int b200_copy(b200_ctx_t ctx, b200_vec_t x, b200_vec_t y) {
 
 namespace b200 {
 template <class T>
-static void launch_dot_kernel(b200_ctx_t ctx, b200_vec_t x, b200_vec_t y, double *result_dev) {
+static int launch_dot_kernel(b200_ctx_t ctx, b200_vec_t x, b200_vec_t y, double *result_dev) {
     const bool vec_ok = aligned16(x->ptr) && aligned16(y->ptr);
     const int grid = std::min(grid_for(ctx, x->len, 32 / (int)sizeof(T) * 2), kDotMaxBlocks);
     ProfScope prof(ctx, B200_PROF_DOT, (int64_t)x->len, 1, 0);
-    const cudaError_t rc = launch_pdl(ctx, dot_kernel<T>, dim3(grid), dim3(kThreads), 0, x->len,
-                                      (const T *)tp<T>(x->ptr), (const T *)tp<T>(y->ptr), ctx->dot_partial,
-                                      ctx->dot_ticket, result_dev, vec_ok);
-    if (rc != cudaSuccess) cuda_fail(rc, "dot_kernel launch", __FILE__, __LINE__);
+    B200_CUDA(launch_pdl(ctx, dot_kernel<T>, dim3(grid), dim3(kThreads), 0, x->len,
+                         (const T *)tp<T>(x->ptr), (const T *)tp<T>(y->ptr), ctx->dot_partial,
+                         ctx->dot_ticket, result_dev, vec_ok));
+    B200_CHECK_LAUNCH();
+    ctx->launches++;
+    return B200_OK;
 }
-} // namespace b200
 
-extern "C" int b200_dot(b200_ctx_t ctx, b200_vec_t x, b200_vec_t y, double *result) {
-    CHECK_CTX(ctx);
-    B200_REQUIRE(x && y && result, "null argument");
-    NOT_RECORDING(ctx, "dot (host-synchronous)");
-    B200_REQUIRE(same_layout(x, y), "dot: size mismatch");
-    if (x->dtype != y->dtype) return B200_BAD_MIX("dot");
-    GUARD(ctx);
+// The stand-alone reduction kernel with the result in mapped host memory: FP32 vectors, and
+// partitioned vectors when the exchange transport is NCCL (the peer-memory transport reduces
+// inside the kernel, api_krylov.cu).  Arguments were checked by b200_dot.
+int dot_legacy(b200_ctx_t ctx, b200_vec_t x, b200_vec_t y, double *result) {
     const bool dist = x->kind == B200_VK_DIST;
-    const bool trivial = x->len == 0 || x->zero_pending || y->zero_pending || x->kind == B200_VK_GHOST;
+    const bool trivial = x->len == 0 || x->zero_pending || y->zero_pending;
+    int rc;
     if (!dist) {
         if (trivial) {
             B200_CUDA(cudaStreamSynchronize(ctx->stream));
             *result = 0.0;
             return B200_OK;
         }
-        if (x->dtype == B200_F64) launch_dot_kernel<double>(ctx, x, y, ctx->dot_result_d);
-        else launch_dot_kernel<float>(ctx, x, y, ctx->dot_result_d);
-        B200_CHECK_LAUNCH();
-        ctx->launches++;
+        rc = x->dtype == B200_F64 ? launch_dot_kernel<double>(ctx, x, y, ctx->dot_result_d)
+                                  : launch_dot_kernel<float>(ctx, x, y, ctx->dot_result_d);
+        if (rc) return rc;
         B200_CUDA(cudaStreamSynchronize(ctx->stream));
         *result = *reinterpret_cast<volatile double *>(ctx->dot_result_h);
         return B200_OK;
@@ -333,12 +334,12 @@ extern "C" int b200_dot(b200_ctx_t ctx, b200_vec_t x, b200_vec_t y, double *resu
     if (trivial) {
         B200_CUDA(cudaMemsetAsync(ctx->dot_dev, 0, sizeof(double), ctx->stream));
     } else {
-        launch_dot_kernel<double>(ctx, x, y, ctx->dot_dev);
-        B200_CHECK_LAUNCH();
-        ctx->launches++;
+        rc = launch_dot_kernel<double>(ctx, x, y, ctx->dot_dev);
+        if (rc) return rc;
     }
     return dist_dot_finish(ctx, result);
 }
+} // namespace b200
 
 namespace b200 {
 template <class T>
@@ -351,7 +352,7 @@ static int axpby_t(b200_ctx_t ctx, double a, b200_vec_t x, double b, b200_vec_t 
         return launch_ew<AxF<T>, false, false, T>(ctx, x->len, f, tp<T>(px), nullptr, nullptr, tp<T>(wr(y)));
     }
     AxpbyF<T> f{(T)a, (T)b};
-    return launch_ew<AxpbyF<T>, true, false, T>(ctx, x->len, f, tp<T>(px), tp<T>(y->ptr), nullptr, tp<T>(y->ptr));
+    return launch_ew<AxpbyF<T>, true, false, T>(ctx, x->len, f, tp<T>(px), tp<T>(y->ptr), nullptr, tp<T>(mut(y)));
 }
 template <class T>
 static int axpbypcz_t(b200_ctx_t ctx, double a, b200_vec_t x, double b, b200_vec_t y, double c, b200_vec_t z) {
@@ -365,7 +366,7 @@ static int axpbypcz_t(b200_ctx_t ctx, double a, b200_vec_t x, double b, b200_vec
         return launch_ew<AxpbyF<T>, true, false, T>(ctx, x->len, f, tp<T>(px), tp<T>(py), nullptr, tp<T>(wr(z)));
     }
     AxpbypczF<T> f{(T)a, (T)b, (T)c};
-    return launch_ew<AxpbypczF<T>, true, true, T>(ctx, x->len, f, tp<T>(px), tp<T>(py), tp<T>(z->ptr), tp<T>(z->ptr));
+    return launch_ew<AxpbypczF<T>, true, true, T>(ctx, x->len, f, tp<T>(px), tp<T>(py), tp<T>(z->ptr), tp<T>(mut(z)));
 }
 template <class T>
 static int vmul_t(b200_ctx_t ctx, double alpha, b200_vec_t x, b200_vec_t y, double beta, b200_vec_t z) {
@@ -379,7 +380,7 @@ static int vmul_t(b200_ctx_t ctx, double alpha, b200_vec_t x, b200_vec_t y, doub
         return launch_ew<VmulF<T>, true, false, T>(ctx, x->len, f, tp<T>(px), tp<T>(py), nullptr, tp<T>(wr(z)));
     }
     VmulAccF<T> f{(T)alpha, (T)beta};
-    return launch_ew<VmulAccF<T>, true, true, T>(ctx, x->len, f, tp<T>(px), tp<T>(py), tp<T>(z->ptr), tp<T>(z->ptr));
+    return launch_ew<VmulAccF<T>, true, true, T>(ctx, x->len, f, tp<T>(px), tp<T>(py), tp<T>(z->ptr), tp<T>(mut(z)));
 }
 } // namespace b200
 
@@ -432,7 +433,7 @@ extern "C" int b200_vmul(b200_ctx_t ctx, double alpha, b200_vec_t x, b200_vec_t 
         }
         VmulAccF<double> f{alpha, beta};
         return launch_ew_mixed<VmulAccF<double>, true, true>(ctx, x->len, f, tp<float>(px), tp<float>(py),
-                                                            (const double *)z->ptr, z->ptr);
+                                                            (const double *)z->ptr, mut(z));
     }
     return B200_BAD_MIX("vmul");
 }
@@ -559,10 +560,10 @@ extern "C" int b200_scatter(b200_ctx_t ctx, b200_index_t I, b200_vec_t src, b200
     ProfScope prof(ctx, B200_PROF_VECTOR + 1, (int64_t)I->n, 1, 0);
     if (src->dtype == B200_F64)
         B200_CUDA(launch_pdl(ctx, scatter_kernel<double>, dim3(grid), dim3(kThreads), 0, I->n,
-                             (const int *)I->idx, ps, dst->ptr));
+                             (const int *)I->idx, ps, mut(dst)));
     else
         B200_CUDA(launch_pdl(ctx, scatter_kernel<float>, dim3(grid), dim3(kThreads), 0, I->n,
-                             (const int *)I->idx, (const float *)tp<float>(ps), tp<float>(dst->ptr)));
+                             (const int *)I->idx, (const float *)tp<float>(ps), tp<float>(mut(dst))));
     B200_CHECK_LAUNCH();
     ctx->launches++;
     return B200_OK;

@@ -48,6 +48,9 @@ constexpr int kThreads      = 256;    // threads per CTA in every streaming kern
 constexpr int kRowsCapMax   = 1024;   // most rows a row block may hold
 constexpr int kNnzCapMax    = 6144;   // most non-zeros a staged row block may hold
 constexpr int kDotMaxBlocks = 2048;   // upper bound on partial sums of one dot product
+constexpr int kMaxRed       = 3;      // scalars one launch may produce (reduce.cuh)
+constexpr int kScalSlots    = 256;    // device scalar table of a context (reduce.cuh)
+struct ScalExchange;                  // multi-GPU exchange buffer of the scalar table
 
 // multi-GPU peer-memory exchange buffers (peer.cuh): [flags 256 B | parity 0 | parity 1]
 constexpr int kMaxRanks   = 16;
@@ -73,6 +76,28 @@ struct b200_ctx_s {
     unsigned int *dot_ticket  = nullptr;  // device, self-resetting
     double       *dot_result_h = nullptr; // pinned + mapped host scalar(s)
     double       *dot_result_d = nullptr; // device alias of dot_result_h
+
+    // device scalar table (reduce.cuh): results of reductions done inside the streaming
+    // kernels stay on the device for the next kernel; the host reads the mapped mirror
+    double       *scal_d  = nullptr;      // [kScalSlots] device
+    double       *scal_h  = nullptr;      // [kScalSlots] pinned + mapped host mirror
+    double       *scal_hd = nullptr;      // device alias of scal_h
+    double       *red_partial = nullptr;  // [kMaxRed * kDotMaxBlocks] per-CTA partial sums
+    unsigned int *red_ticket  = nullptr;  // device, self-resetting
+    bool          scal_used[b200::kScalSlots] = {};
+    unsigned long long scal_seq[b200::kScalSlots] = {};   // uses of each slot so far (multi-GPU parity)
+    b200::ScalExchange  *scal_x_local = nullptr;    // multi-GPU: exchange buffer (peer-mapped)
+    void                *scal_x_peer[16] = {};
+    b200::ScalExchange **scal_x_table = nullptr;    // device array [nranks] of the mapped buffers
+
+    // products left behind by a producer kernel (the fused smoother sweep leaves <rhs, x_new>):
+    // b200_dot / the Krylov steps take them instead of launching a reduction when the operands
+    // are exactly the producer's and unmodified since (generation counters of the vectors)
+    struct Product { b200_vec_t a = nullptr, b = nullptr; uint64_t gen_a = 0, gen_b = 0; int slot = -1; };
+    Product       products[4];
+    int           product_next = 0;
+    int           product_slot0 = -1;     // first of the 4 table slots the products rotate through
+    std::vector<size_t> krylov_sizes;     // sizes of the live Krylov workspaces (b200_krylov_*)
 
     // optional per-launch timing of the CSR streaming kernels (b200_profile_*)
     bool                      profiling = false;
@@ -109,6 +134,7 @@ struct b200_ctx_s {
     int64_t opt_pdl           = 1;        // programmatic dependent launch of the solve kernels
     int64_t opt_cycle_graph   = 1;        // the shim's preconditioner wrapper may record CUDA graphs
     int64_t opt_graph_pdl     = 1;        // keep the PDL attribute on launches recorded into a graph
+    int64_t opt_fused_krylov  = 1;        // the C++ binding's cg / bicgstab use the fused b200_cg_* / b200_bicg_* steps
 
     // CUDA-graph recording of a call sequence (b200_graph_*)
     b200_graph_s *recording   = nullptr;  // non-null between b200_graph_begin and _end / _abort
@@ -135,6 +161,9 @@ struct b200_vec_s {
     // A-pass), dropped by any full overwrite, materialised by any other read.
     bool       zero_pending = false;
     bool       in_graph     = false;   // some recorded graph refers to this vector
+    uint64_t   gen          = 0;       // bumped by every write through the library
+    bool       escaped      = false;   // raw pointer handed out / external storage: contents
+                                       // may change behind the library's back
 };
 
 enum { B200_CK_LOCAL = 0, B200_CK_SQUARE = 1, B200_CK_PROLONG = 2, B200_CK_RESTRICT = 3,

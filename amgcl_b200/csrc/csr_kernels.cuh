@@ -33,6 +33,7 @@
 // type of the OUTPUT vector.
 #pragma once
 #include "common.cuh"
+#include "reduce.cuh"
 
 namespace b200 {
 
@@ -82,6 +83,12 @@ struct CsrArgsT {
     const typename P::TD *d;      // diagonal     (RELAX)
     double        alpha;  // SPMV: alpha; RELAX: omega
     double        beta;   // SPMV_ACC
+    // scalars produced while the rows are in registers (reduce.cuh; FP64 outputs only):
+    //   ndot >= 1: sum_r y_r * w_r  (w == nullptr: RELAX uses the rhs f, otherwise y itself)
+    //   ndot == 2: additionally sum_r y_r^2
+    int           ndot;
+    const double *w;
+    RedOut        red;
 };
 typedef CsrArgsT<PrecDD> CsrArgs;
 
@@ -149,21 +156,36 @@ __device__ __forceinline__ bool issue_block(const CsrArgsT<P> &a, const BlockDes
 }
 
 // ---- per-row epilogue ----------------------------------------------------------
+// acc: the thread's running contributions to the launch's scalars (reduce.cuh)
+struct RowAcc { double s0, s1; };
+
 template <int MODE, class P>
-__device__ __forceinline__ void store_row(const CsrArgsT<P> &a, int r, typename P::TY sum) {
+__device__ __forceinline__ void store_row(const CsrArgsT<P> &a, int r, typename P::TY sum, RowAcc &acc) {
     typedef typename P::TY TY;
+    TY out;
+    double wv = 0.0;
     if (MODE == MODE_SPMV) {
-        a.y[r] = (TY)(a.alpha * sum);
+        out = (TY)(a.alpha * sum);
     } else if (MODE == MODE_SPMV_ACC) {
-        a.y[r] = (TY)(a.alpha * sum + a.beta * a.y[r]);
+        out = (TY)(a.alpha * sum + a.beta * a.y[r]);
     } else if (MODE == MODE_RESID) {
-        a.y[r] = (TY)(a.f[r] - sum);
+        out = (TY)(a.f[r] - sum);
     } else {
         // x_new = (omega*d)*t + x with t = f - A x; same association as the
         // reference's vmul  z = a*x*y + b*z  (builtin.hpp:1238-1265)
-        const TY t = (TY)(a.f[r] - sum);
+        const typename P::TF fr = a.f[r];
+        const TY t = (TY)(fr - sum);
         const TY w = (TY)(a.alpha * a.d[r]);
-        a.y[r] = fma(w, t, (TY)a.x[r]);
+        out = fma(w, t, (TY)a.x[r]);
+        wv = (double)fr;
+    }
+    a.y[r] = out;
+    if (a.ndot) {
+        const double yv = (double)out;
+        if (a.w) wv = a.w[r];
+        else if (MODE != MODE_RELAX) wv = yv;
+        acc.s0 = fma(yv, wv, acc.s0);
+        if (a.ndot > 1) acc.s1 = fma(yv, yv, acc.s1);
     }
 }
 
@@ -202,7 +224,7 @@ __device__ __forceinline__ void wait_for_halo(const CsrArgsT<P> &a, int b) {
 // ---- reduce the rows of a staged block out of shared memory ---------------------
 template <int MODE, int L, bool HALO, class P>
 __device__ __forceinline__ void compute_staged(const CsrArgsT<P> &a, const BlockDesc &d,
-                                               const char *stage, const StageLayout &lay) {
+                                               const char *stage, const StageLayout &lay, RowAcc &acc) {
     typedef typename P::TV TV;
     typedef typename P::TX TX;
     typedef typename P::TY TS;                       // row sums live in the output's type
@@ -263,7 +285,7 @@ __device__ __forceinline__ void compute_staged(const CsrArgsT<P> &a, const Block
             }
 #pragma unroll
             for (int u = 0; u < RU; ++u)
-                if (rowok[u] && lane == 0) store_row<MODE>(a, d.r0 + base + u * G + g, sum[u]);
+                if (rowok[u] && lane == 0) store_row<MODE>(a, d.r0 + base + u * G + g, sum[u], acc);
         }
     } else
     for (int base = 0; base < nr; base += G) {
@@ -298,14 +320,14 @@ __device__ __forceinline__ void compute_staged(const CsrArgsT<P> &a, const Block
 #pragma unroll
             for (int o = L / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
         }
-        if (valid && lane == 0) store_row<MODE>(a, d.r0 + rr, sum);
+        if (valid && lane == 0) store_row<MODE>(a, d.r0 + rr, sum, acc);
     }
 }
 
 // ---- rows too long to stage: whole CTA strides over each row -----------------------
 template <int MODE, bool HALO, class P>
 __device__ __forceinline__ void compute_long(const CsrArgsT<P> &a, const BlockDesc &d,
-                                             double *red_s /* >= 8 doubles */) {
+                                             double *red_s /* >= 8 doubles */, RowAcc &acc) {
     typedef typename P::TX TX;
     typedef typename P::TY TS;
     const TX *__restrict__ x = a.x;
@@ -323,7 +345,7 @@ __device__ __forceinline__ void compute_long(const CsrArgsT<P> &a, const BlockDe
             TS tot = 0;
 #pragma unroll
             for (int w = 0; w < kThreads / 32; ++w) tot += (TS)red_s[w];
-            store_row<MODE>(a, r, tot);
+            store_row<MODE>(a, r, tot, acc);
         }
     }
 }
@@ -340,6 +362,7 @@ __global__ void __launch_bounds__(kThreads, 4) csr_block_kernel(const CsrArgsT<P
     const int b = blockIdx.x;
     const BlockDesc d = load_desc(a, b);          // broadcast loads, uniform
     const bool staged = (d.e1 - d.e0) <= a.nnz_cap;
+    RowAcc acc = {0.0, 0.0};                      // (this variant produces no scalars)
 
     if (staged) {
         if (threadIdx.x == 0) {
@@ -350,10 +373,10 @@ __global__ void __launch_bounds__(kThreads, 4) csr_block_kernel(const CsrArgsT<P
         __syncthreads();
         ptx::mbar_wait(bar, 0);
         wait_for_halo<HALO>(a, b);
-        compute_staged<MODE, L, HALO>(a, d, stage, lay);
+        compute_staged<MODE, L, HALO>(a, d, stage, lay, acc);
     } else {
         wait_for_halo<HALO>(a, b);
-        compute_long<MODE, HALO>(a, d, red_s);
+        compute_long<MODE, HALO>(a, d, red_s, acc);
     }
 }
 
@@ -388,15 +411,16 @@ __global__ void __launch_bounds__(kThreads, 2) csr_ring_kernel(const CsrArgsT<P>
     __syncthreads();
     ptx::pdl_wait();         // vectors (x, f, d, y) come from earlier kernels: from here on
 
+    RowAcc acc = {0.0, 0.0};
     int s = 0, parity = 0;
     for (int i = 0; i < mine; ++i) {
         ptx::mbar_wait(bars + s, parity);
         const BlockDesc d = descs[s];
         wait_for_halo<HALO>(a, first + i * step);
         if ((d.e1 - d.e0) <= a.nnz_cap)
-            compute_staged<MODE, L, HALO>(a, d, stages + (size_t)s * lay.bytes, lay);
+            compute_staged<MODE, L, HALO>(a, d, stages + (size_t)s * lay.bytes, lay, acc);
         else
-            compute_long<MODE, HALO>(a, d, red_s);
+            compute_long<MODE, HALO>(a, d, red_s, acc);
         __syncthreads();                 // every thread is done with stage s (and descs[s])
         if (threadIdx.x == 0 && i + nstages < mine) {
             const BlockDesc n = load_desc(a, first + (i + nstages) * step);
@@ -404,6 +428,10 @@ __global__ void __launch_bounds__(kThreads, 2) csr_ring_kernel(const CsrArgsT<P>
             issue_block(a, n, stages + (size_t)s * lay.bytes, lay, bars + s, policy);
         }
         if (++s == nstages) { s = 0; parity ^= 1; }
+    }
+    if (a.ndot) {
+        double v[2] = {acc.s0, acc.s1};
+        red_finish<2>(a.red, v);
     }
 }
 

@@ -4,6 +4,7 @@
 #pragma once
 #include "common.cuh"
 #include "dist.cuh"
+#include "reduce.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -82,6 +83,12 @@ inline int rd(b200_vec_t v, const double **p) {
 // pointer for a full overwrite
 inline double *wr(b200_vec_t v) {
     v->zero_pending = false;
+    v->gen++;
+    return v->ptr;
+}
+// pointer for an in-place update (the caller has materialised a pending clear)
+inline double *mut(b200_vec_t v) {
+    v->gen++;
     return v->ptr;
 }
 // typed views (FP32 vectors keep their floats behind the same pointer)
@@ -107,7 +114,9 @@ struct GraphSlot {
     bool    *zp;        // &vec->zero_pending (nullptr for operator scratch)
     double  *p0; bool z0;   // on entry
     double  *p1; bool z1;   // on exit
+    uint64_t *gen;      // &vec->gen (nullptr for operator scratch): bumped by every replay
 };
+struct GraphProduct { b200_vec_t a, b; int slot; };   // product a replay leaves in the scalar table
 } // namespace b200
 
 struct b200_graph_s {
@@ -115,6 +124,7 @@ struct b200_graph_s {
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
     std::vector<b200::GraphSlot> slots;
+    std::vector<b200::GraphProduct> products;
     uint64_t destroy_epoch = 0, option_epoch = 0;
     uint64_t launches0 = 0;     // ctx->launches when recording started
     uint64_t launches = 0;      // kernels in the graph
@@ -124,16 +134,16 @@ struct b200_graph_s {
 
 namespace b200 {
 
-inline void touch_slot(b200_ctx_t ctx, double **slot, bool *zp) {
+inline void touch_slot(b200_ctx_t ctx, double **slot, bool *zp, uint64_t *gen = nullptr) {
     b200_graph_s *g = ctx->recording;
     for (const GraphSlot &s : g->slots)
         if (s.slot == slot) return;
-    g->slots.push_back({slot, zp, *slot, zp ? *zp : false, nullptr, false});
+    g->slots.push_back({slot, zp, *slot, zp ? *zp : false, nullptr, false, gen});
 }
 inline void touch(b200_ctx_t ctx, std::initializer_list<b200_vec_t> vs) {
     if (!ctx->recording) return;
     for (b200_vec_t v : vs) {
-        touch_slot(ctx, &v->ptr, &v->zero_pending);
+        touch_slot(ctx, &v->ptr, &v->zero_pending, &v->gen);
         v->in_graph = true;
     }
 }
@@ -177,6 +187,30 @@ inline cudaError_t launch_pdl(b200_ctx_t ctx, void (*kernel)(KArgs...), dim3 gri
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
+
+// ---- implemented in api_krylov.cu: the device scalar table and in-kernel reductions ----------
+int  scal_create(b200_ctx_t ctx);                  // allocate the table (context creation)
+void scal_destroy(b200_ctx_t ctx);
+int  scal_alloc(b200_ctx_t ctx, int count);        // first of `count` consecutive free slots, -1 if none
+void scal_free(b200_ctx_t ctx, int first, int count);
+// RedOut for one launch that leaves `nred` scalars in the given table slots
+// (across_ranks: the operands are partitioned, every rank launches the same kernel and the
+// finishing CTAs all-reduce over the peers)
+void red_out(b200_ctx_t ctx, int nred, const int *slots, RedOut &o, bool across_ranks);
+// products left behind by producer kernels (see b200_ctx_s::Product)
+bool product_wanted(b200_ctx_t ctx, size_t n);
+int  product_take_slot(b200_ctx_t ctx);
+void product_record(b200_ctx_t ctx, b200_vec_t a, b200_vec_t b, int slot);
+int  product_lookup(b200_ctx_t ctx, b200_vec_t a, b200_vec_t b);   // slot or -1
+// one standalone reduction launch: <x,y> (and <x,z> when z != nullptr) into table slots
+int  launch_dot_slots(b200_ctx_t ctx, b200_vec_t x, b200_vec_t y, b200_vec_t z, const int *slots);
+// (api_vectors.cu) stand-alone dot kernel: FP32 vectors, NCCL transport
+int  dot_legacy(b200_ctx_t ctx, b200_vec_t x, b200_vec_t y, double *result);
+
+// ---- implemented in api_matrices.cu: streaming passes that also leave scalars behind ----------
+int  spmv_with_dots(b200_ctx_t ctx, b200_csr_t A, b200_vec_t x, b200_vec_t y, b200_vec_t w, int ndot,
+                    const int *slots);
+int  residual_with_norm(b200_ctx_t ctx, b200_vec_t f, b200_csr_t A, b200_vec_t x, b200_vec_t r, int slot);
 
 // ---- implemented in api_exchange.cu (multi-GPU) ----------------------------------------------
 int  peer_alloc(b200_ctx_t ctx, size_t bytes, void **local, void **peers);

@@ -340,7 +340,8 @@ def main_arm(args, rank, world, local_rank):
             except Exception:
                 pass
     all_csr_ms = sum(p["total_ms"] for p in prof if p["nnz"] > 0 and p["mode"] != "coarse_gemv")
-    streams = {"vec1": 2, "vec2": 3, "vec3": 4, "dot": 2, "relax_zero": 3, "memset": 1, "comm": 1}
+    streams = {"vec1": 2, "vec2": 3, "vec3": 4, "vec4": 5, "vec5": 6, "vec6": 7, "vec7": 8,
+               "dot": 2, "relax_zero": 3, "memset": 1, "comm": 1, "coarse_tail": 1}
     breakdown = []
     for p in sorted(prof, key=lambda q: -q["total_ms"]):
         if p["mode"] in streams:

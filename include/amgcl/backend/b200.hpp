@@ -29,7 +29,10 @@
  * customisation points of amgcl/backend/interface.hpp:191-249.  In addition
  * relaxation::damped_jacobi and relaxation::spai0 are specialised for this
  * backend so a smoother sweep is ONE fused pass over A instead of
- * residual + vmul (damped_jacobi.hpp:108-109, spai0.hpp:91-92).
+ * residual + vmul (damped_jacobi.hpp:108-109, spai0.hpp:91-92), and solver::cg /
+ * solver::bicgstab are specialised so an iteration's vector updates and inner
+ * products are fused passes with device-resident scalars (cg.hpp:180-198,
+ * bicgstab.hpp:198-236; C ABI section "Krylov steps").
  */
 
 #include <iostream>
@@ -43,6 +46,8 @@
 #include <amgcl/backend/interface.hpp>
 #include <amgcl/relaxation/damped_jacobi.hpp>
 #include <amgcl/relaxation/spai0.hpp>
+#include <amgcl/solver/cg.hpp>
+#include <amgcl/solver/bicgstab.hpp>
 
 #include <amgcl_b200.h>
 
@@ -627,6 +632,295 @@ struct spai0< backend::b200<real, C, P, DS> > {
 };
 
 } // namespace relaxation
+
+//---------------------------------------------------------------------------
+// Krylov solvers: same public API as the primary templates, fused iteration body.
+//---------------------------------------------------------------------------
+namespace backend {
+
+/// The same backend under a distinct type: selects the PRIMARY templates of solver::cg /
+/// solver::bicgstab (the reference's call sequence on the b200 primitives).  The
+/// specialisations below delegate to it for everything they do not fuse (left
+/// preconditioning, a user-supplied system matrix of another type, option "fused_krylov" = 0).
+template <typename real, typename C = ptrdiff_t, typename P = C,
+          class DS = solver::b200_dense_inverse<real> >
+struct b200_generic : b200<real, C, P, DS> {};
+
+} // namespace backend
+
+namespace solver {
+
+namespace detail {
+/// Owns the C-ABI workspace (device-resident scalars of one solver instance).
+struct b200_krylov_handle {
+    b200_ctx_t ctx;
+    b200_krylov_t K;
+    b200_krylov_handle(const backend::b200_params &bprm, size_t n) : ctx(bprm.context()), K(0) {
+        int64_t fused = 1;
+        b200_ctx_get_option(ctx, "fused_krylov", &fused);
+        if (fused && b200_krylov_create(ctx, n, &K) != B200_OK) K = 0;   // -> generic path
+    }
+    ~b200_krylov_handle() { if (K) b200_krylov_destroy(K); }
+    b200_krylov_handle(const b200_krylov_handle&) = delete;
+    b200_krylov_handle& operator=(const b200_krylov_handle&) = delete;
+    /// Fused steps are used unless the option was switched off after construction.
+    bool active() const {
+        if (!K) return false;
+        int64_t fused = 1;
+        b200_ctx_get_option(ctx, "fused_krylov", &fused);
+        return fused != 0;
+    }
+};
+// logical layout of b200_krylov_scalars()
+enum { b200_k_rho = 0, b200_k_qp = 1, b200_k_alpha = 2, b200_k_ts = 3, b200_k_tt = 4,
+       b200_k_omega = 5, b200_k_rr = 6, b200_k_ss = 7, b200_k_rho_next = 8, b200_k_count = 9 };
+} // namespace detail
+
+/// Conjugate Gradient on the b200 backend (primary: solver/cg.hpp:62-263).
+/**
+ * Same parameters, same results (iteration count, residual) as the primary template; per
+ * iteration it issues P.apply + two C-ABI steps (b200_cg_direction, b200_cg_step) and one
+ * host synchronisation instead of 7 primitives and 3 synchronisations.
+ */
+template <typename C, typename P, class DS>
+class cg< backend::b200<double, C, P, DS>, detail::default_inner_product > {
+    public:
+        typedef backend::b200<double, C, P, DS> Backend;
+        typedef Backend backend_type;
+        typedef typename Backend::vector     vector;
+        typedef typename Backend::value_type value_type;
+        typedef typename Backend::params     backend_params;
+        typedef double scalar_type;
+        typedef double coef_type;
+
+        typedef cg< backend::b200_generic<double, C, P, DS>, detail::default_inner_product > generic_solver;
+        /// Solver parameters: the primary template's (cg.hpp:80-124).
+        typedef typename generic_solver::params params;
+
+        cg(size_t n, const params &prm = params(),
+           const backend_params &bprm = backend_params(),
+           const detail::default_inner_product& = detail::default_inner_product())
+            : prm(prm), n(n), bprm(bprm), kh(bprm, n),
+              r(Backend::create_vector(n, bprm)), s(Backend::create_vector(n, bprm)),
+              p(Backend::create_vector(n, bprm)), q(Backend::create_vector(n, bprm))
+        { }
+
+        /// Fused path: the system matrix and the vectors live on this backend.
+        template <class VM, class Precond>
+        std::tuple<size_t, scalar_type> operator()(
+                const backend::b200_matrix<VM> &A, const Precond &Prec,
+                const backend::b200_vector<double> &rhs, backend::b200_vector<double> &x) const
+        {
+            if (!kh.active()) return fallback()(A, Prec, rhs, x);
+
+            ios_saver ss(std::cout);
+
+            scalar_type norm_rhs = sqrt(fabs(backend::inner_product(rhs, rhs)));
+            if (norm_rhs < amgcl::detail::eps<scalar_type>(1)) {
+                if (prm.ns_search) {
+                    norm_rhs = math::identity<scalar_type>();
+                } else {
+                    backend::clear(x);
+                    return std::make_tuple(size_t(0), norm_rhs);
+                }
+            }
+            scalar_type eps = std::max(prm.tol * norm_rhs, prm.abstol);
+
+            double rr = 0;
+            AMGCL_CALL_B200(b200_krylov_residual(kh.K, rhs.handle(), A.handle(), x.handle(), r->handle(), &rr));
+            scalar_type res_norm = sqrt(fabs(rr));
+
+            size_t iter = 0;
+            for(; iter < prm.maxiter && res_norm > eps; ++iter) {
+                Prec.apply(*r, *s);
+                // rho = <r,s> (left behind by the last smoother sweep); p = s + (rho/rho_prev) p
+                AMGCL_CALL_B200(b200_cg_direction(kh.K, r->handle(), s->handle(), p->handle()));
+                // q = A p; alpha = rho/<q,p>; x += alpha p; r -= alpha q; <r,r>
+                AMGCL_CALL_B200(b200_cg_step(kh.K, A.handle(), p->handle(), q->handle(),
+                            x.handle(), r->handle(), &rr));
+                res_norm = sqrt(fabs(rr));
+                if (prm.verbose && iter % 5 == 0)
+                    std::cout << iter << "\t" << std::scientific << res_norm / norm_rhs << std::endl;
+            }
+            return std::make_tuple(iter, res_norm / norm_rhs);
+        }
+
+        /// Anything else (foreign matrix / vector types): the reference's sequence.
+        template <class Matrix, class Precond, class Vec1, class Vec2>
+        std::tuple<size_t, scalar_type> operator()(
+                const Matrix &A, const Precond &Prec, const Vec1 &rhs, Vec2 &&x) const
+        {
+            return fallback()(A, Prec, rhs, x);
+        }
+
+        template <class Precond, class Vec1, class Vec2>
+        std::tuple<size_t, scalar_type> operator()(const Precond &Prec, const Vec1 &rhs, Vec2 &&x) const {
+            return (*this)(Prec.system_matrix(), Prec, rhs, x);
+        }
+
+        size_t bytes() const {
+            return backend::bytes(*r) + backend::bytes(*s) + backend::bytes(*p) + backend::bytes(*q)
+                + (generic ? generic->bytes() : 0);
+        }
+
+        friend std::ostream& operator<<(std::ostream &os, const cg &s) {
+            return os
+                << "Type:             CG"
+                << "\nUnknowns:         " << s.n
+                << "\nMemory footprint: " << human_readable_memory(s.bytes())
+                << std::endl;
+        }
+
+    public:
+        params prm;
+
+    private:
+        size_t n;
+        backend_params bprm;
+        detail::b200_krylov_handle kh;
+        std::shared_ptr<vector> r, s, p, q;
+        mutable std::unique_ptr<generic_solver> generic;
+
+        generic_solver& fallback() const {
+            if (!generic) generic.reset(new generic_solver(n, prm, bprm));
+            generic->prm = prm;
+            return *generic;
+        }
+};
+
+/// BiCGStab on the b200 backend (primary: solver/bicgstab.hpp:52-316).
+/**
+ * Right preconditioning (the default) runs as P.apply + b200_bicg_direction / _step_s /
+ * _step_r with two host synchronisations per iteration (its two convergence tests) instead
+ * of six; left preconditioning delegates to the primary template.
+ */
+template <typename C, typename P, class DS>
+class bicgstab< backend::b200<double, C, P, DS>, detail::default_inner_product > {
+    public:
+        typedef backend::b200<double, C, P, DS> Backend;
+        typedef Backend backend_type;
+        typedef typename Backend::vector     vector;
+        typedef typename Backend::value_type value_type;
+        typedef typename Backend::params     backend_params;
+        typedef double scalar_type;
+        typedef double coef_type;
+
+        typedef bicgstab< backend::b200_generic<double, C, P, DS>, detail::default_inner_product > generic_solver;
+        /// Solver parameters: the primary template's (bicgstab.hpp:72-124).
+        typedef typename generic_solver::params params;
+
+        bicgstab(size_t n, const params &prm = params(),
+                 const backend_params &bprm = backend_params(),
+                 const detail::default_inner_product& = detail::default_inner_product())
+            : prm(prm), n(n), bprm(bprm), kh(bprm, n),
+              r (Backend::create_vector(n, bprm)), p (Backend::create_vector(n, bprm)),
+              v (Backend::create_vector(n, bprm)), s (Backend::create_vector(n, bprm)),
+              t (Backend::create_vector(n, bprm)), rh(Backend::create_vector(n, bprm)),
+              T (Backend::create_vector(n, bprm))
+        { }
+
+        template <class VM, class Precond>
+        std::tuple<size_t, scalar_type> operator()(
+                const backend::b200_matrix<VM> &A, const Precond &Prec,
+                const backend::b200_vector<double> &rhs, backend::b200_vector<double> &x) const
+        {
+            namespace side = preconditioner::side;
+            if (!kh.active() || prm.pside != side::right) return fallback()(A, Prec, rhs, x);
+
+            ios_saver ss(std::cout);
+
+            scalar_type norm_rhs = sqrt(fabs(backend::inner_product(rhs, rhs)));
+            if (norm_rhs < amgcl::detail::eps<scalar_type>(1)) {
+                if (prm.ns_search) {
+                    norm_rhs = math::identity<scalar_type>();
+                } else {
+                    backend::clear(x);
+                    return std::make_tuple(size_t(0), norm_rhs);
+                }
+            }
+
+            double rr = 0, ssq = 0, sc[detail::b200_k_count];
+            AMGCL_CALL_B200(b200_krylov_residual(kh.K, rhs.handle(), A.handle(), x.handle(), r->handle(), &rr));
+            AMGCL_CALL_B200(b200_bicg_start(kh.K, r->handle(), rh->handle()));
+
+            scalar_type eps = std::max(norm_rhs * prm.tol, prm.abstol);
+            scalar_type res = prm.check_after ? 2 * eps : sqrt(fabs(rr));
+
+            coef_type rho_prev = 0;
+            size_t iter = 0;
+            for(bool first = true; res > eps && iter < prm.maxiter; ++iter) {
+                if (first) first = false;
+                else precondition(!math::is_zero(rho_prev), "Zero rho in BiCGStab");
+
+                // p = r + beta (p - omega v); p = r on the first iteration
+                AMGCL_CALL_B200(b200_bicg_direction(kh.K, r->handle(), v->handle(), p->handle()));
+                Prec.apply(*p, *T);
+                // v = A T; alpha = rho/<rh,v>; x += alpha T; s = r - alpha v; <s,s>
+                AMGCL_CALL_B200(b200_bicg_step_s(kh.K, A.handle(), rh->handle(), T->handle(), v->handle(),
+                            r->handle(), s->handle(), x.handle(), &ssq));
+                AMGCL_CALL_B200(b200_krylov_scalars(kh.K, sc, detail::b200_k_count));
+                rho_prev = sc[detail::b200_k_rho];
+
+                if ((res = sqrt(fabs(ssq))) > eps) {
+                    Prec.apply(*s, *T);
+                    // t = A T; omega = <t,s>/<t,t>; x += omega T; r = s - omega t; <r,r>; next rho
+                    AMGCL_CALL_B200(b200_bicg_step_r(kh.K, A.handle(), rh->handle(), T->handle(), t->handle(),
+                                s->handle(), r->handle(), x.handle(), &rr));
+                    AMGCL_CALL_B200(b200_krylov_scalars(kh.K, sc, detail::b200_k_count));
+                    precondition(!math::is_zero(sc[detail::b200_k_omega]), "Zero omega in BiCGStab");
+                    res = sqrt(fabs(rr));
+                }
+
+                if (prm.verbose && iter % 5 == 0)
+                    std::cout << iter << "\t" << std::scientific << res / norm_rhs << std::endl;
+            }
+            return std::make_tuple(iter, res / norm_rhs);
+        }
+
+        template <class Matrix, class Precond, class Vec1, class Vec2>
+        std::tuple<size_t, scalar_type> operator()(
+                const Matrix &A, const Precond &Prec, const Vec1 &rhs, Vec2 &&x) const
+        {
+            return fallback()(A, Prec, rhs, x);
+        }
+
+        template <class Precond, class Vec1, class Vec2>
+        std::tuple<size_t, scalar_type> operator()(const Precond &Prec, const Vec1 &rhs, Vec2 &&x) const {
+            return (*this)(Prec.system_matrix(), Prec, rhs, x);
+        }
+
+        size_t bytes() const {
+            return backend::bytes(*r) + backend::bytes(*p) + backend::bytes(*v) + backend::bytes(*s)
+                + backend::bytes(*t) + backend::bytes(*rh) + backend::bytes(*T)
+                + (generic ? generic->bytes() : 0);
+        }
+
+        friend std::ostream& operator<<(std::ostream &os, const bicgstab &s) {
+            return os
+                << "Type:             BiCGStab"
+                << "\nUnknowns:         " << s.n
+                << "\nMemory footprint: " << human_readable_memory(s.bytes())
+                << std::endl;
+        }
+
+    public:
+        params prm;
+
+    private:
+        size_t n;
+        backend_params bprm;
+        detail::b200_krylov_handle kh;
+        std::shared_ptr<vector> r, p, v, s, t, rh, T;
+        mutable std::unique_ptr<generic_solver> generic;
+
+        generic_solver& fallback() const {
+            if (!generic) generic.reset(new generic_solver(n, prm, bprm));
+            generic->prm = prm;
+            return *generic;
+        }
+};
+
+} // namespace solver
 
 //---------------------------------------------------------------------------
 // Whole-cycle CUDA graph (opt-in wrapper)

@@ -52,6 +52,7 @@ typedef struct b200_coarse_s *b200_coarse_t;  /* coarsest-level direct solver   
 typedef struct b200_split_s  *b200_split_t;   /* host view of one rank's operator share */
 typedef struct b200_graph_s  *b200_graph_t;   /* recorded call sequence (CUDA graph)    */
 typedef struct b200_index_s  *b200_index_t;   /* device index list (gather / scatter)   */
+typedef struct b200_krylov_s *b200_krylov_t;  /* device-resident scalars of a Krylov solver */
 
 /* ---------------------------------------------------------------- context */
 
@@ -162,6 +163,9 @@ int b200_split_destroy(b200_split_t sp);
  *                      reports "not recording" and existing graphs are not replayed
  *   "graph_pdl"        1 = launches recorded into a graph keep the PDL attribute (default;
  *                      env B200_GRAPH_PDL)
+ *   "fused_krylov"     1 = the C++ binding's solver::cg / solver::bicgstab specialisations run the
+ *                      fused b200_cg_* / b200_bicg_* steps (default; env B200_FUSED_KRYLOV),
+ *                      0 = they issue the reference's sequence of primitives
  *   "fuse_relax"       1 = single-pass fused smoother sweep (default), 0 = two kernels
  *   "zero_shortcut"    1 = skip the A-pass when x is known to be zero (default)
  * Unknown keys return B200_EINVAL. */
@@ -289,6 +293,63 @@ int b200_scatter(b200_ctx_t ctx, b200_index_t I, b200_vec_t src, b200_vec_t dst)
  * which is what the reference computes in that case (residual == rhs exactly). */
 int b200_relax(b200_ctx_t ctx, b200_csr_t A, b200_vec_t rhs, b200_vec_t x,
                b200_vec_t tmp, b200_vec_t diag, double omega);
+
+/* ---------------------------------------------------------------- Krylov steps */
+
+/* The vector half of a Krylov iteration as fused passes with device-resident scalars.
+ *
+ * The reference's solvers issue every vector update and inner product as a separate backend
+ * call and carry the scalars through the host: solver/cg.hpp:180-198 is
+ *   P.apply(r,s); rho = <r,s>; p = s + (rho/rho_prev) p; q = A p; alpha = rho/<q,p>;
+ *   x += alpha p; r -= alpha q; <r,r>
+ * = 7 calls and 3 host synchronisations per iteration (bicgstab.hpp:198-236: 6).  The steps
+ * below are what the specialisations of amgcl::solver::cg / bicgstab for backend::b200
+ * (include/amgcl/backend/b200.hpp) call instead: each reads its operands once, forms its
+ * coefficient (a quotient of inner products) on the device from a per-context scalar table,
+ * and leaves the inner products of what it just wrote in that table for the next step.  The
+ * products <q,p>, <rh,v>, <t,s>, <t,t> are reduced inside the SpMV kernel that produces q / v /
+ * t; <r,s> is left behind by the fused smoother sweep that ends the V-cycle (b200_relax does
+ * that whenever a workspace of the operator's size exists).  On a multi-GPU context the
+ * kernel that finishes a reduction also all-reduces it over the ranks through peer memory
+ * (replaces mpi/inner_product.hpp:53-62).  The host synchronises only where the algorithm
+ * tests convergence: once per CG iteration, twice per BiCGStab iteration.
+ *
+ * All vectors are FP64 vectors of the workspace's size n; A is an FP64 or FP32 operator.
+ * Functions with a `double *` result are host-synchronous. */
+int b200_krylov_create(b200_ctx_t ctx, size_t n, b200_krylov_t *K);
+int b200_krylov_destroy(b200_krylov_t K);
+/* r = rhs - A x and *rr = <r,r> in one pass; starts a new solve (cg.hpp:176-177,
+ * bicgstab.hpp:180).  If x is known to be zero the pass over A is skipped (r = rhs). */
+int b200_krylov_residual(b200_krylov_t K, b200_vec_t rhs, b200_csr_t A, b200_vec_t x,
+                         b200_vec_t r, double *rr);
+/* The workspace's scalars as the device formed them (synchronises the stream), out[0..count),
+ * count <= 9: rho of the current iteration, <q,p> | <rh,v>, alpha, <t,s>, <t,t>, omega, <r,r>,
+ * <s,s>, rho of the next iteration.  For the breakdown checks of bicgstab.hpp:206,228. */
+int b200_krylov_scalars(b200_krylov_t K, double *out, int count);
+
+/* CG.  b200_cg_direction: rho = <r,s> (taken from the smoother's epilogue when available),
+ * p = s + (rho/rho_prev) p, p = s on the first call of a solve (cg.hpp:183-189).
+ * b200_cg_step: q = A p; alpha = rho/<q,p>; x += alpha p; r -= alpha q; *rr = <r,r>
+ * (cg.hpp:191-198). */
+int b200_cg_direction(b200_krylov_t K, b200_vec_t r, b200_vec_t s, b200_vec_t p);
+int b200_cg_step(b200_krylov_t K, b200_csr_t A, b200_vec_t p, b200_vec_t q, b200_vec_t x,
+                 b200_vec_t r, double *rr);
+
+/* BiCGStab with right preconditioning (bicgstab.hpp:176-236; T = M^-1 p resp. M^-1 s is
+ * applied by the caller between the steps).
+ *   b200_bicg_start      rh = r; rho = <r,rh>                                   :183,200
+ *   b200_bicg_direction  p = r + beta (p - omega v), beta = (rho alpha)/(rho_prev omega);
+ *                        p = r on the first call of a solve                      :202-208
+ *   b200_bicg_step_s     v = A T; alpha = rho/<rh,v>; x += alpha T; s = r - alpha v;
+ *                        *ss = <s,s>                                            :210-222
+ *   b200_bicg_step_r     t = A T; omega = <t,s>/<t,t>; x += omega T; r = s - omega t;
+ *                        *rr = <r,r>; next rho = <r,rh>                         :223-236,200 */
+int b200_bicg_start(b200_krylov_t K, b200_vec_t r, b200_vec_t rh);
+int b200_bicg_direction(b200_krylov_t K, b200_vec_t r, b200_vec_t v, b200_vec_t p);
+int b200_bicg_step_s(b200_krylov_t K, b200_csr_t A, b200_vec_t rh, b200_vec_t T, b200_vec_t v,
+                     b200_vec_t r, b200_vec_t s, b200_vec_t x, double *ss);
+int b200_bicg_step_r(b200_krylov_t K, b200_csr_t A, b200_vec_t rh, b200_vec_t T, b200_vec_t t,
+                     b200_vec_t s, b200_vec_t r, b200_vec_t x, double *rr);
 
 /* ---------------------------------------------------------------- coarse solve */
 
