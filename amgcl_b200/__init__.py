@@ -86,6 +86,8 @@ def lib():
         "b200_vec_data": [_vp, _P(_vp)],
         "b200_vec_upload": [_vp, _vp, _c.c_size_t],
         "b200_vec_download": [_vp, _vp, _c.c_size_t],
+        "b200_vec_download_local": [_vp, _vp, _c.c_size_t],
+        "b200_vec_local_range": [_vp, _P(_c.c_size_t), _P(_c.c_size_t)],
         # FP32 objects of the mixed-precision composition (b200<float> hierarchy)
         "b200_vec_create_f32": [_vp, _c.c_size_t, _P(_vp)],
         "b200_vec_upload_f32": [_vp, _vp, _c.c_size_t],
@@ -149,8 +151,8 @@ def lib():
         "b200_cg_step": [_vp, _vp, _vp, _vp, _vp, _vp, _P(_dbl)],
         "b200_bicg_start": [_vp, _vp, _vp],
         "b200_bicg_direction": [_vp, _vp, _vp, _vp],
-        "b200_bicg_step_s": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _P(_dbl)],
-        "b200_bicg_step_r": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _P(_dbl)],
+        "b200_bicg_step_s": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _P(_dbl), _P(_dbl)],
+        "b200_bicg_step_r": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _P(_dbl), _P(_dbl)],
         "b200_profile_begin": [_vp],
         "b200_profile_end": [_vp, _vp, _i64, _P(_i64)],
     }
@@ -414,13 +416,13 @@ class Krylov:
 
     def bicg_step_s(self, A, rh, T, v, r, s, x):
         out = _dbl()
-        _check(lib().b200_bicg_step_s(self.h, A.h, rh.h, T.h, v.h, r.h, s.h, x.h, _c.byref(out)),
+        _check(lib().b200_bicg_step_s(self.h, A.h, rh.h, T.h, v.h, r.h, s.h, x.h, _c.byref(out), None),
                "b200_bicg_step_s")
         return out.value
 
     def bicg_step_r(self, A, rh, T, t, s, r, x):
         out = _dbl()
-        _check(lib().b200_bicg_step_r(self.h, A.h, rh.h, T.h, t.h, s.h, r.h, x.h, _c.byref(out)),
+        _check(lib().b200_bicg_step_r(self.h, A.h, rh.h, T.h, t.h, s.h, r.h, x.h, _c.byref(out), None),
                "b200_bicg_step_r")
         return out.value
 

@@ -83,7 +83,7 @@ void scal_free(b200_ctx_t ctx, int first, int count) {
     for (int i = 0; i < count; ++i) ctx->scal_used[first + i] = false;
 }
 
-void red_out(b200_ctx_t ctx, int nred, const int *slots, RedOut &o, bool across_ranks) {
+void red_out(b200_ctx_t ctx, int nred, const int *slots, RedOut &o, bool across_ranks, unsigned host_mask) {
     memset(&o, 0, sizeof(o));
     o.partial = ctx->red_partial;
     o.ticket = ctx->red_ticket;
@@ -93,7 +93,7 @@ void red_out(b200_ctx_t ctx, int nred, const int *slots, RedOut &o, bool across_
     o.peers = ctx->scal_x_table;
     for (int k = 0; k < nred; ++k) {
         o.dev[k] = ctx->scal_d + slots[k];
-        o.host[k] = ctx->scal_hd + slots[k];
+        o.host[k] = (host_mask >> k) & 1u ? ctx->scal_hd + slots[k] : nullptr;
         o.slot[k] = slots[k];
         o.seq[k] = ++ctx->scal_seq[slots[k]];
     }
@@ -133,10 +133,10 @@ int product_lookup(b200_ctx_t ctx, b200_vec_t a, b200_vec_t b) {
 // ---- launch helper for the fused vector passes ---------------------------------------------------
 template <class F, int UNR>
 static int launch_fused(b200_ctx_t ctx, size_t len, const F &f, const FusedArgs<F::NIN, F::NOUT> &a,
-                        const int *slots, int prof_streams, bool across_ranks) {
+                        const int *slots, int prof_streams, bool across_ranks, unsigned host_mask = 0) {
     RedOut ro;
     memset(&ro, 0, sizeof(ro));
-    if (F::NRED > 0) red_out(ctx, F::NRED, slots, ro, across_ranks);
+    if (F::NRED > 0) red_out(ctx, F::NRED, slots, ro, across_ranks, host_mask);
     bool vec_ok = true;
     for (int k = 0; k < F::NIN; ++k) vec_ok = vec_ok && aligned16(a.in[k]);
     for (int k = 0; k < F::NOUT; ++k) vec_ok = vec_ok && aligned16(a.out[k]);
@@ -151,7 +151,8 @@ static int launch_fused(b200_ctx_t ctx, size_t len, const F &f, const FusedArgs<
 
 // <x,y> (and <x,z>) of FP64 vectors into table slots; one launch, the all-reduce over the
 // ranks of a partitioned vector happens inside it
-int launch_dot_slots(b200_ctx_t ctx, b200_vec_t x, b200_vec_t y, b200_vec_t z, const int *slots) {
+int launch_dot_slots(b200_ctx_t ctx, b200_vec_t x, b200_vec_t y, b200_vec_t z, const int *slots,
+                     unsigned host_mask) {
     B200_REQUIRE(x->dtype == B200_F64 && y->dtype == B200_F64 && (!z || z->dtype == B200_F64),
                  "in-kernel reductions need FP64 vectors");
     const double *px, *py, *pz = nullptr;
@@ -164,16 +165,16 @@ int launch_dot_slots(b200_ctx_t ctx, b200_vec_t x, b200_vec_t y, b200_vec_t z, c
         if (rc) return rc;
         FusedArgs<3, 0> a;
         a.in[0] = px; a.in[1] = py; a.in[2] = pz; a.out[0] = nullptr;
-        return launch_fused<Dot2F, 2>(ctx, x->len, Dot2F(), a, slots, 0, x->kind == B200_VK_DIST);
+        return launch_fused<Dot2F, 2>(ctx, x->len, Dot2F(), a, slots, 0, x->kind == B200_VK_DIST, host_mask);
     }
     if (px == py) {
         FusedArgs<1, 0> a;
         a.in[0] = px; a.out[0] = nullptr;
-        return launch_fused<NormF, 4>(ctx, x->len, NormF(), a, slots, 0, x->kind == B200_VK_DIST);
+        return launch_fused<NormF, 4>(ctx, x->len, NormF(), a, slots, 0, x->kind == B200_VK_DIST, host_mask);
     }
     FusedArgs<2, 0> a;
     a.in[0] = px; a.in[1] = py; a.out[0] = nullptr;
-    return launch_fused<DotF, 4>(ctx, x->len, DotF(), a, slots, 0, x->kind == B200_VK_DIST);
+    return launch_fused<DotF, 4>(ctx, x->len, DotF(), a, slots, 0, x->kind == B200_VK_DIST, host_mask);
 }
 
 static SaveSlot save_slot(b200_ctx_t ctx, int slot) {
@@ -183,11 +184,15 @@ static SaveSlot save_slot(b200_ctx_t ctx, int slot) {
     return s;
 }
 
-static int sync_read(b200_ctx_t ctx, int slot, double *out) {
+int scal_read(b200_ctx_t ctx, int slot, bool mirrored, double *out) {
+    if (!mirrored)
+        B200_CUDA(cudaMemcpyAsync(ctx->scal_h + slot, ctx->scal_d + slot, sizeof(double),
+                                  cudaMemcpyDeviceToHost, ctx->stream));
     B200_CUDA(cudaStreamSynchronize(ctx->stream));
     *out = *reinterpret_cast<volatile double *>(ctx->scal_h + slot);
     return B200_OK;
 }
+static int sync_read(b200_ctx_t ctx, int slot, double *out) { return scal_read(ctx, slot, true, out); }
 
 } // namespace b200
 
@@ -215,9 +220,9 @@ extern "C" int b200_dot(b200_ctx_t ctx, b200_vec_t x, b200_vec_t y, double *resu
     if (x->dtype == B200_F32 || (dist && !ctx->scal_x_table)) return dot_legacy(ctx, x, y, result);
     // a producer kernel may already have left this very product in the table
     const int have = product_lookup(ctx, x, y);
-    if (have >= 0) return sync_read(ctx, have, result);
+    if (have >= 0) return scal_read(ctx, have, false, result);
     const int slot = SLOT_DOT;
-    int rc = launch_dot_slots(ctx, x, y, nullptr, &slot);
+    int rc = launch_dot_slots(ctx, x, y, nullptr, &slot, 1u);
     if (rc) return rc;
     return sync_read(ctx, slot, result);
 }
@@ -276,12 +281,15 @@ extern "C" int b200_krylov_scalars(b200_krylov_t K, double *out, int count) {
     CHECK_K(K);
     B200_REQUIRE(out != nullptr && count >= 0 && count <= 9, "bad argument");
     GUARD(ctx);
+    // (not every scalar is mirrored to the host by the kernel that forms it: copy the
+    // workspace's part of the table)
+    double tab[K_NSLOTS];
+    B200_CUDA(cudaMemcpyAsync(tab, ctx->scal_d + K->base, sizeof(tab), cudaMemcpyDeviceToHost, ctx->stream));
     B200_CUDA(cudaStreamSynchronize(ctx->stream));
     // logical layout: rho (this iteration's), <q,p> | <rh,v>, alpha, <t,s>, <t,t>, omega, <r,r>,
     // <s,s>, next rho
     const int rel[9] = {K_RHOP0 + K->parity, K_QP, K_ALPHA, K_TS, K_TT, K_OMEGA, K_RR, K_SS, K_RHO_NEXT};
-    for (int i = 0; i < count; ++i)
-        out[i] = *reinterpret_cast<volatile double *>(ctx->scal_h + K->base + rel[i]);
+    for (int i = 0; i < count; ++i) out[i] = tab[rel[i]];
     return B200_OK;
 }
 
@@ -304,7 +312,7 @@ extern "C" int b200_krylov_residual(b200_krylov_t K, b200_vec_t rhs, b200_csr_t 
         if (rc) return rc;
         FusedArgs<1, 1> a;
         a.in[0] = pf; a.out[0] = wr(r);
-        rc = launch_fused<CopyNormF, 2>(ctx, r->len, CopyNormF(), a, &slot, 3, r->kind == B200_VK_DIST);
+        rc = launch_fused<CopyNormF, 2>(ctx, r->len, CopyNormF(), a, &slot, 3, r->kind == B200_VK_DIST, 1u);
     } else {
         rc = residual_with_norm(ctx, rhs, A, x, r, slot);
     }
@@ -325,7 +333,7 @@ extern "C" int b200_cg_direction(b200_krylov_t K, b200_vec_t r, b200_vec_t s, b2
     int rho = product_lookup(ctx, r, s);
     if (rho < 0) {
         rho = K->base + K_RHO;
-        int rc = launch_dot_slots(ctx, r, s, nullptr, &rho);
+        int rc = launch_dot_slots(ctx, r, s, nullptr, &rho, 0u);
         if (rc) return rc;
     }
     K->rho_slot = rho;
@@ -376,7 +384,7 @@ extern "C" int b200_cg_step(b200_krylov_t K, b200_csr_t A, b200_vec_t p, b200_ve
     a.in[0] = pp; a.in[1] = pq; a.in[2] = px; a.in[3] = pr;
     a.out[0] = mut(x); a.out[1] = mut(r);
     const int slot = K->base + K_RR;
-    rc = launch_fused<CgUpdateF, 2>(ctx, x->len, f, a, &slot, 6, x->kind == B200_VK_DIST);
+    rc = launch_fused<CgUpdateF, 2>(ctx, x->len, f, a, &slot, 6, x->kind == B200_VK_DIST, 1u);
     if (rc) return rc;
     return sync_read(ctx, slot, rr);
 }
@@ -438,7 +446,7 @@ extern "C" int b200_bicg_direction(b200_krylov_t K, b200_vec_t r, b200_vec_t v, 
 }
 
 extern "C" int b200_bicg_step_s(b200_krylov_t K, b200_csr_t A, b200_vec_t rh, b200_vec_t T, b200_vec_t v,
-                                b200_vec_t r, b200_vec_t s, b200_vec_t x, double *ss) {
+                                b200_vec_t r, b200_vec_t s, b200_vec_t x, double *ss, double *rho) {
     CHECK_K(K);
     B200_REQUIRE(A && rh && T && v && r && s && x && ss, "null argument");
     B200_REQUIRE(krylov_vec_ok(K, {rh, T, v, r, s, x}), "bicg_step_s: FP64 vectors of the workspace's size expected");
@@ -459,13 +467,16 @@ extern "C" int b200_bicg_step_s(b200_krylov_t K, b200_csr_t A, b200_vec_t rh, b2
     a.in[0] = pT; a.in[1] = px; a.in[2] = pr; a.in[3] = pv;
     a.out[0] = mut(x); a.out[1] = wr(s);
     const int slot = K->base + K_SS;
-    rc = launch_fused<BicgUpdateSF, 2>(ctx, x->len, f, a, &slot, 6, x->kind == B200_VK_DIST);
+    rc = launch_fused<BicgUpdateSF, 2>(ctx, x->len, f, a, &slot, 6, x->kind == B200_VK_DIST, 1u);
     if (rc) return rc;
-    return sync_read(ctx, slot, ss);
+    rc = sync_read(ctx, slot, ss);
+    // rho of this iteration: mirrored by b200_bicg_direction's kernel
+    if (rho) *rho = *reinterpret_cast<volatile double *>(ctx->scal_h + K->base + K_RHOP0 + K->parity);
+    return rc;
 }
 
 extern "C" int b200_bicg_step_r(b200_krylov_t K, b200_csr_t A, b200_vec_t rh, b200_vec_t T, b200_vec_t t,
-                                b200_vec_t s, b200_vec_t r, b200_vec_t x, double *rr) {
+                                b200_vec_t s, b200_vec_t r, b200_vec_t x, double *rr, double *omega) {
     CHECK_K(K);
     B200_REQUIRE(A && rh && T && t && s && r && x && rr, "null argument");
     B200_REQUIRE(krylov_vec_ok(K, {rh, T, t, s, r, x}), "bicg_step_r: FP64 vectors of the workspace's size expected");
@@ -486,7 +497,9 @@ extern "C" int b200_bicg_step_r(b200_krylov_t K, b200_csr_t A, b200_vec_t rh, b2
     a.in[0] = pT; a.in[1] = px; a.in[2] = ps; a.in[3] = pt; a.in[4] = prh;
     a.out[0] = mut(x); a.out[1] = wr(r);
     const int slots_r[2] = {K->base + K_RR, K->base + K_RHO_NEXT};
-    rc = launch_fused<BicgUpdateRF, 2>(ctx, x->len, f, a, slots_r, 7, x->kind == B200_VK_DIST);
+    rc = launch_fused<BicgUpdateRF, 2>(ctx, x->len, f, a, slots_r, 7, x->kind == B200_VK_DIST, 1u);
     if (rc) return rc;
-    return sync_read(ctx, slots_r[0], rr);
+    rc = sync_read(ctx, slots_r[0], rr);
+    if (omega) *omega = *reinterpret_cast<volatile double *>(ctx->scal_h + K->base + K_OMEGA);
+    return rc;
 }

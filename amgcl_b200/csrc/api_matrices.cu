@@ -385,8 +385,13 @@ static int launch_csr_LH(b200_ctx_t ctx, b200_csr_t A, const CsrArgsT<P> &args) 
         const int smem = kHeaderBytes + stages * lay.bytes;
         static bool attr_set[64] = {};
         if (!attr_set[ctx->device & 63]) {
+            // the opt-in limit covers static + dynamic shared memory (red_finish keeps a few
+            // hundred bytes of static scratch)
+            cudaFuncAttributes fa;
+            B200_CUDA(cudaFuncGetAttributes(&fa, csr_ring_kernel<MODE, L, HALO, P>));
             B200_CUDA(cudaFuncSetAttribute(csr_ring_kernel<MODE, L, HALO, P>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           max_smem - (int)fa.sharedSizeBytes));
             attr_set[ctx->device & 63] = true;
         }
         const int64_t cap = (int64_t)ctx->sm_count * ctx->opt_ctas_per_sm;
@@ -546,6 +551,7 @@ struct DotReq {
     int           ndot  = 0;
     const double *w     = nullptr;     // second operand of the first product (nullptr: see CsrArgsT)
     const int    *slots = nullptr;
+    unsigned      host_mask = 0;       // scalars the host will read right after a synchronize
     bool          done  = false;       // set when the launch produced the scalars
 };
 template <class P>
@@ -557,7 +563,7 @@ static void apply_req(b200_ctx_t ctx, b200_csr_t A, CsrArgsT<P> &a, DotReq *req)
     if (across && !ctx->scal_x_table) return;       // NCCL transport: separate reduction instead
     a.ndot = req->ndot;
     a.w = req->w;
-    red_out(ctx, req->ndot, req->slots, a.red, across);
+    red_out(ctx, req->ndot, req->slots, a.red, across, req->host_mask);
     req->done = true;
 }
 
@@ -709,10 +715,10 @@ int spmv_with_dots(b200_ctx_t ctx, b200_csr_t A, b200_vec_t x, b200_vec_t y, b20
 // r = f - A x leaving <r, r> in the table slot
 int residual_with_norm(b200_ctx_t ctx, b200_vec_t f, b200_csr_t A, b200_vec_t x, b200_vec_t r, int slot) {
     DotReq req;
-    req.ndot = 1; req.slots = &slot;
+    req.ndot = 1; req.slots = &slot; req.host_mask = 1u;
     int rc = residual_impl(ctx, f, A, x, r, &req);
     if (rc || req.done || A->kind == B200_CK_GHOST) return rc;
-    return launch_dot_slots(ctx, r, r, nullptr, &slot);
+    return launch_dot_slots(ctx, r, r, nullptr, &slot, 1u);
 }
 } // namespace b200
 

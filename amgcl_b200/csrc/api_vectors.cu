@@ -228,6 +228,36 @@ extern "C" int b200_vec_download(b200_vec_t v, double *host, size_t n) {
     return B200_OK;
 }
 
+// Partitioned vectors (multi-GPU): the block this rank owns, and a download of just that block
+// into its place in a full-size host array -- what a row-distributed caller needs (each rank
+// keeps the rows it owns, cf. amgcl::mpi's distributed vectors), without the all-gather of
+// b200_vec_download.
+extern "C" int b200_vec_local_range(b200_vec_t v, size_t *offset, size_t *len) {
+    B200_REQUIRE(v && offset && len, "null argument");
+    *offset = v->off;
+    *len = v->len;
+    return B200_OK;
+}
+
+extern "C" int b200_vec_download_local(b200_vec_t v, double *host, size_t n) {
+    B200_REQUIRE(v && (host || n == 0), "null argument");
+    NOT_RECORDING(v->ctx, "host transfer");
+    B200_REQUIRE(n == v->n, "size mismatch in vector download");
+    B200_REQUIRE(v->dtype == B200_F64, "b200_vec_download_local: FP64 vector expected");
+    if (v->kind != B200_VK_DIST) return b200_vec_download(v, host, n);
+    b200_ctx_t ctx = v->ctx;
+    GUARD(ctx);
+    if (!v->len) return B200_OK;
+    if (v->zero_pending) {
+        B200_CUDA(cudaStreamSynchronize(ctx->stream));
+        memset(host + v->off, 0, v->len * sizeof(double));
+        return B200_OK;
+    }
+    B200_CUDA(cudaMemcpyAsync(host + v->off, v->ptr, v->len * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA(cudaStreamSynchronize(ctx->stream));
+    return B200_OK;
+}
+
 namespace b200 {
 
 // ---- element-wise launch helpers ----------------------------------------------------------

@@ -196,14 +196,20 @@ void scal_free(b200_ctx_t ctx, int first, int count);
 // RedOut for one launch that leaves `nred` scalars in the given table slots
 // (across_ranks: the operands are partitioned, every rank launches the same kernel and the
 // finishing CTAs all-reduce over the peers)
-void red_out(b200_ctx_t ctx, int nred, const int *slots, RedOut &o, bool across_ranks);
+// host_mask: bit k set = scalar k is also written to the mapped host mirror (only where the
+// host reads it right after a synchronize: a write over PCIe lengthens the kernel's tail)
+void red_out(b200_ctx_t ctx, int nred, const int *slots, RedOut &o, bool across_ranks,
+             unsigned host_mask = 0);
+// value of a table slot on the host (synchronises; copies from the device unless mirrored)
+int  scal_read(b200_ctx_t ctx, int slot, bool mirrored, double *out);
 // products left behind by producer kernels (see b200_ctx_s::Product)
 bool product_wanted(b200_ctx_t ctx, size_t n);
 int  product_take_slot(b200_ctx_t ctx);
 void product_record(b200_ctx_t ctx, b200_vec_t a, b200_vec_t b, int slot);
 int  product_lookup(b200_ctx_t ctx, b200_vec_t a, b200_vec_t b);   // slot or -1
 // one standalone reduction launch: <x,y> (and <x,z> when z != nullptr) into table slots
-int  launch_dot_slots(b200_ctx_t ctx, b200_vec_t x, b200_vec_t y, b200_vec_t z, const int *slots);
+int  launch_dot_slots(b200_ctx_t ctx, b200_vec_t x, b200_vec_t y, b200_vec_t z, const int *slots,
+                      unsigned host_mask = 0);
 // (api_vectors.cu) stand-alone dot kernel: FP32 vectors, NCCL transport
 int  dot_legacy(b200_ctx_t ctx, b200_vec_t x, b200_vec_t y, double *result);
 

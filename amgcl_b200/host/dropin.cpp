@@ -280,7 +280,8 @@ int dropin_solve(void *handle, const double *rhs_host, double *x_host, int64_t *
 
 // End-to-end call as the reference's tutorial does it (poisson3Db_cuda.cu:83-87): the
 // right-hand side comes from the host, the initial guess x0 = 0 is created on the device,
-// the solution goes back to the host.
+// the solution goes back to the host.  On a multi-GPU context every rank moves the rows it owns
+// (rhs rows in, solution rows into their place in x_host), like a row-distributed MPI program.
 int dropin_solve_zero_guess(void *handle, const double *rhs_host, double *x_host, int64_t *iters,
                             double *resid)
 {
@@ -290,7 +291,7 @@ int dropin_solve_zero_guess(void *handle, const double *rhs_host, double *x_host
         amgcl::backend::clear(*h->x);
         size_t it; double r;
         std::tie(it, r) = h->solver->solve(*h->f, *h->x);
-        h->x->download(x_host);
+        h->x->download_local(x_host);
         *iters = (int64_t)it; *resid = r;
         return 0;
     } catch (const std::exception &e) {

@@ -51,8 +51,6 @@ def parse_args():
     ap.add_argument("--graph", type=int, default=0, choices=[0, 1],
                     help="1: amgcl::preconditioner::b200_cycle_graph<amg<...>> -- every V-cycle is one "
                          "CUDA graph launch (single GPU)")
-    ap.add_argument("--ref-sample-iters", type=int, default=8,
-                    help="Krylov iterations per step of the CPU reference sample")
     return ap.parse_args()
 
 
@@ -126,30 +124,81 @@ class ClockSampler:
                 "power_w_max": float(max(power)), "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def pin_openmp():
+    """BASELINE.md section 3 protocol for the CPU arm: threads bound to cores, neighbours
+    close.  Must run before the first OpenMP runtime is loaded (libgomp reads the
+    environment once), i.e. before torch / oracle are imported."""
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+    os.environ.setdefault("OMP_PLACES", "cores")
+
+
+def cpu_topology():
+    """(logical cpus, physical cores, sockets) of this host."""
+    logical = os.cpu_count() or 1
+    try:
+        out = subprocess.run(["lscpu", "-p=CPU,CORE,SOCKET"], stdout=subprocess.PIPE,
+                             stderr=subprocess.DEVNULL, text=True, timeout=10).stdout
+        rows = [tuple(int(v) for v in line.split(",")[:3]) for line in out.splitlines()
+                if line and not line.startswith("#")]
+        avail = None
+        try:
+            avail = os.sched_getaffinity(0)
+        except Exception:
+            pass
+        if avail:
+            rows = [r for r in rows if r[0] in avail] or rows
+        cores = len({(c, sk) for _, c, sk in rows}) or logical
+        sockets = len({sk for _, _, sk in rows}) or 1
+        return len(rows) or logical, cores, sockets
+    except Exception:
+        return logical, logical, 1
+
+
 def pick_threads(ref, step):
-    """Give the CPU reference its best OpenMP thread count on this host (memory-bound
-    kernels often peak below the hardware thread count): time one step per candidate."""
-    hw = os.cpu_count() or ref.threads
-    cands = sorted({c for c in (ref.threads, hw, hw // 2, hw // 4) if c and c >= 1}, reverse=True)
-    best, best_t = cands[0], None
+    """Sweep the OpenMP thread count over {all logical cpus, all physical cores, one socket's
+    cores, half a socket} and keep the fastest (memory-bound kernels often peak below the
+    hardware thread count): one settling step, then the median of three per candidate."""
+    logical, cores, sockets = cpu_topology()
+    cands = sorted({c for c in (logical, cores, cores // sockets, max(1, cores // (2 * sockets)))
+                    if c and c >= 1}, reverse=True)
+    best, best_t, seen = cands[0], None, {}
     for c in cands:
         ref.set_threads(c)
         step()                                   # settle
-        t0 = time.perf_counter()
-        step()
-        dt = time.perf_counter() - t0
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            step()
+            ts.append(time.perf_counter() - t0)
+        dt = float(np.median(ts))
+        seen[c] = dt
         if best_t is None or dt < best_t:
             best, best_t = c, dt
     ref.set_threads(best)
-    return best
+    return best, {"logical": logical, "physical_cores": cores, "sockets": sockets,
+                  "binding": "OMP_PROC_BIND=%s OMP_PLACES=%s" % (os.environ.get("OMP_PROC_BIND"),
+                                                                 os.environ.get("OMP_PLACES")),
+                  "sweep_s_per_sample": {str(k): round(v, 4) for k, v in seen.items()}}
+
+
+def timed_reference_solves(S, rhs, count):
+    """`count` FULL solves of the reference; solve() alone is timed (inside the library,
+    vectors first-touched in parallel beforehand).  Returns (x, iters, resid, seconds[])."""
+    secs = []
+    for _ in range(count):
+        x, it, res, dt = S.solve_timed(rhs)
+        secs.append(dt)
+    return x, it, res, secs
 
 
 # --------------------------------------------------------------------------- reference arm
 def reference_arm(args, rank, world):
     """The reference's own CPU implementation of the path: AMGCL builtin (OpenMP) backend
-    compiled from the reference sources (oracle/_ref), all host threads, same workload.
-    Each step is a bounded sample: the first `ref_sample_iters` Krylov iterations of the
-    solve (every iteration does the same work, so iterations/s is the same metric)."""
+    compiled from the reference sources (oracle/_ref), same workload.  Protocol (BASELINE.md
+    section 3): threads bound (OMP_PROC_BIND=close, OMP_PLACES=cores), thread count swept over
+    {logical, physical, per-socket}, every timed step ONE FULL solve, solve() alone timed,
+    value = iterations / median solve time.  Warm-up steps are truncated (4-iteration)
+    solves: they touch exactly the same memory."""
     if rank != 0:
         return
     import oracle
@@ -163,42 +212,58 @@ def reference_arm(args, rank, world):
     ptr, col, val, rhs = poisson3d(args.n)
     t_gen = time.time() - t0
     t0 = time.time()
-    S = oracle.RefSolver(ptr, col, val, args.relax, args.krylov, maxiter=args.ref_sample_iters,
-                         precision=args.precision)
+    S = oracle.RefSolver(ptr, col, val, args.relax, args.krylov, precision=args.precision)
     t_setup = time.time() - t0
-    cores = pick_threads(ref, lambda: S.solve(rhs))
+    Sq = oracle.RefSolver(ptr, col, val, args.relax, args.krylov, maxiter=4, precision=args.precision)
+    cores, topo = pick_threads(ref, lambda: Sq.solve(rhs))
     for _ in range(args.warmup):
-        S.solve(rhs)
-    iters_total = 0
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        _, it, res = S.solve(rhs)
-        iters_total += it
-    dt = time.perf_counter() - t0
-    value = iters_total / dt
-    sample = "%d %s iterations of the %s solve per step, %d steps" % (
-        args.ref_sample_iters, args.krylov, workload_name(args), args.steps)
+        Sq.solve(rhs)
+    Sq.close()
+    x, it, res, secs = timed_reference_solves(S, rhs, args.steps)
+    S.close()
+    med = float(np.median(secs))
+    value = it / med
+    sample = "%d full %s solves (%d iterations each), solve() only; median %.3f s, min %.3f, max %.3f" % (
+        args.steps, workload_name(args), it, med, min(secs), max(secs))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * med,
+        "mean_ms_per_step": 1e3 * float(np.mean(secs)),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64" if args.precision == "f64" else "f64 krylov + f32 hierarchy",
         "data": "synthetic",
-        "config": {"workload": workload_name(args), "backend": "amgcl::backend::builtin<double> (OpenMP)",
-                   "rows": int(ptr.size - 1), "nnz": int(ptr[-1]), "setup_s": t_setup,
-                   "generate_s": t_gen},
+        "config": config_block(args, int(ptr.size - 1), int(ptr[-1]), t_setup, t_gen,
+                               backend="amgcl::backend::builtin<double> (OpenMP)"),
+        "iters": it, "resid": res,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
-                         "sample": sample},
+                         "sample": sample, "topology": topo},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
 
 
+def config_block(args, nrows, nnz, t_setup, t_gen, backend=None, parallelism="host cores (OpenMP)",
+                 extra=None):
+    """`config` of the JSON line: the same keys for both arms (the driver compares them)."""
+    cfg = {"workload": workload_name(args), "rows": nrows, "nnz": nnz,
+           "relax": args.relax, "krylov": args.krylov, "tol": 1e-8,
+           "step": "one complete solve, rhs=1, x0=0",
+           "l2": "inputs_exceed_l2 (finest matrix %.2f GB >> 126 MB)" % (nnz * 12 / 1e9),
+           "parallelism": parallelism,
+           "setup_s": t_setup, "generate_s": t_gen,
+           "hierarchy": "host (AMGCL smoothed_aggregation)"}
+    if backend:
+        cfg["backend"] = backend
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
 # --------------------------------------------------------------------------- our arm
 def cpu_baseline_leg(args, ptr, col, val, rhs, full_iters):
-    """Reference builtin backend on the box's host cores, one full solve (bounded: the
-    whole 256^3 solve is a few seconds of CPU time on a many-core host)."""
+    """Reference builtin backend on the box's host cores: same protocol as --impl reference
+    (bound threads, swept thread count, solve() only), median of three full solves."""
     import oracle
     if not oracle.have_ref():
         return None
@@ -206,18 +271,44 @@ def cpu_baseline_leg(args, ptr, col, val, rhs, full_iters):
     t0 = time.time()
     S = oracle.RefSolver(ptr, col, val, args.relax, args.krylov, precision=args.precision)
     t_setup = time.time() - t0
-    Sq = oracle.RefSolver(ptr, col, val, args.relax, args.krylov, maxiter=2, precision=args.precision)
-    threads = pick_threads(ref, lambda: Sq.solve(rhs))
+    Sq = oracle.RefSolver(ptr, col, val, args.relax, args.krylov, maxiter=4, precision=args.precision)
+    threads, topo = pick_threads(ref, lambda: Sq.solve(rhs))
+    Sq.solve(rhs)
     Sq.close()
-    S.solve(rhs)                       # warm the caches / page in
-    t0 = time.perf_counter()
-    x, it, res = S.solve(rhs)
-    dt = time.perf_counter() - t0
+    x, it, res, secs = timed_reference_solves(S, rhs, 3)
     S.close()
-    return {"value": it / dt, "unit": UNIT, "cores": threads, "kind": "reference",
-            "sample": "one full %s solve (%d iterations, %.3f s) after one warm-up; setup %.1f s not timed"
-                      % (workload_name(args), it, dt, t_setup),
-            "iters": it, "resid": res, "solve_s": dt}, x
+    med = float(np.median(secs))
+    return {"value": it / med, "unit": UNIT, "cores": threads, "kind": "reference",
+            "sample": "3 full %s solves (%d iterations each), solve() only: median %.3f s (min %.3f, max %.3f); "
+                      "setup %.1f s not timed" % (workload_name(args), it, med, min(secs), max(secs), t_setup),
+            "topology": topo, "iters": it, "resid": res, "solve_s": med}, x
+
+
+def golden_parity(args, iters, resid, x):
+    """This run against the reference's committed known answers for the workload
+    (tests/golden/large_answers.json, written by tests/golden/make_large_answers.py from the
+    real reference): iteration count, final residual, and the solution at 257 sample points.
+    Works at every N -- the multi-GPU lines carry it too."""
+    path = os.path.join(ROOT, "tests", "golden", "large_answers.json")
+    if args.precision != "f64" or not os.path.isfile(path):
+        return None
+    with open(path) as f:
+        known = json.load(f)
+    case = [c for c in known["cases"] if (c["n"], c["relax"], c["krylov"]) == (args.n, args.relax, args.krylov)]
+    if not case:
+        return None
+    c = case[0]
+    idx = np.linspace(0, x.size - 1, len(c["x_samples"])).astype(np.int64)
+    want = np.asarray(c["x_samples"])
+    out = {"golden": "tests/golden/large_answers.json",
+           "iters": iters, "iters_golden": c["iters"],
+           "resid": resid, "resid_golden": c["resid"],
+           "resid_rel_diff": abs(resid - c["resid"]) / c["resid"],
+           "x_samples_rel_err_inf": float(np.abs(x[idx] - want).max() / c["x_max"]),
+           "x_norm2_rel_diff": abs(float(np.linalg.norm(x)) - c["x_norm2"]) / c["x_norm2"]}
+    out["ok"] = bool(out["iters"] == out["iters_golden"] and out["resid_rel_diff"] <= 1e-6 and
+                     out["x_samples_rel_err_inf"] <= 1e-8 and out["x_norm2_rel_diff"] <= 1e-8)
+    return out
 
 
 def main_arm(args, rank, world, local_rank):
@@ -382,43 +473,47 @@ def main_arm(args, rank, world, local_rank):
         t = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_e2e = float(t.item())
-    per_rank_rows = (nrows + world - 1) // world
+    # every rank uploads its rows of rhs and downloads its rows of x (one system: nrows*8 each way)
     e2e = {"value": e2e_iters / t_e2e, "unit": UNIT, "solve_s": t_e2e / args.steps,
-           "h2d_bytes_per_step": per_rank_rows * 8 * world, "d2h_bytes_per_step": nrows * 8 * world,
+           "h2d_bytes_per_step": nrows * 8, "d2h_bytes_per_step": nrows * 8,
            "api": "make_solver<amg<backend::b200<double>,...>, %s>::operator()(rhs, x) via "
                   "dropin_solve_zero_guess: pinned host rhs -> device, x0 = 0 created on the device as in "
-                  "tutorial/1.poisson3Db/poisson3Db_cuda.cu:83-87, solution -> pinned host" % args.krylov}
-    x_gpu = x_h.copy()
+                  "tutorial/1.poisson3Db/poisson3Db_cuda.cu:83-87, solution -> pinned host%s" % (
+                      args.krylov, "" if world == 1 else
+                      " (each rank moves the rows it owns, like amgcl::mpi's row-distributed vectors)")}
+    # the complete solution for the parity check (not timed; N > 1: all-gathered to every rank)
+    x_gpu = x_h.copy() if world == 1 else S.download_x()
 
     # ---- cpu baseline (rank 0, N == 1) ---------------------------------------------------
     cpu = None
     parity = None
+    if rank == 0:
+        parity = golden_parity(args, iters, res, x_gpu)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         got = cpu_baseline_leg(args, ptr, col, val, rhs, iters)
         if got is not None:
             cpu, x_ref = got
-            parity = {"iters_gpu": iters, "iters_ref": cpu.pop("iters"),
-                      "resid_gpu": res, "resid_ref": cpu.pop("resid"),
-                      "x_rel_err_inf": float(np.abs(x_gpu - x_ref).max() / np.abs(x_ref).max())}
+            parity = dict(parity or {})
+            parity.update({"iters_gpu": iters, "iters_ref": cpu.pop("iters"),
+                           "resid_gpu": res, "resid_ref": cpu.pop("resid"),
+                           "x_rel_err_inf": float(np.abs(x_gpu - x_ref).max() / np.abs(x_ref).max())})
             cpu.pop("solve_s", None)
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": solve_s * 1e3, "higher_is_better": True,
-            "scaling": "weak" if world == 1 else "strong", "vs_baseline": None,
+            "scaling": "strong", "vs_baseline": None,       # ONE fixed-size system at every N
             "dtype": "f64" if args.precision == "f64" else "f64 krylov + f32 hierarchy",
             "data": "synthetic",
-            "config": {"workload": workload_name(args), "rows": nrows, "nnz": nnz,
-                       "relax": args.relax, "krylov": args.krylov, "tol": 1e-8,
-                       "step": "one complete solve, rhs=1, x0=0",
-                       "l2": "inputs_exceed_l2 (finest matrix %.2f GB >> 126 MB)" % (nnz * 12 / 1e9),
-                       "parallelism": "single GPU" if world == 1 else
-                                      "one system row-partitioned over %d GPUs (levels with >= %d rows; "
-                                      "exchange: %s)" % (world, dist_min_rows, transport),
-                       "cycle_graph": {"on": bool(args.graph) and world == 1,
+            "config": config_block(
+                args, nrows, nnz, t_setup, t_gen, backend="amgcl::backend::b200<double>",
+                parallelism="single GPU" if world == 1 else
+                "one system row-partitioned over %d GPUs (levels with >= %d rows; exchange: %s)" % (
+                    world, dist_min_rows, transport),
+                extra={"cycle_graph": {"on": bool(args.graph) and world == 1,
                                        "graphs_kernels_replays": list(S.graph_stats())},
-                       "setup_s": t_setup, "generate_s": t_gen, "hierarchy": "host (AMGCL smoothed_aggregation)"},
+                       "fused_krylov": bool(ctx.get_option("fused_krylov"))}),
             "solve_s": solve_s, "iters": iters, "resid": res,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "roofline": roof, "csr_kernel_share_of_step": all_csr_ms / (args.steps * solve_s * 1e3),
@@ -454,6 +549,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world == 1 or args.impl == "reference":
+        pin_openmp()             # CPU legs: bound threads (before any OpenMP runtime loads)
     if args.impl == "reference":
         reference_arm(args, rank, world)
     else:

@@ -141,6 +141,8 @@ class b200_vector {
         /// Copy to a host container (resized by the caller).
         void download(real *host) const { AMGCL_CALL_B200(detail::b200_vec_get(h, host, n)); }
         void upload(const real *host)   { AMGCL_CALL_B200(detail::b200_vec_put(h, host, n)); }
+        /// Multi-GPU: only the rows this rank owns, into their place in the full-size host array.
+        void download_local(double *host) const { AMGCL_CALL_B200(b200_vec_download_local(h, host, n)); }
 
     private:
         b200_ctx_t ctx;
@@ -671,9 +673,6 @@ struct b200_krylov_handle {
         return fused != 0;
     }
 };
-// logical layout of b200_krylov_scalars()
-enum { b200_k_rho = 0, b200_k_qp = 1, b200_k_alpha = 2, b200_k_ts = 3, b200_k_tt = 4,
-       b200_k_omega = 5, b200_k_rr = 6, b200_k_ss = 7, b200_k_rho_next = 8, b200_k_count = 9 };
 } // namespace detail
 
 /// Conjugate Gradient on the b200 backend (primary: solver/cg.hpp:62-263).
@@ -839,7 +838,7 @@ class bicgstab< backend::b200<double, C, P, DS>, detail::default_inner_product >
                 }
             }
 
-            double rr = 0, ssq = 0, sc[detail::b200_k_count];
+            double rr = 0, ssq = 0, rho = 0, omega = 0;
             AMGCL_CALL_B200(b200_krylov_residual(kh.K, rhs.handle(), A.handle(), x.handle(), r->handle(), &rr));
             AMGCL_CALL_B200(b200_bicg_start(kh.K, r->handle(), rh->handle()));
 
@@ -857,17 +856,15 @@ class bicgstab< backend::b200<double, C, P, DS>, detail::default_inner_product >
                 Prec.apply(*p, *T);
                 // v = A T; alpha = rho/<rh,v>; x += alpha T; s = r - alpha v; <s,s>
                 AMGCL_CALL_B200(b200_bicg_step_s(kh.K, A.handle(), rh->handle(), T->handle(), v->handle(),
-                            r->handle(), s->handle(), x.handle(), &ssq));
-                AMGCL_CALL_B200(b200_krylov_scalars(kh.K, sc, detail::b200_k_count));
-                rho_prev = sc[detail::b200_k_rho];
+                            r->handle(), s->handle(), x.handle(), &ssq, &rho));
+                rho_prev = rho;
 
                 if ((res = sqrt(fabs(ssq))) > eps) {
                     Prec.apply(*s, *T);
                     // t = A T; omega = <t,s>/<t,t>; x += omega T; r = s - omega t; <r,r>; next rho
                     AMGCL_CALL_B200(b200_bicg_step_r(kh.K, A.handle(), rh->handle(), T->handle(), t->handle(),
-                                s->handle(), r->handle(), x.handle(), &rr));
-                    AMGCL_CALL_B200(b200_krylov_scalars(kh.K, sc, detail::b200_k_count));
-                    precondition(!math::is_zero(sc[detail::b200_k_omega]), "Zero omega in BiCGStab");
+                                s->handle(), r->handle(), x.handle(), &rr, &omega));
+                    precondition(!math::is_zero(omega), "Zero omega in BiCGStab");
                     res = sqrt(fabs(rr));
                 }
 

@@ -188,6 +188,13 @@ int b200_vec_data(b200_vec_t v, double **device_ptr);
  * until the copy has completed (same semantics as thrust::copy, cuda.hpp:635-660). */
 int b200_vec_upload(b200_vec_t v, const double *host, size_t n);
 int b200_vec_download(b200_vec_t v, double *host, size_t n);
+/* Multi-GPU contexts: the block of a partitioned vector this rank owns ([offset, offset+len) of
+ * the global index range; the whole vector otherwise), and a download of only that block into
+ * its place host[offset .. offset+len) of a full-size host array -- no exchange between the
+ * ranks, other entries of `host` are left untouched (b200_vec_download all-gathers the complete
+ * vector to every rank).  On a single GPU identical to b200_vec_download. */
+int b200_vec_local_range(b200_vec_t v, size_t *offset, size_t *len);
+int b200_vec_download_local(b200_vec_t v, double *host, size_t n);
 /* FP32 vectors (single GPU only).  Every primitive below accepts the precision
  * combinations AMGCL's mixed-precision composition produces -- all FP64, all FP32, and an
  * FP32 matrix / diagonal applied to FP64 vectors (see DESIGN.md "Mixed precision") -- and
@@ -322,9 +329,9 @@ int b200_krylov_destroy(b200_krylov_t K);
  * bicgstab.hpp:180).  If x is known to be zero the pass over A is skipped (r = rhs). */
 int b200_krylov_residual(b200_krylov_t K, b200_vec_t rhs, b200_csr_t A, b200_vec_t x,
                          b200_vec_t r, double *rr);
-/* The workspace's scalars as the device formed them (synchronises the stream), out[0..count),
- * count <= 9: rho of the current iteration, <q,p> | <rh,v>, alpha, <t,s>, <t,t>, omega, <r,r>,
- * <s,s>, rho of the next iteration.  For the breakdown checks of bicgstab.hpp:206,228. */
+/* The workspace's scalars as the device formed them (device -> host copy, synchronises),
+ * out[0..count), count <= 9: rho of the current iteration, <q,p> | <rh,v>, alpha, <t,s>,
+ * <t,t>, omega, <r,r>, <s,s>, rho of the next iteration.  For tests and diagnostics. */
 int b200_krylov_scalars(b200_krylov_t K, double *out, int count);
 
 /* CG.  b200_cg_direction: rho = <r,s> (taken from the smoother's epilogue when available),
@@ -341,15 +348,16 @@ int b200_cg_step(b200_krylov_t K, b200_csr_t A, b200_vec_t p, b200_vec_t q, b200
  *   b200_bicg_direction  p = r + beta (p - omega v), beta = (rho alpha)/(rho_prev omega);
  *                        p = r on the first call of a solve                      :202-208
  *   b200_bicg_step_s     v = A T; alpha = rho/<rh,v>; x += alpha T; s = r - alpha v;
- *                        *ss = <s,s>                                            :210-222
+ *                        *ss = <s,s>; *rho (optional) = this iteration's rho    :210-222
  *   b200_bicg_step_r     t = A T; omega = <t,s>/<t,t>; x += omega T; r = s - omega t;
- *                        *rr = <r,r>; next rho = <r,rh>                         :223-236,200 */
+ *                        *rr = <r,r>; next rho = <r,rh>; *omega (optional)      :223-236,200
+ * rho and omega are returned for the breakdown checks of bicgstab.hpp:206,228. */
 int b200_bicg_start(b200_krylov_t K, b200_vec_t r, b200_vec_t rh);
 int b200_bicg_direction(b200_krylov_t K, b200_vec_t r, b200_vec_t v, b200_vec_t p);
 int b200_bicg_step_s(b200_krylov_t K, b200_csr_t A, b200_vec_t rh, b200_vec_t T, b200_vec_t v,
-                     b200_vec_t r, b200_vec_t s, b200_vec_t x, double *ss);
+                     b200_vec_t r, b200_vec_t s, b200_vec_t x, double *ss, double *rho);
 int b200_bicg_step_r(b200_krylov_t K, b200_csr_t A, b200_vec_t rh, b200_vec_t T, b200_vec_t t,
-                     b200_vec_t s, b200_vec_t r, b200_vec_t x, double *rr);
+                     b200_vec_t s, b200_vec_t r, b200_vec_t x, double *rr, double *omega);
 
 /* ---------------------------------------------------------------- coarse solve */
 

@@ -245,6 +245,8 @@ class _Ref:
         R.ref_destroy.argtypes = [_vp]
         R.ref_destroy.restype = None
         R.ref_solve.argtypes = [_vp, _vp, _vp, _P(_i64), _P(_dbl)]
+        R.ref_solve_timed.argtypes = [_vp, _vp, _vp, _P(_i64), _P(_dbl), _P(_dbl)]
+        R.ref_solve_timed.restype = _c.c_int
         R.ref_apply_precond.argtypes = [_vp, _vp, _vp]
         R.ref_report.argtypes = [_vp, _c.c_char_p, _i64]
         R.ref_report.restype = _i64
@@ -427,6 +429,18 @@ class RefSolver:
         if self.r.R.ref_solve(self.h, _p(rhs), _p(x), _c.byref(it), _c.byref(res)) != 0:
             raise RuntimeError("ref_solve: " + self.r.R.ref_last_error().decode())
         return x, it.value, res.value
+
+    def solve_timed(self, rhs, x0=None):
+        """As solve(); the 4th value is the time of solve() alone, measured inside the library."""
+        rhs = _arr(rhs, np.float64)
+        x = np.zeros(self.n) if x0 is None else _arr(x0, np.float64).copy()
+        it = _i64()
+        res = _dbl()
+        sec = _dbl()
+        if self.r.R.ref_solve_timed(self.h, _p(rhs), _p(x), _c.byref(it), _c.byref(res),
+                                    _c.byref(sec)) != 0:
+            raise RuntimeError("ref_solve_timed: " + self.r.R.ref_last_error().decode())
+        return x, it.value, res.value, sec.value
 
     def apply_precond(self, f):
         f = _arr(f, np.float64)

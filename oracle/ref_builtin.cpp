@@ -257,6 +257,25 @@ int ref_solve(void *handle, const double *rhs, double *x, int64_t *iters, double
     } catch (const std::exception &e) { g_error = e.what(); return -1; }
 }
 
+// As ref_solve, timing solve() alone ("time solve(rhs, x) only"): the
+// host vectors are built -- first-touched in parallel by numa_vector's constructor -- before
+// the clock starts, the copy back happens after it stops.
+int ref_solve_timed(void *handle, const double *rhs, double *x, int64_t *iters, double *resid,
+                    double *seconds)
+{
+    Handle *h = static_cast<Handle *>(handle);
+    try {
+        HostVector f(rhs, rhs + h->n), xx(x, x + h->n);
+        size_t it; double r;
+        const double t0 = omp_get_wtime();
+        std::tie(it, r) = h->solver->solve(f, xx);
+        *seconds = omp_get_wtime() - t0;
+        std::memcpy(x, xx.data(), h->n * sizeof(double));
+        *iters = (int64_t)it; *resid = r;
+        return 0;
+    } catch (const std::exception &e) { g_error = e.what(); return -1; }
+}
+
 int ref_apply_precond(void *handle, const double *f_in, double *x)
 {
     Handle *h = static_cast<Handle *>(handle);

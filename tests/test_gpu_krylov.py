@@ -202,7 +202,9 @@ def test_fused_solver_vs_reference_sequence(ctx, relax, krylov, precision):
             ctx.set_option("fused_krylov", 1)
     (x0, it0, res0, l0), (x1, it1, res1, l1) = out[0], out[1]
     assert it1 == it0
-    tol = 1e-4 if krylov == "bicgstab" else TOL_RESID_REL       # BiCGStab amplifies rounding
+    tol = TOL_RESID_REL
+    if krylov == "bicgstab":                                    # BiCGStab amplifies rounding
+        tol = 1e-3 if precision == "mixed" else 1e-4
     assert abs(res1 - res0) <= tol * res0
     assert rel_err(x1, x0) < (1e-6 if precision == "mixed" else TOL_SOLUTION)
     assert l1 < l0
