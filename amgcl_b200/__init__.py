@@ -720,9 +720,13 @@ def partition(n, nranks, rank):
 
 
 def dist_split(kind, nranks, rank, nrows, ncols, ptr, col, val):
-    """Host view of one rank's share of an operator (kind: 'square' | 'prolong' | 'restrict').
-    Returns dict(nrows, ncols, n_loc, slots, ptr, col, val, send_idx)."""
-    k = {"square": 1, "prolong": 2, "restrict": 3}[kind]
+    """Host view of one rank's share of an operator: always whole rows (the rank's block of
+    the row partition).  kind 'halo': the vector the operator is applied to is partitioned --
+    local columns become [0, n_loc), columns owned by rank o become n_loc + o*slots + position
+    in o's send list; kind 'replicated': that vector is replicated, columns stay global.
+    ('square' is an alias of 'halo'.)  Returns dict(nrows, ncols, n_loc, slots, ptr, col, val,
+    send_idx)."""
+    k = {"halo": 1, "square": 1, "replicated": 2}[kind]
     ptr = np.ascontiguousarray(ptr, dtype=np.int64)
     col = np.ascontiguousarray(col, dtype=np.int64)
     val = _f64(val)

@@ -27,7 +27,7 @@ EXAMPLE_SRC = os.path.join(ROOT, "examples", "poisson_b200.cpp")
 NVCC_COMPILE = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-I", INCLUDE,
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-fopenmp", "-I", INCLUDE,
 ]
 # portable x86-64 flags: the GPU box may have a different CPU than the build box
 CXX_FLAGS = ["-O2", "-mavx2", "-mfma", "-std=c++17", "-fopenmp", "-fPIC", "-shared", "-DAMGCL_NO_BOOST"]
@@ -99,7 +99,8 @@ def build_cuda(force=False, verbose=False):
     if failed:
         raise RuntimeError("\n".join(failed))
     objs = [os.path.join(objdir, u[:-3] + ".o") for u in units]
-    _run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_CUDA] + objs)
+    _run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fopenmp",
+          "-o", LIB_CUDA] + objs + ["-lgomp"])
     return LIB_CUDA
 
 

@@ -24,14 +24,10 @@ static int coarse_create(b200_ctx_t ctx, int64_t n, const Ptr *ptr, const Col *c
     const int64_t nnz = (int64_t)ptr[n];
     B200_REQUIRE(nnz >= 0 && (nnz == 0 || (col && val)), "bad col/val array");
     GUARD(ctx);
+    // multi-GPU: a coarsest level below the partition threshold is replicated -- every rank
+    // forms the inverse and solves redundantly (no exchange); a partitioned one keeps the
+    // inverse on every rank and applies its own rows to the all-gathered right-hand side
     const bool replicated = ctx->dist && n >= ctx->dist_min_rows;
-    if (ctx->dist && ctx->rank != 0 && !replicated) {       // the coarsest level lives on rank 0
-        b200_coarse_s *G = new (std::nothrow) b200_coarse_s();
-        if (!G) return fail(B200_ENOMEM, "out of host memory");
-        G->ctx = ctx; G->n = n; G->ghost = true;
-        *out = G;
-        return B200_OK;
-    }
 
     std::vector<int32_t> hptr((size_t)n + 1), hcol((size_t)nnz);
     for (int64_t i = 0; i <= n; ++i) hptr[(size_t)i] = (int32_t)ptr[i];

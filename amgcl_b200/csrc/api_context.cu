@@ -98,6 +98,11 @@ extern "C" int b200_ctx_destroy(b200_ctx_t ctx) {
     GUARD(ctx);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     scal_destroy(ctx);
+    for (int k = 0; k < 2; ++k) {
+        if (ctx->stage_host[k]) cudaFreeHost(ctx->stage_host[k]);
+        if (ctx->stage_event[k]) cudaEventDestroy(ctx->stage_event[k]);
+    }
+    if (ctx->gather_ticket) cudaFree(ctx->gather_ticket);
     if (ctx->scal_x_local) {
         for (int q = 0; q < ctx->nranks; ++q)
             if (q != ctx->rank && ctx->scal_x_peer[q]) cudaIpcCloseMemHandle(ctx->scal_x_peer[q]);

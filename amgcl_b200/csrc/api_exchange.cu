@@ -40,6 +40,8 @@ extern "C" int b200_dist_init(b200_ctx_t ctx, const char *id, size_t size, int n
     ctx->dist = true;
     B200_CUDA(cudaMalloc(&ctx->push_ticket, sizeof(unsigned int)));
     B200_CUDA(cudaMemset(ctx->push_ticket, 0, sizeof(unsigned int)));
+    B200_CUDA(cudaMalloc(&ctx->gather_ticket, sizeof(unsigned int)));
+    B200_CUDA(cudaMemset(ctx->gather_ticket, 0, sizeof(unsigned int)));
     B200_CUDA(cudaMalloc(&ctx->ipc_dev, (size_t)kMaxRanks * sizeof(cudaIpcMemHandle_t)));
 
     // peer-memory exchange: try to map a small buffer of every peer; agree collectively
@@ -89,21 +91,15 @@ extern "C" int b200_dist_split_i64(int kind, int nranks, int rank, int64_t nrows
                                    b200_split_t *out) {
     B200_REQUIRE(out != nullptr && ptr != nullptr, "null argument");
     B200_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank / nranks");
-    B200_REQUIRE(kind >= 1 && kind <= 3, "kind must be 1 (square), 2 (prolong) or 3 (restrict)");
+    B200_REQUIRE(kind >= 1 && kind <= 3, "kind must be 1 (columns partitioned) or 2 (columns replicated)");
     b200_split_s *sp = new (std::nothrow) b200_split_s();
     if (!sp) return fail(B200_ENOMEM, "out of host memory");
     sp->kind = kind;
-    if (kind == B200_CK_SQUARE) {
-        if (nrows != ncols) { delete sp; return fail(B200_EINVAL, "square operator expected"); }
-        split_square(Partition(nrows, nranks), rank, ptr, col, sp->m);
-    } else if (kind == B200_CK_PROLONG) {
-        split_prolong(Partition(nrows, nranks), rank, ncols, ptr, col, sp->m);
-    } else {
-        split_restrict(Partition(ncols, nranks), rank, nrows, ptr, col, val, sp->m);
-    }
+    // whole rows of `rank`; kind 1 (and the legacy 3): the vector the operator is applied to is
+    // partitioned -> local columns + halo slots; kind 2: it is replicated -> columns untouched
+    split_rows(Partition(nrows, nranks), Partition(ncols, nranks), kind != 2, rank, ptr, col, sp->m);
     const int64_t nnz = sp->m.ptr.back();
-    if (sp->m.val_contiguous) sp->val.assign(val + sp->m.val_offset, val + sp->m.val_offset + nnz);
-    else sp->val = sp->m.val;
+    sp->val.assign(val + sp->m.val_offset, val + sp->m.val_offset + nnz);
     *out = sp;
     return B200_OK;
 }
@@ -178,60 +174,39 @@ void peer_release(b200_ctx_t ctx, void *local, void **peers) {
 }
 
 
-static int launch_push(b200_ctx_t ctx, int64_t count, const double *src, const int *idx,
-                       const PeerTargets &tgt, int64_t seg_stride, unsigned long long seq) {
-    // indexed (halo) pushes: one value per thread; contiguous ones: 8 doubles per thread;
-    // never more than 4 CTAs per SM -- the grid-stride loops cover the rest
-    const int64_t per_cta = idx ? kThreads : (int64_t)kThreads * 8;
-    const int64_t want = std::max<int64_t>(1, (count + per_cta - 1) / per_cta);
-    const unsigned grid = (unsigned)std::min<int64_t>(want, (int64_t)ctx->sm_count * 4);
-    push_kernel<<<grid, kThreads, 0, ctx->stream>>>(count, src, idx, tgt, ctx->nranks, seg_stride,
-                                                    ctx->push_ticket, seq);
-    B200_CHECK_LAUNCH();
-    ctx->launches++;
-    return B200_OK;
-}
-
-// SQUARE operators: make every rank's boundary values of x visible in A->halo.
-// One pack kernel + one in-place ncclAllGather (S doubles per rank) on the stream.
+// HALO operators: make the boundary values of x visible to every rank that gathers them.
+// Peer transport: nothing is launched here -- the consumer kernel pushes this rank's values
+// itself (HaloArgs::push_*) and waits for the peers' flags block by block.  NCCL transport: one
+// pack kernel + one in-place ncclAllGather (S doubles per rank) on the stream.
 int halo_exchange(b200_ctx_t ctx, b200_csr_t A, const double *x, HaloArgs &a) {
+    a = HaloArgs();
     a.xh = A->halo; a.nloc = (int)A->n_loc;
+    a.blk_order = A->blk_order;
     if (A->S == 0) return B200_OK;
-    ProfScope prof(ctx, B200_PROF_COMM, A->n_send, ctx->nranks, 0);
     if (ctx->p2p) {
-        // push my boundary values straight into the halo buffers of the ranks that gather
-        // them, release their flags, then wait for the ranks I gather from
         const int par = (int)(A->seq & 1);
         const unsigned long long seq = ++A->seq;
-        PeerTargets tgt;
-        WaitList w;
-        bool any_wait = false;
-        for (int q = 0; q < kMaxRanks; ++q) { tgt.data[q] = nullptr; tgt.flag[q] = nullptr; w.flag[q] = nullptr; }
+        unsigned int mask = 0;
         for (int q = 0; q < ctx->nranks; ++q) {
-            if (q == ctx->rank) continue;
-            if (A->needed_by[q]) {
-                tgt.data[q] = data_at(A->pb_peer[q], par, A->pb_half) + (size_t)ctx->rank * A->S;
-                tgt.flag[q] = flag_at(A->pb_peer[q], par, ctx->rank);
-            }
-            if (A->need_from[q]) { w.flag[q] = flag_at(A->pb_local, par, q); any_wait = true; }
+            if (q == ctx->rank || !A->xchg[q]) continue;
+            a.push_data[q] = data_at(A->pb_peer[q], par, A->pb_half) + (size_t)ctx->rank * A->S;
+            a.push_flag[q] = flag_at(A->pb_peer[q], par, ctx->rank);
+            mask |= 1u << q;
         }
-        int rc = launch_push(ctx, A->n_send, x, A->send_idx, tgt, 0, seq);
-        if (rc) return rc;
         A->halo = data_at(A->pb_local, par, A->pb_half);   // what the kernel gathers from
         a.xh = A->halo;
-        if (any_wait) {
-            // no separate wait launch: the consumer kernel starts on its interior rows at
-            // once and only blocks that gather remote columns poll the flags
-            unsigned int mask = 0;
-            for (int q = 0; q < ctx->nranks; ++q)
-                if (w.flag[q]) mask |= 1u << q;
-            a.blk_halo = A->blk_halo;
-            a.wait_flags = flag_at(A->pb_local, par, 0);
-            a.wait_mask = mask;
-            a.wait_seq = seq;
-        }
+        a.send_idx = A->send_idx;
+        a.n_send = (int)A->n_send;
+        a.nranks = ctx->nranks;
+        a.push_ticket = ctx->push_ticket;
+        a.push_seq = mask ? seq : 0;
+        a.blk_halo = A->blk_halo;
+        a.wait_flags = flag_at(A->pb_local, par, 0);
+        a.wait_mask = mask;
+        a.wait_seq = seq;
         return B200_OK;
     }
+    ProfScope prof(ctx, B200_PROF_COMM, A->n_send, ctx->nranks, 0);
     double *mine = A->halo + (size_t)ctx->rank * A->S;
     if (A->n_send) {
         const unsigned grid = (unsigned)((A->n_send + kThreads - 1) / kThreads);
@@ -243,138 +218,49 @@ int halo_exchange(b200_ctx_t ctx, b200_csr_t A, const double *x, HaloArgs &a) {
     return B200_OK;
 }
 
-// PROLONG operators: bring the coarse vector to every rank; returns the pointer to gather from.
-int coarse_to_all(b200_ctx_t ctx, b200_csr_t A, b200_vec_t xc, const double **px) {
-    ProfScope prof(ctx, B200_PROF_COMM, A->gl_cols, ctx->nranks, 1);
+// Row shares of a replicated result (gather_rows).  begin: where the kernel stores its rows.
+// Peer transport: straight into every rank's gather buffer (a.gather_*), local y = own buffer.
+// NCCL transport: into this rank's slot of A->ybuf.
+int gather_begin(b200_ctx_t ctx, b200_csr_t A, GatherArgs &g) {
+    g = GatherArgs();
     if (ctx->p2p) {
-        const int par = (int)(A->seq & 1);
-        const unsigned long long seq = ++A->seq;
-        PeerTargets tgt;
-        WaitList w;
-        bool any_wait = false;
-        for (int q = 0; q < kMaxRanks; ++q) { tgt.data[q] = nullptr; tgt.flag[q] = nullptr; w.flag[q] = nullptr; }
-        if (A->coarse_dist) {
-            B200_REQUIRE(xc->kind == B200_VK_DIST && (int64_t)xc->cap == A->coarse_B,
-                         "prolongation: coarse vector is not partitioned like the operator");
-            int rc = materialize(xc);
-            if (rc) return rc;
-            for (int q = 0; q < ctx->nranks; ++q) {
-                if (A->needed_by[q]) {
-                    tgt.data[q] = data_at(A->pb_peer[q], par, A->pb_half) + (size_t)ctx->rank * A->coarse_B;
-                    tgt.flag[q] = flag_at(A->pb_peer[q], par, ctx->rank);
-                }
-                if (A->need_from[q]) { w.flag[q] = flag_at(A->pb_local, par, q); any_wait = true; }
-            }
-            rc = launch_push(ctx, A->coarse_B, xc->ptr, nullptr, tgt, 0, seq);
-            if (rc) return rc;
-            *px = data_at(A->pb_local, par, A->pb_half);
-        } else if (ctx->rank == 0) {
-            B200_REQUIRE(xc->kind == B200_VK_LOCAL, "prolongation: coarse vector must live on rank 0");
-            int rc = materialize(xc);
-            if (rc) return rc;
-            bool any = false;
-            for (int q = 1; q < ctx->nranks; ++q)
-                if (A->needed_by[q]) {
-                    tgt.data[q] = data_at(A->pb_peer[q], par, A->pb_half);
-                    tgt.flag[q] = flag_at(A->pb_peer[q], par, 0);
-                    any = true;
-                }
-            if (any) {
-                rc = launch_push(ctx, A->gl_cols, xc->ptr, nullptr, tgt, 0, seq);
-                if (rc) return rc;
-            }
-            *px = xc->ptr;
-        } else {
-            if (A->need_from[0]) { w.flag[0] = flag_at(A->pb_local, par, 0); any_wait = true; }
-            *px = data_at(A->pb_local, par, A->pb_half);
+        const int par = (int)(A->gseq & 1);
+        const unsigned long long seq = ++A->gseq;
+        for (int q = 0; q < ctx->nranks; ++q) {
+            g.data[q] = data_at(A->gb_peer[q], par, A->gb_half) + (size_t)ctx->rank * A->row_B;
+            g.flag[q] = flag_at(A->gb_peer[q], par, ctx->rank);
         }
-        if (any_wait) {
-            wait_kernel<<<1, 32, 0, ctx->stream>>>(w, ctx->nranks, seq);
-            B200_CHECK_LAUNCH();
-            ctx->launches++;
-        }
+        g.on = 1;
+        g.nranks = ctx->nranks;
+        g.ticket = ctx->gather_ticket;
+        g.seq = seq;
+        g.y_local = g.data[ctx->rank];           // the plain store of a row goes here as well
+        g.data[ctx->rank] = nullptr;             // (so it is not stored twice)
         return B200_OK;
     }
-    if (A->coarse_dist) {
-        B200_REQUIRE(xc->kind == B200_VK_DIST && (int64_t)xc->cap == A->coarse_B,
-                     "prolongation: coarse vector is not partitioned like the operator");
-        int rc = materialize(xc);
-        if (rc) return rc;
-        B200_NCCL(nccl().AllGather(xc->ptr, A->cbuf, (size_t)A->coarse_B, ncclDouble, comm_of(ctx), ctx->stream));
-        *px = A->cbuf;
-        return B200_OK;
-    }
-    if (ctx->rank == 0) {
-        B200_REQUIRE(xc->kind == B200_VK_LOCAL, "prolongation: coarse vector must live on rank 0");
-        int rc = materialize(xc);
-        if (rc) return rc;
-        B200_NCCL(nccl().Broadcast(xc->ptr, xc->ptr, (size_t)A->gl_cols, ncclDouble, 0, comm_of(ctx), ctx->stream));
-        *px = xc->ptr;
-    } else {
-        B200_NCCL(nccl().Broadcast(A->cbuf, A->cbuf, (size_t)A->gl_cols, ncclDouble, 0, comm_of(ctx), ctx->stream));
-        *px = A->cbuf;
-    }
+    g.y_local = A->ybuf + (size_t)ctx->rank * A->row_B;
     return B200_OK;
 }
 
-// RESTRICT operators: combine the per-rank partial sums in A->cbuf into the coarse vector.
-int partials_to_coarse(b200_ctx_t ctx, b200_csr_t A, b200_vec_t yc) {
+// end: all shares -> the replicated vector y (every rank ends up with the complete result)
+int gather_end(b200_ctx_t ctx, b200_csr_t A, const GatherArgs &g, b200_vec_t y) {
     ProfScope prof(ctx, B200_PROF_COMM, A->gl_rows, ctx->nranks, 2);
+    const int64_t count = A->gl_rows;
     if (ctx->p2p) {
-        // every rank stores its partial sums for owner q directly into q's staging area;
-        // the owner adds the staged partials in rank order (deterministic)
-        const int par = (int)(A->seq & 1);
-        const unsigned long long seq = ++A->seq;
-        PeerTargets tgt;
+        const int par = (int)((A->gseq - 1) & 1);
         WaitList w;
-        for (int q = 0; q < kMaxRanks; ++q) { tgt.data[q] = nullptr; tgt.flag[q] = nullptr; w.flag[q] = nullptr; }
-        const int64_t seg = A->coarse_dist ? A->coarse_B : A->gl_rows;     // staged entries per source
-        const int nowners = A->coarse_dist ? ctx->nranks : 1;
-        bool any = false;
-        for (int q = 0; q < nowners; ++q)
-            if (A->needed_by[q]) {
-                tgt.data[q] = data_at(A->pb_peer[q], par, A->pb_half_owner) + (size_t)ctx->rank * seg;
-                tgt.flag[q] = flag_at(A->pb_peer[q], par, ctx->rank);
-                any = true;
-            }
-        if (any) {
-            int rc = launch_push(ctx, seg, A->cbuf, nullptr, tgt, A->coarse_dist ? seg : 0, seq);
-            if (rc) return rc;
-        }
-        const bool owner = A->coarse_dist || ctx->rank == 0;
-        if (owner) {
-            if (A->coarse_dist)
-                B200_REQUIRE(yc->kind == B200_VK_DIST && (int64_t)yc->cap == A->coarse_B,
-                             "restriction: coarse vector is not partitioned like the operator");
-            else
-                B200_REQUIRE(yc->kind == B200_VK_LOCAL, "restriction: coarse vector must live on rank 0");
-            for (int q = 0; q < ctx->nranks; ++q)
-                if (A->need_from[q]) w.flag[q] = flag_at(A->pb_local, par, q);
-            const int64_t count = (int64_t)yc->len;
-            if (count) {
-                const unsigned grid = (unsigned)((count + kThreads - 1) / kThreads);
-                reduce_sum_kernel<<<grid, kThreads, 0, ctx->stream>>>(
-                    count, data_at(A->pb_local, par, A->pb_half), seg, ctx->nranks, w, seq, wr(yc), nullptr);
-                B200_CHECK_LAUNCH();
-                ctx->launches++;
-            }
-            yc->zero_pending = false;
-        }
+        for (int q = 0; q < kMaxRanks; ++q) w.flag[q] = nullptr;
+        for (int q = 0; q < ctx->nranks; ++q) w.flag[q] = flag_at(A->gb_local, par, q);
+        const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((count + kThreads * 4 - 1) / (kThreads * 4),
+                                                                               (int64_t)ctx->sm_count * 4));
+        gather_copy_kernel<<<grid, kThreads, 0, ctx->stream>>>(count, data_at(A->gb_local, par, A->gb_half), w,
+                                                               ctx->nranks, g.seq, wr(y));
+        B200_CHECK_LAUNCH();
+        ctx->launches++;
         return B200_OK;
     }
-    if (A->coarse_dist) {
-        B200_REQUIRE(yc->kind == B200_VK_DIST && (int64_t)yc->cap == A->coarse_B,
-                     "restriction: coarse vector is not partitioned like the operator");
-        B200_NCCL(nccl().ReduceScatter(A->cbuf, wr(yc), (size_t)A->coarse_B, ncclDouble, ncclSum,
-                                       comm_of(ctx), ctx->stream));
-        return B200_OK;
-    }
-    double *dst = A->cbuf;
-    if (ctx->rank == 0) {
-        B200_REQUIRE(yc->kind == B200_VK_LOCAL, "restriction: coarse vector must live on rank 0");
-        dst = wr(yc);
-    }
-    B200_NCCL(nccl().Reduce(A->cbuf, dst, (size_t)A->gl_rows, ncclDouble, ncclSum, 0, comm_of(ctx), ctx->stream));
+    B200_NCCL(nccl().AllGather(g.y_local, A->ybuf, (size_t)A->row_B, ncclDouble, comm_of(ctx), ctx->stream));
+    B200_CUDA(cudaMemcpyAsync(wr(y), A->ybuf, (size_t)count * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     return B200_OK;
 }
 

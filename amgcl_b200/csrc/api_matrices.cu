@@ -71,6 +71,61 @@ static void build_plan(int64_t nrows, const Ptr *ptr, int lanes_opt, int nnz_cap
     plan.blk.push_back(make_int2((int)nrows, (int)nnz));
 }
 
+// Shared validation of a host CSR matrix (both the single-GPU and the distributed path run it
+// BEFORE anything reads through the arrays).
+template <class Ptr, class Col>
+static int csr_validate(int64_t nrows, int64_t ncols, const Ptr *ptr, const Col *col, bool have_val) {
+    B200_REQUIRE(nrows >= 0 && ncols >= 0, "negative matrix dimension");
+    B200_REQUIRE(ptr != nullptr, "null row pointer array");
+    const int64_t imax = std::numeric_limits<int32_t>::max();
+    if (nrows >= imax - 8 || ncols >= imax) return fail(B200_ERANGE, "matrix dimension exceeds int32");
+    B200_REQUIRE(ptr[0] == 0, "ptr[0] must be 0");
+    for (int64_t i = 1; i <= nrows; ++i)
+        if ((int64_t)ptr[i] < (int64_t)ptr[i - 1]) return fail(B200_EINVAL, "row pointers not monotone");
+    const int64_t nnz = (int64_t)ptr[nrows];
+    if (nnz < 0) return fail(B200_EINVAL, "negative number of non-zeros");
+    if (nnz >= imax - 8) return fail(B200_ERANGE, "number of non-zeros exceeds int32");
+    B200_REQUIRE(nnz == 0 || (col != nullptr && have_val), "null col/val array");
+    int bad = 0;
+#pragma omp parallel for reduction(| : bad) schedule(static)
+    for (int64_t e = 0; e < nnz; ++e) {
+        const int64_t c = (int64_t)col[e];
+        bad |= (c < 0 || c >= ncols) ? 1 : 0;
+    }
+    if (bad) return fail(B200_EINVAL, "column index out of range");
+    return B200_OK;
+}
+
+// Host -> device copy of `count` elements through two pinned staging buffers of the context,
+// converting Src -> Dst on the way (index narrowing).  The conversion runs on all host threads
+// and overlaps the DMA of the previous chunk; a plain cudaMemcpy from pageable memory is staged
+// by the driver on one thread at a fraction of the PCIe rate.
+template <class Dst, class Src>
+static cudaError_t staged_upload(b200_ctx_t ctx, Dst *dst, const Src *src, size_t count) {
+    const size_t stage_bytes = (size_t)32 << 20;
+    cudaError_t rc = cudaSuccess;
+    for (int k = 0; k < 2 && rc == cudaSuccess; ++k) {
+        if (!ctx->stage_host[k]) rc = cudaHostAlloc(&ctx->stage_host[k], stage_bytes, cudaHostAllocDefault);
+        if (rc == cudaSuccess && !ctx->stage_event[k])
+            rc = cudaEventCreateWithFlags(&ctx->stage_event[k], cudaEventDisableTiming);
+    }
+    if (rc != cudaSuccess) return rc;
+    const size_t chunk = stage_bytes / sizeof(Dst);
+    int k = 0;
+    for (size_t off = 0; off < count && rc == cudaSuccess; off += chunk, k ^= 1) {
+        const size_t m = std::min(chunk, count - off);
+        rc = cudaEventSynchronize(ctx->stage_event[k]);        // the buffer's previous DMA is done
+        if (rc != cudaSuccess) break;
+        Dst *buf = static_cast<Dst *>(ctx->stage_host[k]);
+        const Src *from = src + off;
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < (int64_t)m; ++i) buf[i] = (Dst)from[i];
+        rc = cudaMemcpyAsync(dst + off, buf, m * sizeof(Dst), cudaMemcpyHostToDevice, ctx->stream);
+        if (rc == cudaSuccess) rc = cudaEventRecord(ctx->stage_event[k], ctx->stream);
+    }
+    return rc;
+}
+
 // Upload one CSR matrix exactly as the kernels will see it (indices narrowed to int32,
 // row-block plan built).  Single-GPU matrices come straight through here; the
 // distributed kinds hand in the local part produced by dist.cuh.
@@ -80,29 +135,15 @@ static int csr_upload(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *p
     CHECK_CTX(ctx);
     B200_REQUIRE(out != nullptr, "null output pointer");
     *out = nullptr;
-    B200_REQUIRE(nrows >= 0 && ncols >= 0, "negative matrix dimension");
-    B200_REQUIRE(ptr != nullptr, "null row pointer array");
-    const int64_t imax = std::numeric_limits<int32_t>::max();
-    if (nrows >= imax - 8 || ncols >= imax) return fail(B200_ERANGE, "matrix dimension exceeds int32");
-    B200_REQUIRE(ptr[0] == 0, "ptr[0] must be 0");
+    int vrc = csr_validate(nrows, ncols, ptr, col, val != nullptr);
+    if (vrc) return vrc;
     const int64_t nnz = (int64_t)ptr[nrows];
-    if (nnz < 0) return fail(B200_EINVAL, "negative number of non-zeros");
-    if (nnz >= imax - 8) return fail(B200_ERANGE, "number of non-zeros exceeds int32");
-    B200_REQUIRE(nnz == 0 || (col != nullptr && val != nullptr), "null col/val array");
     GUARD(ctx);
 
-    // ---- narrow indices, validate ------------------------------------------
-    std::vector<int32_t> hptr((size_t)nrows + 1), hcol((size_t)nnz);
-    for (int64_t i = 0; i <= nrows; ++i) {
-        const int64_t p = (int64_t)ptr[i];
-        if (i && p < (int64_t)ptr[i - 1]) return fail(B200_EINVAL, "row pointers not monotone");
-        hptr[(size_t)i] = (int32_t)p;
-    }
-    for (int64_t e = 0; e < nnz; ++e) {
-        const int64_t c = (int64_t)col[e];
-        if (c < 0 || c >= ncols) return fail(B200_EINVAL, "column index out of range");
-        hcol[(size_t)e] = (int32_t)c;
-    }
+    // ---- narrow the row pointers (the plan needs them on the host) ---------------------
+    std::vector<int32_t> hptr((size_t)nrows + 1);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i <= nrows; ++i) hptr[(size_t)i] = (int32_t)ptr[i];
 
     // ---- row-block plan -------------------------------------------------------
     RowBlockPlan plan;
@@ -147,13 +188,10 @@ static int csr_upload(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *p
     CSR_CUDA(cudaMemsetAsync(A->ptr, 0, ptr_bytes, ctx->stream));
     CSR_CUDA(cudaMemsetAsync(A->col, 0, col_bytes, ctx->stream));
     CSR_CUDA(cudaMemsetAsync(A->val, 0, val_bytes, ctx->stream));
-    CSR_CUDA(cudaMemcpyAsync(A->ptr, hptr.data(), ((size_t)nrows + 1) * sizeof(int),
-                             cudaMemcpyHostToDevice, ctx->stream));
+    CSR_CUDA(staged_upload(ctx, A->ptr, hptr.data(), (size_t)nrows + 1));
     if (nnz) {
-        CSR_CUDA(cudaMemcpyAsync(A->col, hcol.data(), (size_t)nnz * sizeof(int),
-                                 cudaMemcpyHostToDevice, ctx->stream));
-        CSR_CUDA(cudaMemcpyAsync(A->val, val, (size_t)nnz * sizeof(Val),
-                                 cudaMemcpyHostToDevice, ctx->stream));
+        CSR_CUDA(staged_upload(ctx, A->col, col, (size_t)nnz));      // narrowed to int32 on the way
+        CSR_CUDA(staged_upload(ctx, static_cast<Val *>(A->val), val, (size_t)nnz));
     }
     CSR_CUDA(cudaMemcpyAsync(A->blk, blk.data(), blk_bytes, cudaMemcpyHostToDevice, ctx->stream));
     CSR_CUDA(cudaStreamSynchronize(ctx->stream));   // host staging buffers die here
@@ -172,9 +210,11 @@ static void csr_free(b200_csr_t A) {
     if (A->send_idx) cudaFree(A->send_idx);
     if (A->blk_halo) cudaFree(A->blk_halo);
     if (A->halo_owned) cudaFree(A->halo_owned);
-    if (A->cbuf) cudaFree(A->cbuf);
+    if (A->ybuf) cudaFree(A->ybuf);
+    if (A->blk_order) cudaFree(A->blk_order);
     if (A->scratch64) cudaFree(A->scratch64);
     if (A->pb_local) peer_release(A->ctx, A->pb_local, A->pb_peer);
+    if (A->gb_local) peer_release(A->ctx, A->gb_local, A->gb_peer);
     delete A;
 }
 
@@ -189,6 +229,9 @@ static int csr_create_f32(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Pt
     return csr_upload(ctx, nrows, ncols, ptr, col, val, out);
 }
 
+// The public constructor.  On a distributed context (dist.cuh) the shape decides how the
+// operator is shared out: a dimension >= the threshold belongs to a partitioned level, a smaller
+// one to a replicated level; a rank always keeps whole rows.
 template <class Ptr, class Col>
 static int csr_create(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *ptr,
                       const Col *col, const double *val, b200_csr_t *out) {
@@ -198,44 +241,28 @@ static int csr_create(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *p
     *out = nullptr;
     if (!ctx->dist) return csr_upload(ctx, nrows, ncols, ptr, col, val, out);
 
-    B200_REQUIRE(nrows >= 0 && ncols >= 0 && ptr != nullptr && ptr[0] == 0, "bad CSR input");
+    int rc = csr_validate(nrows, ncols, ptr, col, val != nullptr);
+    if (rc) return rc;
     const int64_t nnz = (int64_t)ptr[nrows];
-    B200_REQUIRE(nnz == 0 || (col != nullptr && val != nullptr), "null col/val array");
     const int64_t T = ctx->dist_min_rows;
     const bool rd = nrows >= T, cd = ncols >= T;
-    int kind = B200_CK_LOCAL;
-    if (rd && cd && nrows == ncols) kind = B200_CK_SQUARE;
-    else if (rd && (!cd || nrows > ncols)) kind = B200_CK_PROLONG;
-    else if (cd && (!rd || ncols > nrows)) kind = B200_CK_RESTRICT;
-
-    if (kind == B200_CK_LOCAL) {
-        if (ctx->rank == 0) return csr_upload(ctx, nrows, ncols, ptr, col, val, out);
-        b200_csr_s *G = new (std::nothrow) b200_csr_s();     // ghost: lives on rank 0
-        if (!G) return fail(B200_ENOMEM, "out of host memory");
-        G->ctx = ctx; G->kind = B200_CK_GHOST;
-        G->gl_rows = nrows; G->gl_cols = ncols; G->gl_nnz = nnz;
-        *out = G;
-        return B200_OK;
-    }
-    for (int64_t e = 0; e < nnz; ++e)
-        if ((int64_t)col[e] < 0 || (int64_t)col[e] >= ncols)
-            return fail(B200_EINVAL, "column index out of range");
+    if (!rd && !cd) return csr_upload(ctx, nrows, ncols, ptr, col, val, out);   // replicated level
     GUARD(ctx);
 
-    SplitMatrix sp;
+    // rows: the rank's block of a partitioned result, or its share of a replicated one
     const int P = ctx->nranks, rank = ctx->rank;
-    if (kind == B200_CK_SQUARE) split_square(Partition(nrows, P), rank, ptr, col, sp);
-    else if (kind == B200_CK_PROLONG) split_prolong(Partition(nrows, P), rank, ncols, ptr, col, sp);
-    else split_restrict(Partition(ncols, P), rank, nrows, ptr, col, val, sp);
+    const Partition rows(nrows, P), cols(ncols, P);
+    SplitMatrix sp;
+    split_rows(rows, cols, cd, rank, ptr, col, sp);
 
     b200_csr_t A = nullptr;
-    const double *lval = sp.val_contiguous ? val + sp.val_offset : sp.val.data();
-    int64_t kernel_cols = sp.ncols;
-    if (kind == B200_CK_PROLONG && cd) kernel_cols = Partition(ncols, P).B * P;   // gathered blocks
-    int rc = csr_upload(ctx, sp.nrows, kernel_cols, sp.ptr.data(), sp.col.data(), lval, &A);
+    rc = csr_upload(ctx, sp.nrows, sp.ncols, sp.ptr.data(), sp.col.data(), val + sp.val_offset, &A);
     if (rc) return rc;
-    A->kind = kind;
+    A->kind = cd ? B200_CK_HALO : B200_CK_LOCAL;
     A->gl_rows = nrows; A->gl_cols = ncols; A->gl_nnz = nnz;
+    A->rows_dist = rd; A->cols_dist = cd;
+    A->gather_rows = !rd;
+    A->row_off = rows.lo(rank); A->row_B = rows.B;
     A->n_loc = sp.n_loc;
 #define DCSR_CUDA(call)                                                        \
     do {                                                                       \
@@ -245,22 +272,27 @@ static int csr_create(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *p
             return cuda_fail(rc__, #call, __FILE__, __LINE__);                 \
         }                                                                      \
     } while (0)
-    if (kind == B200_CK_SQUARE) {
+    if (cd) {
         A->S = sp.S;
         A->n_send = (int64_t)sp.send_idx.size();
         std::vector<int32_t> idx(sp.send_idx.begin(), sp.send_idx.end());
         DCSR_CUDA(cudaMalloc(&A->send_idx, std::max<size_t>(1, idx.size()) * sizeof(int)));
-        DCSR_CUDA(cudaMalloc(&A->halo_owned, std::max<size_t>(2, (size_t)(P * sp.S)) * sizeof(double)));
+        const size_t halo_n = std::max<size_t>(2, (size_t)(P * sp.S));
+        DCSR_CUDA(cudaMalloc(&A->halo_owned, halo_n * sizeof(double)));
         A->halo = A->halo_owned;
-        DCSR_CUDA(cudaMemsetAsync(A->halo, 0, std::max<size_t>(2, (size_t)(P * sp.S)) * sizeof(double), ctx->stream));
+        DCSR_CUDA(cudaMemsetAsync(A->halo, 0, halo_n * sizeof(double), ctx->stream));
         if (!idx.empty())
             DCSR_CUDA(cudaMemcpyAsync(A->send_idx, idx.data(), idx.size() * sizeof(int),
                                       cudaMemcpyHostToDevice, ctx->stream));
         A->bytes += idx.size() * sizeof(int) + (size_t)(P * sp.S) * sizeof(double);
-        // which row blocks touch the halo (the same plan csr_upload just built)
+        // which row blocks touch the halo (the same plan csr_upload just built), and the walk
+        // order that puts them last so the peers' pushes land while interior rows are computed
         RowBlockPlan plan;
         build_plan(sp.nrows, sp.ptr.data(), A->lanes, A->nnz_cap, plan);
-        std::vector<unsigned char> bh((size_t)std::max<int64_t>(1, A->nblocks), 0);
+        const size_t nb = (size_t)std::max<int64_t>(1, A->nblocks);
+        std::vector<unsigned char> bh(nb, 0);
+        std::vector<int> order;
+        order.reserve(nb);
         if ((int64_t)plan.blk.size() - 1 == A->nblocks) {
             for (int64_t b = 0; b < A->nblocks; ++b) {
                 const int64_t e0 = plan.blk[(size_t)b].y, e1 = plan.blk[(size_t)b + 1].y;
@@ -270,89 +302,53 @@ static int csr_create(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *p
         } else {
             std::fill(bh.begin(), bh.end(), 1);      // cannot happen; be safe: every block waits
         }
+        for (int64_t b = 0; b < A->nblocks; ++b) if (!bh[(size_t)b]) order.push_back((int)b);
+        for (int64_t b = 0; b < A->nblocks; ++b) if (bh[(size_t)b]) order.push_back((int)b);
+        if (order.empty()) order.push_back(0);
         DCSR_CUDA(cudaMalloc(&A->blk_halo, bh.size()));
+        DCSR_CUDA(cudaMalloc(&A->blk_order, order.size() * sizeof(int)));
         DCSR_CUDA(cudaMemcpyAsync(A->blk_halo, bh.data(), bh.size(), cudaMemcpyHostToDevice, ctx->stream));
+        DCSR_CUDA(cudaMemcpyAsync(A->blk_order, order.data(), order.size() * sizeof(int),
+                                  cudaMemcpyHostToDevice, ctx->stream));
         DCSR_CUDA(cudaStreamSynchronize(ctx->stream));
-    } else {
-        // coarse-side buffer: gathered input of P, partial sums of R
-        const bool coarse_dist = (kind == B200_CK_PROLONG) ? cd : rd;
-        const int64_t nc = (kind == B200_CK_PROLONG) ? ncols : nrows;
-        A->coarse_dist = coarse_dist;
-        A->coarse_B = coarse_dist ? Partition(nc, P).B : nc;
-        A->cbuf_n = coarse_dist ? A->coarse_B * P : nc;
-        DCSR_CUDA(cudaMalloc(&A->cbuf, ((size_t)A->cbuf_n + 2) * sizeof(double)));
-        DCSR_CUDA(cudaMemsetAsync(A->cbuf, 0, ((size_t)A->cbuf_n + 2) * sizeof(double), ctx->stream));
-        A->bytes += (size_t)A->cbuf_n * sizeof(double);
+        // who exchanges with whom: the symmetric closure of "rows of p reference columns of o"
+        // (identical on every rank: derived from the global matrix).  A pair exchanges flags in
+        // BOTH directions even if data flows one way only: that is what bounds how far one
+        // rank can run ahead of another, i.e. what makes two parity buffers enough (peer.cuh).
+        for (int q = 0; q < P; ++q)
+            A->xchg[q] = q != rank && (sp.dep[(size_t)rank * P + q] || sp.dep[(size_t)q * P + rank]);
+    }
+    if (A->gather_rows && !ctx->p2p) {
+        DCSR_CUDA(cudaMalloc(&A->ybuf, ((size_t)P * (size_t)rows.B + 2) * sizeof(double)));
+        DCSR_CUDA(cudaMemsetAsync(A->ybuf, 0, ((size_t)P * (size_t)rows.B + 2) * sizeof(double), ctx->stream));
+        A->bytes += (size_t)P * (size_t)rows.B * sizeof(double);
     }
     DCSR_CUDA(cudaStreamSynchronize(ctx->stream));
 #undef DCSR_CUDA
-
-    // who exchanges with whom (identical on every rank: derived from the global matrix)
-    {
-        std::vector<unsigned char> dep;
-        const int me = rank;
-        if (kind == B200_CK_SQUARE) {
-            const Partition part(nrows, P);
-            dependency_matrix(part, part, ptr, col, dep);
-            for (int q = 0; q < P; ++q) {
-                A->need_from[q] = q != me && dep[(size_t)me * P + q];
-                A->needed_by[q] = q != me && dep[(size_t)q * P + me];
-            }
-        } else if (kind == B200_CK_PROLONG) {
-            // consumer p (fine rows) needs the coarse entries owned by o
-            const Partition fine(nrows, P);
-            const Partition coarse = A->coarse_dist ? Partition(ncols, P) : Partition(ncols, 1);
-            if (A->coarse_dist) {
-                dependency_matrix(fine, coarse, ptr, col, dep);
-                for (int q = 0; q < P; ++q) {
-                    A->need_from[q] = dep[(size_t)me * P + q];
-                    A->needed_by[q] = dep[(size_t)q * P + me];
-                }
-            } else {
-                for (int q = 0; q < P; ++q) {
-                    const bool has = (int64_t)ptr[fine.hi(q)] > (int64_t)ptr[fine.lo(q)];
-                    if (me == 0) A->needed_by[q] = q != 0 && has;
-                    if (q == 0) A->need_from[0] = me != 0 && (int64_t)ptr[fine.hi(me)] > (int64_t)ptr[fine.lo(me)];
-                }
-            }
-        } else {
-            // producer r (fine columns) contributes to the coarse rows owned by o
-            const Partition fine(ncols, P);
-            if (A->coarse_dist) {
-                const Partition coarse(nrows, P);
-                dependency_matrix(coarse, fine, ptr, col, dep);     // dep[o][r]
-                for (int q = 0; q < P; ++q) {
-                    A->need_from[q] = dep[(size_t)me * P + q];       // r = q contributes to me
-                    A->needed_by[q] = dep[(size_t)q * P + me];       // I contribute to owner q
-                }
-            } else {
-                std::vector<unsigned char> has((size_t)P, 0);
-                for (int64_t e = 0; e < nnz; ++e) has[(size_t)fine.owner((int64_t)col[e])] = 1;
-                A->needed_by[0] = has[(size_t)me];
-                if (me == 0)
-                    for (int q = 0; q < P; ++q) A->need_from[q] = has[(size_t)q];
-            }
-        }
-    }
     if (ctx->p2p) {
-        size_t half = 16;
-        if (kind == B200_CK_SQUARE) half = (size_t)P * (size_t)A->S * sizeof(double);
-        else if (kind == B200_CK_PROLONG) half = (size_t)A->cbuf_n * sizeof(double);
-        else if (A->coarse_dist) half = (size_t)P * (size_t)A->coarse_B * sizeof(double);
-        else if (rank == 0) half = (size_t)P * (size_t)nrows * sizeof(double);
-        half = (half + 255) & ~size_t(255);
-        A->pb_half = half;
-        // layout of the buffer a producer writes INTO (the owner's): equal to mine except for
-        // a restriction onto a rank-0-only level, where only rank 0 holds the staging area
-        A->pb_half_owner = half;
-        if (kind == B200_CK_RESTRICT && !A->coarse_dist)
-            A->pb_half_owner = (((size_t)P * (size_t)nrows * sizeof(double)) + 255) & ~size_t(255);
-        int rc2 = peer_alloc(ctx, kFlagBytes + 2 * half, &A->pb_local, A->pb_peer);
-        if (rc2) {
-            csr_free(A);
-            return rc2;
+        // collective allocations: every rank reaches them for every distributed operator
+        if (cd) {
+            size_t half = (size_t)P * (size_t)A->S * sizeof(double);
+            half = (std::max<size_t>(half, 16) + 255) & ~size_t(255);
+            A->pb_half = half;
+            rc = peer_alloc(ctx, kFlagBytes + 2 * half, &A->pb_local, A->pb_peer);
+            if (rc) {
+                csr_free(A);
+                return rc;
+            }
+            A->bytes += kFlagBytes + 2 * half;
         }
-        A->bytes += kFlagBytes + 2 * half;
+        if (A->gather_rows) {
+            size_t half = (size_t)P * (size_t)rows.B * sizeof(double);
+            half = (std::max<size_t>(half, 16) + 255) & ~size_t(255);
+            A->gb_half = half;
+            rc = peer_alloc(ctx, kFlagBytes + 2 * half, &A->gb_local, A->gb_peer);
+            if (rc) {
+                csr_free(A);
+                return rc;
+            }
+            A->bytes += kFlagBytes + 2 * half;
+        }
     }
     *out = A;
     return B200_OK;
@@ -366,7 +362,7 @@ template <int MODE, int L, bool HALO, class P>
 static int launch_csr_LH(b200_ctx_t ctx, b200_csr_t A, const CsrArgsT<P> &args) {
     constexpr bool fp64 = std::is_same<P, PrecDD>::value;
     const StageLayout lay = stage_layout(A->rows_cap, A->nnz_cap, (int)sizeof(typename P::TV));
-    if (fp64 && ctx->opt_spmv_variant == 0) {
+    if (fp64 && ctx->opt_spmv_variant == 0 && !HALO) {
         const int smem = kHeaderBytes + lay.bytes;
         static bool attr_set[64] = {};   // per instantiation and device
         if (!attr_set[ctx->device & 63]) {
@@ -443,7 +439,11 @@ static int halo_into(b200_ctx_t ctx, b200_csr_t A, CsrArgs &a) {
     const int rc = halo_exchange(ctx, A, a.x, h);
     if (rc) return rc;
     a.xh = h.xh; a.nloc = h.nloc;
+    a.blk_order = h.blk_order;
     a.blk_halo = h.blk_halo; a.wait_flags = h.wait_flags; a.wait_mask = h.wait_mask; a.wait_seq = h.wait_seq;
+    a.send_idx = h.send_idx; a.n_send = h.n_send; a.nranks = h.nranks;
+    for (int q = 0; q < kMaxRanks; ++q) { a.push_data[q] = h.push_data[q]; a.push_flag[q] = h.push_flag[q]; }
+    a.push_ticket = h.push_ticket; a.push_seq = h.push_seq;
     return B200_OK;
 }
 
@@ -558,8 +558,8 @@ template <class P>
 static void apply_req(b200_ctx_t ctx, b200_csr_t A, CsrArgsT<P> &a, DotReq *req) {
     if (!req || !req->ndot || ctx->opt_spmv_variant != 1 || a.nblocks == 0) return;
     if (!std::is_same<typename P::TY, double>::value) return;
-    // partitioned operator: every rank launches, the finishing CTAs all-reduce over the peers
-    const bool across = A->kind == B200_CK_SQUARE;
+    // partitioned result: every rank launches, the finishing CTAs all-reduce over the peers
+    const bool across = A->rows_dist;
     if (across && !ctx->scal_x_table) return;       // NCCL transport: separate reduction instead
     a.ndot = req->ndot;
     a.w = req->w;
@@ -613,7 +613,6 @@ static int spmv_impl(b200_ctx_t ctx, double alpha, b200_csr_t A, b200_vec_t x, d
     B200_REQUIRE((int64_t)x->n == A->gl_cols, "spmv: x size != matrix columns");
     B200_REQUIRE((int64_t)y->n == A->gl_rows, "spmv: y size != matrix rows");
     B200_REQUIRE(x != y && (x->ptr != y->ptr || !x->ptr), "spmv: x and y must not alias");
-    if (A->kind == B200_CK_GHOST) return B200_OK;          // operator lives on rank 0
     GUARD(ctx);
     if (A->dtype == B200_F32) {
         // FP32 operator (mixed-precision hierarchy): single GPU, persistent ring kernels
@@ -626,31 +625,33 @@ static int spmv_impl(b200_ctx_t ctx, double alpha, b200_csr_t A, b200_vec_t x, d
     if (!all64({x, y})) return B200_BAD_MIX("spmv");
     CsrArgs a = base_args(A);
     a.alpha = alpha; a.beta = beta;
-    int rc;
-    if (A->kind == B200_CK_PROLONG) {
-        B200_REQUIRE(y->kind == B200_VK_DIST, "prolongation: y must be a partitioned vector");
-        rc = coarse_to_all(ctx, A, x, &a.x);
+    int rc = rd(x, &a.x);
+    if (rc) return rc;
+    // distributed context: x / y are blocks of partitioned vectors or whole replicated ones
+    if (ctx->dist) {
+        B200_REQUIRE((x->kind == B200_VK_DIST) == A->cols_dist && (y->kind == B200_VK_DIST) == A->rows_dist,
+                     "spmv: vectors are not laid out like the operator (partitioned vs replicated)");
+    }
+    if (A->kind == B200_CK_HALO) {
+        rc = halo_into(ctx, A, a);
         if (rc) return rc;
-    } else if (A->kind == B200_CK_RESTRICT) {
-        B200_REQUIRE(beta == 0.0, "restriction on a distributed context needs beta == 0");
-        B200_REQUIRE(x->kind == B200_VK_DIST, "restriction: x must be a partitioned vector");
-        rc = rd(x, &a.x);
+    }
+    if (A->gather_rows) {
+        // y is replicated, x partitioned: this rank computes its share of the rows, the shares
+        // are all-gathered (R onto a small level)
+        B200_REQUIRE(beta == 0.0 || y->zero_pending, "spmv onto a replicated level needs beta == 0");
+        GatherArgs g;
+        rc = gather_begin(ctx, A, g);
         if (rc) return rc;
-        a.y = A->cbuf;
+        a.gather_on = g.on; a.nranks = ctx->nranks;
+        for (int q = 0; q < kMaxRanks; ++q) { a.gather_data[q] = g.data[q]; a.gather_flag[q] = g.flag[q]; }
+        a.gather_ticket = g.ticket; a.gather_seq = g.seq;
+        a.y = g.y_local;
         rc = launch_csr<MODE_SPMV>(ctx, A, a);
         if (rc) return rc;
-        return partials_to_coarse(ctx, A, y);
-    } else {
-        rc = rd(x, &a.x);
-        if (rc) return rc;
-        if (A->kind == B200_CK_SQUARE) {
-            B200_REQUIRE(x->kind == B200_VK_DIST && y->kind == B200_VK_DIST,
-                         "spmv: vectors must be partitioned like the operator");
-            rc = halo_into(ctx, A, a);
-            if (rc) return rc;
-        }
+        return gather_end(ctx, A, g, y);
     }
-    if (A->kind == B200_CK_LOCAL || A->kind == B200_CK_SQUARE) apply_req(ctx, A, a, req);
+    apply_req(ctx, A, a, req);
     if (beta == 0.0 || y->zero_pending) {
         a.y = wr(y);
         return launch_csr<MODE_SPMV>(ctx, A, a);
@@ -668,9 +669,7 @@ static int residual_impl(b200_ctx_t ctx, b200_vec_t f, b200_csr_t A, b200_vec_t 
     B200_REQUIRE((int64_t)f->n == A->gl_rows && (int64_t)r->n == A->gl_rows,
                  "residual: rhs/r size != matrix rows");
     B200_REQUIRE(x != r && (x->ptr != r->ptr || !x->ptr), "residual: x and r must not alias");
-    if (A->kind == B200_CK_GHOST) return B200_OK;
-    B200_REQUIRE(A->kind == B200_CK_LOCAL || A->kind == B200_CK_SQUARE,
-                 "residual: operator must be square");
+    B200_REQUIRE(A->gl_rows == A->gl_cols && !A->gather_rows, "residual: operator must be square");
     GUARD(ctx);
     if (A->dtype == B200_F32) {
         if (all32({f, x, r})) return residual_local<PrecFF>(ctx, f, A, x, r);
@@ -684,7 +683,7 @@ static int residual_impl(b200_ctx_t ctx, b200_vec_t f, b200_csr_t A, b200_vec_t 
     if (rc) return rc;
     rc = rd(f, &a.f);
     if (rc) return rc;
-    if (A->kind == B200_CK_SQUARE) {
+    if (A->kind == B200_CK_HALO) {
         B200_REQUIRE(x->kind == B200_VK_DIST && f->kind == B200_VK_DIST && r->kind == B200_VK_DIST,
                      "residual: vectors must be partitioned like the operator");
         rc = halo_into(ctx, A, a);
@@ -708,7 +707,7 @@ int spmv_with_dots(b200_ctx_t ctx, b200_csr_t A, b200_vec_t x, b200_vec_t y, b20
     }
     req.w = pw;
     int rc = spmv_impl(ctx, 1.0, A, x, 0.0, y, &req);
-    if (rc || req.done || A->kind == B200_CK_GHOST) return rc;
+    if (rc || req.done) return rc;
     return launch_dot_slots(ctx, y, w, ndot == 2 ? y : nullptr, slots);
 }
 
@@ -717,7 +716,7 @@ int residual_with_norm(b200_ctx_t ctx, b200_vec_t f, b200_csr_t A, b200_vec_t x,
     DotReq req;
     req.ndot = 1; req.slots = &slot; req.host_mask = 1u;
     int rc = residual_impl(ctx, f, A, x, r, &req);
-    if (rc || req.done || A->kind == B200_CK_GHOST) return rc;
+    if (rc || req.done) return rc;
     return launch_dot_slots(ctx, r, r, nullptr, &slot, 1u);
 }
 } // namespace b200
@@ -763,7 +762,7 @@ extern "C" int b200_relax(b200_ctx_t ctx, b200_csr_t A, b200_vec_t rhs, b200_vec
                      same_layout(x, tmp),
                  "relax: vector size != matrix rows");
     B200_REQUIRE(x != tmp && x != rhs && tmp != rhs, "relax: x, tmp and rhs must be distinct vectors");
-    if (A->kind == B200_CK_GHOST) return B200_OK;
+    B200_REQUIRE(!A->gather_rows, "relax: operator must be square");
     B200_REQUIRE(x->ptr != tmp->ptr, "relax: x and tmp must not alias");
     GUARD(ctx);
 
@@ -842,7 +841,7 @@ extern "C" int b200_relax(b200_ctx_t ctx, b200_csr_t A, b200_vec_t rhs, b200_vec
     CsrArgs a = base_args(A);
     rc = rd(x, &a.x);
     if (rc) return rc;
-    if (A->kind == B200_CK_SQUARE) {
+    if (A->kind == B200_CK_HALO) {
         B200_REQUIRE(x->kind == B200_VK_DIST, "relax: vectors must be partitioned like the operator");
         rc = halo_into(ctx, A, a);
         if (rc) return rc;

@@ -30,14 +30,8 @@ static int vec_create_typed(b200_ctx_t ctx, size_t n, int dtype, b200_vec_t *out
         v->off = (size_t)part.lo(ctx->rank);
         v->len = (size_t)part.count(ctx->rank);
         v->cap = (size_t)part.B;
-    } else if (ctx->dist && ctx->rank != 0) {
-        v->kind = B200_VK_GHOST;      // the object lives on rank 0; operations here are no-ops
-        v->len = 0;
-        v->cap = 0;
-        v->zero_pending = false;
-        *out = v;
-        return B200_OK;
     } else {
+        // single GPU, or a level below the partition threshold: replicated on every rank
         v->kind = B200_VK_LOCAL;
         v->len = n;
         v->cap = n;

@@ -99,6 +99,10 @@ struct b200_ctx_s {
     int           product_slot0 = -1;     // first of the 4 table slots the products rotate through
     std::vector<size_t> krylov_sizes;     // sizes of the live Krylov workspaces (b200_krylov_*)
 
+    // pinned staging for uploads (csr_upload): two buffers, ping-pong
+    void        *stage_host[2]  = {};
+    cudaEvent_t  stage_event[2] = {};
+
     // optional per-launch timing of the CSR streaming kernels (b200_profile_*)
     bool                      profiling = false;
     std::vector<cudaEvent_t>  prof_events;      // pool, used pairwise
@@ -116,6 +120,7 @@ struct b200_ctx_s {
     // peer-memory exchange (peer.cuh): enabled when CUDA IPC between the ranks works
     bool     p2p           = false;
     unsigned int *push_ticket = nullptr;    // device, self-resetting
+    unsigned int *gather_ticket = nullptr;  // device, self-resetting (row-share gathers)
     void    *ipc_dev       = nullptr;       // device staging for IPC handle exchange
     void    *dot_pb_local  = nullptr;       // [flags | 2 x 16 doubles] shared with the peers
     void    *dot_pb_peer[16] = {};
@@ -166,8 +171,9 @@ struct b200_vec_s {
                                        // may change behind the library's back
 };
 
-enum { B200_CK_LOCAL = 0, B200_CK_SQUARE = 1, B200_CK_PROLONG = 2, B200_CK_RESTRICT = 3,
-       B200_CK_GHOST = 4 };
+// operators on a multi-GPU context (dist.cuh): LOCAL needs no exchange, HALO gathers remote
+// columns from the all-gathered boundary values of a partitioned vector
+enum { B200_CK_LOCAL = 0, B200_CK_HALO = 1 };
 
 struct b200_csr_s {
     b200_ctx_t ctx   = nullptr;
@@ -175,25 +181,30 @@ struct b200_csr_s {
     // distributed operators (dist.cuh)
     int        kind    = B200_CK_LOCAL;
     int64_t    gl_rows = 0, gl_cols = 0, gl_nnz = 0;   // global shape (what the API reports)
-    int64_t    n_loc   = 0;       // SQUARE: owned rows == local columns
-    int64_t    S       = 0;       // SQUARE: halo slots per rank
-    int64_t    n_send  = 0;       // SQUARE: entries this rank contributes
-    int       *send_idx = nullptr;// SQUARE: [n_send] local indices to pack
-    double    *halo    = nullptr; // SQUARE: [nranks*S] boundary values the kernel gathers from
-    double    *halo_owned = nullptr; //       NCCL path: private buffer (peer path: inside pb)
-    double    *cbuf    = nullptr; // PROLONG: gathered coarse vector; RESTRICT: partial sums
-    int64_t    cbuf_n  = 0;
-    bool       coarse_dist = false;   // the coarse side of P/R is itself partitioned
-    int64_t    coarse_B = 0;          // its uniform block
+    bool       rows_dist = false;     // y is a partitioned vector (else replicated / single GPU)
+    bool       cols_dist = false;     // x is a partitioned vector
+    bool       gather_rows = false;   // y replicated but x partitioned: this rank computes a share
+                                      //   of the rows, the shares are all-gathered
+    int64_t    row_off = 0, row_B = 0;//   ... first row and uniform size of a share
+    int64_t    n_loc   = 0;       // HALO: length of this rank's block of x (local columns)
+    int64_t    S       = 0;       // HALO: halo slots per rank
+    int64_t    n_send  = 0;       // HALO: entries this rank contributes
+    int       *send_idx = nullptr;// HALO: [n_send] local indices to pack
+    double    *halo    = nullptr; // HALO: [nranks*S] boundary values the kernel gathers from
+    double    *halo_owned = nullptr; //     NCCL transport: private buffer (peer transport: inside pb)
+    double    *ybuf    = nullptr; // gather_rows, NCCL transport: [nranks*row_B] all-gather buffer
     // peer-memory exchange state (peer.cuh); layout: [flags 256 B | parity 0 | parity 1]
-    void      *pb_local = nullptr;
+    void      *pb_local = nullptr;    // halo of x
     void      *pb_peer[16] = {};
-    size_t     pb_half  = 0;          // bytes of one parity buffer (mine)
-    size_t     pb_half_owner = 0;     // ... of the buffer my contributions are written into
-    unsigned long long seq = 0;       // exchanges done so far (same on every rank)
-    unsigned char *blk_halo = nullptr;  // SQUARE: [nblocks] block gathers remote columns
-    bool       need_from[16] = {};    // ranks whose data this rank consumes
-    bool       needed_by[16] = {};    // ranks that consume this rank's data
+    size_t     pb_half  = 0;          // bytes of one parity buffer
+    void      *gb_local = nullptr;    // gather_rows: the shares of y
+    void      *gb_peer[16] = {};
+    size_t     gb_half  = 0;
+    unsigned long long seq = 0;       // halo exchanges done so far (same on every rank)
+    unsigned long long gseq = 0;      // row gathers done so far
+    unsigned char *blk_halo = nullptr;  // HALO: [nblocks] block gathers remote columns
+    int       *blk_order = nullptr;     // HALO: [nblocks] walk order: interior blocks first
+    bool       xchg[16] = {};         // ranks this rank exchanges halo values with (symmetric)
     int       *ptr   = nullptr;   // [nrows+1] (+ padding) device
     int       *col   = nullptr;   // [nnz]     (+ padding) device
     void      *val   = nullptr;   // [nnz]     (+ padding) device, FP64 or FP32

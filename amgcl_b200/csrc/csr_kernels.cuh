@@ -78,6 +78,25 @@ struct CsrArgsT {
     const unsigned long long *wait_flags;  // flag row of the current parity (16 slots)
     unsigned int              wait_mask;
     unsigned long long        wait_seq;
+    const int                *blk_order;   // [nblocks] walk order: interior blocks first (or nullptr)
+    // ... and THIS rank's boundary values are pushed by this very kernel: right after the
+    // grid dependency resolves every CTA packs a slice of x[send_idx[.]] into the halo buffers
+    // of the ranks that gather them (plain stores over NVLink), the last CTA to finish
+    // releases their flags; then all CTAs go on to the interior row blocks
+    const int                *send_idx;
+    int                       n_send;
+    int                       nranks;
+    double                   *push_data[kMaxRanks];   // my segment in peer q's halo buffer (or nullptr)
+    unsigned long long       *push_flag[kMaxRanks];   // my flag in peer q's flag row (or nullptr)
+    unsigned int             *push_ticket;
+    unsigned long long        push_seq;                // 0: nothing to push / NCCL transport
+    // row shares of a replicated result (R onto a small level): every row is also stored into
+    // every rank's gather buffer; the last CTA releases the flags at the end of the kernel
+    int                       gather_on;
+    double                   *gather_data[kMaxRanks]; // my share's place in rank q's buffer
+    unsigned long long       *gather_flag[kMaxRanks];
+    unsigned int             *gather_ticket;
+    unsigned long long        gather_seq;
     typename P::TY       *y;      // output
     const typename P::TF *f;      // rhs          (RESID, RELAX)
     const typename P::TD *d;      // diagonal     (RELAX)
@@ -126,6 +145,13 @@ __device__ __forceinline__ BlockDesc load_desc(const CsrArgsT<P> &a, int b) {
     d.r0 = lo.x; d.e0 = lo.y;
     d.r1 = hi.x; d.e1 = hi.y;
     return d;
+}
+
+// position in the walk -> row block (multi-GPU: interior blocks first, halo blocks last)
+template <bool HALO, class P>
+__device__ __forceinline__ int block_at(const CsrArgsT<P> &a, int pos) {
+    if (HALO && a.blk_order) return __ldg(a.blk_order + pos);
+    return pos;
 }
 
 // Returns true if the block was staged (false: too long, use the strided path).
@@ -180,6 +206,11 @@ __device__ __forceinline__ void store_row(const CsrArgsT<P> &a, int r, typename 
         wv = (double)fr;
     }
     a.y[r] = out;
+    if (a.gather_on) {
+#pragma unroll 1
+        for (int q = 0; q < a.nranks; ++q)
+            if (a.gather_data[q]) a.gather_data[q][r] = (double)out;
+    }
     if (a.ndot) {
         const double yv = (double)out;
         if (a.w) wv = a.w[r];
@@ -350,6 +381,55 @@ __device__ __forceinline__ void compute_long(const CsrArgsT<P> &a, const BlockDe
     }
 }
 
+// ---- multi-GPU: this rank's side of the exchanges, done by the consumer kernel itself --------
+__device__ __forceinline__ void xchg_st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// all CTAs: pack + push a slice of the boundary values; last CTA: release the consumers' flags
+template <class P>
+__device__ __forceinline__ void halo_push(const CsrArgsT<P> &a) {
+    if (!a.push_seq) return;
+    const typename P::TX *__restrict__ x = a.x;
+    for (int i = blockIdx.x * kThreads + threadIdx.x; i < a.n_send; i += gridDim.x * kThreads) {
+        const double v = (double)x[a.send_idx[i]];
+#pragma unroll 1
+        for (int q = 0; q < a.nranks; ++q)
+            if (a.push_data[q]) a.push_data[q][i] = v;
+    }
+    __threadfence_system();                   // my peer stores are visible system-wide ...
+    __shared__ bool push_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int done = atomicAdd(a.push_ticket, 1u);    // ... before the ticket moves
+        push_last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (push_last) {
+        __threadfence_system();
+        if (threadIdx.x < a.nranks && a.push_flag[threadIdx.x])
+            xchg_st_release_sys(a.push_flag[threadIdx.x], a.push_seq);
+        if (threadIdx.x == 0) *a.push_ticket = 0;
+    }
+}
+// end of a kernel that stored row shares into the peers' gather buffers
+template <class P>
+__device__ __forceinline__ void gather_finish(const CsrArgsT<P> &a) {
+    __threadfence_system();
+    __shared__ bool gather_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int done = atomicAdd(a.gather_ticket, 1u);
+        gather_last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (gather_last) {
+        __threadfence_system();
+        if (threadIdx.x < a.nranks && a.gather_flag[threadIdx.x])
+            xchg_st_release_sys(a.gather_flag[threadIdx.x], a.gather_seq);
+        if (threadIdx.x == 0) *a.gather_ticket = 0;
+    }
+}
+
 // ---- variant 0: one row block per CTA -----------------------------------------------
 template <int MODE, int L, bool HALO, class P>
 __global__ void __launch_bounds__(kThreads, 4) csr_block_kernel(const CsrArgsT<P> a) {
@@ -403,32 +483,34 @@ __global__ void __launch_bounds__(kThreads, 2) csr_ring_kernel(const CsrArgsT<P>
         ptx::fence_mbar_init();
         const int pre = mine < nstages ? mine : nstages;
         for (int i = 0; i < pre; ++i) {
-            const BlockDesc d = load_desc(a, first + i * step);
+            const BlockDesc d = load_desc(a, block_at<HALO>(a, first + i * step));
             descs[i] = d;
             issue_block(a, d, stages + (size_t)i * lay.bytes, lay, bars + i, policy);
         }
     }
     __syncthreads();
     ptx::pdl_wait();         // vectors (x, f, d, y) come from earlier kernels: from here on
+    if (HALO) halo_push(a);  // multi-GPU: my boundary values go out before anything else
 
     RowAcc acc = {0.0, 0.0};
     int s = 0, parity = 0;
     for (int i = 0; i < mine; ++i) {
         ptx::mbar_wait(bars + s, parity);
         const BlockDesc d = descs[s];
-        wait_for_halo<HALO>(a, first + i * step);
+        wait_for_halo<HALO>(a, block_at<HALO>(a, first + i * step));
         if ((d.e1 - d.e0) <= a.nnz_cap)
             compute_staged<MODE, L, HALO>(a, d, stages + (size_t)s * lay.bytes, lay, acc);
         else
             compute_long<MODE, HALO>(a, d, red_s, acc);
         __syncthreads();                 // every thread is done with stage s (and descs[s])
         if (threadIdx.x == 0 && i + nstages < mine) {
-            const BlockDesc n = load_desc(a, first + (i + nstages) * step);
+            const BlockDesc n = load_desc(a, block_at<HALO>(a, first + (i + nstages) * step));
             descs[s] = n;
             issue_block(a, n, stages + (size_t)s * lay.bytes, lay, bars + s, policy);
         }
         if (++s == nstages) { s = 0; parity ^= 1; }
     }
+    if (HALO && a.gather_on) gather_finish(a);
     if (a.ndot) {
         double v[2] = {acc.s0, acc.s1};
         red_finish<2>(a.red, v);

@@ -8,20 +8,23 @@
 // b200_csr_create_* / b200_vec_create keep only this rank's share of every
 // object whose dimension reaches the distribution threshold.
 //
-//   level vectors   uniform contiguous blocks of B = ceil4(n / P) rows
-//   A_l (square)    own rows; local columns -> [0, n_loc), remote columns ->
-//                   n_loc + owner*S + position in the owner's send list.  The
-//                   halo is ONE in-place ncclAllGather of every rank's packed
-//                   boundary values (S doubles per rank) into a P*S buffer the
-//                   kernel gathers from directly -- no unpack step.
-//   P_l (prolong)   own rows, global coarse columns; the coarse vector arrives by
-//                   ncclAllGather (coarse level distributed) or ncclBroadcast
-//                   (coarse level lives on rank 0).
-//   R_l (restrict)  all rows, own columns only; partial sums leave by
-//                   ncclReduceScatter / ncclReduce.
-//   inner products  local kernel + ncclAllReduce of one double.
-//   anything smaller than the threshold lives on rank 0 only; other ranks hold
-//   "ghost" handles whose operations are no-ops.
+//   level vectors   n >= threshold: uniform contiguous blocks of B = ceil4(n / P) rows;
+//                   smaller: replicated -- every rank holds (and computes) the whole vector,
+//                   as mpi::amg consolidates small levels (mpi/amg.hpp:430-465)
+//   operators       every rank keeps WHOLE ROWS (split_rows below), so each row sum is formed
+//                   on one GPU in the reference's order: results equal the single-GPU ones bit
+//                   for bit, only the inner products see a different summation order.
+//                   rows partitioned, columns partitioned  (A_l, P_l, R_l between partitioned
+//                       levels): local columns + halo slots; the halo is the packed boundary
+//                       values of every rank (S doubles per rank) in a P*S buffer the kernel
+//                       gathers from directly -- no unpack step
+//                   rows partitioned, columns replicated   (P_l from a small level): no exchange
+//                   rows replicated,  columns partitioned  (R_l onto a small level): each rank
+//                       computes a share of the rows (halo as above) and the shares are
+//                       all-gathered into the replicated result
+//                   both replicated: every rank computes everything, no exchange
+//   inner products  partitioned vectors: reduced and all-reduced inside the producing kernel
+//                   (reduce.cuh); replicated vectors: local
 //
 // This file holds the pure host logic (partition arithmetic, matrix splitting;
 // exported through b200_dist_split_* so it can be tested on CPU with gloo) and
@@ -111,128 +114,84 @@ struct SplitMatrix {
     int64_t nrows = 0, ncols = 0;         // shape of the local matrix handed to the kernels
     std::vector<int64_t> ptr;             // [nrows+1]
     std::vector<int64_t> col;             // remapped columns
-    int64_t val_offset = 0;               // values are val[val_offset .. ) of the input when
-    bool    val_contiguous = true;        //   contiguous, else `val` below holds a copy
-    std::vector<double>  val;
-    // square operators only
+    int64_t val_offset = 0;               // values are val[val_offset .. ) of the input (always a
+    bool    val_contiguous = true;        //   contiguous slice: a rank keeps whole rows)
+    std::vector<double>  val;             // (unused; kept for the host view of b200_dist_split_*)
+    // column side
     int64_t S = 0;                        // send-list slots per rank (max over ranks)
-    std::vector<int64_t> send_idx;        // local indices this rank contributes, in slot order
-    int64_t n_loc = 0;
+    std::vector<int64_t> send_idx;        // indices (local to my block of x) the others gather, in slot order
+    int64_t n_loc = 0;                    // length of my block of x (columns < n_loc are local)
+    std::vector<unsigned char> dep;       // [P*P] dep[p*P+o] = rows of p reference columns owned by o != p
 };
 
-// A_l: rows of `rank`; columns -> local / halo slots.
+// One rule for every operator of the hierarchy (A_l, P_l, R_l): a rank keeps WHOLE ROWS --
+// the rows [rows.lo(rank), rows.hi(rank)) -- so every row sum is formed on one GPU in the
+// reference's entry order, exactly as on a single GPU.  If the vector the operator is applied
+// to is partitioned (cols_dist), a column owned by this rank (cols partition) becomes the local
+// index c - cols.lo(rank); a column owned by rank o becomes n_loc + o*S + slot, where slot is
+// the column's position in o's send list (the columns of o's block that ANY other rank
+// references, in ascending order) -- the kernel reads those from the all-gathered halo buffer.
+// If the vector is replicated (!cols_dist) columns are left alone.
+// (model: mpi/distributed_matrix.hpp:388-435 splits A into A_loc / A_rem the same way.)
 template <class Ptr, class Col>
-static void split_square(const Partition &part, int rank, const Ptr *ptr, const Col *col,
-                         SplitMatrix &out) {
-    const int64_t n = part.n;
-    const int P = part.P;
-    // mark[c] = 1 if some row not owned by owner(c) references column c
-    std::vector<unsigned char> mark((size_t)n, 0);
+static void split_rows(const Partition &rows, const Partition &cols, bool cols_dist, int rank,
+                       const Ptr *ptr, const Col *col, SplitMatrix &out) {
+    const int P = rows.P;
+    const int64_t rlo = rows.lo(rank), rhi = rows.hi(rank), nr = rhi - rlo;
+    const int64_t e0 = nr ? (int64_t)ptr[rlo] : 0;
+    const int64_t e1 = nr ? (int64_t)ptr[rhi] : 0;
+    out.nrows = nr;
+    out.ptr.resize((size_t)nr + 1);
+    for (int64_t r = rlo; r <= rhi && nr; ++r) out.ptr[(size_t)(r - rlo)] = (int64_t)ptr[r] - e0;
+    if (!nr) out.ptr[0] = 0;
+    out.col.resize((size_t)(e1 - e0));
+    out.val_contiguous = true;
+    out.val_offset = e0;
+    out.send_idx.clear();
+    out.dep.assign((size_t)P * P, 0);
+    if (!cols_dist) {
+        out.S = 0;
+        out.n_loc = cols.n;
+        out.ncols = cols.n;
+        for (int64_t e = e0; e < e1; ++e) out.col[(size_t)(e - e0)] = (int64_t)col[e];
+        return;
+    }
+    const int64_t nc = cols.n;
+    // mark[c] = 1 if some row not owned by owner(c) references column c; dep[p][o]
+    std::vector<unsigned char> mark((size_t)nc, 0);
     for (int p = 0; p < P; ++p) {
-        const int64_t lo = part.lo(p), hi = part.hi(p);
-        for (int64_t r = lo; r < hi; ++r)
-            for (int64_t e = (int64_t)ptr[r]; e < (int64_t)ptr[r + 1]; ++e) {
-                const int64_t c = (int64_t)col[e];
-                if (c < lo || c >= hi) mark[(size_t)c] = 1;
+        const int64_t lo = rows.lo(p), hi = rows.hi(p);
+        const int64_t clo = cols.lo(p), chi = cols.hi(p);
+        unsigned char *drow = out.dep.data() + (size_t)p * P;
+        const int64_t b = lo < hi ? (int64_t)ptr[lo] : 0, e = lo < hi ? (int64_t)ptr[hi] : 0;
+        for (int64_t k = b; k < e; ++k) {
+            const int64_t c = (int64_t)col[k];
+            if (c < clo || c >= chi) {
+                mark[(size_t)c] = 1;
+                drow[cols.owner(c)] = 1;
             }
+        }
     }
     // slot of every marked column inside its owner's send list, S = longest list
-    std::vector<int64_t> slot((size_t)n, -1);
+    std::vector<int64_t> slot((size_t)nc, -1);
     int64_t S = 0;
     for (int p = 0; p < P; ++p) {
         int64_t k = 0;
-        for (int64_t c = part.lo(p); c < part.hi(p); ++c)
+        for (int64_t c = cols.lo(p); c < cols.hi(p); ++c)
             if (mark[(size_t)c]) slot[(size_t)c] = k++;
         S = std::max(S, k);
     }
     S = (S + 1) & ~int64_t(1);            // keep every rank's segment 16-byte aligned
-    const int64_t lo = part.lo(rank), hi = part.hi(rank), n_loc = hi - lo;
+    const int64_t clo = cols.lo(rank), chi = cols.hi(rank), n_loc = chi - clo;
     out.S = S;
     out.n_loc = n_loc;
-    out.nrows = n_loc;
     out.ncols = n_loc + (int64_t)P * S;
-    out.send_idx.clear();
-    for (int64_t c = lo; c < hi; ++c)
-        if (mark[(size_t)c]) out.send_idx.push_back(c - lo);
-    out.ptr.resize((size_t)n_loc + 1);
-    const int64_t e0 = n_loc ? (int64_t)ptr[lo] : 0;
-    const int64_t e1 = n_loc ? (int64_t)ptr[hi] : 0;
-    out.col.resize((size_t)(e1 - e0));
-    for (int64_t r = lo; r <= hi && n_loc; ++r) out.ptr[(size_t)(r - lo)] = (int64_t)ptr[r] - e0;
-    if (!n_loc) out.ptr[0] = 0;
+    for (int64_t c = clo; c < chi; ++c)
+        if (mark[(size_t)c]) out.send_idx.push_back(c - clo);
     for (int64_t e = e0; e < e1; ++e) {
         const int64_t c = (int64_t)col[e];
-        if (c >= lo && c < hi) out.col[(size_t)(e - e0)] = c - lo;
-        else out.col[(size_t)(e - e0)] = n_loc + (int64_t)part.owner(c) * S + slot[(size_t)c];
-    }
-    out.val_contiguous = true;
-    out.val_offset = e0;
-}
-
-// P_l: rows of `rank` (fine partition), columns stay global coarse indices.
-template <class Ptr, class Col>
-static void split_prolong(const Partition &fine, int rank, int64_t ncols, const Ptr *ptr,
-                          const Col *col, SplitMatrix &out) {
-    const int64_t lo = fine.lo(rank), hi = fine.hi(rank), n_loc = hi - lo;
-    out.nrows = n_loc;
-    out.ncols = ncols;
-    out.n_loc = n_loc;
-    out.ptr.resize((size_t)n_loc + 1);
-    const int64_t e0 = n_loc ? (int64_t)ptr[lo] : 0;
-    const int64_t e1 = n_loc ? (int64_t)ptr[hi] : 0;
-    for (int64_t r = lo; r <= hi && n_loc; ++r) out.ptr[(size_t)(r - lo)] = (int64_t)ptr[r] - e0;
-    if (!n_loc) out.ptr[0] = 0;
-    out.col.resize((size_t)(e1 - e0));
-    for (int64_t e = e0; e < e1; ++e) out.col[(size_t)(e - e0)] = (int64_t)col[e];
-    out.val_contiguous = true;
-    out.val_offset = e0;
-}
-
-// R_l: all rows, only the columns `rank` owns (fine partition), remapped to local.
-template <class Ptr, class Col>
-static void split_restrict(const Partition &fine, int rank, int64_t nrows, const Ptr *ptr,
-                           const Col *col, const double *val, SplitMatrix &out) {
-    const int64_t lo = fine.lo(rank), hi = fine.hi(rank);
-    out.nrows = nrows;
-    out.ncols = hi - lo;
-    out.n_loc = hi - lo;
-    out.ptr.assign((size_t)nrows + 1, 0);
-    for (int64_t r = 0; r < nrows; ++r) {
-        int64_t k = 0;
-        for (int64_t e = (int64_t)ptr[r]; e < (int64_t)ptr[r + 1]; ++e) {
-            const int64_t c = (int64_t)col[e];
-            k += (c >= lo && c < hi);
-        }
-        out.ptr[(size_t)r + 1] = out.ptr[(size_t)r] + k;
-    }
-    const int64_t nnz = out.ptr[(size_t)nrows];
-    out.col.resize((size_t)nnz);
-    out.val.resize((size_t)nnz);
-    out.val_contiguous = false;
-    int64_t k = 0;
-    for (int64_t r = 0; r < nrows; ++r)
-        for (int64_t e = (int64_t)ptr[r]; e < (int64_t)ptr[r + 1]; ++e) {
-            const int64_t c = (int64_t)col[e];
-            if (c >= lo && c < hi) {
-                out.col[(size_t)k] = c - lo;
-                out.val[(size_t)k] = val[e];
-                ++k;
-            }
-        }
-}
-
-// dep[p][o] = rows owned by p (row partition) reference columns owned by o (column
-// partition), p != o for square operators.  Identical on every rank (global matrix).
-template <class Ptr, class Col>
-static void dependency_matrix(const Partition &rows, const Partition &cols, const Ptr *ptr,
-                              const Col *col, std::vector<unsigned char> &dep) {
-    const int P = rows.P;
-    dep.assign((size_t)P * P, 0);
-    for (int p = 0; p < P; ++p) {
-        unsigned char *row = dep.data() + (size_t)p * P;
-        for (int64_t r = rows.lo(p); r < rows.hi(p); ++r)
-            for (int64_t e = (int64_t)ptr[r]; e < (int64_t)ptr[r + 1]; ++e)
-                row[cols.owner((int64_t)col[e])] = 1;
+        if (c >= clo && c < chi) out.col[(size_t)(e - e0)] = c - clo;
+        else out.col[(size_t)(e - e0)] = n_loc + (int64_t)cols.owner(c) * S + slot[(size_t)c];
     }
 }
 

@@ -225,14 +225,33 @@ void peer_release(b200_ctx_t ctx, void *local, void **peers);
 struct HaloArgs {
     const double             *xh = nullptr;         // halo values for columns >= nloc
     int                       nloc = 0;
+    const int                *blk_order = nullptr;  // walk order: blocks that wait come last
     const unsigned char      *blk_halo = nullptr;   // peer transport: blocks that must wait
     const unsigned long long *wait_flags = nullptr;
     unsigned int              wait_mask = 0;
     unsigned long long        wait_seq = 0;
+    // peer transport: this rank's boundary values are pushed by the consumer kernel itself
+    const int                *send_idx = nullptr;
+    int                       n_send = 0;
+    int                       nranks = 0;
+    double                   *push_data[kMaxRanks] = {};
+    unsigned long long       *push_flag[kMaxRanks] = {};
+    unsigned int             *push_ticket = nullptr;
+    unsigned long long        push_seq = 0;
 };
 int  halo_exchange(b200_ctx_t ctx, b200_csr_t A, const double *x, HaloArgs &a);
-int  coarse_to_all(b200_ctx_t ctx, b200_csr_t A, b200_vec_t xc, const double **px);
-int  partials_to_coarse(b200_ctx_t ctx, b200_csr_t A, b200_vec_t yc);
+// row shares of a replicated result
+struct GatherArgs {
+    int                 on = 0;                     // peer transport: kernel stores into the peers
+    int                 nranks = 0;
+    double             *data[kMaxRanks] = {};
+    unsigned long long *flag[kMaxRanks] = {};
+    unsigned int       *ticket = nullptr;
+    unsigned long long  seq = 0;
+    double             *y_local = nullptr;          // where the kernel's plain store of a row goes
+};
+int  gather_begin(b200_ctx_t ctx, b200_csr_t A, GatherArgs &g);
+int  gather_end(b200_ctx_t ctx, b200_csr_t A, const GatherArgs &g, b200_vec_t y);
 int  dist_dot_finish(b200_ctx_t ctx, double *result);
 
 } // namespace b200

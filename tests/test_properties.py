@@ -125,35 +125,42 @@ def test_split_square_reproduces_the_global_product(m, P, seed):
 
 @settings(**SETTINGS)
 @given(sparse_matrix(), st.integers(1, 6), st.integers(0, 2 ** 31 - 1))
-def test_split_prolong_and_restrict(m, P, seed):
-    """prolong: rank r owns the fine rows of its block and reads the whole coarse vector;
-    restrict: rank r owns the fine COLUMNS of its block and produces partial sums over all
-    coarse rows that add up to R t."""
+def test_split_rectangular_operators(m, P, seed):
+    """Any rectangular operator (P_l, R_l): a rank keeps whole rows of its block of the row
+    partition.  'replicated': the input vector is replicated, columns stay global; 'halo': the
+    input is partitioned like the columns -- local columns + halo slots filled from every
+    rank's send list.  Either way the rows reassemble to the global product exactly."""
     nr, nc, ptr, col, val, dense = m
     rng = np.random.default_rng(seed)
-    # P_h (fine rows = nr) applied to a coarse vector of nc entries
     u = rng.uniform(-1, 1, nc)
-    fine = [ab.partition(nr, P, r) for r in range(P)]
+    rows = [ab.partition(nr, P, r) for r in range(P)]
+    cols = [ab.partition(nc, P, r) for r in range(P)]
     got = np.zeros(nr)
     for r in range(P):
-        p = ab.dist_split("prolong", P, r, nr, nc, ptr, col, val)
-        _, lo, hi = fine[r]
-        assert p["nrows"] == hi - lo and p["ncols"] == nc
+        p = ab.dist_split("replicated", P, r, nr, nc, ptr, col, val)
+        _, lo, hi = rows[r]
+        assert p["nrows"] == hi - lo and p["ncols"] == nc and p["slots"] == 0
         if hi > lo:
             got[lo:hi] = csr_mv(p["ptr"], p["col"], p["val"], u)
     assert np.allclose(got, dense @ u, rtol=0, atol=1e-12)
-    # R (coarse rows = nr) applied to a fine vector of nc entries partitioned by columns
-    t = rng.uniform(-1, 1, nc)
-    finec = [ab.partition(nc, P, r) for r in range(P)]
-    total = np.zeros(nr)
-    for r in range(P):
-        p = ab.dist_split("restrict", P, r, nr, nc, ptr, col, val)
-        _, lo, hi = finec[r]
-        assert p["nrows"] == nr and p["ncols"] == hi - lo
-        if p["col"].size:
-            assert p["col"].max() < hi - lo
-        total += csr_mv(p["ptr"], p["col"], p["val"], t[lo:hi]) if hi > lo else 0.0
-    assert np.allclose(total, dense @ t, rtol=0, atol=1e-12)
+    parts = [ab.dist_split("halo", P, r, nr, nc, ptr, col, val) for r in range(P)]
+    S = parts[0]["slots"]
+    assert all(p["slots"] == S for p in parts)
+    halo = np.zeros(P * S)
+    for r, p in enumerate(parts):
+        _, clo, chi = cols[r]
+        assert p["n_loc"] == chi - clo and p["ncols"] == (chi - clo) + P * S
+        if p["send_idx"].size:
+            assert p["send_idx"].max() < chi - clo
+        halo[r * S:r * S + p["send_idx"].size] = u[clo + p["send_idx"]]
+    got = np.zeros(nr)
+    for r, p in enumerate(parts):
+        _, lo, hi = rows[r]
+        _, clo, chi = cols[r]
+        assert p["nrows"] == hi - lo
+        if hi > lo:
+            got[lo:hi] = csr_mv(p["ptr"], p["col"], p["val"], np.concatenate([u[clo:chi], halo]))
+    assert np.allclose(got, dense @ u, rtol=0, atol=1e-12)
 
 
 @settings(max_examples=30, deadline=None, suppress_health_check=[HealthCheck.too_slow,
