@@ -669,7 +669,8 @@ static int residual_impl(b200_ctx_t ctx, b200_vec_t f, b200_csr_t A, b200_vec_t 
     B200_REQUIRE((int64_t)f->n == A->gl_rows && (int64_t)r->n == A->gl_rows,
                  "residual: rhs/r size != matrix rows");
     B200_REQUIRE(x != r && (x->ptr != r->ptr || !x->ptr), "residual: x and r must not alias");
-    B200_REQUIRE(A->gl_rows == A->gl_cols && !A->gather_rows, "residual: operator must be square");
+    B200_REQUIRE(!A->gather_rows && (!ctx->dist || A->gl_rows == A->gl_cols || A->kind == B200_CK_LOCAL),
+                 "residual: operator must be square");
     GUARD(ctx);
     if (A->dtype == B200_F32) {
         if (all32({f, x, r})) return residual_local<PrecFF>(ctx, f, A, x, r);

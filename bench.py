@@ -128,12 +128,24 @@ def pin_openmp():
     """BASELINE.md section 3 protocol for the CPU arm: threads bound to cores, neighbours
     close.  Must run before the first OpenMP runtime is loaded (libgomp reads the
     environment once), i.e. before torch / oracle are imported."""
+    cpu_topology()      # BEFORE binding: afterwards this thread's affinity mask is one core
     os.environ.setdefault("OMP_PROC_BIND", "close")
     os.environ.setdefault("OMP_PLACES", "cores")
 
 
+_TOPOLOGY = None
+
+
 def cpu_topology():
-    """(logical cpus, physical cores, sockets) of this host."""
+    """(logical cpus, physical cores, sockets) this process may use; evaluated once, before the
+    OpenMP runtime binds the calling thread."""
+    global _TOPOLOGY
+    if _TOPOLOGY is None:
+        _TOPOLOGY = _cpu_topology()
+    return _TOPOLOGY
+
+
+def _cpu_topology():
     logical = os.cpu_count() or 1
     try:
         out = subprocess.run(["lscpu", "-p=CPU,CORE,SOCKET"], stdout=subprocess.PIPE,
@@ -182,13 +194,39 @@ def pick_threads(ref, step):
 
 
 def timed_reference_solves(S, rhs, count):
-    """`count` FULL solves of the reference; solve() alone is timed (inside the library,
-    vectors first-touched in parallel beforehand).  Returns (x, iters, resid, seconds[])."""
+    """`count` solves of the reference; solve() alone is timed (inside the library, vectors
+    first-touched in parallel beforehand).  Returns (x, iters, resid, seconds[])."""
     secs = []
     for _ in range(count):
         x, it, res, dt = S.solve_timed(rhs)
         secs.append(dt)
     return x, it, res, secs
+
+
+def bounded_reference_sample(args, ptr, col, val, rhs, steps, budget_s, sweep):
+    """`steps` timed solves of the reference within `budget_s` seconds of CPU time: FULL solves
+    when they fit (every box with a many-core host), else solves truncated to as many Krylov
+    iterations as fit (each iteration does the same work, so iterations/s is the same metric;
+    boxes that expose 2 host cores need 26 s per full 256^3 solve).  `sweep`: seconds of one
+    4-iteration solve at the chosen thread count.  Returns (x, iters, resid, seconds[], full?,
+    setup_s)."""
+    import oracle
+    t0 = time.time()
+    S = oracle.RefSolver(ptr, col, val, args.relax, args.krylov, precision=args.precision)
+    t_setup = time.time() - t0
+    x, it_full, res, dt = S.solve_timed(rhs)           # one full solve: settles, gives the count
+    per_iter = dt / max(it_full, 1)
+    fit = int(budget_s / max(steps, 1) / max(per_iter, 1e-9))
+    if fit >= it_full:
+        x, it, res, secs = timed_reference_solves(S, rhs, steps)
+        S.close()
+        return x, it, res, secs, True, t_setup, x, it_full, res
+    S.close()
+    k = max(2, min(it_full, fit))
+    Sk = oracle.RefSolver(ptr, col, val, args.relax, args.krylov, maxiter=k, precision=args.precision)
+    xk, it, resk, secs = timed_reference_solves(Sk, rhs, steps)
+    Sk.close()
+    return xk, it, resk, secs, False, t_setup, x, it_full, res
 
 
 # --------------------------------------------------------------------------- reference arm
@@ -211,20 +249,19 @@ def reference_arm(args, rank, world):
     t0 = time.time()
     ptr, col, val, rhs = poisson3d(args.n)
     t_gen = time.time() - t0
-    t0 = time.time()
-    S = oracle.RefSolver(ptr, col, val, args.relax, args.krylov, precision=args.precision)
-    t_setup = time.time() - t0
     Sq = oracle.RefSolver(ptr, col, val, args.relax, args.krylov, maxiter=4, precision=args.precision)
     cores, topo = pick_threads(ref, lambda: Sq.solve(rhs))
     for _ in range(args.warmup):
         Sq.solve(rhs)
     Sq.close()
-    x, it, res, secs = timed_reference_solves(S, rhs, args.steps)
-    S.close()
+    _, it, _, secs, full, t_setup, x, it_full, res = bounded_reference_sample(
+        args, ptr, col, val, rhs, args.steps, 150.0, topo)
     med = float(np.median(secs))
     value = it / med
-    sample = "%d full %s solves (%d iterations each), solve() only; median %.3f s, min %.3f, max %.3f" % (
-        args.steps, workload_name(args), it, med, min(secs), max(secs))
+    sample = "%d %s %s solves (%d iterations each%s), solve() only; median %.3f s, min %.3f, max %.3f" % (
+        args.steps, "full" if full else "truncated", workload_name(args), it,
+        "" if full else " of %d: a full solve does not fit the time budget on %d host threads" % (it_full, cores),
+        med, min(secs), max(secs))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * med,
@@ -234,7 +271,7 @@ def reference_arm(args, rank, world):
         "data": "synthetic",
         "config": config_block(args, int(ptr.size - 1), int(ptr[-1]), t_setup, t_gen,
                                backend="amgcl::backend::builtin<double> (OpenMP)"),
-        "iters": it, "resid": res,
+        "iters": it_full, "resid": res,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
                          "sample": sample, "topology": topo},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -268,20 +305,17 @@ def cpu_baseline_leg(args, ptr, col, val, rhs, full_iters):
     if not oracle.have_ref():
         return None
     ref = oracle.ref()
-    t0 = time.time()
-    S = oracle.RefSolver(ptr, col, val, args.relax, args.krylov, precision=args.precision)
-    t_setup = time.time() - t0
     Sq = oracle.RefSolver(ptr, col, val, args.relax, args.krylov, maxiter=4, precision=args.precision)
     threads, topo = pick_threads(ref, lambda: Sq.solve(rhs))
-    Sq.solve(rhs)
     Sq.close()
-    x, it, res, secs = timed_reference_solves(S, rhs, 3)
-    S.close()
+    _, it, _, secs, full, t_setup, x, it_full, res = bounded_reference_sample(
+        args, ptr, col, val, rhs, 3, 45.0, topo)
     med = float(np.median(secs))
     return {"value": it / med, "unit": UNIT, "cores": threads, "kind": "reference",
-            "sample": "3 full %s solves (%d iterations each), solve() only: median %.3f s (min %.3f, max %.3f); "
-                      "setup %.1f s not timed" % (workload_name(args), it, med, min(secs), max(secs), t_setup),
-            "topology": topo, "iters": it, "resid": res, "solve_s": med}, x
+            "sample": "3 %s %s solves (%d iterations each), solve() only: median %.3f s (min %.3f, max %.3f); "
+                      "setup %.1f s not timed" % ("full" if full else "truncated", workload_name(args), it, med,
+                                                  min(secs), max(secs), t_setup),
+            "topology": topo, "iters": it_full, "resid": res, "solve_s": med}, x
 
 
 def golden_parity(args, iters, resid, x):
