@@ -74,6 +74,8 @@ def lib():
         "b200_ctx_get_stream": [_vp, _P(_vp)],
         "b200_ctx_device": [_vp, _P(_c.c_int)],
         "b200_ctx_sync": [_vp],
+        "b200_ctx_flush": [_vp],
+        "b200_tail_stats": [_vp, _P(_c.c_uint64), _P(_c.c_uint64)],
         "b200_ctx_launch_count": [_vp, _P(_c.c_uint64)],
         "b200_ctx_reset_launch_count": [_vp],
         "b200_ctx_set_option": [_vp, _c.c_char_p, _i64],
@@ -251,6 +253,16 @@ class Context:
 
     def sync(self):
         _check(lib().b200_ctx_sync(self.h), "b200_ctx_sync")
+
+    def flush(self):
+        """Launch whatever was deferred into the coarse-tail list (option "coarse_tail")."""
+        _check(lib().b200_ctx_flush(self.h), "b200_ctx_flush")
+
+    def tail_stats(self):
+        """(launches of the coarse-tail kernel, calls they executed) since context creation."""
+        f, c = _c.c_uint64(), _c.c_uint64()
+        _check(lib().b200_tail_stats(self.h, _c.byref(f), _c.byref(c)))
+        return f.value, c.value
 
     def set_option(self, key, value):
         _check(lib().b200_ctx_set_option(self.h, key.encode(), int(value)), "b200_ctx_set_option")

@@ -182,8 +182,7 @@ extern "C" int b200_coarse_solve(b200_ctx_t ctx, b200_coarse_t S, b200_vec_t rhs
     touch(ctx, {rhs, x});
     if (ctx->recording) S->in_graph = true;
     B200_REQUIRE((int64_t)rhs->n == S->n && (int64_t)x->n == S->n, "coarse solve: size mismatch");
-    if (S->ghost) return B200_OK;
-    GUARD(ctx);
+    GUARD_DEFER(ctx);
     const int N = (int)S->n;
     const int warps_per_cta = kThreads / 32;
     if (S->replicated) {
@@ -192,6 +191,7 @@ extern "C" int b200_coarse_solve(b200_ctx_t ctx, b200_coarse_t S, b200_vec_t rhs
                      "coarse solve: vectors must be partitioned like the coarsest level");
         int rc = materialize(rhs);
         if (rc) return rc;
+        if ((rc = tail_flush(ctx))) return rc;
         B200_NCCL(nccl().AllGather(rhs->ptr, S->gbuf, (size_t)S->block, ncclDouble, comm_of(ctx), ctx->stream));
         const int nloc = (int)x->len;
         if (nloc) {
@@ -211,6 +211,9 @@ extern "C" int b200_coarse_solve(b200_ctx_t ctx, b200_coarse_t S, b200_vec_t rhs
     const double *pr;
     int rc = rd(rhs, &pr);
     if (rc) return rc;
+    if (rhs->dtype == B200_F64 && tail_enabled(ctx) && (int64_t)N * N <= 4 * ctx->opt_tail_max_nnz)
+        return tail_enqueue_gemv(ctx, N, S->Ainv, pr, wr(x));      // part of the coarse tail
+    if ((rc = tail_flush(ctx))) return rc;
     ProfScope prof(ctx, B200_PROF_COARSE, S->n, S->n, S->n * S->n);
     if (rhs->dtype == B200_F32)
         B200_CUDA(launch_pdl(ctx, coarse_gemv_kernel<float>, dim3((N + warps_per_cta - 1) / warps_per_cta),

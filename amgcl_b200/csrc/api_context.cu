@@ -81,6 +81,7 @@ extern "C" int b200_ctx_create(int device, b200_ctx_t *out) {
     if (const char *e = getenv("B200_CYCLE_GRAPH")) ctx->opt_cycle_graph = atoi(e) ? 1 : 0;
     if (const char *e = getenv("B200_GRAPH_PDL")) ctx->opt_graph_pdl = atoi(e) ? 1 : 0;
     if (const char *e = getenv("B200_FUSED_KRYLOV")) ctx->opt_fused_krylov = atoi(e) ? 1 : 0;
+    if (const char *e = getenv("B200_COARSE_TAIL")) ctx->opt_coarse_tail = atoi(e) ? 1 : 0;
     // any failure below releases what was created so far (b200_ctx_destroy null-checks every member)
     const int rc = ctx_init(ctx, device);
     if (rc != B200_OK) {
@@ -95,9 +96,11 @@ extern "C" int b200_ctx_create(int device, b200_ctx_t *out) {
 
 extern "C" int b200_ctx_destroy(b200_ctx_t ctx) {
     if (!ctx) return B200_OK;
+    tail_destroy(ctx);                            // pending calls are dropped with the context
     GUARD(ctx);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     scal_destroy(ctx);
+    tail_destroy(ctx);
     for (int k = 0; k < 2; ++k) {
         if (ctx->stage_host[k]) cudaFreeHost(ctx->stage_host[k]);
         if (ctx->stage_event[k]) cudaEventDestroy(ctx->stage_event[k]);
@@ -145,6 +148,9 @@ extern "C" int b200_ctx_default(b200_ctx_t *out) {
 extern "C" int b200_ctx_set_stream(b200_ctx_t ctx, void *cuda_stream) {
     CHECK_CTX(ctx);
     NOT_RECORDING(ctx, "stream change");
+    {
+        GUARD(ctx);                               // deferred calls belong on the old stream
+    }
     ctx->option_epoch++;
     ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
     return B200_OK;
@@ -172,6 +178,12 @@ extern "C" int b200_ctx_sync(b200_ctx_t ctx) {
     return B200_OK;
 }
 
+extern "C" int b200_ctx_flush(b200_ctx_t ctx) {
+    CHECK_CTX(ctx);
+    GUARD(ctx);
+    return B200_OK;
+}
+
 extern "C" int b200_ctx_launch_count(b200_ctx_t ctx, uint64_t *count) {
     CHECK_CTX(ctx);
     B200_REQUIRE(count != nullptr, "null output pointer");
@@ -188,6 +200,9 @@ extern "C" int b200_ctx_reset_launch_count(b200_ctx_t ctx) {
 extern "C" int b200_profile_begin(b200_ctx_t ctx) {
     CHECK_CTX(ctx);
     NOT_RECORDING(ctx, "profiling");
+    {
+        GUARD(ctx);
+    }
     ctx->prof_used = 0;
     ctx->prof_recs.clear();
     ctx->profiling = true;
@@ -244,6 +259,9 @@ static int64_t *option_slot(b200_ctx_t ctx, const char *key) {
     if (!strcmp(key, "cycle_graph")) return &ctx->opt_cycle_graph;
     if (!strcmp(key, "graph_pdl")) return &ctx->opt_graph_pdl;
     if (!strcmp(key, "fused_krylov")) return &ctx->opt_fused_krylov;
+    if (!strcmp(key, "coarse_tail")) return &ctx->opt_coarse_tail;
+    if (!strcmp(key, "tail_max_nnz")) return &ctx->opt_tail_max_nnz;
+    if (!strcmp(key, "tail_max_vec")) return &ctx->opt_tail_max_vec;
     return nullptr;
 }
 
@@ -265,6 +283,9 @@ extern "C" int b200_ctx_set_option(b200_ctx_t ctx, const char *key, int64_t valu
         if (value < 0 || value > 1) return fail(B200_EINVAL, "spmv_variant must be 0 or 1");
     }
     B200_REQUIRE(!ctx->recording, "options cannot change while a graph is being recorded");
+    {
+        GUARD(ctx);                               // deferred calls ran under the old value
+    }
     if (*slot != value) ctx->option_epoch++;      // recorded graphs were built with the old value
     *slot = value;
     return B200_OK;

@@ -180,6 +180,10 @@ void peer_release(b200_ctx_t ctx, void *local, void **peers) {
 // pack kernel + one in-place ncclAllGather (S doubles per rank) on the stream.
 int halo_exchange(b200_ctx_t ctx, b200_csr_t A, const double *x, HaloArgs &a) {
     a = HaloArgs();
+    {
+        const int trc = tail_flush(ctx);
+        if (trc) return trc;
+    }
     a.xh = A->halo; a.nloc = (int)A->n_loc;
     a.blk_order = A->blk_order;
     if (A->S == 0) return B200_OK;
@@ -244,6 +248,10 @@ int gather_begin(b200_ctx_t ctx, b200_csr_t A, GatherArgs &g) {
 
 // end: all shares -> the replicated vector y (every rank ends up with the complete result)
 int gather_end(b200_ctx_t ctx, b200_csr_t A, const GatherArgs &g, b200_vec_t y) {
+    {
+        const int trc = tail_flush(ctx);
+        if (trc) return trc;
+    }
     ProfScope prof(ctx, B200_PROF_COMM, A->gl_rows, ctx->nranks, 2);
     const int64_t count = A->gl_rows;
     if (ctx->p2p) {

@@ -235,6 +235,10 @@ extern "C" int b200_krylov_create(b200_ctx_t ctx, size_t n, b200_krylov_t *out) 
     B200_REQUIRE(out != nullptr, "null output pointer");
     *out = nullptr;
     NOT_RECORDING(ctx, "Krylov workspace creation");
+    // multi-GPU: the reductions are all-reduced inside the kernels through peer memory; with the
+    // NCCL transport (option "p2p" = 0) the solvers issue the reference's sequence instead
+    if (ctx->dist && !ctx->scal_x_table)
+        return fail(B200_EINVAL, "fused Krylov steps need the peer-memory transport on a multi-GPU context");
     const int base = scal_alloc(ctx, K_NSLOTS);
     if (base < 0) return fail(B200_ENOMEM, "scalar table exhausted (too many live Krylov workspaces)");
     b200_krylov_s *K = new (std::nothrow) b200_krylov_s();

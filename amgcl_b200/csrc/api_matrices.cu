@@ -5,6 +5,10 @@
 #include "internal.cuh"
 #include "csr_kernels.cuh"
 
+namespace b200 {
+int tail_enqueue_csr(b200_ctx_t ctx, int mode, b200_csr_t A, const CsrArgsT<PrecDD> &a);   // api_tail.cu
+}
+
 using namespace b200;
 
 // ---------------------------------------------------------------------------
@@ -410,6 +414,14 @@ static int launch_csr_L(b200_ctx_t ctx, b200_csr_t A, const CsrArgsT<P> &args) {
 template <int MODE, class P>
 static int launch_csr(b200_ctx_t ctx, b200_csr_t A, const CsrArgsT<P> &args) {
     if (A->nblocks == 0) return B200_OK;
+    // small FP64 operator, nothing to reduce or exchange: defer into the coarse-tail list
+    if (std::is_same<P, PrecDD>::value && !args.ndot && !args.xh && !args.gather_on &&
+        tail_accepts_csr(ctx, A))
+        return tail_enqueue_csr(ctx, MODE, A, *reinterpret_cast<const CsrArgsT<PrecDD> *>(&args));
+    {
+        const int trc = tail_flush(ctx);          // immediate launch: what was deferred goes first
+        if (trc) return trc;
+    }
     if (ctx->recording) A->in_graph = true;
     ProfScope prof(ctx, MODE, A->nrows, A->ncols, A->nnz);
     switch (A->lanes) {
@@ -613,7 +625,7 @@ static int spmv_impl(b200_ctx_t ctx, double alpha, b200_csr_t A, b200_vec_t x, d
     B200_REQUIRE((int64_t)x->n == A->gl_cols, "spmv: x size != matrix columns");
     B200_REQUIRE((int64_t)y->n == A->gl_rows, "spmv: y size != matrix rows");
     B200_REQUIRE(x != y && (x->ptr != y->ptr || !x->ptr), "spmv: x and y must not alias");
-    GUARD(ctx);
+    GUARD_DEFER(ctx);
     if (A->dtype == B200_F32) {
         // FP32 operator (mixed-precision hierarchy): single GPU, persistent ring kernels
         if (all32({x, y})) return spmv_local<PrecFF>(ctx, alpha, A, x, beta, y);
@@ -671,7 +683,7 @@ static int residual_impl(b200_ctx_t ctx, b200_vec_t f, b200_csr_t A, b200_vec_t 
     B200_REQUIRE(x != r && (x->ptr != r->ptr || !x->ptr), "residual: x and r must not alias");
     B200_REQUIRE(!A->gather_rows && (!ctx->dist || A->gl_rows == A->gl_cols || A->kind == B200_CK_LOCAL),
                  "residual: operator must be square");
-    GUARD(ctx);
+    GUARD_DEFER(ctx);
     if (A->dtype == B200_F32) {
         if (all32({f, x, r})) return residual_local<PrecFF>(ctx, f, A, x, r);
         if (all64({f, x, r})) return residual_local<PrecFD>(ctx, f, A, x, r, req);
@@ -739,7 +751,16 @@ namespace b200 {
 
 template <class TD, class TF, class TX>
 static int relax_zero_t(b200_ctx_t ctx, double omega, const double *pd, const double *pf, b200_vec_t x) {
+    if (x->len && std::is_same<TD, double>::value && std::is_same<TF, double>::value &&
+        std::is_same<TX, double>::value && tail_enabled(ctx) && (int64_t)x->len <= ctx->opt_tail_max_vec &&
+        x->kind == B200_VK_LOCAL) {
+        const int rc = tail_enqueue_relax_zero(ctx, x->len, omega, pd, pf, wr(x));
+        x->zero_pending = false;
+        return rc;
+    }
     if (x->len) {
+        const int trc = tail_flush(ctx);
+        if (trc) return trc;
         const int grid = grid_for(ctx, x->len, 2);
         ProfScope prof(ctx, B200_PROF_RELAX_ZERO, (int64_t)x->len, 1, 0);
         B200_CUDA(launch_pdl(ctx, relax_zero_kernel<TD, TF, TX>, dim3(grid), dim3(kThreads), 0, x->len, omega,
@@ -765,7 +786,7 @@ extern "C" int b200_relax(b200_ctx_t ctx, b200_csr_t A, b200_vec_t rhs, b200_vec
     B200_REQUIRE(x != tmp && x != rhs && tmp != rhs, "relax: x, tmp and rhs must be distinct vectors");
     B200_REQUIRE(!A->gather_rows, "relax: operator must be square");
     B200_REQUIRE(x->ptr != tmp->ptr, "relax: x and tmp must not alias");
-    GUARD(ctx);
+    GUARD_DEFER(ctx);
 
     // precision combination: 0 = FP64 throughout, 1 = FP32 throughout,
     // 2 = FP32 operator + diagonal sweeping an FP64 iterate (finest level of a mixed hierarchy;
@@ -807,7 +828,10 @@ extern "C" int b200_relax(b200_ctx_t ctx, b200_csr_t A, b200_vec_t rhs, b200_vec
         if (rc) return rc;
         x->gen++; tmp->gen++;
         if (x->owned && tmp->owned && x->cap == tmp->cap) std::swap(x->ptr, tmp->ptr);
-        else B200_CUDA(cudaMemcpyAsync(x->ptr, tmp->ptr, x->len * x->esz, cudaMemcpyDeviceToDevice, ctx->stream));
+        else {
+            if ((rc = tail_flush(ctx))) return rc;
+            B200_CUDA(cudaMemcpyAsync(x->ptr, tmp->ptr, x->len * x->esz, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
         return B200_OK;
     }
     if (mix == 2) {
@@ -834,7 +858,10 @@ extern "C" int b200_relax(b200_ctx_t ctx, b200_csr_t A, b200_vec_t rhs, b200_vec
         if (rc) return rc;
         x->gen++;
         if (x->owned && x->cap == (size_t)A->nrows) std::swap(x->ptr, A->scratch64);
-        else B200_CUDA(cudaMemcpyAsync(x->ptr, A->scratch64, x->len * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        else {
+            if ((rc = tail_flush(ctx))) return rc;
+            B200_CUDA(cudaMemcpyAsync(x->ptr, A->scratch64, x->len * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        }
         if (req.done) product_record(ctx, rhs, x, pslot);
         return B200_OK;
     }
@@ -864,6 +891,7 @@ extern "C" int b200_relax(b200_ctx_t ctx, b200_csr_t A, b200_vec_t rhs, b200_vec
     if (x->owned && tmp->owned && x->cap == tmp->cap) {
         std::swap(x->ptr, tmp->ptr);          // x now holds the new iterate
     } else {
+        if ((rc = tail_flush(ctx))) return rc;
         B200_CUDA(cudaMemcpyAsync(x->ptr, tmp->ptr, x->len * sizeof(double),
                                   cudaMemcpyDeviceToDevice, ctx->stream));
     }

@@ -99,6 +99,12 @@ struct b200_ctx_s {
     int           product_slot0 = -1;     // first of the 4 table slots the products rotate through
     std::vector<size_t> krylov_sizes;     // sizes of the live Krylov workspaces (b200_krylov_*)
 
+    // coarse tail of the V-cycle (tail_kernels.cuh): calls on small operators are deferred into
+    // a command list and run as ONE kernel when the next non-deferrable call arrives
+    void         *tail = nullptr;         // TailArgs (host): the pending commands
+    unsigned int *tail_bar = nullptr;     // device: barrier state of coarse_tail_kernel
+    uint64_t      tail_flushes = 0, tail_commands = 0;
+
     // pinned staging for uploads (csr_upload): two buffers, ping-pong
     void        *stage_host[2]  = {};
     cudaEvent_t  stage_event[2] = {};
@@ -139,6 +145,9 @@ struct b200_ctx_s {
     int64_t opt_pdl           = 1;        // programmatic dependent launch of the solve kernels
     int64_t opt_cycle_graph   = 1;        // the shim's preconditioner wrapper may record CUDA graphs
     int64_t opt_graph_pdl     = 1;        // keep the PDL attribute on launches recorded into a graph
+    int64_t opt_coarse_tail   = 1;        // defer calls on small operators into one cooperative kernel
+    int64_t opt_tail_max_nnz  = 1500000;  // ... "small": at most this many non-zeros
+    int64_t opt_tail_max_vec  = 262144;   // ... element-wise x = 0 sweeps: at most this many entries
     int64_t opt_fused_krylov  = 1;        // the C++ binding's cg / bicgstab use the fused b200_cg_* / b200_bicg_* steps
 
     // CUDA-graph recording of a call sequence (b200_graph_*)

@@ -63,10 +63,20 @@ struct ProfScope {
     }
 };
 
+// ---- implemented in api_tail.cu: deferred execution of calls on small operators --------------
+int  tail_flush(b200_ctx_t ctx);        // run the pending commands (one launch); no-op if none
+void tail_destroy(b200_ctx_t ctx);
+bool tail_enabled(b200_ctx_t ctx);
+bool tail_accepts_csr(b200_ctx_t ctx, b200_csr_t A);
+int  tail_enqueue_relax_zero(b200_ctx_t ctx, size_t n, double omega, const double *d, const double *f, double *x);
+int  tail_enqueue_gemv(b200_ctx_t ctx, int n, const double *Ainv, const double *rhs, double *x);
+
 // Lazy clear bookkeeping ------------------------------------------------------
 inline int materialize(b200_vec_t v) {
     if (v->zero_pending) {
         if (v->len) {
+            const int trc = tail_flush(v->ctx);       // the memset must follow what was deferred
+            if (trc) return trc;
             ProfScope prof(v->ctx, B200_PROF_MEMSET, (int64_t)v->len, 1, 0);
             B200_CUDA(cudaMemsetAsync(v->ptr, 0, v->len * v->esz, v->ctx->stream));
         }
@@ -272,7 +282,18 @@ inline bool same_layout(b200_vec_t a, b200_vec_t b) {
     B200_REQUIRE(!(ctx)->dist, what ": FP32 objects are not supported on a distributed context")
 #define NOT_RECORDING(ctx, what)                                                        \
     B200_REQUIRE(!(ctx)->recording, what ": not allowed while a graph is being recorded")
-#define GUARD(ctx)                                                             \
+// Every entry point that touches the device runs under GUARD: the context's device is made
+// current and whatever was deferred into the coarse-tail list is launched first, so effects
+// reach the stream in call order.  The four entry points that may themselves be deferred
+// (b200_spmv, b200_residual, b200_relax, b200_coarse_solve) use GUARD_DEFER and flush on
+// every path that launches immediately.
+#define GUARD_DEFER(ctx)                                                       \
     DeviceGuard guard__((ctx)->device);                                        \
     if (!guard__.ok) return fail(B200_ECUDA, "cudaSetDevice failed")
+#define GUARD(ctx)                                                             \
+    GUARD_DEFER(ctx);                                                          \
+    do {                                                                       \
+        const int trc__ = ::b200::tail_flush(ctx);                             \
+        if (trc__) return trc__;                                               \
+    } while (0)
 #define B200_BAD_MIX(what) ::b200::fail(B200_EINVAL, what ": unsupported precision combination")

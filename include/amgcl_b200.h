@@ -82,10 +82,18 @@ int b200_ctx_device(b200_ctx_t ctx, int *device);
 
 /* Block the host until all work issued on the context's stream is done. */
 int b200_ctx_sync(b200_ctx_t ctx);
+/* Calls on small operators may be deferred (option "coarse_tail"); they reach the stream when
+ * the next call that cannot be deferred is made -- every host-synchronous call, b200_ctx_sync,
+ * and this one.  Call it before handing the stream to code that does not go through this
+ * library (recording an event of your own, say). */
+int b200_ctx_flush(b200_ctx_t ctx);
 
 /* Number of kernels launched through this context since creation / reset. */
 int b200_ctx_launch_count(b200_ctx_t ctx, uint64_t *count);
 int b200_ctx_reset_launch_count(b200_ctx_t ctx);
+
+/* Coarse tail statistics: launches of the tail kernel and calls they executed. */
+int b200_tail_stats(b200_ctx_t ctx, uint64_t *flushes, uint64_t *commands);
 
 /* Per-launch device timing of the CSR streaming kernels (the reference's
  * cuda_clock / AMGCL_TIC hooks, cuda.hpp:809-838, only see launch time): between
@@ -98,6 +106,7 @@ int b200_ctx_reset_launch_count(b200_ctx_t ctx);
 #define B200_PROF_RELAX_ZERO  21   /* x = omega*diag.*rhs shortcut of the smoother     */
 #define B200_PROF_COARSE      22   /* dense GEMV of the coarsest-level solve           */
 #define B200_PROF_MEMSET      23   /* materialised lazy clear                          */
+#define B200_PROF_TAIL        24   /* coarse tail: nrows = calls run by the one kernel  */
 #define B200_PROF_COMM        30   /* multi-GPU exchange (pack + NCCL collective)      */
 typedef struct {
     int64_t nrows, ncols, nnz;
@@ -163,6 +172,11 @@ int b200_split_destroy(b200_split_t sp);
  *                      reports "not recording" and existing graphs are not replayed
  *   "graph_pdl"        1 = launches recorded into a graph keep the PDL attribute (default;
  *                      env B200_GRAPH_PDL)
+ *   "coarse_tail"      1 = calls on small operators (at most "tail_max_nnz" non-zeros, default
+ *                      1.5e6; x = 0 sweeps on at most "tail_max_vec" entries) are deferred and run
+ *                      together as ONE cooperative kernel with device-wide barriers between them
+ *                      when the next call that cannot be deferred arrives (default); 0 = every
+ *                      call launches its own kernel.  Results are bit-identical either way.
  *   "fused_krylov"     1 = the C++ binding's solver::cg / solver::bicgstab specialisations run the
  *                      fused b200_cg_* / b200_bicg_* steps (default; env B200_FUSED_KRYLOV),
  *                      0 = they issue the reference's sequence of primitives

@@ -169,6 +169,59 @@ def test_variants_and_fusion_agree(ctx):
         assert it == it0 and abs(r - r0) <= 1e-9 * r0 and rel_err(x, x0) < 1e-12
 
 
+@pytest.mark.parametrize("n", [12, 32, 64])
+@pytest.mark.parametrize("relax,krylov", [("damped_jacobi", "cg"), ("spai0", "bicgstab")])
+def test_coarse_tail_is_bit_transparent(ctx, n, relax, krylov):
+    """Option "coarse_tail": calls on small operators are deferred and run as ONE cooperative
+    kernel (device-wide barriers instead of kernel boundaries).  Same arithmetic in the same
+    order: the solve and the V-cycle alone must give the same bits, with fewer launches."""
+    ptr, col, val, rhs = ab.poisson3d(n)
+    rng = np.random.default_rng(11)
+    f = rng.uniform(-1, 1, rhs.size)
+    out = {}
+    try:
+        for tail in (0, 1):
+            ctx.set_option("coarse_tail", tail)
+            S = ab.DropinSolver(ptr, col, val, relax, krylov, ctx=ctx)
+            S.solve(rhs)
+            l0, t0 = ctx.launches, ctx.tail_stats()
+            x, it, res = S.solve(rhs)
+            l1, t1 = ctx.launches, ctx.tail_stats()
+            out[tail] = (x, it, res, S.apply_precond(f), l1 - l0, t1[0] - t0[0], t1[1] - t0[1])
+            S.close()
+    finally:
+        ctx.set_option("coarse_tail", 1)
+    (x0, it0, r0, m0, l0, f0, c0), (x1, it1, r1, m1, l1, f1, c1) = out[0], out[1]
+    assert (it1, r1) == (it0, r0) and np.array_equal(x1, x0) and np.array_equal(m1, m0)
+    assert f0 == 0 and c0 == 0 and f1 >= it1 and c1 >= 3 * f1        # several calls per tail launch
+    assert l1 < l0 and l0 - l1 == c1 - f1                             # each deferred call saved a launch
+
+
+def test_deferred_calls_keep_call_order(ctx):
+    """Deferred (small-operator) calls interleaved with immediate ones and with host reads."""
+    ptr, col, val, _ = ab.poisson3d(10)
+    n = ptr.size - 1
+    import scipy.sparse as sp
+    M = sp.csr_matrix((val, col, ptr), shape=(n, n))
+    rng = np.random.default_rng(12)
+    a, b = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
+    A = ctx.csr(n, n, ptr, col, val)
+    va, vb, vy, vz = ctx.vector(a), ctx.vector(b), ctx.vector(n), ctx.vector(n)
+    before = ctx.tail_stats()
+    ctx.spmv(1.0, A, va, 0.0, vy)          # deferred
+    ctx.residual(vb, A, vy, vz)            # deferred, reads the deferred result
+    ctx.axpby(2.0, vz, 1.0, vy)            # immediate: flushes first
+    ctx.spmv(1.0, A, vy, 1.0, vz)          # deferred again (beta != 0)
+    got = vz.numpy()                       # host read: flushes
+    y = M @ a
+    z = b - M @ y
+    y = 2.0 * z + y
+    want = M @ y + z
+    assert rel_err(got, want) < 1e-12
+    after = ctx.tail_stats()
+    assert after[0] - before[0] == 2 and after[1] - before[1] == 3
+
+
 def test_dependent_launch_is_bit_transparent(ctx):
     """Programmatic dependent launch only changes when kernels are scheduled: the solve with
     and without it must be bit-identical (same arithmetic, same order)."""

@@ -84,8 +84,7 @@ def main():
     for n in sizes:
         ptr, col, val, rhs = ab.poisson3d(n)
         nrows = ptr.size - 1
-        for mode, min_rows, p2p in (("finest", nrows, 1), ("all>=2000", 2000, 1),
-                                    ("finest", nrows, 0), ("all>=2000", 2000, 0)):
+        for mode, min_rows, p2p in (("finest", nrows, 1), ("all>=2000", 2000, 1), ("all>=2000", 2000, 0)):
             if world == 1 and p2p == 0:
                 continue
             for relax, krylov in (("damped_jacobi", "cg"), ("spai0", "bicgstab")):
