@@ -46,10 +46,13 @@ int tail_flush(b200_ctx_t ctx) {
     TailArgs *t = static_cast<TailArgs *>(ctx->tail);
     if (!t || t->n == 0) return B200_OK;
     if (!ctx->tail_bar) {
-        B200_CUDA(cudaMalloc(&ctx->tail_bar, 2 * sizeof(unsigned int)));
-        B200_CUDA(cudaMemsetAsync(ctx->tail_bar, 0, 2 * sizeof(unsigned int), ctx->stream));
+        B200_CUDA(cudaMalloc(&ctx->tail_bar, sizeof(unsigned long long)));
+        B200_CUDA(cudaMemsetAsync(ctx->tail_bar, 0, sizeof(unsigned long long), ctx->stream));
+        ctx->tail_bar_count = 0;
     }
     t->bar = ctx->tail_bar;
+    t->bar_base = ctx->tail_bar_count;
+    ctx->tail_bar_count += (unsigned long long)(t->n - 1) * (unsigned long long)ctx->sm_count;
     int64_t work = 0;
     for (int k = 0; k < t->n; ++k) work += t->cmd[k].nrows;
     const int n = t->n;
@@ -58,7 +61,7 @@ int tail_flush(b200_ctx_t ctx) {
     ProfScope prof(ctx, B200_PROF_TAIL, (int64_t)n, 1, work);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)ctx->sm_count);       // one CTA per SM, all co-resident
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(kTailThreads);
     cfg.dynamicSmemBytes = 0;
     cfg.stream = ctx->stream;
     cudaLaunchAttribute attr[1];

@@ -102,7 +102,8 @@ struct b200_ctx_s {
     // coarse tail of the V-cycle (tail_kernels.cuh): calls on small operators are deferred into
     // a command list and run as ONE kernel when the next non-deferrable call arrives
     void         *tail = nullptr;         // TailArgs (host): the pending commands
-    unsigned int *tail_bar = nullptr;     // device: barrier state of coarse_tail_kernel
+    unsigned long long *tail_bar = nullptr;   // device: arrival counter of coarse_tail_kernel's barriers
+    unsigned long long  tail_bar_count = 0;   // ... its value once everything launched so far has run
     uint64_t      tail_flushes = 0, tail_commands = 0;
 
     // pinned staging for uploads (csr_upload): two buffers, ping-pong

@@ -159,6 +159,7 @@ def test_smoother_sweep_leaves_the_product_for_the_next_dot(ctx, system):
     K = ab.Krylov(ctx, n)
     rhs, x, tmp, dv = ctx.vector(f), ctx.vector(x0), ctx.vector(n), ctx.vector(d)
     ctx.relax(A, rhs, x, tmp, dv, 0.72)
+    ctx.flush()
     xn = x0 + 0.72 * d * (f - M @ x0)
     before = ctx.launches
     got = ctx.dot(rhs, x)
@@ -174,6 +175,7 @@ def test_smoother_sweep_leaves_the_product_for_the_next_dot(ctx, system):
     K.close()
     # no workspace of this size: nothing extra is computed, dot launches its own kernel
     ctx.relax(A, rhs, x, tmp, dv, 0.72)
+    ctx.flush()                                         # (a small operator: the sweep was deferred)
     before = ctx.launches
     ctx.dot(rhs, x)
     assert ctx.launches == before + 1
