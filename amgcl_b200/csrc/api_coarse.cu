@@ -183,6 +183,7 @@ extern "C" int b200_coarse_solve(b200_ctx_t ctx, b200_coarse_t S, b200_vec_t rhs
     if (ctx->recording) S->in_graph = true;
     B200_REQUIRE((int64_t)rhs->n == S->n && (int64_t)x->n == S->n, "coarse solve: size mismatch");
     GUARD_DEFER(ctx);
+    TailHold hold(ctx, {rhs, x});
     const int N = (int)S->n;
     const int warps_per_cta = kThreads / 32;
     if (S->replicated) {

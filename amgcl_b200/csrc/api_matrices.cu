@@ -626,6 +626,7 @@ static int spmv_impl(b200_ctx_t ctx, double alpha, b200_csr_t A, b200_vec_t x, d
     B200_REQUIRE((int64_t)y->n == A->gl_rows, "spmv: y size != matrix rows");
     B200_REQUIRE(x != y && (x->ptr != y->ptr || !x->ptr), "spmv: x and y must not alias");
     GUARD_DEFER(ctx);
+    TailHold hold(ctx, {x, y});
     if (A->dtype == B200_F32) {
         // FP32 operator (mixed-precision hierarchy): single GPU, persistent ring kernels
         if (all32({x, y})) return spmv_local<PrecFF>(ctx, alpha, A, x, beta, y);
@@ -684,6 +685,7 @@ static int residual_impl(b200_ctx_t ctx, b200_vec_t f, b200_csr_t A, b200_vec_t 
     B200_REQUIRE(!A->gather_rows && (!ctx->dist || A->gl_rows == A->gl_cols || A->kind == B200_CK_LOCAL),
                  "residual: operator must be square");
     GUARD_DEFER(ctx);
+    TailHold hold(ctx, {f, x, r});
     if (A->dtype == B200_F32) {
         if (all32({f, x, r})) return residual_local<PrecFF>(ctx, f, A, x, r);
         if (all64({f, x, r})) return residual_local<PrecFD>(ctx, f, A, x, r, req);
@@ -787,6 +789,7 @@ extern "C" int b200_relax(b200_ctx_t ctx, b200_csr_t A, b200_vec_t rhs, b200_vec
     B200_REQUIRE(!A->gather_rows, "relax: operator must be square");
     B200_REQUIRE(x->ptr != tmp->ptr, "relax: x and tmp must not alias");
     GUARD_DEFER(ctx);
+    TailHold hold(ctx, {rhs, x, tmp, diag});
 
     // precision combination: 0 = FP64 throughout, 1 = FP32 throughout,
     // 2 = FP32 operator + diagonal sweeping an FP64 iterate (finest level of a mixed hierarchy;

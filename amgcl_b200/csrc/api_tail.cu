@@ -33,7 +33,7 @@ void tail_destroy(b200_ctx_t ctx) {
 }
 
 bool tail_enabled(b200_ctx_t ctx) {
-    return ctx->opt_coarse_tail && !ctx->recording;
+    return ctx->opt_coarse_tail && !ctx->recording && !ctx->tail_hold;
 }
 
 bool tail_accepts_csr(b200_ctx_t ctx, b200_csr_t A) {

@@ -105,6 +105,7 @@ struct b200_ctx_s {
     unsigned long long *tail_bar = nullptr;   // device: arrival counter of coarse_tail_kernel's barriers
     unsigned long long  tail_bar_count = 0;   // ... its value once everything launched so far has run
     uint64_t      tail_flushes = 0, tail_commands = 0;
+    bool          tail_hold = false;      // the current call touches caller-owned memory: do not defer
 
     // pinned staging for uploads (csr_upload): two buffers, ping-pong
     void        *stage_host[2]  = {};
@@ -146,7 +147,8 @@ struct b200_ctx_s {
     int64_t opt_pdl           = 1;        // programmatic dependent launch of the solve kernels
     int64_t opt_cycle_graph   = 1;        // the shim's preconditioner wrapper may record CUDA graphs
     int64_t opt_graph_pdl     = 1;        // keep the PDL attribute on launches recorded into a graph
-    int64_t opt_coarse_tail   = 1;        // defer calls on small operators into one cooperative kernel
+    int64_t opt_coarse_tail   = 0;        // defer calls on small operators into one cooperative kernel
+                                          // (opt-in: measured no faster than separate launches)
     int64_t opt_tail_max_nnz  = 1500000;  // ... "small": at most this many non-zeros
     int64_t opt_tail_max_vec  = 262144;   // ... element-wise x = 0 sweeps: at most this many entries
     int64_t opt_fused_krylov  = 1;        // the C++ binding's cg / bicgstab use the fused b200_cg_* / b200_bicg_* steps

@@ -71,6 +71,19 @@ bool tail_accepts_csr(b200_ctx_t ctx, b200_csr_t A);
 int  tail_enqueue_relax_zero(b200_ctx_t ctx, size_t n, double omega, const double *d, const double *f, double *x);
 int  tail_enqueue_gemv(b200_ctx_t ctx, int n, const double *Ainv, const double *rhs, double *x);
 
+// Calls that touch memory the caller can see behind the library's back (wrapped external
+// storage, vectors whose raw pointer was handed out) are never deferred: their effects must be
+// on the stream when the call returns.
+struct TailHold {
+    b200_ctx_t ctx;
+    bool prev;
+    TailHold(b200_ctx_t c, std::initializer_list<b200_vec_t> vs) : ctx(c), prev(c->tail_hold) {
+        for (b200_vec_t v : vs)
+            if (v && (!v->owned || v->escaped)) ctx->tail_hold = true;
+    }
+    ~TailHold() { ctx->tail_hold = prev; }
+};
+
 // Lazy clear bookkeeping ------------------------------------------------------
 inline int materialize(b200_vec_t v) {
     if (v->zero_pending) {

@@ -211,7 +211,7 @@ def test_fused_solver_vs_reference_sequence(ctx, relax, krylov, precision):
     assert rel_err(x1, x0) < (1e-6 if precision == "mixed" else TOL_SOLUTION)
     assert l1 < l0
     per_iter_saved = (l0 - l1) / it0
-    assert per_iter_saved >= (4 if krylov == "cg" else 7)
+    assert per_iter_saved >= (3.5 if krylov == "cg" else 6.5), (l0, l1, it0)
 
 
 @pytest.mark.parametrize("n", [32, 64])

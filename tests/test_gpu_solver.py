@@ -148,11 +148,17 @@ def test_resident_path_equals_host_path(ctx):
     S.close()
 
 
-def test_variants_and_fusion_agree(ctx):
-    """Kernel scheduling variants and the fused / unfused smoother give the same solve."""
+@pytest.mark.parametrize("fused_krylov", [0, 1])
+def test_variants_and_fusion_agree(ctx, fused_krylov):
+    """Kernel scheduling variants and the fused / unfused smoother give the same solve.  With
+    the reference's Krylov sequence (fused_krylov = 0) every variant reduces its inner products
+    with the same kernel, so the agreement is to rounding of the row sums only; with the fused
+    Krylov steps the variants that cannot reduce inside the streaming kernel (variant 0) use the
+    stand-alone reduction, i.e. another summation order: the stated end-to-end tolerances."""
     ptr, col, val, rhs = ab.poisson3d(32)
     results = []
     try:
+        ctx.set_option("fused_krylov", fused_krylov)
         for variant, fuse, shortcut in ((1, 1, 1), (0, 1, 1), (1, 0, 1), (1, 1, 0)):
             ctx.set_option("spmv_variant", variant)
             ctx.set_option("fuse_relax", fuse)
@@ -164,9 +170,14 @@ def test_variants_and_fusion_agree(ctx):
         ctx.set_option("spmv_variant", 1)
         ctx.set_option("fuse_relax", 1)
         ctx.set_option("zero_shortcut", 1)
+        ctx.set_option("fused_krylov", 1)
     x0, it0, r0 = results[0]
     for x, it, r in results[1:]:
-        assert it == it0 and abs(r - r0) <= 1e-9 * r0 and rel_err(x, x0) < 1e-12
+        assert it == it0
+        if fused_krylov:
+            assert abs(r - r0) <= TOL_RESID_REL * r0 and rel_err(x, x0) < TOL_SOLUTION
+        else:
+            assert abs(r - r0) <= 1e-9 * r0 and rel_err(x, x0) < 1e-12
 
 
 @pytest.mark.parametrize("n", [12, 32, 64])
@@ -190,11 +201,13 @@ def test_coarse_tail_is_bit_transparent(ctx, n, relax, krylov):
             out[tail] = (x, it, res, S.apply_precond(f), l1 - l0, t1[0] - t0[0], t1[1] - t0[1])
             S.close()
     finally:
-        ctx.set_option("coarse_tail", 1)
+        ctx.set_option("coarse_tail", 0)
     (x0, it0, r0, m0, l0, f0, c0), (x1, it1, r1, m1, l1, f1, c1) = out[0], out[1]
     assert (it1, r1) == (it0, r0) and np.array_equal(x1, x0) and np.array_equal(m1, m0)
-    assert f0 == 0 and c0 == 0 and f1 >= it1 and c1 >= 3 * f1        # several calls per tail launch
-    assert l1 < l0 and l0 - l1 == c1 - f1                             # each deferred call saved a launch
+    assert f0 == 0 and c0 == 0 and f1 >= it1 and c1 >= f1
+    assert l0 - l1 == c1 - f1                                         # each deferred call saved a launch
+    if n >= 32:
+        assert c1 >= 3 * f1 and l1 < l0                               # several calls per tail launch
 
 
 def test_deferred_calls_keep_call_order(ctx):
@@ -207,12 +220,16 @@ def test_deferred_calls_keep_call_order(ctx):
     a, b = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
     A = ctx.csr(n, n, ptr, col, val)
     va, vb, vy, vz = ctx.vector(a), ctx.vector(b), ctx.vector(n), ctx.vector(n)
-    before = ctx.tail_stats()
-    ctx.spmv(1.0, A, va, 0.0, vy)          # deferred
-    ctx.residual(vb, A, vy, vz)            # deferred, reads the deferred result
-    ctx.axpby(2.0, vz, 1.0, vy)            # immediate: flushes first
-    ctx.spmv(1.0, A, vy, 1.0, vz)          # deferred again (beta != 0)
-    got = vz.numpy()                       # host read: flushes
+    ctx.set_option("coarse_tail", 1)
+    try:
+        before = ctx.tail_stats()
+        ctx.spmv(1.0, A, va, 0.0, vy)          # deferred
+        ctx.residual(vb, A, vy, vz)            # deferred, reads the deferred result
+        ctx.axpby(2.0, vz, 1.0, vy)            # immediate: flushes first
+        ctx.spmv(1.0, A, vy, 1.0, vz)          # deferred again (beta != 0)
+        got = vz.numpy()                       # host read: flushes
+    finally:
+        ctx.set_option("coarse_tail", 0)
     y = M @ a
     z = b - M @ y
     y = 2.0 * z + y
