@@ -260,6 +260,7 @@ static int64_t *option_slot(b200_ctx_t ctx, const char *key) {
     if (!strcmp(key, "graph_pdl")) return &ctx->opt_graph_pdl;
     if (!strcmp(key, "fused_krylov")) return &ctx->opt_fused_krylov;
     if (!strcmp(key, "coarse_tail")) return &ctx->opt_coarse_tail;
+    if (!strcmp(key, "poll_scalars")) return &ctx->opt_poll_scalars;
     if (!strcmp(key, "tail_max_nnz")) return &ctx->opt_tail_max_nnz;
     if (!strcmp(key, "tail_max_vec")) return &ctx->opt_tail_max_vec;
     return nullptr;

@@ -185,7 +185,6 @@ int halo_exchange(b200_ctx_t ctx, b200_csr_t A, const double *x, HaloArgs &a) {
         if (trc) return trc;
     }
     a.xh = A->halo; a.nloc = (int)A->n_loc;
-    a.blk_order = A->blk_order;
     if (A->S == 0) return B200_OK;
     if (ctx->p2p) {
         const int par = (int)(A->seq & 1);
@@ -204,7 +203,6 @@ int halo_exchange(b200_ctx_t ctx, b200_csr_t A, const double *x, HaloArgs &a) {
         a.nranks = ctx->nranks;
         a.push_ticket = ctx->push_ticket;
         a.push_seq = mask ? seq : 0;
-        a.blk_halo = A->blk_halo;
         a.wait_flags = flag_at(A->pb_local, par, 0);
         a.wait_mask = mask;
         a.wait_seq = seq;

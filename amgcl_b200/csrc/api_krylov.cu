@@ -48,6 +48,9 @@ int scal_create(b200_ctx_t ctx) {
     B200_CUDA(cudaHostAlloc(&ctx->scal_h, kScalSlots * sizeof(double), cudaHostAllocMapped));
     memset(ctx->scal_h, 0, kScalSlots * sizeof(double));
     B200_CUDA(cudaHostGetDevicePointer(&ctx->scal_hd, ctx->scal_h, 0));
+    B200_CUDA(cudaHostAlloc(&ctx->scal_ready_h, kScalSlots * sizeof(unsigned long long), cudaHostAllocMapped));
+    memset(ctx->scal_ready_h, 0, kScalSlots * sizeof(unsigned long long));
+    B200_CUDA(cudaHostGetDevicePointer(&ctx->scal_ready_hd, ctx->scal_ready_h, 0));
     B200_CUDA(cudaMalloc(&ctx->red_partial, (size_t)kMaxRed * kDotMaxBlocks * sizeof(double)));
     B200_CUDA(cudaMalloc(&ctx->red_ticket, sizeof(unsigned int)));
     B200_CUDA(cudaMemset(ctx->red_ticket, 0, sizeof(unsigned int)));
@@ -59,6 +62,8 @@ int scal_create(b200_ctx_t ctx) {
 void scal_destroy(b200_ctx_t ctx) {
     if (ctx->scal_d) cudaFree(ctx->scal_d);
     if (ctx->scal_h) cudaFreeHost(ctx->scal_h);
+    if (ctx->scal_ready_h) cudaFreeHost(ctx->scal_ready_h);
+    ctx->scal_ready_h = ctx->scal_ready_hd = nullptr;
     if (ctx->red_partial) cudaFree(ctx->red_partial);
     if (ctx->red_ticket) cudaFree(ctx->red_ticket);
     if (ctx->scal_x_table) cudaFree(ctx->scal_x_table);
@@ -94,6 +99,7 @@ void red_out(b200_ctx_t ctx, int nred, const int *slots, RedOut &o, bool across_
     for (int k = 0; k < nred; ++k) {
         o.dev[k] = ctx->scal_d + slots[k];
         o.host[k] = (host_mask >> k) & 1u ? ctx->scal_hd + slots[k] : nullptr;
+        o.host_seq[k] = ctx->scal_ready_hd + slots[k];
         o.slot[k] = slots[k];
         o.seq[k] = ++ctx->scal_seq[slots[k]];
     }
@@ -185,9 +191,35 @@ static SaveSlot save_slot(b200_ctx_t ctx, int slot) {
 }
 
 int scal_read(b200_ctx_t ctx, int slot, bool mirrored, double *out) {
-    if (!mirrored)
+    if (!mirrored) {
         B200_CUDA(cudaMemcpyAsync(ctx->scal_h + slot, ctx->scal_d + slot, sizeof(double),
                                   cudaMemcpyDeviceToHost, ctx->stream));
+        B200_CUDA(cudaStreamSynchronize(ctx->stream));
+        *out = *reinterpret_cast<volatile double *>(ctx->scal_h + slot);
+        return B200_OK;
+    }
+    // The kernel that finishes the reduction writes the value into mapped host memory and then
+    // releases a "ready" word carrying the launch's sequence number: poll that word instead of
+    // synchronising the stream (a cudaStreamSynchronize costs ~10 us of driver latency, once per
+    // Krylov iteration).  The stream is queried now and then so a failed launch cannot hang us.
+    if (ctx->opt_poll_scalars) {
+        const unsigned long long want = ctx->scal_seq[slot];
+        volatile unsigned long long *ready = ctx->scal_ready_h + slot;
+        for (unsigned long long spins = 1;; ++spins) {
+            if (*ready >= want) {
+                *out = *reinterpret_cast<volatile double *>(ctx->scal_h + slot);
+                return B200_OK;
+            }
+            if ((spins & 0x3ffff) == 0) {
+                const cudaError_t q = cudaStreamQuery(ctx->stream);
+                if (q == cudaSuccess) break;                 // stream drained: the value must be there
+                if (q != cudaErrorNotReady) return cuda_fail(q, "cudaStreamQuery", __FILE__, __LINE__);
+            }
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+        }
+    }
     B200_CUDA(cudaStreamSynchronize(ctx->stream));
     *out = *reinterpret_cast<volatile double *>(ctx->scal_h + slot);
     return B200_OK;

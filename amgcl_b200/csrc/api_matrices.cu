@@ -169,7 +169,12 @@ static int csr_upload(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *p
     const size_t ptr_bytes = ((size_t)nrows + 1 + 8) * sizeof(int);
     const size_t col_bytes = ((size_t)nnz + 8) * sizeof(int);
     const size_t val_bytes = ((size_t)nnz + 8) * sizeof(Val);
-    const size_t blk_bytes = ((size_t)nblocks + 1) * sizeof(int2);
+    const size_t blk_bytes = ((size_t)nblocks + 1) * sizeof(int4);
+    // self-contained block descriptors in walk order (here: the natural order)
+    std::vector<int4> blk4((size_t)nblocks + 1);
+    for (int64_t b = 0; b < nblocks; ++b)
+        blk4[(size_t)b] = make_int4(blk[(size_t)b].x, blk[(size_t)b + 1].x, blk[(size_t)b].y, blk[(size_t)b + 1].y);
+    blk4[(size_t)nblocks] = make_int4((int)nrows, (int)nrows, (int)nnz, (int)nnz);
     auto cleanup = [&]() {
         if (A->ptr) cudaFree(A->ptr);
         if (A->col) cudaFree(A->col);
@@ -197,7 +202,7 @@ static int csr_upload(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *p
         CSR_CUDA(staged_upload(ctx, A->col, col, (size_t)nnz));      // narrowed to int32 on the way
         CSR_CUDA(staged_upload(ctx, static_cast<Val *>(A->val), val, (size_t)nnz));
     }
-    CSR_CUDA(cudaMemcpyAsync(A->blk, blk.data(), blk_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CSR_CUDA(cudaMemcpyAsync(A->blk, blk4.data(), blk_bytes, cudaMemcpyHostToDevice, ctx->stream));
     CSR_CUDA(cudaStreamSynchronize(ctx->stream));   // host staging buffers die here
 #undef CSR_CUDA
     A->bytes = ptr_bytes + col_bytes + val_bytes + blk_bytes;
@@ -212,10 +217,8 @@ static void csr_free(b200_csr_t A) {
     if (A->val) cudaFree(A->val);
     if (A->blk) cudaFree(A->blk);
     if (A->send_idx) cudaFree(A->send_idx);
-    if (A->blk_halo) cudaFree(A->blk_halo);
     if (A->halo_owned) cudaFree(A->halo_owned);
     if (A->ybuf) cudaFree(A->ybuf);
-    if (A->blk_order) cudaFree(A->blk_order);
     if (A->scratch64) cudaFree(A->scratch64);
     if (A->pb_local) peer_release(A->ctx, A->pb_local, A->pb_peer);
     if (A->gb_local) peer_release(A->ctx, A->gb_local, A->gb_peer);
@@ -293,27 +296,23 @@ static int csr_create(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *p
         // order that puts them last so the peers' pushes land while interior rows are computed
         RowBlockPlan plan;
         build_plan(sp.nrows, sp.ptr.data(), A->lanes, A->nnz_cap, plan);
-        const size_t nb = (size_t)std::max<int64_t>(1, A->nblocks);
-        std::vector<unsigned char> bh(nb, 0);
-        std::vector<int> order;
-        order.reserve(nb);
+        std::vector<int4> inner, outer;
         if ((int64_t)plan.blk.size() - 1 == A->nblocks) {
             for (int64_t b = 0; b < A->nblocks; ++b) {
-                const int64_t e0 = plan.blk[(size_t)b].y, e1 = plan.blk[(size_t)b + 1].y;
-                for (int64_t e = e0; e < e1 && !bh[(size_t)b]; ++e)
-                    if (sp.col[(size_t)e] >= sp.n_loc) bh[(size_t)b] = 1;
+                const int2 lo = plan.blk[(size_t)b], hi = plan.blk[(size_t)b + 1];
+                bool halo = false;
+                for (int64_t e = lo.y; e < hi.y && !halo; ++e) halo = sp.col[(size_t)e] >= sp.n_loc;
+                if (halo) outer.push_back(make_int4(~lo.x, hi.x, lo.y, hi.y));
+                else inner.push_back(make_int4(lo.x, hi.x, lo.y, hi.y));
             }
+            inner.insert(inner.end(), outer.begin(), outer.end());
+            if (!inner.empty())
+                DCSR_CUDA(cudaMemcpyAsync(A->blk, inner.data(), inner.size() * sizeof(int4),
+                                          cudaMemcpyHostToDevice, ctx->stream));
         } else {
-            std::fill(bh.begin(), bh.end(), 1);      // cannot happen; be safe: every block waits
+            csr_free(A);                             // cannot happen: same inputs, same plan
+            return fail(B200_EINVAL, "internal error: row-block plans differ");
         }
-        for (int64_t b = 0; b < A->nblocks; ++b) if (!bh[(size_t)b]) order.push_back((int)b);
-        for (int64_t b = 0; b < A->nblocks; ++b) if (bh[(size_t)b]) order.push_back((int)b);
-        if (order.empty()) order.push_back(0);
-        DCSR_CUDA(cudaMalloc(&A->blk_halo, bh.size()));
-        DCSR_CUDA(cudaMalloc(&A->blk_order, order.size() * sizeof(int)));
-        DCSR_CUDA(cudaMemcpyAsync(A->blk_halo, bh.data(), bh.size(), cudaMemcpyHostToDevice, ctx->stream));
-        DCSR_CUDA(cudaMemcpyAsync(A->blk_order, order.data(), order.size() * sizeof(int),
-                                  cudaMemcpyHostToDevice, ctx->stream));
         DCSR_CUDA(cudaStreamSynchronize(ctx->stream));
         // who exchanges with whom: the symmetric closure of "rows of p reference columns of o"
         // (identical on every rank: derived from the global matrix).  A pair exchanges flags in
@@ -451,8 +450,7 @@ static int halo_into(b200_ctx_t ctx, b200_csr_t A, CsrArgs &a) {
     const int rc = halo_exchange(ctx, A, a.x, h);
     if (rc) return rc;
     a.xh = h.xh; a.nloc = h.nloc;
-    a.blk_order = h.blk_order;
-    a.blk_halo = h.blk_halo; a.wait_flags = h.wait_flags; a.wait_mask = h.wait_mask; a.wait_seq = h.wait_seq;
+    a.wait_flags = h.wait_flags; a.wait_mask = h.wait_mask; a.wait_seq = h.wait_seq;
     a.send_idx = h.send_idx; a.n_send = h.n_send; a.nranks = h.nranks;
     for (int q = 0; q < kMaxRanks; ++q) { a.push_data[q] = h.push_data[q]; a.push_flag[q] = h.push_flag[q]; }
     a.push_ticket = h.push_ticket; a.push_seq = h.push_seq;

@@ -82,6 +82,8 @@ struct b200_ctx_s {
     double       *scal_d  = nullptr;      // [kScalSlots] device
     double       *scal_h  = nullptr;      // [kScalSlots] pinned + mapped host mirror
     double       *scal_hd = nullptr;      // device alias of scal_h
+    unsigned long long *scal_ready_h  = nullptr;   // [kScalSlots] mapped: seq of the value in scal_h
+    unsigned long long *scal_ready_hd = nullptr;   // device alias
     double       *red_partial = nullptr;  // [kMaxRed * kDotMaxBlocks] per-CTA partial sums
     unsigned int *red_ticket  = nullptr;  // device, self-resetting
     bool          scal_used[b200::kScalSlots] = {};
@@ -151,6 +153,7 @@ struct b200_ctx_s {
                                           // (opt-in: measured no faster than separate launches)
     int64_t opt_tail_max_nnz  = 1500000;  // ... "small": at most this many non-zeros
     int64_t opt_tail_max_vec  = 262144;   // ... element-wise x = 0 sweeps: at most this many entries
+    int64_t opt_poll_scalars  = 1;        // host reads in-kernel reduction results by polling mapped memory
     int64_t opt_fused_krylov  = 1;        // the C++ binding's cg / bicgstab use the fused b200_cg_* / b200_bicg_* steps
 
     // CUDA-graph recording of a call sequence (b200_graph_*)
@@ -214,8 +217,6 @@ struct b200_csr_s {
     size_t     gb_half  = 0;
     unsigned long long seq = 0;       // halo exchanges done so far (same on every rank)
     unsigned long long gseq = 0;      // row gathers done so far
-    unsigned char *blk_halo = nullptr;  // HALO: [nblocks] block gathers remote columns
-    int       *blk_order = nullptr;     // HALO: [nblocks] walk order: interior blocks first
     bool       xchg[16] = {};         // ranks this rank exchanges halo values with (symmetric)
     int       *ptr   = nullptr;   // [nrows+1] (+ padding) device
     int       *col   = nullptr;   // [nnz]     (+ padding) device
@@ -229,7 +230,8 @@ struct b200_csr_s {
     int        nnz_cap  = 2048;   // staged non-zeros per block
     int64_t    nblocks  = 0;
     int64_t    nlong    = 0;      // blocks too long to stage (handled by the strided path)
-    int2      *blk      = nullptr;// [nblocks+1] device: {first row, first nnz} per block
+    int4      *blk      = nullptr;// [nblocks] device, walk order: {first row (~r if the block gathers halo
+                                  //   columns), end row, first nnz, end nnz}; HALO: interior blocks first
     size_t     bytes    = 0;
 };
 

@@ -63,7 +63,8 @@ struct CsrArgsT {
     const int    *ptr;
     const int    *col;
     const typename P::TV *val;
-    const int2   *blk;    // [nblocks+1]: {first row, first non-zero} of each block
+    const int4   *blk;    // [nblocks] in WALK ORDER: {first row (~first row if the block gathers
+                          //   halo columns), end row, first non-zero, end non-zero}
     int           nrows;
     int           nblocks;
     int           rows_cap;
@@ -74,11 +75,10 @@ struct CsrArgsT {
     // multi-GPU, peer-memory transport: the halo is pushed by the peers while this kernel
     // already works on interior rows; a block that gathers remote columns first waits for
     // the flags of the ranks in wait_mask to reach wait_seq (csrc/peer.cuh protocol)
-    const unsigned char      *blk_halo;    // [nblocks] 1 = block references the halo
+    // (such blocks come last in the walk order, so the transfer overlaps the interior rows)
     const unsigned long long *wait_flags;  // flag row of the current parity (16 slots)
     unsigned int              wait_mask;
     unsigned long long        wait_seq;
-    const int                *blk_order;   // [nblocks] walk order: interior blocks first (or nullptr)
     // ... and THIS rank's boundary values are pushed by this very kernel: right after the
     // grid dependency resolves every CTA packs a slice of x[send_idx[.]] into the halo buffers
     // of the ranks that gather them (plain stores over NVLink), the last CTA to finish
@@ -134,24 +134,18 @@ constexpr int kHeaderBytes = 256;   // mbarriers + per-stage block descriptors
 struct BlockDesc {      // written by the producer thread, read by everyone after the wait
     int r0, r1;         // row range
     int e0, e1;         // non-zero range
+    int halo;           // the block gathers columns owned by other ranks
 };
 
 // ---- issue the bulk copies of one row block ----------------------------------
 template <class P>
 __device__ __forceinline__ BlockDesc load_desc(const CsrArgsT<P> &a, int b) {
-    const int2 lo = __ldg(a.blk + b);
-    const int2 hi = __ldg(a.blk + b + 1);
+    const int4 q = __ldg(a.blk + b);       // one 16-byte load: nothing else to chase
     BlockDesc d;
-    d.r0 = lo.x; d.e0 = lo.y;
-    d.r1 = hi.x; d.e1 = hi.y;
+    d.halo = q.x < 0;
+    d.r0 = q.x < 0 ? ~q.x : q.x;
+    d.r1 = q.y; d.e0 = q.z; d.e1 = q.w;
     return d;
-}
-
-// position in the walk -> row block (multi-GPU: interior blocks first, halo blocks last)
-template <bool HALO, class P>
-__device__ __forceinline__ int block_at(const CsrArgsT<P> &a, int pos) {
-    if (HALO && a.blk_order) return __ldg(a.blk_order + pos);
-    return pos;
 }
 
 // Returns true if the block was staged (false: too long, use the strided path).
@@ -235,9 +229,9 @@ __device__ __forceinline__ typename P::TX gather(const CsrArgsT<P> &a,
 // Block until the peers' halo pushes for this exchange have landed (thread 0 polls the
 // flags with acquire semantics, the CTA follows through the barrier).
 template <bool HALO, class P>
-__device__ __forceinline__ void wait_for_halo(const CsrArgsT<P> &a, int b) {
+__device__ __forceinline__ void wait_for_halo(const CsrArgsT<P> &a, const BlockDesc &d) {
     if (!HALO) return;
-    if (a.blk_halo == nullptr || !a.blk_halo[b]) return;      // uniform per CTA
+    if (!d.halo || !a.wait_mask) return;                       // uniform per CTA
     if (threadIdx.x == 0) {
         unsigned int m = a.wait_mask;
         while (m) {
@@ -405,7 +399,8 @@ __device__ __forceinline__ void halo_push(const CsrArgsT<P> &a) {
     }
     __syncthreads();
     if (push_last) {
-        __threadfence_system();
+        // (st.release.sys orders everything that happens-before it -- all CTAs' stores, via
+        // their fences and the ticket -- before the flag)
         if (threadIdx.x < a.nranks && a.push_flag[threadIdx.x])
             xchg_st_release_sys(a.push_flag[threadIdx.x], a.push_seq);
         if (threadIdx.x == 0) *a.push_ticket = 0;
@@ -423,7 +418,6 @@ __device__ __forceinline__ void gather_finish(const CsrArgsT<P> &a) {
     }
     __syncthreads();
     if (gather_last) {
-        __threadfence_system();
         if (threadIdx.x < a.nranks && a.gather_flag[threadIdx.x])
             xchg_st_release_sys(a.gather_flag[threadIdx.x], a.gather_seq);
         if (threadIdx.x == 0) *a.gather_ticket = 0;
@@ -452,10 +446,10 @@ __global__ void __launch_bounds__(kThreads, 4) csr_block_kernel(const CsrArgsT<P
         }
         __syncthreads();
         ptx::mbar_wait(bar, 0);
-        wait_for_halo<HALO>(a, b);
+        wait_for_halo<HALO>(a, d);
         compute_staged<MODE, L, HALO>(a, d, stage, lay, acc);
     } else {
-        wait_for_halo<HALO>(a, b);
+        wait_for_halo<HALO>(a, d);
         compute_long<MODE, HALO>(a, d, red_s, acc);
     }
 }
@@ -483,7 +477,7 @@ __global__ void __launch_bounds__(kThreads, 2) csr_ring_kernel(const CsrArgsT<P>
         ptx::fence_mbar_init();
         const int pre = mine < nstages ? mine : nstages;
         for (int i = 0; i < pre; ++i) {
-            const BlockDesc d = load_desc(a, block_at<HALO>(a, first + i * step));
+            const BlockDesc d = load_desc(a, first + i * step);
             descs[i] = d;
             issue_block(a, d, stages + (size_t)i * lay.bytes, lay, bars + i, policy);
         }
@@ -497,14 +491,14 @@ __global__ void __launch_bounds__(kThreads, 2) csr_ring_kernel(const CsrArgsT<P>
     for (int i = 0; i < mine; ++i) {
         ptx::mbar_wait(bars + s, parity);
         const BlockDesc d = descs[s];
-        wait_for_halo<HALO>(a, block_at<HALO>(a, first + i * step));
+        wait_for_halo<HALO>(a, d);
         if ((d.e1 - d.e0) <= a.nnz_cap)
             compute_staged<MODE, L, HALO>(a, d, stages + (size_t)s * lay.bytes, lay, acc);
         else
             compute_long<MODE, HALO>(a, d, red_s, acc);
         __syncthreads();                 // every thread is done with stage s (and descs[s])
         if (threadIdx.x == 0 && i + nstages < mine) {
-            const BlockDesc n = load_desc(a, block_at<HALO>(a, first + (i + nstages) * step));
+            const BlockDesc n = load_desc(a, first + (i + nstages) * step);
             descs[s] = n;
             issue_block(a, n, stages + (size_t)s * lay.bytes, lay, bars + s, policy);
         }

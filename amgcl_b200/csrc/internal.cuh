@@ -248,8 +248,6 @@ void peer_release(b200_ctx_t ctx, void *local, void **peers);
 struct HaloArgs {
     const double             *xh = nullptr;         // halo values for columns >= nloc
     int                       nloc = 0;
-    const int                *blk_order = nullptr;  // walk order: blocks that wait come last
-    const unsigned char      *blk_halo = nullptr;   // peer transport: blocks that must wait
     const unsigned long long *wait_flags = nullptr;
     unsigned int              wait_mask = 0;
     unsigned long long        wait_seq = 0;

@@ -115,7 +115,9 @@ fused_vec_kernel(size_t n, F f, FusedArgs<F::NIN, F::NOUT> a, RedOut ro, bool ve
 // a derived scalar goes to the device table and its host mirror
 struct SaveSlot {
     double *d, *h;
-    __device__ void put(double v) const { *d = v; if (h) *h = v; }
+    // (one thread per launch; the system fence orders the host copy before the launch's
+    // "ready" word, which another CTA releases later)
+    __device__ void put(double v) const { *d = v; if (h) { *h = v; __threadfence_system(); } }
 };
 
 // ---- reductions only --------------------------------------------------------------------

@@ -34,7 +34,9 @@ struct RedOut {
     double       *partial;            // [nred * gridDim.x] per-CTA partial sums (scratch)
     unsigned int *ticket;             // self-resetting arrival counter
     double       *dev[kMaxRed];       // where each scalar goes (device)
-    double       *host[kMaxRed];      // mapped host mirror (nullptr: none)
+    double       *host[kMaxRed];      // mapped host mirror (nullptr: none) ...
+    unsigned long long *host_seq[kMaxRed];   // ... and its "ready" word: set to seq[k] after the value,
+                                      // so the host can poll instead of synchronising the stream
     int           nred;
     // multi-GPU: all-reduce inside the finishing CTA
     int           nranks, rank;
@@ -114,7 +116,7 @@ __device__ __forceinline__ void red_finish(const RedOut &o, double (&v)[NRED]) {
             if (q < o.nranks) {
                 ScalExchange *pq = o.peers[q];
                 pq->val[par][o.slot[k]][o.rank] = red_tot[k];
-                __threadfence_system();
+                // (release at system scope orders the store above before the flag)
                 red_st_release_sys(&pq->flag[par][o.slot[k]][o.rank], o.seq[k]);
                 const ScalExchange *mine = o.peers[o.rank];
                 while (red_ld_acquire_sys(&mine->flag[par][o.slot[k]][q]) < o.seq[k]) { }
@@ -140,7 +142,10 @@ __device__ __forceinline__ void red_finish(const RedOut &o, double (&v)[NRED]) {
         for (int k = 0; k < NRED; ++k) {
             if (k >= o.nred) break;
             *o.dev[k] = red_tot[k];
-            if (o.host[k]) *o.host[k] = red_tot[k];
+            if (o.host[k]) {
+                *o.host[k] = red_tot[k];
+                red_st_release_sys(o.host_seq[k], o.seq[k]);
+            }
         }
         *o.ticket = 0;                       // ready for the next launch on this stream
     }

@@ -177,6 +177,9 @@ int b200_split_destroy(b200_split_t sp);
  *                      together as ONE cooperative kernel with device-wide barriers between them
  *                      when the next call that cannot be deferred arrives (default); 0 = every
  *                      call launches its own kernel.  Results are bit-identical either way.
+ *   "poll_scalars"     1 = a host-synchronous result of an in-kernel reduction (b200_dot, the
+ *                      Krylov steps) is awaited by polling the mapped host word the finishing CTA
+ *                      releases (default), 0 = by cudaStreamSynchronize
  *   "fused_krylov"     1 = the C++ binding's solver::cg / solver::bicgstab specialisations run the
  *                      fused b200_cg_* / b200_bicg_* steps (default; env B200_FUSED_KRYLOV),
  *                      0 = they issue the reference's sequence of primitives
