@@ -145,6 +145,37 @@ def cpu_topology():
     return _TOPOLOGY
 
 
+def cgroup_cpu_limit():
+    """CPUs' worth of time the container may use (cgroup v2 cpu.max / v1 cfs quota), or None."""
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()[:2]
+        if quota != "max":
+            return max(1, int(int(quota) / int(period)))
+    except Exception:
+        pass
+    try:
+        with open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us") as f:
+            quota = int(f.read())
+        with open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as f:
+            period = int(f.read())
+        if quota > 0:
+            return max(1, quota // period)
+    except Exception:
+        pass
+    return None
+
+
+def setup_threads(world):
+    """OpenMP threads for AMGCL's host-side setup inside the drop-in library: the CPUs this
+    process may really use, shared between the ranks, at most 32 (the coarsening does not scale
+    further; 128 spinning threads on a container with a CPU quota are far slower than 32)."""
+    logical, cores, _ = cpu_topology()
+    limit = cgroup_cpu_limit()
+    avail = min(cores, limit) if limit else cores
+    return max(1, min(32, avail // max(world, 1)))
+
+
 def _cpu_topology():
     logical = os.cpu_count() or 1
     try:
@@ -171,7 +202,9 @@ def pick_threads(ref, step):
     cores, half a socket} and keep the fastest (memory-bound kernels often peak below the
     hardware thread count): one settling step, then the median of three per candidate."""
     logical, cores, sockets = cpu_topology()
-    cands = sorted({c for c in (logical, cores, cores // sockets, max(1, cores // (2 * sockets)))
+    limit = cgroup_cpu_limit()
+    cands = sorted({c for c in (logical, cores, cores // sockets, max(1, cores // (2 * sockets)),
+                                max(1, cores // (4 * sockets)), limit)
                     if c and c >= 1}, reverse=True)
     best, best_t, seen = cands[0], None, {}
     for c in cands:
@@ -187,7 +220,7 @@ def pick_threads(ref, step):
         if best_t is None or dt < best_t:
             best, best_t = c, dt
     ref.set_threads(best)
-    return best, {"logical": logical, "physical_cores": cores, "sockets": sockets,
+    return best, {"logical": logical, "physical_cores": cores, "sockets": sockets, "cgroup_cpu_limit": limit,
                   "binding": "OMP_PROC_BIND=%s OMP_PLACES=%s" % (os.environ.get("OMP_PROC_BIND"),
                                                                  os.environ.get("OMP_PLACES")),
                   "sweep_s_per_sample": {str(k): round(v, 4) for k, v in seen.items()}}
@@ -361,7 +394,7 @@ def main_arm(args, rank, world, local_rank):
     torch.cuda.set_stream(side)
     ctx = ab.Context(device, stream=side.cuda_stream)
     # host-side setup threads: share the box between the ranks (torchrun exports 1)
-    ab.set_setup_threads(max(1, (os.cpu_count() or 8) // world))
+    ab.set_setup_threads(setup_threads(world))
 
     t0 = time.time()
     ptr, col, val, rhs = ab.poisson3d(args.n)
