@@ -44,7 +44,7 @@ class ProfileEntry(_c.Structure):
 
 
 # vecK: element-wise pass over K+1 vector streams (reads + writes)
-MODE_NAMES = {0: "spmv", 1: "spmv_acc", 2: "residual", 3: "relax", 10: "vec1", 11: "vec2",
+MODE_NAMES = {0: "spmv", 1: "spmv_acc", 2: "residual", 3: "relax", 4: "residual_scaled", 10: "vec1", 11: "vec2",
               12: "vec3", 13: "vec4", 14: "vec5", 15: "vec6", 16: "vec7",
               20: "dot", 21: "relax_zero", 22: "coarse_gemv", 23: "memset", 24: "coarse_tail",
               30: "comm"}

@@ -97,6 +97,7 @@ extern "C" int b200_ctx_create(int device, b200_ctx_t *out) {
 extern "C" int b200_ctx_destroy(b200_ctx_t ctx) {
     if (!ctx) return B200_OK;
     tail_destroy(ctx);                            // pending calls are dropped with the context
+    ctx->lazy_vec = nullptr;
     GUARD(ctx);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     scal_destroy(ctx);
@@ -261,6 +262,7 @@ static int64_t *option_slot(b200_ctx_t ctx, const char *key) {
     if (!strcmp(key, "fused_krylov")) return &ctx->opt_fused_krylov;
     if (!strcmp(key, "coarse_tail")) return &ctx->opt_coarse_tail;
     if (!strcmp(key, "poll_scalars")) return &ctx->opt_poll_scalars;
+    if (!strcmp(key, "fuse_first_sweep")) return &ctx->opt_fuse_first_sweep;
     if (!strcmp(key, "tail_max_nnz")) return &ctx->opt_tail_max_nnz;
     if (!strcmp(key, "tail_max_vec")) return &ctx->opt_tail_max_vec;
     return nullptr;

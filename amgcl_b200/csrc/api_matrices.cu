@@ -615,6 +615,8 @@ static int residual_local(b200_ctx_t ctx, b200_vec_t f, b200_csr_t A, b200_vec_t
 } // namespace b200
 
 namespace b200 {
+static bool first_sweep_fusable(b200_ctx_t ctx, b200_csr_t A);      // (smoother section below)
+
 static int spmv_impl(b200_ctx_t ctx, double alpha, b200_csr_t A, b200_vec_t x, double beta,
                      b200_vec_t y, DotReq *req) {
     CHECK_CTX(ctx);
@@ -682,8 +684,29 @@ static int residual_impl(b200_ctx_t ctx, b200_vec_t f, b200_csr_t A, b200_vec_t 
     B200_REQUIRE(x != r && (x->ptr != r->ptr || !x->ptr), "residual: x and r must not alias");
     B200_REQUIRE(!A->gather_rows && (!ctx->dist || A->gl_rows == A->gl_cols || A->kind == B200_CK_LOCAL),
                  "residual: operator must be square");
-    GUARD_DEFER(ctx);
+    GUARD_RAW(ctx);
     TailHold hold(ctx, {f, x, r});
+    if (ctx->lazy_vec) {
+        // x = (omega*d).*f is still pending (b200_relax from x = 0 was the previous call): if
+        // this is the residual of that very system, one pass forms x on the fly, writes it, and
+        // writes r = f - A x (MODE_RESID_SCALED)
+        if (ctx->lazy_vec == x && x->sc_fvec == f && f != r && x != r && r->ptr != x->ptr &&
+            r->ptr != f->ptr && first_sweep_fusable(ctx, A) && all64({f, x, r}) && (!req || !req->ndot) &&
+            r->owned && !r->escaped && f->ptr == x->sc_f && !f->zero_pending) {
+            ctx->lazy_vec = nullptr;
+            x->scale_pending = false;
+            CsrArgs a = base_args(A);
+            a.x = x->ptr;                         // (not gathered from: see gather_m)
+            a.xw = x->ptr;
+            a.f = x->sc_f; a.d = x->sc_d; a.alpha = x->sc_omega;
+            x->sc_d = x->sc_f = nullptr; x->sc_fvec = nullptr;
+            a.y = wr(r);
+            ctx->fused_first_sweeps++;
+            return launch_csr<MODE_RESID_SCALED>(ctx, A, a);
+        }
+        const int lrc = lazy_flush(ctx);
+        if (lrc) return lrc;
+    }
     if (A->dtype == B200_F32) {
         if (all32({f, x, r})) return residual_local<PrecFF>(ctx, f, A, x, r);
         if (all64({f, x, r})) return residual_local<PrecFD>(ctx, f, A, x, r, req);
@@ -774,6 +797,31 @@ static int relax_zero_t(b200_ctx_t ctx, double omega, const double *pd, const do
 
 } // namespace b200
 
+namespace b200 {
+// The pending first sweep x = (omega*d).*f is written out by its own element-wise kernel
+// (what b200_relax would have launched): some call other than the matching b200_residual came.
+int lazy_flush(b200_ctx_t ctx) {
+    b200_vec_t v = ctx->lazy_vec;
+    if (!v) return B200_OK;
+    ctx->lazy_vec = nullptr;
+    v->scale_pending = false;
+    const double *pd = v->sc_d, *pf = v->sc_f;
+    v->sc_d = v->sc_f = nullptr;
+    v->sc_fvec = nullptr;
+    DeviceGuard guard(ctx->device);
+    if (!guard.ok) return fail(B200_ECUDA, "cudaSetDevice failed");
+    return relax_zero_t<double, double, double>(ctx, v->sc_omega, pd, pf, v);
+}
+
+// first sweep + residual as one pass pays where the extra gathers are cheap (short rows: the
+// finest level and the P-like operators) or where a launch costs more than the work (tiny levels)
+static bool first_sweep_fusable(b200_ctx_t ctx, b200_csr_t A) {
+    return ctx->opt_fuse_first_sweep && ctx->opt_zero_shortcut && ctx->opt_spmv_variant == 1 &&
+           A->dtype == B200_F64 && A->kind == B200_CK_LOCAL && !A->gather_rows && A->nlong == 0 &&
+           A->gl_rows == A->gl_cols && (A->lanes == 1 || A->nrows <= 32768) && !tail_enabled(ctx);
+}
+} // namespace b200
+
 extern "C" int b200_relax(b200_ctx_t ctx, b200_csr_t A, b200_vec_t rhs, b200_vec_t x,
                           b200_vec_t tmp, b200_vec_t diag, double omega) {
     CHECK_CTX(ctx);
@@ -805,7 +853,17 @@ extern "C" int b200_relax(b200_ctx_t ctx, b200_csr_t A, b200_vec_t rhs, b200_vec
     if (rc) return rc;
 
     if (x->zero_pending && ctx->opt_zero_shortcut) {
-        // residual(rhs, A, 0) == rhs exactly, so the sweep reduces to a scaling
+        // residual(rhs, A, 0) == rhs exactly, so the sweep reduces to a scaling ...
+        if (mix == 0 && first_sweep_fusable(ctx, A) && x->owned && !x->escaped && x->kind == B200_VK_LOCAL &&
+            x->len == (size_t)A->nrows && !ctx->dist) {
+            // ... which the b200_residual that normally follows can do on the fly: postpone it
+            x->zero_pending = false;
+            x->scale_pending = true;
+            x->sc_d = pd; x->sc_f = pf; x->sc_fvec = rhs; x->sc_omega = omega;
+            x->gen++;
+            ctx->lazy_vec = x;
+            return B200_OK;
+        }
         if (mix == 0) return relax_zero_t<double, double, double>(ctx, omega, pd, pf, x);
         if (mix == 1) return relax_zero_t<float, float, float>(ctx, omega, pd, pf, x);
         return relax_zero_t<float, double, double>(ctx, omega, pd, pf, x);

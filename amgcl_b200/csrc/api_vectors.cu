@@ -289,7 +289,13 @@ extern "C" int b200_clear(b200_ctx_t ctx, b200_vec_t x) {
     CHECK_CTX(ctx);
     B200_REQUIRE(x, "null argument");
     touch(ctx, {x});
-    if (x->kind == B200_VK_GHOST) return B200_OK;
+    if (x->scale_pending) {                 // a first sweep nobody looked at: dropped
+        x->scale_pending = false;
+        x->sc_d = x->sc_f = nullptr;
+        x->sc_fvec = nullptr;
+        if (ctx->lazy_vec == x) ctx->lazy_vec = nullptr;
+    }
+    x->gen++;
     if (ctx->opt_zero_shortcut) {
         x->zero_pending = true;
         return B200_OK;

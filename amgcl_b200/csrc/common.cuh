@@ -101,6 +101,10 @@ struct b200_ctx_s {
     int           product_slot0 = -1;     // first of the 4 table slots the products rotate through
     std::vector<size_t> krylov_sizes;     // sizes of the live Krylov workspaces (b200_krylov_*)
 
+    b200_vec_t    lazy_vec = nullptr;     // the (single) vector with a pending lazy first sweep
+    int64_t       opt_fuse_first_sweep = 1;   // b200_relax from x = 0 + b200_residual -> one pass
+    uint64_t      fused_first_sweeps = 0;
+
     // coarse tail of the V-cycle (tail_kernels.cuh): calls on small operators are deferred into
     // a command list and run as ONE kernel when the next non-deferrable call arrives
     void         *tail = nullptr;         // TailArgs (host): the pending commands
@@ -181,6 +185,14 @@ struct b200_vec_s {
     // A-pass), dropped by any full overwrite, materialised by any other read.
     bool       zero_pending = false;
     bool       in_graph     = false;   // some recorded graph refers to this vector
+    // Lazy first sweep: the vector is logically x = (omega*d).*f (the smoother sweep from x = 0)
+    // but nothing has been written.  Set by b200_relax, consumed by the b200_residual that
+    // normally follows (which then forms x on the fly and writes it along with the residual:
+    // one pass instead of two); ANY other call on the context materialises it first.
+    bool       scale_pending = false;
+    const double *sc_d = nullptr, *sc_f = nullptr;
+    b200_vec_t sc_fvec = nullptr;
+    double     sc_omega = 0.0;
     uint64_t   gen          = 0;       // bumped by every write through the library
     bool       escaped      = false;   // raw pointer handed out / external storage: contents
                                        // may change behind the library's back

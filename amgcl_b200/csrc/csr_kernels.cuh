@@ -37,7 +37,11 @@
 
 namespace b200 {
 
-enum { MODE_SPMV = 0, MODE_SPMV_ACC = 1, MODE_RESID = 2, MODE_RELAX = 3 };
+enum { MODE_SPMV = 0, MODE_SPMV_ACC = 1, MODE_RESID = 2, MODE_RELAX = 3,
+       // y = f - A x with x = (alpha*d).*f formed on the fly and written to xw: the smoother's
+       // first sweep from x = 0 (relax_zero_kernel) fused into the residual that follows it
+       // (amg.hpp:527-534: apply_pre, then residual)
+       MODE_RESID_SCALED = 4 };
 
 #ifndef B200_GATHER_BATCH
 #define B200_GATHER_BATCH 4
@@ -98,6 +102,7 @@ struct CsrArgsT {
     unsigned int             *gather_ticket;
     unsigned long long        gather_seq;
     typename P::TY       *y;      // output
+    typename P::TX       *xw;     // RESID_SCALED: where x = (alpha*d).*f is written
     const typename P::TF *f;      // rhs          (RESID, RELAX)
     const typename P::TD *d;      // diagonal     (RELAX)
     double        alpha;  // SPMV: alpha; RELAX: omega
@@ -190,6 +195,10 @@ __device__ __forceinline__ void store_row(const CsrArgsT<P> &a, int r, typename 
         out = (TY)(a.alpha * sum + a.beta * a.y[r]);
     } else if (MODE == MODE_RESID) {
         out = (TY)(a.f[r] - sum);
+    } else if (MODE == MODE_RESID_SCALED) {
+        const typename P::TF fr = a.f[r];
+        out = (TY)(fr - sum);
+        a.xw[r] = fma((typename P::TX)(a.alpha * a.d[r]), (typename P::TX)fr, (typename P::TX)0);
     } else {
         // x_new = (omega*d)*t + x with t = f - A x; same association as the
         // reference's vmul  z = a*x*y + b*z  (builtin.hpp:1238-1265)
@@ -224,6 +233,17 @@ __device__ __forceinline__ typename P::TX gather(const CsrArgsT<P> &a,
         return __ldcg(a.xh + (c - a.nloc));
     }
     return __ldg(x + c);
+}
+
+// RESID_SCALED: the gathered vector does not exist yet; its entry c is (alpha*d[c])*f[c],
+// evaluated exactly as relax_zero_kernel does
+template <int MODE, bool HALO, class P>
+__device__ __forceinline__ typename P::TX gather_m(const CsrArgsT<P> &a,
+                                                   const typename P::TX *__restrict__ x, int c) {
+    typedef typename P::TX TX;
+    if (MODE == MODE_RESID_SCALED)
+        return fma((TX)(a.alpha * __ldg(a.d + c)), (TX)__ldg(a.f + c), (TX)0);
+    return gather<HALO>(a, x, c);
 }
 
 // Block until the peers' halo pushes for this exchange have landed (thread 0 polls the
@@ -294,7 +314,7 @@ __device__ __forceinline__ void compute_staged(const CsrArgsT<P> &a, const Block
                 v[u] = p[u] ? val_s[e - vo] : (TV)0;
             }
 #pragma unroll
-            for (int u = 0; u < RU; ++u) xv[u] = p[u] ? gather<HALO>(a, x, c[u]) : (TX)0;
+            for (int u = 0; u < RU; ++u) xv[u] = p[u] ? gather_m<MODE, HALO>(a, x, c[u]) : (TX)0;
 #pragma unroll
             for (int u = 0; u < RU; ++u)
                 if (p[u]) sum[u] = (TS)v[u] * (TS)xv[u];
@@ -302,7 +322,7 @@ __device__ __forceinline__ void compute_staged(const CsrArgsT<P> &a, const Block
 #pragma unroll
             for (int u = 0; u < RU; ++u)
                 for (int e = beg[u] + lane + L; e < end[u]; e += L)
-                    sum[u] = fma((TS)val_s[e - vo], (TS)gather<HALO>(a, x, col_s[e - co]), sum[u]);
+                    sum[u] = fma((TS)val_s[e - vo], (TS)gather_m<MODE, HALO>(a, x, col_s[e - co]), sum[u]);
 #pragma unroll
             for (int o = L / 2; o > 0; o >>= 1) {
 #pragma unroll
@@ -335,7 +355,7 @@ __device__ __forceinline__ void compute_staged(const CsrArgsT<P> &a, const Block
                     v[u] = p[u] ? val_s[eu - vo] : (TV)0;
                 }
 #pragma unroll
-                for (int u = 0; u < U; ++u) xv[u] = gather<HALO>(a, x, c[u]);
+                for (int u = 0; u < U; ++u) xv[u] = gather_m<MODE, HALO>(a, x, c[u]);
 #pragma unroll
                 for (int u = 0; u < U; ++u)
                     if (p[u]) sum = fma((TS)v[u], (TS)xv[u], sum);
@@ -360,7 +380,7 @@ __device__ __forceinline__ void compute_long(const CsrArgsT<P> &a, const BlockDe
         const int beg = __ldg(a.ptr + r), end = __ldg(a.ptr + r + 1);
         TS sum = 0;
         for (int e = beg + threadIdx.x; e < end; e += kThreads)
-            sum = fma((TS)__ldg(a.val + e), (TS)gather<HALO>(a, x, __ldg(a.col + e)), sum);
+            sum = fma((TS)__ldg(a.val + e), (TS)gather_m<MODE, HALO>(a, x, __ldg(a.col + e)), sum);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
         __syncthreads();                       // red_s free from the previous row

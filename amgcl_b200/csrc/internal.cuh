@@ -84,8 +84,15 @@ struct TailHold {
     ~TailHold() { ctx->tail_hold = prev; }
 };
 
+// ---- implemented in api_matrices.cu: the lazy first smoother sweep ---------------------------
+int  lazy_flush(b200_ctx_t ctx);        // write out the pending x = (omega*d).*f, if any
+
 // Lazy clear bookkeeping ------------------------------------------------------
 inline int materialize(b200_vec_t v) {
+    if (v->scale_pending) {
+        const int lrc = lazy_flush(v->ctx);
+        if (lrc) return lrc;
+    }
     if (v->zero_pending) {
         if (v->len) {
             const int trc = tail_flush(v->ctx);       // the memset must follow what was deferred
@@ -298,9 +305,15 @@ inline bool same_layout(b200_vec_t a, b200_vec_t b) {
 // reach the stream in call order.  The four entry points that may themselves be deferred
 // (b200_spmv, b200_residual, b200_relax, b200_coarse_solve) use GUARD_DEFER and flush on
 // every path that launches immediately.
-#define GUARD_DEFER(ctx)                                                       \
+#define GUARD_RAW(ctx)                                                         \
     DeviceGuard guard__((ctx)->device);                                        \
     if (!guard__.ok) return fail(B200_ECUDA, "cudaSetDevice failed")
+#define GUARD_DEFER(ctx)                                                       \
+    GUARD_RAW(ctx);                                                            \
+    do {                                                                       \
+        const int lrc__ = ::b200::lazy_flush(ctx);                             \
+        if (lrc__) return lrc__;                                               \
+    } while (0)
 #define GUARD(ctx)                                                             \
     GUARD_DEFER(ctx);                                                          \
     do {                                                                       \

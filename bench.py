@@ -459,7 +459,7 @@ def main_arm(args, rank, world, local_rank):
         S.solve_resident()
     prof = ctx.profile_end()
     # the finest-level operator (this rank's share of it when partitioned) = most non-zeros
-    csr_prof = [p for p in prof if p["mode"] in ("spmv", "spmv_acc", "residual", "relax")]
+    csr_prof = [p for p in prof if p["mode"] in ("spmv", "spmv_acc", "residual", "relax", "residual_scaled")]
     big = max([p["nnz"] for p in csr_prof if p["nrows"] * 2 > p["ncols"]] or [0])
     finest = [p for p in csr_prof if p["nnz"] == big and p["mode"] != "spmv_acc"]
     peak, peak_src = peaks()
@@ -469,7 +469,7 @@ def main_arm(args, rank, world, local_rank):
             b = p["nnz"] * 12 + (p["nrows"] + 1) * 4 + p["ncols"] * 8 + p["nrows"] * 8
             if p["mode"] in ("residual", "spmv_acc"):
                 b += p["nrows"] * 8
-            elif p["mode"] == "relax":
+            elif p["mode"] in ("relax", "residual_scaled"):      # rhs + diagonal / rhs + x written
                 b += 2 * p["nrows"] * 8
             return b
         tot_b = sum(alg_bytes(p) * p["launches"] for p in finest)
@@ -510,7 +510,7 @@ def main_arm(args, rank, world, local_rank):
             b = p["nnz"] * 12 + (p["nrows"] + 1) * 4 + p["ncols"] * 8 + p["nrows"] * 8
             if p["mode"] in ("residual", "spmv_acc"):
                 b += p["nrows"] * 8
-            elif p["mode"] == "relax":
+            elif p["mode"] in ("relax", "residual_scaled"):
                 b += 2 * p["nrows"] * 8
         breakdown.append({"rows": p["nrows"], "cols": p["ncols"], "nnz": p["nnz"], "kernel": p["mode"],
                           "launches_per_step": p["launches"] / args.steps,

@@ -101,6 +101,7 @@ int b200_tail_stats(b200_ctx_t ctx, uint64_t *flushes, uint64_t *commands);
  * CUDA events on the launching stream; end() aggregates them per (matrix shape,
  * mode).  mode: 0 spmv(beta=0), 1 spmv(beta!=0), 2 residual, 3 fused relax; the
  * vector kernels report nrows = n, ncols = 1, nnz = 0 and one of the modes below. */
+/* (mode 4: residual fused with the smoother's first sweep from x = 0) */
 #define B200_PROF_VECTOR      10   /* element-wise, +1 per extra input stream (10..12) */
 #define B200_PROF_DOT         20
 #define B200_PROF_RELAX_ZERO  21   /* x = omega*diag.*rhs shortcut of the smoother     */
@@ -177,6 +178,11 @@ int b200_split_destroy(b200_split_t sp);
  *                      together as ONE cooperative kernel with device-wide barriers between them
  *                      when the next call that cannot be deferred arrives (default); 0 = every
  *                      call launches its own kernel.  Results are bit-identical either way.
+ *   "fuse_first_sweep" 1 = b200_relax on an x known to be zero followed by b200_residual of the
+ *                      same system (amg.hpp:527-534: pre-smoothing, then the residual to restrict)
+ *                      is ONE pass over A: x = (omega*diag).*rhs is formed on the fly, written,
+ *                      and r = rhs - A x with it (default; operators with short rows and tiny
+ *                      levels only); 0 = two kernels.  Results are bit-identical.
  *   "poll_scalars"     1 = a host-synchronous result of an in-kernel reduction (b200_dot, the
  *                      Krylov steps) is awaited by polling the mapped host word the finishing CTA
  *                      releases (default), 0 = by cudaStreamSynchronize

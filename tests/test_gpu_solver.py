@@ -210,6 +210,62 @@ def test_coarse_tail_is_bit_transparent(ctx, n, relax, krylov):
         assert c1 >= 3 * f1 and l1 < l0                               # several calls per tail launch
 
 
+@pytest.mark.parametrize("relax,krylov", [("damped_jacobi", "cg"), ("spai0", "bicgstab")])
+def test_first_sweep_fusion_is_bit_transparent(ctx, relax, krylov):
+    """Option "fuse_first_sweep": the smoother's sweep from x = 0 is postponed and done on the
+    fly by the residual that follows it (one pass over A instead of an element-wise kernel + a
+    pass).  Same arithmetic: same bits, one launch less per level and cycle."""
+    ptr, col, val, rhs = ab.poisson3d(32)
+    rng = np.random.default_rng(13)
+    f = rng.uniform(-1, 1, rhs.size)
+    out = {}
+    try:
+        for fuse in (0, 1):
+            ctx.set_option("fuse_first_sweep", fuse)
+            S = ab.DropinSolver(ptr, col, val, relax, krylov, ctx=ctx)
+            S.solve(rhs)
+            l0 = ctx.launches
+            x, it, res = S.solve(rhs)
+            out[fuse] = (x, it, res, S.apply_precond(f), ctx.launches - l0)
+            S.close()
+    finally:
+        ctx.set_option("fuse_first_sweep", 1)
+    (x0, it0, r0, m0, l0), (x1, it1, r1, m1, l1) = out[0], out[1]
+    assert (it1, r1) == (it0, r0) and np.array_equal(x1, x0) and np.array_equal(m1, m0)
+    cycles = it0 * (2 if krylov == "bicgstab" else 1)
+    assert l0 - l1 >= cycles                     # at least the finest level, every cycle
+
+
+def test_pending_first_sweep_is_materialised_by_any_other_reader(ctx):
+    ptr, col, val, _ = ab.poisson3d(10)
+    n = ptr.size - 1
+    import scipy.sparse as sp
+    M = sp.csr_matrix((val, col, ptr), shape=(n, n))
+    rng = np.random.default_rng(14)
+    f, g = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
+    d = 1.0 / M.diagonal()
+    A = ctx.csr(n, n, ptr, col, val)
+    vf, vg, vd, x, tmp, r = ctx.vector(f), ctx.vector(g), ctx.vector(d), ctx.vector(n), ctx.vector(n), ctx.vector(n)
+    x1 = 0.72 * d * f
+    # the matching residual: fused
+    ctx.clear(x); ctx.relax(A, vf, x, tmp, vd, 0.72)
+    before = ctx.launches
+    ctx.residual(vf, A, x, r)
+    assert ctx.launches == before + 1
+    assert rel_err(r.numpy(), f - M @ x1) < 1e-13 and rel_err(x.numpy(), x1) < 1e-15
+    # some other reader first: the sweep is written out by its own kernel
+    ctx.clear(x); ctx.relax(A, vf, x, tmp, vd, 0.72)
+    assert abs(ctx.dot(x, x) - x1 @ x1) <= 1e-13 * (x1 @ x1)
+    # a residual against ANOTHER right-hand side: not the fused pass, still right
+    ctx.clear(x); ctx.relax(A, vf, x, tmp, vd, 0.72)
+    ctx.residual(vg, A, x, r)
+    assert rel_err(r.numpy(), g - M @ x1) < 1e-13
+    # cleared again before anybody looked
+    ctx.clear(x); ctx.relax(A, vf, x, tmp, vd, 0.72)
+    ctx.clear(x)
+    assert not x.numpy().any()
+
+
 def test_deferred_calls_keep_call_order(ctx):
     """Deferred (small-operator) calls interleaved with immediate ones and with host reads."""
     ptr, col, val, _ = ab.poisson3d(10)
