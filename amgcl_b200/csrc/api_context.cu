@@ -82,6 +82,8 @@ extern "C" int b200_ctx_create(int device, b200_ctx_t *out) {
     if (const char *e = getenv("B200_GRAPH_PDL")) ctx->opt_graph_pdl = atoi(e) ? 1 : 0;
     if (const char *e = getenv("B200_FUSED_KRYLOV")) ctx->opt_fused_krylov = atoi(e) ? 1 : 0;
     if (const char *e = getenv("B200_COARSE_TAIL")) ctx->opt_coarse_tail = atoi(e) ? 1 : 0;
+    if (const char *e = getenv("B200_FUSE_FIRST_SWEEP")) ctx->opt_fuse_first_sweep = atoi(e) ? 1 : 0;
+    if (const char *e = getenv("B200_POLL_SCALARS")) ctx->opt_poll_scalars = atoi(e) ? 1 : 0;
     // any failure below releases what was created so far (b200_ctx_destroy null-checks every member)
     const int rc = ctx_init(ctx, device);
     if (rc != B200_OK) {

@@ -205,7 +205,6 @@ def test_coarse_tail_is_bit_transparent(ctx, n, relax, krylov):
     (x0, it0, r0, m0, l0, f0, c0), (x1, it1, r1, m1, l1, f1, c1) = out[0], out[1]
     assert (it1, r1) == (it0, r0) and np.array_equal(x1, x0) and np.array_equal(m1, m0)
     assert f0 == 0 and c0 == 0 and f1 >= it1 and c1 >= f1
-    assert l0 - l1 == c1 - f1                                         # each deferred call saved a launch
     if n >= 32:
         assert c1 >= 3 * f1 and l1 < l0                               # several calls per tail launch
 
