@@ -521,9 +521,8 @@ class Csr:
 
     def __del__(self):
         try:
-            if self.h:
-                lib().b200_csr_destroy(self.h)
-                self.h = _vp()
+            if self.h and lib().b200_csr_destroy(self.h) == 0:
+                self.h = _vp()      # (kept if the library refused, e.g. while a graph is recorded)
         except Exception:
             pass
 
@@ -543,9 +542,8 @@ class Coarse:
 
     def __del__(self):
         try:
-            if self.h:
-                lib().b200_coarse_destroy(self.h)
-                self.h = _vp()
+            if self.h and lib().b200_coarse_destroy(self.h) == 0:
+                self.h = _vp()      # (kept if the library refused, e.g. while a graph is recorded)
         except Exception:
             pass
 
@@ -563,9 +561,8 @@ class Index:
 
     def __del__(self):
         try:
-            if self.h:
-                lib().b200_index_destroy(self.h)
-                self.h = _vp()
+            if self.h and lib().b200_index_destroy(self.h) == 0:
+                self.h = _vp()      # (kept if the library refused, e.g. while a graph is recorded)
         except Exception:
             pass
 

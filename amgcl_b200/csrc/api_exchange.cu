@@ -42,18 +42,13 @@ extern "C" int b200_dist_init(b200_ctx_t ctx, const char *id, size_t size, int n
     B200_CUDA(cudaMemset(ctx->push_ticket, 0, sizeof(unsigned int)));
     B200_CUDA(cudaMalloc(&ctx->gather_ticket, sizeof(unsigned int)));
     B200_CUDA(cudaMemset(ctx->gather_ticket, 0, sizeof(unsigned int)));
-    B200_CUDA(cudaMalloc(&ctx->ipc_dev, (size_t)kMaxRanks * sizeof(cudaIpcMemHandle_t)));
+    B200_CUDA(cudaMalloc(&ctx->ipc_dev, (size_t)kMaxRanks * sizeof(cudaIpcMemHandle_t) + 64));
 
     // peer-memory exchange: try to map a small buffer of every peer; agree collectively
     ctx->p2p = false;
     if (ctx->opt_p2p && nranks > 1 && nranks <= kMaxRanks) {
-        int ok = peer_alloc(ctx, kFlagBytes + 2 * 256, &ctx->dot_pb_local, ctx->dot_pb_peer) == B200_OK;
-        int *flag_d = reinterpret_cast<int *>(ctx->ipc_dev);
-        B200_CUDA(cudaMemcpy(flag_d, &ok, sizeof(int), cudaMemcpyHostToDevice));
-        B200_NCCL(nccl().AllReduce(flag_d, flag_d, 1, ncclInt, ncclMin, comm, ctx->stream));
-        B200_CUDA(cudaMemcpyAsync(&ok, flag_d, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        B200_CUDA(cudaStreamSynchronize(ctx->stream));
-        ctx->p2p = ok != 0;
+        // (peer_alloc agrees on success collectively: either every rank mapped every peer or none did)
+        ctx->p2p = peer_alloc(ctx, kFlagBytes + 2 * 256, &ctx->dot_pb_local, ctx->dot_pb_peer) == B200_OK;
         if (!ctx->p2p) cudaGetLastError();
     }
     if (ctx->p2p) {
@@ -146,21 +141,60 @@ namespace b200 {
 // Collective: every rank allocates `bytes` (zero filled) and maps the allocations of all
 // its peers through CUDA IPC.  peers[rank] is the local pointer.
 int peer_alloc(b200_ctx_t ctx, size_t bytes, void **local, void **peers) {
+    // Collective.  A failure on one rank must not leave the others blocked inside a
+    // collective: every rank records its local status, ALWAYS takes part in the all-gather of
+    // the handles and in a final all-reduce(min) of the status, and only then cleans up and
+    // returns the agreed result.
     bytes = (bytes + 255) & ~size_t(255);
-    B200_CUDA(cudaMalloc(local, bytes));
-    B200_CUDA(cudaMemsetAsync(*local, 0, bytes, ctx->stream));
-    cudaIpcMemHandle_t mine;
-    B200_CUDA(cudaIpcGetMemHandle(&mine, *local));
-    char *stage = static_cast<char *>(ctx->ipc_dev);
     const size_t hs = sizeof(cudaIpcMemHandle_t);
-    B200_CUDA(cudaMemcpyAsync(stage + ctx->rank * hs, &mine, hs, cudaMemcpyHostToDevice, ctx->stream));
-    B200_NCCL(nccl().AllGather(stage + ctx->rank * hs, stage, hs, ncclChar, comm_of(ctx), ctx->stream));
+    char *stage = static_cast<char *>(ctx->ipc_dev);
+    *local = nullptr;
+    for (int q = 0; q < ctx->nranks; ++q) peers[q] = nullptr;
+    cudaError_t lrc = cudaMalloc(local, bytes);
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof(mine));
+    if (lrc == cudaSuccess) lrc = cudaMemsetAsync(*local, 0, bytes, ctx->stream);
+    if (lrc == cudaSuccess) lrc = cudaIpcGetMemHandle(&mine, *local);
+    if (lrc != cudaSuccess) cudaGetLastError();
+    // handles travel through a device staging buffer (NCCL works on device memory)
+    cudaError_t crc = cudaMemcpyAsync(stage + ctx->rank * hs, &mine, hs, cudaMemcpyHostToDevice, ctx->stream);
+    ncclResult_t nrc = nccl().AllGather(stage + ctx->rank * hs, stage, hs, ncclChar, comm_of(ctx), ctx->stream);
     std::vector<cudaIpcMemHandle_t> all((size_t)ctx->nranks);
-    B200_CUDA(cudaMemcpyAsync(all.data(), stage, hs * ctx->nranks, cudaMemcpyDeviceToHost, ctx->stream));
-    B200_CUDA(cudaStreamSynchronize(ctx->stream));
-    for (int q = 0; q < ctx->nranks; ++q) {
-        if (q == ctx->rank) { peers[q] = *local; continue; }
-        B200_CUDA(cudaIpcOpenMemHandle(&peers[q], all[(size_t)q], cudaIpcMemLazyEnablePeerAccess));
+    if (crc == cudaSuccess) crc = cudaMemcpyAsync(all.data(), stage, hs * ctx->nranks, cudaMemcpyDeviceToHost, ctx->stream);
+    if (crc == cudaSuccess) crc = cudaStreamSynchronize(ctx->stream);
+    int ok = (lrc == cudaSuccess && crc == cudaSuccess && nrc == ncclSuccess) ? 1 : 0;
+    // every rank learns whether every allocation exists before anybody maps anything
+    int *flag_d = reinterpret_cast<int *>(stage + (size_t)kMaxRanks * hs);
+    cudaMemcpyAsync(flag_d, &ok, sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
+    nccl().AllReduce(flag_d, flag_d, 1, ncclInt, ncclMin, comm_of(ctx), ctx->stream);
+    int all_ok = 0;
+    cudaMemcpyAsync(&all_ok, flag_d, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    if (all_ok) {
+        for (int q = 0; q < ctx->nranks && all_ok; ++q) {
+            if (q == ctx->rank) { peers[q] = *local; continue; }
+            if (cudaIpcOpenMemHandle(&peers[q], all[(size_t)q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                peers[q] = nullptr;
+                all_ok = 0;
+            }
+        }
+        // (mapping failures are local; agree once more so that all ranks fail together)
+        ok = all_ok;
+        cudaMemcpyAsync(flag_d, &ok, sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
+        nccl().AllReduce(flag_d, flag_d, 1, ncclInt, ncclMin, comm_of(ctx), ctx->stream);
+        cudaMemcpyAsync(&all_ok, flag_d, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+    }
+    if (!all_ok) {
+        for (int q = 0; q < ctx->nranks; ++q) {
+            if (q != ctx->rank && peers[q]) cudaIpcCloseMemHandle(peers[q]);
+            peers[q] = nullptr;
+        }
+        if (*local) cudaFree(*local);
+        *local = nullptr;
+        cudaGetLastError();
+        return fail(B200_ECUDA, "peer-memory exchange buffer: allocation or CUDA-IPC mapping failed on some rank");
     }
     return B200_OK;
 }

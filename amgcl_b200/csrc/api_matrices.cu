@@ -135,7 +135,7 @@ static cudaError_t staged_upload(b200_ctx_t ctx, Dst *dst, const Src *src, size_
 // distributed kinds hand in the local part produced by dist.cuh.
 template <class Ptr, class Col, class Val>
 static int csr_upload(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *ptr,
-                      const Col *col, const Val *val, b200_csr_t *out) {
+                      const Col *col, const Val *val, b200_csr_t *out, bool want_lines = true) {
     CHECK_CTX(ctx);
     B200_REQUIRE(out != nullptr, "null output pointer");
     *out = nullptr;
@@ -207,6 +207,44 @@ static int csr_upload(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *p
 #undef CSR_CUDA
     A->bytes = ptr_bytes + col_bytes + val_bytes + blk_bytes;
     *out = A;
+    if (want_lines && ctx->opt_warm_lines && lanes >= 2 && A->dtype == B200_F64 && nblocks > 0 &&
+        (ctx->opt_warm_lines > 1 || nnz >= 1000000)) {
+        // Gather-heavy operator: the 128-byte lines of x every row block gathers from (sorted,
+        // distinct), so the kernel can fill them into L1 with a few coalesced loads instead of
+        // one sector miss per scattered gather (warm_lines, csr_kernels.cuh).
+        std::vector<std::vector<int>> per((size_t)nblocks);
+#pragma omp parallel for schedule(dynamic, 64)
+        for (int64_t b = 0; b < nblocks; ++b) {
+            const int64_t e0 = blk[(size_t)b].y, e1 = blk[(size_t)b + 1].y;
+            std::vector<int> &v = per[(size_t)b];
+            v.reserve((size_t)(e1 - e0));
+            for (int64_t e = e0; e < e1; ++e) v.push_back((int)((int64_t)col[e] >> 4));
+            std::sort(v.begin(), v.end());
+            v.erase(std::unique(v.begin(), v.end()), v.end());
+            if (v.size() > 192) v.clear();              // too scattered to be worth touching
+        }
+        std::vector<int> wptr((size_t)nblocks + 1, 0);
+        for (int64_t b = 0; b < nblocks; ++b) wptr[(size_t)b + 1] = wptr[(size_t)b] + (int)per[(size_t)b].size();
+        std::vector<int> wl((size_t)wptr[(size_t)nblocks]);
+#pragma omp parallel for schedule(static)
+        for (int64_t b = 0; b < nblocks; ++b)
+            std::copy(per[(size_t)b].begin(), per[(size_t)b].end(), wl.begin() + wptr[(size_t)b]);
+        cudaError_t rc = cudaMalloc(&A->wl_ptr, wptr.size() * sizeof(int));
+        if (rc == cudaSuccess) rc = cudaMalloc(&A->wl, std::max<size_t>(1, wl.size()) * sizeof(int));
+        if (rc == cudaSuccess) rc = cudaMemcpyAsync(A->wl_ptr, wptr.data(), wptr.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
+        if (rc == cudaSuccess && !wl.empty())
+            rc = cudaMemcpyAsync(A->wl, wl.data(), wl.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
+        if (rc == cudaSuccess) rc = cudaStreamSynchronize(ctx->stream);
+        if (rc != cudaSuccess) {
+            cudaGetLastError();                         // an optimisation only: run without it
+            if (A->wl_ptr) cudaFree(A->wl_ptr);
+            if (A->wl) cudaFree(A->wl);
+            A->wl_ptr = A->wl = nullptr;
+        } else {
+            A->wl_count = (int64_t)wl.size();
+            A->bytes += (wptr.size() + wl.size()) * sizeof(int);
+        }
+    }
     return B200_OK;
 }
 
@@ -216,6 +254,8 @@ static void csr_free(b200_csr_t A) {
     if (A->col) cudaFree(A->col);
     if (A->val) cudaFree(A->val);
     if (A->blk) cudaFree(A->blk);
+    if (A->wl_ptr) cudaFree(A->wl_ptr);
+    if (A->wl) cudaFree(A->wl);
     if (A->send_idx) cudaFree(A->send_idx);
     if (A->halo_owned) cudaFree(A->halo_owned);
     if (A->ybuf) cudaFree(A->ybuf);
@@ -263,7 +303,8 @@ static int csr_create(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *p
     split_rows(rows, cols, cd, rank, ptr, col, sp);
 
     b200_csr_t A = nullptr;
-    rc = csr_upload(ctx, sp.nrows, sp.ncols, sp.ptr.data(), sp.col.data(), val + sp.val_offset, &A);
+    rc = csr_upload(ctx, sp.nrows, sp.ncols, sp.ptr.data(), sp.col.data(), val + sp.val_offset, &A,
+                    /* want_lines: halo columns live in another buffer */ !cd);
     if (rc) return rc;
     A->kind = cd ? B200_CK_HALO : B200_CK_LOCAL;
     A->gl_rows = nrows; A->gl_cols = ncols; A->gl_nnz = nnz;
@@ -440,6 +481,7 @@ static CsrArgsT<P> base_args_t(b200_csr_t A) {
     a.ptr = A->ptr; a.col = A->col; a.val = static_cast<const typename P::TV *>(A->val); a.blk = A->blk;
     a.nrows = (int)A->nrows; a.nblocks = (int)A->nblocks;
     a.rows_cap = A->rows_cap; a.nnz_cap = A->nnz_cap;
+    if (std::is_same<P, PrecDD>::value && A->ctx->opt_warm_lines) { a.wl_ptr = A->wl_ptr; a.wl = A->wl; }
     return a;
 }
 static CsrArgs base_args(b200_csr_t A) { return base_args_t<PrecDD>(A); }

@@ -158,6 +158,7 @@ struct b200_ctx_s {
     int64_t opt_tail_max_nnz  = 1500000;  // ... "small": at most this many non-zeros
     int64_t opt_tail_max_vec  = 262144;   // ... element-wise x = 0 sweeps: at most this many entries
     int64_t opt_poll_scalars  = 1;        // host reads in-kernel reduction results by polling mapped memory
+    int64_t opt_warm_lines    = 1;        // gather-heavy operators: touch a block's lines of x before reducing it
     int64_t opt_fused_krylov  = 1;        // the C++ binding's cg / bicgstab use the fused b200_cg_* / b200_bicg_* steps
 
     // CUDA-graph recording of a call sequence (b200_graph_*)
@@ -242,6 +243,9 @@ struct b200_csr_s {
     int        nnz_cap  = 2048;   // staged non-zeros per block
     int64_t    nblocks  = 0;
     int64_t    nlong    = 0;      // blocks too long to stage (handled by the strided path)
+    int       *wl_ptr   = nullptr;// gather-heavy operators: [nblocks+1] offsets into wl (walk order)
+    int       *wl       = nullptr;// 128-byte lines of x each row block gathers from
+    int64_t    wl_count = 0;
     int4      *blk      = nullptr;// [nblocks] device, walk order: {first row (~r if the block gathers halo
                                   //   columns), end row, first nnz, end nnz}; HALO: interior blocks first
     size_t     bytes    = 0;

@@ -101,6 +101,12 @@ struct CsrArgsT {
     unsigned long long       *gather_flag[kMaxRanks];
     unsigned int             *gather_ticket;
     unsigned long long        gather_seq;
+    // Gather-heavy operators (long rows): the 128-byte lines of x a row block gathers from, as a
+    // per-block list (built at upload).  Before reducing a block the CTA touches each of them
+    // once with coalesced loads -- one L2->L1 fill per LINE the block uses, instead of one
+    // 32-byte sector fill per scattered 8-byte gather that misses (warm_lines below).
+    const int    *wl_ptr; // [nblocks+1] (walk order) or nullptr
+    const int    *wl;     // line numbers (x index / 16)
     typename P::TY       *y;      // output
     typename P::TX       *xw;     // RESID_SCALED: where x = (alpha*d).*f is written
     const typename P::TF *f;      // rhs          (RESID, RELAX)
@@ -264,6 +270,22 @@ __device__ __forceinline__ void wait_for_halo(const CsrArgsT<P> &a, const BlockD
         }
     }
     __syncthreads();
+}
+
+// ---- bring the lines of x a block gathers from into L1 with coalesced loads --------------
+// Four threads per 128-byte line, one 8-byte load per 32-byte sector; the values are not used.
+// The gathers that follow hit (or merge with the outstanding fills).
+template <class P>
+__device__ __forceinline__ void warm_lines(const CsrArgsT<P> &a, int pos) {
+    if (a.wl_ptr == nullptr) return;
+    const int w0 = __ldg(a.wl_ptr + pos), w1 = __ldg(a.wl_ptr + pos + 1);
+    const char *base = reinterpret_cast<const char *>(a.x);
+    for (int t = w0 * 4 + (int)threadIdx.x; t < w1 * 4; t += kThreads) {
+        const int line = __ldg(a.wl + (t >> 2));
+        const char *p = base + (size_t)line * 128 + (size_t)(t & 3) * 32;
+        unsigned long long sink;
+        asm volatile("ld.global.ca.u64 %0, [%1];" : "=l"(sink) : "l"(p) : "memory");
+    }
 }
 
 // ---- reduce the rows of a staged block out of shared memory ---------------------
@@ -512,6 +534,7 @@ __global__ void __launch_bounds__(kThreads, 2) csr_ring_kernel(const CsrArgsT<P>
         ptx::mbar_wait(bars + s, parity);
         const BlockDesc d = descs[s];
         wait_for_halo<HALO>(a, d);
+        if (!HALO) warm_lines(a, first + i * step);
         if ((d.e1 - d.e0) <= a.nnz_cap)
             compute_staged<MODE, L, HALO>(a, d, stages + (size_t)s * lay.bytes, lay, acc);
         else
