@@ -122,9 +122,77 @@ def full_capture(tag, rep):
         json.dump(traffic, open(os.path.join(PROF, "traffic.json"), "w"), indent=1)
 
 
+def short_any(full):
+    """Readable name for every kernel of the step (CSR ring kernels and the fused vector passes)."""
+    name = full.split("(")[0].replace("void ", "").replace("b200::", "")
+    m = re.match(r"fused_vec_kernel<(\w+), (\d+)>", name)
+    if m:
+        return "fused_vec_kernel<%s>" % m.group(1)
+    m = re.match(r"(\w+_kernel)<(.*)>$", name)
+    if m and m.group(1).startswith("csr_"):
+        return short_name(full)
+    return name.split("<")[0] if name.startswith(("relax_zero", "coarse_gemv", "dot_kernel", "ew_kernel")) else name
+
+
+def iteration_table(tag, raw_csv, what, peak=6586.7):
+    """profiles/<tag>_kernels.md: one row per launch of ONE Krylov iteration captured with
+    ncu --set full (tools/ncu_capture.py): duration, DRAM bytes, achieved DRAM GB/s against the
+    measured HBM peak, and the cache / pipe utilisation that explains the gap."""
+    rows = list(csv.reader(open(raw_csv)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    kn = hdr.index("Kernel Name")
+
+    def num(r, key):
+        if key not in hdr:
+            return None
+        i = hdr.index(key)
+        try:
+            v = float(r[i].replace(",", ""))
+        except ValueError:
+            return None
+        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "us": 1e-6, "ms": 1e-3, "ns": 1e-9,
+                 "second": 1.0, "msecond": 1e-3, "usecond": 1e-6, "nsecond": 1e-9}.get(units[i], 1.0)
+        return v * scale
+
+    out = ["# %s: every kernel of one %s (ncu --set full --clock-control none)" % (tag, what), "",
+           "Captured by `python tools/ncu_capture.py` (pass 2: the launches of the second iteration of "
+           "the first solve).  Durations under ncu are serialised and cold-cache; `DRAM GB/s` = "
+           "(dram__bytes_read.sum + dram__bytes_write.sum) / gpu__time_duration, `of peak` against the "
+           "measured %.1f GB/s (MEASURED_PEAKS.json).  Kernels on operators that fit the 126 MB L2 read "
+           "less from DRAM than they stream: their bound is the launch / dependency latency, see "
+           "DESIGN.md." % peak, "",
+           "| # | kernel | grid | regs | time us | DRAM read MB | DRAM write MB | DRAM GB/s | of peak | "
+           "dram % | L2 % | L1TEX % | SM % | L1 hit % | L2 hit % |",
+           "|---:|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|"]
+    for i, r in enumerate(data):
+        t = num(r, "gpu__time_duration.sum")
+        rd, wr = num(r, "dram__bytes_read.sum") or 0.0, num(r, "dram__bytes_write.sum") or 0.0
+        gbs = (rd + wr) / t / 1e9 if t else 0.0
+
+        def pct(key):
+            v = num(r, key)
+            return "%.1f" % v if v is not None else "n/a"
+        out.append("| %d | `%s` | %s | %s | %.1f | %.1f | %.1f | %.0f | %.2f | %s | %s | %s | %s | %s | %s |" % (
+            i, short_any(r[kn]), r[hdr.index("launch__grid_size")] if "launch__grid_size" in hdr else "",
+            r[hdr.index("launch__registers_per_thread")] if "launch__registers_per_thread" in hdr else "",
+            t * 1e6, rd / 1e6, wr / 1e6, gbs, gbs / peak,
+            pct("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+            pct("lts__throughput.avg.pct_of_peak_sustained_elapsed"),
+            pct("l1tex__throughput.avg.pct_of_peak_sustained_elapsed"),
+            pct("sm__throughput.avg.pct_of_peak_sustained_elapsed"),
+            pct("l1tex__t_sector_hit_rate.pct"), pct("lts__t_sector_hit_rate.pct")))
+    open(os.path.join(PROF, tag + "_kernels.md"), "w").write("\n".join(out) + "\n")
+    return data, hdr, units
+
+
 if __name__ == "__main__":
     os.makedirs(PROF, exist_ok=True)
     tag = sys.argv[1]
-    launch_shares(tag, sys.argv[2])
-    if len(sys.argv) > 3:
-        full_capture(tag, sys.argv[3])
+    if sys.argv[2] == "--iteration":
+        # summarize_ncu.py <tag> --iteration <raw.csv> <launches.csv> "<what>"
+        iteration_table(tag, sys.argv[3], sys.argv[5] if len(sys.argv) > 5 else "Krylov iteration")
+        launch_shares(tag, sys.argv[4])
+    else:
+        launch_shares(tag, sys.argv[2])
+        if len(sys.argv) > 3:
+            full_capture(tag, sys.argv[3])
