@@ -149,13 +149,15 @@ extern "C" int b200_coarse_create_i32(b200_ctx_t ctx, int64_t n, const int32_t *
 extern "C" int b200_coarse_create_i64_f32(b200_ctx_t ctx, int64_t n, const int64_t *ptr,
                                           const int64_t *col, const float *val, b200_coarse_t *S) {
     CHECK_CTX(ctx);
-    B200_REQUIRE_F64_DIST(ctx, "b200_coarse_create_*_f32");
+    B200_REQUIRE(!ctx->dist || n < ctx->dist_min_rows,
+                 "b200_coarse_create_*_f32: a PARTITIONED coarsest level needs an FP64 hierarchy");
     return coarse_create(ctx, n, ptr, col, val, S);
 }
 extern "C" int b200_coarse_create_i32_f32(b200_ctx_t ctx, int64_t n, const int32_t *ptr,
                                           const int32_t *col, const float *val, b200_coarse_t *S) {
     CHECK_CTX(ctx);
-    B200_REQUIRE_F64_DIST(ctx, "b200_coarse_create_*_f32");
+    B200_REQUIRE(!ctx->dist || n < ctx->dist_min_rows,
+                 "b200_coarse_create_*_f32: a PARTITIONED coarsest level needs an FP64 hierarchy");
     return coarse_create(ctx, n, ptr, col, val, S);
 }
 

@@ -212,7 +212,7 @@ void peer_release(b200_ctx_t ctx, void *local, void **peers) {
 // Peer transport: nothing is launched here -- the consumer kernel pushes this rank's values
 // itself (HaloArgs::push_*) and waits for the peers' flags block by block.  NCCL transport: one
 // pack kernel + one in-place ncclAllGather (S doubles per rank) on the stream.
-int halo_exchange(b200_ctx_t ctx, b200_csr_t A, const double *x, HaloArgs &a) {
+int halo_exchange(b200_ctx_t ctx, b200_csr_t A, const void *x, size_t esz, HaloArgs &a) {
     a = HaloArgs();
     {
         const int trc = tail_flush(ctx);
@@ -226,7 +226,7 @@ int halo_exchange(b200_ctx_t ctx, b200_csr_t A, const double *x, HaloArgs &a) {
         unsigned int mask = 0;
         for (int q = 0; q < ctx->nranks; ++q) {
             if (q == ctx->rank || !A->xchg[q]) continue;
-            a.push_data[q] = data_at(A->pb_peer[q], par, A->pb_half) + (size_t)ctx->rank * A->S;
+            a.push_data[q] = data_at(A->pb_peer[q], par, A->pb_half) + (size_t)ctx->rank * A->S * esz;
             a.push_flag[q] = flag_at(A->pb_peer[q], par, ctx->rank);
             mask |= 1u << q;
         }
@@ -243,27 +243,33 @@ int halo_exchange(b200_ctx_t ctx, b200_csr_t A, const double *x, HaloArgs &a) {
         return B200_OK;
     }
     ProfScope prof(ctx, B200_PROF_COMM, A->n_send, ctx->nranks, 0);
-    double *mine = A->halo + (size_t)ctx->rank * A->S;
+    char *mine = static_cast<char *>(A->halo) + (size_t)ctx->rank * A->S * esz;
     if (A->n_send) {
         const unsigned grid = (unsigned)((A->n_send + kThreads - 1) / kThreads);
-        halo_pack_kernel<<<grid, kThreads, 0, ctx->stream>>>(A->n_send, A->send_idx, x, mine);
+        if (esz == sizeof(double))
+            halo_pack_kernel<double><<<grid, kThreads, 0, ctx->stream>>>(A->n_send, A->send_idx,
+                static_cast<const double *>(x), reinterpret_cast<double *>(mine));
+        else
+            halo_pack_kernel<float><<<grid, kThreads, 0, ctx->stream>>>(A->n_send, A->send_idx,
+                static_cast<const float *>(x), reinterpret_cast<float *>(mine));
         B200_CHECK_LAUNCH();
         ctx->launches++;
     }
-    B200_NCCL(nccl().AllGather(mine, A->halo, (size_t)A->S, ncclDouble, comm_of(ctx), ctx->stream));
+    B200_NCCL(nccl().AllGather(mine, A->halo, (size_t)A->S, esz == sizeof(double) ? ncclDouble : ncclFloat,
+                               comm_of(ctx), ctx->stream));
     return B200_OK;
 }
 
 // Row shares of a replicated result (gather_rows).  begin: where the kernel stores its rows.
 // Peer transport: straight into every rank's gather buffer (a.gather_*), local y = own buffer.
 // NCCL transport: into this rank's slot of A->ybuf.
-int gather_begin(b200_ctx_t ctx, b200_csr_t A, GatherArgs &g) {
+int gather_begin(b200_ctx_t ctx, b200_csr_t A, size_t esz, GatherArgs &g) {
     g = GatherArgs();
     if (ctx->p2p) {
         const int par = (int)(A->gseq & 1);
         const unsigned long long seq = ++A->gseq;
         for (int q = 0; q < ctx->nranks; ++q) {
-            g.data[q] = data_at(A->gb_peer[q], par, A->gb_half) + (size_t)ctx->rank * A->row_B;
+            g.data[q] = data_at(A->gb_peer[q], par, A->gb_half) + (size_t)ctx->rank * A->row_B * esz;
             g.flag[q] = flag_at(A->gb_peer[q], par, ctx->rank);
         }
         g.on = 1;
@@ -274,7 +280,7 @@ int gather_begin(b200_ctx_t ctx, b200_csr_t A, GatherArgs &g) {
         g.data[ctx->rank] = nullptr;             // (so it is not stored twice)
         return B200_OK;
     }
-    g.y_local = A->ybuf + (size_t)ctx->rank * A->row_B;
+    g.y_local = reinterpret_cast<char *>(A->ybuf) + (size_t)ctx->rank * A->row_B * esz;
     return B200_OK;
 }
 
@@ -286,6 +292,7 @@ int gather_end(b200_ctx_t ctx, b200_csr_t A, const GatherArgs &g, b200_vec_t y) 
     }
     ProfScope prof(ctx, B200_PROF_COMM, A->gl_rows, ctx->nranks, 2);
     const int64_t count = A->gl_rows;
+    const size_t esz = y->esz;
     if (ctx->p2p) {
         const int par = (int)((A->gseq - 1) & 1);
         WaitList w;
@@ -293,14 +300,20 @@ int gather_end(b200_ctx_t ctx, b200_csr_t A, const GatherArgs &g, b200_vec_t y) 
         for (int q = 0; q < ctx->nranks; ++q) w.flag[q] = flag_at(A->gb_local, par, q);
         const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((count + kThreads * 4 - 1) / (kThreads * 4),
                                                                                (int64_t)ctx->sm_count * 4));
-        gather_copy_kernel<<<grid, kThreads, 0, ctx->stream>>>(count, data_at(A->gb_local, par, A->gb_half), w,
-                                                               ctx->nranks, g.seq, wr(y));
+        const char *staged = data_at(A->gb_local, par, A->gb_half);
+        if (esz == sizeof(double))
+            gather_copy_kernel<double><<<grid, kThreads, 0, ctx->stream>>>(
+                count, reinterpret_cast<const double *>(staged), w, ctx->nranks, g.seq, wr(y));
+        else
+            gather_copy_kernel<float><<<grid, kThreads, 0, ctx->stream>>>(
+                count, reinterpret_cast<const float *>(staged), w, ctx->nranks, g.seq, tp<float>(wr(y)));
         B200_CHECK_LAUNCH();
         ctx->launches++;
         return B200_OK;
     }
-    B200_NCCL(nccl().AllGather(g.y_local, A->ybuf, (size_t)A->row_B, ncclDouble, comm_of(ctx), ctx->stream));
-    B200_CUDA(cudaMemcpyAsync(wr(y), A->ybuf, (size_t)count * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    B200_NCCL(nccl().AllGather(g.y_local, A->ybuf, (size_t)A->row_B, esz == sizeof(double) ? ncclDouble : ncclFloat,
+                               comm_of(ctx), ctx->stream));
+    B200_CUDA(cudaMemcpyAsync(wr(y), A->ybuf, (size_t)count * esz, cudaMemcpyDeviceToDevice, ctx->stream));
     return B200_OK;
 }
 

@@ -265,23 +265,12 @@ static void csr_free(b200_csr_t A) {
     delete A;
 }
 
-// The public constructor: on a distributed context decide from the shape which
-// kind of operator this is (see dist.cuh) and keep only this rank's share.
-template <class Ptr, class Col>
-static int csr_create_f32(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *ptr,
-                          const Col *col, const float *val, b200_csr_t *out) {
-    CHECK_CTX(ctx);
-    NOT_RECORDING(ctx, "matrix creation");
-    B200_REQUIRE_F64_DIST(ctx, "b200_csr_create_*_f32");
-    return csr_upload(ctx, nrows, ncols, ptr, col, val, out);
-}
-
 // The public constructor.  On a distributed context (dist.cuh) the shape decides how the
 // operator is shared out: a dimension >= the threshold belongs to a partitioned level, a smaller
 // one to a replicated level; a rank always keeps whole rows.
-template <class Ptr, class Col>
+template <class Ptr, class Col, class Val>
 static int csr_create(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *ptr,
-                      const Col *col, const double *val, b200_csr_t *out) {
+                      const Col *col, const Val *val, b200_csr_t *out) {
     CHECK_CTX(ctx);
     NOT_RECORDING(ctx, "matrix creation");
     B200_REQUIRE(out != nullptr, "null output pointer");
@@ -363,7 +352,7 @@ static int csr_create(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *p
             A->xchg[q] = q != rank && (sp.dep[(size_t)rank * P + q] || sp.dep[(size_t)q * P + rank]);
     }
     if (A->gather_rows && !ctx->p2p) {
-        DCSR_CUDA(cudaMalloc(&A->ybuf, ((size_t)P * (size_t)rows.B + 2) * sizeof(double)));
+        DCSR_CUDA(cudaMalloc((void **)&A->ybuf, ((size_t)P * (size_t)rows.B + 2) * sizeof(double)));
         DCSR_CUDA(cudaMemsetAsync(A->ybuf, 0, ((size_t)P * (size_t)rows.B + 2) * sizeof(double), ctx->stream));
         A->bytes += (size_t)P * (size_t)rows.B * sizeof(double);
     }
@@ -446,8 +435,7 @@ static int launch_csr_LH(b200_ctx_t ctx, b200_csr_t A, const CsrArgsT<P> &args) 
 
 template <int MODE, int L, class P>
 static int launch_csr_L(b200_ctx_t ctx, b200_csr_t A, const CsrArgsT<P> &args) {
-    if (std::is_same<P, PrecDD>::value && args.xh)
-        return launch_csr_LH<MODE, L, true, PrecDD>(ctx, A, *reinterpret_cast<const CsrArgsT<PrecDD> *>(&args));
+    if (args.xh) return launch_csr_LH<MODE, L, true, P>(ctx, A, args);
     return launch_csr_LH<MODE, L, false, P>(ctx, A, args);
 }
 
@@ -487,14 +475,19 @@ static CsrArgsT<P> base_args_t(b200_csr_t A) {
 static CsrArgs base_args(b200_csr_t A) { return base_args_t<PrecDD>(A); }
 
 // multi-GPU: make the boundary values of a.x visible and tell the kernel where they are
-static int halo_into(b200_ctx_t ctx, b200_csr_t A, CsrArgs &a) {
+template <class P>
+static int halo_into(b200_ctx_t ctx, b200_csr_t A, CsrArgsT<P> &a) {
+    typedef typename P::TX TX;
     HaloArgs h;
-    const int rc = halo_exchange(ctx, A, a.x, h);
+    const int rc = halo_exchange(ctx, A, a.x, sizeof(TX), h);
     if (rc) return rc;
-    a.xh = h.xh; a.nloc = h.nloc;
+    a.xh = static_cast<const TX *>(h.xh); a.nloc = h.nloc;
     a.wait_flags = h.wait_flags; a.wait_mask = h.wait_mask; a.wait_seq = h.wait_seq;
     a.send_idx = h.send_idx; a.n_send = h.n_send; a.nranks = h.nranks;
-    for (int q = 0; q < kMaxRanks; ++q) { a.push_data[q] = h.push_data[q]; a.push_flag[q] = h.push_flag[q]; }
+    for (int q = 0; q < kMaxRanks; ++q) {
+        a.push_data[q] = static_cast<TX *>(h.push_data[q]);
+        a.push_flag[q] = h.push_flag[q];
+    }
     a.push_ticket = h.push_ticket; a.push_seq = h.push_seq;
     return B200_OK;
 }
@@ -517,13 +510,13 @@ extern "C" int b200_csr_create_i32(b200_ctx_t ctx, int64_t nrows, int64_t ncols,
 extern "C" int b200_csr_create_i64_f32(b200_ctx_t ctx, int64_t nrows, int64_t ncols,
                                        const int64_t *ptr, const int64_t *col, const float *val,
                                        b200_csr_t *A) {
-    return csr_create_f32(ctx, nrows, ncols, ptr, col, val, A);
+    return csr_create(ctx, nrows, ncols, ptr, col, val, A);
 }
 
 extern "C" int b200_csr_create_i32_f32(b200_ctx_t ctx, int64_t nrows, int64_t ncols,
                                        const int32_t *ptr, const int32_t *col, const float *val,
                                        b200_csr_t *A) {
-    return csr_create_f32(ctx, nrows, ncols, ptr, col, val, A);
+    return csr_create(ctx, nrows, ncols, ptr, col, val, A);
 }
 
 extern "C" int b200_csr_dtype(b200_csr_t A, int *dtype) {
@@ -619,29 +612,58 @@ static void apply_req(b200_ctx_t ctx, b200_csr_t A, CsrArgsT<P> &a, DotReq *req)
     req->done = true;
 }
 
+// y = alpha*A*x + beta*y for one precision combination, single- or multi-GPU
 template <class P>
-static int spmv_local(b200_ctx_t ctx, double alpha, b200_csr_t A, b200_vec_t x, double beta,
+static int spmv_typed(b200_ctx_t ctx, double alpha, b200_csr_t A, b200_vec_t x, double beta,
                       b200_vec_t y, DotReq *req = nullptr) {
+    typedef typename P::TX TX;
+    typedef typename P::TY TY;
     CsrArgsT<P> a = base_args_t<P>(A);
     const double *px;
     int rc = rd(x, &px);
     if (rc) return rc;
-    a.x = tp<typename P::TX>(px);
+    a.x = tp<TX>(px);
     a.alpha = alpha; a.beta = beta;
+    // distributed context: x / y are blocks of partitioned vectors or whole replicated ones
+    if (ctx->dist) {
+        B200_REQUIRE((x->kind == B200_VK_DIST) == A->cols_dist && (y->kind == B200_VK_DIST) == A->rows_dist,
+                     "spmv: vectors are not laid out like the operator (partitioned vs replicated)");
+    }
+    if (A->kind == B200_CK_HALO) {
+        rc = halo_into(ctx, A, a);
+        if (rc) return rc;
+    }
+    if (A->gather_rows) {
+        // y is replicated, x partitioned: this rank computes its share of the rows, the shares
+        // are all-gathered (R onto a small level)
+        B200_REQUIRE(beta == 0.0 || y->zero_pending, "spmv onto a replicated level needs beta == 0");
+        GatherArgs g;
+        rc = gather_begin(ctx, A, sizeof(TY), g);
+        if (rc) return rc;
+        a.gather_on = g.on; a.nranks = ctx->nranks;
+        for (int q = 0; q < kMaxRanks; ++q) {
+            a.gather_data[q] = static_cast<TY *>(g.data[q]);
+            a.gather_flag[q] = g.flag[q];
+        }
+        a.gather_ticket = g.ticket; a.gather_seq = g.seq;
+        a.y = static_cast<TY *>(g.y_local);
+        rc = launch_csr<MODE_SPMV>(ctx, A, a);
+        if (rc) return rc;
+        return gather_end(ctx, A, g, y);
+    }
     apply_req(ctx, A, a, req);
     if (beta == 0.0 || y->zero_pending) {
-        a.y = tp<typename P::TY>(wr(y));
+        a.y = tp<TY>(wr(y));
         return launch_csr<MODE_SPMV>(ctx, A, a);
     }
-    a.y = tp<typename P::TY>(mut(y));
+    a.y = tp<TY>(mut(y));
     return launch_csr<MODE_SPMV_ACC>(ctx, A, a);
 }
 
 template <class P>
-static int residual_local(b200_ctx_t ctx, b200_vec_t f, b200_csr_t A, b200_vec_t x, b200_vec_t r,
+static int residual_typed(b200_ctx_t ctx, b200_vec_t f, b200_csr_t A, b200_vec_t x, b200_vec_t r,
                           DotReq *req = nullptr) {
     CsrArgsT<P> a = base_args_t<P>(A);
-    apply_req(ctx, A, a, req);
     const double *px, *pf;
     int rc = rd(x, &px);
     if (rc) return rc;
@@ -649,7 +671,14 @@ static int residual_local(b200_ctx_t ctx, b200_vec_t f, b200_csr_t A, b200_vec_t
     if (rc) return rc;
     a.x = tp<typename P::TX>(px);
     a.f = tp<typename P::TF>(pf);
-    a.y = tp<typename P::TY>((f == r) ? mut(r) : wr(r));
+    if (A->kind == B200_CK_HALO) {
+        B200_REQUIRE(x->kind == B200_VK_DIST && f->kind == B200_VK_DIST && r->kind == B200_VK_DIST,
+                     "residual: vectors must be partitioned like the operator");
+        rc = halo_into(ctx, A, a);
+        if (rc) return rc;
+    }
+    a.y = tp<typename P::TY>((f == r) ? mut(r) : wr(r));   // r == f is fine: each row reads f[r] before writing
+    apply_req(ctx, A, a, req);
     return launch_csr<MODE_RESID>(ctx, A, a);
 }
 
@@ -670,49 +699,15 @@ static int spmv_impl(b200_ctx_t ctx, double alpha, b200_csr_t A, b200_vec_t x, d
     GUARD_DEFER(ctx);
     TailHold hold(ctx, {x, y});
     if (A->dtype == B200_F32) {
-        // FP32 operator (mixed-precision hierarchy): single GPU, persistent ring kernels
-        if (all32({x, y})) return spmv_local<PrecFF>(ctx, alpha, A, x, beta, y);
-        if (all64({x, y})) return spmv_local<PrecFD>(ctx, alpha, A, x, beta, y, req);
+        // FP32 operator (mixed-precision hierarchy)
+        if (all32({x, y})) return spmv_typed<PrecFF>(ctx, alpha, A, x, beta, y);
+        if (all64({x, y})) return spmv_typed<PrecFD>(ctx, alpha, A, x, beta, y, req);
         if (x->dtype == B200_F32 && y->dtype == B200_F64)
-            return spmv_local<PrecFFD>(ctx, alpha, A, x, beta, y);
+            return spmv_typed<PrecFFD>(ctx, alpha, A, x, beta, y);
         return B200_BAD_MIX("spmv");
     }
     if (!all64({x, y})) return B200_BAD_MIX("spmv");
-    CsrArgs a = base_args(A);
-    a.alpha = alpha; a.beta = beta;
-    int rc = rd(x, &a.x);
-    if (rc) return rc;
-    // distributed context: x / y are blocks of partitioned vectors or whole replicated ones
-    if (ctx->dist) {
-        B200_REQUIRE((x->kind == B200_VK_DIST) == A->cols_dist && (y->kind == B200_VK_DIST) == A->rows_dist,
-                     "spmv: vectors are not laid out like the operator (partitioned vs replicated)");
-    }
-    if (A->kind == B200_CK_HALO) {
-        rc = halo_into(ctx, A, a);
-        if (rc) return rc;
-    }
-    if (A->gather_rows) {
-        // y is replicated, x partitioned: this rank computes its share of the rows, the shares
-        // are all-gathered (R onto a small level)
-        B200_REQUIRE(beta == 0.0 || y->zero_pending, "spmv onto a replicated level needs beta == 0");
-        GatherArgs g;
-        rc = gather_begin(ctx, A, g);
-        if (rc) return rc;
-        a.gather_on = g.on; a.nranks = ctx->nranks;
-        for (int q = 0; q < kMaxRanks; ++q) { a.gather_data[q] = g.data[q]; a.gather_flag[q] = g.flag[q]; }
-        a.gather_ticket = g.ticket; a.gather_seq = g.seq;
-        a.y = g.y_local;
-        rc = launch_csr<MODE_SPMV>(ctx, A, a);
-        if (rc) return rc;
-        return gather_end(ctx, A, g, y);
-    }
-    apply_req(ctx, A, a, req);
-    if (beta == 0.0 || y->zero_pending) {
-        a.y = wr(y);
-        return launch_csr<MODE_SPMV>(ctx, A, a);
-    }
-    a.y = mut(y);
-    return launch_csr<MODE_SPMV_ACC>(ctx, A, a);
+    return spmv_typed<PrecDD>(ctx, alpha, A, x, beta, y, req);
 }
 
 static int residual_impl(b200_ctx_t ctx, b200_vec_t f, b200_csr_t A, b200_vec_t x, b200_vec_t r,
@@ -750,26 +745,13 @@ static int residual_impl(b200_ctx_t ctx, b200_vec_t f, b200_csr_t A, b200_vec_t 
         if (lrc) return lrc;
     }
     if (A->dtype == B200_F32) {
-        if (all32({f, x, r})) return residual_local<PrecFF>(ctx, f, A, x, r);
-        if (all64({f, x, r})) return residual_local<PrecFD>(ctx, f, A, x, r, req);
-        if (all64({f, x}) && r->dtype == B200_F32) return residual_local<PrecFDF>(ctx, f, A, x, r);
+        if (all32({f, x, r})) return residual_typed<PrecFF>(ctx, f, A, x, r);
+        if (all64({f, x, r})) return residual_typed<PrecFD>(ctx, f, A, x, r, req);
+        if (all64({f, x}) && r->dtype == B200_F32) return residual_typed<PrecFDF>(ctx, f, A, x, r);
         return B200_BAD_MIX("residual");
     }
     if (!all64({f, x, r})) return B200_BAD_MIX("residual");
-    CsrArgs a = base_args(A);
-    int rc = rd(x, &a.x);
-    if (rc) return rc;
-    rc = rd(f, &a.f);
-    if (rc) return rc;
-    if (A->kind == B200_CK_HALO) {
-        B200_REQUIRE(x->kind == B200_VK_DIST && f->kind == B200_VK_DIST && r->kind == B200_VK_DIST,
-                     "residual: vectors must be partitioned like the operator");
-        rc = halo_into(ctx, A, a);
-        if (rc) return rc;
-    }
-    a.y = (f == r) ? mut(r) : wr(r);   // r == f is fine: each row reads f[r] before writing
-    apply_req(ctx, A, a, req);
-    return launch_csr<MODE_RESID>(ctx, A, a);
+    return residual_typed<PrecDD>(ctx, f, A, x, r, req);
 }
 
 // y = A x (alpha = 1, beta = 0) leaving <y, w> (and <y, y> when ndot == 2) in the table slots;
@@ -924,6 +906,11 @@ extern "C" int b200_relax(b200_ctx_t ctx, b200_csr_t A, b200_vec_t rhs, b200_vec
         rc = rd(x, &px);
         if (rc) return rc;
         a.x = tp<float>(px); a.f = tp<float>(pf); a.d = tp<float>(pd); a.alpha = omega;
+        if (A->kind == B200_CK_HALO) {
+            B200_REQUIRE(x->kind == B200_VK_DIST, "relax: vectors must be partitioned like the operator");
+            rc = halo_into(ctx, A, a);
+            if (rc) return rc;
+        }
         a.y = tp<float>(wr(tmp));
         rc = launch_csr<MODE_RELAX>(ctx, A, a);
         if (rc) return rc;
@@ -946,6 +933,11 @@ extern "C" int b200_relax(b200_ctx_t ctx, b200_csr_t A, b200_vec_t rhs, b200_vec
         rc = rd(x, &px);
         if (rc) return rc;
         a.x = px; a.f = pf; a.d = tp<float>(pd); a.alpha = omega;
+        if (A->kind == B200_CK_HALO) {
+            B200_REQUIRE(x->kind == B200_VK_DIST, "relax: vectors must be partitioned like the operator");
+            rc = halo_into(ctx, A, a);
+            if (rc) return rc;
+        }
         a.y = A->scratch64;
         // a Krylov solver of this size is alive: leave <rhs, x_new> behind (cg.hpp:184)
         DotReq req;

@@ -15,7 +15,6 @@ static int vec_create_typed(b200_ctx_t ctx, size_t n, int dtype, b200_vec_t *out
     NOT_RECORDING(ctx, "vector creation");
     B200_REQUIRE(out != nullptr, "null output pointer");
     *out = nullptr;
-    if (dtype == B200_F32) B200_REQUIRE_F64_DIST(ctx, "b200_vec_create_f32");
     GUARD(ctx);
     b200_vec_s *v = new (std::nothrow) b200_vec_s();
     if (!v) return fail(B200_ENOMEM, "out of host memory");
@@ -44,7 +43,8 @@ static int vec_create_typed(b200_ctx_t ctx, size_t n, int dtype, b200_vec_t *out
     }
     if (v->cap > v->len) {
         // padding of a partial block takes part in collectives: keep it zero
-        rc = cudaMemsetAsync(v->ptr + v->len, 0, (v->cap - v->len) * sizeof(double), ctx->stream);
+        rc = cudaMemsetAsync(reinterpret_cast<char *>(v->ptr) + v->len * v->esz, 0, (v->cap - v->len) * v->esz,
+                             ctx->stream);
         if (rc != cudaSuccess) {
             cudaFree(v->ptr);
             delete v;
@@ -142,10 +142,12 @@ extern "C" int b200_vec_upload_f32(b200_vec_t v, const float *host, size_t n) {
     B200_REQUIRE(v && (host || n == 0), "null argument");
     NOT_RECORDING(v->ctx, "host transfer");
     B200_REQUIRE(n == v->n, "size mismatch in vector upload");
-    B200_REQUIRE(v->dtype == B200_F32 && v->kind == B200_VK_LOCAL, "upload_f32: FP32 local vector expected");
+    B200_REQUIRE(v->dtype == B200_F32, "upload_f32: FP32 vector expected");
     GUARD(v->ctx);
-    if (n) {
-        B200_CUDA(cudaMemcpyAsync(wr(v), host, n * sizeof(float), cudaMemcpyHostToDevice, v->ctx->stream));
+    if (v->len) {
+        // distributed: every rank is handed the full host vector and keeps its block
+        B200_CUDA(cudaMemcpyAsync(wr(v), host + v->off, v->len * sizeof(float), cudaMemcpyHostToDevice,
+                                  v->ctx->stream));
         B200_CUDA(cudaStreamSynchronize(v->ctx->stream));
     }
     v->zero_pending = false;
@@ -156,7 +158,8 @@ extern "C" int b200_vec_download_f32(b200_vec_t v, float *host, size_t n) {
     B200_REQUIRE(v && (host || n == 0), "null argument");
     NOT_RECORDING(v->ctx, "host transfer");
     B200_REQUIRE(n == v->n, "size mismatch in vector download");
-    B200_REQUIRE(v->dtype == B200_F32 && v->kind == B200_VK_LOCAL, "download_f32: FP32 local vector expected");
+    B200_REQUIRE(v->dtype == B200_F32 && v->kind == B200_VK_LOCAL,
+                 "download_f32: FP32 vector of a replicated level (or a single GPU) expected");
     GUARD(v->ctx);
     if (!n) return B200_OK;
     int rc = materialize(v);

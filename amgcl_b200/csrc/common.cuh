@@ -158,7 +158,8 @@ struct b200_ctx_s {
     int64_t opt_tail_max_nnz  = 1500000;  // ... "small": at most this many non-zeros
     int64_t opt_tail_max_vec  = 262144;   // ... element-wise x = 0 sweeps: at most this many entries
     int64_t opt_poll_scalars  = 1;        // host reads in-kernel reduction results by polling mapped memory
-    int64_t opt_warm_lines    = 1;        // gather-heavy operators: touch a block's lines of x before reducing it
+    int64_t opt_warm_lines    = 0;        // gather-heavy operators: touch a block's lines of x before reducing it
+                                          // (opt-in experiment: measured no gain)
     int64_t opt_fused_krylov  = 1;        // the C++ binding's cg / bicgstab use the fused b200_cg_* / b200_bicg_* steps
 
     // CUDA-graph recording of a call sequence (b200_graph_*)
@@ -218,8 +219,8 @@ struct b200_csr_s {
     int64_t    S       = 0;       // HALO: halo slots per rank
     int64_t    n_send  = 0;       // HALO: entries this rank contributes
     int       *send_idx = nullptr;// HALO: [n_send] local indices to pack
-    double    *halo    = nullptr; // HALO: [nranks*S] boundary values the kernel gathers from
-    double    *halo_owned = nullptr; //     NCCL transport: private buffer (peer transport: inside pb)
+    void      *halo    = nullptr; // HALO: [nranks*S] boundary values (x's element type) the kernel gathers from
+    void      *halo_owned = nullptr; //     NCCL transport: private buffer (peer transport: inside pb)
     double    *ybuf    = nullptr; // gather_rows, NCCL transport: [nranks*row_B] all-gather buffer
     // peer-memory exchange state (peer.cuh); layout: [flags 256 B | parity 0 | parity 1]
     void      *pb_local = nullptr;    // halo of x

@@ -90,14 +90,14 @@ struct CsrArgsT {
     const int                *send_idx;
     int                       n_send;
     int                       nranks;
-    double                   *push_data[kMaxRanks];   // my segment in peer q's halo buffer (or nullptr)
+    typename P::TX           *push_data[kMaxRanks];   // my segment in peer q's halo buffer (or nullptr)
     unsigned long long       *push_flag[kMaxRanks];   // my flag in peer q's flag row (or nullptr)
     unsigned int             *push_ticket;
     unsigned long long        push_seq;                // 0: nothing to push / NCCL transport
     // row shares of a replicated result (R onto a small level): every row is also stored into
     // every rank's gather buffer; the last CTA releases the flags at the end of the kernel
     int                       gather_on;
-    double                   *gather_data[kMaxRanks]; // my share's place in rank q's buffer
+    typename P::TY           *gather_data[kMaxRanks]; // my share's place in rank q's buffer
     unsigned long long       *gather_flag[kMaxRanks];
     unsigned int             *gather_ticket;
     unsigned long long        gather_seq;
@@ -218,7 +218,7 @@ __device__ __forceinline__ void store_row(const CsrArgsT<P> &a, int r, typename 
     if (a.gather_on) {
 #pragma unroll 1
         for (int q = 0; q < a.nranks; ++q)
-            if (a.gather_data[q]) a.gather_data[q][r] = (double)out;
+            if (a.gather_data[q]) a.gather_data[q][r] = out;
     }
     if (a.ndot) {
         const double yv = (double)out;
@@ -427,7 +427,7 @@ __device__ __forceinline__ void halo_push(const CsrArgsT<P> &a) {
     if (!a.push_seq) return;
     const typename P::TX *__restrict__ x = a.x;
     for (int i = blockIdx.x * kThreads + threadIdx.x; i < a.n_send; i += gridDim.x * kThreads) {
-        const double v = (double)x[a.send_idx[i]];
+        const typename P::TX v = x[a.send_idx[i]];
 #pragma unroll 1
         for (int q = 0; q < a.nranks; ++q)
             if (a.push_data[q]) a.push_data[q][i] = v;

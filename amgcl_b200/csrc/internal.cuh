@@ -195,8 +195,8 @@ namespace b200 {
 inline unsigned long long *flag_at(void *base, int parity, int slot) {
     return reinterpret_cast<unsigned long long *>(base) + parity * kFlagStride + slot;
 }
-inline double *data_at(void *base, int parity, size_t half_bytes) {
-    return reinterpret_cast<double *>(static_cast<char *>(base) + kFlagBytes + (size_t)parity * half_bytes);
+inline char *data_at(void *base, int parity, size_t half_bytes) {
+    return static_cast<char *>(base) + kFlagBytes + (size_t)parity * half_bytes;
 }
 
 // Launch with programmatic stream serialization (PDL) when enabled: the kernel may be
@@ -253,7 +253,7 @@ int  peer_alloc(b200_ctx_t ctx, size_t bytes, void **local, void **peers);
 void peer_release(b200_ctx_t ctx, void *local, void **peers);
 // what halo_exchange hands to the consumer kernel (copied into its CsrArgs)
 struct HaloArgs {
-    const double             *xh = nullptr;         // halo values for columns >= nloc
+    const void               *xh = nullptr;         // halo values for columns >= nloc (x's element type)
     int                       nloc = 0;
     const unsigned long long *wait_flags = nullptr;
     unsigned int              wait_mask = 0;
@@ -262,23 +262,23 @@ struct HaloArgs {
     const int                *send_idx = nullptr;
     int                       n_send = 0;
     int                       nranks = 0;
-    double                   *push_data[kMaxRanks] = {};
+    void                     *push_data[kMaxRanks] = {};
     unsigned long long       *push_flag[kMaxRanks] = {};
     unsigned int             *push_ticket = nullptr;
     unsigned long long        push_seq = 0;
 };
-int  halo_exchange(b200_ctx_t ctx, b200_csr_t A, const double *x, HaloArgs &a);
+int  halo_exchange(b200_ctx_t ctx, b200_csr_t A, const void *x, size_t esz, HaloArgs &a);
 // row shares of a replicated result
 struct GatherArgs {
     int                 on = 0;                     // peer transport: kernel stores into the peers
     int                 nranks = 0;
-    double             *data[kMaxRanks] = {};
+    void               *data[kMaxRanks] = {};       // (y's element type)
     unsigned long long *flag[kMaxRanks] = {};
     unsigned int       *ticket = nullptr;
     unsigned long long  seq = 0;
-    double             *y_local = nullptr;          // where the kernel's plain store of a row goes
+    void               *y_local = nullptr;          // where the kernel's plain store of a row goes
 };
-int  gather_begin(b200_ctx_t ctx, b200_csr_t A, GatherArgs &g);
+int  gather_begin(b200_ctx_t ctx, b200_csr_t A, size_t esz, GatherArgs &g);
 int  gather_end(b200_ctx_t ctx, b200_csr_t A, const GatherArgs &g, b200_vec_t y);
 int  dist_dot_finish(b200_ctx_t ctx, double *result);
 
@@ -296,8 +296,6 @@ inline ncclComm_t comm_of(b200_ctx_t ctx) { return static_cast<ncclComm_t>(ctx->
 inline bool same_layout(b200_vec_t a, b200_vec_t b) {
     return a->n == b->n && a->kind == b->kind && a->len == b->len;
 }
-#define B200_REQUIRE_F64_DIST(ctx, what)                                                    \
-    B200_REQUIRE(!(ctx)->dist, what ": FP32 objects are not supported on a distributed context")
 #define NOT_RECORDING(ctx, what)                                                        \
     B200_REQUIRE(!(ctx)->recording, what ": not allowed while a graph is being recorded")
 // Every entry point that touches the device runs under GUARD: the context's device is made

@@ -54,9 +54,10 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 // dst[i] = staged[i], i < count, once the shares of all ranks have landed: the row shares of a
 // replicated result (R onto a small level) were stored straight into every rank's gather
 // buffer by the kernels that computed them (csr_kernels.cuh: gather_data / gather_finish).
+template <class T>
 __global__ void __launch_bounds__(kThreads)
-gather_copy_kernel(int64_t count, const double *staged, WaitList w, int nranks,
-                   unsigned long long seq, double *__restrict__ dst) {
+gather_copy_kernel(int64_t count, const T *staged, WaitList w, int nranks,
+                   unsigned long long seq, T *__restrict__ dst) {
     if (threadIdx.x < nranks && w.flag[threadIdx.x]) {
         while (ld_acquire_sys(w.flag[threadIdx.x]) < seq) { __nanosleep(20); }
     }
@@ -67,9 +68,10 @@ gather_copy_kernel(int64_t count, const double *staged, WaitList w, int nranks,
 }
 
 // ---- device helper: pack this rank's boundary values into its halo segment ----------
+template <class T>
 __global__ void __launch_bounds__(kThreads)
-halo_pack_kernel(int64_t count, const int *__restrict__ send_idx, const double *__restrict__ x,
-                 double *__restrict__ segment) {
+halo_pack_kernel(int64_t count, const int *__restrict__ send_idx, const T *__restrict__ x,
+                 T *__restrict__ segment) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < count) segment[i] = x[send_idx[i]];
 }

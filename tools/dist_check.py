@@ -114,6 +114,33 @@ def main():
                 ctx.close()
                 if world > 1:
                     dist.barrier()
+    # mixed precision (FP32 hierarchy under the FP64 Krylov solver) on the partitioned context:
+    # against the reference's own mixed run (known_answers.json "mixed": iterations +-1, FP32-sized
+    # solution tolerance, true FP64 residual)
+    mixed = json.load(open(os.path.join(ROOT, "tests", "golden", "known_answers.json")))["mixed"]
+    for n in sizes:
+        ptr, col, val, rhs = ab.poisson3d(n)
+        for relax, krylov in (("damped_jacobi", "cg"), ("spai0", "bicgstab")):
+            case = [c for c in mixed if (c["n"], c["relax"], c["krylov"]) == (n, relax, krylov)]
+            if not case or world == 1:
+                continue
+            ctx = make_ctx(2000, 1)
+            S = ab.DropinSolver(ptr, col, val, relax, krylov, ctx=ctx, precision="mixed")
+            x, it, res = S.solve(rhs)
+            import oracle
+            r = rhs - oracle.c().spmv(1.0, (ptr, col, val), x, 0.0, np.zeros_like(x))
+            c = case[0]
+            rec = {"n": n, "world": world, "precision": "mixed", "relax": relax, "krylov": krylov,
+                   "iters": it, "ref_iters": c["iters"], "resid": res,
+                   "x_norm_rel_diff": abs(np.linalg.norm(x) - c["x_norm2"]) / c["x_norm2"],
+                   "true_resid": float(np.linalg.norm(r) / np.linalg.norm(rhs))}
+            rec["ok"] = bool(abs(it - c["iters"]) <= 1 and rec["x_norm_rel_diff"] < 1e-6 and rec["true_resid"] < 2e-8)
+            ok = ok and rec["ok"]
+            if rank == 0:
+                print(json.dumps(rec), flush=True)
+            S.close()
+            ctx.close()
+            dist.barrier()
     if rank == 0:
         print("DIST_CHECK", "PASS" if ok else "FAIL", flush=True)
     if world > 1:
