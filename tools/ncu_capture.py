@@ -37,10 +37,13 @@ if len(ends) < 3:
     sys.exit(1)
 skip, count = ends[0] + 1, ends[1] - ends[0]
 print("launches:", len(data), "iteration = launches", skip, "..", skip + count - 1)
+# the report itself stays on the box (hundreds of MB with --set full + sources; gpurun_out/ is
+# capped at 64 MiB): only the raw metric table travels
+rep = os.path.join("/tmp", os.path.basename(out) + "_iter")
 subprocess.run(["ncu", "--set", "full", "--clock-control", "none", "--import-source", "on",
-                "-s", str(skip), "-c", str(count), "-f", "-o", out + "_iter"] + target, check=False,
+                "-s", str(skip), "-c", str(count), "-f", "-o", rep] + target, check=False,
                stdout=subprocess.DEVNULL)
-raw = subprocess.run(["ncu", "-i", out + "_iter.ncu-rep", "--page", "raw", "--csv"], stdout=subprocess.PIPE,
+raw = subprocess.run(["ncu", "-i", rep + ".ncu-rep", "--page", "raw", "--csv"], stdout=subprocess.PIPE,
                      stderr=subprocess.DEVNULL, text=True).stdout
 open(out + "_iter_raw.csv", "w").write(raw)
 print("raw csv bytes:", len(raw))
