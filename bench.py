@@ -206,6 +206,10 @@ def pick_threads(ref, step):
     cands = sorted({c for c in (logical, cores, cores // sockets, max(1, cores // (2 * sockets)),
                                 max(1, cores // (4 * sockets)), limit)
                     if c and c >= 1}, reverse=True)
+    if limit:
+        # a CPU quota far below the thread count only produces spinning threads (measured: 128
+        # bound threads on a 16-CPU quota are 17x slower than 16): do not waste minutes on them
+        cands = [c for c in cands if c <= 4 * limit] or [limit]
     best, best_t, seen = cands[0], None, {}
     for c in cands:
         ref.set_threads(c)
