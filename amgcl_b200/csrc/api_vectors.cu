@@ -92,6 +92,10 @@ extern "C" int b200_vec_wrap(b200_ctx_t ctx, double *device_ptr, size_t n, b200_
 
 extern "C" int b200_vec_destroy(b200_vec_t v) {
     if (!v) return B200_OK;
+    if (v->ctx->lazy_vec == v) {            // a pending first sweep nobody will ever read
+        v->ctx->lazy_vec = nullptr;
+        v->scale_pending = false;
+    }
     if (b200_graph_s *g = v->ctx->recording) {
         // Typically a garbage-collected handle of the host language that has nothing to do with
         // the recording: its storage is released once the recording is over (cudaFree would

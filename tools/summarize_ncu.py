@@ -49,17 +49,18 @@ def launch_shares(tag, path):
         a[1] += t
         tot += t
     out = ["# %s: ncu launch list (gpu__time_duration.sum, --clock-control none)" % tag, "",
-           "Command: `ncu --metrics gpu__time_duration.sum --clock-control none -s 900 -c 400 --csv "
-           "python tools/profile_target.py 256 1` (setup launches skipped; %d launches of the first "
-           "solve captured, %.2f ms of kernel time).  Per-launch times under ncu are cold-cache and "
-           "serialised: compare SHARES." % (len(data), tot / 1e6), "",
+           "Command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv "
+           "python tools/profile_target.py <n> 1 ...` (pass 1 of tools/ncu_capture.py: every launch "
+           "of the process, coarse-solver set-up included; %d launches, %.2f ms of kernel time).  "
+           "Per-launch times under ncu are cold-cache and serialised: compare SHARES." % (len(data), tot / 1e6), "",
            "Template arguments of csr_ring_kernel<MODE, L>: MODE 0 spmv(beta=0), 1 spmv(beta!=0), "
-           "2 residual, 3 fused relax; L = lanes per row (L=1 is the finest level A and P).", "",
+           "2 residual, 3 fused relax, 4 residual fused with the smoother's first sweep; L = lanes "
+           "per row (L=1 is the finest level A and P).", "",
            "| kernel | launches | total us | share | avg us |", "|---|---:|---:|---:|---:|"]
     for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         out.append("| `%s` | %d | %.1f | %.1f%% | %.2f |" % (k, n, t / 1e3, 100 * t / tot, t / n / 1e3))
-    finest = sum(t for k, (n, t) in agg.items() if re.match(r"csr_ring_kernel<[023], 1>", k))
-    out += ["", "Finest-level A passes (`csr_ring_kernel<0|2|3, 1>`): %.1f%% of the captured kernel time."
+    finest = sum(t for k, (n, t) in agg.items() if re.match(r"csr_ring_kernel<[0234], 1>", k))
+    out += ["", "Finest-level A passes (`csr_ring_kernel<0|2|3|4, 1>`): %.1f%% of the captured kernel time."
             % (100 * finest / tot)]
     open(os.path.join(PROF, tag + "_launch_shares.md"), "w").write("\n".join(out) + "\n")
     shutil.copy(path, os.path.join(PROF, tag + "_launches.csv"))
