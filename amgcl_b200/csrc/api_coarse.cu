@@ -149,15 +149,11 @@ extern "C" int b200_coarse_create_i32(b200_ctx_t ctx, int64_t n, const int32_t *
 extern "C" int b200_coarse_create_i64_f32(b200_ctx_t ctx, int64_t n, const int64_t *ptr,
                                           const int64_t *col, const float *val, b200_coarse_t *S) {
     CHECK_CTX(ctx);
-    B200_REQUIRE(!ctx->dist || n < ctx->dist_min_rows,
-                 "b200_coarse_create_*_f32: a PARTITIONED coarsest level needs an FP64 hierarchy");
     return coarse_create(ctx, n, ptr, col, val, S);
 }
 extern "C" int b200_coarse_create_i32_f32(b200_ctx_t ctx, int64_t n, const int32_t *ptr,
                                           const int32_t *col, const float *val, b200_coarse_t *S) {
     CHECK_CTX(ctx);
-    B200_REQUIRE(!ctx->dist || n < ctx->dist_min_rows,
-                 "b200_coarse_create_*_f32: a PARTITIONED coarsest level needs an FP64 hierarchy");
     return coarse_create(ctx, n, ptr, col, val, S);
 }
 
@@ -195,12 +191,20 @@ extern "C" int b200_coarse_solve(b200_ctx_t ctx, b200_coarse_t S, b200_vec_t rhs
         int rc = materialize(rhs);
         if (rc) return rc;
         if ((rc = tail_flush(ctx))) return rc;
-        B200_NCCL(nccl().AllGather(rhs->ptr, S->gbuf, (size_t)S->block, ncclDouble, comm_of(ctx), ctx->stream));
+        if (rhs->dtype != x->dtype) return B200_BAD_MIX("coarse solve");
+        const bool f32 = rhs->dtype == B200_F32;
+        B200_NCCL(nccl().AllGather(rhs->ptr, S->gbuf, (size_t)S->block, f32 ? ncclFloat : ncclDouble,
+                                   comm_of(ctx), ctx->stream));
         const int nloc = (int)x->len;
         if (nloc) {
             ProfScope prof(ctx, B200_PROF_COARSE, nloc, S->n, (int64_t)nloc * S->n);
-            coarse_gemv_kernel<double><<<(nloc + warps_per_cta - 1) / warps_per_cta, kThreads, 0, ctx->stream>>>(
-                N, (int)x->off, nloc, S->Ainv, S->gbuf, wr(x));
+            const unsigned grid = (unsigned)((nloc + warps_per_cta - 1) / warps_per_cta);
+            if (f32)
+                coarse_gemv_kernel<float><<<grid, kThreads, 0, ctx->stream>>>(
+                    N, (int)x->off, nloc, S->Ainv, tp<float>(S->gbuf), tp<float>(wr(x)));
+            else
+                coarse_gemv_kernel<double><<<grid, kThreads, 0, ctx->stream>>>(
+                    N, (int)x->off, nloc, S->Ainv, S->gbuf, wr(x));
             B200_CHECK_LAUNCH();
             ctx->launches++;
         }
