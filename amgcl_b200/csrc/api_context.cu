@@ -121,10 +121,10 @@ extern "C" int b200_ctx_destroy(b200_ctx_t ctx) {
     if (ctx->dot_dev) cudaFree(ctx->dot_dev);
     if (ctx->push_ticket) cudaFree(ctx->push_ticket);
     if (ctx->ipc_dev) cudaFree(ctx->ipc_dev);
-    if (ctx->dot_pb_local) {
+    if (ctx->probe_pb_local) {
         for (int q = 0; q < ctx->nranks; ++q)
-            if (q != ctx->rank && ctx->dot_pb_peer[q]) cudaIpcCloseMemHandle(ctx->dot_pb_peer[q]);
-        cudaFree(ctx->dot_pb_local);
+            if (q != ctx->rank && ctx->probe_pb_peer[q]) cudaIpcCloseMemHandle(ctx->probe_pb_peer[q]);
+        cudaFree(ctx->probe_pb_local);
     }
     for (void *ptr : ctx->deferred_free) cudaFree(ptr);
     if (ctx->comm && nccl().handle) nccl().CommDestroy(comm_of(ctx));

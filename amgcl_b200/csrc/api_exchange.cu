@@ -48,7 +48,7 @@ extern "C" int b200_dist_init(b200_ctx_t ctx, const char *id, size_t size, int n
     ctx->p2p = false;
     if (ctx->opt_p2p && nranks > 1 && nranks <= kMaxRanks) {
         // (peer_alloc agrees on success collectively: either every rank mapped every peer or none did)
-        ctx->p2p = peer_alloc(ctx, kFlagBytes + 2 * 256, &ctx->dot_pb_local, ctx->dot_pb_peer) == B200_OK;
+        ctx->p2p = peer_alloc(ctx, kFlagBytes + 2 * 256, &ctx->probe_pb_local, ctx->probe_pb_peer) == B200_OK;
         if (!ctx->p2p) cudaGetLastError();
     }
     if (ctx->p2p) {

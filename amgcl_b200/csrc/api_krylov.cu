@@ -238,11 +238,6 @@ extern "C" int b200_dot(b200_ctx_t ctx, b200_vec_t x, b200_vec_t y, double *resu
     B200_REQUIRE(same_layout(x, y), "dot: size mismatch");
     if (x->dtype != y->dtype) return B200_BAD_MIX("dot");
     GUARD(ctx);
-    if (x->kind == B200_VK_GHOST) {                 // lives on rank 0; nothing to contribute here
-        B200_CUDA(cudaStreamSynchronize(ctx->stream));
-        *result = 0.0;
-        return B200_OK;
-    }
     const bool dist = x->kind == B200_VK_DIST;
     if (!dist && (x->len == 0 || x->zero_pending || y->zero_pending)) {
         B200_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -307,7 +302,6 @@ static bool krylov_vec_ok(b200_krylov_t K, std::initializer_list<b200_vec_t> vs)
     b200_vec_t first = *vs.begin();
     for (b200_vec_t v : vs) {
         if (!v || v->dtype != B200_F64 || v->n != K->n || !same_layout(v, first)) return false;
-        if (v->kind == B200_VK_GHOST) return false;
     }
     return true;
 }

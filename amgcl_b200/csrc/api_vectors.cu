@@ -179,7 +179,6 @@ extern "C" int b200_vec_upload(b200_vec_t v, const double *host, size_t n) {
     B200_REQUIRE(n == v->n, "size mismatch in vector upload");
     B200_REQUIRE(v->dtype == B200_F64, "b200_vec_upload: FP64 vector expected (use _f32)");
     GUARD(v->ctx);
-    if (v->kind == B200_VK_GHOST) return B200_OK;
     if (v->len) {
         // distributed: every rank is handed the full host vector and keeps its block
         B200_CUDA(cudaMemcpyAsync(wr(v), host + v->off, v->len * sizeof(double),
@@ -198,10 +197,6 @@ extern "C" int b200_vec_download(b200_vec_t v, double *host, size_t n) {
     b200_ctx_t ctx = v->ctx;
     GUARD(ctx);
     if (!n) return B200_OK;
-    if (v->kind == B200_VK_GHOST) {          // lives on rank 0 only
-        memset(host, 0, n * sizeof(double));
-        return B200_OK;
-    }
     if (v->kind == B200_VK_DIST) {
         // every rank receives the complete vector: all-gather the blocks, then one D2H copy
         int rc = materialize(v);
@@ -317,7 +312,7 @@ extern "C" int b200_copy(b200_ctx_t ctx, b200_vec_t x, b200_vec_t y) {
     B200_REQUIRE(x && y, "null argument");
     touch(ctx, {x, y});
     B200_REQUIRE(same_layout(x, y), "copy: size mismatch");
-    if (x->kind == B200_VK_GHOST || x == y || x->ptr == y->ptr) return B200_OK;
+    if (x == y || x->ptr == y->ptr) return B200_OK;
     if (x->zero_pending) {
         y->zero_pending = true;
         return B200_OK;
@@ -426,7 +421,6 @@ extern "C" int b200_axpby(b200_ctx_t ctx, double a, b200_vec_t x, double b, b200
     B200_REQUIRE(x && y, "null argument");
     touch(ctx, {x, y});
     B200_REQUIRE(same_layout(x, y), "axpby: size mismatch");
-    if (x->kind == B200_VK_GHOST) return B200_OK;
     GUARD(ctx);
     if (all64({x, y})) return axpby_t<double>(ctx, a, x, b, y);
     if (all32({x, y})) return axpby_t<float>(ctx, a, x, b, y);
@@ -439,7 +433,6 @@ extern "C" int b200_axpbypcz(b200_ctx_t ctx, double a, b200_vec_t x, double b, b
     B200_REQUIRE(x && y && z, "null argument");
     touch(ctx, {x, y, z});
     B200_REQUIRE(same_layout(x, y) && same_layout(x, z), "axpbypcz: size mismatch");
-    if (x->kind == B200_VK_GHOST) return B200_OK;
     GUARD(ctx);
     if (all64({x, y, z})) return axpbypcz_t<double>(ctx, a, x, b, y, c, z);
     if (all32({x, y, z})) return axpbypcz_t<float>(ctx, a, x, b, y, c, z);
@@ -452,7 +445,6 @@ extern "C" int b200_vmul(b200_ctx_t ctx, double alpha, b200_vec_t x, b200_vec_t 
     B200_REQUIRE(x && y && z, "null argument");
     touch(ctx, {x, y, z});
     B200_REQUIRE(same_layout(x, y) && same_layout(x, z), "vmul: size mismatch");
-    if (x->kind == B200_VK_GHOST) return B200_OK;
     GUARD(ctx);
     if (all64({x, y, z})) return vmul_t<double>(ctx, alpha, x, y, beta, z);
     if (all32({x, y, z})) return vmul_t<float>(ctx, alpha, x, y, beta, z);

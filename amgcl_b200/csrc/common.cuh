@@ -136,9 +136,8 @@ struct b200_ctx_s {
     unsigned int *push_ticket = nullptr;    // device, self-resetting
     unsigned int *gather_ticket = nullptr;  // device, self-resetting (row-share gathers)
     void    *ipc_dev       = nullptr;       // device staging for IPC handle exchange
-    void    *dot_pb_local  = nullptr;       // [flags | 2 x 16 doubles] shared with the peers
-    void    *dot_pb_peer[16] = {};
-    unsigned long long dot_seq = 0;
+    void    *probe_pb_local = nullptr;      // small peer-mapped allocation that proves CUDA IPC works
+    void    *probe_pb_peer[16] = {};
     std::vector<void *> deferred_free;      // IPC-exported allocations, freed with the context
 
     // tuning
@@ -169,7 +168,9 @@ struct b200_ctx_s {
     uint64_t     option_epoch  = 0;       // bumped by b200_ctx_set_option / set_stream
 };
 
-enum { B200_VK_LOCAL = 0, B200_VK_DIST = 1, B200_VK_GHOST = 2 };
+// LOCAL: the whole vector lives on this GPU (single GPU, or a replicated level of a multi-GPU
+// context); DIST: this rank's block of a partitioned vector
+enum { B200_VK_LOCAL = 0, B200_VK_DIST = 1 };
 
 struct b200_vec_s {
     b200_ctx_t ctx   = nullptr;
@@ -264,7 +265,6 @@ struct b200_index_s {
 struct b200_coarse_s {
     b200_ctx_t ctx  = nullptr;
     int        dtype = B200_F64;  // element type of the vectors it is applied to
-    bool       ghost = false;     // multi-GPU: the coarsest level lives on rank 0
     bool       replicated = false;// multi-GPU: coarsest level partitioned -> inverse on every rank
     double    *gbuf = nullptr;    // replicated: all-gathered right-hand side [nranks * block]
     int64_t    block = 0;

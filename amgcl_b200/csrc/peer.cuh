@@ -33,11 +33,6 @@ namespace b200 {
 
 // (kMaxRanks, kFlagStride, kFlagBytes: common.cuh)
 
-struct PeerTargets {
-    double             *data[kMaxRanks];   // where my contribution goes in peer q (nullptr: skip)
-    unsigned long long *flag[kMaxRanks];   // flag to release in peer q           (nullptr: skip)
-};
-
 struct WaitList {
     const unsigned long long *flag[kMaxRanks];   // local flags to wait on (nullptr: skip)
 };

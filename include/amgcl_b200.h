@@ -123,33 +123,37 @@ int b200_profile_end(b200_ctx_t ctx, b200_profile_entry *out, int64_t capacity, 
 
 /* One process per GPU (SPMD): every rank runs the same AMGCL program on the same
  * host hierarchy; after b200_dist_init every vector / matrix dimension >=
- * dist_min_rows is partitioned in uniform contiguous row blocks across the ranks,
- * everything smaller lives on rank 0 (other ranks get no-op ghost handles).
+ * dist_min_rows is partitioned in uniform contiguous row blocks across the ranks and
+ * everything smaller is replicated (every rank holds and computes it, as mpi::amg
+ * consolidates small levels, amgcl/mpi/amg.hpp:430-465).  A rank keeps WHOLE ROWS of every
+ * operator, so each row sum is formed on one GPU in the reference's order.
  * Replaces amgcl::mpi::distributed_matrix / comm_pattern / mpi::inner_product
- * (amgcl/mpi/distributed_matrix.hpp:51-557, amgcl/mpi/inner_product.hpp:53-62)
- * with NCCL collectives on device buffers:
- *   A_l x        halo = one in-place ncclAllGather of packed boundary values
- *   P_l u        ncclAllGather / ncclBroadcast of the coarse vector, local rows
- *   R_l t        local columns, ncclReduceScatter / ncclReduce of partial sums
- *   <x, y>       local kernel + ncclAllReduce of one double
- * With dist_min_rows = rows of the finest matrix only the finest level is
- * partitioned (the north-star configuration).  The id comes from
- * b200_nccl_unique_id on rank 0 and is distributed by the caller (e.g. with
+ * (amgcl/mpi/distributed_matrix.hpp:51-557, amgcl/mpi/inner_product.hpp:53-62):
+ *   operator with partitioned input   local columns + halo slots; the halo (every rank's
+ *                                     packed boundary values) is pushed into the peers'
+ *                                     buffers and awaited INSIDE the consumer kernel
+ *   replicated result, partitioned input   each rank computes a share of the rows and stores
+ *                                     them into every rank's gather buffer
+ *   <x, y>                            reduced and all-reduced inside the producing kernel
+ * over CUDA-IPC mapped peer memory (NVLink); with option "p2p" = 0 the same exchanges run
+ * as a pack kernel + ncclAllGather / ncclAllReduce.  With dist_min_rows = rows of the
+ * finest matrix only the finest level is partitioned (the north-star configuration).  The
+ * id comes from b200_nccl_unique_id on rank 0 and is distributed by the caller (e.g. with
  * torch.distributed). */
 int b200_nccl_unique_id(char *id, size_t size /* >= 128 */);
 int b200_dist_init(b200_ctx_t ctx, const char *id, size_t size, int nranks, int rank,
                    int64_t dist_min_rows);
-/* p2p: 1 if the exchanges run through CUDA-IPC mapped peer memory with our own push /
- * wait / reduce kernels over NVLink (default when every rank could map its peers; option
- * "p2p" = 0 before b200_dist_init forces the NCCL collectives), 0 for NCCL. */
+/* p2p: 1 if the exchanges run through CUDA-IPC mapped peer memory inside our own kernels
+ * (default when every rank could map its peers; option "p2p" = 0 before b200_dist_init
+ * forces the NCCL collectives), 0 for NCCL. */
 int b200_dist_info(b200_ctx_t ctx, int *rank, int *nranks, int64_t *dist_min_rows, int *p2p);
 
 /* Pure host helpers (no device, no NCCL) exposing the partition logic to tests.
  * b200_partition: uniform block size and this rank's [lo, hi) for a dimension.
- * b200_dist_split_i64: rank's share of an operator; kind 1 = square (columns
- * remapped to [local | halo slots]), 2 = prolongation (own rows), 3 = restriction
- * (own columns).  slots = halo slots per rank, send_idx = local indices this rank
- * contributes to the all-gathered halo, in slot order. */
+ * b200_dist_split_i64: rank's share of an operator = the rows of its block; kind 1: the
+ * vector the operator is applied to is partitioned (columns remapped to [local | halo
+ * slots]), kind 2: it is replicated (columns untouched).  slots = halo slots per rank,
+ * send_idx = local indices this rank contributes to the all-gathered halo, in slot order. */
 int b200_partition(int64_t n, int nranks, int rank, int64_t *block, int64_t *lo, int64_t *hi);
 int b200_dist_split_i64(int kind, int nranks, int rank, int64_t nrows, int64_t ncols,
                         const int64_t *ptr, const int64_t *col, const double *val,
