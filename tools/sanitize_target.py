@@ -45,4 +45,26 @@ for relax, krylov, prec, graph in (("spai0", "bicgstab", "f64", True), ("damped_
         x, it, res = S.solve(rhs)
     print(relax, krylov, prec, "graph" if graph else "", it, res, S.graph_stats())
     S.close()
+# round 2: the coarse tail as one cooperative kernel, the reference's Krylov sequence on the same
+# backend (fused_krylov = 0), and the stand-alone Krylov steps
+for opt, val_ in (("coarse_tail", 1), ("fused_krylov", 0), ("fuse_first_sweep", 0)):
+    ctx.set_option(opt, val_)
+    S = ab.DropinSolver(ptr, col, val, "damped_jacobi", "cg", coarse_enough=200, ctx=ctx)
+    x, it, res = S.solve(rhs)
+    print(opt, val_, it, res, ctx.tail_stats())
+    S.close()
+    ctx.set_option(opt, 1 - val_)
+n = ptr.size - 1
+A = ctx.csr(n, n, ptr, col, val)
+K = ab.Krylov(ctx, n)
+vs = [ctx.vector(rng.uniform(-1, 1, n)) for _ in range(8)]
+K.residual(vs[0], A, vs[1], vs[2])
+K.cg_direction(vs[2], vs[3], vs[4])
+K.cg_step(A, vs[4], vs[5], vs[1], vs[2])
+K.bicg_start(vs[2], vs[6])
+K.bicg_direction(vs[2], vs[5], vs[4])
+K.bicg_step_s(A, vs[6], vs[3], vs[5], vs[2], vs[7], vs[1])
+K.bicg_step_r(A, vs[6], vs[3], vs[0], vs[7], vs[2], vs[1])
+print("krylov steps", K.scalars())
+K.close()
 print("SANITIZE_TARGET_DONE")
