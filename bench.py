@@ -584,9 +584,13 @@ def main_arm(args, rank, world, local_rank):
                 parallelism="single GPU" if world == 1 else
                 "one system row-partitioned over %d GPUs (levels with >= %d rows; exchange: %s)" % (
                     world, dist_min_rows, transport),
-                extra={"cycle_graph": {"on": bool(args.graph) and world == 1,
-                                       "graphs_kernels_replays": list(S.graph_stats())},
-                       "fused_krylov": bool(ctx.get_option("fused_krylov"))}),
+                ),
+            "options": {"cycle_graph": {"on": bool(args.graph) and world == 1,
+                                        "graphs_kernels_replays": list(S.graph_stats())},
+                        "fused_krylov": bool(ctx.get_option("fused_krylov")),
+                        "fuse_first_sweep": bool(ctx.get_option("fuse_first_sweep")),
+                        "coarse_tail": bool(ctx.get_option("coarse_tail")),
+                        "partition_min_rows": dist_min_rows if world > 1 else None},
             "solve_s": solve_s, "iters": iters, "resid": res,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "roofline": roof, "csr_kernel_share_of_step": all_csr_ms / (args.steps * solve_s * 1e3),
