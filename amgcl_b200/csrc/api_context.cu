@@ -85,6 +85,7 @@ extern "C" int b200_ctx_create(int device, b200_ctx_t *out) {
     if (const char *e = getenv("B200_FUSE_FIRST_SWEEP")) ctx->opt_fuse_first_sweep = atoi(e) ? 1 : 0;
     if (const char *e = getenv("B200_POLL_SCALARS")) ctx->opt_poll_scalars = atoi(e) ? 1 : 0;
     if (const char *e = getenv("B200_WARM_LINES")) ctx->opt_warm_lines = atoi(e);
+    if (const char *e = getenv("B200_SMALL_KERNEL_MAX_NNZ")) ctx->opt_small_kernel_max_nnz = atoll(e);
     // any failure below releases what was created so far (b200_ctx_destroy null-checks every member)
     const int rc = ctx_init(ctx, device);
     if (rc != B200_OK) {
@@ -265,6 +266,7 @@ static int64_t *option_slot(b200_ctx_t ctx, const char *key) {
     if (!strcmp(key, "fused_krylov")) return &ctx->opt_fused_krylov;
     if (!strcmp(key, "coarse_tail")) return &ctx->opt_coarse_tail;
     if (!strcmp(key, "poll_scalars")) return &ctx->opt_poll_scalars;
+    if (!strcmp(key, "small_kernel_max_nnz")) return &ctx->opt_small_kernel_max_nnz;
     if (!strcmp(key, "warm_lines")) return &ctx->opt_warm_lines;
     if (!strcmp(key, "fuse_first_sweep")) return &ctx->opt_fuse_first_sweep;
     if (!strcmp(key, "tail_max_nnz")) return &ctx->opt_tail_max_nnz;

@@ -7,6 +7,8 @@
 
 namespace b200 {
 int tail_enqueue_csr(b200_ctx_t ctx, int mode, b200_csr_t A, const CsrArgsT<PrecDD> &a);   // api_tail.cu
+bool small_csr_accepts(b200_ctx_t ctx, b200_csr_t A);
+int small_csr_launch(b200_ctx_t ctx, int mode, b200_csr_t A, const CsrArgsT<PrecDD> &a);
 }
 
 using namespace b200;
@@ -450,6 +452,10 @@ static int launch_csr(b200_ctx_t ctx, b200_csr_t A, const CsrArgsT<P> &args) {
         const int trc = tail_flush(ctx);          // immediate launch: what was deferred goes first
         if (trc) return trc;
     }
+    // a small FP64 operator: the direct-load kernel (same arithmetic) instead of the ring pipeline
+    if (std::is_same<P, PrecDD>::value && MODE != MODE_RESID_SCALED && !args.ndot && !args.xh &&
+        !args.gather_on && small_csr_accepts(ctx, A))
+        return small_csr_launch(ctx, MODE, A, *reinterpret_cast<const CsrArgsT<PrecDD> *>(&args));
     if (ctx->recording) A->in_graph = true;
     ProfScope prof(ctx, MODE, A->nrows, A->ncols, A->nnz);
     switch (A->lanes) {

@@ -88,6 +88,39 @@ static int tail_push(b200_ctx_t ctx, const TailCmd &c) {
     return B200_OK;
 }
 
+// One small FP64 operator as one plain launch of the direct-load kernel (option
+// "small_kernel_max_nnz"; modes 0-3).  Same arithmetic as the ring kernel.
+bool small_csr_accepts(b200_ctx_t ctx, b200_csr_t A) {
+    return ctx->opt_small_kernel_max_nnz > 0 && A->dtype == B200_F64 && A->kind == B200_CK_LOCAL &&
+           !A->gather_rows && A->nlong == 0 && A->nrows > 0 && A->nnz <= ctx->opt_small_kernel_max_nnz;
+}
+
+int small_csr_launch(b200_ctx_t ctx, int mode, b200_csr_t A, const CsrArgsT<PrecDD> &a) {
+    TailCmd c;
+    memset(&c, 0, sizeof(c));
+    c.op = TAIL_CSR; c.mode = mode; c.nrows = (int)A->nrows; c.lanes = A->lanes;
+    c.ptr = A->ptr; c.col = A->col; c.val = static_cast<const double *>(A->val);
+    c.x = a.x; c.f = a.f; c.d = a.d; c.y = a.y;
+    c.alpha = a.alpha; c.beta = a.beta;
+    const int64_t want = ((int64_t)A->nrows * A->lanes + kThreads - 1) / kThreads;
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)ctx->sm_count * 8));
+    if (ctx->recording) A->in_graph = true;
+    ProfScope prof(ctx, mode, A->nrows, A->ncols, A->nnz);
+    cudaError_t rc;
+    switch (A->lanes) {
+    case 1:  rc = launch_pdl(ctx, small_csr_kernel<1>, dim3(grid), dim3(kThreads), 0, c); break;
+    case 2:  rc = launch_pdl(ctx, small_csr_kernel<2>, dim3(grid), dim3(kThreads), 0, c); break;
+    case 4:  rc = launch_pdl(ctx, small_csr_kernel<4>, dim3(grid), dim3(kThreads), 0, c); break;
+    case 8:  rc = launch_pdl(ctx, small_csr_kernel<8>, dim3(grid), dim3(kThreads), 0, c); break;
+    case 16: rc = launch_pdl(ctx, small_csr_kernel<16>, dim3(grid), dim3(kThreads), 0, c); break;
+    default: rc = launch_pdl(ctx, small_csr_kernel<32>, dim3(grid), dim3(kThreads), 0, c); break;
+    }
+    B200_CUDA(rc);
+    B200_CHECK_LAUNCH();
+    ctx->launches++;
+    return B200_OK;
+}
+
 int tail_enqueue_csr(b200_ctx_t ctx, int mode, b200_csr_t A, const CsrArgsT<PrecDD> &a) {
     TailCmd c;
     memset(&c, 0, sizeof(c));

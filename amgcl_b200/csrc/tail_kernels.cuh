@@ -77,10 +77,10 @@ __device__ __forceinline__ void tail_prefetch_l1(const void *p) {
 struct TailRow { int beg, end; };      // row pointers of a thread's first row, loaded early
 
 // before the barrier: row pointers of my first row of command c, its first lines into L1
-template <int L>
+template <int L, int THREADS = kTailThreads>
 __device__ __forceinline__ TailRow tail_csr_peek(const TailCmd &c) {
     TailRow t = {0, 0};
-    const int r = (blockIdx.x * kTailThreads + threadIdx.x) / L;
+    const int r = (blockIdx.x * THREADS + threadIdx.x) / L;
     if (r < c.nrows) {
         t.beg = __ldg(c.ptr + r);
         t.end = __ldg(c.ptr + r + 1);
@@ -105,12 +105,12 @@ __device__ __forceinline__ TailRow tail_peek(const TailCmd &c) {
 }
 
 // one CSR pass, L lanes per row: the arithmetic of compute_staged<MODE, L> + store_row<MODE>
-template <int L>
+template <int L, int THREADS = kTailThreads>
 __device__ __forceinline__ void tail_csr(const TailCmd &c, const TailRow &first) {
     constexpr int U = 4;
-    const int gid     = (blockIdx.x * kTailThreads + threadIdx.x) / L;
+    const int gid     = (blockIdx.x * THREADS + threadIdx.x) / L;
     const int lane    = threadIdx.x % L;
-    const int ngroups = gridDim.x * kTailThreads / L;
+    const int ngroups = gridDim.x * THREADS / L;
     for (int base = 0; base < c.nrows; base += ngroups) {
         const int  r     = base + gid;
         const bool valid = r < c.nrows;
@@ -161,6 +161,19 @@ __device__ __forceinline__ void tail_csr(const TailCmd &c, const TailRow &first)
             c.y[r] = out;
         }
     }
+}
+
+// ---- one small operator, one plain launch --------------------------------------------------
+// The streaming ring kernel (csr_kernels.cuh) pays for its pipeline -- mbarrier set-up, bulk
+// copies, shared-memory staging -- even when the whole operator is a few hundred kilobytes; on
+// such operators the direct-load row reduction above (same arithmetic, bit for bit) finishes
+// in the time a dependent launch takes anyway.  One row group per L lanes, rows strided over
+// the grid.
+template <int L>
+__global__ void __launch_bounds__(kThreads) small_csr_kernel(const TailCmd c) {
+    const TailRow first = tail_csr_peek<L, kThreads>(c);     // matrix data: before the dependency
+    ptx::pdl_wait();
+    tail_csr<L, kThreads>(c, first);
 }
 
 __global__ void __launch_bounds__(kTailThreads, 1) coarse_tail_kernel(const TailArgs a) {

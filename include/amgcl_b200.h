@@ -187,6 +187,10 @@ int b200_split_destroy(b200_split_t sp);
  *                      is ONE pass over A: x = (omega*diag).*rhs is formed on the fly, written,
  *                      and r = rhs - A x with it (default; operators with short rows and tiny
  *                      levels only); 0 = two kernels.  Results are bit-identical.
+ *   "small_kernel_max_nnz"  FP64 operators with at most this many non-zeros (default 10^6) are
+ *                      applied by a direct-load kernel instead of the TMA ring pipeline, whose
+ *                      set-up costs more than such an operator's whole pass; same arithmetic,
+ *                      bit-identical results; 0 = always the ring kernel
  *   "poll_scalars"     1 = a host-synchronous result of an in-kernel reduction (b200_dot, the
  *                      Krylov steps) is awaited by polling the mapped host word the finishing CTA
  *                      releases (default), 0 = by cudaStreamSynchronize

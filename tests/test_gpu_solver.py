@@ -235,6 +235,28 @@ def test_first_sweep_fusion_is_bit_transparent(ctx, relax, krylov):
     assert l0 - l1 >= cycles                     # at least the finest level, every cycle
 
 
+@pytest.mark.parametrize("relax,krylov,n", [("damped_jacobi", "cg", 32), ("spai0", "bicgstab", 48)])
+def test_small_operator_kernel_is_bit_transparent(ctx, relax, krylov, n):
+    """Option "small_kernel_max_nnz": operators below the threshold are applied by the
+    direct-load kernel instead of the TMA ring pipeline -- same lanes per row, same entry
+    order, same shuffle tree, same epilogue: the same bits."""
+    ptr, col, val, rhs = ab.poisson3d(n)
+    rng = np.random.default_rng(15)
+    f = rng.uniform(-1, 1, rhs.size)
+    out = {}
+    try:
+        for cap in (0, 1000000):
+            ctx.set_option("small_kernel_max_nnz", cap)
+            S = ab.DropinSolver(ptr, col, val, relax, krylov, ctx=ctx)
+            x, it, res = S.solve(rhs)
+            out[cap] = (x, it, res, S.apply_precond(f))
+            S.close()
+    finally:
+        ctx.set_option("small_kernel_max_nnz", 1000000)
+    (x0, it0, r0, m0), (x1, it1, r1, m1) = out[0], out[1000000]
+    assert (it1, r1) == (it0, r0) and np.array_equal(x1, x0) and np.array_equal(m1, m0)
+
+
 def test_pending_first_sweep_is_materialised_by_any_other_reader(ctx):
     ptr, col, val, _ = ab.poisson3d(10)
     n = ptr.size - 1
