@@ -159,7 +159,8 @@ struct b200_ctx_s {
     int64_t opt_poll_scalars  = 1;        // host reads in-kernel reduction results by polling mapped memory
     int64_t opt_warm_lines    = 0;        // gather-heavy operators: touch a block's lines of x before reducing it
                                           // (opt-in experiment: measured no gain)
-    int64_t opt_small_kernel_max_nnz = 1000000;   // FP64 operators up to this size: direct-load kernel
+    int64_t opt_small_kernel_max_nnz = 0;         // FP64 operators up to this size: direct-load kernel
+                                                  // (opt-in: measured slower than the ring kernel)
     int64_t opt_fused_krylov  = 1;        // the C++ binding's cg / bicgstab use the fused b200_cg_* / b200_bicg_* steps
 
     // CUDA-graph recording of a call sequence (b200_graph_*)

@@ -187,10 +187,11 @@ int b200_split_destroy(b200_split_t sp);
  *                      is ONE pass over A: x = (omega*diag).*rhs is formed on the fly, written,
  *                      and r = rhs - A x with it (default; operators with short rows and tiny
  *                      levels only); 0 = two kernels.  Results are bit-identical.
- *   "small_kernel_max_nnz"  FP64 operators with at most this many non-zeros (default 10^6) are
- *                      applied by a direct-load kernel instead of the TMA ring pipeline, whose
- *                      set-up costs more than such an operator's whole pass; same arithmetic,
- *                      bit-identical results; 0 = always the ring kernel
+ *   "small_kernel_max_nnz"  FP64 operators with at most this many non-zeros are applied by a
+ *                      direct-load kernel instead of the TMA ring pipeline; same arithmetic,
+ *                      bit-identical results.  Default 0 = always the ring kernel: measured, the
+ *                      ring kernel wins even on tiny operators because its first bulk copies
+ *                      are issued before the grid dependency resolves (64^3: 1.40 vs 1.60 ms)
  *   "poll_scalars"     1 = a host-synchronous result of an in-kernel reduction (b200_dot, the
  *                      Krylov steps) is awaited by polling the mapped host word the finishing CTA
  *                      releases (default), 0 = by cudaStreamSynchronize

@@ -252,7 +252,7 @@ def test_small_operator_kernel_is_bit_transparent(ctx, relax, krylov, n):
             out[cap] = (x, it, res, S.apply_precond(f))
             S.close()
     finally:
-        ctx.set_option("small_kernel_max_nnz", 1000000)
+        ctx.set_option("small_kernel_max_nnz", 0)
     (x0, it0, r0, m0), (x1, it1, r1, m1) = out[0], out[1000000]
     assert (it1, r1) == (it0, r0) and np.array_equal(x1, x0) and np.array_equal(m1, m0)
 
