@@ -96,6 +96,8 @@ extern "C" int b200_vec_destroy(b200_vec_t v) {
         v->ctx->lazy_vec = nullptr;
         v->scale_pending = false;
     }
+    for (b200_ctx_s::Product &p : v->ctx->products)      // products that name this vector are gone
+        if (p.a == v || p.b == v) p = b200_ctx_s::Product();
     if (b200_graph_s *g = v->ctx->recording) {
         // Typically a garbage-collected handle of the host language that has nothing to do with
         // the recording: its storage is released once the recording is over (cudaFree would
