@@ -132,6 +132,9 @@ def lib():
         "b200_split_destroy": [_vp],
         "b200_plan_i64": [_i64, _vp, _c.c_int, _c.c_int, _vp, _i64, _P(_i64), _P(_c.c_int),
                           _P(_c.c_int), _P(_i64)],
+        "b200_csr_window": [_vp, _P(_c.c_int), _P(_c.c_int), _P(_c.c_int), _P(_i64)],
+        "b200_window_plan_i64": [_i64, _i64, _vp, _vp, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _vp, _vp, _i64,
+                                 _vp, _i64, _P(_i64), _P(_i64), _P(_c.c_int), _P(_c.c_int), _P(_c.c_int)],
         "b200_index_create_i64": [_vp, _vp, _c.c_size_t, _c.c_size_t, _P(_vp)],
         "b200_index_destroy": [_vp],
         "b200_index_size": [_vp, _P(_c.c_size_t)],
@@ -519,12 +522,44 @@ class Csr:
         _check(lib().b200_csr_bytes(self.h, _c.byref(b)))
         return b.value
 
+    def window(self):
+        """Windowed storage of this operator (include/amgcl_b200.h: b200_csr_window)."""
+        w, ms, mr, tot = _c.c_int(), _c.c_int(), _c.c_int(), _i64()
+        _check(lib().b200_csr_window(self.h, _c.byref(w), _c.byref(ms), _c.byref(mr), _c.byref(tot)))
+        return {"windowed": bool(w.value), "max_slots": ms.value, "max_runs": mr.value, "total_slots": tot.value}
+
     def __del__(self):
         try:
             if self.h and lib().b200_csr_destroy(self.h) == 0:
                 self.h = _vp()      # (kept if the library refused, e.g. while a graph is recorded)
         except Exception:
             pass
+
+
+def window_plan(nrows, ncols, ptr, col, lanes=0, nnz_cap=2048, slot_cap=1400, max_ratio=75, gap=2):
+    """Host-only: the row-block plan and the windowed format b200_csr_create would build
+    (b200_window_plan_i64).  Returns None when the operator does not qualify, else a dict with
+    blk [nblocks,6], runs [nruns,2], col16 [nnz], max_slots, max_runs."""
+    ptr = np.ascontiguousarray(ptr, dtype=np.int64)
+    col = np.ascontiguousarray(col, dtype=np.int64)
+    nnz = int(ptr[-1]) if nrows else 0
+    nb, nr = _i64(), _i64()
+    ms, mr, ok = _c.c_int(), _c.c_int(), _c.c_int()
+    L = lib()
+    _check(L.b200_window_plan_i64(nrows, ncols, ptr.ctypes.data, col.ctypes.data, lanes, nnz_cap, slot_cap,
+                                  max_ratio, gap, None, None, 0, None, 0, _c.byref(nb), _c.byref(nr),
+                                  _c.byref(ms), _c.byref(mr), _c.byref(ok)))
+    if not ok.value:
+        return None
+    blk = np.zeros((nb.value, 6), dtype=np.int32)
+    runs = np.zeros((max(1, nr.value), 2), dtype=np.int32)
+    col16 = np.zeros(max(1, nnz), dtype=np.uint16)
+    _check(L.b200_window_plan_i64(nrows, ncols, ptr.ctypes.data, col.ctypes.data, lanes, nnz_cap, slot_cap,
+                                  max_ratio, gap, col16.ctypes.data, runs.ctypes.data, runs.shape[0],
+                                  blk.ctypes.data, blk.shape[0], _c.byref(nb), _c.byref(nr),
+                                  _c.byref(ms), _c.byref(mr), _c.byref(ok)))
+    return {"blk": blk, "runs": runs[:nr.value], "col16": col16[:nnz], "max_slots": ms.value,
+            "max_runs": mr.value}
 
 
 class Coarse:

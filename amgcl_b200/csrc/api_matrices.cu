@@ -4,6 +4,8 @@
 // only: argument checking, bookkeeping, kernel launches; no CPU fallback anywhere).
 #include "internal.cuh"
 #include "csr_kernels.cuh"
+#include "csr_launch.cuh"
+#include "window.cuh"
 
 namespace b200 {
 int tail_enqueue_csr(b200_ctx_t ctx, int mode, b200_csr_t A, const CsrArgsT<PrecDD> &a);   // api_tail.cu
@@ -135,9 +137,11 @@ static cudaError_t staged_upload(b200_ctx_t ctx, Dst *dst, const Src *src, size_
 // Upload one CSR matrix exactly as the kernels will see it (indices narrowed to int32,
 // row-block plan built).  Single-GPU matrices come straight through here; the
 // distributed kinds hand in the local part produced by dist.cuh.
+// halo_from >= 0: columns >= halo_from are owned by other ranks; the row blocks that gather
+// them are marked and walked last, so the peers' pushes land while interior rows are computed.
 template <class Ptr, class Col, class Val>
 static int csr_upload(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *ptr,
-                      const Col *col, const Val *val, b200_csr_t *out, bool want_lines = true) {
+                      const Col *col, const Val *val, b200_csr_t *out, int64_t halo_from = -1) {
     CHECK_CTX(ctx);
     B200_REQUIRE(out != nullptr, "null output pointer");
     *out = nullptr;
@@ -157,7 +161,48 @@ static int csr_upload(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *p
     const int lanes = plan.lanes, rows_cap = plan.rows_cap, nnz_cap = plan.nnz_cap;
     const int64_t nlong = plan.nlong;
     std::vector<int2> &blk = plan.blk;
-    const int64_t nblocks = (int64_t)blk.size() - 1;
+    int64_t nblocks = (int64_t)blk.size() - 1;
+
+    // self-contained block descriptors in walk order
+    std::vector<int4> blk4((size_t)nblocks + 1);
+    if (halo_from >= 0 && nblocks > 0) {
+        std::vector<char> outer((size_t)nblocks, 0);
+#pragma omp parallel for schedule(dynamic, 64)
+        for (int64_t b = 0; b < nblocks; ++b) {
+            bool halo = false;
+            for (int64_t e = blk[(size_t)b].y; e < blk[(size_t)b + 1].y && !halo; ++e)
+                halo = (int64_t)col[e] >= halo_from;
+            outer[(size_t)b] = halo;
+        }
+        size_t k = 0;
+        for (int pass = 0; pass < 2; ++pass)
+            for (int64_t b = 0; b < nblocks; ++b)
+                if (outer[(size_t)b] == pass) {
+                    const int2 lo = blk[(size_t)b], hi = blk[(size_t)b + 1];
+                    blk4[k++] = make_int4(pass ? ~lo.x : lo.x, hi.x, lo.y, hi.y);
+                }
+    } else {
+        for (int64_t b = 0; b < nblocks; ++b)
+            blk4[(size_t)b] = make_int4(blk[(size_t)b].x, blk[(size_t)b + 1].x, blk[(size_t)b].y, blk[(size_t)b + 1].y);
+    }
+    blk4[(size_t)nblocks] = make_int4((int)nrows, (int)nrows, (int)nnz, (int)nnz);
+
+    // ---- windowed format, where the operator qualifies (window.cuh) ------------------------
+    WindowPlan win;
+    bool windowed = false;
+    if (ctx->opt_window && nnz >= ctx->opt_window_min_nnz && nlong == 0 && lanes <= 8 &&
+        ((ctx->opt_window_lanes >> (lanes == 1 ? 0 : lanes == 2 ? 1 : lanes == 4 ? 2 : 3)) & 1)) {
+        // what the default launch configuration leaves for the window beside two stages
+        const StageLayout wl = stage_layout(rows_cap, nnz_cap, (int)sizeof(Val), kWinRunCapMax);
+        const int budget = ring_budget(4) - kHeaderBytes - 2 * wl.bytes;
+        const int slot_cap = std::min(8192, (budget / 8) & ~3);
+        windowed = build_windows(blk4.data(), nblocks, hptr.data(), col, ncols, nnz, slot_cap, kWinRunCapMax,
+                                 (double)ctx->opt_window_ratio / 100.0, (int)ctx->opt_window_gap, win);
+        if (windowed) {                   // (blocks whose window did not fit were cut)
+            blk4.swap(win.blk4);
+            nblocks = (int64_t)blk4.size() - 1;
+        }
+    }
 
     // ---- upload ---------------------------------------------------------------------
     b200_csr_s *A = new (std::nothrow) b200_csr_s();
@@ -172,16 +217,17 @@ static int csr_upload(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *p
     const size_t col_bytes = ((size_t)nnz + 8) * sizeof(int);
     const size_t val_bytes = ((size_t)nnz + 8) * sizeof(Val);
     const size_t blk_bytes = ((size_t)nblocks + 1) * sizeof(int4);
-    // self-contained block descriptors in walk order (here: the natural order)
-    std::vector<int4> blk4((size_t)nblocks + 1);
-    for (int64_t b = 0; b < nblocks; ++b)
-        blk4[(size_t)b] = make_int4(blk[(size_t)b].x, blk[(size_t)b + 1].x, blk[(size_t)b].y, blk[(size_t)b + 1].y);
-    blk4[(size_t)nblocks] = make_int4((int)nrows, (int)nrows, (int)nnz, (int)nnz);
+    const size_t c16_bytes = windowed ? ((size_t)nnz + 16) * sizeof(unsigned short) : 0;
+    const size_t run_bytes = windowed ? (win.runs.size() + 4) * sizeof(int2) : 0;
+    const size_t wbk_bytes = windowed ? ((size_t)nblocks + 1) * sizeof(int2) : 0;
     auto cleanup = [&]() {
         if (A->ptr) cudaFree(A->ptr);
         if (A->col) cudaFree(A->col);
         if (A->val) cudaFree(A->val);
         if (A->blk) cudaFree(A->blk);
+        if (A->col16) cudaFree(A->col16);
+        if (A->wrun) cudaFree(A->wrun);
+        if (A->wblk) cudaFree(A->wblk);
         delete A;
     };
 #define CSR_CUDA(call)                                                         \
@@ -205,11 +251,25 @@ static int csr_upload(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *p
         CSR_CUDA(staged_upload(ctx, static_cast<Val *>(A->val), val, (size_t)nnz));
     }
     CSR_CUDA(cudaMemcpyAsync(A->blk, blk4.data(), blk_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (windowed) {
+        CSR_CUDA(cudaMalloc(&A->col16, c16_bytes));
+        CSR_CUDA(cudaMalloc(&A->wrun, run_bytes));
+        CSR_CUDA(cudaMalloc(&A->wblk, wbk_bytes));
+        CSR_CUDA(cudaMemsetAsync(A->col16, 0, c16_bytes, ctx->stream));
+        CSR_CUDA(cudaMemsetAsync(A->wrun, 0, run_bytes, ctx->stream));
+        CSR_CUDA(cudaMemsetAsync(A->wblk, 0, wbk_bytes, ctx->stream));
+        CSR_CUDA(staged_upload(ctx, A->col16, win.col16.data(), (size_t)nnz));
+        if (!win.runs.empty()) CSR_CUDA(staged_upload(ctx, A->wrun, win.runs.data(), win.runs.size()));
+        CSR_CUDA(staged_upload(ctx, A->wblk, win.wblk.data(), (size_t)nblocks));
+        A->win_slots = (win.max_slots + 3) & ~3;
+        A->win_runs = win.max_runs;
+        A->win_total = win.total_slots;
+    }
     CSR_CUDA(cudaStreamSynchronize(ctx->stream));   // host staging buffers die here
 #undef CSR_CUDA
-    A->bytes = ptr_bytes + col_bytes + val_bytes + blk_bytes;
+    A->bytes = ptr_bytes + col_bytes + val_bytes + blk_bytes + c16_bytes + run_bytes + wbk_bytes;
     *out = A;
-    if (want_lines && ctx->opt_warm_lines && lanes >= 2 && A->dtype == B200_F64 && nblocks > 0 &&
+    if (halo_from < 0 && !windowed && ctx->opt_warm_lines && lanes >= 2 && A->dtype == B200_F64 && nblocks > 0 &&
         (ctx->opt_warm_lines > 1 || nnz >= 1000000)) {
         // Gather-heavy operator: the 128-byte lines of x every row block gathers from (sorted,
         // distinct), so the kernel can fill them into L1 with a few coalesced loads instead of
@@ -258,6 +318,9 @@ static void csr_free(b200_csr_t A) {
     if (A->blk) cudaFree(A->blk);
     if (A->wl_ptr) cudaFree(A->wl_ptr);
     if (A->wl) cudaFree(A->wl);
+    if (A->col16) cudaFree(A->col16);
+    if (A->wrun) cudaFree(A->wrun);
+    if (A->wblk) cudaFree(A->wblk);
     if (A->send_idx) cudaFree(A->send_idx);
     if (A->halo_owned) cudaFree(A->halo_owned);
     if (A->ybuf) cudaFree(A->ybuf);
@@ -295,7 +358,7 @@ static int csr_create(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *p
 
     b200_csr_t A = nullptr;
     rc = csr_upload(ctx, sp.nrows, sp.ncols, sp.ptr.data(), sp.col.data(), val + sp.val_offset, &A,
-                    /* want_lines: halo columns live in another buffer */ !cd);
+                    /* columns from here on live in the halo buffer */ cd ? sp.n_loc : (int64_t)-1);
     if (rc) return rc;
     A->kind = cd ? B200_CK_HALO : B200_CK_LOCAL;
     A->gl_rows = nrows; A->gl_cols = ncols; A->gl_nnz = nnz;
@@ -324,28 +387,6 @@ static int csr_create(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *p
             DCSR_CUDA(cudaMemcpyAsync(A->send_idx, idx.data(), idx.size() * sizeof(int),
                                       cudaMemcpyHostToDevice, ctx->stream));
         A->bytes += idx.size() * sizeof(int) + (size_t)(P * sp.S) * sizeof(double);
-        // which row blocks touch the halo (the same plan csr_upload just built), and the walk
-        // order that puts them last so the peers' pushes land while interior rows are computed
-        RowBlockPlan plan;
-        build_plan(sp.nrows, sp.ptr.data(), A->lanes, A->nnz_cap, plan);
-        std::vector<int4> inner, outer;
-        if ((int64_t)plan.blk.size() - 1 == A->nblocks) {
-            for (int64_t b = 0; b < A->nblocks; ++b) {
-                const int2 lo = plan.blk[(size_t)b], hi = plan.blk[(size_t)b + 1];
-                bool halo = false;
-                for (int64_t e = lo.y; e < hi.y && !halo; ++e) halo = sp.col[(size_t)e] >= sp.n_loc;
-                if (halo) outer.push_back(make_int4(~lo.x, hi.x, lo.y, hi.y));
-                else inner.push_back(make_int4(lo.x, hi.x, lo.y, hi.y));
-            }
-            inner.insert(inner.end(), outer.begin(), outer.end());
-            if (!inner.empty())
-                DCSR_CUDA(cudaMemcpyAsync(A->blk, inner.data(), inner.size() * sizeof(int4),
-                                          cudaMemcpyHostToDevice, ctx->stream));
-        } else {
-            csr_free(A);                             // cannot happen: same inputs, same plan
-            return fail(B200_EINVAL, "internal error: row-block plans differ");
-        }
-        DCSR_CUDA(cudaStreamSynchronize(ctx->stream));
         // who exchanges with whom: the symmetric closure of "rows of p reference columns of o"
         // (identical on every rank: derived from the global matrix).  A pair exchanges flags in
         // BOTH directions even if data flows one way only: that is what bounds how far one
@@ -409,26 +450,16 @@ static int launch_csr_LH(b200_ctx_t ctx, b200_csr_t A, const CsrArgsT<P> &args) 
         csr_block_kernel<MODE, L, HALO, PrecDD><<<(unsigned)A->nblocks, kThreads, smem, ctx->stream>>>(
             *reinterpret_cast<const CsrArgsT<PrecDD> *>(&args));
     } else {
-        int stages = (int)ctx->opt_stages;
-        const int max_smem = 227 * 1024;
-        const int per_cta_budget = max_smem / (int)ctx->opt_ctas_per_sm - 1024;
-        while (stages > 1 && kHeaderBytes + stages * lay.bytes > per_cta_budget) --stages;
-        const int smem = kHeaderBytes + stages * lay.bytes;
-        static bool attr_set[64] = {};
-        if (!attr_set[ctx->device & 63]) {
-            // the opt-in limit covers static + dynamic shared memory (red_finish keeps a few
-            // hundred bytes of static scratch)
-            cudaFuncAttributes fa;
-            B200_CUDA(cudaFuncGetAttributes(&fa, csr_ring_kernel<MODE, L, HALO, P>));
-            B200_CUDA(cudaFuncSetAttribute(csr_ring_kernel<MODE, L, HALO, P>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           max_smem - (int)fa.sharedSizeBytes));
-            attr_set[ctx->device & 63] = true;
+        int rc = B200_OK;
+        bool done = false;
+        if constexpr (L <= 8) {
+            if (use_window<P>(ctx, A)) {
+                rc = launch_ring_win<MODE, L, HALO, P>(ctx, A, args);
+                done = true;
+            }
         }
-        const int64_t cap = (int64_t)ctx->sm_count * ctx->opt_ctas_per_sm;
-        const unsigned grid = (unsigned)std::min<int64_t>(A->nblocks, cap);
-        B200_CUDA(launch_pdl(ctx, csr_ring_kernel<MODE, L, HALO, P>, dim3(grid), dim3(kThreads), (size_t)smem,
-                             args, stages));
+        if (!done) rc = launch_ring_impl<MODE, L, HALO, P, false>(ctx, A, args);
+        if (rc) return rc;
     }
     B200_CHECK_LAUNCH();
     ctx->launches++;
@@ -476,6 +507,7 @@ static CsrArgsT<P> base_args_t(b200_csr_t A) {
     a.nrows = (int)A->nrows; a.nblocks = (int)A->nblocks;
     a.rows_cap = A->rows_cap; a.nnz_cap = A->nnz_cap;
     if (std::is_same<P, PrecDD>::value && A->ctx->opt_warm_lines) { a.wl_ptr = A->wl_ptr; a.wl = A->wl; }
+    a.col16 = A->col16; a.wrun = A->wrun; a.wblk = A->wblk; a.run_cap = A->win_runs;
     return a;
 }
 static CsrArgs base_args(b200_csr_t A) { return base_args_t<PrecDD>(A); }
@@ -551,6 +583,71 @@ extern "C" int b200_plan_i64(int64_t nrows, const int64_t *ptr, int lanes, int n
             blk_out[2 * i + 1] = plan.blk[i].y;
         }
     }
+    return B200_OK;
+}
+
+// The windowed format of a host matrix (window.cuh), for tests: the same plan + windows
+// csr_upload builds, without a device.
+extern "C" int b200_window_plan_i64(int64_t nrows, int64_t ncols, const int64_t *ptr, const int64_t *col,
+                                    int lanes, int nnz_cap, int slot_cap, int max_ratio_percent, int gap,
+                                    uint16_t *col16_out, int32_t *runs_out, int64_t runs_capacity,
+                                    int32_t *blk_out, int64_t blk_capacity, int64_t *nblocks_out,
+                                    int64_t *nruns_out, int *max_slots_out, int *max_runs_out, int *qualifies) {
+    B200_REQUIRE(nrows >= 0 && ncols >= 0 && ptr && nblocks_out && nruns_out && qualifies, "bad argument");
+    B200_REQUIRE(nnz_cap >= 256 && nnz_cap <= kNnzCapMax && nnz_cap % 8 == 0, "bad nnz_cap");
+    B200_REQUIRE(lanes == 0 || (lanes >= 1 && lanes <= 32 && !(lanes & (lanes - 1))), "bad lanes");
+    int rc = csr_validate(nrows, ncols, ptr, col, true);
+    if (rc) return rc;
+    RowBlockPlan plan;
+    build_plan(nrows, ptr, lanes, nnz_cap, plan);
+    int64_t nblocks = (int64_t)plan.blk.size() - 1;
+    std::vector<int4> blk4((size_t)nblocks + 1);
+    for (int64_t b = 0; b < nblocks; ++b)
+        blk4[(size_t)b] = make_int4(plan.blk[(size_t)b].x, plan.blk[(size_t)b + 1].x, plan.blk[(size_t)b].y,
+                                    plan.blk[(size_t)b + 1].y);
+    const int64_t nnz = nrows ? ptr[nrows] : 0;
+    blk4[(size_t)nblocks] = make_int4((int)nrows, (int)nrows, (int)nnz, (int)nnz);
+    std::vector<int32_t> hptr((size_t)nrows + 1);
+    for (int64_t i = 0; i <= nrows; ++i) hptr[(size_t)i] = (int32_t)ptr[i];
+    WindowPlan w;
+    const bool ok = plan.nlong == 0 && plan.lanes <= 8 &&
+                    build_windows(blk4.data(), nblocks, hptr.data(), col, ncols, nnz, slot_cap,
+                                  kWinRunCapMax, max_ratio_percent / 100.0, gap, w);
+    if (ok) {
+        blk4.swap(w.blk4);
+        nblocks = (int64_t)blk4.size() - 1;
+    }
+    *qualifies = ok ? 1 : 0;
+    *nblocks_out = nblocks;
+    *nruns_out = ok ? (int64_t)w.runs.size() : 0;
+    if (max_slots_out) *max_slots_out = ok ? w.max_slots : 0;
+    if (max_runs_out) *max_runs_out = ok ? w.max_runs : 0;
+    if (!ok) return B200_OK;
+    if (blk_out) {
+        B200_REQUIRE(blk_capacity >= nblocks, "block output buffer too small");
+        for (int64_t b = 0; b < nblocks; ++b) {
+            blk_out[6 * b + 0] = blk4[(size_t)b].x; blk_out[6 * b + 1] = blk4[(size_t)b].y;
+            blk_out[6 * b + 2] = blk4[(size_t)b].z; blk_out[6 * b + 3] = blk4[(size_t)b].w;
+            blk_out[6 * b + 4] = w.wblk[(size_t)b].x; blk_out[6 * b + 5] = w.wblk[(size_t)b].y;
+        }
+    }
+    if (runs_out) {
+        B200_REQUIRE(runs_capacity >= (int64_t)w.runs.size(), "run output buffer too small");
+        for (size_t i = 0; i < w.runs.size(); ++i) {
+            runs_out[2 * i] = w.runs[i].x;
+            runs_out[2 * i + 1] = w.runs[i].y;
+        }
+    }
+    if (col16_out) std::copy(w.col16.begin(), w.col16.end(), col16_out);
+    return B200_OK;
+}
+
+extern "C" int b200_csr_window(b200_csr_t A, int *windowed, int *max_slots, int *max_runs, int64_t *total_slots) {
+    B200_REQUIRE(A, "null argument");
+    if (windowed) *windowed = A->col16 ? 1 : 0;
+    if (max_slots) *max_slots = A->win_slots;
+    if (max_runs) *max_runs = A->win_runs;
+    if (total_slots) *total_slots = A->win_total;
     return B200_OK;
 }
 

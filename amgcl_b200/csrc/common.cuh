@@ -157,6 +157,11 @@ struct b200_ctx_s {
     int64_t opt_tail_max_nnz  = 1500000;  // ... "small": at most this many non-zeros
     int64_t opt_tail_max_vec  = 262144;   // ... element-wise x = 0 sweeps: at most this many entries
     int64_t opt_poll_scalars  = 1;        // host reads in-kernel reduction results by polling mapped memory
+    int64_t opt_window        = 1;        // operators that qualify gather x through shared-memory windows
+    int64_t opt_window_min_nnz = 1000000; // ... "qualify": at least this many non-zeros (decided at upload),
+    int64_t opt_window_ratio  = 75;       // ... windows no larger than this percentage of the entries,
+    int64_t opt_window_gap    = 2;        // ... runs are merged across holes of (gap - 1) sectors
+    int64_t opt_window_lanes  = 15;       // ... lanes per row in this set (bit k: 2^k lanes)
     int64_t opt_warm_lines    = 0;        // gather-heavy operators: touch a block's lines of x before reducing it
                                           // (opt-in experiment: measured no gain)
     int64_t opt_small_kernel_max_nnz = 0;         // FP64 operators up to this size: direct-load kernel
@@ -250,6 +255,13 @@ struct b200_csr_s {
     int       *wl_ptr   = nullptr;// gather-heavy operators: [nblocks+1] offsets into wl (walk order)
     int       *wl       = nullptr;// 128-byte lines of x each row block gathers from
     int64_t    wl_count = 0;
+    // windowed operators (csr_kernels.cuh): blocks gather x from a shared-memory window
+    unsigned short *col16 = nullptr;  // [nnz] (+ padding) window-local column of every entry
+    int2      *wrun     = nullptr;// runs of x the windows are made of {first column, len | slot << 16}
+    int2      *wblk     = nullptr;// [nblocks] walk order: {first run, end run}
+    int        win_slots = 0;     // largest window (elements of x)
+    int        win_runs  = 0;     // most runs a block has
+    int64_t    win_total = 0;     // sum of the window sizes (elements): traffic of the fills
     int4      *blk      = nullptr;// [nblocks] device, walk order: {first row (~r if the block gathers halo
                                   //   columns), end row, first nnz, end nnz}; HALO: interior blocks first
     size_t     bytes    = 0;

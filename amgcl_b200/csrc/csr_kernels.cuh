@@ -24,6 +24,17 @@
 //   variant 1: persistent CTAs walking the block list with an S-deep ring of
 //              stages, so S*CTAs/SM bulk copies are always in flight per SM.
 //
+// Windowed operators (WIN).  For an operator whose row blocks gather from few distinct places
+// (the finest A, the prolongations, the coarse A's: on average a block of ~2000 entries reads
+// from ~1000 doubles of x laid out in about ten contiguous runs) the upload also stores, per
+// block, those runs and, per entry, the 16-bit position of its column inside the block's
+// window.  The kernel then fills the window into shared memory with coalesced loads (one
+// 32-byte sector is fetched once per block, not once per scattered 8-byte gather that misses
+// the small L1 left beside the stages) and reduces the rows entirely out of shared memory.  The
+// column stream shrinks from 4 to 2 bytes per entry.  The arithmetic (entry order, shuffle tree,
+// epilogue) is exactly that of the plain path, so the results are bit-identical
+// (tests/test_gpu_window.py).
+//
 // Precision.  Every kernel is a template over the element types of the matrix
 // values, the gathered vector, the right-hand side, the output and the smoother
 // diagonal (struct Prec).  FP64 throughout is the default; the other
@@ -34,6 +45,7 @@
 #pragma once
 #include "common.cuh"
 #include "reduce.cuh"
+#include <type_traits>
 
 namespace b200 {
 
@@ -107,6 +119,12 @@ struct CsrArgsT {
     // 32-byte sector fill per scattered 8-byte gather that misses (warm_lines below).
     const int    *wl_ptr; // [nblocks+1] (walk order) or nullptr
     const int    *wl;     // line numbers (x index / 16)
+    // Windowed operators: window-local column of every entry, the runs of x each block's window
+    // is made of ({first column, length | first slot << 16}), and each block's range of runs
+    const unsigned short *col16;
+    const int2   *wrun;
+    const int2   *wblk;   // [nblocks] in walk order
+    int           run_cap;// most runs a block has (stage layout); 0: not a windowed launch
     typename P::TY       *y;      // output
     typename P::TX       *xw;     // RESID_SCALED: where x = (alpha*d).*f is written
     const typename P::TF *f;      // rhs          (RESID, RELAX)
@@ -124,49 +142,81 @@ typedef CsrArgsT<PrecDD> CsrArgs;
 
 // ---- shared memory layout of one stage --------------------------------------
 struct StageLayout {
-    int val_off, col_off, ptr_off, bytes;
+    int val_off, col_off, ptr_off, run_off, bytes;
 };
-__host__ __device__ inline StageLayout stage_layout(int rows_cap, int nnz_cap, int val_size) {
+// run_cap == 0: plain operator (int32 columns); > 0: windowed (16-bit columns + the block's runs)
+__host__ __device__ inline StageLayout stage_layout(int rows_cap, int nnz_cap, int val_size, int run_cap = 0) {
     StageLayout s;
     s.val_off = 0;
     int val_bytes = nnz_cap * val_size + 16;       // source aligned down to 16 B
     val_bytes = (val_bytes + 15) & ~15;
     s.col_off = s.val_off + val_bytes;
-    int col_bytes = (nnz_cap + 8) * 4;             // +3 align down, +3 round up
+    int col_bytes = run_cap ? (nnz_cap + 16) * 2   // +7 align down, +7 round up
+                            : (nnz_cap + 8) * 4;   // +3 align down, +3 round up
     col_bytes = (col_bytes + 15) & ~15;
     s.ptr_off = s.col_off + col_bytes;
     int ptr_bytes = (rows_cap + 4) * 4;
     ptr_bytes = (ptr_bytes + 15) & ~15;
-    s.bytes = s.ptr_off + ptr_bytes;
+    s.run_off = s.ptr_off + ptr_bytes;
+    int run_bytes = run_cap ? (run_cap + 2) * 8 : 0;   // +1 align down, +1 round up
+    run_bytes = (run_bytes + 15) & ~15;
+    s.bytes = s.run_off + run_bytes;
     return s;
 }
-constexpr int kHeaderBytes = 256;   // mbarriers + per-stage block descriptors
+constexpr int kMaxStages   = 8;
+constexpr int kHeaderBytes = 384;   // mbarriers [0,64) + reduction scratch [64,128) + descriptors [128,384)
+constexpr int kWinRunLen   = 64;    // longest run of a window (longer ones are cut at upload)
 
 struct BlockDesc {      // written by the producer thread, read by everyone after the wait
     int r0, r1;         // row range
     int e0, e1;         // non-zero range
     int halo;           // the block gathers columns owned by other ranks
+    int q0, q1;         // windowed operators: the block's runs
+    int pad_;
 };
+static_assert(sizeof(BlockDesc) * kMaxStages <= kHeaderBytes - 128, "descriptors overflow the header");
 
 // ---- issue the bulk copies of one row block ----------------------------------
-template <class P>
+template <bool WIN = false, class P>
 __device__ __forceinline__ BlockDesc load_desc(const CsrArgsT<P> &a, int b) {
     const int4 q = __ldg(a.blk + b);       // one 16-byte load: nothing else to chase
     BlockDesc d;
     d.halo = q.x < 0;
     d.r0 = q.x < 0 ? ~q.x : q.x;
     d.r1 = q.y; d.e0 = q.z; d.e1 = q.w;
+    d.q0 = d.q1 = 0; d.pad_ = 0;
+    if (WIN) {
+        const int2 w = __ldg(a.wblk + b);
+        d.q0 = w.x; d.q1 = w.y;
+    }
     return d;
 }
 
 // Returns true if the block was staged (false: too long, use the strided path).
-template <class P>
+template <bool WIN = false, class P>
 __device__ __forceinline__ bool issue_block(const CsrArgsT<P> &a, const BlockDesc &d, char *stage,
                                             const StageLayout &lay, uint64_t *bar,
                                             uint64_t policy) {
     typedef typename P::TV TV;
     constexpr int VA = 16 / (int)sizeof(TV);        // values per 16 bytes
     const int nnz = d.e1 - d.e0;
+    if (WIN) {
+        // (a windowed operator has no long blocks)
+        const int a0 = d.e0 & ~(VA - 1);
+        const int nval = ((d.e1 - a0) + VA - 1) & ~(VA - 1);
+        const int c0 = d.e0 & ~7;                   // 16-bit columns: 8 per 16 bytes
+        const int ncol = ((d.e1 - c0) + 7) & ~7;
+        const int nptr = ((d.r1 - d.r0 + 1) + 3) & ~3;
+        const int qa = d.q0 & ~1;                   // runs: 2 per 16 bytes
+        const int nrun = ((d.q1 - qa) + 1) & ~1;
+        const uint32_t bytes = nval * (int)sizeof(TV) + ncol * 2 + nptr * 4 + nrun * 8;
+        ptx::mbar_expect_tx(bar, bytes);
+        if (nval) ptx::bulk_g2s(stage + lay.val_off, a.val + a0, nval * (int)sizeof(TV), bar, policy);
+        if (ncol) ptx::bulk_g2s(stage + lay.col_off, a.col16 + c0, ncol * 2, bar, policy);
+        ptx::bulk_g2s(stage + lay.ptr_off, a.ptr + d.r0, nptr * 4, bar, policy);
+        if (nrun) ptx::bulk_g2s(stage + lay.run_off, a.wrun + qa, nrun * 8, bar, policy);
+        return true;
+    }
     if (nnz > a.nnz_cap) {
         // nothing to stage: complete the phase with a plain arrive
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ptx::smem_addr(bar))
@@ -288,19 +338,45 @@ __device__ __forceinline__ void warm_lines(const CsrArgsT<P> &a, int pos) {
     }
 }
 
+// ---- windowed operators: bring the block's runs of x into shared memory --------------------
+// One warp per run (runs are at most kWinRunLen long and start on a 32-byte boundary of x, so a
+// warp's loads are whole sectors); ends with a CTA barrier.
+template <int MODE, bool HALO, class P>
+__device__ __forceinline__ void fill_window(const CsrArgsT<P> &a, const BlockDesc &d, const char *stage,
+                                            const StageLayout &lay, typename P::TX *win) {
+    const int2 *runs = reinterpret_cast<const int2 *>(stage + lay.run_off) + (d.q0 & 1);
+    const int nq   = d.q1 - d.q0;
+    const int lane = threadIdx.x & 31;
+    const typename P::TX *__restrict__ x = a.x;
+    for (int q = threadIdx.x >> 5; q < nq; q += kThreads / 32) {
+        const int2 rn   = runs[q];
+        const int first = rn.x;
+        const int len   = rn.y & 0xffff;
+        const int slot  = (int)((unsigned)rn.y >> 16);
+#pragma unroll
+        for (int i = lane; i < kWinRunLen; i += 32)
+            if (i < len) win[slot + i] = gather_m<MODE, HALO>(a, x, first + i);
+    }
+    __syncthreads();
+}
+
 // ---- reduce the rows of a staged block out of shared memory ---------------------
-template <int MODE, int L, bool HALO, class P>
+// (WIN: x comes from the block's window, `win`, indexed by the 16-bit columns)
+template <int MODE, int L, bool HALO, class P, bool WIN = false>
 __device__ __forceinline__ void compute_staged(const CsrArgsT<P> &a, const BlockDesc &d,
-                                               const char *stage, const StageLayout &lay, RowAcc &acc) {
+                                               const char *stage, const StageLayout &lay, RowAcc &acc,
+                                               const typename P::TX *win = nullptr) {
     typedef typename P::TV TV;
     typedef typename P::TX TX;
     typedef typename P::TY TS;                       // row sums live in the output's type
+    typedef typename std::conditional<WIN, unsigned short, int>::type CI;
+    static_assert(!(WIN && L >= 16), "windowed operators use at most 8 lanes per row");
     constexpr int VA = 16 / (int)sizeof(TV);
     const TV *val_s = reinterpret_cast<const TV *>(stage + lay.val_off);
-    const int    *col_s = reinterpret_cast<const int *>(stage + lay.col_off);
+    const CI     *col_s = reinterpret_cast<const CI *>(stage + lay.col_off);
     const int    *ptr_s = reinterpret_cast<const int *>(stage + lay.ptr_off);
     const int vo = d.e0 & ~(VA - 1);
-    const int co = d.e0 & ~3;
+    const int co = WIN ? (d.e0 & ~7) : (d.e0 & ~3);
     constexpr int G = kThreads / L;
     const int g    = threadIdx.x / L;
     const int lane = threadIdx.x % L;
@@ -377,7 +453,7 @@ __device__ __forceinline__ void compute_staged(const CsrArgsT<P> &a, const Block
                     v[u] = p[u] ? val_s[eu - vo] : (TV)0;
                 }
 #pragma unroll
-                for (int u = 0; u < U; ++u) xv[u] = gather_m<MODE, HALO>(a, x, c[u]);
+                for (int u = 0; u < U; ++u) xv[u] = WIN ? win[c[u]] : gather_m<MODE, HALO>(a, x, c[u]);
 #pragma unroll
                 for (int u = 0; u < U; ++u)
                     if (p[u]) sum = fma((TS)v[u], (TS)xv[u], sum);
@@ -497,14 +573,17 @@ __global__ void __launch_bounds__(kThreads, 4) csr_block_kernel(const CsrArgsT<P
 }
 
 // ---- variant 1: persistent CTAs, S-deep ring of stages ----------------------------------
-template <int MODE, int L, bool HALO, class P>
+// WIN: windowed operator (16-bit columns, x gathered from a shared-memory window per block)
+template <int MODE, int L, bool HALO, class P, bool WIN = false>
 __global__ void __launch_bounds__(kThreads, 2) csr_ring_kernel(const CsrArgsT<P> a, const int nstages) {
     extern __shared__ __align__(128) char smem[];
     uint64_t  *bars  = reinterpret_cast<uint64_t *>(smem);                 // [<=8]
     double    *red_s = reinterpret_cast<double *>(smem + 64);              // [8]
     BlockDesc *descs = reinterpret_cast<BlockDesc *>(smem + 128);          // [<=8]
-    const StageLayout lay = stage_layout(a.rows_cap, a.nnz_cap, (int)sizeof(typename P::TV));
+    const StageLayout lay = stage_layout(a.rows_cap, a.nnz_cap, (int)sizeof(typename P::TV),
+                                         WIN ? a.run_cap : 0);
     char *stages = smem + kHeaderBytes;
+    typename P::TX *win = reinterpret_cast<typename P::TX *>(stages + (size_t)nstages * lay.bytes);
 
     const int first = blockIdx.x;
     const int step  = gridDim.x;
@@ -519,9 +598,9 @@ __global__ void __launch_bounds__(kThreads, 2) csr_ring_kernel(const CsrArgsT<P>
         ptx::fence_mbar_init();
         const int pre = mine < nstages ? mine : nstages;
         for (int i = 0; i < pre; ++i) {
-            const BlockDesc d = load_desc(a, first + i * step);
+            const BlockDesc d = load_desc<WIN>(a, first + i * step);
             descs[i] = d;
-            issue_block(a, d, stages + (size_t)i * lay.bytes, lay, bars + i, policy);
+            issue_block<WIN>(a, d, stages + (size_t)i * lay.bytes, lay, bars + i, policy);
         }
     }
     __syncthreads();
@@ -534,16 +613,22 @@ __global__ void __launch_bounds__(kThreads, 2) csr_ring_kernel(const CsrArgsT<P>
         ptx::mbar_wait(bars + s, parity);
         const BlockDesc d = descs[s];
         wait_for_halo<HALO>(a, d);
-        if (!HALO) warm_lines(a, first + i * step);
-        if ((d.e1 - d.e0) <= a.nnz_cap)
-            compute_staged<MODE, L, HALO>(a, d, stages + (size_t)s * lay.bytes, lay, acc);
-        else
-            compute_long<MODE, HALO>(a, d, red_s, acc);
-        __syncthreads();                 // every thread is done with stage s (and descs[s])
+        if constexpr (WIN) {
+            const char *stage = stages + (size_t)s * lay.bytes;
+            fill_window<MODE, HALO>(a, d, stage, lay, win);
+            compute_staged<MODE, (L < 16 ? L : 8), HALO, P, WIN>(a, d, stage, lay, acc, win);
+        } else {
+            if (!HALO) warm_lines(a, first + i * step);
+            if ((d.e1 - d.e0) <= a.nnz_cap)
+                compute_staged<MODE, L, HALO>(a, d, stages + (size_t)s * lay.bytes, lay, acc);
+            else
+                compute_long<MODE, HALO>(a, d, red_s, acc);
+        }
+        __syncthreads();                 // every thread is done with stage s, descs[s], the window
         if (threadIdx.x == 0 && i + nstages < mine) {
-            const BlockDesc n = load_desc(a, first + (i + nstages) * step);
+            const BlockDesc n = load_desc<WIN>(a, first + (i + nstages) * step);
             descs[s] = n;
-            issue_block(a, n, stages + (size_t)s * lay.bytes, lay, bars + s, policy);
+            issue_block<WIN>(a, n, stages + (size_t)s * lay.bytes, lay, bars + s, policy);
         }
         if (++s == nstages) { s = 0; parity ^= 1; }
     }

@@ -271,6 +271,25 @@ int b200_plan_i64(int64_t nrows, const int64_t *ptr, int lanes, int nnz_cap,
                   int32_t *blk_out, int64_t blk_capacity, int64_t *nblocks,
                   int *lanes_out, int *rows_cap_out, int64_t *nlong_out);
 
+/* Windowed operators.  An operator whose row blocks gather x from few contiguous places
+ * (the level matrices and prolongations of a structured problem) is additionally stored with
+ * 16-bit window-local columns plus, per row block, the runs of x its window is made of; the
+ * streaming kernel then fills the window into shared memory with coalesced loads and reduces
+ * the rows out of it -- same arithmetic, same bits, fewer bytes (options "window",
+ * "window_min_nnz", "window_ratio", "window_gap", "window_lanes"; decided at upload).
+ * b200_csr_window: whether A carries the format, its largest window / run list and the sum of
+ * all window sizes (elements of x).
+ * b200_window_plan_i64: pure host helper for tests -- plan + windows of a host matrix.
+ * blk_out receives 6 ints per block {first row, end row, first nnz, end nnz, first run, end
+ * run}, runs_out 2 ints per run {first column, length | first slot << 16}, col16_out one
+ * window slot per entry.  *qualifies == 0: the operator would be stored plain. */
+int b200_csr_window(b200_csr_t A, int *windowed, int *max_slots, int *max_runs, int64_t *total_slots);
+int b200_window_plan_i64(int64_t nrows, int64_t ncols, const int64_t *ptr, const int64_t *col,
+                         int lanes, int nnz_cap, int slot_cap, int max_ratio_percent, int gap,
+                         uint16_t *col16_out, int32_t *runs_out, int64_t runs_capacity,
+                         int32_t *blk_out, int64_t blk_capacity, int64_t *nblocks,
+                         int64_t *nruns, int *max_slots, int *max_runs, int *qualifies);
+
 /* ---------------------------------------------------------------- primitives */
 
 /* y = alpha*A*x + beta*y.  y is never read when beta == 0.
