@@ -132,6 +132,8 @@ def lib():
         "b200_split_destroy": [_vp],
         "b200_plan_i64": [_i64, _vp, _c.c_int, _c.c_int, _vp, _i64, _P(_i64), _P(_c.c_int),
                           _P(_c.c_int), _P(_i64)],
+        "b200_csr_offsets": [_vp, _P(_c.c_int), _P(_c.c_int)],
+        "b200_offset_plan_i64": [_i64, _i64, _vp, _vp, _vp, _vp, _P(_c.c_int), _P(_c.c_int)],
         "b200_csr_window": [_vp, _P(_c.c_int), _P(_c.c_int), _P(_c.c_int), _P(_i64)],
         "b200_window_plan_i64": [_i64, _i64, _vp, _vp, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _vp, _vp, _i64,
                                  _vp, _i64, _P(_i64), _P(_i64), _P(_c.c_int), _P(_c.c_int), _P(_c.c_int)],
@@ -522,6 +524,12 @@ class Csr:
         _check(lib().b200_csr_bytes(self.h, _c.byref(b)))
         return b.value
 
+    def offsets(self):
+        """Offset-indexed column storage of this operator (b200_csr_offsets)."""
+        on, cnt = _c.c_int(), _c.c_int()
+        _check(lib().b200_csr_offsets(self.h, _c.byref(on), _c.byref(cnt)))
+        return {"offset_indexed": bool(on.value), "count": cnt.value}
+
     def window(self):
         """Windowed storage of this operator (include/amgcl_b200.h: b200_csr_window)."""
         w, ms, mr, tot = _c.c_int(), _c.c_int(), _c.c_int(), _i64()
@@ -534,6 +542,22 @@ class Csr:
                 self.h = _vp()      # (kept if the library refused, e.g. while a graph is recorded)
         except Exception:
             pass
+
+
+def offset_plan(nrows, ncols, ptr, col):
+    """Host-only: the offset-indexed column format b200_csr_create would build
+    (b200_offset_plan_i64).  None when the operator has more than 256 distinct col - row."""
+    ptr = np.ascontiguousarray(ptr, dtype=np.int64)
+    col = np.ascontiguousarray(col, dtype=np.int64)
+    nnz = int(ptr[-1]) if nrows else 0
+    idx8 = np.zeros(max(1, nnz), dtype=np.uint8)
+    tab = np.zeros(256, dtype=np.int32)
+    cnt, ok = _c.c_int(), _c.c_int()
+    _check(lib().b200_offset_plan_i64(nrows, ncols, ptr.ctypes.data, col.ctypes.data, idx8.ctypes.data,
+                                      tab.ctypes.data, _c.byref(cnt), _c.byref(ok)))
+    if not ok.value:
+        return None
+    return {"idx8": idx8[:nnz], "tab": tab, "count": cnt.value}
 
 
 def window_plan(nrows, ncols, ptr, col, lanes=0, nnz_cap=2048, slot_cap=1400, max_ratio=75, gap=2):

@@ -6,6 +6,7 @@
 #include "csr_kernels.cuh"
 #include "csr_launch.cuh"
 #include "window.cuh"
+#include "offsets.cuh"
 
 namespace b200 {
 int tail_enqueue_csr(b200_ctx_t ctx, int mode, b200_csr_t A, const CsrArgsT<PrecDD> &a);   // api_tail.cu
@@ -187,10 +188,15 @@ static int csr_upload(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *p
     }
     blk4[(size_t)nblocks] = make_int4((int)nrows, (int)nrows, (int)nnz, (int)nnz);
 
+    // ---- offset-indexed columns, where the operator qualifies (offsets.cuh) ------------------
+    OffsetPlan offp;
+    const bool offset_indexed = ctx->opt_offsets && nnz >= ctx->opt_offsets_min_nnz && nlong == 0 && lanes <= 4 &&
+                                build_offsets(nrows, hptr.data(), col, offp);
+
     // ---- windowed format, where the operator qualifies (window.cuh) ------------------------
     WindowPlan win;
     bool windowed = false;
-    if (ctx->opt_window && nnz >= ctx->opt_window_min_nnz && nlong == 0 && lanes <= 8 &&
+    if (!offset_indexed && ctx->opt_window && nnz >= ctx->opt_window_min_nnz && nlong == 0 && lanes <= 8 &&
         ((ctx->opt_window_lanes >> (lanes == 1 ? 0 : lanes == 2 ? 1 : lanes == 4 ? 2 : 3)) & 1)) {
         // what the default launch configuration leaves for the window beside two stages
         const StageLayout wl = stage_layout(rows_cap, nnz_cap, (int)sizeof(Val), kWinRunCapMax);
@@ -220,6 +226,8 @@ static int csr_upload(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *p
     const size_t c16_bytes = windowed ? ((size_t)nnz + 16) * sizeof(unsigned short) : 0;
     const size_t run_bytes = windowed ? (win.runs.size() + 4) * sizeof(int2) : 0;
     const size_t wbk_bytes = windowed ? ((size_t)nblocks + 1) * sizeof(int2) : 0;
+    const size_t ix8_bytes = offset_indexed ? (((size_t)nnz + 32 + 15) & ~(size_t)15) : 0;
+    const size_t tab_bytes = offset_indexed ? kOffTabLen * sizeof(int) : 0;
     auto cleanup = [&]() {
         if (A->ptr) cudaFree(A->ptr);
         if (A->col) cudaFree(A->col);
@@ -228,6 +236,8 @@ static int csr_upload(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *p
         if (A->col16) cudaFree(A->col16);
         if (A->wrun) cudaFree(A->wrun);
         if (A->wblk) cudaFree(A->wblk);
+        if (A->idx8) cudaFree(A->idx8);
+        if (A->off_tab) cudaFree(A->off_tab);
         delete A;
     };
 #define CSR_CUDA(call)                                                         \
@@ -265,9 +275,18 @@ static int csr_upload(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *p
         A->win_runs = win.max_runs;
         A->win_total = win.total_slots;
     }
+    if (offset_indexed) {
+        CSR_CUDA(cudaMalloc(&A->idx8, ix8_bytes));
+        CSR_CUDA(cudaMalloc(&A->off_tab, tab_bytes));
+        CSR_CUDA(cudaMemsetAsync(A->idx8, 0, ix8_bytes, ctx->stream));
+        CSR_CUDA(staged_upload(ctx, A->idx8, offp.idx8.data(), (size_t)nnz));
+        CSR_CUDA(staged_upload(ctx, A->off_tab, offp.tab, (size_t)kOffTabLen));
+        A->off_count = offp.count;
+    }
     CSR_CUDA(cudaStreamSynchronize(ctx->stream));   // host staging buffers die here
 #undef CSR_CUDA
-    A->bytes = ptr_bytes + col_bytes + val_bytes + blk_bytes + c16_bytes + run_bytes + wbk_bytes;
+    A->bytes = ptr_bytes + col_bytes + val_bytes + blk_bytes + c16_bytes + run_bytes + wbk_bytes + ix8_bytes +
+               tab_bytes;
     *out = A;
     if (halo_from < 0 && !windowed && ctx->opt_warm_lines && lanes >= 2 && A->dtype == B200_F64 && nblocks > 0 &&
         (ctx->opt_warm_lines > 1 || nnz >= 1000000)) {
@@ -321,6 +340,8 @@ static void csr_free(b200_csr_t A) {
     if (A->col16) cudaFree(A->col16);
     if (A->wrun) cudaFree(A->wrun);
     if (A->wblk) cudaFree(A->wblk);
+    if (A->idx8) cudaFree(A->idx8);
+    if (A->off_tab) cudaFree(A->off_tab);
     if (A->send_idx) cudaFree(A->send_idx);
     if (A->halo_owned) cudaFree(A->halo_owned);
     if (A->ybuf) cudaFree(A->ybuf);
@@ -452,13 +473,20 @@ static int launch_csr_LH(b200_ctx_t ctx, b200_csr_t A, const CsrArgsT<P> &args) 
     } else {
         int rc = B200_OK;
         bool done = false;
+        const int fmt = launch_format<P>(ctx, A);
+        if constexpr (L <= 4) {
+            if (fmt == FMT_OFFSET) {
+                rc = launch_ring_off<MODE, L, HALO, P>(ctx, A, args);
+                done = true;
+            }
+        }
         if constexpr (L <= 8) {
-            if (use_window<P>(ctx, A)) {
+            if (fmt == FMT_WINDOW) {
                 rc = launch_ring_win<MODE, L, HALO, P>(ctx, A, args);
                 done = true;
             }
         }
-        if (!done) rc = launch_ring_impl<MODE, L, HALO, P, false>(ctx, A, args);
+        if (!done) rc = launch_ring_impl<MODE, L, HALO, P, FMT_PLAIN>(ctx, A, args);
         if (rc) return rc;
     }
     B200_CHECK_LAUNCH();
@@ -508,6 +536,7 @@ static CsrArgsT<P> base_args_t(b200_csr_t A) {
     a.rows_cap = A->rows_cap; a.nnz_cap = A->nnz_cap;
     if (std::is_same<P, PrecDD>::value && A->ctx->opt_warm_lines) { a.wl_ptr = A->wl_ptr; a.wl = A->wl; }
     a.col16 = A->col16; a.wrun = A->wrun; a.wblk = A->wblk; a.run_cap = A->win_runs;
+    a.idx8 = A->idx8; a.off_tab = A->off_tab;
     return a;
 }
 static CsrArgs base_args(b200_csr_t A) { return base_args_t<PrecDD>(A); }
@@ -639,6 +668,31 @@ extern "C" int b200_window_plan_i64(int64_t nrows, int64_t ncols, const int64_t 
         }
     }
     if (col16_out) std::copy(w.col16.begin(), w.col16.end(), col16_out);
+    return B200_OK;
+}
+
+// The offset-indexed format of a host matrix (offsets.cuh), for tests.
+extern "C" int b200_offset_plan_i64(int64_t nrows, int64_t ncols, const int64_t *ptr, const int64_t *col,
+                                    uint8_t *idx8_out, int32_t *tab_out, int *count, int *qualifies) {
+    B200_REQUIRE(nrows >= 0 && ncols >= 0 && ptr && qualifies, "bad argument");
+    int rc = csr_validate(nrows, ncols, ptr, col, true);
+    if (rc) return rc;
+    std::vector<int32_t> hptr((size_t)nrows + 1);
+    for (int64_t i = 0; i <= nrows; ++i) hptr[(size_t)i] = (int32_t)ptr[i];
+    OffsetPlan o;
+    const bool ok = build_offsets(nrows, hptr.data(), col, o);
+    *qualifies = ok ? 1 : 0;
+    if (count) *count = ok ? o.count : 0;
+    if (!ok) return B200_OK;
+    if (idx8_out) std::copy(o.idx8.begin(), o.idx8.end(), idx8_out);
+    if (tab_out) std::copy(o.tab, o.tab + kOffTabLen, tab_out);
+    return B200_OK;
+}
+
+extern "C" int b200_csr_offsets(b200_csr_t A, int *offset_indexed, int *count) {
+    B200_REQUIRE(A, "null argument");
+    if (offset_indexed) *offset_indexed = A->idx8 ? 1 : 0;
+    if (count) *count = A->off_count;
     return B200_OK;
 }
 

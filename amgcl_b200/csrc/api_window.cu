@@ -7,7 +7,7 @@ namespace b200 {
 
 template <int MODE, int L, bool HALO, class P>
 int launch_ring_win(b200_ctx_t ctx, b200_csr_t A, const CsrArgsT<P> &args) {
-    return launch_ring_impl<MODE, L, HALO, P, true>(ctx, A, args);
+    return launch_ring_impl<MODE, L, HALO, P, FMT_WINDOW>(ctx, A, args);
 }
 
 // every (mode, precision) pair api_matrices.cu launches, for 1..8 lanes per row, with and

@@ -157,7 +157,9 @@ struct b200_ctx_s {
     int64_t opt_tail_max_nnz  = 1500000;  // ... "small": at most this many non-zeros
     int64_t opt_tail_max_vec  = 262144;   // ... element-wise x = 0 sweeps: at most this many entries
     int64_t opt_poll_scalars  = 1;        // host reads in-kernel reduction results by polling mapped memory
-    int64_t opt_window        = 1;        // operators that qualify gather x through shared-memory windows
+    int64_t opt_offsets       = 1;        // operators with <= 256 distinct (col - row): 8-bit column indices
+    int64_t opt_offsets_min_nnz = 1000000;// ... from this many non-zeros on (decided at upload)
+    int64_t opt_window        = 0;        // operators that qualify gather x through shared-memory windows
     int64_t opt_window_min_nnz = 1000000; // ... "qualify": at least this many non-zeros (decided at upload),
     int64_t opt_window_ratio  = 75;       // ... windows no larger than this percentage of the entries,
     int64_t opt_window_gap    = 2;        // ... runs are merged across holes of (gap - 1) sectors
@@ -262,6 +264,10 @@ struct b200_csr_s {
     int        win_slots = 0;     // largest window (elements of x)
     int        win_runs  = 0;     // most runs a block has
     int64_t    win_total = 0;     // sum of the window sizes (elements): traffic of the fills
+    // offset-indexed columns (csr_kernels.cuh): col = row + off_tab[idx8]
+    unsigned char *idx8 = nullptr;    // [nnz] (+ padding)
+    int       *off_tab  = nullptr;    // [256] device
+    int        off_count = 0;         // distinct (col - row) offsets
     int4      *blk      = nullptr;// [nblocks] device, walk order: {first row (~r if the block gathers halo
                                   //   columns), end row, first nnz, end nnz}; HALO: interior blocks first
     size_t     bytes    = 0;

@@ -35,6 +35,15 @@
 // epilogue) is exactly that of the plain path, so the results are bit-identical
 // (tests/test_gpu_window.py).
 //
+// Offset-indexed columns (FMT_OFFSET).  In a matrix assembled on a structured grid every entry
+// sits on one of a few diagonals: col - row takes a handful of distinct values (7 for the
+// Poisson stencil, a few more on a partitioned operator where halo columns are renumbered).  If
+// there are at most 256 of them, the upload also stores one BYTE per entry -- the index of its
+// offset in a table -- and the kernel streams 1 instead of 4 bytes of column per entry
+// (9 instead of 12 bytes per FP64 entry, 5 instead of 8 per FP32 entry), rebuilding the column
+// as row + table[index] from shared memory.  Entry order and arithmetic are those of the plain
+// path: bit-identical results (tests/test_gpu_offsets.py).
+//
 // Precision.  Every kernel is a template over the element types of the matrix
 // values, the gathered vector, the right-hand side, the output and the smoother
 // diagonal (struct Prec).  FP64 throughout is the default; the other
@@ -48,6 +57,11 @@
 #include <type_traits>
 
 namespace b200 {
+
+// storage format of the column indices the kernel streams
+enum { FMT_PLAIN = 0,     // int32 column per entry
+       FMT_WINDOW = 1,    // 16-bit position in the block's shared-memory window of x
+       FMT_OFFSET = 2 };  // 8-bit index into a table of (col - row) offsets
 
 enum { MODE_SPMV = 0, MODE_SPMV_ACC = 1, MODE_RESID = 2, MODE_RELAX = 3,
        // y = f - A x with x = (alpha*d).*f formed on the fly and written to xw: the smoother's
@@ -125,6 +139,9 @@ struct CsrArgsT {
     const int2   *wrun;
     const int2   *wblk;   // [nblocks] in walk order
     int           run_cap;// most runs a block has (stage layout); 0: not a windowed launch
+    // Offset-indexed operators: index of every entry's (col - row) in off_tab[256]
+    const unsigned char *idx8;
+    const int    *off_tab;
     typename P::TY       *y;      // output
     typename P::TX       *xw;     // RESID_SCALED: where x = (alpha*d).*f is written
     const typename P::TF *f;      // rhs          (RESID, RELAX)
@@ -144,21 +161,23 @@ typedef CsrArgsT<PrecDD> CsrArgs;
 struct StageLayout {
     int val_off, col_off, ptr_off, run_off, bytes;
 };
-// run_cap == 0: plain operator (int32 columns); > 0: windowed (16-bit columns + the block's runs)
+// run_cap == 0: plain operator (int32 columns); > 0: windowed (16-bit columns + the block's runs);
+// < 0: offset-indexed (8-bit columns)
 __host__ __device__ inline StageLayout stage_layout(int rows_cap, int nnz_cap, int val_size, int run_cap = 0) {
     StageLayout s;
     s.val_off = 0;
     int val_bytes = nnz_cap * val_size + 16;       // source aligned down to 16 B
     val_bytes = (val_bytes + 15) & ~15;
     s.col_off = s.val_off + val_bytes;
-    int col_bytes = run_cap ? (nnz_cap + 16) * 2   // +7 align down, +7 round up
-                            : (nnz_cap + 8) * 4;   // +3 align down, +3 round up
+    int col_bytes = run_cap > 0 ? (nnz_cap + 16) * 2   // +7 align down, +7 round up
+                  : run_cap < 0 ? (nnz_cap + 32)   // +15 align down, +15 round up
+                                : (nnz_cap + 8) * 4;   // +3 align down, +3 round up
     col_bytes = (col_bytes + 15) & ~15;
     s.ptr_off = s.col_off + col_bytes;
     int ptr_bytes = (rows_cap + 4) * 4;
     ptr_bytes = (ptr_bytes + 15) & ~15;
     s.run_off = s.ptr_off + ptr_bytes;
-    int run_bytes = run_cap ? (run_cap + 2) * 8 : 0;   // +1 align down, +1 round up
+    int run_bytes = run_cap > 0 ? (run_cap + 2) * 8 : 0;   // +1 align down, +1 round up
     run_bytes = (run_bytes + 15) & ~15;
     s.bytes = s.run_off + run_bytes;
     return s;
@@ -166,6 +185,11 @@ __host__ __device__ inline StageLayout stage_layout(int rows_cap, int nnz_cap, i
 constexpr int kMaxStages   = 8;
 constexpr int kHeaderBytes = 384;   // mbarriers [0,64) + reduction scratch [64,128) + descriptors [128,384)
 constexpr int kWinRunLen   = 64;    // longest run of a window (longer ones are cut at upload)
+constexpr int kOffTabLen   = 256;   // offset-indexed operators: entries of the (col - row) table
+// what stage_layout wants as run_cap for a launch of format FMT
+template <int FMT, class A> __host__ __device__ inline int layout_key(const A &a) {
+    return FMT == FMT_WINDOW ? a.run_cap : FMT == FMT_OFFSET ? -1 : 0;
+}
 
 struct BlockDesc {      // written by the producer thread, read by everyone after the wait
     int r0, r1;         // row range
@@ -177,7 +201,7 @@ struct BlockDesc {      // written by the producer thread, read by everyone afte
 static_assert(sizeof(BlockDesc) * kMaxStages <= kHeaderBytes - 128, "descriptors overflow the header");
 
 // ---- issue the bulk copies of one row block ----------------------------------
-template <bool WIN = false, class P>
+template <int FMT = FMT_PLAIN, class P>
 __device__ __forceinline__ BlockDesc load_desc(const CsrArgsT<P> &a, int b) {
     const int4 q = __ldg(a.blk + b);       // one 16-byte load: nothing else to chase
     BlockDesc d;
@@ -185,7 +209,7 @@ __device__ __forceinline__ BlockDesc load_desc(const CsrArgsT<P> &a, int b) {
     d.r0 = q.x < 0 ? ~q.x : q.x;
     d.r1 = q.y; d.e0 = q.z; d.e1 = q.w;
     d.q0 = d.q1 = 0; d.pad_ = 0;
-    if (WIN) {
+    if (FMT == FMT_WINDOW) {
         const int2 w = __ldg(a.wblk + b);
         d.q0 = w.x; d.q1 = w.y;
     }
@@ -193,14 +217,28 @@ __device__ __forceinline__ BlockDesc load_desc(const CsrArgsT<P> &a, int b) {
 }
 
 // Returns true if the block was staged (false: too long, use the strided path).
-template <bool WIN = false, class P>
+template <int FMT = FMT_PLAIN, class P>
 __device__ __forceinline__ bool issue_block(const CsrArgsT<P> &a, const BlockDesc &d, char *stage,
                                             const StageLayout &lay, uint64_t *bar,
                                             uint64_t policy) {
     typedef typename P::TV TV;
     constexpr int VA = 16 / (int)sizeof(TV);        // values per 16 bytes
     const int nnz = d.e1 - d.e0;
-    if (WIN) {
+    if (FMT == FMT_OFFSET) {
+        // (an offset-indexed operator has no long blocks)
+        const int a0 = d.e0 & ~(VA - 1);
+        const int nval = ((d.e1 - a0) + VA - 1) & ~(VA - 1);
+        const int c0 = d.e0 & ~15;                  // 8-bit columns: 16 per 16 bytes
+        const int ncol = ((d.e1 - c0) + 15) & ~15;
+        const int nptr = ((d.r1 - d.r0 + 1) + 3) & ~3;
+        const uint32_t bytes = nval * (int)sizeof(TV) + ncol + nptr * 4;
+        ptx::mbar_expect_tx(bar, bytes);
+        if (nval) ptx::bulk_g2s(stage + lay.val_off, a.val + a0, nval * (int)sizeof(TV), bar, policy);
+        if (ncol) ptx::bulk_g2s(stage + lay.col_off, a.idx8 + c0, ncol, bar, policy);
+        ptx::bulk_g2s(stage + lay.ptr_off, a.ptr + d.r0, nptr * 4, bar, policy);
+        return true;
+    }
+    if (FMT == FMT_WINDOW) {
         // (a windowed operator has no long blocks)
         const int a0 = d.e0 & ~(VA - 1);
         const int nval = ((d.e1 - a0) + VA - 1) & ~(VA - 1);
@@ -361,22 +399,26 @@ __device__ __forceinline__ void fill_window(const CsrArgsT<P> &a, const BlockDes
 }
 
 // ---- reduce the rows of a staged block out of shared memory ---------------------
-// (WIN: x comes from the block's window, `win`, indexed by the 16-bit columns)
-template <int MODE, int L, bool HALO, class P, bool WIN = false>
+// FMT_WINDOW: x comes from the block's window, `win`, indexed by the 16-bit columns;
+// FMT_OFFSET: the column of an entry of row r is r + off[8-bit index]
+template <int MODE, int L, bool HALO, class P, int FMT = FMT_PLAIN>
 __device__ __forceinline__ void compute_staged(const CsrArgsT<P> &a, const BlockDesc &d,
                                                const char *stage, const StageLayout &lay, RowAcc &acc,
-                                               const typename P::TX *win = nullptr) {
+                                               const typename P::TX *win = nullptr, const int *off = nullptr) {
+    constexpr bool WIN = FMT == FMT_WINDOW;
+    constexpr bool OFF = FMT == FMT_OFFSET;
     typedef typename P::TV TV;
     typedef typename P::TX TX;
     typedef typename P::TY TS;                       // row sums live in the output's type
-    typedef typename std::conditional<WIN, unsigned short, int>::type CI;
-    static_assert(!(WIN && L >= 16), "windowed operators use at most 8 lanes per row");
+    typedef typename std::conditional<WIN, unsigned short,
+                                      typename std::conditional<OFF, unsigned char, int>::type>::type CI;
+    static_assert(!((WIN || OFF) && L >= 16), "windowed / offset-indexed operators use at most 8 lanes per row");
     constexpr int VA = 16 / (int)sizeof(TV);
     const TV *val_s = reinterpret_cast<const TV *>(stage + lay.val_off);
     const CI     *col_s = reinterpret_cast<const CI *>(stage + lay.col_off);
     const int    *ptr_s = reinterpret_cast<const int *>(stage + lay.ptr_off);
     const int vo = d.e0 & ~(VA - 1);
-    const int co = WIN ? (d.e0 & ~7) : (d.e0 & ~3);
+    const int co = WIN ? (d.e0 & ~7) : OFF ? (d.e0 & ~15) : (d.e0 & ~3);
     constexpr int G = kThreads / L;
     const int g    = threadIdx.x / L;
     const int lane = threadIdx.x % L;
@@ -451,6 +493,10 @@ __device__ __forceinline__ void compute_staged(const CsrArgsT<P> &a, const Block
                     p[u] = eu < end;
                     c[u] = p[u] ? col_s[eu - co] : col_s[e - co];
                     v[u] = p[u] ? val_s[eu - vo] : (TV)0;
+                }
+                if (OFF) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) c[u] = d.r0 + rr + off[c[u]];
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) xv[u] = WIN ? win[c[u]] : gather_m<MODE, HALO>(a, x, c[u]);
@@ -573,17 +619,19 @@ __global__ void __launch_bounds__(kThreads, 4) csr_block_kernel(const CsrArgsT<P
 }
 
 // ---- variant 1: persistent CTAs, S-deep ring of stages ----------------------------------
-// WIN: windowed operator (16-bit columns, x gathered from a shared-memory window per block)
-template <int MODE, int L, bool HALO, class P, bool WIN = false>
+// FMT: storage format of the columns (FMT_PLAIN / FMT_WINDOW / FMT_OFFSET, see the top of the file)
+template <int MODE, int L, bool HALO, class P, int FMT = FMT_PLAIN>
 __global__ void __launch_bounds__(kThreads, 2) csr_ring_kernel(const CsrArgsT<P> a, const int nstages) {
     extern __shared__ __align__(128) char smem[];
     uint64_t  *bars  = reinterpret_cast<uint64_t *>(smem);                 // [<=8]
     double    *red_s = reinterpret_cast<double *>(smem + 64);              // [8]
     BlockDesc *descs = reinterpret_cast<BlockDesc *>(smem + 128);          // [<=8]
     const StageLayout lay = stage_layout(a.rows_cap, a.nnz_cap, (int)sizeof(typename P::TV),
-                                         WIN ? a.run_cap : 0);
+                                         layout_key<FMT>(a));
     char *stages = smem + kHeaderBytes;
+    // behind the stages: the window of x (FMT_WINDOW) or the offset table (FMT_OFFSET)
     typename P::TX *win = reinterpret_cast<typename P::TX *>(stages + (size_t)nstages * lay.bytes);
+    int *off_s = reinterpret_cast<int *>(stages + (size_t)nstages * lay.bytes);
 
     const int first = blockIdx.x;
     const int step  = gridDim.x;
@@ -598,10 +646,14 @@ __global__ void __launch_bounds__(kThreads, 2) csr_ring_kernel(const CsrArgsT<P>
         ptx::fence_mbar_init();
         const int pre = mine < nstages ? mine : nstages;
         for (int i = 0; i < pre; ++i) {
-            const BlockDesc d = load_desc<WIN>(a, first + i * step);
+            const BlockDesc d = load_desc<FMT>(a, first + i * step);
             descs[i] = d;
-            issue_block<WIN>(a, d, stages + (size_t)i * lay.bytes, lay, bars + i, policy);
+            issue_block<FMT>(a, d, stages + (size_t)i * lay.bytes, lay, bars + i, policy);
         }
+    }
+    if constexpr (FMT == FMT_OFFSET) {
+        static_assert(kOffTabLen == kThreads, "one table entry per thread");
+        off_s[threadIdx.x] = __ldg(a.off_tab + threadIdx.x);
     }
     __syncthreads();
     ptx::pdl_wait();         // vectors (x, f, d, y) come from earlier kernels: from here on
@@ -613,10 +665,13 @@ __global__ void __launch_bounds__(kThreads, 2) csr_ring_kernel(const CsrArgsT<P>
         ptx::mbar_wait(bars + s, parity);
         const BlockDesc d = descs[s];
         wait_for_halo<HALO>(a, d);
-        if constexpr (WIN) {
+        if constexpr (FMT == FMT_WINDOW) {
             const char *stage = stages + (size_t)s * lay.bytes;
             fill_window<MODE, HALO>(a, d, stage, lay, win);
-            compute_staged<MODE, (L < 16 ? L : 8), HALO, P, WIN>(a, d, stage, lay, acc, win);
+            compute_staged<MODE, (L < 16 ? L : 8), HALO, P, FMT_WINDOW>(a, d, stage, lay, acc, win);
+        } else if constexpr (FMT == FMT_OFFSET) {
+            compute_staged<MODE, (L < 16 ? L : 8), HALO, P, FMT_OFFSET>(a, d, stages + (size_t)s * lay.bytes, lay,
+                                                                           acc, nullptr, off_s);
         } else {
             if (!HALO) warm_lines(a, first + i * step);
             if ((d.e1 - d.e0) <= a.nnz_cap)
@@ -626,9 +681,9 @@ __global__ void __launch_bounds__(kThreads, 2) csr_ring_kernel(const CsrArgsT<P>
         }
         __syncthreads();                 // every thread is done with stage s, descs[s], the window
         if (threadIdx.x == 0 && i + nstages < mine) {
-            const BlockDesc n = load_desc<WIN>(a, first + (i + nstages) * step);
+            const BlockDesc n = load_desc<FMT>(a, first + (i + nstages) * step);
             descs[s] = n;
-            issue_block<WIN>(a, n, stages + (size_t)s * lay.bytes, lay, bars + s, policy);
+            issue_block<FMT>(a, n, stages + (size_t)s * lay.bytes, lay, bars + s, policy);
         }
         if (++s == nstages) { s = 0; parity ^= 1; }
     }

@@ -271,7 +271,19 @@ int b200_plan_i64(int64_t nrows, const int64_t *ptr, int lanes, int nnz_cap,
                   int32_t *blk_out, int64_t blk_capacity, int64_t *nblocks,
                   int *lanes_out, int *rows_cap_out, int64_t *nlong_out);
 
-/* Windowed operators.  An operator whose row blocks gather x from few contiguous places
+/* Offset-indexed columns.  If col - row takes at most 256 distinct values over the whole
+ * operator (matrices assembled on structured grids: 7 for the Poisson stencil), the upload
+ * also stores one byte per entry -- the index of its offset in a table -- and the streaming
+ * kernel reads 1 instead of 4 bytes of column per entry, rebuilding col = row + table[index];
+ * same entry order and arithmetic, same bits (options "offsets", "offsets_min_nnz"; decided at
+ * upload).  b200_csr_offsets: whether A carries the format and how many offsets it has.
+ * b200_offset_plan_i64: pure host helper for tests (idx8_out [nnz], tab_out [256]). */
+int b200_csr_offsets(b200_csr_t A, int *offset_indexed, int *count);
+int b200_offset_plan_i64(int64_t nrows, int64_t ncols, const int64_t *ptr, const int64_t *col,
+                         uint8_t *idx8_out, int32_t *tab_out, int *count, int *qualifies);
+
+/* Windowed operators (opt-in: measured slower than the plain path on B200).  An
+ * operator whose row blocks gather x from few contiguous places
  * (the level matrices and prolongations of a structured problem) is additionally stored with
  * 16-bit window-local columns plus, per row block, the runs of x its window is made of; the
  * streaming kernel then fills the window into shared memory with coalesced loads and reduces

@@ -1,6 +1,6 @@
-"""GPU parity of the windowed operator format (csr_kernels.cuh WIN, window.cuh): the same
-operator run through the windowed kernel and through the plain one must give the same bits --
-the window only changes where x is read from, not the arithmetic -- and both must agree with
+"""GPU parity of the offset-indexed column format (csr_kernels.cuh FMT_OFFSET, offsets.cuh):
+the same operator streamed with 8-bit column indices and with plain int32 columns must give
+the same bits -- only where the column number comes from changes -- and both must agree with
 the oracle."""
 import numpy as np
 import pytest
@@ -9,61 +9,48 @@ import amgcl_b200 as ab
 import oracle
 from conftest import rel_err
 from test_gpu_primitives import _f32csr, _f32vec
+from test_offsets import diag_matrix
 
 pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture()
-def wctx(ctx):
-    """Every operator that qualifies is windowed, whatever its size."""
-    ctx.set_option("window_min_nnz", 0)
-    ctx.set_option("window", 1)
-    ctx.set_option("offsets", 0)          # (an operator that qualifies for both is offset-indexed)
-    yield ctx
-    ctx.set_option("window_min_nnz", 1000000)
-    ctx.set_option("window_ratio", 75)
-    ctx.set_option("window", 0)
+def octx(ctx):
+    """Every operator that qualifies is offset-indexed, whatever its size."""
+    ctx.set_option("offsets_min_nnz", 0)
     ctx.set_option("offsets", 1)
-    ctx.set_option("lanes", 0)
-
-
-def banded(nr, nc, per_row, seed, spread=1):
-    """Rows of `per_row` entries around the diagonal position (blocks gather from one band)."""
-    rng = np.random.default_rng(seed)
-    lens = rng.integers(max(1, per_row - 3), per_row + 4, nr)
-    lens[::97] = 0                                           # some empty rows
-    ptr = np.zeros(nr + 1, dtype=np.int64)
-    np.cumsum(lens, out=ptr[1:])
-    col = np.empty(ptr[-1], dtype=np.int64)
-    for i in range(nr):
-        c0 = i * (nc - 1) // max(1, nr - 1)
-        cand = np.arange(max(0, c0 - 2 * per_row * spread), min(nc, c0 + 2 * per_row * spread + 1), spread)
-        col[ptr[i]:ptr[i + 1]] = np.sort(rng.choice(cand, lens[i], replace=False))
-    val = rng.uniform(-1, 1, ptr[-1])
-    return ptr, col, val
+    yield ctx
+    ctx.set_option("offsets_min_nnz", 1000000)
+    ctx.set_option("offsets", 1)
 
 
 def both(ctx, fn):
-    """Run fn() with the windowed kernels, then with the plain ones; return both results."""
-    ctx.set_option("window", 1)
+    """fn() with the offset-indexed kernels, then with the plain ones."""
+    ctx.set_option("offsets", 1)
     a = fn()
-    ctx.set_option("window", 0)
+    ctx.set_option("offsets", 0)
     b = fn()
-    ctx.set_option("window", 1)
+    ctx.set_option("offsets", 1)
     return a, b
 
 
-@pytest.mark.parametrize("per_row,lanes", [(6, 1), (30, 2), (50, 4), (100, 8)])
-@pytest.mark.parametrize("shape", [(3001, 3001), (2500, 4001)])
-def test_windowed_kernels_give_the_bits_of_the_plain_ones(wctx, per_row, lanes, shape):
-    ctx = wctx
+STENCILS = {
+    1: [-900, -30, -1, 0, 1, 30, 900],                                              # 7-point
+    2: [d + 30 * j + 900 * k for k in (-1, 0, 1) for j in (-1, 0, 1) for d in (-1, 0, 1)],   # 27-point
+    4: list(range(-26, 27)),                                                        # band of 53
+}
+
+
+@pytest.mark.parametrize("lanes", [1, 2, 4])
+@pytest.mark.parametrize("shape", [(5001, 5001), (4000, 5203)])
+def test_offset_indexed_kernels_give_the_bits_of_the_plain_ones(octx, lanes, shape):
+    ctx = octx
     o = oracle.c()
     nr, nc = shape
-    ptr, col, val = banded(nr, nc, per_row, seed=per_row + nr)
+    ptr, col, val = diag_matrix(nr, nc, STENCILS[lanes], seed=lanes + nr, keep=0.9)
     A = ctx.csr(nr, nc, ptr, col, val)
     assert A.plan()["lanes"] == lanes
-    w = A.window()
-    assert w["windowed"] and 0 < w["total_slots"] < 0.75 * col.size
+    assert A.offsets()["offset_indexed"] and A.offsets()["count"] <= len(STENCILS[lanes])
     rng = np.random.default_rng(1)
     x, y, f = rng.uniform(-1, 1, nc), rng.uniform(-1, 1, nr), rng.uniform(-1, 1, nr)
     vx, vf = ctx.vector(x), ctx.vector(f)
@@ -117,13 +104,13 @@ def test_windowed_kernels_give_the_bits_of_the_plain_ones(wctx, per_row, lanes, 
         K.close()
 
 
-def test_windowed_mixed_precision_combinations(wctx):
+def test_offset_indexed_mixed_precision_combinations(octx):
     """FP32 operator on FP32 / FP64 vectors: every combination the mixed hierarchy launches."""
-    ctx = wctx
-    n = 4000
-    ptr, col, val = banded(n, n, 30, seed=11)
+    ctx = octx
+    n = 6000
+    ptr, col, val = diag_matrix(n, n, STENCILS[2], seed=11)
     A32 = _f32csr(ctx, n, n, ptr, col, val)
-    assert A32.window()["windowed"]
+    assert A32.offsets()["offset_indexed"]
     rng = np.random.default_rng(2)
     x, f, y = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
     d = rng.uniform(0.1, 1.0, n).astype(np.float32)
@@ -146,44 +133,35 @@ def test_windowed_mixed_precision_combinations(wctx):
     assert np.array_equal(a, b)
 
 
-def test_blocks_cut_on_upload_still_compute_the_same(wctx):
-    """Windows that do not fit force the upload to cut row blocks: more blocks, same result."""
-    ctx = wctx
-    ctx.set_option("window_ratio", 1000)
-    ptr, col, val = banded(6000, 90000, 6, seed=4, spread=8)
-    nr, nc = 6000, 90000
-    ctx.set_option("window", 0)
-    Aplain = ctx.csr(nr, nc, ptr, col, val)
-    ctx.set_option("window", 1)
-    A = ctx.csr(nr, nc, ptr, col, val)
-    assert A.window()["windowed"] and not Aplain.window()["windowed"]
-    assert A.plan()["blocks"] > Aplain.plan()["blocks"]
-    rng = np.random.default_rng(6)
-    x = rng.uniform(-1, 1, nc)
-    vx, vy, vz = ctx.vector(x), ctx.vector(nr), ctx.vector(nr)
-    ctx.spmv(1.0, A, vx, 0.0, vy)
-    ctx.spmv(1.0, Aplain, vx, 0.0, vz)
-    assert np.array_equal(vy.numpy(), vz.numpy())
-    assert rel_err(vy.numpy(), oracle.c().spmv(1.0, (ptr, col, val), x, 0.0, np.zeros(nr))) < 1e-12
+def test_operators_with_many_offsets_stay_plain(octx):
+    ctx = octx
+    rng = np.random.default_rng(9)
+    nr = nc = 3000
+    lens = np.full(nr, 8)
+    ptr = np.zeros(nr + 1, dtype=np.int64)
+    np.cumsum(lens, out=ptr[1:])
+    col = np.sort(rng.integers(0, nc, (nr, 8)), axis=1).ravel()
+    A = ctx.csr(nr, nc, ptr, col, rng.uniform(-1, 1, col.size))
+    assert not A.offsets()["offset_indexed"]
 
 
 @pytest.mark.parametrize("relax,krylov,precision", [("damped_jacobi", "cg", "f64"), ("spai0", "bicgstab", "f64"),
                                                      ("damped_jacobi", "cg", "mixed")])
-def test_solver_is_bit_transparent_to_the_windowed_format(wctx, known_answers, relax, krylov, precision):
-    """The whole drop-in solve (hierarchy uploaded windowed where it qualifies) against the same
-    solve with plain operators: same iterations, same solution bits; and the reference's
-    iteration count."""
-    ctx = wctx
+def test_solver_is_bit_transparent_to_the_offset_format(octx, known_answers, relax, krylov, precision):
+    """The whole drop-in solve with the finest operator offset-indexed against the same solve
+    with plain columns: same iterations, same solution bits; and the reference's iteration
+    count."""
+    ctx = octx
     n = 32
     ptr, col, val, rhs = ab.poisson3d(n)
     res = []
-    for window in (1, 0):
-        ctx.set_option("window", window)
+    for on in (1, 0):
+        ctx.set_option("offsets", on)
         S = ab.DropinSolver(ptr, col, val, relax, krylov, ctx=ctx, precision=precision)
         x, it, r = S.solve(rhs)
         res.append((x, it, r))
         S.close()
-    ctx.set_option("window", 0)
+    ctx.set_option("offsets", 1)
     assert res[0][1] == res[1][1] and np.array_equal(res[0][0], res[1][0])
     if precision == "f64":
         case = [c for c in known_answers["cases"] if (c["n"], c["relax"], c["krylov"]) == (n, relax, krylov)][0]

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""A/B of the windowed operator format on the real solve (one GPU): for each option set, build
+"""A/B of the operator storage formats (offset-indexed / windowed columns) on the real solve (one GPU): for each option set, build
 the drop-in solver, check the solution bits against the first set, time the solve and list the
 device time of the big operators.
 
@@ -18,10 +18,14 @@ sys.path.insert(0, ROOT)
 import amgcl_b200 as ab  # noqa: E402
 
 CONFIGS = [
-    ("plain", {"window": 0}),
-    ("window all", {"window": 1, "window_ratio": 75, "window_lanes": 15}),
-    ("window P only", {"window": 1, "window_ratio": 50, "window_lanes": 15}),
-    ("window +A1", {"window": 1, "window_ratio": 125, "window_lanes": 15, "window_gap": 1}),
+    ("plain", {"window": 0, "offsets": 0}),
+    ("offsets", {"window": 0, "offsets": 1}),
+    ("offsets, 3 CTAs x 3 stages", {"window": 0, "offsets": 1, "ctas_per_sm": 3, "stages": 3}),
+    ("offsets, nnz_cap 3584 x 3 CTAs", {"window": 0, "offsets": 1, "nnz_cap": 3584, "ctas_per_sm": 3}),
+    ("offsets, 5 CTAs", {"window": 0, "offsets": 1, "ctas_per_sm": 5}),
+    ("window all", {"offsets": 0, "window": 1, "window_ratio": 75, "window_lanes": 15}),
+    ("window P only", {"offsets": 0, "window": 1, "window_ratio": 50, "window_lanes": 15}),
+    ("window +A1", {"offsets": 0, "window": 1, "window_ratio": 125, "window_lanes": 15, "window_gap": 1}),
 ]
 
 
@@ -46,8 +50,10 @@ def main():
     ref_hash = None
     for k in which:
         name, opts = CONFIGS[k]
-        for key in ("window_ratio", "window_lanes", "window_gap"):
-            ctx.set_option(key, {"window_ratio": 75, "window_lanes": 15, "window_gap": 2}[key])
+        defaults = {"window_ratio": 75, "window_lanes": 15, "window_gap": 2, "ctas_per_sm": 4, "stages": 2,
+                    "nnz_cap": 2048}
+        for key, v in defaults.items():
+            ctx.set_option(key, v)
         for key, v in opts.items():
             ctx.set_option(key, v)
         t0 = time.time()
