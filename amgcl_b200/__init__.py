@@ -132,6 +132,8 @@ def lib():
         "b200_split_destroy": [_vp],
         "b200_plan_i64": [_i64, _vp, _c.c_int, _c.c_int, _vp, _i64, _P(_i64), _P(_c.c_int),
                           _P(_c.c_int), _P(_i64)],
+        "b200_csr_patterns": [_vp, _P(_c.c_int), _P(_c.c_int), _P(_c.c_int)],
+        "b200_pattern_plan_i64": [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _P(_c.c_int), _P(_c.c_int), _P(_c.c_int)],
         "b200_csr_offsets": [_vp, _P(_c.c_int), _P(_c.c_int)],
         "b200_offset_plan_i64": [_i64, _i64, _vp, _vp, _vp, _vp, _P(_c.c_int), _P(_c.c_int)],
         "b200_csr_window": [_vp, _P(_c.c_int), _P(_c.c_int), _P(_c.c_int), _P(_i64)],
@@ -524,6 +526,12 @@ class Csr:
         _check(lib().b200_csr_bytes(self.h, _c.byref(b)))
         return b.value
 
+    def patterns(self):
+        """Pattern-indexed row storage of this operator (b200_csr_patterns)."""
+        on, cnt, tot = _c.c_int(), _c.c_int(), _c.c_int()
+        _check(lib().b200_csr_patterns(self.h, _c.byref(on), _c.byref(cnt), _c.byref(tot)))
+        return {"pattern_indexed": bool(on.value), "count": cnt.value, "total": tot.value}
+
     def offsets(self):
         """Offset-indexed column storage of this operator (b200_csr_offsets)."""
         on, cnt = _c.c_int(), _c.c_int()
@@ -542,6 +550,23 @@ class Csr:
                 self.h = _vp()      # (kept if the library refused, e.g. while a graph is recorded)
         except Exception:
             pass
+
+
+def pattern_plan(nrows, ncols, ptr, col):
+    """Host-only: the pattern-indexed row format b200_csr_create would build
+    (b200_pattern_plan_i64).  None when the operator has too many row patterns."""
+    ptr = np.ascontiguousarray(ptr, dtype=np.int64)
+    col = np.ascontiguousarray(col, dtype=np.int64)
+    pid = np.zeros(max(1, nrows), dtype=np.uint8)
+    start = np.zeros(257, dtype=np.uint16)
+    off = np.zeros(1024, dtype=np.int32)
+    cnt, tot, ok = _c.c_int(), _c.c_int(), _c.c_int()
+    _check(lib().b200_pattern_plan_i64(nrows, ncols, ptr.ctypes.data, col.ctypes.data, pid.ctypes.data,
+                                       start.ctypes.data, off.ctypes.data, _c.byref(cnt), _c.byref(tot),
+                                       _c.byref(ok)))
+    if not ok.value:
+        return None
+    return {"pid": pid[:nrows], "start": start, "off": off, "count": cnt.value, "total": tot.value}
 
 
 def offset_plan(nrows, ncols, ptr, col):

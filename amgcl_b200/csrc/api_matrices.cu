@@ -7,6 +7,7 @@
 #include "csr_launch.cuh"
 #include "window.cuh"
 #include "offsets.cuh"
+#include "patterns.cuh"
 
 namespace b200 {
 int tail_enqueue_csr(b200_ctx_t ctx, int mode, b200_csr_t A, const CsrArgsT<PrecDD> &a);   // api_tail.cu
@@ -188,9 +189,14 @@ static int csr_upload(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *p
     }
     blk4[(size_t)nblocks] = make_int4((int)nrows, (int)nrows, (int)nnz, (int)nnz);
 
+    // ---- pattern-indexed rows, where the operator qualifies (patterns.cuh) -------------------
+    PatternPlan patp;
+    const bool pattern_indexed = ctx->opt_patterns && nnz >= ctx->opt_patterns_min_nnz && nlong == 0 &&
+                                 lanes <= 4 && build_patterns(nrows, hptr.data(), col, patp);
+
     // ---- offset-indexed columns, where the operator qualifies (offsets.cuh) ------------------
     OffsetPlan offp;
-    const bool offset_indexed = ctx->opt_offsets && nnz >= ctx->opt_offsets_min_nnz && nlong == 0 && lanes <= 4 &&
+    const bool offset_indexed = !pattern_indexed && ctx->opt_offsets && nnz >= ctx->opt_offsets_min_nnz && nlong == 0 && lanes <= 4 &&
                                 build_offsets(nrows, hptr.data(), col, offp);
 
     // ---- windowed format, where the operator qualifies (window.cuh) ------------------------
@@ -199,7 +205,7 @@ static int csr_upload(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *p
     if (!offset_indexed && ctx->opt_window && nnz >= ctx->opt_window_min_nnz && nlong == 0 && lanes <= 8 &&
         ((ctx->opt_window_lanes >> (lanes == 1 ? 0 : lanes == 2 ? 1 : lanes == 4 ? 2 : 3)) & 1)) {
         // what the default launch configuration leaves for the window beside two stages
-        const StageLayout wl = stage_layout(rows_cap, nnz_cap, (int)sizeof(Val), kWinRunCapMax);
+        const StageLayout wl = stage_layout(rows_cap, nnz_cap, (int)sizeof(Val), FMT_WINDOW, kWinRunCapMax);
         const int budget = ring_budget(4) - kHeaderBytes - 2 * wl.bytes;
         const int slot_cap = std::min(8192, (budget / 8) & ~3);
         windowed = build_windows(blk4.data(), nblocks, hptr.data(), col, ncols, nnz, slot_cap, kWinRunCapMax,
@@ -228,6 +234,8 @@ static int csr_upload(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *p
     const size_t wbk_bytes = windowed ? ((size_t)nblocks + 1) * sizeof(int2) : 0;
     const size_t ix8_bytes = offset_indexed ? (((size_t)nnz + 32 + 15) & ~(size_t)15) : 0;
     const size_t tab_bytes = offset_indexed ? kOffTabLen * sizeof(int) : 0;
+    const size_t pid_bytes = pattern_indexed ? (((size_t)nrows + 32 + 15) & ~(size_t)15) : 0;
+    const size_t pat_bytes = pattern_indexed ? kPatOffCap * sizeof(int) + (kPatCap + 1 + 7) * sizeof(unsigned short) : 0;
     auto cleanup = [&]() {
         if (A->ptr) cudaFree(A->ptr);
         if (A->col) cudaFree(A->col);
@@ -238,6 +246,9 @@ static int csr_upload(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *p
         if (A->wblk) cudaFree(A->wblk);
         if (A->idx8) cudaFree(A->idx8);
         if (A->off_tab) cudaFree(A->off_tab);
+        if (A->pid) cudaFree(A->pid);
+        if (A->pat_start) cudaFree(A->pat_start);
+        if (A->pat_off) cudaFree(A->pat_off);
         delete A;
     };
 #define CSR_CUDA(call)                                                         \
@@ -283,10 +294,21 @@ static int csr_upload(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *p
         CSR_CUDA(staged_upload(ctx, A->off_tab, offp.tab, (size_t)kOffTabLen));
         A->off_count = offp.count;
     }
+    if (pattern_indexed) {
+        CSR_CUDA(cudaMalloc(&A->pid, pid_bytes));
+        CSR_CUDA(cudaMalloc(&A->pat_start, (kPatCap + 1 + 7) * sizeof(unsigned short)));
+        CSR_CUDA(cudaMalloc(&A->pat_off, kPatOffCap * sizeof(int)));
+        CSR_CUDA(cudaMemsetAsync(A->pid, 0, pid_bytes, ctx->stream));
+        CSR_CUDA(staged_upload(ctx, A->pid, patp.pid.data(), (size_t)nrows));
+        CSR_CUDA(staged_upload(ctx, A->pat_start, patp.start.data(), (size_t)kPatCap + 1));
+        CSR_CUDA(staged_upload(ctx, A->pat_off, patp.off.data(), (size_t)kPatOffCap));
+        A->pat_count = patp.count;
+        A->pat_total = patp.total;
+    }
     CSR_CUDA(cudaStreamSynchronize(ctx->stream));   // host staging buffers die here
 #undef CSR_CUDA
     A->bytes = ptr_bytes + col_bytes + val_bytes + blk_bytes + c16_bytes + run_bytes + wbk_bytes + ix8_bytes +
-               tab_bytes;
+               tab_bytes + pid_bytes + pat_bytes;
     *out = A;
     if (halo_from < 0 && !windowed && ctx->opt_warm_lines && lanes >= 2 && A->dtype == B200_F64 && nblocks > 0 &&
         (ctx->opt_warm_lines > 1 || nnz >= 1000000)) {
@@ -342,6 +364,9 @@ static void csr_free(b200_csr_t A) {
     if (A->wblk) cudaFree(A->wblk);
     if (A->idx8) cudaFree(A->idx8);
     if (A->off_tab) cudaFree(A->off_tab);
+    if (A->pid) cudaFree(A->pid);
+    if (A->pat_start) cudaFree(A->pat_start);
+    if (A->pat_off) cudaFree(A->pat_off);
     if (A->send_idx) cudaFree(A->send_idx);
     if (A->halo_owned) cudaFree(A->halo_owned);
     if (A->ybuf) cudaFree(A->ybuf);
@@ -475,6 +500,12 @@ static int launch_csr_LH(b200_ctx_t ctx, b200_csr_t A, const CsrArgsT<P> &args) 
         bool done = false;
         const int fmt = launch_format<P>(ctx, A);
         if constexpr (L <= 4) {
+            if (fmt == FMT_PATTERN) {
+                rc = launch_ring_pat<MODE, L, HALO, P>(ctx, A, args);
+                done = true;
+            }
+        }
+        if constexpr (L <= 4) {
             if (fmt == FMT_OFFSET) {
                 rc = launch_ring_off<MODE, L, HALO, P>(ctx, A, args);
                 done = true;
@@ -537,6 +568,7 @@ static CsrArgsT<P> base_args_t(b200_csr_t A) {
     if (std::is_same<P, PrecDD>::value && A->ctx->opt_warm_lines) { a.wl_ptr = A->wl_ptr; a.wl = A->wl; }
     a.col16 = A->col16; a.wrun = A->wrun; a.wblk = A->wblk; a.run_cap = A->win_runs;
     a.idx8 = A->idx8; a.off_tab = A->off_tab;
+    a.pid = A->pid; a.pat_start = A->pat_start; a.pat_off = A->pat_off; a.pat_total = A->pat_total;
     return a;
 }
 static CsrArgs base_args(b200_csr_t A) { return base_args_t<PrecDD>(A); }
@@ -686,6 +718,35 @@ extern "C" int b200_offset_plan_i64(int64_t nrows, int64_t ncols, const int64_t 
     if (!ok) return B200_OK;
     if (idx8_out) std::copy(o.idx8.begin(), o.idx8.end(), idx8_out);
     if (tab_out) std::copy(o.tab, o.tab + kOffTabLen, tab_out);
+    return B200_OK;
+}
+
+// The pattern-indexed format of a host matrix (patterns.cuh), for tests.
+extern "C" int b200_pattern_plan_i64(int64_t nrows, int64_t ncols, const int64_t *ptr, const int64_t *col,
+                                     uint8_t *pid_out, uint16_t *start_out, int32_t *off_out, int *count,
+                                     int *total, int *qualifies) {
+    B200_REQUIRE(nrows >= 0 && ncols >= 0 && ptr && qualifies, "bad argument");
+    int rc = csr_validate(nrows, ncols, ptr, col, true);
+    if (rc) return rc;
+    std::vector<int32_t> hptr((size_t)nrows + 1);
+    for (int64_t i = 0; i <= nrows; ++i) hptr[(size_t)i] = (int32_t)ptr[i];
+    PatternPlan o;
+    const bool ok = build_patterns(nrows, hptr.data(), col, o);
+    *qualifies = ok ? 1 : 0;
+    if (count) *count = ok ? o.count : 0;
+    if (total) *total = ok ? o.total : 0;
+    if (!ok) return B200_OK;
+    if (pid_out) std::copy(o.pid.begin(), o.pid.end(), pid_out);
+    if (start_out) std::copy(o.start.begin(), o.start.end(), start_out);
+    if (off_out) std::copy(o.off.begin(), o.off.end(), off_out);
+    return B200_OK;
+}
+
+extern "C" int b200_csr_patterns(b200_csr_t A, int *pattern_indexed, int *count, int *total) {
+    B200_REQUIRE(A, "null argument");
+    if (pattern_indexed) *pattern_indexed = A->pid ? 1 : 0;
+    if (count) *count = A->pat_count;
+    if (total) *total = A->pat_total;
     return B200_OK;
 }
 

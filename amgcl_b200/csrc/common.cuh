@@ -157,6 +157,8 @@ struct b200_ctx_s {
     int64_t opt_tail_max_nnz  = 1500000;  // ... "small": at most this many non-zeros
     int64_t opt_tail_max_vec  = 262144;   // ... element-wise x = 0 sweeps: at most this many entries
     int64_t opt_poll_scalars  = 1;        // host reads in-kernel reduction results by polling mapped memory
+    int64_t opt_patterns      = 1;        // operators with <= 256 distinct row patterns: no per-entry columns
+    int64_t opt_patterns_min_nnz = 1000000;// ... from this many non-zeros on (decided at upload)
     int64_t opt_offsets       = 1;        // operators with <= 256 distinct (col - row): 8-bit column indices
     int64_t opt_offsets_min_nnz = 1000000;// ... from this many non-zeros on (decided at upload)
     int64_t opt_window        = 0;        // operators that qualify gather x through shared-memory windows
@@ -268,6 +270,11 @@ struct b200_csr_s {
     unsigned char *idx8 = nullptr;    // [nnz] (+ padding)
     int       *off_tab  = nullptr;    // [256] device
     int        off_count = 0;         // distinct (col - row) offsets
+    // pattern-indexed rows (csr_kernels.cuh): col of the k-th entry of row r = r + pat_off[pat_start[pid[r]] + k]
+    unsigned char  *pid       = nullptr;  // [nrows] (+ padding)
+    unsigned short *pat_start = nullptr;  // [257] device
+    int            *pat_off   = nullptr;  // [1024] device
+    int        pat_count = 0, pat_total = 0;
     int4      *blk      = nullptr;// [nblocks] device, walk order: {first row (~r if the block gathers halo
                                   //   columns), end row, first nnz, end nnz}; HALO: interior blocks first
     size_t     bytes    = 0;

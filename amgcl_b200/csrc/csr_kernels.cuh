@@ -44,6 +44,14 @@
 // as row + table[index] from shared memory.  Entry order and arithmetic are those of the plain
 // path: bit-identical results (tests/test_gpu_offsets.py).
 //
+// Pattern-indexed rows (FMT_PATTERN).  On such a matrix whole ROWS repeat: the tuple of offsets
+// (col - row of every entry, in entry order) of a row is one of a few patterns (27 for the
+// Poisson problem: interior + boundary combinations).  With at most 256 patterns the upload
+// stores one byte per ROW and no column information per entry at all: the kernel streams the
+// values (8 or 4 bytes per entry), the row pointers and the pattern ids, and rebuilds
+// col = row + pattern[k] for the k-th entry of the row from a table in shared memory -- one
+// shared-memory load per entry, as many as the plain path needs for its staged column.
+//
 // Precision.  Every kernel is a template over the element types of the matrix
 // values, the gathered vector, the right-hand side, the output and the smoother
 // diagonal (struct Prec).  FP64 throughout is the default; the other
@@ -61,7 +69,8 @@ namespace b200 {
 // storage format of the column indices the kernel streams
 enum { FMT_PLAIN = 0,     // int32 column per entry
        FMT_WINDOW = 1,    // 16-bit position in the block's shared-memory window of x
-       FMT_OFFSET = 2 };  // 8-bit index into a table of (col - row) offsets
+       FMT_OFFSET = 2,    // 8-bit index into a table of (col - row) offsets
+       FMT_PATTERN = 3 }; // no per-entry column: 8-bit pattern id per row, col = row + pattern[k]
 
 enum { MODE_SPMV = 0, MODE_SPMV_ACC = 1, MODE_RESID = 2, MODE_RELAX = 3,
        // y = f - A x with x = (alpha*d).*f formed on the fly and written to xw: the smoother's
@@ -142,6 +151,12 @@ struct CsrArgsT {
     // Offset-indexed operators: index of every entry's (col - row) in off_tab[256]
     const unsigned char *idx8;
     const int    *off_tab;
+    // Pattern-indexed operators: pattern id of every row, first table entry of every pattern
+    // ([257]), and the table of offsets itself
+    const unsigned char  *pid;
+    const unsigned short *pat_start;
+    const int    *pat_off;
+    int           pat_total;   // entries of pat_off in use (<= kPatOffCap)
     typename P::TY       *y;      // output
     typename P::TX       *xw;     // RESID_SCALED: where x = (alpha*d).*f is written
     const typename P::TF *f;      // rhs          (RESID, RELAX)
@@ -159,37 +174,41 @@ typedef CsrArgsT<PrecDD> CsrArgs;
 
 // ---- shared memory layout of one stage --------------------------------------
 struct StageLayout {
-    int val_off, col_off, ptr_off, run_off, bytes;
+    int val_off, col_off, ptr_off, run_off, pid_off, bytes;
 };
-// run_cap == 0: plain operator (int32 columns); > 0: windowed (16-bit columns + the block's runs);
-// < 0: offset-indexed (8-bit columns)
-__host__ __device__ inline StageLayout stage_layout(int rows_cap, int nnz_cap, int val_size, int run_cap = 0) {
+// fmt: storage format of the columns (FMT_*); run_cap: FMT_WINDOW only, most runs a block has
+__host__ __device__ inline StageLayout stage_layout(int rows_cap, int nnz_cap, int val_size,
+                                                    int fmt = FMT_PLAIN, int run_cap = 0) {
     StageLayout s;
     s.val_off = 0;
     int val_bytes = nnz_cap * val_size + 16;       // source aligned down to 16 B
     val_bytes = (val_bytes + 15) & ~15;
     s.col_off = s.val_off + val_bytes;
-    int col_bytes = run_cap > 0 ? (nnz_cap + 16) * 2   // +7 align down, +7 round up
-                  : run_cap < 0 ? (nnz_cap + 32)   // +15 align down, +15 round up
-                                : (nnz_cap + 8) * 4;   // +3 align down, +3 round up
+    int col_bytes = fmt == FMT_WINDOW  ? (nnz_cap + 16) * 2   // +7 align down, +7 round up
+                  : fmt == FMT_OFFSET  ? (nnz_cap + 32)       // +15 align down, +15 round up
+                  : fmt == FMT_PATTERN ? 0
+                                       : (nnz_cap + 8) * 4;   // +3 align down, +3 round up
     col_bytes = (col_bytes + 15) & ~15;
     s.ptr_off = s.col_off + col_bytes;
     int ptr_bytes = (rows_cap + 4) * 4;
     ptr_bytes = (ptr_bytes + 15) & ~15;
     s.run_off = s.ptr_off + ptr_bytes;
-    int run_bytes = run_cap > 0 ? (run_cap + 2) * 8 : 0;   // +1 align down, +1 round up
+    int run_bytes = fmt == FMT_WINDOW ? (run_cap + 2) * 8 : 0;   // +1 align down, +1 round up
     run_bytes = (run_bytes + 15) & ~15;
-    s.bytes = s.run_off + run_bytes;
+    s.pid_off = s.run_off + run_bytes;
+    int pid_bytes = fmt == FMT_PATTERN ? rows_cap + 32 : 0;      // +15 align down, +15 round up
+    pid_bytes = (pid_bytes + 15) & ~15;
+    s.bytes = s.pid_off + pid_bytes;
     return s;
 }
 constexpr int kMaxStages   = 8;
 constexpr int kHeaderBytes = 384;   // mbarriers [0,64) + reduction scratch [64,128) + descriptors [128,384)
 constexpr int kWinRunLen   = 64;    // longest run of a window (longer ones are cut at upload)
 constexpr int kOffTabLen   = 256;   // offset-indexed operators: entries of the (col - row) table
-// what stage_layout wants as run_cap for a launch of format FMT
-template <int FMT, class A> __host__ __device__ inline int layout_key(const A &a) {
-    return FMT == FMT_WINDOW ? a.run_cap : FMT == FMT_OFFSET ? -1 : 0;
-}
+constexpr int kPatCap      = 256;   // pattern-indexed operators: most row patterns ...
+constexpr int kPatOffCap   = 1024;  // ... and most offsets in all patterns together
+// shared memory behind the stages: the window of x / the offset table / the pattern tables
+constexpr int kPatTabBytes = kPatOffCap * 4 + ((kPatCap + 1) * 2 + 15) / 16 * 16;
 
 struct BlockDesc {      // written by the producer thread, read by everyone after the wait
     int r0, r1;         // row range
@@ -224,6 +243,20 @@ __device__ __forceinline__ bool issue_block(const CsrArgsT<P> &a, const BlockDes
     typedef typename P::TV TV;
     constexpr int VA = 16 / (int)sizeof(TV);        // values per 16 bytes
     const int nnz = d.e1 - d.e0;
+    if (FMT == FMT_PATTERN) {
+        // (a pattern-indexed operator has no long blocks)
+        const int a0 = d.e0 & ~(VA - 1);
+        const int nval = ((d.e1 - a0) + VA - 1) & ~(VA - 1);
+        const int nptr = ((d.r1 - d.r0 + 1) + 3) & ~3;
+        const int p0 = d.r0 & ~15;                  // pattern ids: 16 per 16 bytes
+        const int npid = ((d.r1 - p0) + 15) & ~15;
+        const uint32_t bytes = nval * (int)sizeof(TV) + nptr * 4 + npid;
+        ptx::mbar_expect_tx(bar, bytes);
+        if (nval) ptx::bulk_g2s(stage + lay.val_off, a.val + a0, nval * (int)sizeof(TV), bar, policy);
+        ptx::bulk_g2s(stage + lay.ptr_off, a.ptr + d.r0, nptr * 4, bar, policy);
+        ptx::bulk_g2s(stage + lay.pid_off, a.pid + p0, npid, bar, policy);
+        return true;
+    }
     if (FMT == FMT_OFFSET) {
         // (an offset-indexed operator has no long blocks)
         const int a0 = d.e0 & ~(VA - 1);
@@ -400,19 +433,23 @@ __device__ __forceinline__ void fill_window(const CsrArgsT<P> &a, const BlockDes
 
 // ---- reduce the rows of a staged block out of shared memory ---------------------
 // FMT_WINDOW: x comes from the block's window, `win`, indexed by the 16-bit columns;
-// FMT_OFFSET: the column of an entry of row r is r + off[8-bit index]
+// FMT_OFFSET: the column of an entry of row r is r + off[8-bit index];
+// FMT_PATTERN: the column of the k-th entry of row r is r + off[pstart[pattern id of r] + k]
 template <int MODE, int L, bool HALO, class P, int FMT = FMT_PLAIN>
 __device__ __forceinline__ void compute_staged(const CsrArgsT<P> &a, const BlockDesc &d,
                                                const char *stage, const StageLayout &lay, RowAcc &acc,
-                                               const typename P::TX *win = nullptr, const int *off = nullptr) {
+                                               const typename P::TX *win = nullptr, const int *off = nullptr,
+                                               const unsigned short *pstart = nullptr) {
     constexpr bool WIN = FMT == FMT_WINDOW;
     constexpr bool OFF = FMT == FMT_OFFSET;
+    constexpr bool PAT = FMT == FMT_PATTERN;
     typedef typename P::TV TV;
     typedef typename P::TX TX;
     typedef typename P::TY TS;                       // row sums live in the output's type
     typedef typename std::conditional<WIN, unsigned short,
                                       typename std::conditional<OFF, unsigned char, int>::type>::type CI;
-    static_assert(!((WIN || OFF) && L >= 16), "windowed / offset-indexed operators use at most 8 lanes per row");
+    static_assert(!((WIN || OFF || PAT) && L >= 16), "compressed column formats use at most 8 lanes per row");
+    const unsigned char *pid_s = reinterpret_cast<const unsigned char *>(stage + lay.pid_off) + (d.r0 & 15);
     constexpr int VA = 16 / (int)sizeof(TV);
     const TV *val_s = reinterpret_cast<const TV *>(stage + lay.val_off);
     const CI     *col_s = reinterpret_cast<const CI *>(stage + lay.col_off);
@@ -480,6 +517,9 @@ __device__ __forceinline__ void compute_staged(const CsrArgsT<P> &a, const Block
         if (valid) {
             const int beg = ptr_s[rr];
             const int end = ptr_s[rr + 1];
+            // PAT: the row's pattern starts at off[pb + beg], so entry e sits at off[pb + e]
+            int pb = 0;
+            if (PAT) pb = (int)pstart[pid_s[rr]] - beg;
             // U independent gathers in flight per lane, then the FMAs in entry order
             constexpr int U = kGatherBatch;
             for (int e = beg + lane; e < end; e += U * L) {
@@ -491,7 +531,8 @@ __device__ __forceinline__ void compute_staged(const CsrArgsT<P> &a, const Block
                 for (int u = 0; u < U; ++u) {
                     const int eu = e + u * L;
                     p[u] = eu < end;
-                    c[u] = p[u] ? col_s[eu - co] : col_s[e - co];
+                    if (PAT) c[u] = d.r0 + rr + off[pb + (p[u] ? eu : e)];
+                    else c[u] = p[u] ? col_s[eu - co] : col_s[e - co];
                     v[u] = p[u] ? val_s[eu - vo] : (TV)0;
                 }
                 if (OFF) {
@@ -626,12 +667,13 @@ __global__ void __launch_bounds__(kThreads, 2) csr_ring_kernel(const CsrArgsT<P>
     uint64_t  *bars  = reinterpret_cast<uint64_t *>(smem);                 // [<=8]
     double    *red_s = reinterpret_cast<double *>(smem + 64);              // [8]
     BlockDesc *descs = reinterpret_cast<BlockDesc *>(smem + 128);          // [<=8]
-    const StageLayout lay = stage_layout(a.rows_cap, a.nnz_cap, (int)sizeof(typename P::TV),
-                                         layout_key<FMT>(a));
+    const StageLayout lay = stage_layout(a.rows_cap, a.nnz_cap, (int)sizeof(typename P::TV), FMT, a.run_cap);
     char *stages = smem + kHeaderBytes;
-    // behind the stages: the window of x (FMT_WINDOW) or the offset table (FMT_OFFSET)
+    // behind the stages: the window of x (FMT_WINDOW), the offset table (FMT_OFFSET), or the
+    // patterns' offsets followed by the patterns' first entries (FMT_PATTERN)
     typename P::TX *win = reinterpret_cast<typename P::TX *>(stages + (size_t)nstages * lay.bytes);
     int *off_s = reinterpret_cast<int *>(stages + (size_t)nstages * lay.bytes);
+    unsigned short *pstart_s = reinterpret_cast<unsigned short *>(off_s + kPatOffCap);
 
     const int first = blockIdx.x;
     const int step  = gridDim.x;
@@ -655,6 +697,10 @@ __global__ void __launch_bounds__(kThreads, 2) csr_ring_kernel(const CsrArgsT<P>
         static_assert(kOffTabLen == kThreads, "one table entry per thread");
         off_s[threadIdx.x] = __ldg(a.off_tab + threadIdx.x);
     }
+    if constexpr (FMT == FMT_PATTERN) {
+        for (int i = threadIdx.x; i < a.pat_total; i += kThreads) off_s[i] = __ldg(a.pat_off + i);
+        for (int i = threadIdx.x; i <= kPatCap; i += kThreads) pstart_s[i] = __ldg(a.pat_start + i);
+    }
     __syncthreads();
     ptx::pdl_wait();         // vectors (x, f, d, y) come from earlier kernels: from here on
     if (HALO) halo_push(a);  // multi-GPU: my boundary values go out before anything else
@@ -672,6 +718,9 @@ __global__ void __launch_bounds__(kThreads, 2) csr_ring_kernel(const CsrArgsT<P>
         } else if constexpr (FMT == FMT_OFFSET) {
             compute_staged<MODE, (L < 16 ? L : 8), HALO, P, FMT_OFFSET>(a, d, stages + (size_t)s * lay.bytes, lay,
                                                                            acc, nullptr, off_s);
+        } else if constexpr (FMT == FMT_PATTERN) {
+            compute_staged<MODE, (L < 16 ? L : 8), HALO, P, FMT_PATTERN>(a, d, stages + (size_t)s * lay.bytes, lay,
+                                                                            acc, nullptr, off_s, pstart_s);
         } else {
             if (!HALO) warm_lines(a, first + i * step);
             if ((d.e1 - d.e0) <= a.nnz_cap)

@@ -1,6 +1,6 @@
 // csr_launch.cuh -- launching the persistent ring kernel (csr_kernels.cuh).  Shared by
-// api_matrices.cu (plain operators), api_window.cu (windowed operators) and api_offsets.cu
-// (offset-indexed operators): the kernel instantiations of each storage format are compiled in
+// api_matrices.cu (plain operators), api_window.cu (windowed operators), api_offsets.cu
+// (offset-indexed operators) and api_patterns.cu (pattern-indexed operators): the kernel instantiations of each storage format are compiled in
 // a translation unit of their own so the build stays parallel.
 #pragma once
 #include "internal.cuh"
@@ -17,10 +17,10 @@ inline int ring_budget(int ctas) { return 228 * 1024 / ctas - 1024 - 1536; }
 // windowed launch does not fit even with one stage.
 template <class P>
 inline int ring_smem(b200_ctx_t ctx, b200_csr_t A, int fmt, int *stages_out) {
-    const StageLayout lay = stage_layout(A->rows_cap, A->nnz_cap, (int)sizeof(typename P::TV),
-                                         fmt == FMT_WINDOW ? A->win_runs : fmt == FMT_OFFSET ? -1 : 0);
+    const StageLayout lay = stage_layout(A->rows_cap, A->nnz_cap, (int)sizeof(typename P::TV), fmt, A->win_runs);
     const int extra = fmt == FMT_WINDOW ? (int)(((size_t)A->win_slots * sizeof(typename P::TX) + 15) & ~(size_t)15)
-                      : fmt == FMT_OFFSET ? kOffTabLen * (int)sizeof(int) : 0;
+                      : fmt == FMT_OFFSET ? kOffTabLen * (int)sizeof(int)
+                      : fmt == FMT_PATTERN ? kPatTabBytes : 0;
     int stages = (int)ctx->opt_stages;
     const int per_cta_budget = ring_budget((int)ctx->opt_ctas_per_sm);
     while (stages > 1 && kHeaderBytes + stages * lay.bytes + extra > per_cta_budget) --stages;
@@ -57,11 +57,15 @@ int launch_ring_win(b200_ctx_t ctx, b200_csr_t A, const CsrArgsT<P> &args);
 // offset-indexed operators (defined and instantiated in api_offsets.cu: 1..4 lanes per row)
 template <int MODE, int L, bool HALO, class P>
 int launch_ring_off(b200_ctx_t ctx, b200_csr_t A, const CsrArgsT<P> &args);
+// pattern-indexed operators (defined and instantiated in api_patterns.cu: 1..4 lanes per row)
+template <int MODE, int L, bool HALO, class P>
+int launch_ring_pat(b200_ctx_t ctx, b200_csr_t A, const CsrArgsT<P> &args);
 
 // which storage format does this launch stream?
 template <class P>
 inline int launch_format(b200_ctx_t ctx, b200_csr_t A) {
     if (ctx->opt_spmv_variant != 1) return FMT_PLAIN;
+    if (A->pid && ctx->opt_patterns && A->lanes <= 4) return FMT_PATTERN;
     if (A->idx8 && ctx->opt_offsets && A->lanes <= 4) return FMT_OFFSET;
     if (A->col16 && ctx->opt_window && A->lanes <= 8 && A->win_runs >= 1) {
         int stages;

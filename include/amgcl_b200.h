@@ -271,6 +271,21 @@ int b200_plan_i64(int64_t nrows, const int64_t *ptr, int lanes, int nnz_cap,
                   int32_t *blk_out, int64_t blk_capacity, int64_t *nblocks,
                   int *lanes_out, int *rows_cap_out, int64_t *nlong_out);
 
+/* Pattern-indexed rows.  In a matrix assembled on a structured grid whole rows repeat: the
+ * tuple (col - row of every entry, in entry order) of a row is one of a few patterns (27 for
+ * the 7-point Poisson problem).  With at most 256 patterns (1024 offsets in all) the upload
+ * also stores one byte per ROW, and the streaming kernel reads no column information per
+ * entry at all (8 instead of 12 bytes per FP64 entry), rebuilding col = row + pattern[k] from
+ * a table in shared memory; same entry order and arithmetic, same bits (options "patterns",
+ * "patterns_min_nnz"; decided at upload; preferred over offset-indexed columns).
+ * b200_csr_patterns: whether A carries the format, its patterns and their total length.
+ * b200_pattern_plan_i64: pure host helper for tests (pid_out [nrows], start_out [257],
+ * off_out [1024]). */
+int b200_csr_patterns(b200_csr_t A, int *pattern_indexed, int *count, int *total);
+int b200_pattern_plan_i64(int64_t nrows, int64_t ncols, const int64_t *ptr, const int64_t *col,
+                          uint8_t *pid_out, uint16_t *start_out, int32_t *off_out, int *count,
+                          int *total, int *qualifies);
+
 /* Offset-indexed columns.  If col - row takes at most 256 distinct values over the whole
  * operator (matrices assembled on structured grids: 7 for the Poisson stencil), the upload
  * also stores one byte per entry -- the index of its offset in a table -- and the streaming

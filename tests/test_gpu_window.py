@@ -18,12 +18,14 @@ def wctx(ctx):
     """Every operator that qualifies is windowed, whatever its size."""
     ctx.set_option("window_min_nnz", 0)
     ctx.set_option("window", 1)
-    ctx.set_option("offsets", 0)          # (an operator that qualifies for both is offset-indexed)
+    ctx.set_option("offsets", 0)          # (an operator that also qualifies for a compressed
+    ctx.set_option("patterns", 0)         #  column format is stored that way)
     yield ctx
     ctx.set_option("window_min_nnz", 1000000)
     ctx.set_option("window_ratio", 75)
     ctx.set_option("window", 0)
     ctx.set_option("offsets", 1)
+    ctx.set_option("patterns", 1)
     ctx.set_option("lanes", 0)
 
 

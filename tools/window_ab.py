@@ -18,14 +18,17 @@ sys.path.insert(0, ROOT)
 import amgcl_b200 as ab  # noqa: E402
 
 CONFIGS = [
-    ("plain", {"window": 0, "offsets": 0}),
-    ("offsets", {"window": 0, "offsets": 1}),
+    ("plain", {"window": 0, "offsets": 0, "patterns": 0}),
+    ("offsets", {"window": 0, "offsets": 1, "patterns": 0}),
+    ("patterns", {"window": 0, "offsets": 0, "patterns": 1}),
+    ("patterns, nnz_cap 2560", {"window": 0, "offsets": 0, "patterns": 1, "nnz_cap": 2560}),
+    ("patterns, 3 stages", {"window": 0, "offsets": 0, "patterns": 1, "stages": 3}),
     ("offsets, 3 CTAs x 3 stages", {"window": 0, "offsets": 1, "ctas_per_sm": 3, "stages": 3}),
     ("offsets, nnz_cap 3584 x 3 CTAs", {"window": 0, "offsets": 1, "nnz_cap": 3584, "ctas_per_sm": 3}),
     ("offsets, 5 CTAs", {"window": 0, "offsets": 1, "ctas_per_sm": 5}),
-    ("window all", {"offsets": 0, "window": 1, "window_ratio": 75, "window_lanes": 15}),
-    ("window P only", {"offsets": 0, "window": 1, "window_ratio": 50, "window_lanes": 15}),
-    ("window +A1", {"offsets": 0, "window": 1, "window_ratio": 125, "window_lanes": 15, "window_gap": 1}),
+    ("window all", {"offsets": 0, "patterns": 0, "window": 1, "window_ratio": 75, "window_lanes": 15}),
+    ("window P only", {"offsets": 0, "patterns": 0, "window": 1, "window_ratio": 50, "window_lanes": 15}),
+    ("window +A1", {"offsets": 0, "patterns": 0, "window": 1, "window_ratio": 125, "window_lanes": 15, "window_gap": 1}),
 ]
 
 
