@@ -311,28 +311,51 @@ __device__ __forceinline__ bool issue_block(const CsrArgsT<P> &a, const BlockDes
 // acc: the thread's running contributions to the launch's scalars (reduce.cuh)
 struct RowAcc { double s0, s1; };
 
+// what the epilogue of a row reads besides the row sum; loaded BEFORE the row's gathers are
+// issued so that it arrives with them (one memory round per row instead of two)
+template <class P>
+struct RowOps {
+    typename P::TF f;     // rhs           (RESID, RESID_SCALED, RELAX)
+    typename P::TD d;     // diagonal      (RESID_SCALED, RELAX)
+    typename P::TX x;     // old iterate   (RELAX)
+    typename P::TY y;     // old output    (SPMV_ACC)
+    double         w;     // dot weight    (ndot with w)
+};
 template <int MODE, class P>
-__device__ __forceinline__ void store_row(const CsrArgsT<P> &a, int r, typename P::TY sum, RowAcc &acc) {
+__device__ __forceinline__ RowOps<P> load_row_ops(const CsrArgsT<P> &a, int r) {
+    RowOps<P> o;
+    o.f = 0; o.d = 0; o.x = 0; o.y = 0; o.w = 0.0;
+    if (MODE == MODE_SPMV_ACC) o.y = a.y[r];
+    if (MODE == MODE_RESID || MODE == MODE_RESID_SCALED || MODE == MODE_RELAX) o.f = a.f[r];
+    if (MODE == MODE_RESID_SCALED || MODE == MODE_RELAX) o.d = a.d[r];
+    if (MODE == MODE_RELAX) o.x = a.x[r];
+    if (a.ndot && a.w) o.w = a.w[r];
+    return o;
+}
+
+template <int MODE, class P>
+__device__ __forceinline__ void store_row(const CsrArgsT<P> &a, int r, typename P::TY sum, RowAcc &acc,
+                                          const RowOps<P> &o) {
     typedef typename P::TY TY;
     TY out;
     double wv = 0.0;
     if (MODE == MODE_SPMV) {
         out = (TY)(a.alpha * sum);
     } else if (MODE == MODE_SPMV_ACC) {
-        out = (TY)(a.alpha * sum + a.beta * a.y[r]);
+        out = (TY)(a.alpha * sum + a.beta * o.y);
     } else if (MODE == MODE_RESID) {
-        out = (TY)(a.f[r] - sum);
+        out = (TY)(o.f - sum);
     } else if (MODE == MODE_RESID_SCALED) {
-        const typename P::TF fr = a.f[r];
+        const typename P::TF fr = o.f;
         out = (TY)(fr - sum);
-        a.xw[r] = fma((typename P::TX)(a.alpha * a.d[r]), (typename P::TX)fr, (typename P::TX)0);
+        a.xw[r] = fma((typename P::TX)(a.alpha * o.d), (typename P::TX)fr, (typename P::TX)0);
     } else {
         // x_new = (omega*d)*t + x with t = f - A x; same association as the
         // reference's vmul  z = a*x*y + b*z  (builtin.hpp:1238-1265)
-        const typename P::TF fr = a.f[r];
+        const typename P::TF fr = o.f;
         const TY t = (TY)(fr - sum);
-        const TY w = (TY)(a.alpha * a.d[r]);
-        out = fma(w, t, (TY)a.x[r]);
+        const TY w = (TY)(a.alpha * o.d);
+        out = fma(w, t, (TY)o.x);
         wv = (double)fr;
     }
     a.y[r] = out;
@@ -343,11 +366,16 @@ __device__ __forceinline__ void store_row(const CsrArgsT<P> &a, int r, typename 
     }
     if (a.ndot) {
         const double yv = (double)out;
-        if (a.w) wv = a.w[r];
+        if (a.w) wv = o.w;
         else if (MODE != MODE_RELAX) wv = yv;
         acc.s0 = fma(yv, wv, acc.s0);
         if (a.ndot > 1) acc.s1 = fma(yv, yv, acc.s1);
     }
+}
+// (operands loaded on the spot: the paths that do not overlap them with the gathers)
+template <int MODE, class P>
+__device__ __forceinline__ void store_row(const CsrArgsT<P> &a, int r, typename P::TY sum, RowAcc &acc) {
+    store_row<MODE>(a, r, sum, acc, load_row_ops<MODE>(a, r));
 }
 
 // ---- x[col]: local columns from the vector, remote ones from the all-gathered halo --
@@ -514,17 +542,21 @@ __device__ __forceinline__ void compute_staged(const CsrArgsT<P> &a, const Block
         const int  rr    = base + g;
         const bool valid = rr < nr;
         TS sum = 0;
+        RowOps<P> ops;
+        ops.f = 0; ops.d = 0; ops.x = 0; ops.y = 0; ops.w = 0.0;
         if (valid) {
+            // the epilogue's operands travel with the row's gathers
+            if (lane == 0) ops = load_row_ops<MODE>(a, d.r0 + rr);
             const int beg = ptr_s[rr];
             const int end = ptr_s[rr + 1];
             // PAT: the row's pattern starts at off[pb + beg], so entry e sits at off[pb + e]
             int pb = 0;
             if (PAT) pb = (int)pstart[pid_s[rr]] - beg;
-            // U independent gathers in flight per lane, then the FMAs in entry order
-            constexpr int U = kGatherBatch;
+            // U independent gathers in flight per lane, then the FMAs in entry order (one lane per
+            // row: short rows, a whole row of up to 8 entries goes out in one round)
+            constexpr int U = (L == 1) ? 2 * kGatherBatch : kGatherBatch;
             for (int e = beg + lane; e < end; e += U * L) {
                 int  c[U];
-                TV   v[U];
                 TX   xv[U];
                 bool p[U];
 #pragma unroll
@@ -533,24 +565,26 @@ __device__ __forceinline__ void compute_staged(const CsrArgsT<P> &a, const Block
                     p[u] = eu < end;
                     if (PAT) c[u] = d.r0 + rr + off[pb + (p[u] ? eu : e)];
                     else c[u] = p[u] ? col_s[eu - co] : col_s[e - co];
-                    v[u] = p[u] ? val_s[eu - vo] : (TV)0;
                 }
                 if (OFF) {
 #pragma unroll
                     for (int u = 0; u < U; ++u) c[u] = d.r0 + rr + off[c[u]];
                 }
 #pragma unroll
-                for (int u = 0; u < U; ++u) xv[u] = WIN ? win[c[u]] : gather_m<MODE, HALO>(a, x, c[u]);
+                for (int u = 0; u < U; ++u)
+                    xv[u] = !p[u] ? (TX)0 : WIN ? win[c[u]] : gather_m<MODE, HALO>(a, x, c[u]);
+                // (the values come from shared memory when they are needed: no registers held
+                //  across the gathers)
 #pragma unroll
                 for (int u = 0; u < U; ++u)
-                    if (p[u]) sum = fma((TS)v[u], (TS)xv[u], sum);
+                    if (p[u]) sum = fma((TS)val_s[e + u * L - vo], (TS)xv[u], sum);
             }
         }
         if (L > 1) {
 #pragma unroll
             for (int o = L / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
         }
-        if (valid && lane == 0) store_row<MODE>(a, d.r0 + rr, sum, acc);
+        if (valid && lane == 0) store_row<MODE>(a, d.r0 + rr, sum, acc, ops);
     }
 }
 
@@ -662,7 +696,7 @@ __global__ void __launch_bounds__(kThreads, 4) csr_block_kernel(const CsrArgsT<P
 // ---- variant 1: persistent CTAs, S-deep ring of stages ----------------------------------
 // FMT: storage format of the columns (FMT_PLAIN / FMT_WINDOW / FMT_OFFSET, see the top of the file)
 template <int MODE, int L, bool HALO, class P, int FMT = FMT_PLAIN>
-__global__ void __launch_bounds__(kThreads, 2) csr_ring_kernel(const CsrArgsT<P> a, const int nstages) {
+__global__ void __launch_bounds__(kThreads, 4) csr_ring_kernel(const CsrArgsT<P> a, const int nstages) {
     extern __shared__ __align__(128) char smem[];
     uint64_t  *bars  = reinterpret_cast<uint64_t *>(smem);                 // [<=8]
     double    *red_s = reinterpret_cast<double *>(smem + 64);              // [8]

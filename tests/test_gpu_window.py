@@ -106,17 +106,16 @@ def test_windowed_kernels_give_the_bits_of_the_plain_ones(wctx, per_row, lanes, 
         assert rel_err(sweep(False)[:nr], x1) < 1e-12
 
         # the streaming pass that also leaves scalars behind (CG: q = A p with <q, p>)
-        K = ab.Krylov(ctx, nr)
-
         def step():
+            K = ab.Krylov(ctx, nr)                    # (fresh scalars: no history from the other run)
             vp, vq, vxx, vr = ctx.vector(x), ctx.vector(nr), ctx.vector(y), ctx.vector(f)
             K.cg_direction(vf, vf, vp)
             K.cg_step(A, vp, vq, vxx, vr)
             s = K.scalars()
+            K.close()
             return np.concatenate([vq.numpy(), vxx.numpy(), vr.numpy(), [s["qp"], s["alpha"], s["rr"]]])
         a, b = both(ctx, step)
         assert np.array_equal(a, b)
-        K.close()
 
 
 def test_windowed_mixed_precision_combinations(wctx):
