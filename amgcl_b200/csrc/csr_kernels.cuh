@@ -202,7 +202,8 @@ __host__ __device__ inline StageLayout stage_layout(int rows_cap, int nnz_cap, i
     return s;
 }
 constexpr int kMaxStages   = 8;
-constexpr int kHeaderBytes = 384;   // mbarriers [0,64) + reduction scratch [64,128) + descriptors [128,384)
+constexpr int kHeaderBytes = 448;   // mbarriers [0,64) + reduction scratch [64,128) + descriptors [128,384)
+                                    // + per-stage "warps done" counters [384,416)
 constexpr int kWinRunLen   = 64;    // longest run of a window (longer ones are cut at upload)
 constexpr int kOffTabLen   = 256;   // offset-indexed operators: entries of the (col - row) table
 constexpr int kPatCap      = 256;   // pattern-indexed operators: most row patterns ...
@@ -217,7 +218,7 @@ struct BlockDesc {      // written by the producer thread, read by everyone afte
     int q0, q1;         // windowed operators: the block's runs
     int pad_;
 };
-static_assert(sizeof(BlockDesc) * kMaxStages <= kHeaderBytes - 128, "descriptors overflow the header");
+static_assert(sizeof(BlockDesc) * kMaxStages <= 384 - 128, "descriptors overflow the header");
 
 // ---- issue the bulk copies of one row block ----------------------------------
 template <int FMT = FMT_PLAIN, class P>
@@ -701,6 +702,7 @@ __global__ void __launch_bounds__(kThreads, 4) csr_ring_kernel(const CsrArgsT<P>
     uint64_t  *bars  = reinterpret_cast<uint64_t *>(smem);                 // [<=8]
     double    *red_s = reinterpret_cast<double *>(smem + 64);              // [8]
     BlockDesc *descs = reinterpret_cast<BlockDesc *>(smem + 128);          // [<=8]
+    unsigned  *done  = reinterpret_cast<unsigned *>(smem + 384);           // [<=8] warps done with a stage
     const StageLayout lay = stage_layout(a.rows_cap, a.nnz_cap, (int)sizeof(typename P::TV), FMT, a.run_cap);
     char *stages = smem + kHeaderBytes;
     // behind the stages: the window of x (FMT_WINDOW), the offset table (FMT_OFFSET), or the
@@ -712,13 +714,12 @@ __global__ void __launch_bounds__(kThreads, 4) csr_ring_kernel(const CsrArgsT<P>
     const int first = blockIdx.x;
     const int step  = gridDim.x;
     const int mine  = (a.nblocks - first + step - 1) / step;   // blocks this CTA owns
-    uint64_t policy = 0;
+    const uint64_t policy = ptx::policy_evict_first();     // (any warp's first lane may issue a refill)
 
     // PDL: the prologue below only reads matrix data (never written by a kernel), so it may
     // run before the predecessor's writes are visible
     if (threadIdx.x == 0) {
-        policy = ptx::policy_evict_first();
-        for (int s = 0; s < nstages; ++s) ptx::mbar_init(bars + s, 1);
+        for (int s = 0; s < nstages; ++s) { ptx::mbar_init(bars + s, 1); done[s] = 0; }
         ptx::fence_mbar_init();
         const int pre = mine < nstages ? mine : nstages;
         for (int i = 0; i < pre; ++i) {
@@ -746,27 +747,50 @@ __global__ void __launch_bounds__(kThreads, 4) csr_ring_kernel(const CsrArgsT<P>
         const BlockDesc d = descs[s];
         wait_for_halo<HALO>(a, d);
         if constexpr (FMT == FMT_WINDOW) {
+            // the window is filled and used by the whole CTA: block-synchronous
             const char *stage = stages + (size_t)s * lay.bytes;
             fill_window<MODE, HALO>(a, d, stage, lay, win);
             compute_staged<MODE, (L < 16 ? L : 8), HALO, P, FMT_WINDOW>(a, d, stage, lay, acc, win);
-        } else if constexpr (FMT == FMT_OFFSET) {
-            compute_staged<MODE, (L < 16 ? L : 8), HALO, P, FMT_OFFSET>(a, d, stages + (size_t)s * lay.bytes, lay,
-                                                                           acc, nullptr, off_s);
-        } else if constexpr (FMT == FMT_PATTERN) {
-            compute_staged<MODE, (L < 16 ? L : 8), HALO, P, FMT_PATTERN>(a, d, stages + (size_t)s * lay.bytes, lay,
-                                                                            acc, nullptr, off_s, pstart_s);
+            __syncthreads();             // every thread is done with stage s, descs[s], the window
+            if (threadIdx.x == 0 && i + nstages < mine) {
+                const BlockDesc n = load_desc<FMT>(a, first + (i + nstages) * step);
+                descs[s] = n;
+                issue_block<FMT>(a, n, stages + (size_t)s * lay.bytes, lay, bars + s, policy);
+            }
         } else {
-            if (!HALO) warm_lines(a, first + i * step);
-            if ((d.e1 - d.e0) <= a.nnz_cap)
-                compute_staged<MODE, L, HALO>(a, d, stages + (size_t)s * lay.bytes, lay, acc);
-            else
-                compute_long<MODE, HALO>(a, d, red_s, acc);
-        }
-        __syncthreads();                 // every thread is done with stage s, descs[s], the window
-        if (threadIdx.x == 0 && i + nstages < mine) {
-            const BlockDesc n = load_desc<FMT>(a, first + (i + nstages) * step);
-            descs[s] = n;
-            issue_block<FMT>(a, n, stages + (size_t)s * lay.bytes, lay, bars + s, policy);
+            if constexpr (FMT == FMT_OFFSET) {
+                compute_staged<MODE, (L < 16 ? L : 8), HALO, P, FMT_OFFSET>(a, d, stages + (size_t)s * lay.bytes,
+                                                                               lay, acc, nullptr, off_s);
+            } else if constexpr (FMT == FMT_PATTERN) {
+                compute_staged<MODE, (L < 16 ? L : 8), HALO, P, FMT_PATTERN>(a, d, stages + (size_t)s * lay.bytes,
+                                                                                lay, acc, nullptr, off_s, pstart_s);
+            } else {
+                if (!HALO) warm_lines(a, first + i * step);
+                if ((d.e1 - d.e0) <= a.nnz_cap)
+                    compute_staged<MODE, L, HALO>(a, d, stages + (size_t)s * lay.bytes, lay, acc);
+                else
+                    compute_long<MODE, HALO>(a, d, red_s, acc);      // (whole CTA: has its own barriers)
+            }
+            // No CTA barrier between blocks: a warp that is done with this block moves on to the
+            // next stage at once (rows differ in length, gathers in latency; the barrier was the
+            // largest stall of the long-row operators).  The LAST warp to finish refills the stage:
+            // its arrive.expect_tx (release) / the others' wait (acquire) on the stage's mbarrier
+            // publish the new descriptor, the counter below orders everyone's reads of the stage
+            // before the refill.
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0) {
+                __threadfence_block();
+                const unsigned arrived = atomicAdd(done + s, 1u);
+                if (arrived == kThreads / 32 - 1) {
+                    done[s] = 0;
+                    __threadfence_block();
+                    if (i + nstages < mine) {
+                        const BlockDesc n = load_desc<FMT>(a, first + (i + nstages) * step);
+                        descs[s] = n;
+                        issue_block<FMT>(a, n, stages + (size_t)s * lay.bytes, lay, bars + s, policy);
+                    }
+                }
+            }
         }
         if (++s == nstages) { s = 0; parity ^= 1; }
     }
