@@ -132,6 +132,7 @@ def lib():
         "b200_split_destroy": [_vp],
         "b200_plan_i64": [_i64, _vp, _c.c_int, _c.c_int, _vp, _i64, _P(_i64), _P(_c.c_int),
                           _P(_c.c_int), _P(_i64)],
+        "b200_ctx_largest_operator": [_vp, _P(_i64), _P(_c.c_int)],
         "b200_csr_patterns": [_vp, _P(_c.c_int), _P(_c.c_int), _P(_c.c_int)],
         "b200_pattern_plan_i64": [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _P(_c.c_int), _P(_c.c_int), _P(_c.c_int)],
         "b200_csr_offsets": [_vp, _P(_c.c_int), _P(_c.c_int)],
@@ -301,6 +302,13 @@ class Context:
         m = _i64()
         _check(lib().b200_dist_info(self.h, _c.byref(r), _c.byref(n), _c.byref(m), _c.byref(p)))
         return {"rank": r.value, "nranks": n.value, "dist_min_rows": m.value, "p2p": bool(p.value)}
+
+    def largest_operator(self):
+        """(non-zeros, column format) of the largest operator uploaded so far; format is one of
+        'plain', 'window', 'offset', 'pattern'."""
+        nnz, fmt = _i64(), _c.c_int()
+        _check(lib().b200_ctx_largest_operator(self.h, _c.byref(nnz), _c.byref(fmt)))
+        return nnz.value, ("plain", "window", "offset", "pattern")[fmt.value]
 
     def profile_begin(self):
         _check(lib().b200_profile_begin(self.h), "b200_profile_begin")

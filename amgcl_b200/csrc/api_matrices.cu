@@ -309,6 +309,10 @@ static int csr_upload(b200_ctx_t ctx, int64_t nrows, int64_t ncols, const Ptr *p
 #undef CSR_CUDA
     A->bytes = ptr_bytes + col_bytes + val_bytes + blk_bytes + c16_bytes + run_bytes + wbk_bytes + ix8_bytes +
                tab_bytes + pid_bytes + pat_bytes;
+    if (nnz > ctx->big_nnz) {
+        ctx->big_nnz = nnz;
+        ctx->big_fmt = pattern_indexed ? FMT_PATTERN : offset_indexed ? FMT_OFFSET : windowed ? FMT_WINDOW : FMT_PLAIN;
+    }
     *out = A;
     if (halo_from < 0 && !windowed && ctx->opt_warm_lines && lanes >= 2 && A->dtype == B200_F64 && nblocks > 0 &&
         (ctx->opt_warm_lines > 1 || nnz >= 1000000)) {
@@ -739,6 +743,13 @@ extern "C" int b200_pattern_plan_i64(int64_t nrows, int64_t ncols, const int64_t
     if (pid_out) std::copy(o.pid.begin(), o.pid.end(), pid_out);
     if (start_out) std::copy(o.start.begin(), o.start.end(), start_out);
     if (off_out) std::copy(o.off.begin(), o.off.end(), off_out);
+    return B200_OK;
+}
+
+extern "C" int b200_ctx_largest_operator(b200_ctx_t ctx, int64_t *nnz, int *format) {
+    CHECK_CTX(ctx);
+    if (nnz) *nnz = ctx->big_nnz;
+    if (format) *format = ctx->big_fmt;
     return B200_OK;
 }
 

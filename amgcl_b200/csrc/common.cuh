@@ -157,6 +157,8 @@ struct b200_ctx_s {
     int64_t opt_tail_max_nnz  = 1500000;  // ... "small": at most this many non-zeros
     int64_t opt_tail_max_vec  = 262144;   // ... element-wise x = 0 sweeps: at most this many entries
     int64_t opt_poll_scalars  = 1;        // host reads in-kernel reduction results by polling mapped memory
+    int64_t big_nnz = -1;                 // the largest operator uploaded so far and the column
+    int     big_fmt = 0;                  // format it is stored in (FMT_*; for the bench's roofline)
     int64_t opt_patterns      = 1;        // operators with <= 256 distinct row patterns: no per-entry columns
     int64_t opt_patterns_min_nnz = 1000000;// ... from this many non-zeros on (decided at upload)
     int64_t opt_offsets       = 1;        // operators with <= 256 distinct (col - row): 8-bit column indices

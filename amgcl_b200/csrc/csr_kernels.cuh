@@ -746,37 +746,32 @@ __global__ void __launch_bounds__(kThreads, 4) csr_ring_kernel(const CsrArgsT<P>
         ptx::mbar_wait(bars + s, parity);
         const BlockDesc d = descs[s];
         wait_for_halo<HALO>(a, d);
+        const char *stage = stages + (size_t)s * lay.bytes;
+        // Compressed formats (the short-row finest operator): no CTA barrier between blocks -- a
+        // warp that is done with this block moves on to the next stage at once, and the LAST
+        // warp to finish refills the stage.  Measured on the 256^3 solve: -5 % on those passes;
+        // on the plain-format operators (long rows, half of the warps without rows in a block)
+        // the same scheme costs 10-15 %, so they stay block-synchronous.
+        constexpr bool kDecoupled = FMT == FMT_OFFSET || FMT == FMT_PATTERN;
         if constexpr (FMT == FMT_WINDOW) {
-            // the window is filled and used by the whole CTA: block-synchronous
-            const char *stage = stages + (size_t)s * lay.bytes;
             fill_window<MODE, HALO>(a, d, stage, lay, win);
             compute_staged<MODE, (L < 16 ? L : 8), HALO, P, FMT_WINDOW>(a, d, stage, lay, acc, win);
-            __syncthreads();             // every thread is done with stage s, descs[s], the window
-            if (threadIdx.x == 0 && i + nstages < mine) {
-                const BlockDesc n = load_desc<FMT>(a, first + (i + nstages) * step);
-                descs[s] = n;
-                issue_block<FMT>(a, n, stages + (size_t)s * lay.bytes, lay, bars + s, policy);
-            }
+        } else if constexpr (FMT == FMT_OFFSET) {
+            compute_staged<MODE, (L < 16 ? L : 8), HALO, P, FMT_OFFSET>(a, d, stage, lay, acc, nullptr, off_s);
+        } else if constexpr (FMT == FMT_PATTERN) {
+            compute_staged<MODE, (L < 16 ? L : 8), HALO, P, FMT_PATTERN>(a, d, stage, lay, acc, nullptr, off_s,
+                                                                            pstart_s);
         } else {
-            if constexpr (FMT == FMT_OFFSET) {
-                compute_staged<MODE, (L < 16 ? L : 8), HALO, P, FMT_OFFSET>(a, d, stages + (size_t)s * lay.bytes,
-                                                                               lay, acc, nullptr, off_s);
-            } else if constexpr (FMT == FMT_PATTERN) {
-                compute_staged<MODE, (L < 16 ? L : 8), HALO, P, FMT_PATTERN>(a, d, stages + (size_t)s * lay.bytes,
-                                                                                lay, acc, nullptr, off_s, pstart_s);
-            } else {
-                if (!HALO) warm_lines(a, first + i * step);
-                if ((d.e1 - d.e0) <= a.nnz_cap)
-                    compute_staged<MODE, L, HALO>(a, d, stages + (size_t)s * lay.bytes, lay, acc);
-                else
-                    compute_long<MODE, HALO>(a, d, red_s, acc);      // (whole CTA: has its own barriers)
-            }
-            // No CTA barrier between blocks: a warp that is done with this block moves on to the
-            // next stage at once (rows differ in length, gathers in latency; the barrier was the
-            // largest stall of the long-row operators).  The LAST warp to finish refills the stage:
+            if (!HALO) warm_lines(a, first + i * step);
+            if ((d.e1 - d.e0) <= a.nnz_cap)
+                compute_staged<MODE, L, HALO>(a, d, stage, lay, acc);
+            else
+                compute_long<MODE, HALO>(a, d, red_s, acc);
+        }
+        if constexpr (kDecoupled) {
             // its arrive.expect_tx (release) / the others' wait (acquire) on the stage's mbarrier
-            // publish the new descriptor, the counter below orders everyone's reads of the stage
-            // before the refill.
+            // publish the new descriptor; the counter orders everyone's reads of the stage before
+            // the refill
             __syncwarp();
             if ((threadIdx.x & 31) == 0) {
                 __threadfence_block();
@@ -790,6 +785,13 @@ __global__ void __launch_bounds__(kThreads, 4) csr_ring_kernel(const CsrArgsT<P>
                         issue_block<FMT>(a, n, stages + (size_t)s * lay.bytes, lay, bars + s, policy);
                     }
                 }
+            }
+        } else {
+            __syncthreads();             // every thread is done with stage s, descs[s], the window
+            if (threadIdx.x == 0 && i + nstages < mine) {
+                const BlockDesc n = load_desc<FMT>(a, first + (i + nstages) * step);
+                descs[s] = n;
+                issue_block<FMT>(a, n, stages + (size_t)s * lay.bytes, lay, bars + s, policy);
             }
         }
         if (++s == nstages) { s = 0; parity ^= 1; }

@@ -478,12 +478,28 @@ def main_arm(args, rank, world, local_rank):
             elif p["mode"] in ("relax", "residual_scaled"):      # rhs + diagonal / rhs + x written
                 b += 2 * p["nrows"] * 8
             return b
+        # what the kernel really streams: the finest operator is stored pattern-indexed (no
+        # per-entry columns: 8 B per entry + row pointer + 1 B pattern id per row) or
+        # offset-indexed (1 B of column per entry) when it qualifies -- fewer bytes than the CSR
+        # figure SURVEY.md section 8(d) counts, same arithmetic
+        fmt = ctx.largest_operator()[1]
+        col_b, row_b = {"pattern": (0, 5), "offset": (1, 4)}.get(fmt, (4, 4))
+
+        def streamed_bytes(p):
+            return alg_bytes(p) - p["nnz"] * (4 - col_b) + (p["nrows"] + 1) * (row_b - 4)
         tot_b = sum(alg_bytes(p) * p["launches"] for p in finest)
+        tot_s = sum(streamed_bytes(p) * p["launches"] for p in finest)
         tot_ms = sum(p["total_ms"] for p in finest)
         tot_l = sum(p["launches"] for p in finest)
         ach = tot_b / (tot_ms * 1e-3) / 1e9
+        ach_s = tot_s / (tot_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": "csr_ring_kernel (finest level A: spmv/residual/relax)",
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                # achieved counts the CSR bytes of SURVEY.md 8(d) (12 B per entry); with a compressed
+                # column format the kernel moves fewer, so frac can exceed what the memory system
+                # delivered: `streamed` is the same launches on the bytes actually moved
+                "column_format": fmt,
+                "streamed": {"achieved": ach_s, "frac": ach_s / peak, "bytes_per_launch": tot_s / tot_l},
                 "peak_source": peak_src, "traffic": None,
                 "bytes_per_launch": tot_b / tot_l, "launches": tot_l,
                 "avg_launch_ms": tot_ms / tot_l,
@@ -590,6 +606,7 @@ def main_arm(args, rank, world, local_rank):
                         "fused_krylov": bool(ctx.get_option("fused_krylov")),
                         "fuse_first_sweep": bool(ctx.get_option("fuse_first_sweep")),
                         "coarse_tail": bool(ctx.get_option("coarse_tail")),
+                        "column_formats": {k: bool(ctx.get_option(k)) for k in ("patterns", "offsets", "window")},
                         "partition_min_rows": dist_min_rows if world > 1 else None},
             "solve_s": solve_s, "iters": iters, "resid": res,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,

@@ -282,6 +282,10 @@ int b200_plan_i64(int64_t nrows, const int64_t *ptr, int lanes, int nnz_cap,
  * b200_pattern_plan_i64: pure host helper for tests (pid_out [nrows], start_out [257],
  * off_out [1024]). */
 int b200_csr_patterns(b200_csr_t A, int *pattern_indexed, int *count, int *total);
+/* The largest operator (this rank's non-zeros) uploaded through ctx so far and the column
+ * format it is stored in: 0 plain, 1 windowed, 2 offset-indexed, 3 pattern-indexed (what
+ * bench.py needs to count the bytes the finest-level passes really stream). */
+int b200_ctx_largest_operator(b200_ctx_t ctx, int64_t *nnz, int *format);
 int b200_pattern_plan_i64(int64_t nrows, int64_t ncols, const int64_t *ptr, const int64_t *col,
                           uint8_t *pid_out, uint16_t *start_out, int32_t *off_out, int *count,
                           int *total, int *qualifies);
