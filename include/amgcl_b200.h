@@ -198,6 +198,15 @@ int b200_split_destroy(b200_split_t sp);
  *   "fused_krylov"     1 = the C++ binding's solver::cg / solver::bicgstab specialisations run the
  *                      fused b200_cg_* / b200_bicg_* steps (default; env B200_FUSED_KRYLOV),
  *                      0 = they issue the reference's sequence of primitives
+ *   "patterns"         1 = operators with at most 256 row patterns (created afterwards, at least
+ *                      "patterns_min_nnz" non-zeros, default 1e6) are also stored pattern-indexed
+ *                      and streamed without per-entry columns (default; env B200_PATTERNS);
+ *                      0 = not built / not used.  Bit-identical either way (see below).
+ *   "offsets"          the same for offset-indexed columns ("offsets_min_nnz"; env B200_OFFSETS);
+ *                      used where an operator does not qualify for "patterns"
+ *   "window"           1 = operators that qualify are also stored windowed ("window_min_nnz",
+ *                      "window_ratio" percent, "window_gap", "window_lanes"); default 0:
+ *                      measured slower than the plain path (env B200_WINDOW)
  *   "fuse_relax"       1 = single-pass fused smoother sweep (default), 0 = two kernels
  *   "zero_shortcut"    1 = skip the A-pass when x is known to be zero (default)
  * Unknown keys return B200_EINVAL. */

@@ -23,13 +23,15 @@ PROF = os.path.join(ROOT, "profiles")
 def short_name(full):
     """'void b200::csr_ring_kernel<3, 1, 0, Prec<double, ...>>(args)' -> 'csr_ring_kernel<3, 1> f64'."""
     name = full.split("(")[0].replace("void ", "").replace("b200::", "")
-    m = re.match(r"(csr_\w+_kernel)<(\d+), (\d+), (\d+), Prec<([^>]*)>>", name)
+    name = name.replace("(int)", "").replace("(bool)", "")
+    m = re.match(r"(csr_\w+_kernel)<(\d+), (\d+), (\d+), Prec<([^>]*)>(?:, (\d+))?>", name)
     if m:
         types = [t.strip() for t in m.group(5).split(",")]
         prec = "f64" if all(t == "double" for t in types) else \
                "f32" if all(t == "float" for t in types) else "mixed"
-        return "%s<%s, %s>%s %s" % (m.group(1), m.group(2), m.group(3),
-                                    " halo" if m.group(4) == "1" else "", prec)
+        fmt = {"1": " window", "2": " offset", "3": " pattern"}.get(m.group(6) or "0", "")
+        return "%s<%s, %s>%s %s%s" % (m.group(1), m.group(2), m.group(3),
+                                      " halo" if m.group(4) == "1" else "", prec, fmt)
     return name
 
 
@@ -162,9 +164,11 @@ def iteration_table(tag, raw_csv, what, peak=6586.7):
            "measured %.1f GB/s (MEASURED_PEAKS.json).  Kernels on operators that fit the 126 MB L2 read "
            "less from DRAM than they stream: their bound is the launch / dependency latency, see "
            "DESIGN.md." % peak, "",
+           "`stall`: warps stalled per issued instruction at a CTA barrier / on a long-scoreboard (global "
+           "memory) dependency; `issue %`: cycles a scheduler issued.", "",
            "| # | kernel | grid | regs | time us | DRAM read MB | DRAM write MB | DRAM GB/s | of peak | "
-           "dram % | L2 % | L1TEX % | SM % | L1 hit % | L2 hit % |",
-           "|---:|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|"]
+           "dram % | L2 % | L1TEX % | SM % | L1 hit % | L2 hit % | stall barrier | stall long sb | issue % |",
+           "|---:|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|"]
     for i, r in enumerate(data):
         t = num(r, "gpu__time_duration.sum")
         rd, wr = num(r, "dram__bytes_read.sum") or 0.0, num(r, "dram__bytes_write.sum") or 0.0
@@ -173,7 +177,7 @@ def iteration_table(tag, raw_csv, what, peak=6586.7):
         def pct(key):
             v = num(r, key)
             return "%.1f" % v if v is not None else "n/a"
-        out.append("| %d | `%s` | %s | %s | %.1f | %.1f | %.1f | %.0f | %.2f | %s | %s | %s | %s | %s | %s |" % (
+        out.append("| %d | `%s` | %s | %s | %.1f | %.1f | %.1f | %.0f | %.2f | %s | %s | %s | %s | %s | %s | %s | %s | %s |" % (
             i, short_any(r[kn]), r[hdr.index("launch__grid_size")] if "launch__grid_size" in hdr else "",
             r[hdr.index("launch__registers_per_thread")] if "launch__registers_per_thread" in hdr else "",
             t * 1e6, rd / 1e6, wr / 1e6, gbs, gbs / peak,
@@ -181,7 +185,10 @@ def iteration_table(tag, raw_csv, what, peak=6586.7):
             pct("lts__throughput.avg.pct_of_peak_sustained_elapsed"),
             pct("l1tex__throughput.avg.pct_of_peak_sustained_elapsed"),
             pct("sm__throughput.avg.pct_of_peak_sustained_elapsed"),
-            pct("l1tex__t_sector_hit_rate.pct"), pct("lts__t_sector_hit_rate.pct")))
+            pct("l1tex__t_sector_hit_rate.pct"), pct("lts__t_sector_hit_rate.pct"),
+            pct("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio"),
+            pct("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio"),
+            pct("smsp__issue_active.avg.pct_of_peak_sustained_active")))
     open(os.path.join(PROF, tag + "_kernels.md"), "w").write("\n".join(out) + "\n")
     return data, hdr, units
 
@@ -189,7 +196,10 @@ def iteration_table(tag, raw_csv, what, peak=6586.7):
 if __name__ == "__main__":
     os.makedirs(PROF, exist_ok=True)
     tag = sys.argv[1]
-    if sys.argv[2] == "--iteration":
+    if sys.argv[2] == "--csr-only":
+        # summarize_ncu.py <tag> --csr-only <raw.csv> "<what>": a capture filtered to the CSR kernels
+        iteration_table(tag, sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else "Krylov iteration")
+    elif sys.argv[2] == "--iteration":
         # summarize_ncu.py <tag> --iteration <raw.csv> <launches.csv> "<what>"
         iteration_table(tag, sys.argv[3], sys.argv[5] if len(sys.argv) > 5 else "Krylov iteration")
         launch_shares(tag, sys.argv[4])
