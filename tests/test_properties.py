@@ -192,3 +192,74 @@ def test_file_formats_round_trip(tmp_path_factory, m, seed):
     pdm = str(d / "d.mtx")
     bio.write_mm(pdm, dense)
     assert np.array_equal(bio.read_mm(pdm), dense)
+
+
+# ---- column formats (patterns.cuh / offsets.cuh / window.cuh): whatever the matrix, a planner
+# either declines or returns a format that reproduces every column ---------------------------
+
+@st.composite
+def structured_matrix(draw):
+    """Entries on a few diagonals (structured-grid like), randomly thinned, possibly rectangular,
+    or fully random columns."""
+    nr = draw(st.integers(1, 700))
+    nc = draw(st.integers(1, 900))
+    seed = draw(st.integers(0, 2 ** 31 - 1))
+    kind = draw(st.sampled_from(["diagonals", "few_diagonals_full", "random"]))
+    rng = np.random.default_rng(seed)
+    if kind == "random":
+        lens = rng.integers(0, 12, nr)
+        ptr = np.zeros(nr + 1, dtype=np.int64)
+        np.cumsum(lens, out=ptr[1:])
+        col = np.concatenate([np.sort(rng.integers(0, nc, k)) for k in lens] + [np.zeros(0, dtype=np.int64)])
+        return nr, nc, ptr, col.astype(np.int64)
+    ndiag = draw(st.integers(1, 40 if kind == "diagonals" else 6))
+    offs = np.unique(rng.integers(-nr, nc, ndiag))
+    keep = 1.0 if kind == "few_diagonals_full" else draw(st.sampled_from([0.3, 0.7, 0.95]))
+    rows = np.repeat(np.arange(nr, dtype=np.int64), offs.size)
+    cols = rows + np.tile(offs, nr)
+    ok = (cols >= 0) & (cols < nc) & (rng.uniform(size=cols.size) < keep)
+    rows, cols = rows[ok], cols[ok]
+    ptr = np.zeros(nr + 1, dtype=np.int64)
+    np.cumsum(np.bincount(rows, minlength=nr), out=ptr[1:])
+    return nr, nc, ptr, cols
+
+
+@settings(**SETTINGS)
+@given(structured_matrix())
+def test_pattern_and_offset_formats_reproduce_the_columns(m):
+    from test_offsets import decode as decode_offsets
+    from test_patterns import decode as decode_patterns
+    nr, nc, ptr, col = m
+    rows = np.repeat(np.arange(nr, dtype=np.int64), np.diff(ptr))
+    ndist = np.unique(col - rows).size if col.size else 0
+    o = ab.offset_plan(nr, nc, ptr, col)
+    if col.size == 0:
+        assert o is None
+    else:
+        assert (o is not None) == (ndist <= 256)
+    if o is not None:
+        assert o["count"] == ndist and (decode_offsets(o, ptr) == col).all()
+    p = ab.pattern_plan(nr, nc, ptr, col)
+    if p is not None:
+        assert p["count"] <= 256 and p["total"] <= 1024
+        assert (decode_patterns(p, ptr) == col).all()
+        # the patterns are distinct and together exactly as long as `total`
+        pats = {tuple(p["off"][p["start"][k]:p["start"][k + 1]]) for k in range(p["count"])}
+        assert len(pats) == p["count"] and p["start"][p["count"]] == p["total"]
+    else:
+        # declined: really more than 256 patterns, or more than 1024 offsets in all
+        tuples = {tuple(col[ptr[r]:ptr[r + 1]] - r) for r in range(nr)}
+        assert col.size == 0 or len(tuples) > 256 or sum(len(t) for t in tuples) > 1024
+
+
+@settings(**SETTINGS)
+@given(structured_matrix(), st.sampled_from([256, 512, 1400]), st.sampled_from([1, 2]))
+def test_window_format_reproduces_the_columns(m, slot_cap, gap):
+    from test_window import _decode
+    nr, nc, ptr, col = m
+    w = ab.window_plan(nr, nc, ptr, col, slot_cap=slot_cap, max_ratio=100000, gap=gap)
+    if w is None:
+        return                      # (declined: a quad of rows alone does not fit the caps)
+    got, rows = _decode(w, nc)
+    assert rows == nr and (got == col).all()
+    assert w["max_slots"] <= slot_cap and w["max_runs"] <= 126
