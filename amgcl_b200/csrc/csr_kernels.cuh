@@ -24,16 +24,18 @@
 //   variant 1: persistent CTAs walking the block list with an S-deep ring of
 //              stages, so S*CTAs/SM bulk copies are always in flight per SM.
 //
-// Windowed operators (WIN).  For an operator whose row blocks gather from few distinct places
-// (the finest A, the prolongations, the coarse A's: on average a block of ~2000 entries reads
-// from ~1000 doubles of x laid out in about ten contiguous runs) the upload also stores, per
-// block, those runs and, per entry, the 16-bit position of its column inside the block's
-// window.  The kernel then fills the window into shared memory with coalesced loads (one
-// 32-byte sector is fetched once per block, not once per scattered 8-byte gather that misses
-// the small L1 left beside the stages) and reduces the rows entirely out of shared memory.  The
-// column stream shrinks from 4 to 2 bytes per entry.  The arithmetic (entry order, shuffle tree,
-// epilogue) is exactly that of the plain path, so the results are bit-identical
-// (tests/test_gpu_window.py).
+// Column formats (template parameter FMT): how the kernel learns the column of an entry.  The
+// arithmetic (entry order, lanes, shuffle tree, epilogue) is shared, so every format gives the
+// bits of the plain one (tests/test_gpu_formats.py, tests/test_gpu_window.py); measurements in
+// DESIGN.md section 3.1b.
+//
+// Windowed operators (FMT_WINDOW; opt-in: measured slower than the plain path).  For an operator
+// whose row blocks gather from few distinct places the upload also stores, per block, the runs
+// of x it reads and, per entry, the 16-bit position of its column inside the block's window.
+// The kernel fills the window into shared memory with coalesced loads (one 32-byte sector is
+// fetched once per block, not once per scattered 8-byte gather that misses the small L1 left
+// beside the stages) and reduces the rows entirely out of shared memory; the column stream
+// shrinks from 4 to 2 bytes per entry.
 //
 // Offset-indexed columns (FMT_OFFSET).  In a matrix assembled on a structured grid every entry
 // sits on one of a few diagonals: col - row takes a handful of distinct values (7 for the
@@ -41,8 +43,7 @@
 // there are at most 256 of them, the upload also stores one BYTE per entry -- the index of its
 // offset in a table -- and the kernel streams 1 instead of 4 bytes of column per entry
 // (9 instead of 12 bytes per FP64 entry, 5 instead of 8 per FP32 entry), rebuilding the column
-// as row + table[index] from shared memory.  Entry order and arithmetic are those of the plain
-// path: bit-identical results (tests/test_gpu_offsets.py).
+// as row + table[index] from shared memory.
 //
 // Pattern-indexed rows (FMT_PATTERN).  On such a matrix whole ROWS repeat: the tuple of offsets
 // (col - row of every entry, in entry order) of a row is one of a few patterns (27 for the
@@ -50,7 +51,11 @@
 // stores one byte per ROW and no column information per entry at all: the kernel streams the
 // values (8 or 4 bytes per entry), the row pointers and the pattern ids, and rebuilds
 // col = row + pattern[k] for the k-th entry of the row from a table in shared memory -- one
-// shared-memory load per entry, as many as the plain path needs for its staged column.
+// shared-memory load per entry, as many as the plain path needs for its staged column.  The
+// default for every operator that qualifies (the finest level of a structured-grid problem).
+//
+// Between blocks the CTA synchronises with a barrier (plain, windowed) or not at all
+// (offset- / pattern-indexed: the last warp done with a stage refills it) -- see the ring kernel.
 //
 // Precision.  Every kernel is a template over the element types of the matrix
 // values, the gathered vector, the right-hand side, the output and the smoother
