@@ -42,3 +42,20 @@ def test_too_many_patterns_do_not_qualify():
     # few patterns, but longer than the table
     ptr, col, val = diag_matrix(3000, 6000, list(range(0, 1100)), seed=2, keep=1.0)
     assert ab.pattern_plan(3000, 6000, ptr, col) is None
+
+
+def test_a_ranks_block_of_the_partitioned_operator_still_qualifies():
+    """Multi-GPU: a rank keeps whole rows of the finest operator with the halo columns
+    renumbered to [n_loc + owner * slots + position) (dist.cuh).  A face of the slab maps to one
+    constant offset, so the block has a few more patterns than the whole operator, not many."""
+    n = 16
+    ptr, col, val, rhs = ab.poisson3d(n)
+    nr = ptr.size - 1
+    for nranks in (2, 4, 8):
+        for rank in range(nranks):
+            sp = ab.dist_split("halo", nranks, rank, nr, nr, ptr, col, val)
+            p = ab.pattern_plan(sp["nrows"], sp["ncols"], sp["ptr"], sp["col"])
+            assert p is not None and p["count"] <= 2 * 27 and p["total"] <= 1024
+            assert (decode(p, sp["ptr"]) == sp["col"]).all()
+            o = ab.offset_plan(sp["nrows"], sp["ncols"], sp["ptr"], sp["col"])
+            assert o is not None and o["count"] <= 9
